@@ -1,0 +1,264 @@
+/*
+ * rayito_b200 -- C ABI of the B200 render core (librayito_b200.so).
+ *
+ * This is the drop-in boundary for Rayito's render hot path.  The reference has no
+ * FFI; its only seams are C++ calls, and each entry point below names the reference
+ * call it stands behind (file:line relative to the reference repository, Stage 7
+ * unless noted).  Every signature uses plain pointers and sizes.  All functions
+ * return 0 on success or a negative RtStatus; rt_last_error_string() describes the
+ * last failure on the calling thread.  There is no CPU fallback: without a CUDA
+ * device every compute entry point fails with RT_ERR_CUDA.
+ *
+ * Host buffers passed in are borrowed for the duration of the call only.
+ */
+#ifndef RAYITO_B200_H
+#define RAYITO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RT_ABI_VERSION 1
+
+typedef enum RtStatus
+{
+    RT_OK = 0,
+    RT_ERR_ARG = -1,        /* bad argument / inconsistent scene description */
+    RT_ERR_CUDA = -2,       /* CUDA runtime failure (including "no device") */
+    RT_ERR_DEPTH = -3,      /* a BVH is deeper than 49: the reference's 50-entry
+                               traversal stack (RAccel.h:379,414,502) would overflow */
+    RT_ERR_UNSUPPORTED = -4
+} RtStatus;
+
+/* Mirrors Rayito::Ray (RRay.h:31-36; sizeof == 32). */
+typedef struct RtRay
+{
+    float origin[3];
+    float direction[3];
+    float tmax;
+    float time;
+} RtRay;
+
+/* Result of scene.intersect(): Intersection::m_t and the identity of the winner
+ * (RRay.h:98-105).  shape is the index in "finite shapes in insertion order, then
+ * infinite shapes" or -1; face / tri are the mesh face and fan triangle, else -1.
+ * On a miss t is the ray's tmax. */
+typedef struct RtHit
+{
+    float t;
+    int32_t shape;
+    int32_t face;
+    int32_t tri;
+} RtHit;
+
+/* RtHit plus the shading inputs the reference stores in Intersection
+ * (m_normal, m_colorModifier -- always a grey value: 1 or 0.2). */
+typedef struct RtHitEx
+{
+    float t;
+    int32_t shape;
+    int32_t face;
+    int32_t tri;
+    float normal[3];
+    float color_modifier;
+} RtHitEx;
+
+enum { RT_SHAPE_PLANE = 0, RT_SHAPE_SPHERE = 1, RT_SHAPE_RECT = 2, RT_SHAPE_MESH = 3 };
+enum { RT_BRDF_NONE = 0 /* Emitter */, RT_BRDF_LAMBERT = 1, RT_BRDF_GLOSSY = 2, RT_BRDF_MIRROR = 3 };
+enum { RT_NO_INDEX = 0xffffffffu };
+
+/* One member of the ShapeSet (RScene.h:246-252).  A ShapeLight (RLight.h:250-332)
+ * is flattened to the geometry and transform of the shape it wraps, with the
+ * light's Emitter as material and light >= 0. */
+typedef struct RtShape
+{
+    uint32_t type;       /* RT_SHAPE_* */
+    uint32_t geom;       /* index into planes / spheres / rects / meshes */
+    uint32_t xform;      /* index into xforms */
+    uint32_t material;   /* index into materials */
+    int32_t light;       /* index into lights, or -1 */
+} RtShape;
+
+/* Keyed scale-rotate-translate transform (RMath.h:619-941); num_keys == 0 is the
+ * keyless identity.  Rotation keys must already be normalised (Transform::prepare). */
+typedef struct RtXform
+{
+    uint32_t first_key;
+    uint32_t num_keys;
+} RtXform;
+
+typedef struct RtPlane  { float position[3]; float normal[3]; uint32_t bullseye; } RtPlane;
+typedef struct RtSphere { float position[3]; float radius; } RtSphere;
+typedef struct RtRect   { float position[3]; float side1[3]; float side2[3]; } RtRect;
+
+/* Polygon mesh (RMesh.h:39-60) with its face BVH in the reference node format. */
+typedef struct RtMesh
+{
+    uint32_t first_vertex, num_vertices;     /* into vertices (xyz triples) */
+    uint32_t first_normal, num_normals;      /* into normals */
+    uint32_t first_face, num_faces;          /* into face_start / face_flags */
+    uint32_t first_node, num_nodes;          /* into mesh_nodes */
+    uint32_t first_cdf;                      /* into face_area_cdf (num_faces + 1 floats) */
+    float total_area;
+} RtMesh;
+
+/* Rayito::BvhNode as laid out by the reference (RAccel.h:136-145, 32 bytes):
+ * flags bits 0-1 = split axis, bit 2 = leaf (RAccel.h:119-124). */
+typedef struct RtBvhNode
+{
+    float bbox_min[3];
+    float bbox_max[3];
+    uint32_t first_child_or_prim;
+    uint32_t flags;
+} RtBvhNode;
+
+typedef struct RtMaterial
+{
+    float color[3];       /* reflectance (Diffuse/Glossy/Reflection) */
+    float emittance[3];   /* Emitter: color * power (RMaterial.h:537) */
+    float exponent;       /* Glossy: 1 / roughness^2 (RMaterial.h:211) */
+    uint32_t brdf;        /* RT_BRDF_* */
+} RtMaterial;
+
+/* Flat scene: what ShapeSet::prepare() leaves behind (RScene.h:186-205). */
+typedef struct RtSceneDesc
+{
+    uint32_t abi_version;            /* RT_ABI_VERSION */
+    uint32_t set_xform;              /* transform of the ShapeSet itself */
+
+    uint32_t num_finite;             /* ShapeSet::m_shapes, insertion order */
+    uint32_t num_infinite;           /* ShapeSet::m_infiniteShapes (planes) */
+    const RtShape* shapes;           /* num_finite + num_infinite entries */
+
+    uint32_t num_top_nodes;          /* 0 => linear list (<= 2 finite shapes, RScene.h:135) */
+    const RtBvhNode* top_nodes;
+
+    uint32_t num_xforms;
+    const RtXform* xforms;
+    uint32_t num_keys;
+    const float* key_time;           /* num_keys */
+    const float* key_scale;          /* num_keys * 3 */
+    const float* key_rotation;       /* num_keys * 4, (w, x, y, z) */
+    const float* key_translation;    /* num_keys * 3 */
+
+    uint32_t num_planes;  const RtPlane* planes;
+    uint32_t num_spheres; const RtSphere* spheres;
+    uint32_t num_rects;   const RtRect* rects;
+    uint32_t num_meshes;  const RtMesh* meshes;
+
+    uint32_t num_vertices;   const float* vertices;      /* xyz */
+    uint32_t num_normals;    const float* normals;       /* xyz */
+    uint32_t num_faces;
+    const uint32_t* face_start;      /* num_faces + 1 offsets into the index arrays */
+    const uint32_t* face_has_normals;/* num_faces flags */
+    uint32_t num_indices;
+    const uint32_t* vertex_index;    /* mesh-local vertex indices */
+    const uint32_t* normal_index;    /* mesh-local normal indices (ignored if !has_normals) */
+    uint32_t num_mesh_nodes; const RtBvhNode* mesh_nodes;
+    uint32_t num_cdf;        const float* face_area_cdf;
+
+    uint32_t num_materials;  const RtMaterial* materials;
+    uint32_t num_lights;     const uint32_t* lights;     /* shape indices, findLights() order */
+} RtSceneDesc;
+
+/* PerspectiveCamera after its constructor ran (RaytraceMain.cpp:205-222). */
+typedef struct RtCamera
+{
+    float origin[3];
+    float forward[3];
+    float right[3];
+    float up[3];
+    float tan_fov;
+    float focal_distance;
+    float lens_radius;
+    float shutter_open;
+    float shutter_close;
+} RtCamera;
+
+/* Arguments of raytrace() (rayito.h:138-144) plus the screen-tile partition used
+ * to shard one image over ranks. */
+typedef struct RtRenderParams
+{
+    uint32_t width, height;
+    uint32_t pixel_samples_hint;     /* spp = hint^2 */
+    uint32_t light_samples_hint;     /* light samples per bounce = hint^2 */
+    uint32_t max_ray_depth;
+    uint32_t tile_size;              /* square tiles; 0 = library default */
+    uint32_t rank, world;            /* this call renders tiles with index % world == rank */
+    uint32_t max_batch_samples;      /* wavefront size cap; 0 = library default */
+    uint32_t flags;                  /* RT_RENDER_* */
+} RtRenderParams;
+
+enum { RT_RENDER_COUNT_WORK = 1u  /* also count node pops / triangle tests (slower) */ };
+
+typedef struct RtRenderStats
+{
+    uint64_t samples;             /* pixel samples traced */
+    uint64_t closest_rays;        /* scene.intersect calls (RaytraceMain.cpp:294,423) */
+    uint64_t any_rays;            /* scene.doesIntersect calls (RaytraceMain.cpp:395) */
+    uint64_t node_pops;           /* BVH nodes popped, both levels (RT_RENDER_COUNT_WORK) */
+    uint64_t tri_tests;           /* triangles tested */
+    uint64_t shape_tests;         /* analytic shapes tested */
+    uint64_t xform_evals;         /* keyed transforms evaluated */
+    uint64_t kernel_launches;     /* CUDA kernels launched by this call */
+    float render_ms;              /* device time of the render (CUDA events) */
+    float trace_ms;               /* device time inside the traversal kernels */
+    float upload_ms;              /* host->device scene/camera copies inside this call */
+    float download_ms;            /* device->host image copy inside this call */
+} RtRenderStats;
+
+typedef struct RtScene RtScene;
+
+const char* rt_last_error_string(void);
+int rt_abi_version(void);
+/* Number of visible CUDA devices (0 when there is none; never fails). */
+int rt_device_count(void);
+
+/* Upload a prepared scene to `device`.  Stands behind scene.prepare() at
+ * RaytraceMain.cpp:497.  Fails with RT_ERR_DEPTH if any BVH is deeper than 49. */
+int rt_scene_create(const RtSceneDesc* desc, int device, RtScene** out_scene);
+int rt_scene_destroy(RtScene* scene);
+
+/* ShapeSet::intersect (RScene.h:120-156) for n rays; host buffers. */
+int rt_trace_closest(RtScene* scene, const RtRay* rays, size_t n, RtHit* hits);
+int rt_trace_closest_ex(RtScene* scene, const RtRay* rays, size_t n, RtHitEx* hits);
+/* ShapeSet::doesIntersect (RScene.h:158-184) for n rays; hits[i] is 0 or 1. */
+int rt_trace_any(RtScene* scene, const RtRay* rays, size_t n, uint8_t* hits);
+
+/* Same, on buffers already resident on the scene's device, enqueued on `stream`
+ * (a cudaStream_t passed as void*; NULL = the legacy default stream).  These do
+ * not synchronise.  work, if not NULL, is a device array of 4 uint64 counters
+ * {node_pops, tri_tests, shape_tests, xform_evals} that the kernel adds to. */
+int rt_trace_closest_device(RtScene* scene, const RtRay* d_rays, size_t n, RtHit* d_hits,
+                            uint64_t* d_work, void* stream);
+int rt_trace_any_device(RtScene* scene, const RtRay* d_rays, size_t n, uint8_t* d_hits,
+                        uint64_t* d_work, void* stream);
+
+/* raytrace() (RaytraceMain.cpp:485-579): render the tiles of this rank into rgb
+ * (width*height*3 floats, row-major, rows top-down like Image::pixel).  Pixels
+ * of other ranks' tiles are left untouched.  Host output buffer. */
+int rt_render(RtScene* scene, const RtCamera* camera, const RtRenderParams* params,
+              float* rgb, RtRenderStats* stats);
+/* Same with a device output buffer; enqueues on `stream` and synchronises it
+ * before returning so that stats are final. */
+int rt_render_device(RtScene* scene, const RtCamera* camera, const RtRenderParams* params,
+                     float* d_rgb, RtRenderStats* stats, void* stream);
+
+/* Generate only the camera rays of pixel-sample `psi` for every pixel of this
+ * rank's tiles (RenderThread::run, RaytraceMain.cpp:112-142): rays[y*width+x]. */
+int rt_generate_camera_rays(RtScene* scene, const RtCamera* camera, const RtRenderParams* params,
+                            uint32_t psi, RtRay* rays);
+
+/* displayImage() (MainWindow.cpp:37-91): exposure, gamma, clamp, truncate to
+ * 8 bits.  out is width*height*4 bytes B,G,R,A.  Host buffers. */
+int rt_tonemap_bgra8(int device, const float* rgb, size_t num_pixels, float exposure_stops, float gamma,
+                     uint8_t* bgra);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* RAYITO_B200_H */

@@ -1,0 +1,60 @@
+/*
+ * rayito_b200_host -- C helpers of the host library (librayito_host.so).
+ *
+ * The host library is the C++ mirror of the Rayito API (namespace Rayito: Shape,
+ * ShapeSet, Plane, Sphere, Mesh, lights, materials, PerspectiveCamera, raytrace()).
+ * These few C entry points exist so that tools and tests written in another
+ * language can (a) build the reference GUI's scenes through that C++ API
+ * (MainWindow.cpp:139-229 scene 1, :289-361 scene 2, plus the synthetic big-mesh
+ * scene of BASELINE.json) and get the flattened RtSceneDesc that
+ * rt_scene_create() consumes, and (b) call Rayito::raytrace() end to end.
+ */
+#ifndef RAYITO_B200_HOST_H
+#define RAYITO_B200_HOST_H
+
+#include "rayito_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum
+{
+    RTH_RECIPE_STAGE7_SCENE1 = 1,   /* needs obj_path = .../models/bumpy.obj */
+    RTH_RECIPE_STAGE7_SCENE2 = 2,
+    RTH_RECIPE_SYNTHETIC_MESH = 5   /* grid_u x grid_v quads on a displaced sphere */
+};
+
+typedef struct RthScene RthScene;
+
+const char* rth_last_error_string(void);
+
+/* Build a recipe scene with the C++ API, run findLights() + prepare() (host BVH
+ * builds included) and flatten it.  Returns NULL on failure. */
+RthScene* rth_scene_create(int recipe, const char* obj_path, unsigned grid_u, unsigned grid_v);
+void rth_scene_destroy(RthScene* scene);
+/* Flattened scene; valid until rth_scene_destroy(). */
+const RtSceneDesc* rth_scene_desc(const RthScene* scene);
+double rth_scene_prepare_seconds(const RthScene* scene);
+/* Deepest leaf of the top-level BVH (mesh < 0) or of mesh #mesh (root = 0). */
+unsigned rth_scene_depth(const RthScene* scene, int mesh);
+
+/* PerspectiveCamera constructor (RaytraceMain.cpp:205-222).  spec14 = fov degrees,
+ * origin xyz, target xyz, up xyz, focal distance, lens radius, shutter open, close. */
+int rth_camera(const float* spec14, RtCamera* out);
+/* The camera the reference GUI uses for the recipe, at the UI default settings. */
+void rth_scene_default_camera(const RthScene* scene, float* spec14);
+
+/* Build the recipe scene and call Rayito::raytrace() on it (what the GUI's render
+ * button does, MainWindow.cpp:232-238).  rgb = width*height*3 floats. */
+int rth_raytrace(int recipe, const char* obj_path, unsigned grid_u, unsigned grid_v,
+                 const float* spec14, unsigned width, unsigned height,
+                 unsigned pixel_samples_hint, unsigned light_samples_hint, unsigned max_ray_depth,
+                 int device, unsigned rank, unsigned world, int count_work,
+                 float* rgb, RtRenderStats* stats);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* RAYITO_B200_HOST_H */

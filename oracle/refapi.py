@@ -1,0 +1,178 @@
+"""ORACLE (test infrastructure): ctypes access to oracle/_ref/libref_s7.so, the
+UNMODIFIED reference Stage 7 render core compiled from /root/reference by
+oracle/Makefile.  Only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference leg may import this module; the product never does.
+
+The library is built in the CPU container (where /root/reference exists) and
+travels to the GPU box inside the repository snapshot; nothing here reads
+/root/reference at run time.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "_ref", "libref_s7.so")
+
+REFHIT_DTYPE = np.dtype([("t", "<f4"), ("shape", "<i4"), ("face", "<i4"), ("tri", "<i4"),
+                         ("normal", "<f4", 3), ("color_modifier", "<f4", 3)])
+
+
+class RefRenderStats(C.Structure):
+    _fields_ = [("render_seconds", C.c_double), ("prepare_seconds", C.c_double),
+                ("closest_calls", C.c_uint64), ("any_calls", C.c_uint64), ("threads", C.c_uint)]
+
+
+_lib = None
+
+
+def available():
+    return os.path.exists(LIB_PATH)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not available():
+            raise RuntimeError("oracle/_ref/libref_s7.so is missing: run `make -C oracle ref` where /root/reference exists")
+        L = C.CDLL(LIB_PATH, mode=C.RTLD_LOCAL)
+        vp = C.c_void_p
+        L.ref_scene_create.restype = vp
+        L.ref_scene_create.argtypes = [C.c_int, C.c_char_p, C.c_uint, C.c_uint]
+        L.ref_scene_destroy.argtypes = [vp]
+        L.ref_scene_num_finite.argtypes = [vp]
+        L.ref_scene_num_infinite.argtypes = [vp]
+        L.ref_scene_prepare_seconds.restype = C.c_double
+        L.ref_scene_prepare_seconds.argtypes = [vp]
+        L.ref_trace_closest.argtypes = [vp, vp, C.c_size_t, vp]
+        L.ref_trace_any.argtypes = [vp, vp, C.c_size_t, vp]
+        L.ref_render.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_uint, C.c_uint, C.c_uint, vp,
+                                 C.POINTER(RefRenderStats), C.c_int]
+        L.ref_recorded_rays.restype = C.c_size_t
+        L.ref_recorded_rays.argtypes = [C.c_int, vp, C.c_size_t]
+        L.ref_bvh_nodes.restype = C.c_uint
+        L.ref_bvh_nodes.argtypes = [vp, C.c_int, vp, C.c_uint]
+        L.ref_mesh_counts.argtypes = [vp, C.c_int] + [C.POINTER(C.c_uint)] * 4
+        L.ref_mesh_data.argtypes = [vp, C.c_int] + [vp] * 7
+        L.ref_shape_keys.restype = C.c_uint
+        L.ref_shape_keys.argtypes = [vp, C.c_int, vp, C.c_uint]
+        L.ref_rng_sequence.argtypes = [C.c_uint, C.c_uint, C.c_size_t, vp]
+        L.ref_cmj_1d.argtypes = [C.c_uint, C.c_uint, C.c_uint, vp]
+        L.ref_cmj_2d.argtypes = [C.c_uint, C.c_uint, C.c_uint, C.c_uint, vp]
+        L.ref_camera_rays.argtypes = [vp, vp, C.c_size_t, vp]
+        L.ref_build_info.restype = C.c_char_p
+        _lib = L
+    return _lib
+
+
+class RefScene:
+    """A recipe scene built against the reference's own classes and prepared once."""
+
+    def __init__(self, recipe, obj_path=None, grid=(0, 0)):
+        self.handle = lib().ref_scene_create(recipe, obj_path.encode() if obj_path else None, grid[0], grid[1])
+        if not self.handle:
+            raise RuntimeError("ref_scene_create failed")
+
+    @property
+    def num_finite(self):
+        return lib().ref_scene_num_finite(self.handle)
+
+    @property
+    def num_infinite(self):
+        return lib().ref_scene_num_infinite(self.handle)
+
+    def trace_closest(self, rays):
+        rays = np.ascontiguousarray(rays)
+        out = np.zeros(len(rays), REFHIT_DTYPE)
+        lib().ref_trace_closest(self.handle, rays.ctypes.data, len(rays), out.ctypes.data)
+        return out
+
+    def trace_any(self, rays):
+        rays = np.ascontiguousarray(rays)
+        out = np.zeros(len(rays), np.uint8)
+        lib().ref_trace_any(self.handle, rays.ctypes.data, len(rays), out.ctypes.data)
+        return out
+
+    def render(self, camera_spec14, width, height, ps, ls=1, depth=3, record_rays=False):
+        spec = np.ascontiguousarray(camera_spec14, np.float32)
+        img = np.zeros((height, width, 3), np.float32)
+        stats = RefRenderStats()
+        rc = lib().ref_render(self.handle, spec.ctypes.data, width, height, ps, ls, depth, img.ctypes.data,
+                              C.byref(stats), 1 if record_rays else 0)
+        if rc != 0:
+            raise RuntimeError("ref_render failed")
+        return img, stats
+
+    def recorded_rays(self, kind, dtype):
+        n = lib().ref_recorded_rays(kind, None, 0)
+        out = np.zeros(n, dtype)
+        lib().ref_recorded_rays(kind, out.ctypes.data, n)
+        return out
+
+    def bvh_nodes(self, shape=-1):
+        n = lib().ref_bvh_nodes(self.handle, shape, None, 0)
+        out = np.zeros((n, 8), np.uint32)
+        if n:
+            lib().ref_bvh_nodes(self.handle, shape, out.ctypes.data, n)
+        return out
+
+    def mesh(self, shape):
+        counts = [C.c_uint() for _ in range(4)]
+        if lib().ref_mesh_counts(self.handle, shape, *[C.byref(c) for c in counts]) != 0:
+            return None
+        nv, nn, nf, ni = [c.value for c in counts]
+        m = {
+            "vertices": np.zeros((nv, 3), np.float32), "normals": np.zeros((nn, 3), np.float32),
+            "face_sizes": np.zeros(nf, np.uint32), "vertex_index": np.zeros(ni, np.uint32),
+            "normal_index": np.zeros(ni, np.uint32), "area_cdf": np.zeros(nf + 1, np.float32),
+            "bbox": np.zeros(6, np.float32),
+        }
+        lib().ref_mesh_data(self.handle, shape, m["vertices"].ctypes.data, m["normals"].ctypes.data,
+                            m["face_sizes"].ctypes.data, m["vertex_index"].ctypes.data,
+                            m["normal_index"].ctypes.data, m["area_cdf"].ctypes.data, m["bbox"].ctypes.data)
+        return m
+
+    def shape_keys(self, shape):
+        n = lib().ref_shape_keys(self.handle, shape, None, 0)
+        out = np.zeros((n, 11), np.float32)
+        if n:
+            lib().ref_shape_keys(self.handle, shape, out.ctypes.data, n)
+        return out
+
+    def close(self):
+        if self.handle:
+            lib().ref_scene_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def rng_sequence(z, w, count):
+    out = np.zeros(count, np.uint32)
+    lib().ref_rng_sequence(z, w, count, out.ctypes.data)
+    return out
+
+
+def cmj_1d(samples, permutation, count):
+    out = np.zeros(count, np.float32)
+    lib().ref_cmj_1d(samples, permutation, count, out.ctypes.data)
+    return out
+
+
+def cmj_2d(xs, ys, permutation, count):
+    out = np.zeros((count, 2), np.float32)
+    lib().ref_cmj_2d(xs, ys, permutation, count, out.ctypes.data)
+    return out
+
+
+def camera_rays(camera_spec14, args5, ray_dtype):
+    spec = np.ascontiguousarray(camera_spec14, np.float32)
+    args = np.ascontiguousarray(args5, np.float32)
+    out = np.zeros(len(args), ray_dtype)
+    lib().ref_camera_rays(spec.ctypes.data, args.ctypes.data, len(args), out.ctypes.data)
+    return out

@@ -1,0 +1,292 @@
+"""ctypes bindings of the two native libraries (include/rayito_b200.h,
+include/rayito_b200_host.h).  Thin by design: the product is the CUDA core; Python
+only moves pointers.  Loading fails loudly if the libraries are not built, and
+every compute call raises when the CUDA core reports an error -- there is no
+Python or CPU fallback for any of them."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+
+class RtError(RuntimeError):
+    pass
+
+
+class RtRay(C.Structure):
+    _fields_ = [("origin", C.c_float * 3), ("direction", C.c_float * 3), ("tmax", C.c_float), ("time", C.c_float)]
+
+
+RAY_DTYPE = np.dtype([("origin", "<f4", 3), ("direction", "<f4", 3), ("tmax", "<f4"), ("time", "<f4")])
+HIT_DTYPE = np.dtype([("t", "<f4"), ("shape", "<i4"), ("face", "<i4"), ("tri", "<i4")])
+HITEX_DTYPE = np.dtype([("t", "<f4"), ("shape", "<i4"), ("face", "<i4"), ("tri", "<i4"),
+                        ("normal", "<f4", 3), ("color_modifier", "<f4")])
+
+
+class RtCamera(C.Structure):
+    _fields_ = [("origin", C.c_float * 3), ("forward", C.c_float * 3), ("right", C.c_float * 3), ("up", C.c_float * 3),
+                ("tan_fov", C.c_float), ("focal_distance", C.c_float), ("lens_radius", C.c_float),
+                ("shutter_open", C.c_float), ("shutter_close", C.c_float)]
+
+
+class RtRenderParams(C.Structure):
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32),
+                ("pixel_samples_hint", C.c_uint32), ("light_samples_hint", C.c_uint32),
+                ("max_ray_depth", C.c_uint32), ("tile_size", C.c_uint32),
+                ("rank", C.c_uint32), ("world", C.c_uint32),
+                ("max_batch_samples", C.c_uint32), ("flags", C.c_uint32)]
+
+
+RT_RENDER_COUNT_WORK = 1
+
+
+class RtRenderStats(C.Structure):
+    _fields_ = [("samples", C.c_uint64), ("closest_rays", C.c_uint64), ("any_rays", C.c_uint64),
+                ("node_pops", C.c_uint64), ("tri_tests", C.c_uint64), ("shape_tests", C.c_uint64),
+                ("xform_evals", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("render_ms", C.c_float), ("trace_ms", C.c_float), ("upload_ms", C.c_float), ("download_ms", C.c_float)]
+
+    def as_dict(self):
+        return {name: getattr(self, name) for name, _ in self._fields_}
+
+
+class RtSceneDesc(C.Structure):
+    """Opaque to Python except for a few counters used by tests (layout of
+    include/rayito_b200.h RtSceneDesc)."""
+    _p = C.c_void_p
+    _u = C.c_uint32
+    _fields_ = [("abi_version", _u), ("set_xform", _u),
+                ("num_finite", _u), ("num_infinite", _u), ("shapes", _p),
+                ("num_top_nodes", _u), ("top_nodes", _p),
+                ("num_xforms", _u), ("xforms", _p),
+                ("num_keys", _u), ("key_time", _p), ("key_scale", _p), ("key_rotation", _p), ("key_translation", _p),
+                ("num_planes", _u), ("planes", _p), ("num_spheres", _u), ("spheres", _p),
+                ("num_rects", _u), ("rects", _p), ("num_meshes", _u), ("meshes", _p),
+                ("num_vertices", _u), ("vertices", _p), ("num_normals", _u), ("normals", _p),
+                ("num_faces", _u), ("face_start", _p), ("face_has_normals", _p),
+                ("num_indices", _u), ("vertex_index", _p), ("normal_index", _p),
+                ("num_mesh_nodes", _u), ("mesh_nodes", _p),
+                ("num_cdf", _u), ("face_area_cdf", _p),
+                ("num_materials", _u), ("materials", _p),
+                ("num_lights", _u), ("lights", _p)]
+
+
+class RtMesh(C.Structure):
+    _u = C.c_uint32
+    _fields_ = [("first_vertex", _u), ("num_vertices", _u), ("first_normal", _u), ("num_normals", _u),
+                ("first_face", _u), ("num_faces", _u), ("first_node", _u), ("num_nodes", _u),
+                ("first_cdf", _u), ("total_area", C.c_float)]
+
+
+class RtShape(C.Structure):
+    _u = C.c_uint32
+    _fields_ = [("type", _u), ("geom", _u), ("xform", _u), ("material", _u), ("light", C.c_int32)]
+
+
+class RtXform(C.Structure):
+    _fields_ = [("first_key", C.c_uint32), ("num_keys", C.c_uint32)]
+
+
+RECIPE_STAGE7_SCENE1 = 1
+RECIPE_STAGE7_SCENE2 = 2
+RECIPE_SYNTHETIC_MESH = 5
+
+# Every symbol include/rayito_b200.h declares (checked by the CPU test-suite)
+CORE_SYMBOLS = [
+    "rt_last_error_string", "rt_abi_version", "rt_device_count",
+    "rt_scene_create", "rt_scene_destroy",
+    "rt_trace_closest", "rt_trace_closest_ex", "rt_trace_any",
+    "rt_trace_closest_device", "rt_trace_any_device",
+    "rt_render", "rt_render_device", "rt_generate_camera_rays", "rt_tonemap_bgra8",
+]
+HOST_SYMBOLS = [
+    "rth_last_error_string", "rth_scene_create", "rth_scene_destroy", "rth_scene_desc",
+    "rth_scene_prepare_seconds", "rth_scene_depth", "rth_camera", "rth_scene_default_camera", "rth_raytrace",
+]
+
+_core = None
+_host = None
+
+
+def core():
+    """librayito_b200.so (built on demand; raises if it cannot be built or loaded)."""
+    global _core
+    if _core is None:
+        path = _build.build_core()
+        lib = C.CDLL(path, mode=C.RTLD_LOCAL)
+        vp, sz, u32 = C.c_void_p, C.c_size_t, C.c_uint32
+        lib.rt_last_error_string.restype = C.c_char_p
+        lib.rt_scene_create.argtypes = [vp, C.c_int, C.POINTER(vp)]
+        lib.rt_scene_destroy.argtypes = [vp]
+        lib.rt_trace_closest.argtypes = [vp, vp, sz, vp]
+        lib.rt_trace_closest_ex.argtypes = [vp, vp, sz, vp]
+        lib.rt_trace_any.argtypes = [vp, vp, sz, vp]
+        lib.rt_trace_closest_device.argtypes = [vp, vp, sz, vp, vp, vp]
+        lib.rt_trace_any_device.argtypes = [vp, vp, sz, vp, vp, vp]
+        lib.rt_render.argtypes = [vp, C.POINTER(RtCamera), C.POINTER(RtRenderParams), vp, C.POINTER(RtRenderStats)]
+        lib.rt_render_device.argtypes = [vp, C.POINTER(RtCamera), C.POINTER(RtRenderParams), vp,
+                                         C.POINTER(RtRenderStats), vp]
+        lib.rt_generate_camera_rays.argtypes = [vp, C.POINTER(RtCamera), C.POINTER(RtRenderParams), u32, vp]
+        lib.rt_tonemap_bgra8.argtypes = [C.c_int, vp, sz, C.c_float, C.c_float, vp]
+        _core = lib
+    return _core
+
+
+def host():
+    """librayito_host.so (the C++ mirror of the Rayito API)."""
+    global _host
+    if _host is None:
+        core()
+        path = _build.build_host()
+        lib = C.CDLL(path, mode=C.RTLD_LOCAL)
+        vp = C.c_void_p
+        lib.rth_last_error_string.restype = C.c_char_p
+        lib.rth_scene_create.restype = vp
+        lib.rth_scene_create.argtypes = [C.c_int, C.c_char_p, C.c_uint, C.c_uint]
+        lib.rth_scene_destroy.argtypes = [vp]
+        lib.rth_scene_desc.restype = C.POINTER(RtSceneDesc)
+        lib.rth_scene_desc.argtypes = [vp]
+        lib.rth_scene_prepare_seconds.restype = C.c_double
+        lib.rth_scene_prepare_seconds.argtypes = [vp]
+        lib.rth_scene_depth.restype = C.c_uint
+        lib.rth_scene_depth.argtypes = [vp, C.c_int]
+        lib.rth_camera.argtypes = [vp, C.POINTER(RtCamera)]
+        lib.rth_scene_default_camera.argtypes = [vp, vp]
+        lib.rth_raytrace.argtypes = [C.c_int, C.c_char_p, C.c_uint, C.c_uint, vp, C.c_uint, C.c_uint,
+                                     C.c_uint, C.c_uint, C.c_uint, C.c_int, C.c_uint, C.c_uint, C.c_int,
+                                     vp, C.POINTER(RtRenderStats)]
+        _host = lib
+    return _host
+
+
+def check(rc, what="rayito_b200"):
+    if rc != 0:
+        raise RtError("%s failed (%d): %s" % (what, rc, core().rt_last_error_string().decode()))
+
+
+class HostScene:
+    """A recipe scene built with the C++ host API, prepared and flattened."""
+
+    def __init__(self, recipe, obj_path=None, grid=(0, 0)):
+        lib = host()
+        path = obj_path.encode() if obj_path else None
+        self.handle = lib.rth_scene_create(recipe, path, grid[0], grid[1])
+        if not self.handle:
+            raise RtError("rth_scene_create: " + lib.rth_last_error_string().decode())
+        self.recipe = recipe
+        self.obj_path = obj_path
+        self.grid = grid
+
+    @property
+    def desc(self):
+        return host().rth_scene_desc(self.handle)
+
+    @property
+    def prepare_seconds(self):
+        return host().rth_scene_prepare_seconds(self.handle)
+
+    def depth(self, mesh=-1):
+        return host().rth_scene_depth(self.handle, mesh)
+
+    def default_camera_spec(self):
+        spec = np.zeros(14, np.float32)
+        host().rth_scene_default_camera(self.handle, spec.ctypes.data)
+        return spec
+
+    def close(self):
+        if self.handle:
+            host().rth_scene_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def camera_from_spec(spec14):
+    spec = np.ascontiguousarray(spec14, np.float32)
+    cam = RtCamera()
+    if host().rth_camera(spec.ctypes.data, C.byref(cam)) != 0:
+        raise RtError("rth_camera failed")
+    return cam
+
+
+class DeviceScene:
+    """RtScene handle: a flattened scene uploaded to one GPU."""
+
+    def __init__(self, desc, device=0):
+        self.handle = C.c_void_p()
+        check(core().rt_scene_create(C.cast(desc, C.c_void_p), device, C.byref(self.handle)), "rt_scene_create")
+        self.device = device
+
+    def trace_closest(self, rays, extended=False):
+        rays = np.ascontiguousarray(rays)
+        assert rays.dtype == RAY_DTYPE
+        hits = np.empty(len(rays), HITEX_DTYPE if extended else HIT_DTYPE)
+        fn = core().rt_trace_closest_ex if extended else core().rt_trace_closest
+        check(fn(self.handle, rays.ctypes.data, len(rays), hits.ctypes.data), "rt_trace_closest")
+        return hits
+
+    def trace_any(self, rays):
+        rays = np.ascontiguousarray(rays)
+        assert rays.dtype == RAY_DTYPE
+        hits = np.empty(len(rays), np.uint8)
+        check(core().rt_trace_any(self.handle, rays.ctypes.data, len(rays), hits.ctypes.data), "rt_trace_any")
+        return hits
+
+    def render(self, camera, width, height, ps, ls=1, depth=3, rank=0, world=1, tile_size=0,
+               max_batch_samples=0, count_work=False, out=None):
+        params = RtRenderParams(width, height, ps, ls, depth, tile_size, rank, world, max_batch_samples,
+                                RT_RENDER_COUNT_WORK if count_work else 0)
+        if out is None:
+            out = np.zeros((height, width, 3), np.float32)
+        stats = RtRenderStats()
+        check(core().rt_render(self.handle, C.byref(camera), C.byref(params), out.ctypes.data, C.byref(stats)),
+              "rt_render")
+        return out, stats
+
+    def render_device(self, camera, params, d_rgb_ptr, stream=None):
+        stats = RtRenderStats()
+        check(core().rt_render_device(self.handle, C.byref(camera), C.byref(params), d_rgb_ptr, C.byref(stats),
+                                      stream), "rt_render_device")
+        return stats
+
+    def camera_rays(self, camera, width, height, ps, psi, ls=1, depth=3):
+        params = RtRenderParams(width, height, ps, ls, depth, 0, 0, 1, 0, 0)
+        rays = np.zeros(width * height, RAY_DTYPE)
+        check(core().rt_generate_camera_rays(self.handle, C.byref(camera), C.byref(params), psi, rays.ctypes.data),
+              "rt_generate_camera_rays")
+        return rays
+
+    def close(self):
+        if self.handle:
+            core().rt_scene_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def tonemap_bgra8(rgb, exposure_stops=0.0, gamma=2.2, device=0):
+    rgb = np.ascontiguousarray(rgb, np.float32)
+    n = rgb.size // 3
+    out = np.empty((n, 4), np.uint8)
+    check(core().rt_tonemap_bgra8(device, rgb.ctypes.data, n, exposure_stops, gamma, out.ctypes.data), "rt_tonemap_bgra8")
+    return out.reshape(rgb.shape[:-1] + (4,))
+
+
+def make_rays(origins, directions, tmax=1.0e30, time=0.0):
+    n = len(origins)
+    rays = np.zeros(n, RAY_DTYPE)
+    rays["origin"] = origins
+    rays["direction"] = directions
+    rays["tmax"] = tmax
+    rays["time"] = time
+    return rays

@@ -1,0 +1,277 @@
+// librayito_b200.so -- C ABI (include/rayito_b200.h) and the ray-batch kernels.
+//
+// Built for sm_100a only, with -fmad=false (see rt_device.cuh for the arithmetic
+// contract).  There is deliberately no CPU implementation in this library: every
+// compute entry point needs a CUDA device and fails loudly without one.
+#include <cstdio>
+#include <string>
+
+#include "rt_scene.cuh"
+#include "rt_trace.cuh"
+#include "rt_render.cuh"
+
+thread_local std::string g_rt_error;
+
+int rt_fail(int code, const std::string& what)
+{
+    g_rt_error = what;
+    return code;
+}
+
+int rt_cuda_fail(cudaError_t e, const char* where)
+{
+    g_rt_error = std::string("CUDA error at ") + where + ": " + cudaGetErrorString(e);
+    cudaGetLastError();
+    return RT_ERR_CUDA;
+}
+
+// ---------------------------------------------------------------------------
+// Ray-batch kernels: one ray per thread.
+// ---------------------------------------------------------------------------
+
+__device__ __forceinline__ void load_ray(const RtRay* rays, size_t i, V3& o, V3& d, float& tmax, float& time)
+{
+    const float4* p = reinterpret_cast<const float4*>(rays + i);
+    float4 a = __ldg(p);
+    float4 b = __ldg(p + 1);
+    o = mk(a.x, a.y, a.z);
+    d = mk(a.w, b.x, b.y);
+    tmax = b.z;
+    time = b.w;
+}
+
+__device__ __forceinline__ void flush_work(const WorkCount& wc, uint64_t* work)
+{
+    // Warp-reduce, then one atomic per counter per warp
+    uint32_t v[4] = { wc.node_pops, wc.tri_tests, wc.shape_tests, wc.xform_evals };
+    for (int k = 0; k < 4; ++k)
+    {
+        uint32_t x = v[k];
+        for (int off = 16; off > 0; off >>= 1)
+            x += __shfl_down_sync(0xffffffffu, x, off);
+        if ((threadIdx.x & 31) == 0 && x)
+            atomicAdd(reinterpret_cast<unsigned long long*>(work + k), (unsigned long long)x);
+    }
+}
+
+template <int CAP, bool COUNT, bool EX>
+__global__ void __launch_bounds__(128)
+k_trace_closest(const __grid_constant__ DScene sc, const RtRay* __restrict__ rays, size_t n,
+                void* __restrict__ hits, uint64_t* work)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    WorkCount wc = { 0, 0, 0, 0 };
+    if (i < n)
+    {
+        V3 o, d;
+        float tmax, time;
+        load_ray(rays, i, o, d, tmax, time);
+        LocalRay r0;
+        ClosestHit h = trace_closest<CAP, COUNT>(sc, o, d, tmax, time, r0, wc);
+        int32_t face = -1, tri = -1;
+        if (h.tri_rec >= 0)
+        {
+            face = (int32_t)__float_as_uint(__ldg(sc.tris + 3 * (size_t)h.tri_rec + 0).w);
+            tri = (int32_t)__float_as_uint(__ldg(sc.tris + 3 * (size_t)h.tri_rec + 1).w);
+        }
+        if (EX)
+        {
+            V3 nrm;
+            float cm;
+            hit_shading_inputs(sc, r0, time, h, nrm, cm);
+            float4* out = reinterpret_cast<float4*>(static_cast<RtHitEx*>(hits) + i);
+            out[0] = make_float4(h.t, __int_as_float(h.shape), __int_as_float(face), __int_as_float(tri));
+            out[1] = make_float4(nrm.x, nrm.y, nrm.z, cm);
+        }
+        else
+        {
+            float4* out = reinterpret_cast<float4*>(static_cast<RtHit*>(hits) + i);
+            out[0] = make_float4(h.t, __int_as_float(h.shape), __int_as_float(face), __int_as_float(tri));
+        }
+    }
+    if (COUNT)
+        flush_work(wc, work);
+}
+
+template <int CAP, bool COUNT>
+__global__ void __launch_bounds__(128)
+k_trace_any(const __grid_constant__ DScene sc, const RtRay* __restrict__ rays, size_t n,
+            uint8_t* __restrict__ hits, uint64_t* work)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    WorkCount wc = { 0, 0, 0, 0 };
+    if (i < n)
+    {
+        V3 o, d;
+        float tmax, time;
+        load_ray(rays, i, o, d, tmax, time);
+        hits[i] = trace_any<CAP, COUNT>(sc, o, d, tmax, time, wc) ? 1 : 0;
+    }
+    if (COUNT)
+        flush_work(wc, work);
+}
+
+template <bool COUNT, bool EX>
+static int launch_closest(RtScene* s, const RtRay* d_rays, size_t n, void* d_hits, uint64_t* d_work, cudaStream_t st)
+{
+    if (n == 0) return RT_OK;
+    unsigned blocks = (unsigned)((n + 127) / 128);
+    if (s->stack_cap <= 32)       k_trace_closest<32, COUNT, EX><<<blocks, 128, 0, st>>>(s->d, d_rays, n, d_hits, d_work);
+    else if (s->stack_cap <= 64)  k_trace_closest<64, COUNT, EX><<<blocks, 128, 0, st>>>(s->d, d_rays, n, d_hits, d_work);
+    else                          k_trace_closest<104, COUNT, EX><<<blocks, 128, 0, st>>>(s->d, d_rays, n, d_hits, d_work);
+    RT_CUDA(cudaGetLastError());
+    return RT_OK;
+}
+
+template <bool COUNT>
+static int launch_any(RtScene* s, const RtRay* d_rays, size_t n, uint8_t* d_hits, uint64_t* d_work, cudaStream_t st)
+{
+    if (n == 0) return RT_OK;
+    unsigned blocks = (unsigned)((n + 127) / 128);
+    if (s->stack_cap <= 32)       k_trace_any<32, COUNT><<<blocks, 128, 0, st>>>(s->d, d_rays, n, d_hits, d_work);
+    else if (s->stack_cap <= 64)  k_trace_any<64, COUNT><<<blocks, 128, 0, st>>>(s->d, d_rays, n, d_hits, d_work);
+    else                          k_trace_any<104, COUNT><<<blocks, 128, 0, st>>>(s->d, d_rays, n, d_hits, d_work);
+    RT_CUDA(cudaGetLastError());
+    return RT_OK;
+}
+
+static int ensure_scratch(RtScene* s, size_t in_bytes, size_t out_bytes)
+{
+    if (in_bytes > s->scratch_in_bytes)
+    {
+        if (s->scratch_in) cudaFree(s->scratch_in);
+        s->scratch_in = NULL;
+        s->scratch_in_bytes = 0;
+        RT_CUDA(cudaMalloc(&s->scratch_in, in_bytes));
+        s->scratch_in_bytes = in_bytes;
+    }
+    if (out_bytes > s->scratch_out_bytes)
+    {
+        if (s->scratch_out) cudaFree(s->scratch_out);
+        s->scratch_out = NULL;
+        s->scratch_out_bytes = 0;
+        RT_CUDA(cudaMalloc(&s->scratch_out, out_bytes));
+        s->scratch_out_bytes = out_bytes;
+    }
+    return RT_OK;
+}
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+extern "C"
+{
+
+const char* rt_last_error_string(void) { return g_rt_error.c_str(); }
+
+int rt_abi_version(void) { return RT_ABI_VERSION; }
+
+int rt_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int rt_scene_create(const RtSceneDesc* desc, int device, RtScene** out_scene)
+{
+    return rt_scene_build(desc, device, out_scene);
+}
+
+int rt_scene_destroy(RtScene* s)
+{
+    if (s == NULL) return RT_OK;
+    cudaSetDevice(s->device);
+    rt_render_release(s);
+    if (s->scratch_in) cudaFree(s->scratch_in);
+    if (s->scratch_out) cudaFree(s->scratch_out);
+    if (s->d_work) cudaFree(s->d_work);
+    if (s->arena) cudaFree(s->arena);
+    delete s;
+    return RT_OK;
+}
+
+int rt_trace_closest_device(RtScene* s, const RtRay* d_rays, size_t n, RtHit* d_hits, uint64_t* d_work, void* stream)
+{
+    if (s == NULL || (n && (d_rays == NULL || d_hits == NULL))) return rt_fail(RT_ERR_ARG, "null argument");
+    RT_CUDA(cudaSetDevice(s->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return d_work ? launch_closest<true, false>(s, d_rays, n, d_hits, d_work, st)
+                  : launch_closest<false, false>(s, d_rays, n, d_hits, NULL, st);
+}
+
+int rt_trace_any_device(RtScene* s, const RtRay* d_rays, size_t n, uint8_t* d_hits, uint64_t* d_work, void* stream)
+{
+    if (s == NULL || (n && (d_rays == NULL || d_hits == NULL))) return rt_fail(RT_ERR_ARG, "null argument");
+    RT_CUDA(cudaSetDevice(s->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return d_work ? launch_any<true>(s, d_rays, n, d_hits, d_work, st)
+                  : launch_any<false>(s, d_rays, n, d_hits, NULL, st);
+}
+
+static int trace_closest_host(RtScene* s, const RtRay* rays, size_t n, void* hits, bool ex)
+{
+    if (s == NULL || (n && (rays == NULL || hits == NULL))) return rt_fail(RT_ERR_ARG, "null argument");
+    if (n == 0) return RT_OK;
+    RT_CUDA(cudaSetDevice(s->device));
+    size_t out_bytes = n * (ex ? sizeof(RtHitEx) : sizeof(RtHit));
+    int rc = ensure_scratch(s, n * sizeof(RtRay), out_bytes);
+    if (rc != RT_OK) return rc;
+    RT_CUDA(cudaMemcpy(s->scratch_in, rays, n * sizeof(RtRay), cudaMemcpyHostToDevice));
+    rc = ex ? launch_closest<false, true>(s, static_cast<const RtRay*>(s->scratch_in), n, s->scratch_out, NULL, 0)
+            : launch_closest<false, false>(s, static_cast<const RtRay*>(s->scratch_in), n, s->scratch_out, NULL, 0);
+    if (rc != RT_OK) return rc;
+    RT_CUDA(cudaMemcpy(hits, s->scratch_out, out_bytes, cudaMemcpyDeviceToHost));
+    return RT_OK;
+}
+
+int rt_trace_closest(RtScene* s, const RtRay* rays, size_t n, RtHit* hits)
+{
+    return trace_closest_host(s, rays, n, hits, false);
+}
+
+int rt_trace_closest_ex(RtScene* s, const RtRay* rays, size_t n, RtHitEx* hits)
+{
+    return trace_closest_host(s, rays, n, hits, true);
+}
+
+int rt_trace_any(RtScene* s, const RtRay* rays, size_t n, uint8_t* hits)
+{
+    if (s == NULL || (n && (rays == NULL || hits == NULL))) return rt_fail(RT_ERR_ARG, "null argument");
+    if (n == 0) return RT_OK;
+    RT_CUDA(cudaSetDevice(s->device));
+    int rc = ensure_scratch(s, n * sizeof(RtRay), n);
+    if (rc != RT_OK) return rc;
+    RT_CUDA(cudaMemcpy(s->scratch_in, rays, n * sizeof(RtRay), cudaMemcpyHostToDevice));
+    rc = launch_any<false>(s, static_cast<const RtRay*>(s->scratch_in), n, static_cast<uint8_t*>(s->scratch_out), NULL, 0);
+    if (rc != RT_OK) return rc;
+    RT_CUDA(cudaMemcpy(hits, s->scratch_out, n, cudaMemcpyDeviceToHost));
+    return RT_OK;
+}
+
+int rt_render(RtScene* s, const RtCamera* camera, const RtRenderParams* params, float* rgb, RtRenderStats* stats)
+{
+    return rt_render_impl(s, camera, params, rgb, false, stats, 0);
+}
+
+int rt_render_device(RtScene* s, const RtCamera* camera, const RtRenderParams* params, float* d_rgb,
+                     RtRenderStats* stats, void* stream)
+{
+    return rt_render_impl(s, camera, params, d_rgb, true, stats, static_cast<cudaStream_t>(stream));
+}
+
+int rt_generate_camera_rays(RtScene* s, const RtCamera* camera, const RtRenderParams* params, uint32_t psi, RtRay* rays)
+{
+    return rt_camera_rays_impl(s, camera, params, psi, rays);
+}
+
+int rt_tonemap_bgra8(int device, const float* rgb, size_t num_pixels, float exposure_stops, float gamma, uint8_t* bgra)
+{
+    return rt_tonemap_impl(device, rgb, num_pixels, exposure_stops, gamma, bgra);
+}
+
+} // extern "C"

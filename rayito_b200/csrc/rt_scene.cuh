@@ -1,0 +1,431 @@
+// RtScene: the device-resident scene behind the C ABI, and its upload path.
+//
+// rt_scene_create() validates an RtSceneDesc (what ShapeSet::prepare() leaves
+// behind in the reference, RScene.h:186-205 / RMesh.h:89-129), expands polygon
+// faces into fan-triangle records, re-encodes mesh leaves to point at them, and
+// copies everything into ONE HBM arena with a single host->device transfer.
+#ifndef RAYITO_B200_RT_SCENE_CUH
+#define RAYITO_B200_RT_SCENE_CUH
+
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "rt_device.cuh"
+
+extern thread_local std::string g_rt_error;
+
+int rt_fail(int code, const std::string& what);
+int rt_cuda_fail(cudaError_t e, const char* where);
+
+#define RT_CUDA(call)                                               \
+    do {                                                            \
+        cudaError_t e__ = (call);                                   \
+        if (e__ != cudaSuccess) return rt_cuda_fail(e__, #call);    \
+    } while (0)
+
+struct RtScene
+{
+    int device;
+    void* arena;                // one allocation holding every array below
+    size_t arena_bytes;
+    DScene d;                   // device pointers into the arena
+    int stack_cap;              // traversal stack entries needed (both levels)
+    uint32_t num_tris;
+    uint32_t num_faces;
+    std::vector<uint32_t> light_shapes;
+    float upload_ms;
+    // scratch for the host-buffer entry points (grown on demand)
+    void* scratch_in;
+    void* scratch_out;
+    size_t scratch_in_bytes, scratch_out_bytes;
+    uint64_t* d_work;           // 4 counters
+    struct RenderBuffers* render;   // wavefront state (rt_render.cuh), lazily created
+};
+
+namespace rt_detail
+{
+
+// Deepest leaf (root = 0) of a reference-format BVH; -1 if malformed.
+inline int bvh_depth(const RtBvhNode* nodes, uint32_t count, uint32_t num_prims, std::string& why)
+{
+    if (count == 0)
+        return 0;
+    std::vector<std::pair<uint32_t, int> > todo;
+    todo.push_back(std::make_pair(0u, 0));
+    int deepest = 0;
+    size_t visited = 0;
+    while (!todo.empty())
+    {
+        std::pair<uint32_t, int> cur = todo.back();
+        todo.pop_back();
+        if (++visited > count)
+        {
+            why = "BVH has a cycle or shared children";
+            return -1;
+        }
+        const RtBvhNode& n = nodes[cur.first];
+        if (cur.second > deepest) deepest = cur.second;
+        if (n.flags & RT_NODE_LEAF)
+        {
+            if (n.first_child_or_prim >= num_prims)
+            {
+                why = "BVH leaf names a primitive that does not exist";
+                return -1;
+            }
+            continue;
+        }
+        if ((n.flags & RT_NODE_AXIS) == 3u)
+        {
+            why = "BVH node with split axis 3";
+            return -1;
+        }
+        if ((uint64_t)n.first_child_or_prim + 1 >= count)
+        {
+            why = "BVH child index out of range";
+            return -1;
+        }
+        todo.push_back(std::make_pair(n.first_child_or_prim + 1, cur.second + 1));
+        todo.push_back(std::make_pair(n.first_child_or_prim, cur.second + 1));
+    }
+    return deepest;
+}
+
+struct ArenaBuilder
+{
+    std::vector<unsigned char> bytes;
+    // Append an array, 256-byte aligned; returns its offset
+    size_t put(const void* src, size_t n)
+    {
+        size_t off = (bytes.size() + 255) & ~(size_t)255;
+        bytes.resize(off + (n ? n : 16));
+        if (n) std::memcpy(&bytes[off], src, n);
+        return off;
+    }
+};
+
+inline float vlen(const float* v) { return std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
+
+} // namespace rt_detail
+
+inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_scene)
+{
+    using namespace rt_detail;
+    if (desc == NULL || out_scene == NULL)
+        return rt_fail(RT_ERR_ARG, "null argument");
+    *out_scene = NULL;
+    if (desc->abi_version != RT_ABI_VERSION)
+        return rt_fail(RT_ERR_ARG, "RtSceneDesc.abi_version mismatch");
+    const uint32_t num_shapes = desc->num_finite + desc->num_infinite;
+    if (num_shapes > 0 && desc->shapes == NULL)
+        return rt_fail(RT_ERR_ARG, "shapes is null");
+    if (desc->set_xform >= desc->num_xforms)
+        return rt_fail(RT_ERR_ARG, "set_xform out of range");
+    if (desc->num_finite > 2 && desc->num_top_nodes == 0)
+        return rt_fail(RT_ERR_ARG, "more than two finite shapes need a top-level BVH (RScene.h:135)");
+    if (desc->num_finite <= 2 && desc->num_top_nodes != 0)
+        return rt_fail(RT_ERR_ARG, "a top-level BVH is only used with more than two finite shapes");
+
+    for (uint32_t i = 0; i < desc->num_xforms; ++i)
+    {
+        const RtXform& x = desc->xforms[i];
+        if ((uint64_t)x.first_key + x.num_keys > desc->num_keys)
+            return rt_fail(RT_ERR_ARG, "transform key range out of bounds");
+        for (uint32_t k = 1; k < x.num_keys; ++k)
+            if (!(desc->key_time[x.first_key + k - 1] < desc->key_time[x.first_key + k]))
+                return rt_fail(RT_ERR_ARG, "transform key times must be strictly increasing");
+    }
+
+    // Shapes
+    std::vector<DShape> shapes(num_shapes);
+    for (uint32_t i = 0; i < num_shapes; ++i)
+    {
+        const RtShape& s = desc->shapes[i];
+        uint32_t limit = s.type == RT_SHAPE_PLANE ? desc->num_planes :
+                         s.type == RT_SHAPE_SPHERE ? desc->num_spheres :
+                         s.type == RT_SHAPE_RECT ? desc->num_rects :
+                         s.type == RT_SHAPE_MESH ? desc->num_meshes : 0;
+        if (s.geom >= limit || s.xform >= desc->num_xforms || s.material >= desc->num_materials)
+            return rt_fail(RT_ERR_ARG, "shape refers to missing geometry, transform or material");
+        if ((i < desc->num_finite) == (s.type == RT_SHAPE_PLANE))
+            return rt_fail(RT_ERR_ARG, "planes must be the infinite shapes and only they");
+        if (s.light >= (int32_t)desc->num_lights)
+            return rt_fail(RT_ERR_ARG, "shape light index out of range");
+        DShape d;
+        std::memset(&d, 0, sizeof(d));
+        d.type = s.type; d.geom = s.geom; d.xform = s.xform; d.material = s.material; d.light = s.light;
+        shapes[i] = d;
+    }
+    for (uint32_t l = 0; l < desc->num_lights; ++l)
+        if (desc->lights[l] >= num_shapes || desc->shapes[desc->lights[l]].light != (int32_t)l)
+            return rt_fail(RT_ERR_ARG, "lights[] and RtShape.light disagree");
+
+    // BVH depths (the reference's fixed 50-entry stack, RAccel.h:379)
+    std::string why;
+    int top_depth = bvh_depth(desc->top_nodes, desc->num_top_nodes, desc->num_finite, why);
+    if (top_depth < 0)
+        return rt_fail(RT_ERR_ARG, "top-level " + why);
+    if (top_depth > 49)
+        return rt_fail(RT_ERR_DEPTH, "top-level BVH deeper than 49");
+    int mesh_depth = -1;
+    for (uint32_t m = 0; m < desc->num_meshes; ++m)
+    {
+        const RtMesh& mesh = desc->meshes[m];
+        if ((uint64_t)mesh.first_node + mesh.num_nodes > desc->num_mesh_nodes ||
+            (uint64_t)mesh.first_face + mesh.num_faces > desc->num_faces ||
+            (uint64_t)mesh.first_vertex + mesh.num_vertices > desc->num_vertices ||
+            (uint64_t)mesh.first_normal + mesh.num_normals > desc->num_normals ||
+            (uint64_t)mesh.first_cdf + mesh.num_faces + 1 > desc->num_cdf)
+            return rt_fail(RT_ERR_ARG, "mesh ranges out of bounds");
+        if (mesh.num_nodes != 0 && mesh.num_nodes != 2 * mesh.num_faces - 1)
+            return rt_fail(RT_ERR_ARG, "mesh BVH must have 2*faces-1 nodes");
+        int d = bvh_depth(desc->mesh_nodes + mesh.first_node, mesh.num_nodes, mesh.num_faces, why);
+        if (d < 0)
+            return rt_fail(RT_ERR_ARG, "mesh " + why);
+        if (d > 49)
+            return rt_fail(RT_ERR_DEPTH, "mesh BVH deeper than 49: the reference's 50-entry traversal stack would overflow");
+        if (d > mesh_depth) mesh_depth = d;
+    }
+    int stack_cap = (desc->num_top_nodes ? top_depth + 1 : (int)desc->num_finite) + (mesh_depth >= 0 ? mesh_depth + 1 : 0);
+
+    // Fan-expand faces into triangle records
+    std::vector<uint32_t> face_first_tri(desc->num_faces + 1, 0);
+    for (uint32_t f = 0; f < desc->num_faces; ++f)
+    {
+        uint32_t n = desc->face_start[f + 1] - desc->face_start[f];
+        if (desc->face_start[f + 1] < desc->face_start[f] || n < 3 || desc->face_start[f + 1] > desc->num_indices)
+            return rt_fail(RT_ERR_ARG, "face with fewer than 3 vertices or bad face_start");
+        if (n - 2 >= (1u << 28))
+            return rt_fail(RT_ERR_ARG, "face with too many vertices");
+        face_first_tri[f + 1] = face_first_tri[f] + (n - 2);
+    }
+    const uint32_t num_tris = face_first_tri[desc->num_faces];
+    std::vector<float4> tris((size_t)num_tris * 3);
+    std::vector<uint4> tri_normals(num_tris);
+    std::vector<DMesh> meshes(desc->num_meshes);
+    std::vector<DNode> mesh_nodes(desc->num_mesh_nodes);
+    for (uint32_t m = 0; m < desc->num_meshes; ++m)
+    {
+        const RtMesh& mesh = desc->meshes[m];
+        DMesh dm;
+        dm.first_node = mesh.first_node;
+        dm.num_nodes = mesh.num_nodes;
+        dm.first_tri = face_first_tri[mesh.first_face];
+        dm.first_face = mesh.first_face;
+        dm.num_faces = mesh.num_faces;
+        dm.first_cdf = mesh.first_cdf;
+        dm.total_area = mesh.total_area;
+        dm.pad = 0;
+        meshes[m] = dm;
+        for (uint32_t f = 0; f < mesh.num_faces; ++f)
+        {
+            uint32_t gf = mesh.first_face + f;
+            uint32_t start = desc->face_start[gf];
+            uint32_t n = desc->face_start[gf + 1] - start;
+            bool has_n = desc->face_has_normals[gf] != 0;
+            for (uint32_t k = 0; k + 2 < n; ++k)
+            {
+                uint32_t vi[3] = { desc->vertex_index[start], desc->vertex_index[start + k + 1], desc->vertex_index[start + k + 2] };
+                uint32_t rec = face_first_tri[gf] + k;
+                uint32_t words[3] = { f, k, has_n ? 1u : 0u };
+                for (int c = 0; c < 3; ++c)
+                {
+                    if (vi[c] >= mesh.num_vertices)
+                        return rt_fail(RT_ERR_ARG, "vertex index out of range");
+                    const float* v = desc->vertices + 3 * (size_t)(mesh.first_vertex + vi[c]);
+                    float w;
+                    std::memcpy(&w, &words[c], 4);
+                    tris[(size_t)rec * 3 + c] = make_float4(v[0], v[1], v[2], w);
+                }
+                uint4 ni = make_uint4(0, 0, 0, 0);
+                if (has_n)
+                {
+                    uint32_t a = desc->normal_index[start], b = desc->normal_index[start + k + 1], c = desc->normal_index[start + k + 2];
+                    if (a >= mesh.num_normals || b >= mesh.num_normals || c >= mesh.num_normals)
+                        return rt_fail(RT_ERR_ARG, "normal index out of range");
+                    ni = make_uint4(mesh.first_normal + a, mesh.first_normal + b, mesh.first_normal + c, 0);
+                }
+                tri_normals[rec] = ni;
+            }
+        }
+        for (uint32_t i = 0; i < mesh.num_nodes; ++i)
+        {
+            const RtBvhNode& n = desc->mesh_nodes[mesh.first_node + i];
+            uint32_t word = n.first_child_or_prim, flags = n.flags;
+            if (flags & RT_NODE_LEAF)
+            {
+                uint32_t gf = mesh.first_face + n.first_child_or_prim;
+                word = face_first_tri[gf];
+                flags = RT_NODE_LEAF | ((face_first_tri[gf + 1] - face_first_tri[gf]) << 3);
+            }
+            float wf, ff;
+            std::memcpy(&wf, &word, 4);
+            std::memcpy(&ff, &flags, 4);
+            DNode dn;
+            dn.q0 = make_float4(n.bbox_min[0], n.bbox_min[1], n.bbox_min[2], n.bbox_max[0]);
+            dn.q1 = make_float4(n.bbox_max[1], n.bbox_max[2], wf, ff);
+            mesh_nodes[mesh.first_node + i] = dn;
+        }
+    }
+    std::vector<DNode> top_nodes(desc->num_top_nodes);
+    for (uint32_t i = 0; i < desc->num_top_nodes; ++i)
+    {
+        const RtBvhNode& n = desc->top_nodes[i];
+        float wf, ff;
+        std::memcpy(&wf, &n.first_child_or_prim, 4);
+        std::memcpy(&ff, &n.flags, 4);
+        DNode dn;
+        dn.q0 = make_float4(n.bbox_min[0], n.bbox_min[1], n.bbox_min[2], n.bbox_max[0]);
+        dn.q1 = make_float4(n.bbox_max[1], n.bbox_max[2], wf, ff);
+        top_nodes[i] = dn;
+    }
+
+    // Analytic shapes with their per-call constants folded in
+    std::vector<DPlane> planes(desc->num_planes);
+    for (uint32_t i = 0; i < desc->num_planes; ++i)
+    {
+        const RtPlane& p = desc->planes[i];
+        DPlane d;
+        d.px = p.position[0]; d.py = p.position[1]; d.pz = p.position[2];
+        d.nx = p.normal[0]; d.ny = p.normal[1]; d.nz = p.normal[2];
+        d.pos_dot_n = p.position[0] * p.normal[0] + p.position[1] * p.normal[1] + p.position[2] * p.normal[2];
+        d.bullseye = p.bullseye;
+        planes[i] = d;
+    }
+    std::vector<DSphere> spheres(desc->num_spheres);
+    for (uint32_t i = 0; i < desc->num_spheres; ++i)
+    {
+        const RtSphere& s = desc->spheres[i];
+        DSphere d = { s.position[0], s.position[1], s.position[2], s.radius };
+        spheres[i] = d;
+    }
+    std::vector<DRect> rects(desc->num_rects);
+    for (uint32_t i = 0; i < desc->num_rects; ++i)
+    {
+        const RtRect& r = desc->rects[i];
+        DRect d;
+        std::memset(&d, 0, sizeof(d));
+        d.px = r.position[0]; d.py = r.position[1]; d.pz = r.position[2];
+        // cross(side1, side2).normalized()  (RLight.h:66)
+        float n[3] = { r.side1[1] * r.side2[2] - r.side1[2] * r.side2[1],
+                       r.side1[2] * r.side2[0] - r.side1[0] * r.side2[2],
+                       r.side1[0] * r.side2[1] - r.side1[1] * r.side2[0] };
+        float nl = vlen(n);
+        if (nl > 0) { n[0] /= nl; n[1] /= nl; n[2] /= nl; }
+        d.nx = n[0]; d.ny = n[1]; d.nz = n[2];
+        float l1 = vlen(r.side1), l2 = vlen(r.side2);
+        d.len1 = l1; d.len2 = l2;
+        d.s1x = r.side1[0]; d.s1y = r.side1[1]; d.s1z = r.side1[2];
+        d.s2x = r.side2[0]; d.s2y = r.side2[1]; d.s2z = r.side2[2];
+        if (l1 > 0) { d.s1x /= l1; d.s1y /= l1; d.s1z /= l1; }
+        if (l2 > 0) { d.s2x /= l2; d.s2y /= l2; d.s2z /= l2; }
+        d.pos_dot_n = r.position[0] * n[0] + r.position[1] * n[1] + r.position[2] * n[2];
+        d.r1x = r.side1[0]; d.r1y = r.side1[1]; d.r1z = r.side1[2];
+        d.r2x = r.side2[0]; d.r2y = r.side2[1]; d.r2z = r.side2[2];
+        rects[i] = d;
+    }
+    std::vector<DXform> xforms(desc->num_xforms);
+    for (uint32_t i = 0; i < desc->num_xforms; ++i)
+    {
+        xforms[i].first_key = desc->xforms[i].first_key;
+        xforms[i].num_keys = desc->xforms[i].num_keys;
+    }
+
+    // One arena, one copy
+    ArenaBuilder ab;
+    size_t o_shapes = ab.put(shapes.data(), shapes.size() * sizeof(DShape));
+    size_t o_top = ab.put(top_nodes.data(), top_nodes.size() * sizeof(DNode));
+    size_t o_mnodes = ab.put(mesh_nodes.data(), mesh_nodes.size() * sizeof(DNode));
+    size_t o_tris = ab.put(tris.data(), tris.size() * sizeof(float4));
+    size_t o_trin = ab.put(tri_normals.data(), tri_normals.size() * sizeof(uint4));
+    size_t o_normals = ab.put(desc->normals, (size_t)desc->num_normals * 12);
+    size_t o_xforms = ab.put(xforms.data(), xforms.size() * sizeof(DXform));
+    size_t o_ktime = ab.put(desc->key_time, (size_t)desc->num_keys * 4);
+    size_t o_kscale = ab.put(desc->key_scale, (size_t)desc->num_keys * 12);
+    size_t o_krot = ab.put(desc->key_rotation, (size_t)desc->num_keys * 16);
+    size_t o_ktrans = ab.put(desc->key_translation, (size_t)desc->num_keys * 12);
+    size_t o_planes = ab.put(planes.data(), planes.size() * sizeof(DPlane));
+    size_t o_spheres = ab.put(spheres.data(), spheres.size() * sizeof(DSphere));
+    size_t o_rects = ab.put(rects.data(), rects.size() * sizeof(DRect));
+    size_t o_meshes = ab.put(meshes.data(), meshes.size() * sizeof(DMesh));
+    size_t o_cdf = ab.put(desc->face_area_cdf, (size_t)desc->num_cdf * 4);
+    size_t o_mats = ab.put(desc->materials, (size_t)desc->num_materials * sizeof(RtMaterial));
+    size_t o_lights = ab.put(desc->lights, (size_t)desc->num_lights * 4);
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    {
+        cudaGetLastError();
+        return rt_fail(RT_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+    }
+    if (device < 0 || device >= ndev)
+        return rt_fail(RT_ERR_ARG, "device ordinal out of range");
+    RT_CUDA(cudaSetDevice(device));
+
+    RtScene* sc = new RtScene();
+    sc->device = device;
+    sc->arena = NULL;
+    sc->arena_bytes = ab.bytes.size();
+    sc->stack_cap = stack_cap;
+    sc->num_tris = num_tris;
+    sc->num_faces = desc->num_faces;
+    sc->light_shapes.assign(desc->lights, desc->lights + desc->num_lights);
+    sc->scratch_in = sc->scratch_out = NULL;
+    sc->scratch_in_bytes = sc->scratch_out_bytes = 0;
+    sc->d_work = NULL;
+    sc->render = NULL;
+
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaError_t err = cudaMalloc(&sc->arena, sc->arena_bytes);
+    if (err == cudaSuccess) err = cudaMalloc((void**)&sc->d_work, 4 * sizeof(uint64_t));
+    if (err == cudaSuccess) err = cudaMemset(sc->d_work, 0, 4 * sizeof(uint64_t));
+    cudaEventRecord(e0, 0);
+    if (err == cudaSuccess) err = cudaMemcpy(sc->arena, ab.bytes.data(), sc->arena_bytes, cudaMemcpyHostToDevice);
+    cudaEventRecord(e1, 0);
+    cudaEventSynchronize(e1);
+    sc->upload_ms = 0.0f;
+    cudaEventElapsedTime(&sc->upload_ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (err != cudaSuccess)
+    {
+        if (sc->arena) cudaFree(sc->arena);
+        if (sc->d_work) cudaFree(sc->d_work);
+        delete sc;
+        return rt_cuda_fail(err, "scene upload");
+    }
+
+    const char* base = static_cast<const char*>(sc->arena);
+    DScene& d = sc->d;
+    d.set_xform = desc->set_xform;
+    d.num_finite = desc->num_finite;
+    d.num_infinite = desc->num_infinite;
+    d.num_top_nodes = desc->num_top_nodes;
+    d.num_lights = desc->num_lights;
+    d.shapes = reinterpret_cast<const DShape*>(base + o_shapes);
+    d.top_nodes = reinterpret_cast<const DNode*>(base + o_top);
+    d.mesh_nodes = reinterpret_cast<const DNode*>(base + o_mnodes);
+    d.tris = reinterpret_cast<const float4*>(base + o_tris);
+    d.tri_normals = reinterpret_cast<const uint4*>(base + o_trin);
+    d.normals = reinterpret_cast<const float*>(base + o_normals);
+    d.xforms = reinterpret_cast<const DXform*>(base + o_xforms);
+    d.key_time = reinterpret_cast<const float*>(base + o_ktime);
+    d.key_scale = reinterpret_cast<const float*>(base + o_kscale);
+    d.key_rot = reinterpret_cast<const float*>(base + o_krot);
+    d.key_trans = reinterpret_cast<const float*>(base + o_ktrans);
+    d.planes = reinterpret_cast<const DPlane*>(base + o_planes);
+    d.spheres = reinterpret_cast<const DSphere*>(base + o_spheres);
+    d.rects = reinterpret_cast<const DRect*>(base + o_rects);
+    d.meshes = reinterpret_cast<const DMesh*>(base + o_meshes);
+    d.face_area_cdf = reinterpret_cast<const float*>(base + o_cdf);
+    d.materials = reinterpret_cast<const RtMaterial*>(base + o_mats);
+    d.lights = reinterpret_cast<const uint32_t*>(base + o_lights);
+
+    *out_scene = sc;
+    return RT_OK;
+}
+
+#endif // RAYITO_B200_RT_SCENE_CUH

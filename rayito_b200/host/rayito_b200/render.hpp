@@ -1,0 +1,137 @@
+// Image, cameras and raytrace(): the top of the Rayito API surface
+// (reference: Rayito_Stage7_QT/rayito.h, RaytraceMain.cpp:205-267, 485-579).
+//
+// raytrace() keeps the reference signature.  It prepares the scene on the host
+// exactly as the reference does, flattens it (scene.hpp), uploads it through the
+// C ABI (include/rayito_b200.h) and renders on the GPU; there is no CPU renderer
+// behind it and it throws std::runtime_error when the CUDA core fails.
+#ifndef RAYITO_B200_RENDER_HPP
+#define RAYITO_B200_RENDER_HPP
+
+#include <cstddef>
+
+#include "scene.hpp"
+
+namespace Rayito
+{
+
+// rayito.h:25-44
+class Image
+{
+public:
+    Image(size_t width, size_t height) : m_width(width), m_height(height), m_pixels(new Color[width * height]) { }
+    virtual ~Image() { delete[] m_pixels; }
+
+    size_t width() const { return m_width; }
+    size_t height() const { return m_height; }
+    Color& pixel(size_t x, size_t y) { return m_pixels[y * m_width + x]; }
+    // Contiguous float RGB storage (Color is three floats)
+    float* data() { return &m_pixels[0].m_r; }
+
+protected:
+    size_t m_width, m_height;
+    Color* m_pixels;
+
+private:
+    Image(const Image&);
+    Image& operator=(const Image&);
+};
+
+// rayito.h:51-67
+class Camera
+{
+public:
+    Camera(float shutterOpen = 0.0f, float shutterClose = 0.0f)
+        : m_shutterOpen(shutterOpen), m_shutterClose(shutterClose) { }
+    virtual ~Camera() { }
+
+    // Device description of this camera; false if it has none
+    virtual bool describe(RtCamera& out) const = 0;
+
+protected:
+    float m_shutterOpen;
+    float m_shutterClose;
+};
+
+class PerspectiveCamera : public Camera
+{
+public:
+    // Look-at basis and tan(fov) computed as in RaytraceMain.cpp:205-222: the
+    // tangent takes the FULL field of view as the half angle and is evaluated in
+    // double (M_PI) before rounding to float; right/up are not re-normalised.
+    PerspectiveCamera(float fieldOfViewInDegrees,
+                      const Point& origin,
+                      const Vector& target,
+                      const Vector& targetUpDirection,
+                      float focalDistance,
+                      float lensRadius,
+                      float shutterOpen,
+                      float shutterClose)
+        : Camera(shutterOpen, shutterClose),
+          m_origin(origin),
+          m_forward((target - origin).normalized()),
+          m_tanFov(std::tan(fieldOfViewInDegrees * M_PI / 180.0f)),
+          m_focalDistance(focalDistance),
+          m_lensRadius(lensRadius)
+    {
+        m_right = cross(m_forward, targetUpDirection);
+        m_up = cross(m_right, m_forward);
+    }
+
+    virtual bool describe(RtCamera& out) const
+    {
+        out.origin[0] = m_origin.m_x; out.origin[1] = m_origin.m_y; out.origin[2] = m_origin.m_z;
+        out.forward[0] = m_forward.m_x; out.forward[1] = m_forward.m_y; out.forward[2] = m_forward.m_z;
+        out.right[0] = m_right.m_x; out.right[1] = m_right.m_y; out.right[2] = m_right.m_z;
+        out.up[0] = m_up.m_x; out.up[1] = m_up.m_y; out.up[2] = m_up.m_z;
+        out.tan_fov = m_tanFov;
+        out.focal_distance = m_focalDistance;
+        out.lens_radius = m_lensRadius;
+        out.shutter_open = m_shutterOpen;
+        out.shutter_close = m_shutterClose;
+        return true;
+    }
+
+protected:
+    Point m_origin;
+    Vector m_forward;
+    Vector m_right;
+    Vector m_up;
+    float m_tanFov;
+    float m_focalDistance;
+    float m_lensRadius;
+};
+
+// rayito.h:138-144.  Caller owns (deletes) the returned Image.
+Image* raytrace(ShapeSet& scene,
+                const Camera& cam,
+                size_t width,
+                size_t height,
+                unsigned int pixelSamplesHint,
+                unsigned int lightSamplesHint,
+                unsigned int maxRayDepth);
+
+} // namespace Rayito
+
+namespace rayito_b200
+{
+
+// Process-wide knobs of the GPU backend behind raytrace()
+struct RenderOptions
+{
+    int device;              // CUDA device ordinal
+    unsigned rank, world;    // screen-tile shard rendered by this process
+    unsigned tileSize;       // 0 = core default
+    unsigned maxBatchSamples;// 0 = core default
+    bool countWork;          // fill node/triangle counters in lastStats()
+    RenderOptions() : device(0), rank(0), world(1), tileSize(0), maxBatchSamples(0), countWork(false) { }
+};
+
+RenderOptions& renderOptions();
+// Statistics of the most recent raytrace() on this thread
+const RtRenderStats& lastStats();
+void detail_setLastStats(const RtRenderStats& stats);
+
+} // namespace rayito_b200
+
+#endif // RAYITO_B200_RENDER_HPP

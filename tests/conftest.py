@@ -1,0 +1,56 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def obj_path():
+    from rayito_b200 import build
+    build.stage_assets()
+    return build.model_path("bumpy.obj")
+
+
+@pytest.fixture(scope="session")
+def ref():
+    """The compiled reference (oracle/_ref).  Tests that need it are skipped when
+    the library was not built (it is built by __graft_entry__.build())."""
+    from oracle import refapi
+    if not refapi.available():
+        pytest.skip("oracle/_ref/libref_s7.so not built")
+    return refapi
+
+
+@pytest.fixture(scope="session")
+def capi():
+    from rayito_b200 import capi as _capi
+    _capi.host()
+    return _capi
+
+
+@pytest.fixture(scope="session")
+def scene1_host(capi, obj_path):
+    return capi.HostScene(capi.RECIPE_STAGE7_SCENE1, obj_path)
+
+
+@pytest.fixture(scope="session")
+def scene1_ref(ref, obj_path):
+    return ref.RefScene(1, obj_path)
+
+
+@pytest.fixture(scope="session")
+def scene2_host(capi):
+    return capi.HostScene(capi.RECIPE_STAGE7_SCENE2)
+
+
+@pytest.fixture(scope="session")
+def scene2_ref(ref):
+    return ref.RefScene(2)
