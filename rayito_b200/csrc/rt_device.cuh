@@ -110,6 +110,7 @@ struct DScene
     const DNode* mesh_nodes;
     const float4* tris;          // 3 per triangle
     const uint4* tri_normals;    // 1 per triangle: n0, n1, n2, unused
+    const uint32_t* face_first_tri; // per global face (+1): first triangle record
     const float* normals;        // xyz, all meshes
     const DXform* xforms;
     const float* key_time;

@@ -1,9 +1,1003 @@
-// placeholder until the wavefront renderer lands
+// Wavefront path tracer: raytrace() / RenderThread::run() / pathTrace() of the
+// reference (Rayito_Stage7_QT/RaytraceMain.cpp:64-185, 270-482, 485-579) as a
+// sequence of wide kernels over a batch of pixel samples.
+//
+//   pixel setup   per pixel: the 5*depth+3 sampler permutations by MWC jump-ahead
+//   ray gen       per sample: CMJ subpixel/lens/time -> camera ray          (:120-142)
+//   per bounce b:
+//     trace path  closest hit + shading inputs                              (:293-298)
+//     shade       emission rule, material, bounce sampling, throughput      (:303-328, 451-477)
+//     per light sample l:
+//       light     pick light, sample its surface, BRDF-sample -> 2 rays     (:358-422)
+//       trace     shadow rays (any hit) and BRDF-MIS probes (closest hit)   (:395, :423)
+//       resolve   visibility, light pdf, MIS weights, accumulate            (:396-447)
+//   accumulate    ordered per-pixel sum over samples, box filter            (:145-156)
+//
+// Paths live in fixed slots (sample index = pixel-in-batch * spp + psi, so the 32
+// lanes of a warp start as 32 samples of one pixel); stages communicate through
+// index queues filled with warp-aggregated atomics, so every kernel runs only on
+// live work (ray compaction) and dead lanes never reach the traversal loop.
+// All per-path arithmetic is order-independent of the queues: images are
+// deterministic, and per-pixel sums run in ascending sample order like the CPU.
 #ifndef RAYITO_B200_RT_RENDER_CUH
 #define RAYITO_B200_RT_RENDER_CUH
+
+#include <algorithm>
+#include <vector>
+
 #include "rt_scene.cuh"
-inline void rt_render_release(RtScene*) { }
-inline int rt_render_impl(RtScene*, const RtCamera*, const RtRenderParams*, float*, bool, RtRenderStats*, cudaStream_t) { return rt_fail(RT_ERR_UNSUPPORTED, "render not built"); }
-inline int rt_camera_rays_impl(RtScene*, const RtCamera*, const RtRenderParams*, uint32_t, RtRay*) { return rt_fail(RT_ERR_UNSUPPORTED, "render not built"); }
-inline int rt_tonemap_impl(int, const float*, size_t, float, float, uint8_t*) { return rt_fail(RT_ERR_UNSUPPORTED, "render not built"); }
-#endif
+#include "rt_shade.cuh"
+
+#define RT_DEFAULT_TILE 32u
+#define RT_DEFAULT_BATCH (8u << 20)
+#define RT_MAX_DEPTH 16u
+#define RT_BLOCK 128
+
+enum { CTL_PATH_A = 0, CTL_PATH_B = 1, CTL_LIT = 2, CTL_SHADOW = 3, CTL_MIS = 4, CTL_WORDS = 8 };
+
+// Device pointers and constants of one render call
+struct RenderCtx
+{
+    DScene sc;
+    RtCamera cam;
+    uint32_t width, height;
+    uint32_t ps, ls, depth;
+    uint32_t spp;               // ps * ps
+    uint32_t nls;               // ls * ls light samples per bounce (0 when the scene has no lights)
+    uint32_t tile, tiles_x;
+    uint32_t num_pixels;        // pixels in this batch (tiles * tile^2, some may be off-image)
+    uint32_t num_samples;       // num_pixels * spp
+    const uint32_t* tile_ids;   // tiles of this batch
+    float aspect;
+
+    uint32_t* pix_xy;           // per pixel: y << 16 | x, or 0xffffffff
+    uint32_t* perms;            // [(5*depth+3)][num_pixels]
+    float4* ray_o;              // origin xyz, time
+    float4* ray_d;              // direction xyz, -
+    float4* hit0;               // t, shape, tri record, -
+    float4* hit1;               // normal xyz, colour modifier
+    float4* thr;                // throughput rgb, (numBounces | numDirac << 8)
+    float4* res;                // radiance rgb
+    float4* pos_time;           // hit position xyz, time
+    float4* wo_mat;             // outgoing xyz, material index
+    float4* light_thr;          // throughput at the bounce being lit
+    float4* light_res;          // lightResult accumulator
+    float4* sh_dir;             // shadow direction xyz, tMax
+    float4* sh_L;               // light-sample term rgb, valid flag
+    uint8_t* occluded;
+    float4* mis_dir;            // probe direction xyz, brdf pdf (0 = none)
+    float4* mis_P;              // partial BRDF-sample term rgb, light shape id
+    float4* mis_hit0;
+    float4* mis_hit1;
+    uint32_t* q_path[2];
+    uint32_t* q_lit;
+    uint32_t* q_shadow;
+    uint32_t* q_mis;
+    uint32_t* ctl;              // CTL_WORDS queue counters
+    uint64_t* totals;           // 0 closest rays, 1 any rays, 2..5 work counters
+    float* image;               // width*height*3
+};
+
+struct RenderBuffers
+{
+    size_t cap_samples, cap_pixels, cap_tiles;
+    uint32_t cap_perm_slots;
+    void* block;                // one allocation for all per-sample state
+    size_t block_bytes;
+    RenderCtx ctx;              // pointers filled in
+    uint32_t* d_tile_ids;
+    float* d_image;             // for the host-output entry point
+    size_t image_floats;
+    cudaEvent_t ev[4];
+};
+
+// ---------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------
+
+// Append to a queue: one atomicAdd per warp
+__device__ __forceinline__ void queue_push(uint32_t* queue, uint32_t* counter, bool want, uint32_t value)
+{
+    uint32_t mask = __ballot_sync(0xffffffffu, want);
+    if (mask == 0)
+        return;
+    uint32_t lane = threadIdx.x & 31;
+    uint32_t leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if (lane == leader)
+        base = atomicAdd(counter, __popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (want)
+        queue[base + __popc(mask & ((1u << lane) - 1))] = value;
+}
+
+__device__ __forceinline__ V3 xyz(float4 v) { return mk(v.x, v.y, v.z); }
+__device__ __forceinline__ Color3 rgb(float4 v) { return mkc(v.x, v.y, v.z); }
+
+#define RT_GRID_STRIDE(j, n) \
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x, j##_end = ((n) + 31u) & ~31u; j < j##_end; j += gridDim.x * blockDim.x)
+
+// ---------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(RT_BLOCK)
+k_pixel_setup(const __grid_constant__ RenderCtx c)
+{
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p == 0)
+        for (int k = 0; k < CTL_WORDS; ++k) c.ctl[k] = 0;
+    if (p >= c.num_pixels)
+        return;
+    uint32_t per_tile = c.tile * c.tile;
+    uint32_t tile = c.tile_ids[p / per_tile];
+    uint32_t off = p % per_tile;
+    uint32_t x = (tile % c.tiles_x) * c.tile + off % c.tile;
+    uint32_t y = (tile / c.tiles_x) * c.tile + off / c.tile;
+    if (x >= c.width || y >= c.height)
+    {
+        c.pix_xy[p] = 0xffffffffu;
+        return;
+    }
+    c.pix_xy[p] = (y << 16) | x;
+    uint32_t perm[5 * RT_MAX_DEPTH + 3];
+    ChunkGrid g = chunk_grid(c.width, c.height);
+    pixel_permutations(g, x, y, c.depth, perm);
+    uint32_t slots = 5 * c.depth + 3;
+    for (uint32_t s = 0; s < slots; ++s)
+        c.perms[(size_t)s * c.num_pixels + p] = perm[s];
+}
+
+// RenderThread::run inner loop body up to makeRay (RaytraceMain.cpp:120-142) and
+// PerspectiveCamera::makeRay (:224-267)
+__device__ __forceinline__ void camera_ray(const RenderCtx& c, uint32_t p, uint32_t psi, uint32_t x, uint32_t y,
+                                           V3& origin, V3& dir, float& time)
+{
+    uint32_t D5 = 5 * c.depth;
+    uint32_t perm_time = c.perms[(size_t)(D5 + 0) * c.num_pixels + p];
+    uint32_t perm_lens = c.perms[(size_t)(D5 + 1) * c.num_pixels + p];
+    uint32_t perm_sub = c.perms[(size_t)(D5 + 2) * c.num_pixels + p];
+    float pu, pv;
+    cmj_sample2d(psi, c.ps, c.ps, perm_sub, pu, pv);
+    float xu = ((float)x + pu) / (float)c.width;
+    float yu = 1.0f - ((float)y + pv) / (float)c.height;
+    float lens_u, lens_v;
+    cmj_sample2d(psi, c.ps, c.ps, perm_lens, lens_u, lens_v);
+    float time_u = cmj_sample1d(psi, c.spp, perm_time);
+
+    float xs = (xu - 0.5f) * c.aspect + 0.5f;
+    float ys = yu;
+    const RtCamera& cam = c.cam;
+    V3 fwd = mk(cam.forward[0], cam.forward[1], cam.forward[2]);
+    V3 right = mk(cam.right[0], cam.right[1], cam.right[2]);
+    V3 up = mk(cam.up[0], cam.up[1], cam.up[2]);
+    origin = mk(cam.origin[0], cam.origin[1], cam.origin[2]);
+    dir = fwd + right * ((xs - 0.5f) * cam.tan_fov) + up * ((ys - 0.5f) * cam.tan_fov);
+    dir = normalized3(dir);
+    time = cam.shutter_open + (cam.shutter_close - cam.shutter_open) * time_u;
+    if (cam.lens_radius > 0)
+    {
+        float hshift, vshift;
+        uniform_disk(lens_u, lens_v, hshift, vshift);
+        hshift *= cam.lens_radius;
+        vshift *= cam.lens_radius;
+        V3 local_dir = normalized3(mk((xs - 0.5f) * cam.tan_fov, (ys - 0.5f) * cam.tan_fov, 1.0f));
+        float focus_t = (cam.focal_distance - 0.0f) / local_dir.z;
+        V3 focus = origin + dir * focus_t;
+        origin = origin + (right * hshift + up * vshift);
+        dir = normalized3(focus - origin);
+    }
+}
+
+__global__ void __launch_bounds__(RT_BLOCK)
+k_raygen(const __grid_constant__ RenderCtx c)
+{
+    RT_GRID_STRIDE(i, c.num_samples)
+    {
+        bool live = false;
+        if (i < c.num_samples)
+        {
+            uint32_t p = i / c.spp, psi = i % c.spp;
+            uint32_t xy = c.pix_xy[p];
+            if (xy != 0xffffffffu)
+            {
+                V3 o, d;
+                float time;
+                camera_ray(c, p, psi, xy & 0xffffu, xy >> 16, o, d, time);
+                c.ray_o[i] = make_float4(o.x, o.y, o.z, time);
+                c.ray_d[i] = make_float4(d.x, d.y, d.z, 0.0f);
+                c.thr[i] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(0u));
+                c.res[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                live = true;
+            }
+        }
+        queue_push(c.q_path[0], c.ctl + CTL_PATH_A, live, i);
+    }
+}
+
+// Camera rays only (rt_generate_camera_rays)
+__global__ void __launch_bounds__(RT_BLOCK)
+k_camera_rays(const __grid_constant__ RenderCtx c, uint32_t psi, RtRay* out)
+{
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= c.num_pixels)
+        return;
+    uint32_t xy = c.pix_xy[p];
+    if (xy == 0xffffffffu)
+        return;
+    uint32_t x = xy & 0xffffu, y = xy >> 16;
+    V3 o, d;
+    float time;
+    camera_ray(c, p, psi, x, y, o, d, time);
+    RtRay r;
+    r.origin[0] = o.x; r.origin[1] = o.y; r.origin[2] = o.z;
+    r.direction[0] = d.x; r.direction[1] = d.y; r.direction[2] = d.z;
+    r.tmax = RT_RAY_TMAX;
+    r.time = time;
+    out[(size_t)y * c.width + x] = r;
+}
+
+template <int CAP, bool COUNT>
+__global__ void __launch_bounds__(RT_BLOCK)
+k_trace_paths(const __grid_constant__ RenderCtx c, int cur)
+{
+    const uint32_t n = c.ctl[cur];
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+    {
+        atomicAdd(reinterpret_cast<unsigned long long*>(c.totals + 0), (unsigned long long)n);
+        c.ctl[cur ^ 1] = 0;          // queues the next kernel (shade) will fill
+        c.ctl[CTL_LIT] = 0;
+    }
+    WorkCount wc = { 0, 0, 0, 0 };
+    RT_GRID_STRIDE(j, n)
+    {
+        if (j < n)
+        {
+            uint32_t i = c.q_path[cur][j];
+            float4 ro = c.ray_o[i], rd = c.ray_d[i];
+            LocalRay r0;
+            ClosestHit h = trace_closest<CAP, COUNT>(c.sc, xyz(ro), xyz(rd), RT_RAY_TMAX, ro.w, r0, wc);
+            V3 nrm;
+            float cm;
+            hit_shading_inputs(c.sc, r0, ro.w, h, nrm, cm);
+            c.hit0[i] = make_float4(h.t, __int_as_float(h.shape), __int_as_float(h.tri_rec), 0.0f);
+            c.hit1[i] = make_float4(nrm.x, nrm.y, nrm.z, cm);
+        }
+    }
+    if (COUNT)
+    {
+        uint32_t v[4] = { wc.node_pops, wc.tri_tests, wc.shape_tests, wc.xform_evals };
+        for (int k = 0; k < 4; ++k)
+        {
+            uint32_t x = v[k];
+            for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
+            if ((threadIdx.x & 31) == 0 && x)
+                atomicAdd(reinterpret_cast<unsigned long long*>(c.totals + 2 + k), (unsigned long long)x);
+        }
+    }
+}
+
+// pathTrace, one bounce, everything that does not need further rays
+__global__ void __launch_bounds__(RT_BLOCK)
+k_shade(const __grid_constant__ RenderCtx c, int cur, uint32_t bounce)
+{
+    const uint32_t n = c.ctl[cur];
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+    {
+        c.ctl[CTL_SHADOW] = 0;
+        c.ctl[CTL_MIS] = 0;
+    }
+    RT_GRID_STRIDE(j, n)
+    {
+        bool lit = false, alive = false;
+        uint32_t i = 0;
+        if (j < n)
+        {
+            i = c.q_path[cur][j];
+            float4 h0 = c.hit0[i];
+            int shape = __float_as_int(h0.y);
+            if (shape >= 0)
+            {
+                float4 ro = c.ray_o[i], rd = c.ray_d[i], h1 = c.hit1[i], th = c.thr[i], rs = c.res[i];
+                uint32_t state = __float_as_uint(th.w);
+                uint32_t nb = state & 0xffu, nd = (state >> 8) & 0xffu;
+                Color3 thr = rgb(th), result = rgb(rs);
+                DShape sh = load_shape(c.sc, (uint32_t)shape);
+                RtMaterial mat = c.sc.materials[sh.material];
+
+                // Emission only when seen directly or through mirrors (:303-306)
+                if (nb == 0 || nb == nd)
+                    result = result + thr * mkc(mat.emittance[0], mat.emittance[1], mat.emittance[2]);
+
+                if (mat.brdf != RT_BRDF_NONE)      // an Emitter ends the path (:320-323)
+                {
+                    V3 o = xyz(ro), d = xyz(rd);
+                    V3 position = o + h0.x * d;
+                    V3 normal = xyz(h1);
+                    V3 outgoing = -d;
+                    float cm = h1.w;
+                    bool dirac = mat.brdf == RT_BRDF_MIRROR;
+                    if (dirac)
+                        nd++;
+                    if (!dirac && c.nls > 0)
+                    {
+                        lit = true;
+                        c.light_thr[i] = make_float4(thr.r, thr.g, thr.b, 0.0f);
+                        c.light_res[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                        c.pos_time[i] = make_float4(position.x, position.y, position.z, ro.w);
+                        c.wo_mat[i] = make_float4(outgoing.x, outgoing.y, outgoing.z, __uint_as_float(sh.material));
+                    }
+
+                    // Next leg of the path (:451-477)
+                    uint32_t p = i / c.spp, psi = i % c.spp;
+                    uint32_t perm = c.perms[(size_t)(5 * bounce + 0) * c.num_pixels + p];
+                    float u, v;
+                    cmj_sample2d(psi, c.ps, c.ps, perm, u, v);
+                    V3 incoming;
+                    float pdf = 0.0f;
+                    float value = brdf_sample(mat.brdf, mat.exponent, incoming, outgoing, normal, u, v, pdf);
+                    if (pdf > 0.0f)
+                    {
+                        Color3 mc = mkc(mat.color[0], mat.color[1], mat.color[2]);
+                        Color3 f = mkc(cm, cm, cm) * mc * value * (fabsf(dot3(-incoming, normal)) / (pdf * 1.0f));
+                        thr = thr * f;
+                        nb++;
+                        V3 nd3 = -incoming;
+                        c.ray_o[i] = make_float4(position.x, position.y, position.z, ro.w);
+                        c.ray_d[i] = make_float4(nd3.x, nd3.y, nd3.z, 0.0f);
+                        alive = nb < c.depth;
+                    }
+                }
+                c.thr[i] = make_float4(thr.r, thr.g, thr.b, __uint_as_float(nb | (nd << 8)));
+                c.res[i] = make_float4(result.r, result.g, result.b, 0.0f);
+            }
+        }
+        queue_push(c.q_lit, c.ctl + CTL_LIT, lit, i);
+        queue_push(c.q_path[cur ^ 1], c.ctl + (cur ^ 1), alive, i);
+    }
+}
+
+// One light sample of the direct-lighting loop (:336-422): produces at most one
+// shadow ray and one BRDF-MIS probe per lit path
+__global__ void __launch_bounds__(RT_BLOCK)
+k_light_sample(const __grid_constant__ RenderCtx c, uint32_t bounce, uint32_t lsi)
+{
+    const uint32_t n = c.ctl[CTL_LIT];
+    RT_GRID_STRIDE(j, n)
+    {
+        bool want_shadow = false, want_mis = false;
+        uint32_t i = 0;
+        if (j < n)
+        {
+            i = c.q_lit[j];
+            uint32_t p = i / c.spp, psi = i % c.spp;
+            float4 pt = c.pos_time[i], wm = c.wo_mat[i], h1 = c.hit1[i];
+            V3 position = xyz(pt), outgoing = xyz(wm), normal = xyz(h1);
+            float time = pt.w, cm = h1.w;
+            RtMaterial mat = c.sc.materials[__float_as_uint(wm.w)];
+            Color3 mc = mkc(mat.color[0], mat.color[1], mat.color[2]);
+
+            uint32_t idx = psi * c.nls + lsi;
+            uint32_t n1 = c.ps * c.ls * c.ps * c.ls, n2 = c.ps * c.ls;
+            const uint32_t* pp = c.perms + (size_t)(5 * bounce) * c.num_pixels + p;
+            uint32_t perm_sel = pp[(size_t)1 * c.num_pixels];
+            uint32_t perm_elem = pp[(size_t)2 * c.num_pixels];
+            uint32_t perm_light = pp[(size_t)3 * c.num_pixels];
+            uint32_t perm_brdf = pp[(size_t)4 * c.num_pixels];
+
+            // Random light (:358-364)
+            float liu = cmj_sample1d(idx, n1, perm_sel);
+            uint32_t light_index = (uint32_t)(liu * (float)c.sc.num_lights);
+            if (light_index >= c.sc.num_lights)
+                light_index = c.sc.num_lights - 1;
+            uint32_t light_shape = c.sc.lights[light_index];
+            DShape lsh = load_shape(c.sc, light_shape);
+            RtMaterial lmat = c.sc.materials[lsh.material];
+            Color3 emitted = mkc(lmat.emittance[0], lmat.emittance[1], lmat.emittance[2]);
+
+            float lsu, lsv;
+            cmj_sample2d(idx, n2, n2, perm_light, lsu, lsv);
+            float leu = cmj_sample1d(idx, n1, perm_elem);
+            V3 lpos, lnrm;
+            float lpdf;
+            light_sample(c.sc, lsh, position, time, lsu, lsv, leu, lpos, lnrm, lpdf);
+
+            float4 shl = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (lpdf > 0.0f)
+            {
+                V3 li = position - lpos;
+                float dist;
+                li = normalized3(li, &dist);
+                float bpdf = 0.0f;
+                float bres = brdf_evaluate(mat.brdf, mat.exponent, li, outgoing, normal, bpdf);
+                if (bres > 0.0f && bpdf > 0.0f)
+                {
+                    V3 sd = -li;
+                    float mis = power_heuristic(lpdf, bpdf);
+                    Color3 L = emitted * mkc(cm, cm, cm) * mc * bres * fabsf(dot3(sd, normal)) * mis / (lpdf * 1.0f);
+                    c.sh_dir[i] = make_float4(sd.x, sd.y, sd.z, dist - RT_RAY_TMIN);
+                    shl = make_float4(L.r, L.g, L.b, 1.0f);
+                    want_shadow = true;
+                }
+            }
+            c.sh_L[i] = shl;
+
+            // BRDF sample towards (hopefully) the same light (:410-422)
+            float bsu, bsv;
+            cmj_sample2d(idx, n2, n2, perm_brdf, bsu, bsv);
+            V3 bi;
+            float bpdf = 0.0f;
+            float bres = brdf_sample(mat.brdf, mat.exponent, bi, outgoing, normal, bsu, bsv, bpdf);
+            float4 md = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (bpdf > 0.0f && bres > 0.0f)
+            {
+                V3 pd = -bi;
+                Color3 P = emitted * mkc(cm, cm, cm) * mc * bres * fabsf(dot3(pd, normal));
+                md = make_float4(pd.x, pd.y, pd.z, bpdf);
+                c.mis_P[i] = make_float4(P.r, P.g, P.b, __uint_as_float(light_shape));
+                want_mis = true;
+            }
+            c.mis_dir[i] = md;
+        }
+        queue_push(c.q_shadow, c.ctl + CTL_SHADOW, want_shadow, i);
+        queue_push(c.q_mis, c.ctl + CTL_MIS, want_mis, i);
+    }
+}
+
+template <int CAP, bool COUNT>
+__global__ void __launch_bounds__(RT_BLOCK)
+k_trace_shadow(const __grid_constant__ RenderCtx c)
+{
+    const uint32_t n = c.ctl[CTL_SHADOW];
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        atomicAdd(reinterpret_cast<unsigned long long*>(c.totals + 1), (unsigned long long)n);
+    WorkCount wc = { 0, 0, 0, 0 };
+    RT_GRID_STRIDE(j, n)
+    {
+        if (j < n)
+        {
+            uint32_t i = c.q_shadow[j];
+            float4 pt = c.pos_time[i], sd = c.sh_dir[i];
+            c.occluded[i] = trace_any<CAP, COUNT>(c.sc, xyz(pt), xyz(sd), sd.w, pt.w, wc) ? 1 : 0;
+        }
+    }
+    if (COUNT)
+    {
+        uint32_t v[4] = { wc.node_pops, wc.tri_tests, wc.shape_tests, wc.xform_evals };
+        for (int k = 0; k < 4; ++k)
+        {
+            uint32_t x = v[k];
+            for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
+            if ((threadIdx.x & 31) == 0 && x)
+                atomicAdd(reinterpret_cast<unsigned long long*>(c.totals + 2 + k), (unsigned long long)x);
+        }
+    }
+}
+
+template <int CAP, bool COUNT>
+__global__ void __launch_bounds__(RT_BLOCK)
+k_trace_mis(const __grid_constant__ RenderCtx c)
+{
+    const uint32_t n = c.ctl[CTL_MIS];
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        atomicAdd(reinterpret_cast<unsigned long long*>(c.totals + 0), (unsigned long long)n);
+    WorkCount wc = { 0, 0, 0, 0 };
+    RT_GRID_STRIDE(j, n)
+    {
+        if (j < n)
+        {
+            uint32_t i = c.q_mis[j];
+            float4 pt = c.pos_time[i], md = c.mis_dir[i];
+            LocalRay r0;
+            ClosestHit h = trace_closest<CAP, COUNT>(c.sc, xyz(pt), xyz(md), RT_RAY_TMAX, pt.w, r0, wc);
+            V3 nrm;
+            float cm;
+            hit_shading_inputs(c.sc, r0, pt.w, h, nrm, cm);
+            c.mis_hit0[i] = make_float4(h.t, __int_as_float(h.shape), 0.0f, 0.0f);
+            c.mis_hit1[i] = make_float4(nrm.x, nrm.y, nrm.z, cm);
+        }
+    }
+    if (COUNT)
+    {
+        uint32_t v[4] = { wc.node_pops, wc.tri_tests, wc.shape_tests, wc.xform_evals };
+        for (int k = 0; k < 4; ++k)
+        {
+            uint32_t x = v[k];
+            for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
+            if ((threadIdx.x & 31) == 0 && x)
+                atomicAdd(reinterpret_cast<unsigned long long*>(c.totals + 2 + k), (unsigned long long)x);
+        }
+    }
+}
+
+// Combine the two MIS samples of light sample `lsi` (:396-439) and, after the last
+// one, fold the bounce's direct lighting into the path (:443-447)
+__global__ void __launch_bounds__(RT_BLOCK)
+k_resolve(const __grid_constant__ RenderCtx c, uint32_t lsi)
+{
+    const uint32_t n = c.ctl[CTL_LIT];
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+    {
+        c.ctl[CTL_SHADOW] = 0;      // refilled by the next light sample, if any
+        c.ctl[CTL_MIS] = 0;
+    }
+    RT_GRID_STRIDE(j, n)
+    {
+        if (j >= n)
+            continue;
+        uint32_t i = c.q_lit[j];
+        Color3 lr = rgb(c.light_res[i]);
+        float4 shl = c.sh_L[i];
+        if (shl.w != 0.0f && !c.occluded[i])
+            lr = lr + rgb(shl);
+        float4 md = c.mis_dir[i];
+        if (md.w > 0.0f)
+        {
+            float4 mp = c.mis_P[i], mh0 = c.mis_hit0[i];
+            uint32_t light_shape = __float_as_uint(mp.w);
+            if (__float_as_int(mh0.y) == (int)light_shape)
+            {
+                float4 pt = c.pos_time[i], mh1 = c.mis_hit1[i];
+                DShape lsh = load_shape(c.sc, light_shape);
+                float lpdf = light_intersect_pdf(c.sc, lsh, xyz(pt), xyz(md), pt.w, mh0.x, xyz(mh1));
+                if (lpdf > 0.0f)
+                {
+                    float mis = power_heuristic(md.w, lpdf);
+                    lr = lr + rgb(mp) * mis / (md.w * 1.0f);
+                }
+            }
+        }
+        if (lsi + 1 == c.nls)
+        {
+            float weight = (float)c.sc.num_lights / (float)c.nls;
+            lr = lr * weight;
+            float4 rs = c.res[i];
+            Color3 result = rgb(rs) + rgb(c.light_thr[i]) * lr;
+            c.res[i] = make_float4(result.r, result.g, result.b, 0.0f);
+        }
+        else
+        {
+            c.light_res[i] = make_float4(lr.r, lr.g, lr.b, 0.0f);
+        }
+    }
+}
+
+// Box filter: samples summed in ascending order, then divided (:145-156)
+__global__ void __launch_bounds__(RT_BLOCK)
+k_accumulate(const __grid_constant__ RenderCtx c)
+{
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= c.num_pixels)
+        return;
+    uint32_t xy = c.pix_xy[p];
+    if (xy == 0xffffffffu)
+        return;
+    Color3 sum = mkc(0.0f, 0.0f, 0.0f);
+    const float4* r = c.res + (size_t)p * c.spp;
+    for (uint32_t s = 0; s < c.spp; ++s)
+        sum = sum + rgb(r[s]);
+    sum = sum / (float)c.spp;
+    uint32_t x = xy & 0xffffu, y = xy >> 16;
+    float* out = c.image + ((size_t)y * c.width + x) * 3;
+    out[0] = sum.r;
+    out[1] = sum.g;
+    out[2] = sum.b;
+}
+
+// displayImage (MainWindow.cpp:37-91): negative -> green, pow(c * 2^exposure, 1/gamma),
+// NaN -> blue, clamp, truncate.  Output bytes B, G, R, A.
+__global__ void k_tonemap(const float* __restrict__ rgb_in, size_t n, float exposure, float gamma_exp, uint8_t* __restrict__ out)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    float r = rgb_in[3 * i], g = rgb_in[3 * i + 1], b = rgb_in[3 * i + 2];
+    if (r < 0.0f || g < 0.0f || b < 0.0f)
+    {
+        r = 0.0f; g = 1.0f; b = 0.0f;
+    }
+    else
+    {
+        r = ref_powf(r * exposure, gamma_exp);
+        g = ref_powf(g * exposure, gamma_exp);
+        b = ref_powf(b * exposure, gamma_exp);
+        if (r != r || g != g || b != b)
+        {
+            r = 0.0f; g = 0.0f; b = 1.0f;
+        }
+    }
+    r = std_max(0.0f, std_min(1.0f, r));
+    g = std_max(0.0f, std_min(1.0f, g));
+    b = std_max(0.0f, std_min(1.0f, b));
+    out[4 * i + 3] = 0xff;
+    out[4 * i + 2] = (uint8_t)(r * 255.0f);
+    out[4 * i + 1] = (uint8_t)(g * 255.0f);
+    out[4 * i + 0] = (uint8_t)(b * 255.0f);
+}
+
+// ---------------------------------------------------------------------------
+// host orchestration
+// ---------------------------------------------------------------------------
+
+inline void rt_render_release(RtScene* s)
+{
+    RenderBuffers* rb = s->render;
+    if (rb == NULL)
+        return;
+    if (rb->block) cudaFree(rb->block);
+    if (rb->d_tile_ids) cudaFree(rb->d_tile_ids);
+    if (rb->d_image) cudaFree(rb->d_image);
+    for (int i = 0; i < 4; ++i) cudaEventDestroy(rb->ev[i]);
+    delete rb;
+    s->render = NULL;
+}
+
+namespace rt_detail
+{
+
+struct Carver
+{
+    char* base;
+    size_t off;
+    template <typename T> T* take(size_t count)
+    {
+        off = (off + 255) & ~(size_t)255;
+        T* p = base ? reinterpret_cast<T*>(base + off) : NULL;
+        off += count * sizeof(T);
+        return p;
+    }
+};
+
+inline size_t carve(RenderCtx& c, char* base, size_t samples, size_t pixels, uint32_t slots)
+{
+    Carver k = { base, 0 };
+    c.pix_xy = k.take<uint32_t>(pixels);
+    c.perms = k.take<uint32_t>(pixels * slots);
+    c.ray_o = k.take<float4>(samples);
+    c.ray_d = k.take<float4>(samples);
+    c.hit0 = k.take<float4>(samples);
+    c.hit1 = k.take<float4>(samples);
+    c.thr = k.take<float4>(samples);
+    c.res = k.take<float4>(samples);
+    c.pos_time = k.take<float4>(samples);
+    c.wo_mat = k.take<float4>(samples);
+    c.light_thr = k.take<float4>(samples);
+    c.light_res = k.take<float4>(samples);
+    c.sh_dir = k.take<float4>(samples);
+    c.sh_L = k.take<float4>(samples);
+    c.occluded = k.take<uint8_t>(samples);
+    c.mis_dir = k.take<float4>(samples);
+    c.mis_P = k.take<float4>(samples);
+    c.mis_hit0 = k.take<float4>(samples);
+    c.mis_hit1 = k.take<float4>(samples);
+    c.q_path[0] = k.take<uint32_t>(samples);
+    c.q_path[1] = k.take<uint32_t>(samples);
+    c.q_lit = k.take<uint32_t>(samples);
+    c.q_shadow = k.take<uint32_t>(samples);
+    c.q_mis = k.take<uint32_t>(samples);
+    c.ctl = k.take<uint32_t>(CTL_WORDS);
+    c.totals = k.take<uint64_t>(8);
+    return k.off + 256;
+}
+
+// Tiles of `rank`: diagonal interleave so every rank gets tiles from all image
+// regions (sky rows are ~1 ray/sample, mesh pixels 6+)
+inline void rank_tiles(uint32_t tiles_x, uint32_t tiles_y, uint32_t rank, uint32_t world, std::vector<uint32_t>& out)
+{
+    out.clear();
+    for (uint32_t ty = 0; ty < tiles_y; ++ty)
+        for (uint32_t tx = 0; tx < tiles_x; ++tx)
+            if ((tx + ty) % world == rank)
+                out.push_back(ty * tiles_x + tx);
+}
+
+} // namespace rt_detail
+
+struct RenderPlan
+{
+    uint32_t tile, tiles_x, tiles_y;
+    uint32_t spp, slots;
+    uint32_t tiles_per_batch;
+    std::vector<uint32_t> tiles;
+};
+
+inline int rt_plan(const RtScene* s, const RtRenderParams* prm, RenderPlan& plan)
+{
+    if (prm->width == 0 || prm->height == 0 || prm->width > 65535 || prm->height > 65535)
+        return rt_fail(RT_ERR_ARG, "image size must be 1..65535");
+    if (prm->pixel_samples_hint == 0 || prm->pixel_samples_hint > 1024)
+        return rt_fail(RT_ERR_ARG, "pixel_samples_hint must be 1..1024");
+    if (prm->max_ray_depth > RT_MAX_DEPTH)
+        return rt_fail(RT_ERR_ARG, "max_ray_depth above the supported 16");
+    if (prm->world == 0 || prm->rank >= prm->world)
+        return rt_fail(RT_ERR_ARG, "rank/world invalid");
+    uint64_t n1 = (uint64_t)prm->pixel_samples_hint * prm->light_samples_hint;
+    if (n1 * n1 > 0xffffffffull)
+        return rt_fail(RT_ERR_ARG, "(pixel_samples*light_samples)^2 does not fit the sampler's 32-bit index");
+    (void)s;
+    plan.tile = prm->tile_size ? prm->tile_size : RT_DEFAULT_TILE;
+    plan.tiles_x = (prm->width + plan.tile - 1) / plan.tile;
+    plan.tiles_y = (prm->height + plan.tile - 1) / plan.tile;
+    plan.spp = prm->pixel_samples_hint * prm->pixel_samples_hint;
+    plan.slots = 5 * prm->max_ray_depth + 3;
+    uint64_t batch = prm->max_batch_samples ? prm->max_batch_samples : RT_DEFAULT_BATCH;
+    uint64_t per_tile = (uint64_t)plan.tile * plan.tile * plan.spp;
+    if (per_tile >= (1ull << 31))
+        return rt_fail(RT_ERR_ARG, "tile_size^2 * spp too large; use a smaller tile");
+    plan.tiles_per_batch = (uint32_t)std::max<uint64_t>(1, batch / per_tile);
+    rt_detail::rank_tiles(plan.tiles_x, plan.tiles_y, prm->rank, prm->world, plan.tiles);
+    if (plan.tiles_per_batch > plan.tiles.size())
+        plan.tiles_per_batch = (uint32_t)std::max<size_t>(1, plan.tiles.size());
+    return RT_OK;
+}
+
+inline int rt_render_reserve(RtScene* s, const RenderPlan& plan)
+{
+    size_t pixels = (size_t)plan.tiles_per_batch * plan.tile * plan.tile;
+    size_t samples = pixels * plan.spp;
+    RenderBuffers* rb = s->render;
+    if (rb == NULL)
+    {
+        rb = new RenderBuffers();
+        std::memset(rb, 0, sizeof(*rb));
+        for (int i = 0; i < 4; ++i) cudaEventCreate(&rb->ev[i]);
+        s->render = rb;
+    }
+    if (samples > rb->cap_samples || pixels > rb->cap_pixels || plan.slots > rb->cap_perm_slots)
+    {
+        if (rb->block) cudaFree(rb->block);
+        rb->block = NULL;
+        rb->cap_samples = rb->cap_pixels = 0;
+        RenderCtx probe;
+        size_t bytes = rt_detail::carve(probe, NULL, samples, pixels, plan.slots);
+        RT_CUDA(cudaMalloc(&rb->block, bytes));
+        rb->block_bytes = bytes;
+        rb->cap_samples = samples;
+        rb->cap_pixels = pixels;
+        rb->cap_perm_slots = plan.slots;
+    }
+    rt_detail::carve(rb->ctx, static_cast<char*>(rb->block), rb->cap_samples, rb->cap_pixels, rb->cap_perm_slots);
+    if (plan.tiles.size() > rb->cap_tiles)
+    {
+        if (rb->d_tile_ids) cudaFree(rb->d_tile_ids);
+        rb->d_tile_ids = NULL;
+        rb->cap_tiles = 0;
+        RT_CUDA(cudaMalloc((void**)&rb->d_tile_ids, plan.tiles.size() * sizeof(uint32_t)));
+        rb->cap_tiles = plan.tiles.size();
+    }
+    return RT_OK;
+}
+
+template <bool COUNT>
+static int rt_launch_batch(RtScene* s, const RenderCtx& c, cudaStream_t st, uint64_t& launches)
+{
+    const int cap = s->stack_cap;
+    int dev_sms = 148;
+    cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, s->device);
+    const unsigned wide = (unsigned)std::min<uint64_t>(((uint64_t)c.num_samples + RT_BLOCK - 1) / RT_BLOCK, (uint64_t)dev_sms * 32);
+    const unsigned pix_blocks = (c.num_pixels + RT_BLOCK - 1) / RT_BLOCK;
+
+    k_pixel_setup<<<pix_blocks, RT_BLOCK, 0, st>>>(c);
+    k_raygen<<<wide, RT_BLOCK, 0, st>>>(c);
+    launches += 2;
+    int cur = 0;
+    for (uint32_t b = 0; b < c.depth; ++b)
+    {
+        if (cap <= 32)      k_trace_paths<32, COUNT><<<wide, RT_BLOCK, 0, st>>>(c, cur);
+        else if (cap <= 64) k_trace_paths<64, COUNT><<<wide, RT_BLOCK, 0, st>>>(c, cur);
+        else                k_trace_paths<104, COUNT><<<wide, RT_BLOCK, 0, st>>>(c, cur);
+        k_shade<<<wide, RT_BLOCK, 0, st>>>(c, cur, b);
+        launches += 2;
+        for (uint32_t l = 0; l < c.nls; ++l)
+        {
+            k_light_sample<<<wide, RT_BLOCK, 0, st>>>(c, b, l);
+            if (cap <= 32)      { k_trace_shadow<32, COUNT><<<wide, RT_BLOCK, 0, st>>>(c);  k_trace_mis<32, COUNT><<<wide, RT_BLOCK, 0, st>>>(c); }
+            else if (cap <= 64) { k_trace_shadow<64, COUNT><<<wide, RT_BLOCK, 0, st>>>(c);  k_trace_mis<64, COUNT><<<wide, RT_BLOCK, 0, st>>>(c); }
+            else                { k_trace_shadow<104, COUNT><<<wide, RT_BLOCK, 0, st>>>(c); k_trace_mis<104, COUNT><<<wide, RT_BLOCK, 0, st>>>(c); }
+            k_resolve<<<wide, RT_BLOCK, 0, st>>>(c, l);
+            launches += 4;
+        }
+        cur ^= 1;
+    }
+    k_accumulate<<<pix_blocks, RT_BLOCK, 0, st>>>(c);
+    launches += 1;
+    RT_CUDA(cudaGetLastError());
+    return RT_OK;
+}
+
+inline int rt_fill_ctx(RtScene* s, const RtCamera* camera, const RtRenderParams* prm, const RenderPlan& plan, RenderCtx& c)
+{
+    c = s->render->ctx;
+    c.sc = s->d;
+    c.cam = *camera;
+    c.width = prm->width;
+    c.height = prm->height;
+    c.ps = prm->pixel_samples_hint;
+    c.ls = prm->light_samples_hint;
+    c.depth = prm->max_ray_depth;
+    c.spp = plan.spp;
+    // samplers.m_numLightSamples = lights.empty() ? 0 : ls*ls  (RaytraceMain.cpp:77)
+    c.nls = s->d.num_lights == 0 ? 0 : prm->light_samples_hint * prm->light_samples_hint;
+    c.tile = plan.tile;
+    c.tiles_x = plan.tiles_x;
+    c.aspect = (float)prm->width / (float)prm->height;
+    return RT_OK;
+}
+
+inline int rt_render_impl(RtScene* s, const RtCamera* camera, const RtRenderParams* prm, float* rgb_out, bool out_on_device,
+                          RtRenderStats* stats, cudaStream_t st)
+{
+    if (s == NULL || camera == NULL || prm == NULL || rgb_out == NULL)
+        return rt_fail(RT_ERR_ARG, "null argument");
+    RT_CUDA(cudaSetDevice(s->device));
+    RenderPlan plan;
+    int rc = rt_plan(s, prm, plan);
+    if (rc != RT_OK) return rc;
+    rc = rt_render_reserve(s, plan);
+    if (rc != RT_OK) return rc;
+    RenderBuffers* rb = s->render;
+
+    const size_t image_floats = (size_t)prm->width * prm->height * 3;
+    float* d_image = rgb_out;
+    if (!out_on_device)
+    {
+        if (rb->image_floats < image_floats)
+        {
+            if (rb->d_image) cudaFree(rb->d_image);
+            rb->d_image = NULL;
+            rb->image_floats = 0;
+            RT_CUDA(cudaMalloc((void**)&rb->d_image, image_floats * sizeof(float)));
+            rb->image_floats = image_floats;
+        }
+        d_image = rb->d_image;
+        RT_CUDA(cudaMemsetAsync(d_image, 0, image_floats * sizeof(float), st));
+    }
+
+    RenderCtx c;
+    rt_fill_ctx(s, camera, prm, plan, c);
+    c.image = d_image;
+    c.tile_ids = rb->d_tile_ids;
+
+    RT_CUDA(cudaEventRecord(rb->ev[0], st));
+    if (!plan.tiles.empty())
+        RT_CUDA(cudaMemcpyAsync(rb->d_tile_ids, plan.tiles.data(), plan.tiles.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    RT_CUDA(cudaMemsetAsync(c.totals, 0, 8 * sizeof(uint64_t), st));
+    RT_CUDA(cudaEventRecord(rb->ev[1], st));
+
+    const bool count = (prm->flags & RT_RENDER_COUNT_WORK) != 0;
+    uint64_t launches = 0;
+    uint64_t samples = 0;
+    for (size_t t0 = 0; t0 < plan.tiles.size(); t0 += plan.tiles_per_batch)
+    {
+        size_t nt = std::min<size_t>(plan.tiles_per_batch, plan.tiles.size() - t0);
+        c.tile_ids = rb->d_tile_ids + t0;
+        c.num_pixels = (uint32_t)(nt * plan.tile * plan.tile);
+        c.num_samples = c.num_pixels * plan.spp;
+        rc = count ? rt_launch_batch<true>(s, c, st, launches) : rt_launch_batch<false>(s, c, st, launches);
+        if (rc != RT_OK) return rc;
+    }
+    RT_CUDA(cudaEventRecord(rb->ev[2], st));
+
+    uint64_t totals[8] = { 0 };
+    RT_CUDA(cudaMemcpyAsync(totals, c.totals, sizeof(totals), cudaMemcpyDeviceToHost, st));
+    if (!out_on_device)
+    {
+        if (prm->world == 1)
+        {
+            RT_CUDA(cudaMemcpyAsync(rgb_out, d_image, image_floats * sizeof(float), cudaMemcpyDeviceToHost, st));
+        }
+        else
+        {
+            // Only this rank's tiles are written back; other pixels stay untouched
+            for (size_t k = 0; k < plan.tiles.size(); ++k)
+            {
+                uint32_t tx = plan.tiles[k] % plan.tiles_x, ty = plan.tiles[k] / plan.tiles_x;
+                uint32_t x0 = tx * plan.tile, y0 = ty * plan.tile;
+                uint32_t w = std::min(plan.tile, prm->width - x0), h = std::min(plan.tile, prm->height - y0);
+                size_t off = ((size_t)y0 * prm->width + x0) * 3;
+                RT_CUDA(cudaMemcpy2DAsync(rgb_out + off, (size_t)prm->width * 12, d_image + off, (size_t)prm->width * 12,
+                                          (size_t)w * 12, h, cudaMemcpyDeviceToHost, st));
+            }
+        }
+    }
+    RT_CUDA(cudaEventRecord(rb->ev[3], st));
+    RT_CUDA(cudaStreamSynchronize(st));
+
+    for (size_t k = 0; k < plan.tiles.size(); ++k)
+    {
+        uint32_t tx = plan.tiles[k] % plan.tiles_x, ty = plan.tiles[k] / plan.tiles_x;
+        uint32_t x0 = tx * plan.tile, y0 = ty * plan.tile;
+        uint32_t w = std::min(plan.tile, prm->width - x0), h = std::min(plan.tile, prm->height - y0);
+        samples += (uint64_t)w * h * plan.spp;
+    }
+    if (stats != NULL)
+    {
+        std::memset(stats, 0, sizeof(*stats));
+        stats->samples = samples;
+        stats->closest_rays = totals[0];
+        stats->any_rays = totals[1];
+        stats->node_pops = totals[2];
+        stats->tri_tests = totals[3];
+        stats->shape_tests = totals[4];
+        stats->xform_evals = totals[5];
+        stats->kernel_launches = launches;
+        cudaEventElapsedTime(&stats->upload_ms, rb->ev[0], rb->ev[1]);
+        cudaEventElapsedTime(&stats->render_ms, rb->ev[1], rb->ev[2]);
+        cudaEventElapsedTime(&stats->download_ms, rb->ev[2], rb->ev[3]);
+        stats->trace_ms = 0.0f;
+    }
+    return RT_OK;
+}
+
+inline int rt_camera_rays_impl(RtScene* s, const RtCamera* camera, const RtRenderParams* prm, uint32_t psi, RtRay* rays)
+{
+    if (s == NULL || camera == NULL || prm == NULL || rays == NULL)
+        return rt_fail(RT_ERR_ARG, "null argument");
+    RT_CUDA(cudaSetDevice(s->device));
+    RenderPlan plan;
+    int rc = rt_plan(s, prm, plan);
+    if (rc != RT_OK) return rc;
+    if (psi >= plan.spp)
+        return rt_fail(RT_ERR_ARG, "psi out of range");
+    rc = rt_render_reserve(s, plan);
+    if (rc != RT_OK) return rc;
+    RenderBuffers* rb = s->render;
+    size_t n = (size_t)prm->width * prm->height;
+    rc = RT_OK;
+    RtRay* d_rays = NULL;
+    RT_CUDA(cudaMalloc((void**)&d_rays, n * sizeof(RtRay)));
+    cudaMemset(d_rays, 0, n * sizeof(RtRay));
+    RenderCtx c;
+    rt_fill_ctx(s, camera, prm, plan, c);
+    c.image = NULL;
+    if (!plan.tiles.empty())
+        cudaMemcpy(rb->d_tile_ids, plan.tiles.data(), plan.tiles.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
+    for (size_t t0 = 0; t0 < plan.tiles.size(); t0 += plan.tiles_per_batch)
+    {
+        size_t nt = std::min<size_t>(plan.tiles_per_batch, plan.tiles.size() - t0);
+        c.tile_ids = rb->d_tile_ids + t0;
+        c.num_pixels = (uint32_t)(nt * plan.tile * plan.tile);
+        c.num_samples = c.num_pixels * plan.spp;
+        unsigned blocks = (c.num_pixels + RT_BLOCK - 1) / RT_BLOCK;
+        k_pixel_setup<<<blocks, RT_BLOCK>>>(c);
+        k_camera_rays<<<blocks, RT_BLOCK>>>(c, psi, d_rays);
+    }
+    cudaError_t e = cudaMemcpy(rays, d_rays, n * sizeof(RtRay), cudaMemcpyDeviceToHost);
+    cudaFree(d_rays);
+    if (e != cudaSuccess) return rt_cuda_fail(e, "camera rays");
+    return RT_OK;
+}
+
+inline int rt_tonemap_impl(int device, const float* rgb_in, size_t num_pixels, float exposure_stops, float gamma, uint8_t* bgra)
+{
+    if (rgb_in == NULL || bgra == NULL)
+        return rt_fail(RT_ERR_ARG, "null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    {
+        cudaGetLastError();
+        return rt_fail(RT_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+    }
+    RT_CUDA(cudaSetDevice(device));
+    if (num_pixels == 0) return RT_OK;
+    float* d_in = NULL;
+    uint8_t* d_out = NULL;
+    RT_CUDA(cudaMalloc((void**)&d_in, num_pixels * 12));
+    cudaError_t e = cudaMalloc((void**)&d_out, num_pixels * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(d_in, rgb_in, num_pixels * 12, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess)
+    {
+        // gammaExponent = 1.0f / gamma; exposure = pow(2.0f, stops)  (MainWindow.cpp:43-45)
+        float gamma_exp = 1.0f / gamma;
+        float exposure = std::pow(2.0f, exposure_stops);
+        k_tonemap<<<(unsigned)((num_pixels + 255) / 256), 256>>>(d_in, num_pixels, exposure, gamma_exp, d_out);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(bgra, d_out, num_pixels * 4, cudaMemcpyDeviceToHost);
+    cudaFree(d_in);
+    if (d_out) cudaFree(d_out);
+    if (e != cudaSuccess) return rt_cuda_fail(e, "tonemap");
+    return RT_OK;
+}
+
+#endif // RAYITO_B200_RT_RENDER_CUH

@@ -339,6 +339,7 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
     size_t o_mnodes = ab.put(mesh_nodes.data(), mesh_nodes.size() * sizeof(DNode));
     size_t o_tris = ab.put(tris.data(), tris.size() * sizeof(float4));
     size_t o_trin = ab.put(tri_normals.data(), tri_normals.size() * sizeof(uint4));
+    size_t o_fft = ab.put(face_first_tri.data(), face_first_tri.size() * sizeof(uint32_t));
     size_t o_normals = ab.put(desc->normals, (size_t)desc->num_normals * 12);
     size_t o_xforms = ab.put(xforms.data(), xforms.size() * sizeof(DXform));
     size_t o_ktime = ab.put(desc->key_time, (size_t)desc->num_keys * 4);
@@ -410,6 +411,7 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
     d.mesh_nodes = reinterpret_cast<const DNode*>(base + o_mnodes);
     d.tris = reinterpret_cast<const float4*>(base + o_tris);
     d.tri_normals = reinterpret_cast<const uint4*>(base + o_trin);
+    d.face_first_tri = reinterpret_cast<const uint32_t*>(base + o_fft);
     d.normals = reinterpret_cast<const float*>(base + o_normals);
     d.xforms = reinterpret_cast<const DXform*>(base + o_xforms);
     d.key_time = reinterpret_cast<const float*>(base + o_ktime);

@@ -1,0 +1,158 @@
+"""GPU parity tests of the wavefront renderer against the compiled reference's own
+raytrace() on the same scene, resolution and sample counts.
+
+Bars (BASELINE.json north_star): camera rays bit-exact (the counter-based sample
+stream reproduces the reference's); Monte-Carlo images within a stated per-pixel
+RMSE.  The device evaluates cos/sin/pow in double and rounds once, glibc's float
+versions are correctly rounded for all but a sliver of inputs, so in practice most
+pixels come out BIT-identical; the tolerances below are what is asserted."""
+import numpy as np
+import pytest
+
+from tests.raybatches import bits
+
+pytestmark = pytest.mark.gpu
+
+# Stated tolerances for Monte-Carlo stages (linear float RGB, per pixel, relative to
+# the image's mean luminance), and for the 8-bit display image (gamma 2.2).
+RMSE_REL_TOL = 0.02
+MIN_IDENTICAL_FRACTION = 0.90
+
+
+def _rays_as_rows(rays):
+    return np.ascontiguousarray(rays).view(np.uint32).reshape(len(rays), 8)
+
+
+def _sorted_rows(rows):
+    return rows[np.lexsort(rows.T[::-1])]
+
+
+@pytest.fixture(scope="module")
+def dev1(capi, scene1_host):
+    d = capi.DeviceScene(scene1_host.desc)
+    yield d
+    d.close()
+
+
+@pytest.fixture(scope="module")
+def dev2(capi, scene2_host):
+    d = capi.DeviceScene(scene2_host.desc)
+    yield d
+    d.close()
+
+
+def _compare_images(mine, theirs, label):
+    assert mine.shape == theirs.shape
+    assert not np.isnan(mine).any(), label + ": NaN pixels"
+    same = (bits(mine) == bits(theirs)).all(axis=-1)
+    rmse = float(np.sqrt(np.mean((mine.astype(np.float64) - theirs.astype(np.float64)) ** 2)))
+    rel = rmse / max(float(theirs.mean()), 1e-12)
+    g_m = np.clip(np.power(np.clip(mine, 0, None), 1 / 2.2), 0, 1) * 255.0
+    g_t = np.clip(np.power(np.clip(theirs, 0, None), 1 / 2.2), 0, 1) * 255.0
+    diff8 = np.abs(g_m.astype(np.uint8).astype(int) - g_t.astype(np.uint8).astype(int))
+    print("%s: identical pixels %.4f, rmse %.3e (rel %.3e), 8-bit max diff %d, 8-bit pixels differing %.4f" % (
+        label, same.mean(), rmse, rel, diff8.max(), (diff8.max(axis=-1) > 0).mean()))
+    return same.mean(), rel
+
+
+def test_camera_rays_reproduce_reference_stream(dev1, scene1_ref, scene1_host, capi):
+    """Every camera ray the reference casts for a frame, found among its recorded
+    rays by origin, must be generated bit-for-bit by the counter-based stream (MWC
+    jump-ahead + CMJ), for every pixel and every pixel-sample index."""
+    spec = scene1_host.default_camera_spec()
+    cam = capi.camera_from_spec(spec)
+    W, H, ps = 72, 44, 3      # 4x4 chunks of 18x11
+    _img, _stats = scene1_ref.render(spec, W, H, ps, ls=1, depth=3, record_rays=True)
+    rec = scene1_ref.recorded_rays(0, capi.RAY_DTYPE)
+    origin = np.array(spec[1:4], np.float32)
+    primary = rec[(rec["origin"] == origin).all(axis=1) & (rec["tmax"] == np.float32(1e30))]
+    assert len(primary) == W * H * ps * ps
+    mine = np.concatenate([dev1.camera_rays(cam, W, H, ps, psi) for psi in range(ps * ps)])
+    assert np.array_equal(_sorted_rows(_rays_as_rows(mine)), _sorted_rows(_rays_as_rows(primary)))
+
+
+def test_camera_rays_uneven_chunks(dev1, scene1_ref, scene1_host, capi):
+    """Image sizes that do not divide by four make a fifth row/column of chunks."""
+    spec = scene1_host.default_camera_spec()
+    cam = capi.camera_from_spec(spec)
+    W, H, ps = 50, 31, 2
+    scene1_ref.render(spec, W, H, ps, ls=1, depth=1, record_rays=True)
+    rec = scene1_ref.recorded_rays(0, capi.RAY_DTYPE)
+    origin = np.array(spec[1:4], np.float32)
+    primary = rec[(rec["origin"] == origin).all(axis=1)]
+    mine = np.concatenate([dev1.camera_rays(cam, W, H, ps, psi) for psi in range(ps * ps)])
+    assert np.array_equal(_sorted_rows(_rays_as_rows(mine)), _sorted_rows(_rays_as_rows(primary)))
+
+
+@pytest.mark.parametrize("W,H,ps,ls,depth", [(128, 72, 4, 1, 3), (64, 36, 2, 2, 4), (40, 24, 1, 1, 1)])
+def test_scene1_image_matches_reference(dev1, scene1_ref, scene1_host, capi, W, H, ps, ls, depth):
+    spec = scene1_host.default_camera_spec()
+    cam = capi.camera_from_spec(spec)
+    theirs, rstats = scene1_ref.render(spec, W, H, ps, ls=ls, depth=depth)
+    mine, stats = dev1.render(cam, W, H, ps, ls=ls, depth=depth)
+    same, rel = _compare_images(mine, theirs, "scene1 %dx%d ps%d ls%d d%d" % (W, H, ps, ls, depth))
+    assert stats.samples == W * H * ps * ps
+    # ray counts: a "ray" is one scene.intersect / doesIntersect call of pathTrace
+    ref_rays = rstats.closest_calls + rstats.any_calls
+    my_rays = stats.closest_rays + stats.any_rays
+    assert abs(my_rays - ref_rays) <= 0.002 * ref_rays, (my_rays, ref_rays)
+    assert rel <= RMSE_REL_TOL
+    assert same >= MIN_IDENTICAL_FRACTION
+
+
+def test_scene2_image_matches_reference(dev2, scene2_ref, scene2_host, capi):
+    spec = scene2_host.default_camera_spec()
+    cam = capi.camera_from_spec(spec)
+    W, H, ps = 96, 64, 3
+    theirs, rstats = scene2_ref.render(spec, W, H, ps, ls=1, depth=3)
+    mine, stats = dev2.render(cam, W, H, ps, ls=1, depth=3)
+    same, rel = _compare_images(mine, theirs, "scene2")
+    assert rel <= RMSE_REL_TOL
+    assert same >= MIN_IDENTICAL_FRACTION
+
+
+def test_tile_sharding_is_exact(dev1, scene1_host, capi):
+    """Any partition of the image into rank-owned tiles reproduces the single-GPU
+    image bit for bit (the sample stream is position-addressable), and small
+    batches give the same image as one big batch."""
+    spec = scene1_host.default_camera_spec()
+    cam = capi.camera_from_spec(spec)
+    W, H, ps = 100, 60, 2
+    whole, _ = dev1.render(cam, W, H, ps)
+    for world in (2, 3):
+        merged = np.full((H, W, 3), -1.0, np.float32)
+        total = 0
+        for rank in range(world):
+            _, st = dev1.render(cam, W, H, ps, rank=rank, world=world, tile_size=16, out=merged)
+            total += st.samples
+        assert total == W * H * ps * ps
+        assert np.array_equal(bits(merged), bits(whole))
+    small, _ = dev1.render(cam, W, H, ps, tile_size=8, max_batch_samples=1024)
+    assert np.array_equal(bits(small), bits(whole))
+
+
+def test_work_counters(dev1, scene1_host, capi):
+    spec = scene1_host.default_camera_spec()
+    cam = capi.camera_from_spec(spec)
+    img_a, plain = dev1.render(cam, 64, 36, 2)
+    img_b, counted = dev1.render(cam, 64, 36, 2, count_work=True)
+    assert np.array_equal(bits(img_a), bits(img_b))
+    assert counted.closest_rays == plain.closest_rays and counted.any_rays == plain.any_rays
+    rays = counted.closest_rays + counted.any_rays
+    assert 4.0 < counted.node_pops / rays < 40.0
+    assert counted.tri_tests > 0 and counted.shape_tests > 0 and counted.xform_evals > rays
+
+
+def test_tonemap_matches_display_image(capi):
+    rng = np.random.RandomState(5)
+    rgb = rng.uniform(0, 2.0, size=(257, 3)).astype(np.float32)
+    rgb[3] = (-0.1, 0.5, 0.5)          # negative -> green
+    rgb[4] = (np.nan, 0.5, 0.5)        # NaN -> blue
+    out = capi.tonemap_bgra8(rgb, exposure_stops=0.0, gamma=2.2)
+    assert tuple(out[3]) == (0, 255, 0, 255)
+    assert tuple(out[4]) == (255, 0, 0, 255)
+    ok = np.ones(len(rgb), bool)
+    ok[3] = ok[4] = False
+    expect = np.clip(np.power(rgb[ok].astype(np.float64), 1 / np.float32(2.2)), 0, 1)
+    got = out[ok][:, [2, 1, 0]].astype(int)
+    assert np.abs(got - np.floor(expect * 255.0)).max() <= 1
