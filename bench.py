@@ -1,0 +1,413 @@
+#!/usr/bin/env python
+"""bench.py -- Mrays/s of the Rayito render hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c4|...]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): BASELINE.json configs[3], the north-star target --
+Stage 7 scene 1 (bumpy.obj, keyed transforms / motion blur, mirror BRDF) at
+3840x2160, 256 spp (pixel samples hint 16), 1 light sample, ray depth 3.  One
+"step" renders the whole frame once.  A "ray" is one scene.intersect /
+scene.doesIntersect call of pathTrace: path segments + BSDF-MIS
+probes + shadow rays.
+
+value      whole-job Mrays/s, scene and camera resident in HBM, image left in HBM;
+           CUDA events on the launching stream, max over ranks.
+e2e        the same metric through the reference-facing C++ call Rayito::raytrace()
+           (host scene -> prepare() -> flatten -> upload -> render -> image in host
+           memory), wall clock, host<->device copies inside the timed region.
+roofline   the traversal kernels (closest-hit / any-hit): algorithmic bytes per ray
+           B = 48 + 32 N_pop + 36 N_tri + 16 N_shape + 40 K_xf (the
+           counts come from the kernels' own exact work counters, which the tests
+           pin to the reference's traversal) over their summed CUDA-event time,
+           against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
+cpu_baseline / --impl reference
+           the UNMODIFIED reference raytrace() (oracle/_ref, 16 worker threads by
+           design) on the box's host cores, same scene and spp at a reduced
+           resolution (throughput is a rate; the sample is stated).
+
+The oracle is used here only as the timed CPU baseline, never on the measured path.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (recipe, width, height, pixel samples hint, light samples hint, depth, grid)
+    "c4": dict(recipe=1, width=3840, height=2160, ps=16, ls=1, depth=3, grid=(0, 0),
+               label="Rayito_Stage7 scene 1 (bumpy.obj, motion blur, mirror BRDF) 3840x2160 256spp ls1 depth3"),
+    "c4-1080p": dict(recipe=1, width=1920, height=1080, ps=16, ls=1, depth=3, grid=(0, 0),
+                     label="Rayito_Stage7 scene 1 1920x1080 256spp ls1 depth3"),
+    "c4-small": dict(recipe=1, width=480, height=270, ps=16, ls=1, depth=3, grid=(0, 0),
+                     label="Rayito_Stage7 scene 1 480x270 256spp ls1 depth3"),
+    "scene2": dict(recipe=2, width=3840, height=2160, ps=16, ls=1, depth=3, grid=(0, 0),
+                   label="Rayito_Stage7 scene 2 (falling spheres, tumbling boxes) 3840x2160 256spp"),
+    "c5": dict(recipe=5, width=3840, height=2160, ps=8, ls=1, depth=3, grid=(2236, 2236),
+               label="synthetic displaced sphere, 4 999 696 quads = 9 999 392 triangles, 3840x2160 64spp"),
+}
+CPU_SAMPLE = dict(width=480, height=270)      # same scene, same spp, reduced resolution
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+                power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def algorithmic_bytes(stats):
+    """B = 32 (ray in) + 16 (hit out) per ray + 32 per node popped
+    + 36 per triangle tested + 16 per analytic shape tested + 40 per keyed
+    transform evaluated."""
+    rays = stats["closest_rays"] + stats["any_rays"]
+    return (48 * rays + 32 * stats["node_pops"] + 36 * stats["tri_tests"] + 16 * stats["shape_tests"]
+            + 40 * stats["xform_evals"])
+
+
+def run_reference(args, wl, rank, world):
+    """--impl reference: the unmodified reference raytrace() on the host cores."""
+    if rank != 0:
+        return
+    from oracle import refapi
+    from rayito_b200 import build
+    import numpy as np
+    cores = os.cpu_count() or 1
+    obj = build.model_path("bumpy.obj") if wl["recipe"] == 1 else None
+    scene = refapi.RefScene(wl["recipe"], obj, wl["grid"])
+    spec = np.array([30, -4, 5, 15, 0, 0, 0, 0, 1, 0, 16, 0, 0, 1], np.float32) if wl["recipe"] != 2 else \
+        np.array([30, -4, 10, 30, 0, 5, 0, 0, 1, 0, 16, 0, 0, 1], np.float32)
+    W, H = CPU_SAMPLE["width"], CPU_SAMPLE["height"]
+    times, rays = [], 0
+    for step in range(args.warmup + args.steps):
+        _img, st = scene.render(spec, W, H, wl["ps"], ls=wl["ls"], depth=wl["depth"])
+        if step >= args.warmup:
+            times.append(st.render_seconds)
+            rays = st.closest_calls + st.any_calls
+        log("[reference] step %d: %.2f s, %.2f Mrays/s" % (step, st.render_seconds,
+                                                           (st.closest_calls + st.any_calls) / st.render_seconds / 1e6))
+    total = sum(times)
+    value = rays * len(times) / total / 1e6
+    threads = min(16, cores)
+    sample = ("same scene/spp/ls/depth at %dx%d (%.1f M samples, %.1f M rays per step); reference raytrace() "
+              "incl. prepare(); 16 worker threads by design (RaytraceMain.cpp:504-519) on %d host cores"
+              % (W, H, W * H * wl["ps"] ** 2 / 1e6, rays / 1e6, cores))
+    line = {
+        "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["label"], "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": threads, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--batch", type=int, default=0, help="max samples per wavefront batch (0 = core default)")
+    ap.add_argument("--tile", type=int, default=0)
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, wl, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from rayito_b200 import build, capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the render core has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    # ---- scene: built with the C++ host API, flattened, uploaded once ------------
+    obj = build.model_path("bumpy.obj") if wl["recipe"] == 1 else None
+    t0 = time.perf_counter()
+    hscene = capi.HostScene(wl["recipe"], obj, wl["grid"])
+    host_prepare_s = time.perf_counter() - t0
+    dscene = capi.DeviceScene(hscene.desc, device=local_rank)
+    spec = hscene.default_camera_spec()
+    cam = capi.camera_from_spec(spec)
+    W, H, ps, ls, depth = wl["width"], wl["height"], wl["ps"], wl["ls"], wl["depth"]
+
+    image = torch.zeros((H, W, 3), dtype=torch.float32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+    stream = torch.cuda.current_stream(dev)
+
+    def params(flags=0):
+        return capi.RtRenderParams(W, H, ps, ls, depth, args.tile, rank, world, args.batch, flags)
+
+    def step(flags=0):
+        st = dscene.render_device(cam, params(flags), image.data_ptr(), stream.cuda_stream)
+        if world > 1:
+            # the one collective of the path: tile assembly on rank 0.  Every pixel is
+            # owned by exactly one rank and zero elsewhere, so the sum is exact.
+            dist.reduce(image, dst=0, op=dist.ReduceOp.SUM)
+        return st
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # exact work counters (deterministic per frame) from one untimed instrumented step
+    image.zero_()
+    counted = step(capi.RT_RENDER_COUNT_WORK).as_dict()
+    log("[rank %d] counted step: %s" % (rank, counted))
+
+    for _ in range(args.warmup):
+        image.zero_()
+        flush.zero_()
+        step()
+
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    trace_ms = 0.0
+    trace_launches = 0
+    render_ms = 0.0
+    ev0.record(stream)
+    for _ in range(args.steps):
+        image.zero_()
+        flush.zero_()             # L2 flush between timed steps
+        st = step(capi.RT_RENDER_TIME_TRACE)
+        launches += st.kernel_launches
+        trace_ms += st.trace_ms
+        trace_launches += st.trace_launches
+        render_ms += st.render_ms
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    elapsed_ms = ev0.elapsed_time(ev1)
+
+    # ---- aggregate over ranks ------------------------------------------------------
+    def allsum(x):
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def allmax(x):
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    rays_rank = counted["closest_rays"] + counted["any_rays"]
+    rays_total = allsum(rays_rank)
+    samples_total = allsum(counted["samples"])
+    max_ms = allmax(elapsed_ms)
+    launches_total = allsum(launches)
+    value = rays_total * args.steps / (max_ms / 1e3) / 1e6
+    # traversal roofline: sum over ranks of algorithmic bytes / max over ranks of traversal time
+    bytes_rank = algorithmic_bytes(counted)
+    bytes_total = allsum(bytes_rank)
+    trace_ms_max = allmax(trace_ms)
+    peak, peak_src = load_peaks()
+    achieved = bytes_total * args.steps / (trace_ms_max / 1e3) / 1e9 / world    # per GPU
+    roofline = {
+        "bound": "hbm", "kernel": "k_trace_paths + k_trace_mis (closest hit) + k_trace_shadow (any hit)",
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+        "traffic": None,
+        "bytes_per_ray": bytes_total / rays_total,
+        "per_ray": {"node_pops": allsum(counted["node_pops"]) / rays_total,
+                    "tri_tests": allsum(counted["tri_tests"]) / rays_total,
+                    "shape_tests": allsum(counted["shape_tests"]) / rays_total,
+                    "xform_evals": allsum(counted["xform_evals"]) / rays_total},
+        "launches_per_step": trace_launches / max(args.steps, 1),
+        "bytes_per_launch": bytes_rank / max(trace_launches / max(args.steps, 1), 1),
+        "avg_launch_ms": trace_ms / max(trace_launches, 1),
+        "trace_share_of_step": trace_ms_max / max_ms,
+        "trace_mrays_per_s_per_gpu": rays_total * args.steps / (trace_ms_max / 1e3) / 1e6 / world,
+        "note": "scene is %.1f MB and L2-resident by nature of this config: the HBM fraction is reported as the "
+                "contract asks, but L2/latency binds first (SURVEY.md 8d)" % (hscene_bytes(hscene) / 1e6),
+    }
+
+    # ---- e2e: through Rayito::raytrace() with host buffers -------------------------
+    e2e = None
+    if not args.no_e2e:
+        e2e = measure_e2e(args, wl, capi, obj, spec, rank, world, local_rank, dev, dist, torch, np, rays_total,
+                          hscene_bytes(hscene))
+
+    # ---- CPU baseline (rank 0, N=1 only) -------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = measure_cpu_baseline(wl, obj, spec)
+
+    if rank == 0:
+        line = {
+            "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": max_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["label"], "parallelism": "screen tiles x%d (diagonal interleave), scene replicated" % world,
+                       "samples_per_step": samples_total, "rays_per_step": rays_total,
+                       "rays_per_sample": rays_total / samples_total,
+                       "msamples_per_s": samples_total * args.steps / (max_ms / 1e3) / 1e6,
+                       "l2": "256 MB flush buffer written between timed steps; per-batch path state (~2 GB) >> L2",
+                       "host_prepare_s": host_prepare_s, "render_ms_per_step_rank0": render_ms / args.steps},
+            "clocks": clocks, "gpu_launches": int(launches_total), "roofline": roofline,
+        }
+        if e2e is not None:
+            line["e2e"] = e2e
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def hscene_bytes(hscene):
+    d = hscene.desc.contents
+    return (d.num_mesh_nodes * 32 + d.num_top_nodes * 32 + d.num_vertices * 12 + d.num_normals * 12
+            + d.num_indices * 8 + d.num_faces * 8 + d.num_cdf * 4 + d.num_keys * 44)
+
+
+def measure_e2e(args, wl, capi, obj, spec, rank, world, local_rank, dev, dist, torch, np, rays_total, scene_bytes):
+    """Wall-clock Mrays/s through Rayito::raytrace() (rth_raytrace = what the GUI's
+    render button does): host scene in, host image out, every step."""
+    import ctypes as C
+    W, H, ps, ls, depth = wl["width"], wl["height"], wl["ps"], wl["ls"], wl["depth"]
+    img = np.zeros((H, W, 3), np.float32)
+    stats = capi.RtRenderStats()
+    lib = capi.host()
+    path = obj.encode() if obj else None
+
+    def one():
+        rc = lib.rth_raytrace(wl["recipe"], path, wl["grid"][0], wl["grid"][1], spec.ctypes.data, W, H, ps, ls, depth,
+                              local_rank, rank, world, 0, img.ctypes.data, C.byref(stats))
+        if rc != 0:
+            raise RuntimeError("rth_raytrace: " + lib.rth_last_error_string().decode())
+        if world > 1:
+            t = torch.from_numpy(img).to(dev)
+            dist.reduce(t, dst=0, op=dist.ReduceOp.SUM)
+            if rank == 0:
+                t.cpu()
+        return stats.render_ms
+
+    one()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    n = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(n):
+        one()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    wall = time.perf_counter() - t0
+    t = torch.tensor([wall], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    wall = float(t.item())
+    return {"value": rays_total * n / wall / 1e6, "unit": "Mrays/s",
+            "h2d_bytes_per_step": int(scene_bytes), "d2h_bytes_per_step": int(W * H * 12 / world),
+            "steps": n, "ms_per_step": 1e3 * wall / n,
+            "includes": "scene build from OBJ text + prepare() (host BVH build) + flatten + upload + render + image download"}
+
+
+def measure_cpu_baseline(wl, obj, spec):
+    from oracle import refapi
+    if not refapi.available():
+        return {"value": None, "unit": "Mrays/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
+    cores = os.cpu_count() or 1
+    scene = refapi.RefScene(wl["recipe"], obj, wl["grid"])
+    W, H = CPU_SAMPLE["width"], CPU_SAMPLE["height"]
+    if wl["recipe"] == 5:
+        W, H = 240, 135
+    _img, st = scene.render(spec, W, H, wl["ps"], ls=wl["ls"], depth=wl["depth"])
+    rays = st.closest_calls + st.any_calls
+    return {"value": rays / st.render_seconds / 1e6, "unit": "Mrays/s", "cores": min(16, cores), "kind": "reference",
+            "host_cores": cores, "seconds": st.render_seconds, "prepare_seconds": st.prepare_seconds,
+            "sample": "unmodified reference raytrace() (oracle/_ref), same scene/spp/ls/depth at %dx%d = %.1f M samples, "
+                      "%.1f M rays; includes prepare(); reference uses exactly 16 worker threads" % (
+                          W, H, W * H * wl["ps"] ** 2 / 1e6, rays / 1e6)}
+
+
+if __name__ == "__main__":
+    main()

@@ -192,7 +192,11 @@ typedef struct RtRenderParams
     uint32_t flags;                  /* RT_RENDER_* */
 } RtRenderParams;
 
-enum { RT_RENDER_COUNT_WORK = 1u  /* also count node pops / triangle tests (slower) */ };
+enum
+{
+    RT_RENDER_COUNT_WORK = 1u,  /* also count node pops / triangle tests (slower) */
+    RT_RENDER_TIME_TRACE = 2u   /* CUDA-event pairs around every traversal kernel -> trace_ms */
+};
 
 typedef struct RtRenderStats
 {
@@ -204,8 +208,9 @@ typedef struct RtRenderStats
     uint64_t shape_tests;         /* analytic shapes tested */
     uint64_t xform_evals;         /* keyed transforms evaluated */
     uint64_t kernel_launches;     /* CUDA kernels launched by this call */
+    uint64_t trace_launches;      /* of which traversal kernels (closest / any hit) */
     float render_ms;              /* device time of the render (CUDA events) */
-    float trace_ms;               /* device time inside the traversal kernels */
+    float trace_ms;               /* device time inside the traversal kernels (RT_RENDER_TIME_TRACE) */
     float upload_ms;              /* host->device scene/camera copies inside this call */
     float download_ms;            /* device->host image copy inside this call */
 } RtRenderStats;

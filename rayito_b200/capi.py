@@ -40,12 +40,13 @@ class RtRenderParams(C.Structure):
 
 
 RT_RENDER_COUNT_WORK = 1
+RT_RENDER_TIME_TRACE = 2
 
 
 class RtRenderStats(C.Structure):
     _fields_ = [("samples", C.c_uint64), ("closest_rays", C.c_uint64), ("any_rays", C.c_uint64),
                 ("node_pops", C.c_uint64), ("tri_tests", C.c_uint64), ("shape_tests", C.c_uint64),
-                ("xform_evals", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("xform_evals", C.c_uint64), ("kernel_launches", C.c_uint64), ("trace_launches", C.c_uint64),
                 ("render_ms", C.c_float), ("trace_ms", C.c_float), ("upload_ms", C.c_float), ("download_ms", C.c_float)]
 
     def as_dict(self):
@@ -239,9 +240,9 @@ class DeviceScene:
         return hits
 
     def render(self, camera, width, height, ps, ls=1, depth=3, rank=0, world=1, tile_size=0,
-               max_batch_samples=0, count_work=False, out=None):
+               max_batch_samples=0, count_work=False, time_trace=False, out=None):
         params = RtRenderParams(width, height, ps, ls, depth, tile_size, rank, world, max_batch_samples,
-                                RT_RENDER_COUNT_WORK if count_work else 0)
+                                (RT_RENDER_COUNT_WORK if count_work else 0) | (RT_RENDER_TIME_TRACE if time_trace else 0))
         if out is None:
             out = np.zeros((height, width, 3), np.float32)
         stats = RtRenderStats()

@@ -89,6 +89,8 @@ struct RenderBuffers
     float* d_image;             // for the host-output entry point
     size_t image_floats;
     cudaEvent_t ev[4];
+    std::vector<cudaEvent_t>* trace_events;   // start/stop pairs around traversal kernels (RT_RENDER_TIME_TRACE)
+    size_t trace_events_used;
 };
 
 // ---------------------------------------------------------------------------
@@ -628,6 +630,11 @@ inline void rt_render_release(RtScene* s)
     if (rb->d_tile_ids) cudaFree(rb->d_tile_ids);
     if (rb->d_image) cudaFree(rb->d_image);
     for (int i = 0; i < 4; ++i) cudaEventDestroy(rb->ev[i]);
+    if (rb->trace_events)
+    {
+        for (size_t i = 0; i < rb->trace_events->size(); ++i) cudaEventDestroy((*rb->trace_events)[i]);
+        delete rb->trace_events;
+    }
     delete rb;
     s->render = NULL;
 }
@@ -768,9 +775,26 @@ inline int rt_render_reserve(RtScene* s, const RenderPlan& plan)
     return RT_OK;
 }
 
-template <bool COUNT>
-static int rt_launch_batch(RtScene* s, const RenderCtx& c, cudaStream_t st, uint64_t& launches)
+// Event pair helpers: traversal kernels are timed on the launching stream
+inline void rt_trace_mark(RenderBuffers* rb, bool timed, cudaStream_t st)
 {
+    if (!timed)
+        return;
+    if (rb->trace_events == NULL)
+        rb->trace_events = new std::vector<cudaEvent_t>();
+    if (rb->trace_events_used == rb->trace_events->size())
+    {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        rb->trace_events->push_back(e);
+    }
+    cudaEventRecord((*rb->trace_events)[rb->trace_events_used++], st);
+}
+
+template <bool COUNT>
+static int rt_launch_batch(RtScene* s, const RenderCtx& c, cudaStream_t st, uint64_t& launches, bool timed, uint64_t& trace_launches)
+{
+    RenderBuffers* rb = s->render;
     const int cap = s->stack_cap;
     int dev_sms = 148;
     cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, s->device);
@@ -783,17 +807,23 @@ static int rt_launch_batch(RtScene* s, const RenderCtx& c, cudaStream_t st, uint
     int cur = 0;
     for (uint32_t b = 0; b < c.depth; ++b)
     {
+        rt_trace_mark(rb, timed, st);
         if (cap <= 32)      k_trace_paths<32, COUNT><<<wide, RT_BLOCK, 0, st>>>(c, cur);
         else if (cap <= 64) k_trace_paths<64, COUNT><<<wide, RT_BLOCK, 0, st>>>(c, cur);
         else                k_trace_paths<104, COUNT><<<wide, RT_BLOCK, 0, st>>>(c, cur);
+        rt_trace_mark(rb, timed, st);
+        trace_launches += 1;
         k_shade<<<wide, RT_BLOCK, 0, st>>>(c, cur, b);
         launches += 2;
         for (uint32_t l = 0; l < c.nls; ++l)
         {
             k_light_sample<<<wide, RT_BLOCK, 0, st>>>(c, b, l);
+            rt_trace_mark(rb, timed, st);
             if (cap <= 32)      { k_trace_shadow<32, COUNT><<<wide, RT_BLOCK, 0, st>>>(c);  k_trace_mis<32, COUNT><<<wide, RT_BLOCK, 0, st>>>(c); }
             else if (cap <= 64) { k_trace_shadow<64, COUNT><<<wide, RT_BLOCK, 0, st>>>(c);  k_trace_mis<64, COUNT><<<wide, RT_BLOCK, 0, st>>>(c); }
             else                { k_trace_shadow<104, COUNT><<<wide, RT_BLOCK, 0, st>>>(c); k_trace_mis<104, COUNT><<<wide, RT_BLOCK, 0, st>>>(c); }
+            rt_trace_mark(rb, timed, st);
+            trace_launches += 2;
             k_resolve<<<wide, RT_BLOCK, 0, st>>>(c, l);
             launches += 4;
         }
@@ -865,7 +895,9 @@ inline int rt_render_impl(RtScene* s, const RtCamera* camera, const RtRenderPara
     RT_CUDA(cudaEventRecord(rb->ev[1], st));
 
     const bool count = (prm->flags & RT_RENDER_COUNT_WORK) != 0;
-    uint64_t launches = 0;
+    const bool timed = (prm->flags & RT_RENDER_TIME_TRACE) != 0;
+    rb->trace_events_used = 0;
+    uint64_t launches = 0, trace_launches = 0;
     uint64_t samples = 0;
     for (size_t t0 = 0; t0 < plan.tiles.size(); t0 += plan.tiles_per_batch)
     {
@@ -873,7 +905,8 @@ inline int rt_render_impl(RtScene* s, const RtCamera* camera, const RtRenderPara
         c.tile_ids = rb->d_tile_ids + t0;
         c.num_pixels = (uint32_t)(nt * plan.tile * plan.tile);
         c.num_samples = c.num_pixels * plan.spp;
-        rc = count ? rt_launch_batch<true>(s, c, st, launches) : rt_launch_batch<false>(s, c, st, launches);
+        rc = count ? rt_launch_batch<true>(s, c, st, launches, timed, trace_launches)
+                   : rt_launch_batch<false>(s, c, st, launches, timed, trace_launches);
         if (rc != RT_OK) return rc;
     }
     RT_CUDA(cudaEventRecord(rb->ev[2], st));
@@ -925,6 +958,18 @@ inline int rt_render_impl(RtScene* s, const RtCamera* camera, const RtRenderPara
         cudaEventElapsedTime(&stats->render_ms, rb->ev[1], rb->ev[2]);
         cudaEventElapsedTime(&stats->download_ms, rb->ev[2], rb->ev[3]);
         stats->trace_ms = 0.0f;
+        stats->trace_launches = trace_launches;
+        if (timed && rb->trace_events)
+        {
+            double total = 0.0;
+            for (size_t k = 0; k + 1 < rb->trace_events_used; k += 2)
+            {
+                float ms = 0.0f;
+                cudaEventElapsedTime(&ms, (*rb->trace_events)[k], (*rb->trace_events)[k + 1]);
+                total += ms;
+            }
+            stats->trace_ms = (float)total;
+        }
     }
     return RT_OK;
 }
