@@ -62,7 +62,9 @@ def _run(cmd, cwd=None):
 def build_core(force=False, verbose=False):
     srcs = _sources(CSRC, (".cu", ".cuh", ".h")) + _sources(INCLUDE, (".h",))
     if force or _newer(CORE_LIB, srcs):
-        cmd = [NVCC] + NVCC_FLAGS + ["-I" + INCLUDE, os.path.join(CSRC, "rt_core.cu"), "-o", CORE_LIB]
+        # RT_NVCC_EXTRA: extra -D switches for tuning runs (e.g. "-DRT_ADVANCE_STEPS=2")
+        extra = os.environ.get("RT_NVCC_EXTRA", "").split()
+        cmd = [NVCC] + NVCC_FLAGS + extra + ["-I" + INCLUDE, os.path.join(CSRC, "rt_core.cu"), "-o", CORE_LIB]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         out = _run(cmd)

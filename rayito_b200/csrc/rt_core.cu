@@ -8,6 +8,7 @@
 
 #include "rt_scene.cuh"
 #include "rt_trace.cuh"
+#include "rt_wave.cuh"
 #include "rt_render.cuh"
 
 thread_local std::string g_rt_error;
@@ -54,71 +55,116 @@ __device__ __forceinline__ void flush_work(const WorkCount& wc, uint64_t* work)
     }
 }
 
-template <int CAP, bool COUNT, bool EX>
-__global__ void __launch_bounds__(128)
-k_trace_closest(const __grid_constant__ DScene sc, const RtRay* __restrict__ rays, size_t n,
-                void* __restrict__ hits, uint64_t* work)
+// Ray-batch adaptors for the wave traversal
+struct BatchIO
 {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    WorkCount wc = { 0, 0, 0, 0 };
-    if (i < n)
+    const RtRay* rays;
+    float4* raw;        // closest: (t, shape, triangle record, -)
+    uint8_t* any;       // any hit: 0 / 1
+    __device__ __forceinline__ bool load(uint32_t j, V3& o, V3& d, float& tmax, float& time, uint32_t& tag) const
     {
-        V3 o, d;
-        float tmax, time;
-        load_ray(rays, i, o, d, tmax, time);
-        LocalRay r0;
-        ClosestHit h = trace_closest<CAP, COUNT>(sc, o, d, tmax, time, r0, wc);
-        int32_t face = -1, tri = -1;
-        if (h.tri_rec >= 0)
-        {
-            face = (int32_t)__float_as_uint(__ldg(sc.tris + 3 * (size_t)h.tri_rec + 0).w);
-            tri = (int32_t)__float_as_uint(__ldg(sc.tris + 3 * (size_t)h.tri_rec + 1).w);
-        }
-        if (EX)
-        {
-            V3 nrm;
-            float cm;
-            hit_shading_inputs(sc, r0, time, h, nrm, cm);
-            float4* out = reinterpret_cast<float4*>(static_cast<RtHitEx*>(hits) + i);
-            out[0] = make_float4(h.t, __int_as_float(h.shape), __int_as_float(face), __int_as_float(tri));
-            out[1] = make_float4(nrm.x, nrm.y, nrm.z, cm);
-        }
-        else
-        {
-            float4* out = reinterpret_cast<float4*>(static_cast<RtHit*>(hits) + i);
-            out[0] = make_float4(h.t, __int_as_float(h.shape), __int_as_float(face), __int_as_float(tri));
-        }
+        tag = j;
+        load_ray(rays, j, o, d, tmax, time);
+        return true;
     }
+    __device__ __forceinline__ void store(uint32_t tag, const WaveResult& r) const
+    {
+        if (raw) raw[tag] = make_float4(r.t, __int_as_float(r.shape), __int_as_float(r.tri_rec), 0.0f);
+        else any[tag] = r.any_hit ? 1 : 0;
+    }
+};
+
+template <int CAP, bool ANY, bool COUNT>
+__global__ void __launch_bounds__(128)
+k_trace_batch(const __grid_constant__ DScene sc, const RtRay* __restrict__ rays, uint32_t n,
+              float4* raw, uint8_t* any, uint32_t* cursor, uint64_t* work)
+{
+    WorkCount wc = { 0, 0, 0, 0 };
+    BatchIO io = { rays, raw, any };
+    trace_wave<CAP, ANY, COUNT>(sc, io, n, cursor, wc);
     if (COUNT)
         flush_work(wc, work);
 }
 
-template <int CAP, bool COUNT>
+// (t, shape, triangle record) -> RtHit / RtHitEx: face and fan-triangle ids, and for
+// the extended record the shading normal and colour modifier (hit_shading_inputs)
+template <bool EX>
 __global__ void __launch_bounds__(128)
-k_trace_any(const __grid_constant__ DScene sc, const RtRay* __restrict__ rays, size_t n,
-            uint8_t* __restrict__ hits, uint64_t* work)
+k_finalize_batch(const __grid_constant__ DScene sc, const RtRay* __restrict__ rays, uint32_t n,
+                 const float4* raw, void* __restrict__ hits)
 {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    WorkCount wc = { 0, 0, 0, 0 };
-    if (i < n)
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    float4 r = raw[i];
+    ClosestHit h;
+    h.t = r.x;
+    h.shape = __float_as_int(r.y);
+    h.tri_rec = __float_as_int(r.z);
+    int32_t face = -1, tri = -1;
+    if (h.tri_rec >= 0)
+    {
+        face = (int32_t)__float_as_uint(__ldg(sc.tris + 3 * (size_t)h.tri_rec + 0).w);
+        tri = (int32_t)__float_as_uint(__ldg(sc.tris + 3 * (size_t)h.tri_rec + 1).w);
+    }
+    float4 first = make_float4(h.t, __int_as_float(h.shape), __int_as_float(face), __int_as_float(tri));
+    if (EX)
     {
         V3 o, d;
         float tmax, time;
         load_ray(rays, i, o, d, tmax, time);
-        hits[i] = trace_any<CAP, COUNT>(sc, o, d, tmax, time, wc) ? 1 : 0;
+        TRS set_trs = xform_eval(sc, sc.set_xform, time);
+        LocalRay r0;
+        r0.o = to_local_point(set_trs, o);
+        r0.d = to_local_vector(set_trs, d);
+        r0.inv = r0.d; r0.neg = 0;
+        V3 nrm;
+        float cm;
+        hit_shading_inputs(sc, r0, time, h, nrm, cm);
+        float4* out = reinterpret_cast<float4*>(static_cast<RtHitEx*>(hits) + i);
+        out[0] = first;
+        out[1] = make_float4(nrm.x, nrm.y, nrm.z, cm);
     }
-    if (COUNT)
-        flush_work(wc, work);
+    else
+    {
+        reinterpret_cast<float4*>(hits)[i] = first;     // may alias raw: same slot, read before write
+    }
+}
+
+static unsigned persistent_blocks(const void* kernel, int device)
+{
+    int sms = 148, per_sm = 4;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 128, 0) != cudaSuccess || per_sm < 1)
+        per_sm = 4;
+    return (unsigned)(sms * per_sm);
+}
+
+template <bool ANY, bool COUNT>
+static int launch_batch_trace(RtScene* s, const RtRay* d_rays, size_t n, float4* raw, uint8_t* any, uint64_t* d_work, cudaStream_t st)
+{
+    if (n == 0) return RT_OK;
+    if (n >= 0xffffffffull) return rt_fail(RT_ERR_ARG, "ray batch too large (>= 2^32 rays)");
+    RT_CUDA(cudaMemsetAsync(s->d_cursor, 0, sizeof(uint32_t), st));
+    const uint32_t n32 = (uint32_t)n;
+    if (s->stack_cap <= 32)
+        k_trace_batch<32, ANY, COUNT><<<persistent_blocks((const void*)k_trace_batch<32, ANY, COUNT>, s->device), 128, 0, st>>>(s->d, d_rays, n32, raw, any, s->d_cursor, d_work);
+    else if (s->stack_cap <= 64)
+        k_trace_batch<64, ANY, COUNT><<<persistent_blocks((const void*)k_trace_batch<64, ANY, COUNT>, s->device), 128, 0, st>>>(s->d, d_rays, n32, raw, any, s->d_cursor, d_work);
+    else
+        k_trace_batch<104, ANY, COUNT><<<persistent_blocks((const void*)k_trace_batch<104, ANY, COUNT>, s->device), 128, 0, st>>>(s->d, d_rays, n32, raw, any, s->d_cursor, d_work);
+    RT_CUDA(cudaGetLastError());
+    return RT_OK;
 }
 
 template <bool COUNT, bool EX>
-static int launch_closest(RtScene* s, const RtRay* d_rays, size_t n, void* d_hits, uint64_t* d_work, cudaStream_t st)
+static int launch_closest(RtScene* s, const RtRay* d_rays, size_t n, void* d_hits, float4* d_raw, uint64_t* d_work, cudaStream_t st)
 {
     if (n == 0) return RT_OK;
+    int rc = launch_batch_trace<false, COUNT>(s, d_rays, n, d_raw, NULL, d_work, st);
+    if (rc != RT_OK) return rc;
     unsigned blocks = (unsigned)((n + 127) / 128);
-    if (s->stack_cap <= 32)       k_trace_closest<32, COUNT, EX><<<blocks, 128, 0, st>>>(s->d, d_rays, n, d_hits, d_work);
-    else if (s->stack_cap <= 64)  k_trace_closest<64, COUNT, EX><<<blocks, 128, 0, st>>>(s->d, d_rays, n, d_hits, d_work);
-    else                          k_trace_closest<104, COUNT, EX><<<blocks, 128, 0, st>>>(s->d, d_rays, n, d_hits, d_work);
+    k_finalize_batch<EX><<<blocks, 128, 0, st>>>(s->d, d_rays, (uint32_t)n, d_raw, d_hits);
     RT_CUDA(cudaGetLastError());
     return RT_OK;
 }
@@ -126,13 +172,7 @@ static int launch_closest(RtScene* s, const RtRay* d_rays, size_t n, void* d_hit
 template <bool COUNT>
 static int launch_any(RtScene* s, const RtRay* d_rays, size_t n, uint8_t* d_hits, uint64_t* d_work, cudaStream_t st)
 {
-    if (n == 0) return RT_OK;
-    unsigned blocks = (unsigned)((n + 127) / 128);
-    if (s->stack_cap <= 32)       k_trace_any<32, COUNT><<<blocks, 128, 0, st>>>(s->d, d_rays, n, d_hits, d_work);
-    else if (s->stack_cap <= 64)  k_trace_any<64, COUNT><<<blocks, 128, 0, st>>>(s->d, d_rays, n, d_hits, d_work);
-    else                          k_trace_any<104, COUNT><<<blocks, 128, 0, st>>>(s->d, d_rays, n, d_hits, d_work);
-    RT_CUDA(cudaGetLastError());
-    return RT_OK;
+    return launch_batch_trace<true, COUNT>(s, d_rays, n, NULL, d_hits, d_work, st);
 }
 
 static int ensure_scratch(RtScene* s, size_t in_bytes, size_t out_bytes)
@@ -190,6 +230,7 @@ int rt_scene_destroy(RtScene* s)
     if (s->scratch_in) cudaFree(s->scratch_in);
     if (s->scratch_out) cudaFree(s->scratch_out);
     if (s->d_work) cudaFree(s->d_work);
+    if (s->d_cursor) cudaFree(s->d_cursor);
     if (s->arena) cudaFree(s->arena);
     delete s;
     return RT_OK;
@@ -200,8 +241,10 @@ int rt_trace_closest_device(RtScene* s, const RtRay* d_rays, size_t n, RtHit* d_
     if (s == NULL || (n && (d_rays == NULL || d_hits == NULL))) return rt_fail(RT_ERR_ARG, "null argument");
     RT_CUDA(cudaSetDevice(s->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    return d_work ? launch_closest<true, false>(s, d_rays, n, d_hits, d_work, st)
-                  : launch_closest<false, false>(s, d_rays, n, d_hits, NULL, st);
+    // the raw (t, shape, record) result is written into d_hits itself and converted in place
+    float4* raw = reinterpret_cast<float4*>(d_hits);
+    return d_work ? launch_closest<true, false>(s, d_rays, n, d_hits, raw, d_work, st)
+                  : launch_closest<false, false>(s, d_rays, n, d_hits, raw, NULL, st);
 }
 
 int rt_trace_any_device(RtScene* s, const RtRay* d_rays, size_t n, uint8_t* d_hits, uint64_t* d_work, void* stream)
@@ -219,11 +262,14 @@ static int trace_closest_host(RtScene* s, const RtRay* rays, size_t n, void* hit
     if (n == 0) return RT_OK;
     RT_CUDA(cudaSetDevice(s->device));
     size_t out_bytes = n * (ex ? sizeof(RtHitEx) : sizeof(RtHit));
-    int rc = ensure_scratch(s, n * sizeof(RtRay), out_bytes);
+    // scratch_out holds the output records followed by the raw (t, shape, record) results
+    size_t raw_off = (out_bytes + 255) & ~(size_t)255;
+    int rc = ensure_scratch(s, n * sizeof(RtRay), raw_off + n * sizeof(float4));
     if (rc != RT_OK) return rc;
     RT_CUDA(cudaMemcpy(s->scratch_in, rays, n * sizeof(RtRay), cudaMemcpyHostToDevice));
-    rc = ex ? launch_closest<false, true>(s, static_cast<const RtRay*>(s->scratch_in), n, s->scratch_out, NULL, 0)
-            : launch_closest<false, false>(s, static_cast<const RtRay*>(s->scratch_in), n, s->scratch_out, NULL, 0);
+    float4* raw = reinterpret_cast<float4*>(static_cast<char*>(s->scratch_out) + raw_off);
+    rc = ex ? launch_closest<false, true>(s, static_cast<const RtRay*>(s->scratch_in), n, s->scratch_out, raw, NULL, 0)
+            : launch_closest<false, false>(s, static_cast<const RtRay*>(s->scratch_in), n, s->scratch_out, raw, NULL, 0);
     if (rc != RT_OK) return rc;
     RT_CUDA(cudaMemcpy(hits, s->scratch_out, out_bytes, cudaMemcpyDeviceToHost));
     return RT_OK;

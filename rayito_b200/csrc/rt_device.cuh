@@ -244,14 +244,60 @@ __device__ __forceinline__ TRS xform_eval(const DScene& sc, uint32_t xform, floa
     return r;
 }
 
+// Exact shortcuts.  Most transforms in a scene have an identity rotation and unit
+// scale (the ShapeSet itself, every translated-only shape), yet the reference still
+// runs q*v and the division for them.  Skipping that arithmetic is bit-identical
+// when it provably cannot change a bit:
+//   * dividing by exactly (1,1,1) returns the operand;
+//   * rotating by exactly (1; 0,0,0): t = 2 cross(qv, v) is a vector of signed
+//     zeros, so v + t*w + cross(qv, t) == v for every component of v that is not
+//     itself a zero (x + (+-0) == x).  A zero component may change sign (-0 -> +0,
+//     which flips 1/x and the traversal order), so those rays take the full path.
+// (Non-finite components are not shortcut-safe either; rays are finite.)
+__device__ __forceinline__ bool trs_identity_rotation(const TRS& x)
+{
+    return x.qw == 1.0f && x.qv.x == 0.0f && x.qv.y == 0.0f && x.qv.z == 0.0f;
+}
+__device__ __forceinline__ bool trs_unit_scale(const TRS& x)
+{
+    return x.s.x == 1.0f && x.s.y == 1.0f && x.s.z == 1.0f;
+}
+__device__ __forceinline__ bool no_zero_component(V3 v)
+{
+    return v.x != 0.0f && v.y != 0.0f && v.z != 0.0f;
+}
+
+__device__ __forceinline__ V3 rotate_exact(float qw, V3 qv, V3 v, bool identity)
+{
+    if (identity && no_zero_component(v))
+        return v;
+    return quat_rotate(qw, qv, v);
+}
+
 // Transform::toLocalPoint / toLocalVector (RMath.h:814-827)
-__device__ __forceinline__ V3 to_local_point(const TRS& x, V3 p) { return quat_rotate(x.qw, -x.qv, p - x.t) / x.s; }
-__device__ __forceinline__ V3 to_local_vector(const TRS& x, V3 v) { return quat_rotate(x.qw, -x.qv, v) / x.s; }
+__device__ __forceinline__ V3 to_local_point(const TRS& x, V3 p)
+{
+    V3 r = rotate_exact(x.qw, -x.qv, p - x.t, trs_identity_rotation(x));
+    return trs_unit_scale(x) ? r : r / x.s;
+}
+__device__ __forceinline__ V3 to_local_vector(const TRS& x, V3 v)
+{
+    V3 r = rotate_exact(x.qw, -x.qv, v, trs_identity_rotation(x));
+    return trs_unit_scale(x) ? r : r / x.s;
+}
 // fromLocalPoint / fromLocalVector / fromLocalNormal (RMath.h:819-842)
-__device__ __forceinline__ V3 from_local_point(const TRS& x, V3 p) { return quat_rotate(x.qw, x.qv, p * x.s) + x.t; }
-__device__ __forceinline__ V3 from_local_vector(const TRS& x, V3 v) { return quat_rotate(x.qw, x.qv, v * x.s); }
-__device__ __forceinline__ V3 from_local_normal(const TRS& x, V3 n) { return quat_rotate(x.qw, x.qv, n); }
-__device__ __forceinline__ V3 to_local_normal(const TRS& x, V3 n) { return quat_rotate(x.qw, -x.qv, n); }
+__device__ __forceinline__ V3 from_local_point(const TRS& x, V3 p)
+{
+    V3 v = trs_unit_scale(x) ? p : p * x.s;        // p * 1 == p
+    return rotate_exact(x.qw, x.qv, v, trs_identity_rotation(x)) + x.t;
+}
+__device__ __forceinline__ V3 from_local_vector(const TRS& x, V3 v)
+{
+    V3 w = trs_unit_scale(x) ? v : v * x.s;
+    return rotate_exact(x.qw, x.qv, w, trs_identity_rotation(x));
+}
+__device__ __forceinline__ V3 from_local_normal(const TRS& x, V3 n) { return rotate_exact(x.qw, x.qv, n, trs_identity_rotation(x)); }
+__device__ __forceinline__ V3 to_local_normal(const TRS& x, V3 n) { return rotate_exact(x.qw, -x.qv, n, trs_identity_rotation(x)); }
 
 // ---------------------------------------------------------------------------
 // Slab test (BBox::intersects, RAccel.h:47-59).  t0/t1 are clipped in place.

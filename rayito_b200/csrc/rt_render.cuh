@@ -27,13 +27,15 @@
 
 #include "rt_scene.cuh"
 #include "rt_shade.cuh"
+#include "rt_wave.cuh"
 
 #define RT_DEFAULT_TILE 32u
 #define RT_DEFAULT_BATCH (8u << 20)
 #define RT_MAX_DEPTH 16u
 #define RT_BLOCK 128
 
-enum { CTL_PATH_A = 0, CTL_PATH_B = 1, CTL_LIT = 2, CTL_SHADOW = 3, CTL_MIS = 4, CTL_WORDS = 8 };
+enum { CTL_PATH_A = 0, CTL_PATH_B = 1, CTL_LIT = 2, CTL_SHADOW = 3, CTL_MIS = 4,
+       CTL_CUR_PATH = 5, CTL_CUR_SHADOW = 6, CTL_CUR_MIS = 7, CTL_WORDS = 8 };
 
 // Device pointers and constants of one render call
 struct RenderCtx
@@ -239,6 +241,55 @@ k_camera_rays(const __grid_constant__ RenderCtx c, uint32_t psi, RtRay* out)
     out[(size_t)y * c.width + x] = r;
 }
 
+__device__ __forceinline__ void flush_work_counters(const WorkCount& wc, uint64_t* totals)
+{
+    uint32_t v[4] = { wc.node_pops, wc.tri_tests, wc.shape_tests, wc.xform_evals };
+    for (int k = 0; k < 4; ++k)
+    {
+        uint32_t x = v[k];
+        for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
+        if ((threadIdx.x & 31) == 0 && x)
+            atomicAdd(reinterpret_cast<unsigned long long*>(totals + 2 + k), (unsigned long long)x);
+    }
+}
+
+// Queue adaptors for the wave traversal (rt_wave.cuh)
+struct PathIO
+{
+    const uint32_t* queue;
+    const float4* ray_o;
+    const float4* ray_d;
+    float4* hit0;
+    __device__ __forceinline__ bool load(uint32_t j, V3& o, V3& d, float& tmax, float& time, uint32_t& tag) const
+    {
+        tag = queue[j];
+        float4 a = ray_o[tag], b = ray_d[tag];
+        o = xyz(a); d = xyz(b); tmax = RT_RAY_TMAX; time = a.w;
+        return true;
+    }
+    __device__ __forceinline__ void store(uint32_t tag, const WaveResult& r) const
+    {
+        hit0[tag] = make_float4(r.t, __int_as_float(r.shape), __int_as_float(r.tri_rec), 0.0f);
+    }
+};
+
+struct ShadowIO
+{
+    const uint32_t* queue;
+    const float4* pos_time;
+    const float4* sh_dir;
+    uint8_t* occluded;
+    __device__ __forceinline__ bool load(uint32_t j, V3& o, V3& d, float& tmax, float& time, uint32_t& tag) const
+    {
+        tag = queue[j];
+        float4 a = pos_time[tag], b = sh_dir[tag];
+        o = xyz(a); d = xyz(b); tmax = b.w; time = a.w;
+        return true;
+    }
+    __device__ __forceinline__ void store(uint32_t tag, const WaveResult& r) const { occluded[tag] = r.any_hit ? 1 : 0; }
+};
+
+// Path segments: closest hit (RaytraceMain.cpp:293-298)
 template <int CAP, bool COUNT>
 __global__ void __launch_bounds__(RT_BLOCK)
 k_trace_paths(const __grid_constant__ RenderCtx c, int cur)
@@ -251,32 +302,10 @@ k_trace_paths(const __grid_constant__ RenderCtx c, int cur)
         c.ctl[CTL_LIT] = 0;
     }
     WorkCount wc = { 0, 0, 0, 0 };
-    RT_GRID_STRIDE(j, n)
-    {
-        if (j < n)
-        {
-            uint32_t i = c.q_path[cur][j];
-            float4 ro = c.ray_o[i], rd = c.ray_d[i];
-            LocalRay r0;
-            ClosestHit h = trace_closest<CAP, COUNT>(c.sc, xyz(ro), xyz(rd), RT_RAY_TMAX, ro.w, r0, wc);
-            V3 nrm;
-            float cm;
-            hit_shading_inputs(c.sc, r0, ro.w, h, nrm, cm);
-            c.hit0[i] = make_float4(h.t, __int_as_float(h.shape), __int_as_float(h.tri_rec), 0.0f);
-            c.hit1[i] = make_float4(nrm.x, nrm.y, nrm.z, cm);
-        }
-    }
+    PathIO io = { c.q_path[cur], c.ray_o, c.ray_d, c.hit0 };
+    trace_wave<CAP, false, COUNT>(c.sc, io, n, c.ctl + CTL_CUR_PATH, wc);
     if (COUNT)
-    {
-        uint32_t v[4] = { wc.node_pops, wc.tri_tests, wc.shape_tests, wc.xform_evals };
-        for (int k = 0; k < 4; ++k)
-        {
-            uint32_t x = v[k];
-            for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
-            if ((threadIdx.x & 31) == 0 && x)
-                atomicAdd(reinterpret_cast<unsigned long long*>(c.totals + 2 + k), (unsigned long long)x);
-        }
-    }
+        flush_work_counters(wc, c.totals);
 }
 
 // pathTrace, one bounce, everything that does not need further rays
@@ -288,6 +317,9 @@ k_shade(const __grid_constant__ RenderCtx c, int cur, uint32_t bounce)
     {
         c.ctl[CTL_SHADOW] = 0;
         c.ctl[CTL_MIS] = 0;
+        c.ctl[CTL_CUR_SHADOW] = 0;
+        c.ctl[CTL_CUR_MIS] = 0;
+        c.ctl[CTL_CUR_PATH] = 0;
     }
     RT_GRID_STRIDE(j, n)
     {
@@ -300,7 +332,24 @@ k_shade(const __grid_constant__ RenderCtx c, int cur, uint32_t bounce)
             int shape = __float_as_int(h0.y);
             if (shape >= 0)
             {
-                float4 ro = c.ray_o[i], rd = c.ray_d[i], h1 = c.hit1[i], th = c.thr[i], rs = c.res[i];
+                float4 ro = c.ray_o[i], rd = c.ray_d[i], th = c.thr[i], rs = c.res[i];
+                // Intersection::m_normal / m_colorModifier of the winning hit, computed
+                // here where all 32 lanes are busy rather than in the traversal loop
+                float4 h1;
+                {
+                    ClosestHit h;
+                    h.t = h0.x; h.shape = shape; h.tri_rec = __float_as_int(h0.z);
+                    TRS set_trs = xform_eval(c.sc, c.sc.set_xform, ro.w);
+                    LocalRay r0;
+                    r0.o = to_local_point(set_trs, xyz(ro));
+                    r0.d = to_local_vector(set_trs, xyz(rd));
+                    r0.inv = r0.d; r0.neg = 0;
+                    V3 nrm;
+                    float cmod;
+                    hit_shading_inputs(c.sc, r0, ro.w, h, nrm, cmod);
+                    h1 = make_float4(nrm.x, nrm.y, nrm.z, cmod);
+                    c.hit1[i] = h1;
+                }
                 uint32_t state = __float_as_uint(th.w);
                 uint32_t nb = state & 0xffu, nd = (state >> 8) & 0xffu;
                 Color3 thr = rgb(th), result = rgb(rs);
@@ -446,6 +495,7 @@ k_light_sample(const __grid_constant__ RenderCtx c, uint32_t bounce, uint32_t ls
     }
 }
 
+// Shadow rays: any hit (RaytraceMain.cpp:394-395)
 template <int CAP, bool COUNT>
 __global__ void __launch_bounds__(RT_BLOCK)
 k_trace_shadow(const __grid_constant__ RenderCtx c)
@@ -454,28 +504,13 @@ k_trace_shadow(const __grid_constant__ RenderCtx c)
     if (blockIdx.x == 0 && threadIdx.x == 0)
         atomicAdd(reinterpret_cast<unsigned long long*>(c.totals + 1), (unsigned long long)n);
     WorkCount wc = { 0, 0, 0, 0 };
-    RT_GRID_STRIDE(j, n)
-    {
-        if (j < n)
-        {
-            uint32_t i = c.q_shadow[j];
-            float4 pt = c.pos_time[i], sd = c.sh_dir[i];
-            c.occluded[i] = trace_any<CAP, COUNT>(c.sc, xyz(pt), xyz(sd), sd.w, pt.w, wc) ? 1 : 0;
-        }
-    }
+    ShadowIO io = { c.q_shadow, c.pos_time, c.sh_dir, c.occluded };
+    trace_wave<CAP, true, COUNT>(c.sc, io, n, c.ctl + CTL_CUR_SHADOW, wc);
     if (COUNT)
-    {
-        uint32_t v[4] = { wc.node_pops, wc.tri_tests, wc.shape_tests, wc.xform_evals };
-        for (int k = 0; k < 4; ++k)
-        {
-            uint32_t x = v[k];
-            for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
-            if ((threadIdx.x & 31) == 0 && x)
-                atomicAdd(reinterpret_cast<unsigned long long*>(c.totals + 2 + k), (unsigned long long)x);
-        }
-    }
+        flush_work_counters(wc, c.totals);
 }
 
+// BSDF-sampled MIS probes: closest hit (RaytraceMain.cpp:422-423)
 template <int CAP, bool COUNT>
 __global__ void __launch_bounds__(RT_BLOCK)
 k_trace_mis(const __grid_constant__ RenderCtx c)
@@ -484,32 +519,10 @@ k_trace_mis(const __grid_constant__ RenderCtx c)
     if (blockIdx.x == 0 && threadIdx.x == 0)
         atomicAdd(reinterpret_cast<unsigned long long*>(c.totals + 0), (unsigned long long)n);
     WorkCount wc = { 0, 0, 0, 0 };
-    RT_GRID_STRIDE(j, n)
-    {
-        if (j < n)
-        {
-            uint32_t i = c.q_mis[j];
-            float4 pt = c.pos_time[i], md = c.mis_dir[i];
-            LocalRay r0;
-            ClosestHit h = trace_closest<CAP, COUNT>(c.sc, xyz(pt), xyz(md), RT_RAY_TMAX, pt.w, r0, wc);
-            V3 nrm;
-            float cm;
-            hit_shading_inputs(c.sc, r0, pt.w, h, nrm, cm);
-            c.mis_hit0[i] = make_float4(h.t, __int_as_float(h.shape), 0.0f, 0.0f);
-            c.mis_hit1[i] = make_float4(nrm.x, nrm.y, nrm.z, cm);
-        }
-    }
+    PathIO io = { c.q_mis, c.pos_time, c.mis_dir, c.mis_hit0 };
+    trace_wave<CAP, false, COUNT>(c.sc, io, n, c.ctl + CTL_CUR_MIS, wc);
     if (COUNT)
-    {
-        uint32_t v[4] = { wc.node_pops, wc.tri_tests, wc.shape_tests, wc.xform_evals };
-        for (int k = 0; k < 4; ++k)
-        {
-            uint32_t x = v[k];
-            for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
-            if ((threadIdx.x & 31) == 0 && x)
-                atomicAdd(reinterpret_cast<unsigned long long*>(c.totals + 2 + k), (unsigned long long)x);
-        }
-    }
+        flush_work_counters(wc, c.totals);
 }
 
 // Combine the two MIS samples of light sample `lsi` (:396-439) and, after the last
@@ -522,6 +535,8 @@ k_resolve(const __grid_constant__ RenderCtx c, uint32_t lsi)
     {
         c.ctl[CTL_SHADOW] = 0;      // refilled by the next light sample, if any
         c.ctl[CTL_MIS] = 0;
+        c.ctl[CTL_CUR_SHADOW] = 0;
+        c.ctl[CTL_CUR_MIS] = 0;
     }
     RT_GRID_STRIDE(j, n)
     {
@@ -539,9 +554,20 @@ k_resolve(const __grid_constant__ RenderCtx c, uint32_t lsi)
             uint32_t light_shape = __float_as_uint(mp.w);
             if (__float_as_int(mh0.y) == (int)light_shape)
             {
-                float4 pt = c.pos_time[i], mh1 = c.mis_hit1[i];
+                float4 pt = c.pos_time[i];
                 DShape lsh = load_shape(c.sc, light_shape);
-                float lpdf = light_intersect_pdf(c.sc, lsh, xyz(pt), xyz(md), pt.w, mh0.x, xyz(mh1));
+                // normal of the probe's hit (only needed once the probe found the light)
+                ClosestHit h;
+                h.t = mh0.x; h.shape = (int32_t)light_shape; h.tri_rec = __float_as_int(mh0.z);
+                TRS set_trs = xform_eval(c.sc, c.sc.set_xform, pt.w);
+                LocalRay r0;
+                r0.o = to_local_point(set_trs, xyz(pt));
+                r0.d = to_local_vector(set_trs, xyz(md));
+                r0.inv = r0.d; r0.neg = 0;
+                V3 hn;
+                float hcm;
+                hit_shading_inputs(c.sc, r0, pt.w, h, hn, hcm);
+                float lpdf = light_intersect_pdf(c.sc, lsh, xyz(pt), xyz(md), pt.w, mh0.x, hn);
                 if (lpdf > 0.0f)
                 {
                     float mis = power_heuristic(md.w, lpdf);
@@ -800,6 +826,32 @@ static int rt_launch_batch(RtScene* s, const RenderCtx& c, cudaStream_t st, uint
     cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, s->device);
     const unsigned wide = (unsigned)std::min<uint64_t>(((uint64_t)c.num_samples + RT_BLOCK - 1) / RT_BLOCK, (uint64_t)dev_sms * 32);
     const unsigned pix_blocks = (c.num_pixels + RT_BLOCK - 1) / RT_BLOCK;
+    // persistent traversal kernels: exactly as many blocks as can be resident
+    unsigned tg_path, tg_shadow, tg_mis;
+    {
+        int a = 4, b = 4, d = 4;
+        if (cap <= 32)
+        {
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_trace_paths<32, COUNT>, RT_BLOCK, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_trace_shadow<32, COUNT>, RT_BLOCK, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d, k_trace_mis<32, COUNT>, RT_BLOCK, 0);
+        }
+        else if (cap <= 64)
+        {
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_trace_paths<64, COUNT>, RT_BLOCK, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_trace_shadow<64, COUNT>, RT_BLOCK, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d, k_trace_mis<64, COUNT>, RT_BLOCK, 0);
+        }
+        else
+        {
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_trace_paths<104, COUNT>, RT_BLOCK, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_trace_shadow<104, COUNT>, RT_BLOCK, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d, k_trace_mis<104, COUNT>, RT_BLOCK, 0);
+        }
+        tg_path = (unsigned)(dev_sms * std::max(a, 1));
+        tg_shadow = (unsigned)(dev_sms * std::max(b, 1));
+        tg_mis = (unsigned)(dev_sms * std::max(d, 1));
+    }
 
     k_pixel_setup<<<pix_blocks, RT_BLOCK, 0, st>>>(c);
     k_raygen<<<wide, RT_BLOCK, 0, st>>>(c);
@@ -808,9 +860,9 @@ static int rt_launch_batch(RtScene* s, const RenderCtx& c, cudaStream_t st, uint
     for (uint32_t b = 0; b < c.depth; ++b)
     {
         rt_trace_mark(rb, timed, st);
-        if (cap <= 32)      k_trace_paths<32, COUNT><<<wide, RT_BLOCK, 0, st>>>(c, cur);
-        else if (cap <= 64) k_trace_paths<64, COUNT><<<wide, RT_BLOCK, 0, st>>>(c, cur);
-        else                k_trace_paths<104, COUNT><<<wide, RT_BLOCK, 0, st>>>(c, cur);
+        if (cap <= 32)      k_trace_paths<32, COUNT><<<tg_path, RT_BLOCK, 0, st>>>(c, cur);
+        else if (cap <= 64) k_trace_paths<64, COUNT><<<tg_path, RT_BLOCK, 0, st>>>(c, cur);
+        else                k_trace_paths<104, COUNT><<<tg_path, RT_BLOCK, 0, st>>>(c, cur);
         rt_trace_mark(rb, timed, st);
         trace_launches += 1;
         k_shade<<<wide, RT_BLOCK, 0, st>>>(c, cur, b);
@@ -819,9 +871,9 @@ static int rt_launch_batch(RtScene* s, const RenderCtx& c, cudaStream_t st, uint
         {
             k_light_sample<<<wide, RT_BLOCK, 0, st>>>(c, b, l);
             rt_trace_mark(rb, timed, st);
-            if (cap <= 32)      { k_trace_shadow<32, COUNT><<<wide, RT_BLOCK, 0, st>>>(c);  k_trace_mis<32, COUNT><<<wide, RT_BLOCK, 0, st>>>(c); }
-            else if (cap <= 64) { k_trace_shadow<64, COUNT><<<wide, RT_BLOCK, 0, st>>>(c);  k_trace_mis<64, COUNT><<<wide, RT_BLOCK, 0, st>>>(c); }
-            else                { k_trace_shadow<104, COUNT><<<wide, RT_BLOCK, 0, st>>>(c); k_trace_mis<104, COUNT><<<wide, RT_BLOCK, 0, st>>>(c); }
+            if (cap <= 32)      { k_trace_shadow<32, COUNT><<<tg_shadow, RT_BLOCK, 0, st>>>(c);  k_trace_mis<32, COUNT><<<tg_mis, RT_BLOCK, 0, st>>>(c); }
+            else if (cap <= 64) { k_trace_shadow<64, COUNT><<<tg_shadow, RT_BLOCK, 0, st>>>(c);  k_trace_mis<64, COUNT><<<tg_mis, RT_BLOCK, 0, st>>>(c); }
+            else                { k_trace_shadow<104, COUNT><<<tg_shadow, RT_BLOCK, 0, st>>>(c); k_trace_mis<104, COUNT><<<tg_mis, RT_BLOCK, 0, st>>>(c); }
             rt_trace_mark(rb, timed, st);
             trace_launches += 2;
             k_resolve<<<wide, RT_BLOCK, 0, st>>>(c, l);

@@ -41,6 +41,7 @@ struct RtScene
     void* scratch_out;
     size_t scratch_in_bytes, scratch_out_bytes;
     uint64_t* d_work;           // 4 counters
+    uint32_t* d_cursor;         // queue cursor of the ray-batch entry points
     struct RenderBuffers* render;   // wavefront state (rt_render.cuh), lazily created
 };
 
@@ -375,6 +376,7 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
     sc->scratch_in = sc->scratch_out = NULL;
     sc->scratch_in_bytes = sc->scratch_out_bytes = 0;
     sc->d_work = NULL;
+    sc->d_cursor = NULL;
     sc->render = NULL;
 
     cudaEvent_t e0, e1;
@@ -383,6 +385,7 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
     cudaError_t err = cudaMalloc(&sc->arena, sc->arena_bytes);
     if (err == cudaSuccess) err = cudaMalloc((void**)&sc->d_work, 4 * sizeof(uint64_t));
     if (err == cudaSuccess) err = cudaMemset(sc->d_work, 0, 4 * sizeof(uint64_t));
+    if (err == cudaSuccess) err = cudaMalloc((void**)&sc->d_cursor, 64);
     cudaEventRecord(e0, 0);
     if (err == cudaSuccess) err = cudaMemcpy(sc->arena, ab.bytes.data(), sc->arena_bytes, cudaMemcpyHostToDevice);
     cudaEventRecord(e1, 0);
@@ -395,6 +398,7 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
     {
         if (sc->arena) cudaFree(sc->arena);
         if (sc->d_work) cudaFree(sc->d_work);
+        if (sc->d_cursor) cudaFree(sc->d_cursor);
         delete sc;
         return rt_cuda_fail(err, "scene upload");
     }
