@@ -262,6 +262,25 @@ int rt_generate_camera_rays(RtScene* scene, const RtCamera* camera, const RtRend
 int rt_tonemap_bgra8(int device, const float* rgb, size_t num_pixels, float exposure_stops, float gamma,
                      uint8_t* bgra);
 
+/* ---- host-side pieces of the path (no device needed) ------------------------- */
+
+/* Tile partition used to shard one image over `world` ranks: owners[ty*tiles_x+tx] is
+ * the rank that renders that tile (tile_size 0 = library default).  Either count
+ * pointer may be NULL; owners may be NULL to query the counts only. */
+int rt_tile_owners(uint32_t width, uint32_t height, uint32_t tile_size, uint32_t world,
+                   uint32_t* owners, uint32_t* tiles_x, uint32_t* tiles_y, uint32_t* tile_size_used);
+
+/* The 5*depth+3 sampler permutations the reference draws for pixel (x, y)
+ * (RaytraceMain.cpp:69-108, 159-169), computed by MWC jump-ahead exactly as the
+ * device does.  out[5b+0..4] = bounce, light selection, light element, light, brdf of
+ * bounce b; out[5*depth+0..2] = time, lens, subpixel. */
+int rt_sample_permutations(uint32_t width, uint32_t height, uint32_t depth, uint32_t x, uint32_t y, uint32_t* out);
+
+/* CorrelatedMultiJitterSampler::sample1D / sample2D (RSampling.h:272-306), the same
+ * code the device compiles. */
+float rt_cmj_sample1d(uint32_t index, uint32_t samples, uint32_t permutation);
+void rt_cmj_sample2d(uint32_t index, uint32_t x_samples, uint32_t y_samples, uint32_t permutation, float* u, float* v);
+
 #ifdef __cplusplus
 }
 #endif

@@ -101,6 +101,7 @@ CORE_SYMBOLS = [
     "rt_trace_closest", "rt_trace_closest_ex", "rt_trace_any",
     "rt_trace_closest_device", "rt_trace_any_device",
     "rt_render", "rt_render_device", "rt_generate_camera_rays", "rt_tonemap_bgra8",
+    "rt_tile_owners", "rt_sample_permutations", "rt_cmj_sample1d", "rt_cmj_sample2d",
 ]
 HOST_SYMBOLS = [
     "rth_last_error_string", "rth_scene_create", "rth_scene_destroy", "rth_scene_desc",
@@ -131,6 +132,11 @@ def core():
                                          C.POINTER(RtRenderStats), vp]
         lib.rt_generate_camera_rays.argtypes = [vp, C.POINTER(RtCamera), C.POINTER(RtRenderParams), u32, vp]
         lib.rt_tonemap_bgra8.argtypes = [C.c_int, vp, sz, C.c_float, C.c_float, vp]
+        lib.rt_tile_owners.argtypes = [u32, u32, u32, u32, vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]
+        lib.rt_sample_permutations.argtypes = [u32, u32, u32, u32, u32, vp]
+        lib.rt_cmj_sample1d.restype = C.c_float
+        lib.rt_cmj_sample1d.argtypes = [u32, u32, u32]
+        lib.rt_cmj_sample2d.argtypes = [u32, u32, u32, u32, C.POINTER(C.c_float), C.POINTER(C.c_float)]
         _core = lib
     return _core
 
@@ -281,6 +287,21 @@ def tonemap_bgra8(rgb, exposure_stops=0.0, gamma=2.2, device=0):
     out = np.empty((n, 4), np.uint8)
     check(core().rt_tonemap_bgra8(device, rgb.ctypes.data, n, exposure_stops, gamma, out.ctypes.data), "rt_tonemap_bgra8")
     return out.reshape(rgb.shape[:-1] + (4,))
+
+
+def tile_owners(width, height, world, tile_size=0):
+    """(owners[tiles_y, tiles_x], tile size) of the screen-tile partition."""
+    tx, ty, ts = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    check(core().rt_tile_owners(width, height, tile_size, world, None, C.byref(tx), C.byref(ty), C.byref(ts)))
+    owners = np.zeros((ty.value, tx.value), np.uint32)
+    check(core().rt_tile_owners(width, height, tile_size, world, owners.ctypes.data, None, None, None))
+    return owners, ts.value
+
+
+def sample_permutations(width, height, depth, x, y):
+    out = np.zeros(5 * depth + 3, np.uint32)
+    check(core().rt_sample_permutations(width, height, depth, x, y, out.ctypes.data))
+    return out
 
 
 def make_rays(origins, directions, tmax=1.0e30, time=0.0):

@@ -315,6 +315,49 @@ int rt_generate_camera_rays(RtScene* s, const RtCamera* camera, const RtRenderPa
     return rt_camera_rays_impl(s, camera, params, psi, rays);
 }
 
+int rt_tile_owners(uint32_t width, uint32_t height, uint32_t tile_size, uint32_t world,
+                   uint32_t* owners, uint32_t* tiles_x, uint32_t* tiles_y, uint32_t* tile_size_used)
+{
+    if (width == 0 || height == 0 || world == 0)
+        return rt_fail(RT_ERR_ARG, "width, height and world must be positive");
+    uint32_t tile = tile_size ? tile_size : RT_DEFAULT_TILE;
+    uint32_t tx = (width + tile - 1) / tile, ty = (height + tile - 1) / tile;
+    if (tiles_x) *tiles_x = tx;
+    if (tiles_y) *tiles_y = ty;
+    if (tile_size_used) *tile_size_used = tile;
+    if (owners)
+    {
+        std::vector<uint32_t> mine;
+        for (uint32_t r = 0; r < world; ++r)
+        {
+            rt_detail::rank_tiles(tx, ty, r, world, mine);
+            for (size_t k = 0; k < mine.size(); ++k) owners[mine[k]] = r;
+        }
+    }
+    return RT_OK;
+}
+
+int rt_sample_permutations(uint32_t width, uint32_t height, uint32_t depth, uint32_t x, uint32_t y, uint32_t* out)
+{
+    if (out == NULL || width == 0 || height == 0 || x >= width || y >= height || depth > RT_MAX_DEPTH)
+        return rt_fail(RT_ERR_ARG, "bad argument");
+    ChunkGrid g = chunk_grid(width, height);
+    if (!chunk_covers(g, x, y))
+        return rt_fail(RT_ERR_ARG, "pixel lies outside every reference chunk (image narrower than 4 pixels): it is never rendered");
+    pixel_permutations(g, x, y, depth, out);
+    return RT_OK;
+}
+
+float rt_cmj_sample1d(uint32_t index, uint32_t samples, uint32_t permutation)
+{
+    return cmj_sample1d(index, samples, permutation);
+}
+
+void rt_cmj_sample2d(uint32_t index, uint32_t x_samples, uint32_t y_samples, uint32_t permutation, float* u, float* v)
+{
+    cmj_sample2d(index, x_samples, y_samples, permutation, *u, *v);
+}
+
 int rt_tonemap_bgra8(int device, const float* rgb, size_t num_pixels, float exposure_stops, float gamma, uint8_t* bgra)
 {
     return rt_tonemap_impl(device, rgb, num_pixels, exposure_stops, gamma, bgra);

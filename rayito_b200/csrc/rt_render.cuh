@@ -143,9 +143,20 @@ k_pixel_setup(const __grid_constant__ RenderCtx c)
         c.pix_xy[p] = 0xffffffffu;
         return;
     }
+    ChunkGrid g = chunk_grid(c.width, c.height);
+    if (!chunk_covers(g, x, y))
+    {
+        // never rendered by the reference: stays Image's default black
+        c.pix_xy[p] = 0xffffffffu;
+        if (c.image)
+        {
+            float* out = c.image + ((size_t)y * c.width + x) * 3;
+            out[0] = out[1] = out[2] = 0.0f;
+        }
+        return;
+    }
     c.pix_xy[p] = (y << 16) | x;
     uint32_t perm[5 * RT_MAX_DEPTH + 3];
-    ChunkGrid g = chunk_grid(c.width, c.height);
     pixel_permutations(g, x, y, c.depth, perm);
     uint32_t slots = 5 * c.depth + 3;
     for (uint32_t s = 0; s < slots; ++s)

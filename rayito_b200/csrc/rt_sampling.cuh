@@ -87,6 +87,14 @@ __host__ __device__ __forceinline__ ChunkGrid chunk_grid(uint32_t width, uint32_
     return g;
 }
 
+// QUIRK: for images narrower (or lower) than 4 pixels the reference makes at most two
+// one-pixel chunks per axis (RaytraceMain.cpp:508-516), so pixels beyond them are
+// never rendered and keep Image's default black.
+__host__ __device__ __forceinline__ bool chunk_covers(const ChunkGrid& g, uint32_t x, uint32_t y)
+{
+    return x < g.nx * g.cw && y < g.ny * g.ch;
+}
+
 // The 5*depth+3 permutations pixel (x, y) renders with.  out[] order:
 //   per bounce b: out[5b+0] bounce, +1 light selection, +2 light element, +3 light, +4 brdf
 //   then out[5D+0] time, out[5D+1] lens, out[5D+2] subpixel
