@@ -43,16 +43,40 @@ struct DNode
     float4 q1;
 };
 
-struct DShape            // 32 bytes, two 128-bit loads
+// Transform classes decided at upload (exactly, from the key values):
+//   GENERAL    anything
+//   TRANSLATE  every rotation key is exactly (1;0,0,0) and every scale key exactly
+//              (1,1,1): then rotation(t) and scaling(t) are exactly identity for
+//              EVERY t -- lerp(1,1,t) = fl(fl(1-t)+t) = 1 for t in [0,1], and the
+//              normalised lerp of identity quaternions is w/sqrt(w*w) = 1 -- so only
+//              translation(t) needs evaluating
+//   STATIC     TRANSLATE with at most one key: the translation is a constant, kept
+//              in the shape record itself
+#define RT_XF_GENERAL 0u
+#define RT_XF_TRANSLATE 1u
+#define RT_XF_STATIC 2u
+
+struct DShapeMem         // 32 bytes in HBM, two 128-bit loads
+{
+    uint32_t type_kind;  // RT_SHAPE_* | RT_XF_* << 8
+    uint32_t geom, xform, material;
+    int32_t light;
+    float tx, ty, tz;    // translation of a STATIC transform
+};
+
+struct DShape            // the same, decoded into registers (load_shape)
 {
     uint32_t type, geom, xform, material;
     int32_t light;
-    uint32_t pad0, pad1, pad2;
+    uint32_t xkind;
+    float tx, ty, tz;
 };
 
 struct DXform
 {
     uint32_t first_key, num_keys;
+    uint32_t kind;       // RT_XF_*
+    uint32_t pad;
 };
 
 struct DPlane            // 32 bytes
@@ -105,7 +129,7 @@ struct DScene
     uint32_t num_top_nodes;
     uint32_t num_lights;
 
-    const DShape* shapes;
+    const DShapeMem* shapes;
     const DNode* top_nodes;
     const DNode* mesh_nodes;
     const float4* tris;          // 3 per triangle
@@ -150,7 +174,9 @@ __device__ __forceinline__ float length3(V3 a) { return sqrtf(length2(a)); }
 
 // Vector::normalize (RMath.h:194): divide by the length when it is positive;
 // returns the old length through *len when asked.
-__device__ __forceinline__ V3 normalized3(V3 a, float* len = nullptr)
+// (out of line: one sqrt and three IEEE divisions, used at a dozen call sites of the
+// shading kernels)
+__device__ __noinline__ V3 normalized3(V3 a, float* len = nullptr)
 {
     float l = length3(a);
     if (len) *len = l;
@@ -175,7 +201,7 @@ struct TRS
 };
 
 // q * v = v + w*t + cross(qv, t), t = 2 cross(qv, v)   (RMath.h:536-549)
-__device__ __forceinline__ V3 quat_rotate(float qw, V3 qv, V3 v)
+__device__ __noinline__ V3 quat_rotate(float qw, V3 qv, V3 v)
 {
     V3 t = 2.0f * cross3(qv, v);
     return v + t * qw + cross3(qv, t);
@@ -204,7 +230,7 @@ __device__ __forceinline__ uint32_t xform_bracket(const float* __restrict__ time
 // translation(time), scaling(time), rotation(time) (RMath.h:681-715) evaluated
 // ONCE per (ray, shape); the reference re-evaluates them per use, but each is a
 // pure function of time so the values are the same.
-__device__ __forceinline__ TRS xform_eval(const DScene& sc, uint32_t xform, float time)
+__device__ __noinline__ TRS xform_eval(const DScene& sc, uint32_t xform, float time)
 {
     TRS r;
     DXform x = sc.xforms[xform];
@@ -214,6 +240,27 @@ __device__ __forceinline__ TRS xform_eval(const DScene& sc, uint32_t xform, floa
         r.s = mk(1.0f, 1.0f, 1.0f);
         r.qw = 1.0f;
         r.qv = mk(0.0f, 0.0f, 0.0f);
+        return r;
+    }
+    if (x.kind != RT_XF_GENERAL)
+    {
+        // translation-only transform: rotation(t) and scaling(t) are exactly identity
+        r.s = mk(1.0f, 1.0f, 1.0f);
+        r.qw = 1.0f;
+        r.qv = mk(0.0f, 0.0f, 0.0f);
+        if (x.num_keys == 1)
+        {
+            const float* T1 = sc.key_trans + 3 * x.first_key;
+            r.t = mk(T1[0], T1[1], T1[2]);
+            return r;
+        }
+        float m;
+        uint32_t k = x.first_key + xform_bracket(sc.key_time + x.first_key, x.num_keys, time, m);
+        const float* Tk = sc.key_trans + 3 * k;
+        if (m == 0.0f)
+            r.t = mk(Tk[0], Tk[1], Tk[2]);
+        else
+            r.t = mk(Tk[0], Tk[1], Tk[2]) * (1.0f - m) + mk(Tk[3], Tk[4], Tk[5]) * m;
         return r;
     }
     float mix;
@@ -274,16 +321,20 @@ __device__ __forceinline__ V3 rotate_exact(float qw, V3 qv, V3 v, bool identity)
     return quat_rotate(qw, qv, v);
 }
 
+// Component-wise division by a non-unit scale: rare, kept out of line so the three
+// IEEE division sequences exist once per kernel
+__device__ __noinline__ V3 scale_divide(V3 r, V3 s) { return r / s; }
+
 // Transform::toLocalPoint / toLocalVector (RMath.h:814-827)
 __device__ __forceinline__ V3 to_local_point(const TRS& x, V3 p)
 {
     V3 r = rotate_exact(x.qw, -x.qv, p - x.t, trs_identity_rotation(x));
-    return trs_unit_scale(x) ? r : r / x.s;
+    return trs_unit_scale(x) ? r : scale_divide(r, x.s);
 }
 __device__ __forceinline__ V3 to_local_vector(const TRS& x, V3 v)
 {
     V3 r = rotate_exact(x.qw, -x.qv, v, trs_identity_rotation(x));
-    return trs_unit_scale(x) ? r : r / x.s;
+    return trs_unit_scale(x) ? r : scale_divide(r, x.s);
 }
 // fromLocalPoint / fromLocalVector / fromLocalNormal (RMath.h:819-842)
 __device__ __forceinline__ V3 from_local_point(const TRS& x, V3 p)

@@ -28,6 +28,7 @@
 #include "rt_scene.cuh"
 #include "rt_shade.cuh"
 #include "rt_wave.cuh"
+#include "rt_split.cuh"
 
 #define RT_DEFAULT_TILE 32u
 #define RT_DEFAULT_BATCH (8u << 20)
@@ -35,7 +36,9 @@
 #define RT_BLOCK 128
 
 enum { CTL_PATH_A = 0, CTL_PATH_B = 1, CTL_LIT = 2, CTL_SHADOW = 3, CTL_MIS = 4,
-       CTL_CUR_PATH = 5, CTL_CUR_SHADOW = 6, CTL_CUR_MIS = 7, CTL_WORDS = 8 };
+       CTL_CUR_PATH = 5, CTL_CUR_SHADOW = 6, CTL_CUR_MIS = 7,
+       // split traversal: mesh / resume queue counts and cursors, double buffered
+       CTL_MESH_N = 8, CTL_MESH_CUR = 10, CTL_RES_N = 12, CTL_RES_CUR = 14, CTL_WORDS = 16 };
 
 // Device pointers and constants of one render call
 struct RenderCtx
@@ -75,6 +78,9 @@ struct RenderCtx
     uint32_t* q_lit;
     uint32_t* q_shadow;
     uint32_t* q_mis;
+    uint32_t* q_meshq[2];       // split traversal: slots waiting for a mesh pass
+    uint32_t* q_resume[2];      // ... for a top-level resume pass
+    SplitBufs split;            // suspended-ray state
     uint32_t* ctl;              // CTL_WORDS queue counters
     uint64_t* totals;           // 0 closest rays, 1 any rays, 2..5 work counters
     float* image;               // width*height*3
@@ -317,6 +323,31 @@ k_trace_paths(const __grid_constant__ RenderCtx c, int cur)
     trace_wave<CAP, false, COUNT>(c.sc, io, n, c.ctl + CTL_CUR_PATH, wc);
     if (COUNT)
         flush_work_counters(wc, c.totals);
+}
+
+// ---- split traversal kernels (rt_split.cuh) ---------------------------------
+template <bool ANY, bool COUNT, bool FRESH, class IO>
+__global__ void __launch_bounds__(RT_BLOCK)
+k_split_top(const __grid_constant__ DScene sc, const IO io, const SplitBufs sb, const SplitPass ps, uint64_t* totals, int count_slot)
+{
+    split_zero(ps);
+    if (FRESH && count_slot >= 0 && blockIdx.x == 0 && threadIdx.x == 0)
+        atomicAdd(reinterpret_cast<unsigned long long*>(totals + count_slot), (unsigned long long)*ps.in_count);
+    WorkCount wc = { 0, 0, 0, 0 };
+    trace_top<ANY, COUNT, FRESH>(sc, io, sb, ps, wc);
+    if (COUNT)
+        flush_work_counters(wc, totals);
+}
+
+template <int CAP, bool ANY, bool COUNT, class IO>
+__global__ void __launch_bounds__(RT_BLOCK)
+k_split_mesh(const __grid_constant__ DScene sc, const IO io, const SplitBufs sb, const SplitPass ps, uint64_t* totals)
+{
+    split_zero(ps);
+    WorkCount wc = { 0, 0, 0, 0 };
+    trace_mesh<CAP, ANY, COUNT>(sc, io, sb, ps, wc);
+    if (COUNT)
+        flush_work_counters(wc, totals);
 }
 
 // pathTrace, one bounce, everything that does not need further rays
@@ -719,6 +750,16 @@ inline size_t carve(RenderCtx& c, char* base, size_t samples, size_t pixels, uin
     c.q_lit = k.take<uint32_t>(samples);
     c.q_shadow = k.take<uint32_t>(samples);
     c.q_mis = k.take<uint32_t>(samples);
+    c.q_meshq[0] = k.take<uint32_t>(samples);
+    c.q_meshq[1] = k.take<uint32_t>(samples);
+    c.q_resume[0] = k.take<uint32_t>(samples);
+    c.q_resume[1] = k.take<uint32_t>(samples);
+    c.split.ray_o = k.take<float4>(samples);
+    c.split.ray_d = k.take<float4>(samples);
+    c.split.hit = k.take<float4>(samples);
+    c.split.stack = k.take<float4>(samples * RT_SPLIT_TOPCAP);
+    c.split.mesh_o = k.take<float4>(samples);
+    c.split.mesh_d = k.take<float4>(samples);
     c.ctl = k.take<uint32_t>(CTL_WORDS);
     c.totals = k.take<uint64_t>(8);
     return k.off + 256;
@@ -828,8 +869,61 @@ inline void rt_trace_mark(RenderBuffers* rb, bool timed, cudaStream_t st)
     cudaEventRecord((*rb->trace_events)[rb->trace_events_used++], st);
 }
 
+// One traversal stage in split mode: fresh top-level pass, then (mesh pass, resume
+// pass) once per mesh shape of the scene.  Counts live on the device; passes with an
+// empty queue exit at once.
+template <bool ANY, bool COUNT, class IO>
+static void rt_launch_split_stage(RtScene* s, const RenderCtx& c, const IO& io, const uint32_t* fresh_count,
+                                  uint32_t* fresh_cursor, int count_slot, unsigned grid, cudaStream_t st, uint64_t& launches)
+{
+    cudaMemsetAsync(c.ctl + CTL_MESH_N, 0, 8 * sizeof(uint32_t), st);
+    SplitPass p;
+    p.in_queue = NULL;
+    p.in_count = fresh_count;
+    p.cursor = fresh_cursor;
+    p.out_queue = c.q_meshq[0];
+    p.out_count = c.ctl + CTL_MESH_N + 0;
+    p.zero[0] = p.zero[1] = p.zero[2] = p.zero[3] = NULL;
+    k_split_top<ANY, COUNT, true, IO><<<grid, RT_BLOCK, 0, st>>>(c.sc, io, c.split, p, c.totals, count_slot);
+    launches += 1;
+    const bool deep = s->mesh_stack_need > 32;
+    for (uint32_t k = 0; k < s->num_mesh_shapes; ++k)
+    {
+        const int a = (int)(k & 1), b = (int)((k + 1) & 1);
+        SplitPass m;
+        m.in_queue = c.q_meshq[a];
+        m.in_count = c.ctl + CTL_MESH_N + a;
+        m.cursor = c.ctl + CTL_MESH_CUR + a;
+        m.out_queue = c.q_resume[a];
+        m.out_count = c.ctl + CTL_RES_N + a;
+        m.zero[0] = c.ctl + CTL_MESH_N + b;
+        m.zero[1] = c.ctl + CTL_MESH_CUR + b;
+        m.zero[2] = m.zero[3] = NULL;
+        if (deep) k_split_mesh<64, ANY, COUNT, IO><<<grid, RT_BLOCK, 0, st>>>(c.sc, io, c.split, m, c.totals);
+        else      k_split_mesh<32, ANY, COUNT, IO><<<grid, RT_BLOCK, 0, st>>>(c.sc, io, c.split, m, c.totals);
+        SplitPass r;
+        r.in_queue = c.q_resume[a];
+        r.in_count = c.ctl + CTL_RES_N + a;
+        r.cursor = c.ctl + CTL_RES_CUR + a;
+        r.out_queue = c.q_meshq[b];
+        r.out_count = c.ctl + CTL_MESH_N + b;
+        r.zero[0] = c.ctl + CTL_RES_N + b;
+        r.zero[1] = c.ctl + CTL_RES_CUR + b;
+        r.zero[2] = r.zero[3] = NULL;
+        k_split_top<ANY, COUNT, false, IO><<<grid, RT_BLOCK, 0, st>>>(c.sc, io, c.split, r, c.totals, -1);
+        launches += 2;
+    }
+}
+
+// Small kernel that does the queue bookkeeping k_trace_paths does in unified mode
+__global__ void k_stage_prologue(const __grid_constant__ RenderCtx c, int cur)
+{
+    c.ctl[cur ^ 1] = 0;
+    c.ctl[CTL_LIT] = 0;
+}
+
 template <bool COUNT>
-static int rt_launch_batch(RtScene* s, const RenderCtx& c, cudaStream_t st, uint64_t& launches, bool timed, uint64_t& trace_launches)
+static int rt_launch_batch(RtScene* s, const RenderCtx& c, cudaStream_t st, uint64_t& launches, bool timed, uint64_t& trace_launches, bool split)
 {
     RenderBuffers* rb = s->render;
     const int cap = s->stack_cap;
@@ -863,6 +957,14 @@ static int rt_launch_batch(RtScene* s, const RenderCtx& c, cudaStream_t st, uint
         tg_shadow = (unsigned)(dev_sms * std::max(b, 1));
         tg_mis = (unsigned)(dev_sms * std::max(d, 1));
     }
+    // split kernels are lighter; size their persistent grid from the heaviest of them
+    unsigned tg_split;
+    {
+        int a = 4, b = 4;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_split_top<false, COUNT, true, PathIO>, RT_BLOCK, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_split_mesh<64, false, COUNT, PathIO>, RT_BLOCK, 0);
+        tg_split = (unsigned)(dev_sms * std::max(std::min(a, b), 1));
+    }
 
     k_pixel_setup<<<pix_blocks, RT_BLOCK, 0, st>>>(c);
     k_raygen<<<wide, RT_BLOCK, 0, st>>>(c);
@@ -871,22 +973,48 @@ static int rt_launch_batch(RtScene* s, const RenderCtx& c, cudaStream_t st, uint
     for (uint32_t b = 0; b < c.depth; ++b)
     {
         rt_trace_mark(rb, timed, st);
-        if (cap <= 32)      k_trace_paths<32, COUNT><<<tg_path, RT_BLOCK, 0, st>>>(c, cur);
-        else if (cap <= 64) k_trace_paths<64, COUNT><<<tg_path, RT_BLOCK, 0, st>>>(c, cur);
-        else                k_trace_paths<104, COUNT><<<tg_path, RT_BLOCK, 0, st>>>(c, cur);
+        if (split)
+        {
+            uint64_t before = launches;
+            k_stage_prologue<<<1, 1, 0, st>>>(c, cur);
+            PathIO io = { c.q_path[cur], c.ray_o, c.ray_d, c.hit0 };
+            rt_launch_split_stage<false, COUNT>(s, c, io, c.ctl + cur, c.ctl + CTL_CUR_PATH, 0, tg_split, st, launches);
+            launches += 1;
+            trace_launches += launches - before;
+            launches -= 1;      // the shared "+= 2" below accounts for trace + shade
+        }
+        else
+        {
+            if (cap <= 32)      k_trace_paths<32, COUNT><<<tg_path, RT_BLOCK, 0, st>>>(c, cur);
+            else if (cap <= 64) k_trace_paths<64, COUNT><<<tg_path, RT_BLOCK, 0, st>>>(c, cur);
+            else                k_trace_paths<104, COUNT><<<tg_path, RT_BLOCK, 0, st>>>(c, cur);
+            trace_launches += 1;
+        }
         rt_trace_mark(rb, timed, st);
-        trace_launches += 1;
         k_shade<<<wide, RT_BLOCK, 0, st>>>(c, cur, b);
         launches += 2;
         for (uint32_t l = 0; l < c.nls; ++l)
         {
             k_light_sample<<<wide, RT_BLOCK, 0, st>>>(c, b, l);
             rt_trace_mark(rb, timed, st);
-            if (cap <= 32)      { k_trace_shadow<32, COUNT><<<tg_shadow, RT_BLOCK, 0, st>>>(c);  k_trace_mis<32, COUNT><<<tg_mis, RT_BLOCK, 0, st>>>(c); }
-            else if (cap <= 64) { k_trace_shadow<64, COUNT><<<tg_shadow, RT_BLOCK, 0, st>>>(c);  k_trace_mis<64, COUNT><<<tg_mis, RT_BLOCK, 0, st>>>(c); }
-            else                { k_trace_shadow<104, COUNT><<<tg_shadow, RT_BLOCK, 0, st>>>(c); k_trace_mis<104, COUNT><<<tg_mis, RT_BLOCK, 0, st>>>(c); }
+            if (split)
+            {
+                uint64_t before = launches;
+                ShadowIO sio = { c.q_shadow, c.pos_time, c.sh_dir, c.occluded };
+                rt_launch_split_stage<true, COUNT>(s, c, sio, c.ctl + CTL_SHADOW, c.ctl + CTL_CUR_SHADOW, 1, tg_split, st, launches);
+                PathIO mio = { c.q_mis, c.pos_time, c.mis_dir, c.mis_hit0 };
+                rt_launch_split_stage<false, COUNT>(s, c, mio, c.ctl + CTL_MIS, c.ctl + CTL_CUR_MIS, 0, tg_split, st, launches);
+                trace_launches += launches - before;
+                launches -= 2;  // the shared "+= 4" below accounts for two traces
+            }
+            else
+            {
+                if (cap <= 32)      { k_trace_shadow<32, COUNT><<<tg_shadow, RT_BLOCK, 0, st>>>(c);  k_trace_mis<32, COUNT><<<tg_mis, RT_BLOCK, 0, st>>>(c); }
+                else if (cap <= 64) { k_trace_shadow<64, COUNT><<<tg_shadow, RT_BLOCK, 0, st>>>(c);  k_trace_mis<64, COUNT><<<tg_mis, RT_BLOCK, 0, st>>>(c); }
+                else                { k_trace_shadow<104, COUNT><<<tg_shadow, RT_BLOCK, 0, st>>>(c); k_trace_mis<104, COUNT><<<tg_mis, RT_BLOCK, 0, st>>>(c); }
+                trace_launches += 2;
+            }
             rt_trace_mark(rb, timed, st);
-            trace_launches += 2;
             k_resolve<<<wide, RT_BLOCK, 0, st>>>(c, l);
             launches += 4;
         }
@@ -959,6 +1087,9 @@ inline int rt_render_impl(RtScene* s, const RtCamera* camera, const RtRenderPara
 
     const bool count = (prm->flags & RT_RENDER_COUNT_WORK) != 0;
     const bool timed = (prm->flags & RT_RENDER_TIME_TRACE) != 0;
+    const bool split = (prm->flags & RT_RENDER_UNIFIED_TRAVERSAL) == 0 && s->num_mesh_shapes >= 1 &&
+                       s->num_mesh_shapes <= RT_SPLIT_MAX_MESHES && s->top_stack_need <= RT_SPLIT_TOPCAP &&
+                       s->mesh_stack_need <= 64;
     rb->trace_events_used = 0;
     uint64_t launches = 0, trace_launches = 0;
     uint64_t samples = 0;
@@ -968,8 +1099,8 @@ inline int rt_render_impl(RtScene* s, const RtCamera* camera, const RtRenderPara
         c.tile_ids = rb->d_tile_ids + t0;
         c.num_pixels = (uint32_t)(nt * plan.tile * plan.tile);
         c.num_samples = c.num_pixels * plan.spp;
-        rc = count ? rt_launch_batch<true>(s, c, st, launches, timed, trace_launches)
-                   : rt_launch_batch<false>(s, c, st, launches, timed, trace_launches);
+        rc = count ? rt_launch_batch<true>(s, c, st, launches, timed, trace_launches, split)
+                   : rt_launch_batch<false>(s, c, st, launches, timed, trace_launches, split);
         if (rc != RT_OK) return rc;
     }
     RT_CUDA(cudaEventRecord(rb->ev[2], st));

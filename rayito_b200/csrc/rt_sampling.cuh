@@ -212,9 +212,18 @@ __host__ __device__ __forceinline__ void cmj_sample2d(uint32_t index, uint32_t x
 // rounded but for ~1e-9 of inputs).  Remaining last-bit disagreements with glibc
 // are why Monte-Carlo images carry an RMSE bar rather than a bit-exact one.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ float ref_cosf(float x) { return (float)cos((double)x); }
-__device__ __forceinline__ float ref_sinf(float x) { return (float)sin((double)x); }
-__device__ __forceinline__ float ref_powf(float x, float y) { return (float)pow((double)x, (double)y); }
+// Out of line: the double-precision bodies are hundreds of instructions each and
+// would otherwise be inlined at every call site (k_light_sample was 94 KB of SASS).
+__device__ __noinline__ void ref_sincosf(float x, float& s, float& c)
+{
+    double ds, dc;
+    sincos((double)x, &ds, &dc);
+    s = (float)ds;
+    c = (float)dc;
+}
+__device__ __forceinline__ float ref_cosf(float x) { float s, c; ref_sincosf(x, s, c); return c; }
+__device__ __forceinline__ float ref_sinf(float x) { float s, c; ref_sincosf(x, s, c); return s; }
+__device__ __noinline__ float ref_powf(float x, float y) { return (float)pow((double)x, (double)y); }
 
 // Vector(0,1,0)-or-(1,0,0) frame around a direction (RMath.h:946-955)
 __device__ __forceinline__ void make_frame(V3 ref, V3& x, V3& y, V3& z)
@@ -273,8 +282,10 @@ __device__ __forceinline__ void concentric_disk(float u1, float u2, float& dx, f
         }
     }
     theta = (float)((double)theta * (RT_PI_D / 4.0));      // theta *= M_PI / 4.0f, in double
-    dx = r * ref_cosf(theta);
-    dy = r * ref_sinf(theta);
+    float sn, cs;
+    ref_sincosf(theta, sn, cs);
+    dx = r * cs;
+    dy = r * sn;
 }
 
 // uniformToCosineHemisphere (RSampling.h:500-508)
@@ -292,7 +303,9 @@ __device__ __forceinline__ V3 uniform_sphere(float u1, float u2)
     float z = 1.0f - 2.0f * u1;
     float radius = sqrtf(std_max(0.0f, 1.0f - z * z));
     float phi = (float)((RT_PI_D * 2.0) * (double)u2);     // M_PI * 2.0f * u2
-    return mk(radius * ref_cosf(phi), radius * ref_sinf(phi), z);
+    float sn, cs;
+    ref_sincosf(phi, sn, cs);
+    return mk(radius * cs, radius * sn, z);
 }
 
 // uniformToCone / uniformConePdf (RSampling.h:512-523)
@@ -301,7 +314,9 @@ __device__ __forceinline__ V3 uniform_cone(float u1, float u2, float cos_theta_m
     float cos_theta = u1 * (cos_theta_max - 1.0f) + 1.0f;
     float sin_theta = sqrtf(std_max(0.0f, 1.0f - cos_theta * cos_theta));
     float phi = (float)(((double)u2 * RT_PI_D) * 2.0);     // u2 * M_PI * 2.0f
-    return mk(ref_cosf(phi) * sin_theta, ref_sinf(phi) * sin_theta, cos_theta);
+    float sn, cs;
+    ref_sincosf(phi, sn, cs);
+    return mk(cs * sin_theta, sn * sin_theta, cos_theta);
 }
 
 __device__ __forceinline__ float uniform_cone_pdf(float cos_theta_max)
@@ -317,8 +332,10 @@ __device__ __forceinline__ void uniform_disk(float u1, float u2, float& dx, floa
 {
     float radius = sqrtf(u1);
     float theta = (float)((RT_PI_D * 2.0) * (double)u2);
-    dx = radius * ref_cosf(theta);
-    dy = radius * ref_sinf(theta);
+    float sn, cs;
+    ref_sincosf(theta, sn, cs);
+    dx = radius * cs;
+    dy = radius * sn;
 }
 
 // uniformToBarycentricTriangle (RSampling.h:527-532)

@@ -32,6 +32,9 @@ struct RtScene
     size_t arena_bytes;
     DScene d;                   // device pointers into the arena
     int stack_cap;              // traversal stack entries needed (both levels)
+    int top_stack_need;         // ... by the top level alone
+    int mesh_stack_need;        // ... by the deepest mesh alone
+    uint32_t num_mesh_shapes;   // finite shapes that are meshes (max suspensions per ray)
     uint32_t num_tris;
     uint32_t num_faces;
     std::vector<uint32_t> light_shapes;
@@ -139,7 +142,28 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
     }
 
     // Shapes
-    std::vector<DShape> shapes(num_shapes);
+    // Classify transforms (rt_device.cuh RT_XF_*): exact comparisons on the key values
+    std::vector<uint32_t> xf_kind(desc->num_xforms, RT_XF_GENERAL);
+    for (uint32_t i = 0; i < desc->num_xforms; ++i)
+    {
+        const RtXform& x = desc->xforms[i];
+        bool translate_only = true;
+        for (uint32_t k = x.first_key; k < x.first_key + x.num_keys; ++k)
+        {
+            const float* r = desc->key_rotation + 4 * (size_t)k;
+            const float* sc3 = desc->key_scale + 3 * (size_t)k;
+            // +0 only: a -0 component would not behave like the keyless identity
+            uint32_t bits[3];
+            std::memcpy(bits, r + 1, 12);
+            if (!(r[0] == 1.0f && bits[0] == 0 && bits[1] == 0 && bits[2] == 0 &&
+                  sc3[0] == 1.0f && sc3[1] == 1.0f && sc3[2] == 1.0f))
+                translate_only = false;
+        }
+        if (translate_only)
+            xf_kind[i] = x.num_keys <= 1 ? RT_XF_STATIC : RT_XF_TRANSLATE;
+    }
+
+    std::vector<DShapeMem> shapes(num_shapes);
     for (uint32_t i = 0; i < num_shapes; ++i)
     {
         const RtShape& s = desc->shapes[i];
@@ -153,9 +177,15 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
             return rt_fail(RT_ERR_ARG, "planes must be the infinite shapes and only they");
         if (s.light >= (int32_t)desc->num_lights)
             return rt_fail(RT_ERR_ARG, "shape light index out of range");
-        DShape d;
+        DShapeMem d;
         std::memset(&d, 0, sizeof(d));
-        d.type = s.type; d.geom = s.geom; d.xform = s.xform; d.material = s.material; d.light = s.light;
+        d.type_kind = s.type | (xf_kind[s.xform] << 8);
+        d.geom = s.geom; d.xform = s.xform; d.material = s.material; d.light = s.light;
+        if (xf_kind[s.xform] == RT_XF_STATIC && desc->xforms[s.xform].num_keys == 1)
+        {
+            const float* t = desc->key_translation + 3 * (size_t)desc->xforms[s.xform].first_key;
+            d.tx = t[0]; d.ty = t[1]; d.tz = t[2];
+        }
         shapes[i] = d;
     }
     for (uint32_t l = 0; l < desc->num_lights; ++l)
@@ -331,11 +361,13 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
     {
         xforms[i].first_key = desc->xforms[i].first_key;
         xforms[i].num_keys = desc->xforms[i].num_keys;
+        xforms[i].kind = xf_kind[i];
+        xforms[i].pad = 0;
     }
 
     // One arena, one copy
     ArenaBuilder ab;
-    size_t o_shapes = ab.put(shapes.data(), shapes.size() * sizeof(DShape));
+    size_t o_shapes = ab.put(shapes.data(), shapes.size() * sizeof(DShapeMem));
     size_t o_top = ab.put(top_nodes.data(), top_nodes.size() * sizeof(DNode));
     size_t o_mnodes = ab.put(mesh_nodes.data(), mesh_nodes.size() * sizeof(DNode));
     size_t o_tris = ab.put(tris.data(), tris.size() * sizeof(float4));
@@ -370,6 +402,11 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
     sc->arena = NULL;
     sc->arena_bytes = ab.bytes.size();
     sc->stack_cap = stack_cap;
+    sc->top_stack_need = desc->num_top_nodes ? top_depth + 1 : (int)desc->num_finite;
+    sc->mesh_stack_need = mesh_depth >= 0 ? mesh_depth + 1 : 0;
+    sc->num_mesh_shapes = 0;
+    for (uint32_t i = 0; i < desc->num_finite; ++i)
+        if (desc->shapes[i].type == RT_SHAPE_MESH) sc->num_mesh_shapes++;
     sc->num_tris = num_tris;
     sc->num_faces = desc->num_faces;
     sc->light_shapes.assign(desc->lights, desc->lights + desc->num_lights);
@@ -410,7 +447,7 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
     d.num_infinite = desc->num_infinite;
     d.num_top_nodes = desc->num_top_nodes;
     d.num_lights = desc->num_lights;
-    d.shapes = reinterpret_cast<const DShape*>(base + o_shapes);
+    d.shapes = reinterpret_cast<const DShapeMem*>(base + o_shapes);
     d.top_nodes = reinterpret_cast<const DNode*>(base + o_top);
     d.mesh_nodes = reinterpret_cast<const DNode*>(base + o_mnodes);
     d.tris = reinterpret_cast<const float4*>(base + o_tris);

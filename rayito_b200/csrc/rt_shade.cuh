@@ -95,7 +95,9 @@ __device__ __forceinline__ float brdf_sample(uint32_t brdf, float exponent, V3& 
         float cos_theta = ref_powf(1.0f - u2, 1.0f / (exponent + 1.0f));
         float sin2_theta = std_max(0.0f, 1.0f - cos_theta * cos_theta);
         float sin_theta = sqrtf(sin2_theta);
-        V3 local_half = mk(sin_theta * ref_cosf(phi), sin_theta * ref_sinf(phi), cos_theta);
+        float sn, cs;
+        ref_sincosf(phi, sn, cs);
+        V3 local_half = mk(sin_theta * cs, sin_theta * sn, cos_theta);
         V3 x, y, z;
         make_frame(normal, x, y, z);
         V3 half = frame_to_world(local_half, x, y, z);
@@ -134,7 +136,7 @@ __device__ __forceinline__ void light_sample(const DScene& sc, const DShape& sh,
     out_pdf = 0.0f;
     out_pos = mk(0.0f, 0.0f, 0.0f);
     out_normal = mk(0.0f, 0.0f, 0.0f);
-    TRS trs = xform_eval(sc, sh.xform, ref_time);
+    TRS trs = shape_xform(sc, sh, ref_time);
     if (sh.type == RT_SHAPE_RECT)
     {
         // RLight.h:186-218
@@ -188,7 +190,7 @@ __device__ __forceinline__ void light_sample(const DScene& sc, const DShape& sh,
         // The probe ray is built with time 0 (Ray's default), pushed out of local
         // space and straight back in by Sphere::intersect -- at time 0, not at the
         // sample's time (RScene.h:562-565, RRay.h:57).  Reproduced literally.
-        TRS trs0 = xform_eval(sc, sh.xform, 0.0f);
+        TRS trs0 = shape_xform(sc, sh, 0.0f);
         V3 wo = from_local_point(trs0, local_ref);
         V3 wd = from_local_vector(trs0, cone);
         V3 lo = to_local_point(trs0, wo) - centre;
@@ -265,7 +267,7 @@ __device__ __forceinline__ void light_sample(const DScene& sc, const DShape& sh,
 __device__ __forceinline__ float light_intersect_pdf(const DScene& sc, const DShape& sh, V3 ray_o, V3 ray_d, float time,
                                                      float t, V3 hit_normal)
 {
-    TRS trs = xform_eval(sc, sh.xform, time);
+    TRS trs = shape_xform(sc, sh, time);
     if (sh.type == RT_SHAPE_RECT)
     {
         DRect rc = sc.rects[sh.geom];

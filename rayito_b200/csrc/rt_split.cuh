@@ -1,0 +1,566 @@
+// Split two-level traversal: top-level passes and mesh passes as separate
+// warp-persistent kernels.
+//
+// The unified wave kernel (rt_wave.cuh) still mixed two very different kinds of
+// work in one warp: short top-level walks (5 pops, 2-3 analytic shapes with their
+// keyed-transform warps) and long face-BVH walks inside a mesh (tens of pops and
+// triangle tests).  ncu showed 6-10 of 32 lanes active: the few lanes deep inside a
+// mesh dragged every scheduling round while the short rays came and went.
+//
+// Here a ray that reaches a mesh leaf of the top-level tree is SUSPENDED: its set-
+// local ray, current m_t / winner and its (tiny) top-level stack are written to
+// per-slot arrays and its slot is queued for a mesh pass.  A mesh pass warps the
+// ray into mesh-local space at the ray's time, walks the face BVH with
+// [kRayTMin, m_t] exactly as Mesh::intersect does (RMesh.h:62-81), updates m_t and
+// queues the slot for a resume pass, which reloads the stack and continues the
+// top-level walk where it stopped.  A mesh is one leaf of the top-level tree, so a
+// ray suspends at most once per mesh: 1 + 2*M passes cover every ray.
+//
+// Per-ray pop order, (t0,t1) inheritance, culling against the current m_t and
+// acceptance tests are untouched -- a suspended ray sees exactly the state it would
+// have had -- so results stay bit-identical to the unified kernel and to the
+// reference (the tests compare work counters and images between the two modes).
+#ifndef RAYITO_B200_RT_SPLIT_CUH
+#define RAYITO_B200_RT_SPLIT_CUH
+
+#include "rt_wave.cuh"
+
+#ifndef RT_TOP_REFILL_MIN
+#define RT_TOP_REFILL_MIN 12
+#endif
+#ifndef RT_TOP_ADVANCE_STEPS
+#define RT_TOP_ADVANCE_STEPS 4
+#endif
+#ifndef RT_TOP_SERVICE_MIN
+#define RT_TOP_SERVICE_MIN 6
+#endif
+#ifndef RT_MESH_REFILL_MIN
+#define RT_MESH_REFILL_MIN 12
+#endif
+#ifndef RT_MESH_ADVANCE_STEPS
+#define RT_MESH_ADVANCE_STEPS 4
+#endif
+#ifndef RT_MESH_SERVICE_MIN
+#define RT_MESH_SERVICE_MIN 4
+#endif
+
+#define RT_SPLIT_TOPCAP 8        /* top-level stack entries a suspended ray can carry */
+#define RT_SPLIT_MAX_MESHES 12   /* more mesh shapes than this: use the unified kernel */
+
+// Per-slot suspended-ray state (slot = path sample index / ray index)
+struct SplitBufs
+{
+    float4* ray_o;      // set-local origin xyz, time
+    float4* ray_d;      // set-local direction xyz, tMax
+    float4* hit;        // m_t, winner shape, winner triangle record, (mesh shape to enter | sp << 24)
+    float4* stack;      // RT_SPLIT_TOPCAP entries per slot: node, t0, t1, -
+    float4* mesh_o;     // mesh-local origin xyz (computed by the top pass at mesh entry)
+    float4* mesh_d;     // mesh-local direction xyz
+};
+
+// One pass: where the work comes from, where suspended / resumed slots go, and
+// which counters this kernel zeroes for the passes after it (none of which it uses)
+struct SplitPass
+{
+    const uint32_t* in_queue;    // resume / mesh passes: slots to process
+    const uint32_t* in_count;    // number of entries (device memory)
+    uint32_t* cursor;            // atomic work cursor of this pass
+    uint32_t* out_queue;         // top pass: mesh queue; mesh pass: resume queue
+    uint32_t* out_count;
+    uint32_t* zero[4];           // counters to reset (may be NULL)
+};
+
+__device__ __forceinline__ void split_zero(const SplitPass& ps)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (int k = 0; k < 4; ++k)
+            if (ps.zero[k]) *ps.zero[k] = 0;
+}
+
+// Append to a queue: one atomicAdd per warp.  All 32 lanes must call.
+__device__ __forceinline__ void warp_queue_push(uint32_t* queue, uint32_t* counter, bool want, uint32_t value)
+{
+    uint32_t mask = __ballot_sync(0xffffffffu, want);
+    if (mask == 0)
+        return;
+    uint32_t lane = threadIdx.x & 31;
+    uint32_t leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if (lane == leader)
+        base = atomicAdd(counter, __popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (want)
+        queue[base + __popc(mask & ((1u << lane) - 1))] = value;
+}
+
+// ---------------------------------------------------------------------------
+// Top-level pass.  FRESH: rays come from the stage's IO (queue of path slots);
+// otherwise they are resumed from their suspended state.
+// ---------------------------------------------------------------------------
+template <bool ANY, bool COUNT, bool FRESH, class IO>
+__device__ __forceinline__ void trace_top(const DScene& sc, const IO& io, const SplitBufs& sb, const SplitPass& ps, WorkCount& wc)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t lt_mask = (1u << lane) - 1;
+    const uint32_t n = *ps.in_count;
+
+    uint32_t stk_node[RT_SPLIT_TOPCAP];
+    float stk_t0[RT_SPLIT_TOPCAP];
+    float stk_t1[RT_SPLIT_TOPCAP];
+
+    bool active = false;
+    bool exhausted = false;
+    uint32_t tag = 0;
+    float time = 0.0f, tmax = 0.0f;
+    LocalRay r0;
+    r0.o = r0.d = r0.inv = mk(0.0f, 0.0f, 0.0f);
+    r0.neg = 0;
+    WaveResult res;
+    res.t = 0.0f; res.shape = -1; res.tri_rec = -1; res.any_hit = false;
+    int sp = 0;
+    bool parked = false;
+    uint32_t park_shape = 0;
+
+    for (;;)
+    {
+        // ------------------------------------------------------------ refill
+        uint32_t idle = __ballot_sync(0xffffffffu, !active);
+        if (!exhausted && (idle == 0xffffffffu || __popc(idle) >= RT_TOP_REFILL_MIN))
+        {
+            uint32_t need = __popc(idle);
+            uint32_t base = 0;
+            if (lane == 0)
+                base = atomicAdd(ps.cursor, need);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base + need >= n)
+                exhausted = true;
+            uint32_t j = base + __popc(idle & lt_mask);
+            if (!active && j < n)
+            {
+                active = true;
+                parked = false;
+                sp = 0;
+                if (FRESH)
+                {
+                    V3 o, d;
+                    io.load(j, o, d, tmax, time, tag);
+                    res.t = tmax;
+                    res.shape = -1;
+                    res.tri_rec = -1;
+                    res.any_hit = false;
+                    TRS set_trs = xform_eval(sc, sc.set_xform, time);
+                    if (COUNT) wc.xform_evals++;
+                    r0.o = to_local_point(set_trs, o);
+                    r0.d = to_local_vector(set_trs, d);
+                    local_ray_finish(r0);
+                    for (uint32_t k = 0; k < sc.num_infinite; ++k)
+                    {
+                        uint32_t sid = sc.num_finite + k;
+                        DShape sh = load_shape(sc, sid);
+                        TRS trs = shape_xform(sc, sh, time);
+                        V3 lo = to_local_point(trs, r0.o);
+                        V3 ld = to_local_vector(trs, r0.d);
+                        if (COUNT) { wc.xform_evals++; wc.shape_tests++; }
+                        float t;
+                        if (plane_test(sc.planes[sh.geom], lo, ld, res.t, t))
+                        {
+                            if (ANY) { res.any_hit = true; break; }
+                            res.t = t;
+                            res.shape = (int32_t)sid;
+                        }
+                    }
+                    if (!(ANY && res.any_hit))
+                    {
+                        if (sc.num_top_nodes > 0)
+                        {
+                            stk_node[0] = 0;
+                            stk_t0[0] = RT_RAY_TMIN;
+                            stk_t1[0] = res.t;
+                            sp = 1;
+                        }
+                        else
+                        {
+                            for (uint32_t k = sc.num_finite; k > 0; --k)
+                            {
+                                stk_node[sp] = RT_TOKEN_SHAPE | (k - 1);
+                                stk_t0[sp] = 0.0f;
+                                stk_t1[sp] = 0.0f;
+                                ++sp;
+                            }
+                        }
+                    }
+                }
+                else
+                {
+                    // resume a suspended ray: the mesh pass has updated m_t / the winner
+                    tag = ps.in_queue[j];
+                    float4 a = sb.ray_o[tag], b = sb.ray_d[tag], h = sb.hit[tag];
+                    r0.o = xyz4(a); time = a.w;
+                    r0.d = xyz4(b); tmax = b.w;
+                    local_ray_finish(r0);
+                    res.t = h.x;
+                    res.shape = __float_as_int(h.y);
+                    res.tri_rec = __float_as_int(h.z);
+                    res.any_hit = false;
+                    sp = (int)(__float_as_uint(h.w) >> 24);
+                    const float4* st = sb.stack + (size_t)tag * RT_SPLIT_TOPCAP;
+                    #pragma unroll
+                    for (int k = 0; k < RT_SPLIT_TOPCAP; ++k)
+                    {
+                        if (k < sp)
+                        {
+                            float4 e = st[k];
+                            stk_node[k] = __float_as_uint(e.x);
+                            stk_t0[k] = e.y;
+                            stk_t1[k] = e.z;
+                        }
+                    }
+                }
+            }
+        }
+        if (__ballot_sync(0xffffffffu, active) == 0)
+        {
+            if (exhausted)
+                break;
+            continue;
+        }
+
+        // ----------------------------------------------------------- advance
+        #pragma unroll 1
+        for (int it = 0; it < RT_TOP_ADVANCE_STEPS && active && !parked && sp > 0; ++it)
+        {
+            --sp;
+            uint32_t node_id = stk_node[sp];
+            if (node_id & RT_TOKEN_SHAPE)
+            {
+                parked = true;
+                park_shape = node_id & ~RT_TOKEN_SHAPE;
+                break;
+            }
+            DNode nd = load_node(sc.top_nodes, node_id);
+            if (COUNT) wc.node_pops++;
+            uint32_t flags = __float_as_uint(nd.q1.w);
+            uint32_t word = __float_as_uint(nd.q1.z);
+            if (flags & RT_NODE_LEAF)
+            {
+                parked = true;
+                park_shape = word;
+                break;
+            }
+            float t0 = stk_t0[sp];
+            float t1 = stk_t1[sp];
+            if (!ANY)
+            {
+                if (t0 >= res.t)
+                    continue;
+                if (t1 > res.t)
+                    t1 = res.t;
+            }
+            if (!box_test(nd.q0, nd.q1, r0.o, r0.inv, t0, t1))
+                continue;
+            uint32_t axis = flags & RT_NODE_AXIS;
+            bool neg = (r0.neg >> axis) & 1u;
+            uint32_t near_id = neg ? word : word + 1;
+            uint32_t far_id = neg ? word + 1 : word;
+            stk_node[sp] = far_id;  stk_t0[sp] = t0; stk_t1[sp] = t1;
+            ++sp;
+            stk_node[sp] = near_id; stk_t0[sp] = t0; stk_t1[sp] = t1;
+            ++sp;
+        }
+
+        const uint32_t m_shape = __ballot_sync(0xffffffffu, parked);
+        const uint32_t m_adv = __ballot_sync(0xffffffffu, active && !parked && sp > 0);
+        const bool do_shape = m_shape != 0 && (m_adv == 0 || exhausted || __popc(m_shape) >= RT_TOP_SERVICE_MIN);
+
+        // ----------------------------------------------------------- service
+        bool suspend = false;
+        if (do_shape && parked)
+        {
+            DShape sh = load_shape(sc, park_shape);
+            if (sh.type == RT_SHAPE_MESH)
+            {
+                // Mesh::intersect / doesIntersect (RMesh.h:62-81): warp the ray into
+                // mesh-local space and pop the face BVH's root here; most rays that
+                // reach a mesh leaf miss the mesh's root box and never need a mesh pass.
+                DMesh m = sc.meshes[sh.geom];
+                if (m.num_nodes > 0)
+                {
+                    TRS trs = shape_xform(sc, sh, time);
+                    if (COUNT) wc.xform_evals++;
+                    LocalRay rm;
+                    rm.o = to_local_point(trs, r0.o);
+                    rm.d = to_local_vector(trs, r0.d);
+                    local_ray_finish(rm);
+                    DNode root = load_node(sc.mesh_nodes + m.first_node, 0);
+                    if (COUNT) wc.node_pops++;
+                    bool enter = true;
+                    if (!(__float_as_uint(root.q1.w) & RT_NODE_LEAF))
+                    {
+                        float t0 = RT_RAY_TMIN, t1 = ANY ? tmax : res.t;
+                        if (!ANY && t0 >= res.t)
+                            enter = false;
+                        else
+                            enter = box_test(root.q0, root.q1, rm.o, rm.inv, t0, t1);
+                    }
+                    if (enter)
+                    {
+                        suspend = true;
+                        sb.mesh_o[tag] = make_float4(rm.o.x, rm.o.y, rm.o.z, 0.0f);
+                        sb.mesh_d[tag] = make_float4(rm.d.x, rm.d.y, rm.d.z, 0.0f);
+                    }
+                }
+            }
+            else
+            {
+                TRS trs = shape_xform(sc, sh, time);
+                if (COUNT) wc.xform_evals++;
+                V3 lo = to_local_point(trs, r0.o);
+                V3 ld = to_local_vector(trs, r0.d);
+                if (sh.type == RT_SHAPE_SPHERE)
+                {
+                    DSphere s = sc.spheres[sh.geom];
+                    if (COUNT) wc.shape_tests++;
+                    V3 c = lo - mk(s.px, s.py, s.pz);
+                    if (ANY)
+                    {
+                        if (sphere_any(c, ld, s.radius, tmax)) { res.any_hit = true; sp = 0; }
+                    }
+                    else
+                    {
+                        float t;
+                        if (sphere_closest(c, ld, s.radius, res.t, t))
+                        {
+                            res.t = t;
+                            res.shape = (int32_t)park_shape;
+                            res.tri_rec = -1;
+                        }
+                    }
+                }
+                else if (sh.type == RT_SHAPE_RECT)
+                {
+                    if (COUNT) wc.shape_tests++;
+                    float t;
+                    if (rect_test(sc.rects[sh.geom], lo, ld, ANY ? tmax : res.t, t))
+                    {
+                        if (ANY) { res.any_hit = true; sp = 0; }
+                        else
+                        {
+                            res.t = t;
+                            res.shape = (int32_t)park_shape;
+                            res.tri_rec = -1;
+                        }
+                    }
+                }
+            }
+            parked = false;
+        }
+        if (__ballot_sync(0xffffffffu, suspend))
+        {
+            if (suspend)
+            {
+                sb.ray_o[tag] = make_float4(r0.o.x, r0.o.y, r0.o.z, time);
+                sb.ray_d[tag] = make_float4(r0.d.x, r0.d.y, r0.d.z, tmax);
+                sb.hit[tag] = make_float4(res.t, __int_as_float(res.shape), __int_as_float(res.tri_rec),
+                                          __uint_as_float(park_shape | ((uint32_t)sp << 24)));
+                float4* st = sb.stack + (size_t)tag * RT_SPLIT_TOPCAP;
+                #pragma unroll
+                for (int k = 0; k < RT_SPLIT_TOPCAP; ++k)
+                    if (k < sp)
+                        st[k] = make_float4(__uint_as_float(stk_node[k]), stk_t0[k], stk_t1[k], 0.0f);
+                active = false;
+            }
+            warp_queue_push(ps.out_queue, ps.out_count, suspend, tag);
+        }
+
+        // ------------------------------------------------------------- retire
+        if (active && !parked && sp == 0)
+        {
+            io.store(tag, res);
+            active = false;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Mesh pass: Mesh::intersect / doesIntersect for suspended rays
+// ---------------------------------------------------------------------------
+template <int CAP, bool ANY, bool COUNT, class IO>
+__device__ __forceinline__ void trace_mesh(const DScene& sc, const IO& io, const SplitBufs& sb, const SplitPass& ps, WorkCount& wc)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t lt_mask = (1u << lane) - 1;
+    const uint32_t n = *ps.in_count;
+
+    uint32_t stk_node[CAP];
+    float stk_t0[CAP];
+    float stk_t1[CAP];
+
+    bool active = false;
+    bool exhausted = false;
+    uint32_t tag = 0;
+    float tmax = 0.0f;
+    LocalRay r1;
+    r1.o = r1.d = r1.inv = mk(0.0f, 0.0f, 0.0f);
+    r1.neg = 0;
+    float best = 0.0f;           // m_t
+    int32_t best_rec = -1;       // triangle record accepted in this mesh, if any
+    bool any_hit = false;
+    uint32_t mesh_shape = 0, meta = 0;
+    const DNode* mesh_nodes = sc.mesh_nodes;
+    int sp = 0;
+    bool parked = false;
+    uint32_t park_word = 0, park_count = 0;
+
+    for (;;)
+    {
+        uint32_t idle = __ballot_sync(0xffffffffu, !active);
+        if (!exhausted && (idle == 0xffffffffu || __popc(idle) >= RT_MESH_REFILL_MIN))
+        {
+            uint32_t need = __popc(idle);
+            uint32_t base = 0;
+            if (lane == 0)
+                base = atomicAdd(ps.cursor, need);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base + need >= n)
+                exhausted = true;
+            uint32_t j = base + __popc(idle & lt_mask);
+            if (!active && j < n)
+            {
+                active = true;
+                parked = false;
+                tag = ps.in_queue[j];
+                float4 a = sb.ray_o[tag], b = sb.ray_d[tag], h = sb.hit[tag];
+                tmax = b.w;
+                best = h.x;
+                best_rec = -1;
+                any_hit = false;
+                meta = __float_as_uint(h.w);
+                mesh_shape = meta & 0xffffffu;
+                DShape sh = load_shape(sc, mesh_shape);
+                DMesh m = sc.meshes[sh.geom];
+                // the top pass already warped the ray into mesh-local space and found
+                // that it enters the root; redo the root's slab test (same inputs, same
+                // bits) only to get the clipped range its children inherit
+                float4 mo = sb.mesh_o[tag], md = sb.mesh_d[tag];
+                r1.o = xyz4(mo);
+                r1.d = xyz4(md);
+                local_ray_finish(r1);
+                mesh_nodes = sc.mesh_nodes + m.first_node;
+                DNode root = load_node(mesh_nodes, 0);
+                uint32_t rflags = __float_as_uint(root.q1.w);
+                uint32_t rword = __float_as_uint(root.q1.z);
+                sp = 0;
+                if (rflags & RT_NODE_LEAF)
+                {
+                    parked = true;
+                    park_word = rword;
+                    park_count = rflags >> 3;
+                }
+                else
+                {
+                    float t0 = RT_RAY_TMIN, t1 = ANY ? tmax : best;
+                    box_test(root.q0, root.q1, r1.o, r1.inv, t0, t1);
+                    bool neg = (r1.neg >> (rflags & RT_NODE_AXIS)) & 1u;
+                    stk_node[0] = neg ? rword + 1 : rword;  stk_t0[0] = t0; stk_t1[0] = t1;
+                    stk_node[1] = neg ? rword : rword + 1;  stk_t0[1] = t0; stk_t1[1] = t1;
+                    sp = 2;
+                }
+                (void)a; (void)b;
+            }
+        }
+        if (__ballot_sync(0xffffffffu, active) == 0)
+        {
+            if (exhausted)
+                break;
+            continue;
+        }
+
+        #pragma unroll 1
+        for (int it = 0; it < RT_MESH_ADVANCE_STEPS && active && !parked && sp > 0; ++it)
+        {
+            --sp;
+            DNode nd = load_node(mesh_nodes, stk_node[sp]);
+            if (COUNT) wc.node_pops++;
+            uint32_t flags = __float_as_uint(nd.q1.w);
+            uint32_t word = __float_as_uint(nd.q1.z);
+            if (flags & RT_NODE_LEAF)
+            {
+                parked = true;
+                park_word = word;
+                park_count = flags >> 3;
+                break;
+            }
+            float t0 = stk_t0[sp];
+            float t1 = stk_t1[sp];
+            if (!ANY)
+            {
+                if (t0 >= best)
+                    continue;
+                if (t1 > best)
+                    t1 = best;
+            }
+            if (!box_test(nd.q0, nd.q1, r1.o, r1.inv, t0, t1))
+                continue;
+            uint32_t axis = flags & RT_NODE_AXIS;
+            bool neg = (r1.neg >> axis) & 1u;
+            uint32_t near_id = neg ? word : word + 1;
+            uint32_t far_id = neg ? word + 1 : word;
+            stk_node[sp] = far_id;  stk_t0[sp] = t0; stk_t1[sp] = t1;
+            ++sp;
+            stk_node[sp] = near_id; stk_t0[sp] = t0; stk_t1[sp] = t1;
+            ++sp;
+        }
+
+        const uint32_t m_tri = __ballot_sync(0xffffffffu, parked);
+        const uint32_t m_adv = __ballot_sync(0xffffffffu, active && !parked && sp > 0);
+        const bool do_tri = m_tri != 0 && (m_adv == 0 || exhausted || __popc(m_tri) >= RT_MESH_SERVICE_MIN);
+
+        if (do_tri && parked)
+        {
+            for (uint32_t k = 0; k < park_count; ++k)
+            {
+                V3 p0, p1, p2;
+                uint32_t w0, w1, w2;
+                load_tri(sc, park_word + k, p0, p1, p2, w0, w1, w2);
+                if (COUNT) wc.tri_tests++;
+                float t, beta, gamma;
+                if (tri_closest(r1.o, r1.d, p0, p1, p2, ANY ? tmax : best, t, beta, gamma))
+                {
+                    if (ANY) { any_hit = true; sp = 0; break; }
+                    best = t;
+                    best_rec = (int32_t)(park_word + k);
+                }
+            }
+            parked = false;
+        }
+
+        // retire: hand the slot back to a top-level resume pass (or finish a shadow ray)
+        const bool done = active && !parked && sp == 0;
+        if (__ballot_sync(0xffffffffu, done))
+        {
+            bool resume = false;
+            if (done)
+            {
+                if (ANY && any_hit)
+                {
+                    WaveResult r;
+                    r.t = tmax; r.shape = -1; r.tri_rec = -1; r.any_hit = true;
+                    io.store(tag, r);
+                }
+                else
+                {
+                    if (best_rec >= 0)
+                    {
+                        float4 h = sb.hit[tag];
+                        sb.hit[tag] = make_float4(best, __int_as_float((int32_t)mesh_shape), __int_as_float(best_rec), h.w);
+                    }
+                    resume = true;
+                }
+                active = false;
+            }
+            warp_queue_push(ps.out_queue, ps.out_count, resume, tag);
+        }
+    }
+}
+
+#endif // RAYITO_B200_RT_SPLIT_CUH

@@ -114,7 +114,7 @@ __device__ __forceinline__ void trace_wave(const DScene& sc, const IO& io, uint3
                     {
                         uint32_t sid = sc.num_finite + k;
                         DShape sh = load_shape(sc, sid);
-                        TRS trs = xform_eval(sc, sh.xform, time);
+                        TRS trs = shape_xform(sc, sh, time);
                         V3 lo = to_local_point(trs, r0.o);
                         V3 ld = to_local_vector(trs, r0.d);
                         if (COUNT) { wc.xform_evals++; wc.shape_tests++; }
@@ -243,7 +243,7 @@ __device__ __forceinline__ void trace_wave(const DScene& sc, const IO& io, uint3
         if (do_shape && parked == PARK_SHAPE)
         {
             DShape sh = load_shape(sc, park_word);
-            TRS trs = xform_eval(sc, sh.xform, time);
+            TRS trs = shape_xform(sc, sh, time);
             if (COUNT) wc.xform_evals++;
             V3 lo = to_local_point(trs, r0.o);
             V3 ld = to_local_vector(trs, r0.d);
