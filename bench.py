@@ -304,8 +304,10 @@ def main():
         "avg_launch_ms": trace_ms / max(trace_launches, 1),
         "trace_share_of_step": trace_ms_max / max_ms,
         "trace_mrays_per_s_per_gpu": rays_total * args.steps / (trace_ms_max / 1e3) / 1e6 / world,
-        "note": "scene is %.1f MB and L2-resident by nature of this config: the HBM fraction is reported as the "
-                "contract asks, but L2/latency binds first (SURVEY.md 8d)" % (hscene_bytes(hscene) / 1e6),
+        "note": ("scene is %.1f MB: %s" % (hscene_bytes(hscene) / 1e6,
+                 "L2-resident by nature of this config, so the HBM fraction is reported as the contract asks but "
+                 "L2 latency / SIMT divergence binds first (SURVEY.md 8d)" if hscene_bytes(hscene) < 100e6 else
+                 "HBM-resident, random node/triangle gathers: the HBM roofline is the binding one")),
     }
 
     # ---- e2e: through Rayito::raytrace() with host buffers -------------------------

@@ -54,3 +54,16 @@ def scene2_host(capi):
 @pytest.fixture(scope="session")
 def scene2_ref(ref):
     return ref.RefScene(2)
+
+
+SYNTH_GRID = (192, 160)
+
+
+@pytest.fixture(scope="session")
+def scene5_host(capi):
+    return capi.HostScene(capi.RECIPE_SYNTHETIC_MESH, None, SYNTH_GRID)
+
+
+@pytest.fixture(scope="session")
+def scene5_ref(ref):
+    return ref.RefScene(5, None, SYNTH_GRID)

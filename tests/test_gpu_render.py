@@ -113,6 +113,20 @@ def test_scene2_image_matches_reference(dev2, scene2_ref, scene2_host, capi):
     assert same >= MIN_IDENTICAL_FRACTION
 
 
+def test_synthetic_mesh_image_matches_reference(capi, scene5_host, scene5_ref):
+    dev = capi.DeviceScene(scene5_host.desc)
+    spec = scene5_host.default_camera_spec()
+    cam = capi.camera_from_spec(spec)
+    W, H, ps = 80, 45, 2
+    theirs, rstats = scene5_ref.render(spec, W, H, ps, ls=1, depth=3)
+    mine, stats = dev.render(cam, W, H, ps, ls=1, depth=3)
+    dev.close()
+    same, rel = _compare_images(mine, theirs, "synthetic mesh")
+    assert rel <= RMSE_REL_TOL and same >= MIN_IDENTICAL_FRACTION
+    ref_rays = rstats.closest_calls + rstats.any_calls
+    assert abs(int(stats.closest_rays + stats.any_rays) - ref_rays) <= 0.002 * ref_rays
+
+
 def test_tile_sharding_is_exact(dev1, scene1_host, capi):
     """Any partition of the image into rank-owned tiles reproduces the single-GPU
     image bit for bit (the sample stream is position-addressable), and small

@@ -95,6 +95,17 @@ def test_scene2_tumbling_cubes(dev2, scene2_ref):
     _compare_any(dev2, scene2_ref, rays, "scene2 any")
 
 
+def test_synthetic_mesh_scene(capi, scene5_host, scene5_ref):
+    """The procedural displaced-sphere mesh of BASELINE.json configs[4] (small grid):
+    two finite shapes besides the mesh -> top-level BVH of 4 shapes, deep face BVH."""
+    dev = capi.DeviceScene(scene5_host.desc)
+    rays = random_rays(1 << 17, seed=51, center=(0, 0.2, 0), radius=9.0, target_radius=2.6, shadow_fraction=0.3)
+    hits = _compare_closest(dev, scene5_ref, rays, "synthetic")
+    assert (hits["face"] >= 0).mean() > 0.4
+    _compare_any(dev, scene5_ref, rays, "synthetic any")
+    dev.close()
+
+
 def test_empty_and_tiny_batches(dev1, capi):
     empty = np.zeros(0, capi.RAY_DTYPE)
     assert len(dev1.trace_closest(empty)) == 0
