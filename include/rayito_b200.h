@@ -263,6 +263,25 @@ int rt_generate_camera_rays(RtScene* scene, const RtCamera* camera, const RtRend
 int rt_tonemap_bgra8(int device, const float* rgb, size_t num_pixels, float exposure_stops, float gamma,
                      uint8_t* bgra);
 
+/* ---- Stage 1 (BASELINE.json configs[0]) ------------------------------------------ */
+
+/* Stage 1 plane (Rayito_Stage1/rayito.h:465-512): one-sided, flat colour, normal
+ * already normalised by the constructor. */
+typedef struct RtStage1Plane
+{
+    float position[3];
+    float normal[3];
+    float color[3];
+} RtStage1Plane;
+
+/* The whole Stage 1 program (Rayito_Stage1/main.cpp:65-135): one ray per pixel
+ * through the pixel CORNERS (x/(W-1), 1 - y/(H-1)), closest plane in list order with
+ * kRayTMin = 1e-5 (rayito.h:301), colour clamped and truncated to 8 bits.  `camera`
+ * holds makeCameraRay's basis (main.cpp:28-52: forward, right and up all normalised,
+ * tan of the full field of view).  rgb8 = width*height*3 bytes, the P6 payload. */
+int rt_stage1_render(int device, const RtStage1Plane* planes, uint32_t num_planes, const RtCamera* camera,
+                     uint32_t width, uint32_t height, uint8_t* rgb8);
+
 /* ---- host-side pieces of the path (no device needed) ------------------------- */
 
 /* Tile partition used to shard one image over `world` ranks: owners[ty*tiles_x+tx] is

@@ -53,6 +53,12 @@ int rth_raytrace(int recipe, const char* obj_path, unsigned grid_u, unsigned gri
                  int device, unsigned rank, unsigned world, int count_work,
                  float* rgb, RtRenderStats* stats);
 
+/* Stage 1 program (Rayito_Stage1/main.cpp:65-135): builds its scene (one pink plane at
+ * y = -2) and camera (fov 30 at the origin looking down +z) with makeCameraRay's basis
+ * arithmetic (main.cpp:28-52), renders on the GPU and returns the P6 payload
+ * (width*height*3 bytes); what `make && ./rayito` writes after the "P6" header. */
+int rth_stage1_render(int device, unsigned width, unsigned height, unsigned char* rgb8);
+
 #ifdef __cplusplus
 }
 #endif

@@ -102,11 +102,12 @@ CORE_SYMBOLS = [
     "rt_trace_closest", "rt_trace_closest_ex", "rt_trace_any",
     "rt_trace_closest_device", "rt_trace_any_device",
     "rt_render", "rt_render_device", "rt_generate_camera_rays", "rt_tonemap_bgra8",
-    "rt_tile_owners", "rt_sample_permutations", "rt_cmj_sample1d", "rt_cmj_sample2d",
+    "rt_tile_owners", "rt_sample_permutations", "rt_cmj_sample1d", "rt_cmj_sample2d", "rt_stage1_render",
 ]
 HOST_SYMBOLS = [
     "rth_last_error_string", "rth_scene_create", "rth_scene_destroy", "rth_scene_desc",
     "rth_scene_prepare_seconds", "rth_scene_depth", "rth_camera", "rth_scene_default_camera", "rth_raytrace",
+    "rth_stage1_render",
 ]
 
 _core = None
@@ -165,6 +166,7 @@ def host():
         lib.rth_raytrace.argtypes = [C.c_int, C.c_char_p, C.c_uint, C.c_uint, vp, C.c_uint, C.c_uint,
                                      C.c_uint, C.c_uint, C.c_uint, C.c_int, C.c_uint, C.c_uint, C.c_int,
                                      vp, C.POINTER(RtRenderStats)]
+        lib.rth_stage1_render.argtypes = [C.c_int, C.c_uint, C.c_uint, vp]
         _host = lib
     return _host
 
@@ -289,6 +291,14 @@ def tonemap_bgra8(rgb, exposure_stops=0.0, gamma=2.2, device=0):
     out = np.empty((n, 4), np.uint8)
     check(core().rt_tonemap_bgra8(device, rgb.ctypes.data, n, exposure_stops, gamma, out.ctypes.data), "rt_tonemap_bgra8")
     return out.reshape(rgb.shape[:-1] + (4,))
+
+
+def stage1_render(width=512, height=512, device=0):
+    """The Stage 1 program on the GPU: P6 payload as an (H, W, 3) uint8 array."""
+    out = np.zeros((height, width, 3), np.uint8)
+    if host().rth_stage1_render(device, width, height, out.ctypes.data) != 0:
+        raise RtError("rth_stage1_render: " + host().rth_last_error_string().decode())
+    return out
 
 
 def tile_owners(width, height, world, tile_size=0):

@@ -315,6 +315,12 @@ int rt_generate_camera_rays(RtScene* s, const RtCamera* camera, const RtRenderPa
     return rt_camera_rays_impl(s, camera, params, psi, rays);
 }
 
+int rt_stage1_render(int device, const RtStage1Plane* planes, uint32_t num_planes, const RtCamera* camera,
+                     uint32_t width, uint32_t height, uint8_t* rgb8)
+{
+    return rt_stage1_impl(device, planes, num_planes, camera, width, height, rgb8);
+}
+
 int rt_tile_owners(uint32_t width, uint32_t height, uint32_t tile_size, uint32_t world,
                    uint32_t* owners, uint32_t* tiles_x, uint32_t* tiles_y, uint32_t* tile_size_used)
 {

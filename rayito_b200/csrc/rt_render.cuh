@@ -685,6 +685,81 @@ __global__ void k_tonemap(const float* __restrict__ rgb_in, size_t n, float expo
     out[4 * i + 0] = (uint8_t)(b * 255.0f);
 }
 
+// Stage 1 (Rayito_Stage1/main.cpp:93-135, rayito.h:474-509): rays through pixel
+// corners, closest one-sided plane in list order, kRayTMin = 1e-5, 8-bit truncation.
+// Stage 1's Vector::normalize divides unconditionally (rayito.h:194).
+__global__ void k_stage1(const RtStage1Plane* __restrict__ planes, uint32_t num_planes, const RtCamera cam,
+                         uint32_t width, uint32_t height, uint8_t* __restrict__ out)
+{
+    uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t y = blockIdx.y;
+    if (x >= width || y >= height)
+        return;
+    float yu = 1.0f - ((float)y / (float)(height - 1));
+    float xu = (float)x / (float)(width - 1);
+    V3 fwd = mk(cam.forward[0], cam.forward[1], cam.forward[2]);
+    V3 right = mk(cam.right[0], cam.right[1], cam.right[2]);
+    V3 up = mk(cam.up[0], cam.up[1], cam.up[2]);
+    V3 o = mk(cam.origin[0], cam.origin[1], cam.origin[2]);
+    V3 d = fwd + right * ((xu - 0.5f) * cam.tan_fov) + up * ((yu - 0.5f) * cam.tan_fov);
+    float len = length3(d);
+    d = mk(d.x / len, d.y / len, d.z / len);
+    float best = RT_RAY_TMAX;
+    float r = 0.0f, g = 0.0f, b = 0.0f;
+    for (uint32_t k = 0; k < num_planes; ++k)
+    {
+        V3 n = mk(planes[k].normal[0], planes[k].normal[1], planes[k].normal[2]);
+        V3 p = mk(planes[k].position[0], planes[k].position[1], planes[k].position[2]);
+        float n_dot_d = dot3(n, d);
+        if (n_dot_d >= 0.0f)
+            continue;
+        float t = (dot3(p, n) - dot3(o, n)) / dot3(d, n);
+        if (t >= best || t < 0.00001f)
+            continue;
+        best = t;
+        r = planes[k].color[0]; g = planes[k].color[1]; b = planes[k].color[2];
+    }
+    r = std_max(0.0f, std_min(1.0f, r));
+    g = std_max(0.0f, std_min(1.0f, g));
+    b = std_max(0.0f, std_min(1.0f, b));
+    uint8_t* px = out + ((size_t)y * width + x) * 3;
+    px[0] = (uint8_t)(r * 255.0f);
+    px[1] = (uint8_t)(g * 255.0f);
+    px[2] = (uint8_t)(b * 255.0f);
+}
+
+inline int rt_stage1_impl(int device, const RtStage1Plane* planes, uint32_t num_planes, const RtCamera* cam,
+                          uint32_t width, uint32_t height, uint8_t* rgb8)
+{
+    if (cam == NULL || rgb8 == NULL || (num_planes && planes == NULL) || width < 2 || height < 2)
+        return rt_fail(RT_ERR_ARG, "bad argument (Stage 1 needs width, height >= 2)");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    {
+        cudaGetLastError();
+        return rt_fail(RT_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+    }
+    RT_CUDA(cudaSetDevice(device));
+    RtStage1Plane* d_planes = NULL;
+    uint8_t* d_out = NULL;
+    size_t bytes = (size_t)width * height * 3;
+    cudaError_t e = cudaMalloc((void**)&d_planes, sizeof(RtStage1Plane) * (num_planes ? num_planes : 1));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_out, bytes);
+    if (e == cudaSuccess && num_planes)
+        e = cudaMemcpy(d_planes, planes, sizeof(RtStage1Plane) * num_planes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess)
+    {
+        dim3 grid((width + 127) / 128, height);
+        k_stage1<<<grid, 128>>>(d_planes, num_planes, *cam, width, height, d_out);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(rgb8, d_out, bytes, cudaMemcpyDeviceToHost);
+    if (d_planes) cudaFree(d_planes);
+    if (d_out) cudaFree(d_out);
+    if (e != cudaSuccess) return rt_cuda_fail(e, "stage 1 render");
+    return RT_OK;
+}
+
 // ---------------------------------------------------------------------------
 // host orchestration
 // ---------------------------------------------------------------------------

@@ -385,4 +385,41 @@ int rth_raytrace(int recipe, const char* obj_path, unsigned grid_u, unsigned gri
     }
 }
 
+int rth_stage1_render(int device, unsigned width, unsigned height, unsigned char* rgb8)
+{
+    using namespace Rayito;
+    // Scene of Rayito_Stage1/main.cpp:68-74
+    RtStage1Plane plane;
+    Vector n = Vector(0.0f, 1.0f, 0.0f);
+    {   // Stage 1's normalize divides unconditionally (rayito.h:194)
+        float len = n.length();
+        n = Vector(n.m_x / len, n.m_y / len, n.m_z / len);
+    }
+    plane.position[0] = 0.0f; plane.position[1] = -2.0f; plane.position[2] = 0.0f;
+    plane.normal[0] = n.m_x; plane.normal[1] = n.m_y; plane.normal[2] = n.m_z;
+    plane.color[0] = 1.0f; plane.color[1] = 0.5f; plane.color[2] = 0.8f;
+    // makeCameraRay's per-call basis (main.cpp:35-40), hoisted: it does not depend on the pixel
+    Point origin(0.0f, 0.0f, 0.0f), target(0.0f, 0.0f, 1.0f), upDir(0.0f, 1.0f, 0.0f);
+    Vector forward = target - origin;
+    float fl = forward.length();
+    forward = Vector(forward.m_x / fl, forward.m_y / fl, forward.m_z / fl);
+    Vector right = cross(forward, upDir);
+    float rl = right.length();
+    right = Vector(right.m_x / rl, right.m_y / rl, right.m_z / rl);
+    Vector up = cross(right, forward);
+    float ul = up.length();
+    up = Vector(up.m_x / ul, up.m_y / ul, up.m_z / ul);
+    RtCamera cam;
+    std::memset(&cam, 0, sizeof(cam));
+    cam.origin[0] = origin.m_x; cam.origin[1] = origin.m_y; cam.origin[2] = origin.m_z;
+    cam.forward[0] = forward.m_x; cam.forward[1] = forward.m_y; cam.forward[2] = forward.m_z;
+    cam.right[0] = right.m_x; cam.right[1] = right.m_y; cam.right[2] = right.m_z;
+    cam.up[0] = up.m_x; cam.up[1] = up.m_y; cam.up[2] = up.m_z;
+    cam.tan_fov = std::tan(30.0f * M_PI / 180.0f);
+    int rc = rt_stage1_render(device, &plane, 1, &cam, width, height, rgb8);
+    if (rc != RT_OK)
+        t_hostError = rt_last_error_string();
+    return rc;
+}
+
 } // extern "C"

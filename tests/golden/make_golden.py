@@ -58,6 +58,20 @@ def main():
     for xs, ys, perm in [(4, 4, 4242), (16, 16, 0xcafef00d), (3, 5, 17), (32, 32, 1)]:
         cmj["cmj2d_%d_%d_%d" % (xs, ys, perm)] = refapi.cmj_2d(xs, ys, perm, min(xs * ys, 256))
     np.savez_compressed(os.path.join(HERE, "sample_stream.npz"), **rng, **cmj)
+    # Stage 1's golden image (Rayito_Stage1/out_ref.ppm) is two flat colours: keep its digest and
+    # its structure instead of a 786 KB copy
+    import hashlib
+    import json
+    data = open("/root/reference/Rayito_Stage1/out_ref.ppm", "rb").read()
+    cut = data.index(b"255\n") + 4
+    px = np.frombuffer(data[cut:], np.uint8).reshape(512, 512, 3)
+    lit = np.flatnonzero(px.any(axis=(1, 2)))
+    desc = {"source": "Rayito_Stage1/out_ref.ppm", "md5": hashlib.md5(data).hexdigest(), "bytes": len(data),
+            "header": data[:cut].decode(), "width": 512, "height": 512,
+            "first_lit_row": int(lit[0]), "last_lit_row": int(lit[-1]),
+            "lit_colour": [int(v) for v in px[lit[0], 0]], "payload_md5": hashlib.md5(data[cut:]).hexdigest()}
+    assert (px[lit[0]:] == px[lit[0], 0]).all() and not px[:lit[0]].any()
+    json.dump(desc, open(os.path.join(HERE, "stage1_out_ref.json"), "w"), indent=1)
     print("golden fixtures written to", HERE)
 
 
