@@ -301,6 +301,12 @@ int rt_sample_permutations(uint32_t width, uint32_t height, uint32_t depth, uint
 float rt_cmj_sample1d(uint32_t index, uint32_t samples, uint32_t permutation);
 void rt_cmj_sample2d(uint32_t index, uint32_t x_samples, uint32_t y_samples, uint32_t permutation, float* u, float* v);
 
+/* The device's sinf / cosf / powf (rt_libm.cuh: the C library's algorithms restated,
+ * see there), evaluated on the host from the same source, for n arguments.
+ * kind 0 = sinf(x), 1 = cosf(x), 2 = powf(x, y), 3 / 4 = the sine / cosine of the
+ * shared-reduction sincos.  y may be NULL unless kind is 2. */
+int rt_libm_eval(int kind, const float* x, const float* y, size_t n, float* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -103,6 +103,7 @@ CORE_SYMBOLS = [
     "rt_trace_closest_device", "rt_trace_any_device",
     "rt_render", "rt_render_device", "rt_generate_camera_rays", "rt_tonemap_bgra8",
     "rt_tile_owners", "rt_sample_permutations", "rt_cmj_sample1d", "rt_cmj_sample2d", "rt_stage1_render",
+    "rt_libm_eval",
 ]
 HOST_SYMBOLS = [
     "rth_last_error_string", "rth_scene_create", "rth_scene_destroy", "rth_scene_desc",
@@ -134,6 +135,7 @@ def core():
                                          C.POINTER(RtRenderStats), vp]
         lib.rt_generate_camera_rays.argtypes = [vp, C.POINTER(RtCamera), C.POINTER(RtRenderParams), u32, vp]
         lib.rt_tonemap_bgra8.argtypes = [C.c_int, vp, sz, C.c_float, C.c_float, vp]
+        lib.rt_libm_eval.argtypes = [C.c_int, vp, vp, sz, vp]
         lib.rt_tile_owners.argtypes = [u32, u32, u32, u32, vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]
         lib.rt_sample_permutations.argtypes = [u32, u32, u32, u32, u32, vp]
         lib.rt_cmj_sample1d.restype = C.c_float
@@ -298,6 +300,18 @@ def stage1_render(width=512, height=512, device=0):
     out = np.zeros((height, width, 3), np.uint8)
     if host().rth_stage1_render(device, width, height, out.ctypes.data) != 0:
         raise RtError("rth_stage1_render: " + host().rth_last_error_string().decode())
+    return out
+
+
+def libm_eval(kind, x, y=None):
+    """Host build of the device's sinf (0) / cosf (1) / powf (2)."""
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.empty_like(x)
+    yp = None
+    if y is not None:
+        y = np.ascontiguousarray(y, np.float32)
+        yp = y.ctypes.data
+    check(core().rt_libm_eval(kind, x.ctypes.data, yp, x.size, out.ctypes.data), "rt_libm_eval")
     return out
 
 

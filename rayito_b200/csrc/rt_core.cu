@@ -364,6 +364,24 @@ void rt_cmj_sample2d(uint32_t index, uint32_t x_samples, uint32_t y_samples, uin
     cmj_sample2d(index, x_samples, y_samples, permutation, *u, *v);
 }
 
+int rt_libm_eval(int kind, const float* x, const float* y, size_t n, float* out)
+{
+    if (x == NULL || out == NULL || (kind == 2 && y == NULL) || kind < 0 || kind > 4)
+        return rt_fail(RT_ERR_ARG, "bad argument");
+    for (size_t i = 0; i < n; ++i)
+    {
+        if (kind >= 3)
+        {
+            float sn, cs;
+            rtm_sincosf(x[i], sn, cs);
+            out[i] = kind == 3 ? sn : cs;
+        }
+        else
+            out[i] = kind == 0 ? rtm_sinf(x[i]) : kind == 1 ? rtm_cosf(x[i]) : rtm_powf(x[i], y[i]);
+    }
+    return RT_OK;
+}
+
 int rt_tonemap_bgra8(int device, const float* rgb, size_t num_pixels, float exposure_stops, float gamma, uint8_t* bgra)
 {
     return rt_tonemap_impl(device, rgb, num_pixels, exposure_stops, gamma, bgra);

@@ -12,6 +12,7 @@
 #define RAYITO_B200_RT_SAMPLING_CUH
 
 #include "rt_device.cuh"
+#include "rt_libm.cuh"
 
 #define RT_PI_D 3.14159265358979323846   /* M_PI: a double, as on the reference's libc */
 
@@ -205,25 +206,18 @@ __host__ __device__ __forceinline__ void cmj_sample2d(uint32_t index, uint32_t x
 
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------
-// libm.  The reference calls glibc's float cos/sin/pow, which are correctly
-// rounded for all but a sliver of inputs; CUDA's float versions are 1-2 ulp
-// functions.  These feed sample DIRECTIONS, so to follow the reference's paths as
-// closely as possible they are evaluated in double and rounded once (correctly
-// rounded but for ~1e-9 of inputs).  Remaining last-bit disagreements with glibc
-// are why Monte-Carlo images carry an RMSE bar rather than a bit-exact one.
+// libm.  The reference calls the C library's float cos/sin/pow; they feed sample
+// DIRECTIONS, so they are reproduced bit for bit (rt_libm.cuh restates glibc 2.39's
+// algorithms; tests/test_libm_cpu.py pins the host build of that file to the C
+// library).  Kept out of line: they are called from a dozen places.
 // ---------------------------------------------------------------------------
-// Out of line: the double-precision bodies are hundreds of instructions each and
-// would otherwise be inlined at every call site (k_light_sample was 94 KB of SASS).
 __device__ __noinline__ void ref_sincosf(float x, float& s, float& c)
 {
-    double ds, dc;
-    sincos((double)x, &ds, &dc);
-    s = (float)ds;
-    c = (float)dc;
+    rtm_sincosf(x, s, c);
 }
-__device__ __forceinline__ float ref_cosf(float x) { float s, c; ref_sincosf(x, s, c); return c; }
-__device__ __forceinline__ float ref_sinf(float x) { float s, c; ref_sincosf(x, s, c); return s; }
-__device__ __noinline__ float ref_powf(float x, float y) { return (float)pow((double)x, (double)y); }
+__device__ __forceinline__ float ref_cosf(float x) { return rtm_cosf(x); }
+__device__ __forceinline__ float ref_sinf(float x) { return rtm_sinf(x); }
+__device__ __noinline__ float ref_powf(float x, float y) { return rtm_powf(x, y); }
 
 // Vector(0,1,0)-or-(1,0,0) frame around a direction (RMath.h:946-955)
 __device__ __forceinline__ void make_frame(V3 ref, V3& x, V3& y, V3& z)
