@@ -3,9 +3,10 @@ raytrace() on the same scene, resolution and sample counts.
 
 Bars (BASELINE.json north_star): camera rays bit-exact (the counter-based sample
 stream reproduces the reference's); Monte-Carlo images within a stated per-pixel
-RMSE.  The device evaluates cos/sin/pow in double and rounds once, glibc's float
-versions are correctly rounded for all but a sliver of inputs, so in practice most
-pixels come out BIT-identical; the tolerances below are what is asserted."""
+RMSE.  Since the device also reproduces the C library's sinf/cosf/powf bit for bit
+(rt_libm.cuh) every sample takes the reference's path, so the float images come out
+BIT-IDENTICAL and the ray counts equal; that is what is asserted here, the RMSE bar
+being the contract's fallback."""
 import numpy as np
 import pytest
 
@@ -15,9 +16,8 @@ pytestmark = pytest.mark.gpu
 
 # Stated tolerances for Monte-Carlo stages (linear float RGB, per pixel, relative to
 # the image's mean luminance), and for the 8-bit display image (gamma 2.2).
-RMSE_REL_TOL = 0.02
-MIN_IDENTICAL_FRACTION = 0.90
-# (measured on B200: 99.5-100 % of pixels bit-identical, relative RMSE <= 6e-6)
+RMSE_REL_TOL = 0.0
+MIN_IDENTICAL_FRACTION = 1.0
 
 
 def _rays_as_rows(rays):
@@ -97,7 +97,7 @@ def test_scene1_image_matches_reference(dev1, scene1_ref, scene1_host, capi, W, 
     # ray counts: a "ray" is one scene.intersect / doesIntersect call of pathTrace
     ref_rays = rstats.closest_calls + rstats.any_calls
     my_rays = stats.closest_rays + stats.any_rays
-    assert abs(my_rays - ref_rays) <= 0.002 * ref_rays, (my_rays, ref_rays)
+    assert stats.closest_rays == rstats.closest_calls and stats.any_rays == rstats.any_calls, (my_rays, ref_rays)
     assert rel <= RMSE_REL_TOL
     assert same >= MIN_IDENTICAL_FRACTION
 
@@ -123,8 +123,20 @@ def test_synthetic_mesh_image_matches_reference(capi, scene5_host, scene5_ref):
     dev.close()
     same, rel = _compare_images(mine, theirs, "synthetic mesh")
     assert rel <= RMSE_REL_TOL and same >= MIN_IDENTICAL_FRACTION
-    ref_rays = rstats.closest_calls + rstats.any_calls
-    assert abs(int(stats.closest_rays + stats.any_rays) - ref_rays) <= 0.002 * ref_rays
+    assert stats.closest_rays == rstats.closest_calls and stats.any_rays == rstats.any_calls
+
+
+def test_scene1_full_sample_count_matches_reference(dev1, scene1_ref, scene1_host, capi):
+    """The bench configuration's sample count (256 spp, ls 1, depth 3) at a resolution the
+    CPU reference finishes in seconds: 8.3 M samples, every pixel bit-identical."""
+    spec = scene1_host.default_camera_spec()
+    cam = capi.camera_from_spec(spec)
+    W, H, ps = 240, 135, 16
+    theirs, rstats = scene1_ref.render(spec, W, H, ps, ls=1, depth=3)
+    mine, stats = dev1.render(cam, W, H, ps, ls=1, depth=3)
+    same, rel = _compare_images(mine, theirs, "scene1 240x135 256spp")
+    assert same == 1.0 and rel == 0.0
+    assert stats.closest_rays == rstats.closest_calls and stats.any_rays == rstats.any_calls
 
 
 def test_tile_sharding_is_exact(dev1, scene1_host, capi):
