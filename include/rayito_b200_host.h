@@ -22,6 +22,7 @@ enum
 {
     RTH_RECIPE_STAGE7_SCENE1 = 1,   /* needs obj_path = .../models/bumpy.obj */
     RTH_RECIPE_STAGE7_SCENE2 = 2,
+    RTH_RECIPE_STAGE7_SCENE1_MESHLIGHT = 3, /* scene 1 with bumpy.obj as a mesh light (MainWindow.cpp:193-196) */
     RTH_RECIPE_SYNTHETIC_MESH = 5   /* grid_u x grid_v quads on a displaced sphere */
 };
 

@@ -188,6 +188,7 @@ bool buildInto(RefScene& rs)
     switch (rs.sceneId)
     {
     case 1: return rayito_recipes::buildStage7Scene1(*rs.set, *rs.store, rs.objPath.c_str());
+    case 3: return rayito_recipes::buildStage7Scene1(*rs.set, *rs.store, rs.objPath.c_str(), true);
     case 2: return rayito_recipes::buildStage7Scene2(*rs.set, *rs.store);
     case 5: return rayito_recipes::buildSyntheticMeshScene(*rs.set, *rs.store, rs.gridU, rs.gridV);
     default: return false;

@@ -93,6 +93,7 @@ class RtXform(C.Structure):
 
 RECIPE_STAGE7_SCENE1 = 1
 RECIPE_STAGE7_SCENE2 = 2
+RECIPE_STAGE7_SCENE1_MESHLIGHT = 3
 RECIPE_SYNTHETIC_MESH = 5
 
 # Every symbol include/rayito_b200.h declares (checked by the CPU test-suite)

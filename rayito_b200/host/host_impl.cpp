@@ -292,6 +292,10 @@ RthScene* rth_scene_create(int recipe, const char* obj_path, unsigned grid_u, un
         s->cameraSpec = rayito_recipes::defaultCameraScene1();
         built = rayito_recipes::buildStage7Scene1(s->set, s->store, obj_path ? obj_path : "");
         break;
+    case RTH_RECIPE_STAGE7_SCENE1_MESHLIGHT:
+        s->cameraSpec = rayito_recipes::defaultCameraScene1();
+        built = rayito_recipes::buildStage7Scene1(s->set, s->store, obj_path ? obj_path : "", true);
+        break;
     case RTH_RECIPE_STAGE7_SCENE2:
         s->cameraSpec = rayito_recipes::defaultCameraScene2();
         built = rayito_recipes::buildStage7Scene2(s->set, s->store);
@@ -353,6 +357,7 @@ int rth_raytrace(int recipe, const char* obj_path, unsigned grid_u, unsigned gri
         switch (recipe)
         {
         case RTH_RECIPE_STAGE7_SCENE1: built = rayito_recipes::buildStage7Scene1(set, store, obj_path ? obj_path : ""); break;
+        case RTH_RECIPE_STAGE7_SCENE1_MESHLIGHT: built = rayito_recipes::buildStage7Scene1(set, store, obj_path ? obj_path : "", true); break;
         case RTH_RECIPE_STAGE7_SCENE2: built = rayito_recipes::buildStage7Scene2(set, store); break;
         case RTH_RECIPE_SYNTHETIC_MESH: built = rayito_recipes::buildSyntheticMeshScene(set, store, grid_u, grid_v); break;
         default: break;

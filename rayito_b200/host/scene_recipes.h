@@ -112,7 +112,7 @@ inline Rayito::Mesh* makeCubeMesh()
 // is the insertion order and must not change (it fixes BVH prim indices).
 // Returns false if the OBJ mesh could not be read.
 template <typename SetT>
-bool buildStage7Scene1(SetT& set, SceneStore& st, const char* objPath)
+bool buildStage7Scene1(SetT& set, SceneStore& st, const char* objPath, bool objIsMeshLight = false)
 {
     using namespace Rayito;
     Material* blueishLambert  = st.keep(new DiffuseMaterial(Color(0.6f, 0.6f, 0.9f)));
@@ -160,7 +160,16 @@ bool buildStage7Scene1(SetT& set, SceneStore& st, const char* objPath)
     obj->transform().setTranslation(0.0f, Vector(0.2f, 0.0f, 0.0f));
     obj->transform().rotate(0.5f, Quaternion(Vector(0.0f, 1.0f, 0.0f), M_PI / 4.0f));
     obj->transform().rotate(1.0f, Quaternion(Vector(0.0f, 1.0f, 0.0f), M_PI / 2.0f));
-    set.addShape(obj);
+    if (objIsMeshLight)
+    {
+        // the reference's MAKE_OBJ_A_MESH_LIGHT variant (MainWindow.cpp:193-196)
+        st.wrapped.push_back(st.shapes.back());
+        st.shapes.pop_back();
+        ShapeLight* meshLight = st.add(new ShapeLight(obj, Color(1.0f, 1.0f, 1.0f), 10.0f));
+        set.addShape(meshLight);
+    }
+    else
+        set.addShape(obj);
 
     RectangleLight* areaLight = st.add(new RectangleLight(Point(),
                                                           Vector(3.0f, 0.0f, 0.0f),

@@ -139,6 +139,36 @@ def test_scene1_full_sample_count_matches_reference(dev1, scene1_ref, scene1_hos
     assert stats.closest_rays == rstats.closest_calls and stats.any_rays == rstats.any_calls
 
 
+def test_depth_of_field_matches_reference(dev1, scene1_ref, scene1_host, capi):
+    """Thin-lens camera (RaytraceMain.cpp:237-264): lens radius > 0, focal distance 16."""
+    spec = scene1_host.default_camera_spec().copy()
+    spec[11] = 0.35      # lens radius
+    cam = capi.camera_from_spec(spec)
+    W, H, ps = 96, 54, 3
+    theirs, rstats = scene1_ref.render(spec, W, H, ps, ls=1, depth=2)
+    mine, stats = dev1.render(cam, W, H, ps, ls=1, depth=2)
+    same, rel = _compare_images(mine, theirs, "scene1 depth of field")
+    assert same == 1.0 and rel == 0.0
+    assert stats.closest_rays == rstats.closest_calls and stats.any_rays == rstats.any_calls
+
+
+def test_mesh_light_matches_reference(capi, ref, obj_path):
+    """bumpy.obj as an area light: face pick by area CDF, triangle sampling, Mesh::pdfSA
+    (RMesh.h:133-196), through a ShapeLight."""
+    host = capi.HostScene(capi.RECIPE_STAGE7_SCENE1_MESHLIGHT, obj_path)
+    refscene = ref.RefScene(3, obj_path)
+    dev = capi.DeviceScene(host.desc)
+    spec = host.default_camera_spec()
+    cam = capi.camera_from_spec(spec)
+    W, H, ps = 80, 45, 2
+    theirs, rstats = refscene.render(spec, W, H, ps, ls=2, depth=2)
+    mine, stats = dev.render(cam, W, H, ps, ls=2, depth=2)
+    dev.close()
+    same, rel = _compare_images(mine, theirs, "scene1 mesh light")
+    assert same == 1.0 and rel == 0.0
+    assert stats.closest_rays == rstats.closest_calls and stats.any_rays == rstats.any_calls
+
+
 def test_tile_sharding_is_exact(dev1, scene1_host, capi):
     """Any partition of the image into rank-owned tiles reproduces the single-GPU
     image bit for bit (the sample stream is position-addressable), and small
