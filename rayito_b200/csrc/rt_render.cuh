@@ -31,14 +31,24 @@
 #include "rt_split.cuh"
 
 #define RT_DEFAULT_TILE 32u
-#define RT_DEFAULT_BATCH (8u << 20)
+#define RT_DEFAULT_BATCH (16u << 20)    /* samples per wavefront batch: ~11 GB of state, amortises kernel tails */
 #define RT_MAX_DEPTH 16u
+#ifndef RT_BLOCK
 #define RT_BLOCK 128
+#endif
 
-enum { CTL_PATH_A = 0, CTL_PATH_B = 1, CTL_LIT = 2, CTL_SHADOW = 3, CTL_MIS = 4,
-       CTL_CUR_PATH = 5, CTL_CUR_SHADOW = 6, CTL_CUR_MIS = 7,
+// Queue counters.  Ray queues are binned by direction octant (8 bins) so that the
+// lanes of a traversal warp share the near/far child order; the shade queue is binned
+// by hit shape (16 bins) so that the lanes of a shading warp share shape type and BRDF.
+#ifndef RT_QBINS
+#define RT_QBINS 8
+#endif
+#define RT_SBINS 16
+enum { CTL_PATH_A = 0, CTL_PATH_B = 8, CTL_SHADOW = 16, CTL_MIS = 24, CTL_SHADE = 32, CTL_LIT = 48,   // (room for 8 ray bins)
+       CTL_CUR_PATH = 49, CTL_CUR_SHADOW = 50, CTL_CUR_MIS = 51,
        // split traversal: mesh / resume queue counts and cursors, double buffered
-       CTL_MESH_N = 8, CTL_MESH_CUR = 10, CTL_RES_N = 12, CTL_RES_CUR = 14, CTL_WORDS = 16 };
+       CTL_MESH_N = 52, CTL_MESH_CUR = 54, CTL_RES_N = 56, CTL_RES_CUR = 58, CTL_WORDS = 64 };
+#define CTL_PATH(cur) ((cur) ? CTL_PATH_B : CTL_PATH_A)
 
 // Device pointers and constants of one render call
 struct RenderCtx
@@ -74,7 +84,9 @@ struct RenderCtx
     float4* mis_P;              // partial BRDF-sample term rgb, light shape id
     float4* mis_hit0;
     float4* mis_hit1;
-    uint32_t* q_path[2];
+    uint32_t qcap;              // capacity of one queue bin (= samples of the batch buffers)
+    uint32_t* q_path[2];        // RT_QBINS bins each
+    uint32_t* q_shade;          // RT_SBINS bins: hit paths waiting for k_shade
     uint32_t* q_lit;
     uint32_t* q_shadow;
     uint32_t* q_mis;
@@ -105,20 +117,52 @@ struct RenderBuffers
 // helpers
 // ---------------------------------------------------------------------------
 
-// Append to a queue: one atomicAdd per warp
-__device__ __forceinline__ void queue_push(uint32_t* queue, uint32_t* counter, bool want, uint32_t value)
+// Append to bin `bin` of a binned queue (items[bin * cap + k]).  Opportunistic warp
+// aggregation: the lanes that happen to call together and target the same bin share
+// one atomicAdd; callers may be divergent.
+__device__ __forceinline__ void bq_push(uint32_t* items, uint32_t* counts, uint32_t cap, uint32_t bin, uint32_t value)
 {
-    uint32_t mask = __ballot_sync(0xffffffffu, want);
-    if (mask == 0)
-        return;
-    uint32_t lane = threadIdx.x & 31;
-    uint32_t leader = __ffs(mask) - 1;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t active = __activemask();
+    const uint32_t peers = __match_any_sync(active, bin);
+    const uint32_t leader = __ffs(peers) - 1;
     uint32_t base = 0;
     if (lane == leader)
-        base = atomicAdd(counter, __popc(mask));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (want)
-        queue[base + __popc(mask & ((1u << lane) - 1))] = value;
+        base = atomicAdd(counts + bin, __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    items[(size_t)bin * cap + base + __popc(peers & ((1u << lane) - 1))] = value;
+}
+
+// Read side of a binned queue: entry j of the concatenation of the bins
+template <int NB>
+struct BinQ
+{
+    const uint32_t* items;
+    const uint32_t* counts;
+    uint32_t cap;
+    __device__ __forceinline__ uint32_t total() const
+    {
+        uint32_t n = 0;
+        #pragma unroll
+        for (int b = 0; b < NB; ++b) n += counts[b];
+        return n;
+    }
+    __device__ __forceinline__ uint32_t at(uint32_t j) const
+    {
+        uint32_t b = 0;
+        #pragma unroll
+        for (int k = 0; k < NB - 1; ++k)
+        {
+            uint32_t cnt = counts[k];
+            if (b == (uint32_t)k && j >= cnt) { j -= cnt; b = k + 1; }
+        }
+        return items[(size_t)b * cap + j];
+    }
+};
+
+__device__ __forceinline__ uint32_t dir_octant(V3 d)
+{
+    return ((d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u)) % RT_QBINS;
 }
 
 __device__ __forceinline__ V3 xyz(float4 v) { return mk(v.x, v.y, v.z); }
@@ -215,7 +259,6 @@ k_raygen(const __grid_constant__ RenderCtx c)
 {
     RT_GRID_STRIDE(i, c.num_samples)
     {
-        bool live = false;
         if (i < c.num_samples)
         {
             uint32_t p = i / c.spp, psi = i % c.spp;
@@ -229,10 +272,9 @@ k_raygen(const __grid_constant__ RenderCtx c)
                 c.ray_d[i] = make_float4(d.x, d.y, d.z, 0.0f);
                 c.thr[i] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(0u));
                 c.res[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                live = true;
+                bq_push(c.q_path[0], c.ctl + CTL_PATH_A, c.qcap, dir_octant(d), i);
             }
         }
-        queue_push(c.q_path[0], c.ctl + CTL_PATH_A, live, i);
     }
 }
 
@@ -270,16 +312,20 @@ __device__ __forceinline__ void flush_work_counters(const WorkCount& wc, uint64_
     }
 }
 
-// Queue adaptors for the wave traversal (rt_wave.cuh)
+// Queue adaptors for the traversal kernels (rt_wave.cuh, rt_split.cuh)
 struct PathIO
 {
-    const uint32_t* queue;
+    BinQ<RT_QBINS> queue;
     const float4* ray_o;
     const float4* ray_d;
     float4* hit0;
+    // hits are handed to the shading stage binned by shape; misses end the path here
+    uint32_t* shade_items;
+    uint32_t* shade_counts;
+    __device__ __forceinline__ uint32_t count() const { return queue.total(); }
     __device__ __forceinline__ bool load(uint32_t j, V3& o, V3& d, float& tmax, float& time, uint32_t& tag) const
     {
-        tag = queue[j];
+        tag = queue.at(j);
         float4 a = ray_o[tag], b = ray_d[tag];
         o = xyz(a); d = xyz(b); tmax = RT_RAY_TMAX; time = a.w;
         return true;
@@ -287,18 +333,41 @@ struct PathIO
     __device__ __forceinline__ void store(uint32_t tag, const WaveResult& r) const
     {
         hit0[tag] = make_float4(r.t, __int_as_float(r.shape), __int_as_float(r.tri_rec), 0.0f);
+        if (r.shape >= 0)
+            bq_push(shade_items, shade_counts, queue.cap, min((uint32_t)r.shape, (uint32_t)(RT_SBINS - 1)), tag);
+    }
+};
+
+struct MisIO
+{
+    BinQ<RT_QBINS> queue;
+    const float4* pos_time;
+    const float4* mis_dir;
+    float4* mis_hit0;
+    __device__ __forceinline__ uint32_t count() const { return queue.total(); }
+    __device__ __forceinline__ bool load(uint32_t j, V3& o, V3& d, float& tmax, float& time, uint32_t& tag) const
+    {
+        tag = queue.at(j);
+        float4 a = pos_time[tag], b = mis_dir[tag];
+        o = xyz(a); d = xyz(b); tmax = RT_RAY_TMAX; time = a.w;
+        return true;
+    }
+    __device__ __forceinline__ void store(uint32_t tag, const WaveResult& r) const
+    {
+        mis_hit0[tag] = make_float4(r.t, __int_as_float(r.shape), __int_as_float(r.tri_rec), 0.0f);
     }
 };
 
 struct ShadowIO
 {
-    const uint32_t* queue;
+    BinQ<RT_QBINS> queue;
     const float4* pos_time;
     const float4* sh_dir;
     uint8_t* occluded;
+    __device__ __forceinline__ uint32_t count() const { return queue.total(); }
     __device__ __forceinline__ bool load(uint32_t j, V3& o, V3& d, float& tmax, float& time, uint32_t& tag) const
     {
-        tag = queue[j];
+        tag = queue.at(j);
         float4 a = pos_time[tag], b = sh_dir[tag];
         o = xyz(a); d = xyz(b); tmax = b.w; time = a.w;
         return true;
@@ -306,20 +375,32 @@ struct ShadowIO
     __device__ __forceinline__ void store(uint32_t tag, const WaveResult& r) const { occluded[tag] = r.any_hit ? 1 : 0; }
 };
 
+__host__ __device__ __forceinline__ PathIO make_path_io(const RenderCtx& c, int cur)
+{
+    PathIO io = { { c.q_path[cur], c.ctl + CTL_PATH(cur), c.qcap }, c.ray_o, c.ray_d, c.hit0, c.q_shade, c.ctl + CTL_SHADE };
+    return io;
+}
+__host__ __device__ __forceinline__ MisIO make_mis_io(const RenderCtx& c)
+{
+    MisIO io = { { c.q_mis, c.ctl + CTL_MIS, c.qcap }, c.pos_time, c.mis_dir, c.mis_hit0 };
+    return io;
+}
+__host__ __device__ __forceinline__ ShadowIO make_shadow_io(const RenderCtx& c)
+{
+    ShadowIO io = { { c.q_shadow, c.ctl + CTL_SHADOW, c.qcap }, c.pos_time, c.sh_dir, c.occluded };
+    return io;
+}
+
 // Path segments: closest hit (RaytraceMain.cpp:293-298)
 template <int CAP, bool COUNT>
 __global__ void __launch_bounds__(RT_BLOCK)
 k_trace_paths(const __grid_constant__ RenderCtx c, int cur)
 {
-    const uint32_t n = c.ctl[cur];
+    PathIO io = make_path_io(c, cur);
+    const uint32_t n = io.count();
     if (blockIdx.x == 0 && threadIdx.x == 0)
-    {
         atomicAdd(reinterpret_cast<unsigned long long*>(c.totals + 0), (unsigned long long)n);
-        c.ctl[cur ^ 1] = 0;          // queues the next kernel (shade) will fill
-        c.ctl[CTL_LIT] = 0;
-    }
     WorkCount wc = { 0, 0, 0, 0 };
-    PathIO io = { c.q_path[cur], c.ray_o, c.ray_d, c.hit0 };
     trace_wave<CAP, false, COUNT>(c.sc, io, n, c.ctl + CTL_CUR_PATH, wc);
     if (COUNT)
         flush_work_counters(wc, c.totals);
@@ -332,7 +413,7 @@ k_split_top(const __grid_constant__ DScene sc, const IO io, const SplitBufs sb, 
 {
     split_zero(ps);
     if (FRESH && count_slot >= 0 && blockIdx.x == 0 && threadIdx.x == 0)
-        atomicAdd(reinterpret_cast<unsigned long long*>(totals + count_slot), (unsigned long long)*ps.in_count);
+        atomicAdd(reinterpret_cast<unsigned long long*>(totals + count_slot), (unsigned long long)io.count());
     WorkCount wc = { 0, 0, 0, 0 };
     trace_top<ANY, COUNT, FRESH>(sc, io, sb, ps, wc);
     if (COUNT)
@@ -354,22 +435,20 @@ k_split_mesh(const __grid_constant__ DScene sc, const IO io, const SplitBufs sb,
 __global__ void __launch_bounds__(RT_BLOCK)
 k_shade(const __grid_constant__ RenderCtx c, int cur, uint32_t bounce)
 {
-    const uint32_t n = c.ctl[cur];
+    const BinQ<RT_SBINS> shade = { c.q_shade, c.ctl + CTL_SHADE, c.qcap };
+    const uint32_t n = shade.total();
     if (blockIdx.x == 0 && threadIdx.x == 0)
     {
-        c.ctl[CTL_SHADOW] = 0;
-        c.ctl[CTL_MIS] = 0;
+        for (int b = 0; b < RT_QBINS; ++b) { c.ctl[CTL_SHADOW + b] = 0; c.ctl[CTL_MIS + b] = 0; }
         c.ctl[CTL_CUR_SHADOW] = 0;
         c.ctl[CTL_CUR_MIS] = 0;
         c.ctl[CTL_CUR_PATH] = 0;
     }
     RT_GRID_STRIDE(j, n)
     {
-        bool lit = false, alive = false;
-        uint32_t i = 0;
         if (j < n)
         {
-            i = c.q_path[cur][j];
+            const uint32_t i = shade.at(j);
             float4 h0 = c.hit0[i];
             int shape = __float_as_int(h0.y);
             if (shape >= 0)
@@ -414,7 +493,7 @@ k_shade(const __grid_constant__ RenderCtx c, int cur, uint32_t bounce)
                         nd++;
                     if (!dirac && c.nls > 0)
                     {
-                        lit = true;
+                        bq_push(c.q_lit, c.ctl + CTL_LIT, c.qcap, 0, i);
                         c.light_thr[i] = make_float4(thr.r, thr.g, thr.b, 0.0f);
                         c.light_res[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                         c.pos_time[i] = make_float4(position.x, position.y, position.z, ro.w);
@@ -438,15 +517,14 @@ k_shade(const __grid_constant__ RenderCtx c, int cur, uint32_t bounce)
                         V3 nd3 = -incoming;
                         c.ray_o[i] = make_float4(position.x, position.y, position.z, ro.w);
                         c.ray_d[i] = make_float4(nd3.x, nd3.y, nd3.z, 0.0f);
-                        alive = nb < c.depth;
+                        if (nb < c.depth)
+                            bq_push(c.q_path[cur ^ 1], c.ctl + CTL_PATH(cur ^ 1), c.qcap, dir_octant(nd3), i);
                     }
                 }
                 c.thr[i] = make_float4(thr.r, thr.g, thr.b, __uint_as_float(nb | (nd << 8)));
                 c.res[i] = make_float4(result.r, result.g, result.b, 0.0f);
             }
         }
-        queue_push(c.q_lit, c.ctl + CTL_LIT, lit, i);
-        queue_push(c.q_path[cur ^ 1], c.ctl + (cur ^ 1), alive, i);
     }
 }
 
@@ -458,11 +536,9 @@ k_light_sample(const __grid_constant__ RenderCtx c, uint32_t bounce, uint32_t ls
     const uint32_t n = c.ctl[CTL_LIT];
     RT_GRID_STRIDE(j, n)
     {
-        bool want_shadow = false, want_mis = false;
-        uint32_t i = 0;
         if (j < n)
         {
-            i = c.q_lit[j];
+            const uint32_t i = c.q_lit[j];
             uint32_t p = i / c.spp, psi = i % c.spp;
             float4 pt = c.pos_time[i], wm = c.wo_mat[i], h1 = c.hit1[i];
             V3 position = xyz(pt), outgoing = xyz(wm), normal = xyz(h1);
@@ -510,7 +586,7 @@ k_light_sample(const __grid_constant__ RenderCtx c, uint32_t bounce, uint32_t ls
                     Color3 L = emitted * mkc(cm, cm, cm) * mc * bres * fabsf(dot3(sd, normal)) * mis / (lpdf * 1.0f);
                     c.sh_dir[i] = make_float4(sd.x, sd.y, sd.z, dist - RT_RAY_TMIN);
                     shl = make_float4(L.r, L.g, L.b, 1.0f);
-                    want_shadow = true;
+                    bq_push(c.q_shadow, c.ctl + CTL_SHADOW, c.qcap, dir_octant(sd), i);
                 }
             }
             c.sh_L[i] = shl;
@@ -528,12 +604,10 @@ k_light_sample(const __grid_constant__ RenderCtx c, uint32_t bounce, uint32_t ls
                 Color3 P = emitted * mkc(cm, cm, cm) * mc * bres * fabsf(dot3(pd, normal));
                 md = make_float4(pd.x, pd.y, pd.z, bpdf);
                 c.mis_P[i] = make_float4(P.r, P.g, P.b, __uint_as_float(light_shape));
-                want_mis = true;
+                bq_push(c.q_mis, c.ctl + CTL_MIS, c.qcap, dir_octant(pd), i);
             }
             c.mis_dir[i] = md;
         }
-        queue_push(c.q_shadow, c.ctl + CTL_SHADOW, want_shadow, i);
-        queue_push(c.q_mis, c.ctl + CTL_MIS, want_mis, i);
     }
 }
 
@@ -542,11 +616,11 @@ template <int CAP, bool COUNT>
 __global__ void __launch_bounds__(RT_BLOCK)
 k_trace_shadow(const __grid_constant__ RenderCtx c)
 {
-    const uint32_t n = c.ctl[CTL_SHADOW];
+    ShadowIO io = make_shadow_io(c);
+    const uint32_t n = io.count();
     if (blockIdx.x == 0 && threadIdx.x == 0)
         atomicAdd(reinterpret_cast<unsigned long long*>(c.totals + 1), (unsigned long long)n);
     WorkCount wc = { 0, 0, 0, 0 };
-    ShadowIO io = { c.q_shadow, c.pos_time, c.sh_dir, c.occluded };
     trace_wave<CAP, true, COUNT>(c.sc, io, n, c.ctl + CTL_CUR_SHADOW, wc);
     if (COUNT)
         flush_work_counters(wc, c.totals);
@@ -557,11 +631,11 @@ template <int CAP, bool COUNT>
 __global__ void __launch_bounds__(RT_BLOCK)
 k_trace_mis(const __grid_constant__ RenderCtx c)
 {
-    const uint32_t n = c.ctl[CTL_MIS];
+    MisIO io = make_mis_io(c);
+    const uint32_t n = io.count();
     if (blockIdx.x == 0 && threadIdx.x == 0)
         atomicAdd(reinterpret_cast<unsigned long long*>(c.totals + 0), (unsigned long long)n);
     WorkCount wc = { 0, 0, 0, 0 };
-    PathIO io = { c.q_mis, c.pos_time, c.mis_dir, c.mis_hit0 };
     trace_wave<CAP, false, COUNT>(c.sc, io, n, c.ctl + CTL_CUR_MIS, wc);
     if (COUNT)
         flush_work_counters(wc, c.totals);
@@ -575,8 +649,7 @@ k_resolve(const __grid_constant__ RenderCtx c, uint32_t lsi)
     const uint32_t n = c.ctl[CTL_LIT];
     if (blockIdx.x == 0 && threadIdx.x == 0)
     {
-        c.ctl[CTL_SHADOW] = 0;      // refilled by the next light sample, if any
-        c.ctl[CTL_MIS] = 0;
+        for (int b = 0; b < RT_QBINS; ++b) { c.ctl[CTL_SHADOW + b] = 0; c.ctl[CTL_MIS + b] = 0; }   // refilled by the next light sample
         c.ctl[CTL_CUR_SHADOW] = 0;
         c.ctl[CTL_CUR_MIS] = 0;
     }
@@ -820,11 +893,13 @@ inline size_t carve(RenderCtx& c, char* base, size_t samples, size_t pixels, uin
     c.mis_P = k.take<float4>(samples);
     c.mis_hit0 = k.take<float4>(samples);
     c.mis_hit1 = k.take<float4>(samples);
-    c.q_path[0] = k.take<uint32_t>(samples);
-    c.q_path[1] = k.take<uint32_t>(samples);
+    c.qcap = (uint32_t)samples;
+    c.q_path[0] = k.take<uint32_t>(samples * RT_QBINS);
+    c.q_path[1] = k.take<uint32_t>(samples * RT_QBINS);
+    c.q_shade = k.take<uint32_t>(samples * RT_SBINS);
     c.q_lit = k.take<uint32_t>(samples);
-    c.q_shadow = k.take<uint32_t>(samples);
-    c.q_mis = k.take<uint32_t>(samples);
+    c.q_shadow = k.take<uint32_t>(samples * RT_QBINS);
+    c.q_mis = k.take<uint32_t>(samples * RT_QBINS);
     c.q_meshq[0] = k.take<uint32_t>(samples);
     c.q_meshq[1] = k.take<uint32_t>(samples);
     c.q_resume[0] = k.take<uint32_t>(samples);
@@ -891,7 +966,7 @@ inline int rt_plan(const RtScene* s, const RtRenderParams* prm, RenderPlan& plan
     return RT_OK;
 }
 
-inline int rt_render_reserve(RtScene* s, const RenderPlan& plan)
+inline int rt_render_reserve(RtScene* s, RenderPlan& plan)
 {
     size_t pixels = (size_t)plan.tiles_per_batch * plan.tile * plan.tile;
     size_t samples = pixels * plan.spp;
@@ -910,7 +985,24 @@ inline int rt_render_reserve(RtScene* s, const RenderPlan& plan)
         rb->cap_samples = rb->cap_pixels = 0;
         RenderCtx probe;
         size_t bytes = rt_detail::carve(probe, NULL, samples, pixels, plan.slots);
-        RT_CUDA(cudaMalloc(&rb->block, bytes));
+        // leave room for the rest of the process: shrink the batch until it fits in
+        // at most 60 % of the free device memory, and on allocation failure
+        for (;;)
+        {
+            size_t free_b = 0, total_b = 0;
+            cudaMemGetInfo(&free_b, &total_b);
+            cudaError_t e = bytes <= free_b / 10 * 6 ? cudaMalloc(&rb->block, bytes) : cudaErrorMemoryAllocation;
+            if (e == cudaSuccess)
+                break;
+            cudaGetLastError();
+            rb->block = NULL;
+            if (plan.tiles_per_batch <= 1)
+                return rt_cuda_fail(cudaErrorMemoryAllocation, "wavefront state allocation");
+            plan.tiles_per_batch = (plan.tiles_per_batch + 1) / 2;
+            pixels = (size_t)plan.tiles_per_batch * plan.tile * plan.tile;
+            samples = pixels * plan.spp;
+            bytes = rt_detail::carve(probe, NULL, samples, pixels, plan.slots);
+        }
         rb->block_bytes = bytes;
         rb->cap_samples = samples;
         rb->cap_pixels = pixels;
@@ -948,13 +1040,13 @@ inline void rt_trace_mark(RenderBuffers* rb, bool timed, cudaStream_t st)
 // pass) once per mesh shape of the scene.  Counts live on the device; passes with an
 // empty queue exit at once.
 template <bool ANY, bool COUNT, class IO>
-static void rt_launch_split_stage(RtScene* s, const RenderCtx& c, const IO& io, const uint32_t* fresh_count,
+static void rt_launch_split_stage(RtScene* s, const RenderCtx& c, const IO& io,
                                   uint32_t* fresh_cursor, int count_slot, unsigned grid, cudaStream_t st, uint64_t& launches)
 {
     cudaMemsetAsync(c.ctl + CTL_MESH_N, 0, 8 * sizeof(uint32_t), st);
     SplitPass p;
     p.in_queue = NULL;
-    p.in_count = fresh_count;
+    p.in_count = NULL;           // the fresh pass counts its IO's binned queue
     p.cursor = fresh_cursor;
     p.out_queue = c.q_meshq[0];
     p.out_count = c.ctl + CTL_MESH_N + 0;
@@ -993,7 +1085,9 @@ static void rt_launch_split_stage(RtScene* s, const RenderCtx& c, const IO& io, 
 // Small kernel that does the queue bookkeeping k_trace_paths does in unified mode
 __global__ void k_stage_prologue(const __grid_constant__ RenderCtx c, int cur)
 {
-    c.ctl[cur ^ 1] = 0;
+    // counters of the queues this bounce's path trace and shade kernels fill
+    for (int b = 0; b < RT_QBINS; ++b) c.ctl[CTL_PATH(cur ^ 1) + b] = 0;
+    for (int b = 0; b < RT_SBINS; ++b) c.ctl[CTL_SHADE + b] = 0;
     c.ctl[CTL_LIT] = 0;
 }
 
@@ -1052,14 +1146,16 @@ static int rt_launch_batch(RtScene* s, const RenderCtx& c, cudaStream_t st, uint
         {
             uint64_t before = launches;
             k_stage_prologue<<<1, 1, 0, st>>>(c, cur);
-            PathIO io = { c.q_path[cur], c.ray_o, c.ray_d, c.hit0 };
-            rt_launch_split_stage<false, COUNT>(s, c, io, c.ctl + cur, c.ctl + CTL_CUR_PATH, 0, tg_split, st, launches);
+            PathIO io = make_path_io(c, cur);
+            rt_launch_split_stage<false, COUNT>(s, c, io, c.ctl + CTL_CUR_PATH, 0, tg_split, st, launches);
             launches += 1;
             trace_launches += launches - before;
             launches -= 1;      // the shared "+= 2" below accounts for trace + shade
         }
         else
         {
+            k_stage_prologue<<<1, 1, 0, st>>>(c, cur);
+            launches += 1;
             if (cap <= 32)      k_trace_paths<32, COUNT><<<tg_path, RT_BLOCK, 0, st>>>(c, cur);
             else if (cap <= 64) k_trace_paths<64, COUNT><<<tg_path, RT_BLOCK, 0, st>>>(c, cur);
             else                k_trace_paths<104, COUNT><<<tg_path, RT_BLOCK, 0, st>>>(c, cur);
@@ -1075,10 +1171,10 @@ static int rt_launch_batch(RtScene* s, const RenderCtx& c, cudaStream_t st, uint
             if (split)
             {
                 uint64_t before = launches;
-                ShadowIO sio = { c.q_shadow, c.pos_time, c.sh_dir, c.occluded };
-                rt_launch_split_stage<true, COUNT>(s, c, sio, c.ctl + CTL_SHADOW, c.ctl + CTL_CUR_SHADOW, 1, tg_split, st, launches);
-                PathIO mio = { c.q_mis, c.pos_time, c.mis_dir, c.mis_hit0 };
-                rt_launch_split_stage<false, COUNT>(s, c, mio, c.ctl + CTL_MIS, c.ctl + CTL_CUR_MIS, 0, tg_split, st, launches);
+                ShadowIO sio = make_shadow_io(c);
+                rt_launch_split_stage<true, COUNT>(s, c, sio, c.ctl + CTL_CUR_SHADOW, 1, tg_split, st, launches);
+                MisIO mio = make_mis_io(c);
+                rt_launch_split_stage<false, COUNT>(s, c, mio, c.ctl + CTL_CUR_MIS, 0, tg_split, st, launches);
                 trace_launches += launches - before;
                 launches -= 2;  // the shared "+= 4" below accounts for two traces
             }

@@ -102,7 +102,7 @@ __device__ __forceinline__ void trace_top(const DScene& sc, const IO& io, const 
 {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t lt_mask = (1u << lane) - 1;
-    const uint32_t n = *ps.in_count;
+    const uint32_t n = FRESH ? io.count() : *ps.in_count;
 
     uint32_t stk_node[RT_SPLIT_TOPCAP];
     float stk_t0[RT_SPLIT_TOPCAP];
