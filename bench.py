@@ -49,9 +49,20 @@ WORKLOADS = {
                      label="Rayito_Stage7 scene 1 480x270 256spp ls1 depth3"),
     "scene2": dict(recipe=2, width=3840, height=2160, ps=16, ls=1, depth=3, grid=(0, 0),
                    label="Rayito_Stage7 scene 2 (falling spheres, tumbling boxes) 3840x2160 256spp"),
-    "c5": dict(recipe=5, width=3840, height=2160, ps=8, ls=1, depth=3, grid=(2236, 2236),
-               label="synthetic displaced sphere, 4 999 696 quads = 9 999 392 triangles, 3840x2160 64spp"),
+    "c5": dict(recipe=5, width=3840, height=2160, ps=32, ls=1, depth=3, grid=(2236, 2236),
+               label="synthetic displaced sphere, 4 999 696 quads = 9 999 392 triangles, 3840x2160 1024spp"),
+    "c5-64spp": dict(recipe=5, width=3840, height=2160, ps=8, ls=1, depth=3, grid=(2236, 2236),
+                     label="synthetic displaced sphere, 4 999 696 quads = 9 999 392 triangles, 3840x2160 64spp"),
+    "c3": dict(recipe=6, stage=6, width=1920, height=1080, ps=8, ls=1, depth=3, grid=(0, 0),
+               label="Rayito_Stage6 scene (bumpy.obj, BVH, two area lights, Stage 6 rules) 1920x1080 64spp ls1 depth3"),
 }
+CAMERA_SPEC = {       # fov, origin, target, up, focal distance, lens radius, shutter open/close (GUI defaults)
+    1: [30, -4, 5, 15, 0, 0, 0, 0, 1, 0, 16, 0, 0, 1],
+    2: [30, -4, 10, 30, 0, 5, 0, 0, 1, 0, 16, 0, 0, 1],
+    5: [30, -4, 5, 15, 0, 0, 0, 0, 1, 0, 16, 0, 0, 1],
+    6: [30, -2, 5, 15, 0, 0, 0, 0, 1, 0, 16, 0, 0, 0],
+}
+NEEDS_OBJ = (1, 6)
 CPU_SAMPLE = dict(width=480, height=270)      # same scene, same spp, reduced resolution
 
 
@@ -137,10 +148,9 @@ def run_reference(args, wl, rank, world):
     from rayito_b200 import build
     import numpy as np
     cores = os.cpu_count() or 1
-    obj = build.model_path("bumpy.obj") if wl["recipe"] == 1 else None
-    scene = refapi.RefScene(wl["recipe"], obj, wl["grid"])
-    spec = np.array([30, -4, 5, 15, 0, 0, 0, 0, 1, 0, 16, 0, 0, 1], np.float32) if wl["recipe"] != 2 else \
-        np.array([30, -4, 10, 30, 0, 5, 0, 0, 1, 0, 16, 0, 0, 1], np.float32)
+    obj = build.model_path("bumpy.obj") if wl["recipe"] in NEEDS_OBJ else None
+    scene = refapi.RefScene(wl["recipe"], obj, wl["grid"], stage=wl.get("stage", 7))
+    spec = np.array(CAMERA_SPEC[wl["recipe"]], np.float32)
     W, H = CPU_SAMPLE["width"], CPU_SAMPLE["height"]
     times, rays = [], 0
     for step in range(args.warmup + args.steps):
@@ -204,7 +214,7 @@ def main():
     dev = torch.device("cuda", local_rank)
 
     # ---- scene: built with the C++ host API, flattened, uploaded once ------------
-    obj = build.model_path("bumpy.obj") if wl["recipe"] == 1 else None
+    obj = build.model_path("bumpy.obj") if wl["recipe"] in NEEDS_OBJ else None
     t0 = time.perf_counter()
     hscene = capi.HostScene(wl["recipe"], obj, wl["grid"])
     host_prepare_s = time.perf_counter() - t0
@@ -395,10 +405,10 @@ def measure_e2e(args, wl, capi, obj, spec, rank, world, local_rank, dev, dist, t
 
 def measure_cpu_baseline(wl, obj, spec):
     from oracle import refapi
-    if not refapi.available():
+    if not refapi.available(wl.get("stage", 7)):
         return {"value": None, "unit": "Mrays/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
     cores = os.cpu_count() or 1
-    scene = refapi.RefScene(wl["recipe"], obj, wl["grid"])
+    scene = refapi.RefScene(wl["recipe"], obj, wl["grid"], stage=wl.get("stage", 7))
     W, H = CPU_SAMPLE["width"], CPU_SAMPLE["height"]
     if wl["recipe"] == 5:
         W, H = 240, 135

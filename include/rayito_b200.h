@@ -162,7 +162,17 @@ typedef struct RtSceneDesc
 
     uint32_t num_materials;  const RtMaterial* materials;
     uint32_t num_lights;     const uint32_t* lights;     /* shape indices, findLights() order */
+
+    /* Which stage's rules apply (RT_SEMANTICS_*).  Stage 6 (Rayito_Stage6_QT) has no
+     * transforms at all (every xform must be keyless and is not applied, so a -0.0
+     * stays -0.0), a face claims a hit at its FIRST fan triangle (S6 RMesh.h:204-209),
+     * flat-shaded faces keep the un-normalised geometric normal (S6 RMesh.h:298), and
+     * the renderer loops over every light and counts emission at bounce 0 only
+     * (S6 RaytraceMain.cpp:250, 274-384). */
+    uint32_t semantics;
 } RtSceneDesc;
+
+enum { RT_SEMANTICS_STAGE7 = 0, RT_SEMANTICS_STAGE6 = 6 };
 
 /* PerspectiveCamera after its constructor ran (RaytraceMain.cpp:205-222). */
 typedef struct RtCamera

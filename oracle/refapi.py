@@ -24,15 +24,56 @@ class RefRenderStats(C.Structure):
                 ("closest_calls", C.c_uint64), ("any_calls", C.c_uint64), ("threads", C.c_uint)]
 
 
+LIB6_PATH = os.path.join(HERE, "_ref", "libref_s6.so")
+
 _lib = None
+_lib6 = None
 
 
-def available():
-    return os.path.exists(LIB_PATH)
+def available(stage=7):
+    return os.path.exists(LIB6_PATH if stage == 6 else LIB_PATH)
 
 
-def lib():
-    global _lib
+class _Stage6Lib:
+    """libref_s6.so (the unmodified Stage 6 core) under the Stage 7 driver's names: ref_x -> ref6_x"""
+
+    def __init__(self):
+        if not available(6):
+            raise RuntimeError("oracle/_ref/libref_s6.so is missing: run `make -C oracle ref` where /root/reference exists")
+        L = C.CDLL(LIB6_PATH, mode=C.RTLD_LOCAL)
+        vp = C.c_void_p
+        L.ref6_scene_create.restype = vp
+        L.ref6_scene_create.argtypes = [C.c_int, C.c_char_p, C.c_uint, C.c_uint]
+        L.ref6_scene_destroy.argtypes = [vp]
+        L.ref6_scene_num_finite.argtypes = [vp]
+        L.ref6_scene_num_infinite.argtypes = [vp]
+        L.ref6_scene_prepare_seconds.restype = C.c_double
+        L.ref6_scene_prepare_seconds.argtypes = [vp]
+        L.ref6_trace_closest.argtypes = [vp, vp, C.c_size_t, vp]
+        L.ref6_trace_any.argtypes = [vp, vp, C.c_size_t, vp]
+        L.ref6_render.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_uint, C.c_uint, C.c_uint, vp,
+                                  C.POINTER(RefRenderStats), C.c_int]
+        L.ref6_recorded_rays.restype = C.c_size_t
+        L.ref6_recorded_rays.argtypes = [C.c_int, vp, C.c_size_t]
+        L.ref6_bvh_nodes.restype = C.c_uint
+        L.ref6_bvh_nodes.argtypes = [vp, C.c_int, vp, C.c_uint]
+        L.ref6_mesh_counts.argtypes = [vp, C.c_int] + [C.POINTER(C.c_uint)] * 4
+        L.ref6_mesh_data.argtypes = [vp, C.c_int] + [vp] * 7
+        L.ref6_build_info.restype = C.c_char_p
+        self._L = L
+
+    def __getattr__(self, name):
+        if name.startswith("ref_"):
+            return getattr(self._L, "ref6_" + name[4:])
+        raise AttributeError(name)
+
+
+def lib(stage=7):
+    global _lib, _lib6
+    if stage == 6:
+        if _lib6 is None:
+            _lib6 = _Stage6Lib()
+        return _lib6
     if _lib is None:
         if not available():
             raise RuntimeError("oracle/_ref/libref_s7.so is missing: run `make -C oracle ref` where /root/reference exists")
@@ -69,57 +110,58 @@ def lib():
 class RefScene:
     """A recipe scene built against the reference's own classes and prepared once."""
 
-    def __init__(self, recipe, obj_path=None, grid=(0, 0)):
-        self.handle = lib().ref_scene_create(recipe, obj_path.encode() if obj_path else None, grid[0], grid[1])
+    def __init__(self, recipe, obj_path=None, grid=(0, 0), stage=7):
+        self.stage = stage
+        self.handle = lib(stage).ref_scene_create(recipe, obj_path.encode() if obj_path else None, grid[0], grid[1])
         if not self.handle:
             raise RuntimeError("ref_scene_create failed")
 
     @property
     def num_finite(self):
-        return lib().ref_scene_num_finite(self.handle)
+        return lib(self.stage).ref_scene_num_finite(self.handle)
 
     @property
     def num_infinite(self):
-        return lib().ref_scene_num_infinite(self.handle)
+        return lib(self.stage).ref_scene_num_infinite(self.handle)
 
     def trace_closest(self, rays):
         rays = np.ascontiguousarray(rays)
         out = np.zeros(len(rays), REFHIT_DTYPE)
-        lib().ref_trace_closest(self.handle, rays.ctypes.data, len(rays), out.ctypes.data)
+        lib(self.stage).ref_trace_closest(self.handle, rays.ctypes.data, len(rays), out.ctypes.data)
         return out
 
     def trace_any(self, rays):
         rays = np.ascontiguousarray(rays)
         out = np.zeros(len(rays), np.uint8)
-        lib().ref_trace_any(self.handle, rays.ctypes.data, len(rays), out.ctypes.data)
+        lib(self.stage).ref_trace_any(self.handle, rays.ctypes.data, len(rays), out.ctypes.data)
         return out
 
     def render(self, camera_spec14, width, height, ps, ls=1, depth=3, record_rays=False):
         spec = np.ascontiguousarray(camera_spec14, np.float32)
         img = np.zeros((height, width, 3), np.float32)
         stats = RefRenderStats()
-        rc = lib().ref_render(self.handle, spec.ctypes.data, width, height, ps, ls, depth, img.ctypes.data,
+        rc = lib(self.stage).ref_render(self.handle, spec.ctypes.data, width, height, ps, ls, depth, img.ctypes.data,
                               C.byref(stats), 1 if record_rays else 0)
         if rc != 0:
             raise RuntimeError("ref_render failed")
         return img, stats
 
     def recorded_rays(self, kind, dtype):
-        n = lib().ref_recorded_rays(kind, None, 0)
+        n = lib(self.stage).ref_recorded_rays(kind, None, 0)
         out = np.zeros(n, dtype)
-        lib().ref_recorded_rays(kind, out.ctypes.data, n)
+        lib(self.stage).ref_recorded_rays(kind, out.ctypes.data, n)
         return out
 
     def bvh_nodes(self, shape=-1):
-        n = lib().ref_bvh_nodes(self.handle, shape, None, 0)
+        n = lib(self.stage).ref_bvh_nodes(self.handle, shape, None, 0)
         out = np.zeros((n, 8), np.uint32)
         if n:
-            lib().ref_bvh_nodes(self.handle, shape, out.ctypes.data, n)
+            lib(self.stage).ref_bvh_nodes(self.handle, shape, out.ctypes.data, n)
         return out
 
     def mesh(self, shape):
         counts = [C.c_uint() for _ in range(4)]
-        if lib().ref_mesh_counts(self.handle, shape, *[C.byref(c) for c in counts]) != 0:
+        if lib(self.stage).ref_mesh_counts(self.handle, shape, *[C.byref(c) for c in counts]) != 0:
             return None
         nv, nn, nf, ni = [c.value for c in counts]
         m = {
@@ -128,21 +170,21 @@ class RefScene:
             "normal_index": np.zeros(ni, np.uint32), "area_cdf": np.zeros(nf + 1, np.float32),
             "bbox": np.zeros(6, np.float32),
         }
-        lib().ref_mesh_data(self.handle, shape, m["vertices"].ctypes.data, m["normals"].ctypes.data,
+        lib(self.stage).ref_mesh_data(self.handle, shape, m["vertices"].ctypes.data, m["normals"].ctypes.data,
                             m["face_sizes"].ctypes.data, m["vertex_index"].ctypes.data,
                             m["normal_index"].ctypes.data, m["area_cdf"].ctypes.data, m["bbox"].ctypes.data)
         return m
 
     def shape_keys(self, shape):
-        n = lib().ref_shape_keys(self.handle, shape, None, 0)
+        n = lib(self.stage).ref_shape_keys(self.handle, shape, None, 0)
         out = np.zeros((n, 11), np.float32)
         if n:
-            lib().ref_shape_keys(self.handle, shape, out.ctypes.data, n)
+            lib(self.stage).ref_shape_keys(self.handle, shape, out.ctypes.data, n)
         return out
 
     def close(self):
         if self.handle:
-            lib().ref_scene_destroy(self.handle)
+            lib(self.stage).ref_scene_destroy(self.handle)
             self.handle = None
 
     def __del__(self):

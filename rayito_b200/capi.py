@@ -72,7 +72,7 @@ class RtSceneDesc(C.Structure):
                 ("num_mesh_nodes", _u), ("mesh_nodes", _p),
                 ("num_cdf", _u), ("face_area_cdf", _p),
                 ("num_materials", _u), ("materials", _p),
-                ("num_lights", _u), ("lights", _p)]
+                ("num_lights", _u), ("lights", _p), ("semantics", _u)]
 
 
 class RtMesh(C.Structure):
@@ -95,6 +95,7 @@ RECIPE_STAGE7_SCENE1 = 1
 RECIPE_STAGE7_SCENE2 = 2
 RECIPE_STAGE7_SCENE1_MESHLIGHT = 3
 RECIPE_SYNTHETIC_MESH = 5
+RECIPE_STAGE6_SCENE = 6
 
 # Every symbol include/rayito_b200.h declares (checked by the CPU test-suite)
 CORE_SYMBOLS = [

@@ -128,6 +128,7 @@ struct DScene
     uint32_t num_finite, num_infinite;
     uint32_t num_top_nodes;
     uint32_t num_lights;
+    uint32_t stage6;             // RT_SEMANTICS_STAGE6 rules (no transforms, first fan triangle wins, ...)
 
     const DShapeMem* shapes;
     const DNode* top_nodes;
@@ -198,6 +199,7 @@ struct TRS
     float qw;    // rotation(time)
     V3 qv;
     V3 s;        // scaling(time)
+    bool absent; // Stage 6: the shape has no transform at all (nothing is applied, -0.0 stays -0.0)
 };
 
 // q * v = v + w*t + cross(qv, t), t = 2 cross(qv, v)   (RMath.h:536-549)
@@ -233,6 +235,7 @@ __device__ __forceinline__ uint32_t xform_bracket(const float* __restrict__ time
 __device__ __noinline__ TRS xform_eval(const DScene& sc, uint32_t xform, float time)
 {
     TRS r;
+    r.absent = sc.stage6 != 0;
     DXform x = sc.xforms[xform];
     if (x.num_keys == 0)
     {
@@ -314,9 +317,9 @@ __device__ __forceinline__ bool no_zero_component(V3 v)
     return v.x != 0.0f && v.y != 0.0f && v.z != 0.0f;
 }
 
-__device__ __forceinline__ V3 rotate_exact(float qw, V3 qv, V3 v, bool identity)
+__device__ __forceinline__ V3 rotate_exact(float qw, V3 qv, V3 v, bool identity, bool absent = false)
 {
-    if (identity && no_zero_component(v))
+    if (absent || (identity && no_zero_component(v)))
         return v;
     return quat_rotate(qw, qv, v);
 }
@@ -328,27 +331,27 @@ __device__ __noinline__ V3 scale_divide(V3 r, V3 s) { return r / s; }
 // Transform::toLocalPoint / toLocalVector (RMath.h:814-827)
 __device__ __forceinline__ V3 to_local_point(const TRS& x, V3 p)
 {
-    V3 r = rotate_exact(x.qw, -x.qv, p - x.t, trs_identity_rotation(x));
+    V3 r = rotate_exact(x.qw, -x.qv, p - x.t, trs_identity_rotation(x), x.absent);
     return trs_unit_scale(x) ? r : scale_divide(r, x.s);
 }
 __device__ __forceinline__ V3 to_local_vector(const TRS& x, V3 v)
 {
-    V3 r = rotate_exact(x.qw, -x.qv, v, trs_identity_rotation(x));
+    V3 r = rotate_exact(x.qw, -x.qv, v, trs_identity_rotation(x), x.absent);
     return trs_unit_scale(x) ? r : scale_divide(r, x.s);
 }
 // fromLocalPoint / fromLocalVector / fromLocalNormal (RMath.h:819-842)
 __device__ __forceinline__ V3 from_local_point(const TRS& x, V3 p)
 {
     V3 v = trs_unit_scale(x) ? p : p * x.s;        // p * 1 == p
-    return rotate_exact(x.qw, x.qv, v, trs_identity_rotation(x)) + x.t;
+    return rotate_exact(x.qw, x.qv, v, trs_identity_rotation(x), x.absent) + x.t;
 }
 __device__ __forceinline__ V3 from_local_vector(const TRS& x, V3 v)
 {
     V3 w = trs_unit_scale(x) ? v : v * x.s;
-    return rotate_exact(x.qw, x.qv, w, trs_identity_rotation(x));
+    return rotate_exact(x.qw, x.qv, w, trs_identity_rotation(x), x.absent);
 }
-__device__ __forceinline__ V3 from_local_normal(const TRS& x, V3 n) { return rotate_exact(x.qw, x.qv, n, trs_identity_rotation(x)); }
-__device__ __forceinline__ V3 to_local_normal(const TRS& x, V3 n) { return rotate_exact(x.qw, -x.qv, n, trs_identity_rotation(x)); }
+__device__ __forceinline__ V3 from_local_normal(const TRS& x, V3 n) { return rotate_exact(x.qw, x.qv, n, trs_identity_rotation(x), x.absent); }
+__device__ __forceinline__ V3 to_local_normal(const TRS& x, V3 n) { return rotate_exact(x.qw, -x.qv, n, trs_identity_rotation(x), x.absent); }
 
 // ---------------------------------------------------------------------------
 // Slab test (BBox::intersects, RAccel.h:47-59).  t0/t1 are clipped in place.

@@ -58,7 +58,9 @@ struct RenderCtx
     uint32_t width, height;
     uint32_t ps, ls, depth;
     uint32_t spp;               // ps * ps
-    uint32_t nls;               // ls * ls light samples per bounce (0 when the scene has no lights)
+    uint32_t nls;               // light-sample iterations per bounce: ls*ls (Stage 7, one random light each),
+                                // num_lights*ls*ls (Stage 6, every light in turn); 0 without lights
+    uint32_t ls2;               // ls * ls
     uint32_t tile, tiles_x;
     uint32_t num_pixels;        // pixels in this batch (tiles * tile^2, some may be off-image)
     uint32_t num_samples;       // num_pixels * spp
@@ -478,7 +480,8 @@ k_shade(const __grid_constant__ RenderCtx c, int cur, uint32_t bounce)
                 RtMaterial mat = c.sc.materials[sh.material];
 
                 // Emission only when seen directly or through mirrors (:303-306)
-                if (nb == 0 || nb == nd)
+                // (Stage 6: only when seen directly, S6 RaytraceMain.cpp:250)
+                if (nb == 0 || (nb == nd && !c.sc.stage6))
                     result = result + thr * mkc(mat.emittance[0], mat.emittance[1], mat.emittance[2]);
 
                 if (mat.brdf != RT_BRDF_NONE)      // an Emitter ends the path (:320-323)
@@ -546,7 +549,6 @@ k_light_sample(const __grid_constant__ RenderCtx c, uint32_t bounce, uint32_t ls
             RtMaterial mat = c.sc.materials[__float_as_uint(wm.w)];
             Color3 mc = mkc(mat.color[0], mat.color[1], mat.color[2]);
 
-            uint32_t idx = psi * c.nls + lsi;
             uint32_t n1 = c.ps * c.ls * c.ps * c.ls, n2 = c.ps * c.ls;
             const uint32_t* pp = c.perms + (size_t)(5 * bounce) * c.num_pixels + p;
             uint32_t perm_sel = pp[(size_t)1 * c.num_pixels];
@@ -554,11 +556,28 @@ k_light_sample(const __grid_constant__ RenderCtx c, uint32_t bounce, uint32_t ls
             uint32_t perm_light = pp[(size_t)3 * c.num_pixels];
             uint32_t perm_brdf = pp[(size_t)4 * c.num_pixels];
 
-            // Random light (:358-364)
-            float liu = cmj_sample1d(idx, n1, perm_sel);
-            uint32_t light_index = (uint32_t)(liu * (float)c.sc.num_lights);
-            if (light_index >= c.sc.num_lights)
-                light_index = c.sc.num_lights - 1;
+            uint32_t idx, light_index;
+            if (c.sc.stage6)
+            {
+                // Every light in turn, ls*ls samples each (S6 RaytraceMain.cpp:274-384).
+                // The reference draws these from one serial, data-dependent Rng, which has
+                // no parallel equivalent; the counter-based stream stands in (same strata,
+                // decorrelated per light), so Stage 6 images match statistically, not bitwise.
+                light_index = lsi / c.ls2;
+                idx = psi * c.ls2 + lsi % c.ls2;
+                uint32_t salt = (light_index + 1u) * 0x9e3779b9u;
+                salt ^= salt >> 15; salt *= 0x85ebca6bu; salt ^= salt >> 13;
+                perm_elem ^= salt; perm_light ^= salt * 0x9e3779b9u; perm_brdf ^= salt * 0x85ebca6bu;
+            }
+            else
+            {
+                // Random light (:358-364)
+                idx = psi * c.nls + lsi;
+                float liu = cmj_sample1d(idx, n1, perm_sel);
+                light_index = (uint32_t)(liu * (float)c.sc.num_lights);
+                if (light_index >= c.sc.num_lights)
+                    light_index = c.sc.num_lights - 1;
+            }
             uint32_t light_shape = c.sc.lights[light_index];
             DShape lsh = load_shape(c.sc, light_shape);
             RtMaterial lmat = c.sc.materials[lsh.material];
@@ -690,7 +709,20 @@ k_resolve(const __grid_constant__ RenderCtx c, uint32_t lsi)
                 }
             }
         }
-        if (lsi + 1 == c.nls)
+        if (c.sc.stage6)
+        {
+            // after a light's last sample: average and add (S6 RaytraceMain.cpp:375-383)
+            if ((lsi + 1) % c.ls2 == 0)
+            {
+                lr = lr / (float)c.ls2;
+                float4 rs = c.res[i];
+                Color3 result = rgb(rs) + rgb(c.light_thr[i]) * lr;
+                c.res[i] = make_float4(result.r, result.g, result.b, 0.0f);
+                lr = mkc(0.0f, 0.0f, 0.0f);
+            }
+            c.light_res[i] = make_float4(lr.r, lr.g, lr.b, 0.0f);
+        }
+        else if (lsi + 1 == c.nls)
         {
             float weight = (float)c.sc.num_lights / (float)c.nls;
             lr = lr * weight;
@@ -1209,7 +1241,10 @@ inline int rt_fill_ctx(RtScene* s, const RtCamera* camera, const RtRenderParams*
     c.depth = prm->max_ray_depth;
     c.spp = plan.spp;
     // samplers.m_numLightSamples = lights.empty() ? 0 : ls*ls  (RaytraceMain.cpp:77)
-    c.nls = s->d.num_lights == 0 ? 0 : prm->light_samples_hint * prm->light_samples_hint;
+    c.ls2 = prm->light_samples_hint * prm->light_samples_hint;
+    c.nls = s->d.num_lights == 0 ? 0 : c.ls2;
+    if (s->d.stage6)
+        c.nls = s->d.num_lights * c.ls2;
     c.tile = plan.tile;
     c.tiles_x = plan.tiles_x;
     c.aspect = (float)prm->width / (float)prm->height;

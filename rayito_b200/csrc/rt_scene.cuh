@@ -131,9 +131,13 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
     if (desc->num_finite <= 2 && desc->num_top_nodes != 0)
         return rt_fail(RT_ERR_ARG, "a top-level BVH is only used with more than two finite shapes");
 
+    if (desc->semantics != RT_SEMANTICS_STAGE7 && desc->semantics != RT_SEMANTICS_STAGE6)
+        return rt_fail(RT_ERR_ARG, "unknown RtSceneDesc.semantics");
     for (uint32_t i = 0; i < desc->num_xforms; ++i)
     {
         const RtXform& x = desc->xforms[i];
+        if (desc->semantics == RT_SEMANTICS_STAGE6 && x.num_keys != 0)
+            return rt_fail(RT_ERR_ARG, "Stage 6 semantics has no transforms: every xform must be keyless");
         if ((uint64_t)x.first_key + x.num_keys > desc->num_keys)
             return rt_fail(RT_ERR_ARG, "transform key range out of bounds");
         for (uint32_t k = 1; k < x.num_keys; ++k)
@@ -447,6 +451,7 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
     d.num_infinite = desc->num_infinite;
     d.num_top_nodes = desc->num_top_nodes;
     d.num_lights = desc->num_lights;
+    d.stage6 = desc->semantics == RT_SEMANTICS_STAGE6 ? 1u : 0u;
     d.shapes = reinterpret_cast<const DShapeMem*>(base + o_shapes);
     d.top_nodes = reinterpret_cast<const DNode*>(base + o_top);
     d.mesh_nodes = reinterpret_cast<const DNode*>(base + o_mnodes);

@@ -529,6 +529,7 @@ __device__ __forceinline__ void trace_mesh(const DScene& sc, const IO& io, const
                     if (ANY) { any_hit = true; sp = 0; break; }
                     best = t;
                     best_rec = (int32_t)(park_word + k);
+                    if (sc.stage6) break;        // S6 RMesh.h:204-209
                 }
             }
             parked = false;

@@ -94,6 +94,7 @@ __device__ __forceinline__ TRS shape_xform(const DScene& sc, const DShape& sh, f
     if (sh.xkind == RT_XF_STATIC)
     {
         TRS r;
+        r.absent = sc.stage6 != 0;
         r.t = mk(sh.tx, sh.ty, sh.tz);
         r.s = mk(1.0f, 1.0f, 1.0f);
         r.qw = 1.0f;
@@ -175,7 +176,7 @@ __device__ __forceinline__ void hit_shading_inputs(const DScene& sc, const Local
         }
         else
         {
-            sn = normalized3(g);
+            sn = sc.stage6 ? g : normalized3(g);      // Stage 6 keeps the raw cross product (S6 RMesh.h:298)
         }
         n = from_local_normal(trs, sn);
     }

@@ -236,6 +236,7 @@ __device__ __forceinline__ void trace_wave(const DScene& sc, const IO& io, uint3
                     res.t = t;
                     res.shape = (int32_t)mesh_shape;
                     res.tri_rec = (int32_t)(park_word + k);
+                    if (sc.stage6) break;        // S6 RMesh.h:204-209: the first fan triangle to hit claims the face
                 }
             }
             parked = PARK_NONE;

@@ -15,6 +15,7 @@
 #include "rayito.h"
 #include "RMesh.h"
 #include "scene_recipes.h"
+#include "scene_recipes_s6.h"
 #include "rayito_b200_host.h"
 
 namespace Rayito
@@ -173,6 +174,7 @@ Image* raytrace(ShapeSet& scene,
     rayito_b200::FlatScene flat;
     if (!scene.flattenScene(flat, lights))
         throw std::runtime_error("rayito_b200: cannot flatten scene: " + flat.error);
+    flat.semantics = rayito_b200::stageSemantics();
     RtCamera camera;
     if (!cam.describe(camera))
         throw std::runtime_error("rayito_b200: camera has no device description");
@@ -217,6 +219,12 @@ Image* raytrace(ShapeSet& scene,
 namespace rayito_b200
 {
 
+unsigned& stageSemantics()
+{
+    static unsigned semantics = RT_SEMANTICS_STAGE7;
+    return semantics;
+}
+
 RenderOptions& renderOptions()
 {
     static RenderOptions options;
@@ -252,6 +260,14 @@ namespace
 {
 thread_local std::string t_hostError;
 
+// The recipe entry points pick the stage rules per call and restore them afterwards
+struct StageScope
+{
+    unsigned saved;
+    explicit StageScope(unsigned semantics) : saved(rayito_b200::stageSemantics()) { rayito_b200::stageSemantics() = semantics; }
+    ~StageScope() { rayito_b200::stageSemantics() = saved; }
+};
+
 RthScene* finish(RthScene* s, bool built)
 {
     if (!built)
@@ -260,6 +276,7 @@ RthScene* finish(RthScene* s, bool built)
         delete s;
         return NULL;
     }
+    s->flat.semantics = rayito_b200::stageSemantics();
     s->set.findLights(s->lights);
     struct timespec a, b;
     clock_gettime(CLOCK_MONOTONIC, &a);
@@ -286,8 +303,13 @@ RthScene* rth_scene_create(int recipe, const char* obj_path, unsigned grid_u, un
 {
     RthScene* s = new RthScene();
     bool built = false;
+    StageScope stage(recipe == RTH_RECIPE_STAGE6_SCENE ? RT_SEMANTICS_STAGE6 : RT_SEMANTICS_STAGE7);
     switch (recipe)
     {
+    case RTH_RECIPE_STAGE6_SCENE:
+        s->cameraSpec = rayito_recipes::defaultCameraStage6();
+        built = rayito_recipes::buildStage6Scene(s->set, s->store, obj_path ? obj_path : "");
+        break;
     case RTH_RECIPE_STAGE7_SCENE1:
         s->cameraSpec = rayito_recipes::defaultCameraScene1();
         built = rayito_recipes::buildStage7Scene1(s->set, s->store, obj_path ? obj_path : "");
@@ -354,8 +376,10 @@ int rth_raytrace(int recipe, const char* obj_path, unsigned grid_u, unsigned gri
         Rayito::ShapeSet set;
         rayito_recipes::SceneStore store;
         bool built = false;
+        StageScope stage(recipe == RTH_RECIPE_STAGE6_SCENE ? RT_SEMANTICS_STAGE6 : RT_SEMANTICS_STAGE7);
         switch (recipe)
         {
+        case RTH_RECIPE_STAGE6_SCENE: built = rayito_recipes::buildStage6Scene(set, store, obj_path ? obj_path : ""); break;
         case RTH_RECIPE_STAGE7_SCENE1: built = rayito_recipes::buildStage7Scene1(set, store, obj_path ? obj_path : ""); break;
         case RTH_RECIPE_STAGE7_SCENE1_MESHLIGHT: built = rayito_recipes::buildStage7Scene1(set, store, obj_path ? obj_path : "", true); break;
         case RTH_RECIPE_STAGE7_SCENE2: built = rayito_recipes::buildStage7Scene2(set, store); break;

@@ -145,7 +145,9 @@ class Bvh
 public:
     explicit Bvh(T& object) : m_object(object), m_maxDepth(0) { }
 
-    bool build()
+    // rootBox: box of the root node when it is not the union of the element boxes
+    // (Stage 6 passes m_object.bbox(), S6 RAccel.h:259; Stage 7 the union, RAccel.h:284)
+    bool build(const BBox* rootBox = NULL)
     {
         m_nodes.clear();
         m_maxDepth = 0;
@@ -168,7 +170,7 @@ public:
         // pre-order: a node reserves both child slots, then its left subtree is
         // built completely before its right subtree (RAccel.h:366-371).
         std::vector<Job> jobs;
-        Job root = { 0, count, 0, 0, whole };
+        Job root = { 0, count, 0, 0, rootBox ? *rootBox : whole };
         jobs.push_back(root);
         while (!jobs.empty())
         {

@@ -18,6 +18,12 @@
 namespace rayito_b200
 {
 
+// Which tutorial stage's rules raytrace() and prepare() follow: RT_SEMANTICS_STAGE7
+// (default) or RT_SEMANTICS_STAGE6 (see RtSceneDesc.semantics).  Process-wide; an
+// application built for the Stage 6 API sets it once before building its scene
+// (or compiles with -DRAYITO_B200_STAGE=6, see rayito.h).
+unsigned& stageSemantics();
+
 struct FlatScene
 {
     unsigned setXform;
@@ -43,9 +49,10 @@ struct FlatScene
     std::vector<RtMaterial> materials;
     std::vector<uint32_t> lights;
 
+    unsigned semantics;          // RT_SEMANTICS_*
     std::string error;
 
-    FlatScene() : setXform(0), numFinite(0), numInfinite(0), topDepth(0) { }
+    FlatScene() : setXform(0), numFinite(0), numInfinite(0), topDepth(0), semantics(RT_SEMANTICS_STAGE7) { }
 
     unsigned addXform(const Rayito::Transform& t)
     {
@@ -111,6 +118,7 @@ struct FlatScene
         d.num_cdf = (uint32_t)faceAreaCdf.size();      d.face_area_cdf = ptr(faceAreaCdf);
         d.num_materials = (uint32_t)materials.size();  d.materials = ptr(materials);
         d.num_lights = (uint32_t)lights.size();        d.lights = ptr(lights);
+        d.semantics = semantics;
         return d;
     }
 

@@ -78,6 +78,24 @@ public:
         m_up = cross(m_right, m_forward);
     }
 
+    // Stage 6 signature (S6 RaytraceMain.cpp:152-157): no shutter
+    PerspectiveCamera(float fieldOfViewInDegrees,
+                      const Point& origin,
+                      const Vector& target,
+                      const Vector& targetUpDirection,
+                      float focalDistance,
+                      float lensRadius)
+        : Camera(0.0f, 0.0f),
+          m_origin(origin),
+          m_forward((target - origin).normalized()),
+          m_tanFov(std::tan(fieldOfViewInDegrees * M_PI / 180.0f)),
+          m_focalDistance(focalDistance),
+          m_lensRadius(lensRadius)
+    {
+        m_right = cross(m_forward, targetUpDirection);
+        m_up = cross(m_right, m_forward);
+    }
+
     virtual bool describe(RtCamera& out) const
     {
         out.origin[0] = m_origin.m_x; out.origin[1] = m_origin.m_y; out.origin[2] = m_origin.m_z;

@@ -349,7 +349,10 @@ public:
         }
         m_faceAreaCDF.push_back(m_totalArea);
 
-        m_bvh.build();
+        if (rayito_b200::stageSemantics() == RT_SEMANTICS_STAGE6)
+            m_bvh.build(&m_bbox);       // all vertices, used by a face or not (S6 RMesh.h:82-86)
+        else
+            m_bvh.build();
     }
 
     virtual unsigned int numElements() const { return (unsigned int)m_faces.size(); }

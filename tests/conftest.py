@@ -67,3 +67,22 @@ def scene5_host(capi):
 @pytest.fixture(scope="session")
 def scene5_ref(ref):
     return ref.RefScene(5, None, SYNTH_GRID)
+
+
+@pytest.fixture(scope="session")
+def ref6():
+    """The compiled Stage 6 reference (oracle/_ref/libref_s6.so)."""
+    from oracle import refapi
+    if not refapi.available(6):
+        pytest.skip("oracle/_ref/libref_s6.so not built")
+    return refapi
+
+
+@pytest.fixture(scope="session")
+def scene6_host(capi, obj_path):
+    return capi.HostScene(capi.RECIPE_STAGE6_SCENE, obj_path)
+
+
+@pytest.fixture(scope="session")
+def scene6_ref(ref6, obj_path):
+    return ref6.RefScene(6, obj_path, stage=6)

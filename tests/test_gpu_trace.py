@@ -106,6 +106,44 @@ def test_synthetic_mesh_scene(capi, scene5_host, scene5_ref):
     dev.close()
 
 
+def test_stage6_scene(capi, scene6_host, scene6_ref):
+    """Stage 6 rules (config C3): no transforms at all (-0.0 is not canonicalised), a face
+    claims the hit at its first fan triangle, flat normals stay un-normalised."""
+    assert scene6_host.desc.contents.semantics == 6
+    dev = capi.DeviceScene(scene6_host.desc)
+    rays = random_rays(1 << 18, seed=61, center=(0, -0.5, 0), radius=12.0, target_radius=4.0)
+    hits = _compare_closest(dev, scene6_ref, rays, "stage6 random")
+    assert set(np.unique(hits["shape"])) >= set(range(-1, 9))
+    rays = random_rays(1 << 18, seed=62, center=(0.0, 0.0, 0.0), radius=6.0, target_radius=1.4)
+    hits = _compare_closest(dev, scene6_ref, rays, "stage6 mesh focus")
+    assert (hits["shape"] == 5).mean() > 0.3
+    _compare_any(dev, scene6_ref, rays, "stage6 mesh focus any")
+    # the box (shape 4): flat shading keeps the raw cross product as the normal
+    rays = random_rays(1 << 16, seed=63, center=(0.5, -1.5, -1.5), radius=5.0, target_radius=0.8)
+    hits = _compare_closest(dev, scene6_ref, rays, "stage6 box")
+    assert (hits["shape"] == 4).mean() > 0.3
+    rays = axis_parallel_rays(1 << 16, seed=64)
+    _compare_closest(dev, scene6_ref, rays, "stage6 axis-parallel")
+    _compare_any(dev, scene6_ref, rays, "stage6 axis-parallel any")
+    rays = random_rays(1 << 17, seed=65, center=(0, -0.5, 0), radius=12.0, target_radius=4.0, shadow_fraction=0.7)
+    _compare_any(dev, scene6_ref, rays, "stage6 any")
+    dev.close()
+
+
+def test_stage6_recorded_path_rays(capi, scene6_host, scene6_ref):
+    """Every ray the Stage 6 reference casts while rendering a small frame."""
+    dev = capi.DeviceScene(scene6_host.desc)
+    spec = scene6_host.default_camera_spec()
+    _img, stats = scene6_ref.render(spec, 96, 54, 2, ls=1, depth=3, record_rays=True)
+    closest = scene6_ref.recorded_rays(0, capi.RAY_DTYPE)
+    shadow = scene6_ref.recorded_rays(1, capi.RAY_DTYPE)
+    assert len(closest) == stats.closest_calls and len(shadow) == stats.any_calls
+    assert len(closest) > 50000 and len(shadow) > 20000
+    _compare_closest(dev, scene6_ref, closest, "stage6 recorded closest")
+    _compare_any(dev, scene6_ref, shadow, "stage6 recorded any")
+    dev.close()
+
+
 def test_empty_and_tiny_batches(dev1, capi):
     empty = np.zeros(0, capi.RAY_DTYPE)
     assert len(dev1.trace_closest(empty)) == 0
