@@ -292,6 +292,60 @@ typedef struct RtStage1Plane
 int rt_stage1_render(int device, const RtStage1Plane* planes, uint32_t num_planes, const RtCamera* camera,
                      uint32_t width, uint32_t height, uint8_t* rgb8);
 
+/* ---- Stage 2 / Stage 3: the serial-Rng programs ------------------------------- */
+/* Rayito_Stage2/main.cpp and Rayito_Stage3/main.cpp (BASELINE config C2 is the Stage 3
+ * pixel-sample sweep).  A handful of analytic shapes in a linear list, closest hit also
+ * for shadow rays, kRayTMin = 1e-5, ONE Rng for the whole image in scan order.  The
+ * library finds every sample's position in that stream on the device (see
+ * csrc/rt_stage23.cuh) and reproduces the programs' images bit for bit. */
+enum { RT_S23_PLANE = 0, RT_S23_SPHERE = 1, RT_S23_RECT = 2 };
+enum { RT_S23_MAT_LAMBERT = 0, RT_S23_MAT_PHONG = 1, RT_S23_MAT_EMITTER = 2 };
+enum { RT_S23_MAX_SHAPES = 16, RT_S23_MAX_LIGHTS = 4 };
+
+typedef struct RtS23Shape
+{
+    uint32_t type;          /* RT_S23_* */
+    uint32_t material;      /* index into RtS23Scene.materials; a light's is its Emitter */
+    float position[3];      /* plane point / sphere centre / rectangle corner */
+    float normal[3];        /* plane: normalised by the constructor (Rayito_Stage3/rayito.h:735) */
+    float side1[3], side2[3];   /* rectangle light */
+    float radius;
+    uint32_t bullseye;      /* plane: colour modifier 0.2 on alternate rings (rayito.h:773) */
+} RtS23Shape;
+
+typedef struct RtS23Material
+{
+    uint32_t kind;          /* RT_S23_MAT_* (Stage 2 surfaces: LAMBERT with the shape's colour) */
+    float color[3];
+    float exponent;         /* Phong */
+    float emittance[3];     /* Emitter: colour * power (rayito.h:490); zero otherwise */
+} RtS23Material;
+
+typedef struct RtS23Scene
+{
+    uint32_t num_shapes;    const RtS23Shape* shapes;        /* ShapeSet list order */
+    uint32_t num_materials; const RtS23Material* materials;
+    uint32_t num_lights;    const uint32_t* lights;          /* shape indices, findLights() order */
+} RtS23Scene;
+
+typedef struct RtS23Params
+{
+    uint32_t stage;                             /* 2 or 3 */
+    uint32_t width, height;
+    uint32_t pixel_samples_u, pixel_samples_v;  /* Stage 3: strata (reference 4 x 4); Stage 2: u = random samples per pixel (64), v ignored */
+    uint32_t light_samples_u, light_samples_v;  /* Stage 3: strata per light (reference 4 x 4); Stage 2: ignored (one sample) */
+    uint32_t seed_z, seed_w;                    /* Rng() defaults: 362436069, 521288629 (main.cpp:35) */
+} RtS23Params;
+
+/* Renders the whole program.  `camera` holds makeCameraRay's basis (main.cpp:55-79:
+ * forward, right, up normalised; tan of the FULL field of view).  rgb (may be NULL):
+ * width*height*3 floats, pixelColor after the box-filter division and before clamp();
+ * rgb8 (may be NULL): the P6 payload the program streams into out.ppm.  stats (may be
+ * NULL): samples, closest_rays (= every ShapeSet::intersect call), render_ms = stream
+ * pre-pass (upload_ms) + shading (trace_ms), trace_launches = pre-pass rounds. */
+int rt_stage23_render(int device, const RtS23Scene* scene, const RtCamera* camera, const RtS23Params* params,
+                      float* rgb, uint8_t* rgb8, RtRenderStats* stats);
+
 /* ---- host-side pieces of the path (no device needed) ------------------------- */
 
 /* Tile partition used to shard one image over `world` ranks: owners[ty*tiles_x+tx] is

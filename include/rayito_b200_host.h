@@ -61,6 +61,15 @@ int rth_raytrace(int recipe, const char* obj_path, unsigned grid_u, unsigned gri
  * (width*height*3 bytes); what `make && ./rayito` writes after the "P6" header. */
 int rth_stage1_render(int device, unsigned width, unsigned height, unsigned char* rgb8);
 
+/* Stage 2 and Stage 3 programs (Rayito_Stage2/main.cpp:93-228, Rayito_Stage3/main.cpp:162-279):
+ * build the program's scene and camera (fov 45 at (0,5,15) looking at the origin) with
+ * the reference's own constructor arithmetic and render on the GPU.  stage = 2: samples_u
+ * random samples per pixel (reference 64), samples_v ignored; stage = 3: samples_u x
+ * samples_v stratified samples per pixel (reference 4 x 4; config C2 sweeps 1..16 squared),
+ * 4 x 4 samples per light.  rgb / rgb8 / stats as for rt_stage23_render. */
+int rth_stage23_render(int device, int stage, unsigned width, unsigned height, unsigned samples_u, unsigned samples_v,
+                       float* rgb, unsigned char* rgb8, RtRenderStats* stats);
+
 #ifdef __cplusplus
 }
 #endif

@@ -218,3 +218,53 @@ def camera_rays(camera_spec14, args5, ray_dtype):
     out = np.zeros(len(args), ray_dtype)
     lib().ref_camera_rays(spec.ctypes.data, args.ctypes.data, len(args), out.ctypes.data)
     return out
+
+
+# ---- Stage 2 / Stage 3 (serial-Rng programs; oracle/ref_s2_driver.cpp, ref_s3_driver.cpp) ----
+_stage_libs = {}
+
+
+def stage_lib(stage):
+    """libref_s2.so / libref_s3.so: the unmodified Stage 2 / Stage 3 code with a variable sample count"""
+    if stage not in _stage_libs:
+        path = os.path.join(HERE, "_ref", "libref_s%d.so" % stage)
+        if not os.path.exists(path):
+            raise RuntimeError("%s is missing: run `make -C oracle ref` where /root/reference exists" % path)
+        L = C.CDLL(path, mode=C.RTLD_LOCAL)
+        vp = C.c_void_p
+        if stage == 2:
+            L.ref2_render.argtypes = [C.c_uint, C.c_uint, C.c_uint, vp, vp, vp, vp]
+            L.ref2_constants.argtypes = [vp]
+            L.ref2_build_info.restype = C.c_char_p
+        else:
+            L.ref3_render.argtypes = [C.c_uint, C.c_uint, C.c_uint, C.c_uint, vp, vp, vp, vp]
+            L.ref3_constants.argtypes = [vp]
+            L.ref3_build_info.restype = C.c_char_p
+        _stage_libs[stage] = L
+    return _stage_libs[stage]
+
+
+def stage_available(stage):
+    return os.path.exists(os.path.join(HERE, "_ref", "libref_s%d.so" % stage))
+
+
+def stage_binary(stage):
+    """The unmodified CLI (writes out.ppm into its cwd)"""
+    return os.path.join(HERE, "_ref", "stage%d" % stage)
+
+
+def stage_render(stage, width, height, samples_u, samples_v=1, want_flags=False):
+    """Returns (float rgb before clamp, uint8 rgb as written to out.ppm, hit flags or None, rays).
+    Stage 2 takes samples_u purely random samples per pixel; Stage 3 samples_u x samples_v strata."""
+    L = stage_lib(stage)
+    rgb = np.zeros((height, width, 3), np.float32)
+    rgb8 = np.zeros((height, width, 3), np.uint8)
+    n = width * height * samples_u * (samples_v if stage == 3 else 1)
+    flags = np.zeros(n, np.uint8) if want_flags else None
+    rays = C.c_uint64(0)
+    fp = flags.ctypes.data if want_flags else None
+    if stage == 2:
+        L.ref2_render(width, height, samples_u, rgb.ctypes.data, rgb8.ctypes.data, fp, C.addressof(rays))
+    else:
+        L.ref3_render(width, height, samples_u, samples_v, rgb.ctypes.data, rgb8.ctypes.data, fp, C.addressof(rays))
+    return rgb, rgb8, flags, rays.value

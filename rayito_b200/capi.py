@@ -105,12 +105,12 @@ CORE_SYMBOLS = [
     "rt_trace_closest_device", "rt_trace_any_device",
     "rt_render", "rt_render_device", "rt_generate_camera_rays", "rt_tonemap_bgra8",
     "rt_tile_owners", "rt_sample_permutations", "rt_cmj_sample1d", "rt_cmj_sample2d", "rt_stage1_render",
-    "rt_libm_eval",
+    "rt_libm_eval", "rt_stage23_render",
 ]
 HOST_SYMBOLS = [
     "rth_last_error_string", "rth_scene_create", "rth_scene_destroy", "rth_scene_desc",
     "rth_scene_prepare_seconds", "rth_scene_depth", "rth_camera", "rth_scene_default_camera", "rth_raytrace",
-    "rth_stage1_render",
+    "rth_stage1_render", "rth_stage23_render",
 ]
 
 _core = None
@@ -171,6 +171,7 @@ def host():
                                      C.c_uint, C.c_uint, C.c_uint, C.c_int, C.c_uint, C.c_uint, C.c_int,
                                      vp, C.POINTER(RtRenderStats)]
         lib.rth_stage1_render.argtypes = [C.c_int, C.c_uint, C.c_uint, vp]
+        lib.rth_stage23_render.argtypes = [C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_uint, vp, vp, vp]
         _host = lib
     return _host
 
@@ -303,6 +304,18 @@ def stage1_render(width=512, height=512, device=0):
     if host().rth_stage1_render(device, width, height, out.ctypes.data) != 0:
         raise RtError("rth_stage1_render: " + host().rth_last_error_string().decode())
     return out
+
+
+def stage23_render(stage, width=512, height=512, samples_u=4, samples_v=4, device=0):
+    """The Stage 2 / Stage 3 program on the GPU.  Returns (float rgb before clamp,
+    uint8 P6 payload, RtRenderStats).  Stage 2: samples_u random samples per pixel."""
+    rgb = np.zeros((height, width, 3), np.float32)
+    rgb8 = np.zeros((height, width, 3), np.uint8)
+    stats = RtRenderStats()
+    if host().rth_stage23_render(device, stage, width, height, samples_u, samples_v, rgb.ctypes.data,
+                                 rgb8.ctypes.data, C.addressof(stats)) != 0:
+        raise RtError("rth_stage23_render: " + host().rth_last_error_string().decode())
+    return rgb, rgb8, stats
 
 
 def libm_eval(kind, x, y=None):

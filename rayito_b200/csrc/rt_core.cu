@@ -10,6 +10,7 @@
 #include "rt_trace.cuh"
 #include "rt_wave.cuh"
 #include "rt_render.cuh"
+#include "rt_stage23.cuh"
 
 thread_local std::string g_rt_error;
 
@@ -319,6 +320,12 @@ int rt_stage1_render(int device, const RtStage1Plane* planes, uint32_t num_plane
                      uint32_t width, uint32_t height, uint8_t* rgb8)
 {
     return rt_stage1_impl(device, planes, num_planes, camera, width, height, rgb8);
+}
+
+int rt_stage23_render(int device, const RtS23Scene* scene, const RtCamera* camera, const RtS23Params* params,
+                      float* rgb, uint8_t* rgb8, RtRenderStats* stats)
+{
+    return rt_detail::rt_stage23_impl(device, scene, camera, params, rgb, rgb8, stats);
 }
 
 int rt_tile_owners(uint32_t width, uint32_t height, uint32_t tile_size, uint32_t world,

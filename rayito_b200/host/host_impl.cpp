@@ -452,3 +452,141 @@ int rth_stage1_render(int device, unsigned width, unsigned height, unsigned char
 }
 
 } // extern "C"
+
+namespace
+{
+
+// Stage 1-3 vectors normalise by dividing unconditionally (Rayito_Stage3/rayito.h:194)
+Rayito::Vector dividedByLength(const Rayito::Vector& v)
+{
+    float len = v.length();
+    return Rayito::Vector(v.m_x / len, v.m_y / len, v.m_z / len);
+}
+
+RtS23Shape s23Shape(unsigned type, unsigned material, const Rayito::Point& p)
+{
+    RtS23Shape s;
+    std::memset(&s, 0, sizeof(s));
+    s.type = type;
+    s.material = material;
+    s.position[0] = p.m_x; s.position[1] = p.m_y; s.position[2] = p.m_z;
+    return s;
+}
+
+RtS23Shape s23Plane(unsigned material, const Rayito::Point& p, const Rayito::Vector& normal, bool bullseye)
+{
+    RtS23Shape s = s23Shape(RT_S23_PLANE, material, p);
+    Rayito::Vector n = dividedByLength(normal);          // Plane ctor: normal.normalized()
+    s.normal[0] = n.m_x; s.normal[1] = n.m_y; s.normal[2] = n.m_z;
+    s.bullseye = bullseye ? 1 : 0;
+    return s;
+}
+
+RtS23Shape s23Sphere(unsigned material, const Rayito::Point& p, float radius)
+{
+    RtS23Shape s = s23Shape(RT_S23_SPHERE, material, p);
+    s.radius = radius;
+    return s;
+}
+
+RtS23Shape s23Rect(unsigned material, const Rayito::Point& p, const Rayito::Vector& a, const Rayito::Vector& b)
+{
+    RtS23Shape s = s23Shape(RT_S23_RECT, material, p);
+    s.side1[0] = a.m_x; s.side1[1] = a.m_y; s.side1[2] = a.m_z;
+    s.side2[0] = b.m_x; s.side2[1] = b.m_y; s.side2[2] = b.m_z;
+    return s;
+}
+
+RtS23Material s23Material(unsigned kind, const Rayito::Color& c, float exponent = 0.0f)
+{
+    RtS23Material m;
+    std::memset(&m, 0, sizeof(m));
+    m.kind = kind;
+    m.color[0] = c.m_r; m.color[1] = c.m_g; m.color[2] = c.m_b;
+    m.exponent = exponent;
+    return m;
+}
+
+// Emitter(colour, power): emittance() = m_color * m_power (rayito.h:490)
+RtS23Material s23Emitter(const Rayito::Color& c, float power)
+{
+    RtS23Material m = s23Material(RT_S23_MAT_EMITTER, Rayito::Color(0.0f, 0.0f, 0.0f));
+    Rayito::Color e = c * power;
+    m.emittance[0] = e.m_r; m.emittance[1] = e.m_g; m.emittance[2] = e.m_b;
+    return m;
+}
+
+} // namespace
+
+extern "C" int rth_stage23_render(int device, int stage, unsigned width, unsigned height, unsigned samples_u,
+                                  unsigned samples_v, float* rgb, unsigned char* rgb8, RtRenderStats* stats)
+{
+    using namespace Rayito;
+    std::vector<RtS23Shape> shapes;
+    std::vector<RtS23Material> materials;
+    std::vector<uint32_t> lights;
+    if (stage == 2)
+    {
+        // Rayito_Stage2/main.cpp:96-122: white bullseye plane, two rectangle lights
+        materials.push_back(s23Material(RT_S23_MAT_LAMBERT, Color(1.0f, 1.0f, 1.0f)));
+        materials.push_back(s23Emitter(Color(1.0f, 0.5f, 1.0f), 3.0f));
+        materials.push_back(s23Emitter(Color(1.0f, 1.0f, 0.5f), 0.75f));
+        shapes.push_back(s23Plane(0, Point(0.0f, -2.0f, 0.0f), Vector(0.0f, 1.0f, 0.0f), true));
+        shapes.push_back(s23Rect(1, Point(-2.5f, 2.0f, -2.5f), Vector(5.0f, 0.0f, 0.0f), Vector(0.0f, 0.0f, 5.0f)));
+        shapes.push_back(s23Rect(2, Point(-2.0f, -1.0f, -2.0f), Vector(4.0f, 0.0f, 0.0f), Vector(0.0f, 0.0f, 4.0f)));
+        lights.push_back(1);
+        lights.push_back(2);
+    }
+    else if (stage == 3)
+    {
+        // Rayito_Stage3/main.cpp:165-201
+        materials.push_back(s23Material(RT_S23_MAT_LAMBERT, Color(0.9f, 0.9f, 1.0f)));
+        materials.push_back(s23Material(RT_S23_MAT_LAMBERT, Color(0.9f, 0.7f, 0.8f)));
+        materials.push_back(s23Material(RT_S23_MAT_PHONG, Color(0.7f, 0.9f, 0.7f), 16.0f));
+        materials.push_back(s23Emitter(Color(1.0f, 1.0f, 1.0f), 1.0f));
+        materials.push_back(s23Emitter(Color(1.0f, 1.0f, 0.1f), 4.0f));
+        shapes.push_back(s23Plane(0, Point(0.0f, -2.0f, 0.0f), Vector(0.0f, 1.0f, 0.0f), true));
+        shapes.push_back(s23Sphere(1, Point(3.0f, -1.0f, 0.0f), 1.0f));
+        shapes.push_back(s23Sphere(2, Point(-3.0f, 0.0f, -2.0f), 2.0f));
+        shapes.push_back(s23Rect(3, Point(-2.5f, 4.0f, -2.5f), Vector(5.0f, 0.0f, 0.0f), Vector(0.0f, 0.0f, 5.0f)));
+        shapes.push_back(s23Sphere(4, Point(0.0f, 0.0f, 2.0f), 1.0f));      // ShapeLight around a sphere
+        lights.push_back(3);
+        lights.push_back(4);
+    }
+    else
+    {
+        t_hostError = "stage must be 2 or 3";
+        return -1;
+    }
+    // makeCameraRay's basis (main.cpp:62-67), which does not depend on the pixel
+    Point origin(0.0f, 5.0f, 15.0f), target(0.0f, 0.0f, 0.0f), upDir(0.0f, 1.0f, 0.0f);
+    Vector forward = dividedByLength(target - origin);
+    Vector right = dividedByLength(cross(forward, upDir));
+    Vector up = dividedByLength(cross(right, forward));
+    RtCamera cam;
+    std::memset(&cam, 0, sizeof(cam));
+    cam.origin[0] = origin.m_x; cam.origin[1] = origin.m_y; cam.origin[2] = origin.m_z;
+    cam.forward[0] = forward.m_x; cam.forward[1] = forward.m_y; cam.forward[2] = forward.m_z;
+    cam.right[0] = right.m_x; cam.right[1] = right.m_y; cam.right[2] = right.m_z;
+    cam.up[0] = up.m_x; cam.up[1] = up.m_y; cam.up[2] = up.m_z;
+    cam.tan_fov = std::tan(45.0f * M_PI / 180.0f);
+
+    RtS23Scene scene;
+    scene.num_shapes = (uint32_t)shapes.size();       scene.shapes = &shapes[0];
+    scene.num_materials = (uint32_t)materials.size(); scene.materials = &materials[0];
+    scene.num_lights = (uint32_t)lights.size();       scene.lights = &lights[0];
+    RtS23Params prm;
+    std::memset(&prm, 0, sizeof(prm));
+    prm.stage = (uint32_t)stage;
+    prm.width = width;
+    prm.height = height;
+    prm.pixel_samples_u = samples_u;
+    prm.pixel_samples_v = stage == 2 ? 1 : samples_v;
+    prm.light_samples_u = prm.light_samples_v = 4;    // kNumLightSamplesU/V (Rayito_Stage3/main.cpp:92-93)
+    prm.seed_z = 362436069u;
+    prm.seed_w = 521288629u;
+    int rc = rt_stage23_render(device, &scene, &cam, &prm, rgb, rgb8, stats);
+    if (rc != RT_OK)
+        t_hostError = rt_last_error_string();
+    return rc;
+}

@@ -29,7 +29,41 @@ def hits_fixture(name, ref_scene, batches):
     print(name, len(rays), "rays,", int((closest["shape"] >= 0).sum()), "hits,", int(shadow.sum()), "occluded")
 
 
+def stage23_fixture():
+    """Stage 2: the reference's golden image Rayito_Stage2/out_ref.ppm (reproducible here).
+    Stage 3: Rayito_Stage3/out_ref.ppm is NOT reproducible by the reference's own code
+    (SURVEY.md section 4), so the vector is the rebuilt reference binary's out.ppm.  Kept
+    as digests plus a 32x32 decimation (every 16th pixel) for readable failures."""
+    import hashlib
+    import json
+    import subprocess
+    import tempfile
+    out = {}
+    for stage in (2, 3):
+        with tempfile.TemporaryDirectory(dir=os.path.join(ROOT, "oracle", "_build")) as d:
+            subprocess.run([refapi.stage_binary(stage)], cwd=d, check=True)
+            data = open(os.path.join(d, "out.ppm"), "rb").read()
+        cut = data.index(b"255\n") + 4
+        px = np.frombuffer(data[cut:], np.uint8).reshape(512, 512, 3)
+        golden = open("/root/reference/Rayito_Stage%d/out_ref.ppm" % stage, "rb").read()
+        gpx = np.frombuffer(golden[golden.index(b"255\n") + 4:], np.uint8).reshape(512, 512, 3)
+        out["stage%d" % stage] = {
+            "source": "oracle/_ref/stage%d (Rayito_Stage%d/main.cpp, g++ -O3) -> out.ppm" % (stage, stage),
+            "md5": hashlib.md5(data).hexdigest(), "payload_md5": hashlib.md5(data[cut:]).hexdigest(),
+            "bytes": len(data), "header": data[:cut].decode(), "width": 512, "height": 512,
+            "decimated_16": px[::16, ::16].tolist(),
+            "out_ref_ppm_md5": hashlib.md5(golden).hexdigest(),
+            "pixels_differing_from_out_ref_ppm": int((px != gpx).any(axis=-1).sum()),
+        }
+        print("stage", stage, out["stage%d" % stage]["md5"], "differs from out_ref.ppm in",
+              out["stage%d" % stage]["pixels_differing_from_out_ref_ppm"], "pixels")
+    json.dump(out, open(os.path.join(HERE, "stage23_out.json"), "w"))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "stage23":
+        stage23_fixture()
+        return
     obj = build.model_path("bumpy.obj")
     s1 = refapi.RefScene(1, obj)
     hits_fixture("scene1_hits.npz", s1, [
@@ -72,6 +106,7 @@ def main():
             "lit_colour": [int(v) for v in px[lit[0], 0]], "payload_md5": hashlib.md5(data[cut:]).hexdigest()}
     assert (px[lit[0]:] == px[lit[0], 0]).all() and not px[:lit[0]].any()
     json.dump(desc, open(os.path.join(HERE, "stage1_out_ref.json"), "w"), indent=1)
+    stage23_fixture()
     print("golden fixtures written to", HERE)
 
 
