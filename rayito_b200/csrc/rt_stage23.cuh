@@ -10,9 +10,9 @@
 // hit or miss on silhouette pixels).  The reference resolves this by being sequential.
 // Here:
 //   1. k_s23_guess    -- every sample's hit predicate with centred jitter (parallel);
-//   2. k_s23_prepass  -- per image segment, a windowed fix-point: evaluate a window of
-//      samples with offsets from the assumed flags, accept everything up to the first
-//      disagreement, restart behind it.  Samples whose hit does not depend on the jitter
+//   2. k_s23_prepass  -- per image segment (one warp each), a windowed fix-point: evaluate
+//      a window of 32 samples with offsets from the assumed flags, accept everything up to
+//      the first disagreement, restart behind it.  Samples whose hit does not depend on the jitter
 //      (all but silhouettes) are accepted a whole window at a time;
 //   3. k_s23_segfix   -- chains the segments' hit counts; segments whose incoming count
 //      changed are redone (their silhouette samples may flip), until nothing changes;
@@ -26,6 +26,8 @@
 #ifndef RAYITO_B200_RT_STAGE23_CUH
 #define RAYITO_B200_RT_STAGE23_CUH
 
+#include <mutex>
+
 #include "rt_sampling.cuh"
 #include "rt_shade.cuh"
 
@@ -33,15 +35,25 @@ namespace rt_detail
 {
 
 #define RT_S23_TMIN 0.00001f          /* kRayTMin of Stages 1-3 (Rayito_Stage3/rayito.h:303) */
-#define RT_S23_PRE_THREADS 256
-#define RT_S23_PRE_PER_THREAD 4
-#define RT_S23_WINDOW (RT_S23_PRE_THREADS * RT_S23_PRE_PER_THREAD)
 #define RT_S23_MAX_TERMS 3            /* Stage 2: emitted + one term per light (<= 2 lights) */
+
+// Pure functions of a shape's constants that the reference evaluates inside every intersect
+// call (rayito.h:618,634-637,747,826).  Same inputs, same IEEE operations => same bits, so they
+// are computed once per render (on the host, in float, without contraction).
+struct S23Derived
+{
+    float n[3];             // rectangle: cross(side1, side2).normalized()
+    float pos_dot_n;        // dot(m_position, normal) (plane and rectangle)
+    float s1n[3], s2n[3];   // rectangle: normalised sides
+    float len1, len2;       // ... and their lengths
+    float r2;               // sphere: m_radius * m_radius
+};
 
 struct S23Ctx
 {
     RtS23Shape shapes[RT_S23_MAX_SHAPES];
     RtS23Material materials[RT_S23_MAX_SHAPES];
+    S23Derived derived[RT_S23_MAX_SHAPES];      // per-shape values the reference recomputes on every call
     uint32_t lights[RT_S23_MAX_LIGHTS];         // shape indices, list order
     uint32_t num_shapes, num_lights;
     RtCamera cam;
@@ -63,6 +75,8 @@ struct S23Ctx
     unsigned long long* seg_hout;                // ... after it
     uint32_t* seg_dirty;
     uint32_t* any_dirty;
+    uint32_t* seg_sensitive;                     // scheduling hint from k_s23_guess
+    const uint32_t* pow_table;                   // MWC multiplier powers for short jumps (see k_s23_prepass)
     float4* sample_terms;                        // [terms][num_samples]
     float* rgb;                                  // width*height*3, before clamp
     uint8_t* rgb8;
@@ -114,9 +128,10 @@ __device__ __forceinline__ void s23_camera_ray(const S23Ctx& c, float xu, float 
 // Screen position of sample k given its two jitter draws (first draw -> yu, second -> xu)
 __device__ __forceinline__ void s23_screen(const S23Ctx& c, uint64_t k, float r_first, float r_second, float& xu, float& yu)
 {
-    uint32_t s = (uint32_t)(k % c.spp);
-    uint64_t p = k / c.spp;
-    uint32_t x = (uint32_t)(p % c.width), y = (uint32_t)(p / c.width);
+    // num_samples < 2^32: 32-bit divisions (64-bit ones cost ten times as much on the serial chain)
+    uint32_t k32 = (uint32_t)k;
+    uint32_t p = k32 / c.spp, s = k32 - p * c.spp;
+    uint32_t y = p / c.width, x = p - y * c.width;
     if (c.stage == 2)
     {
         // Rayito_Stage2/main.cpp:156-157
@@ -133,8 +148,9 @@ __device__ __forceinline__ void s23_screen(const S23Ctx& c, uint64_t k, float r_
 }
 
 // ShapeSet::intersect (rayito.h:543-558): every list entry in order, each accepting
-// only t < current m_t.  SHADING = also fill normal / colour modifier.
-template <bool SHADING>
+// only t < current m_t.  SHADING = also fill normal / colour modifier.  ANY = only the
+// boolean result is wanted: the first accepted hit decides it.
+template <bool SHADING, bool ANY>
 __device__ __forceinline__ bool s23_intersect(const S23Ctx& c, V3 o, V3 d, float tmax, S23Hit& h)
 {
     h.t = tmax;
@@ -146,6 +162,7 @@ __device__ __forceinline__ bool s23_intersect(const S23Ctx& c, V3 o, V3 d, float
     for (uint32_t i = 0; i < c.num_shapes; ++i)
     {
         const RtS23Shape& sh = c.shapes[i];
+        const S23Derived& dv = c.derived[i];
         V3 pos = mk(sh.position[0], sh.position[1], sh.position[2]);
         if (sh.type == RT_S23_PLANE)
         {
@@ -154,9 +171,10 @@ __device__ __forceinline__ bool s23_intersect(const S23Ctx& c, V3 o, V3 d, float
             float n_dot_d = dot3(n, d);
             if (n_dot_d >= 0.0f)
                 continue;
-            float t = (dot3(pos, n) - dot3(o, n)) / dot3(d, n);
+            float t = (dv.pos_dot_n - dot3(o, n)) / dot3(d, n);
             if (t >= h.t || t < RT_S23_TMIN)
                 continue;
+            if (ANY) return true;
             h.t = t;
             h.shape = (int)i;
             h.is_light_self = false;
@@ -179,7 +197,7 @@ __device__ __forceinline__ bool s23_intersect(const S23Ctx& c, V3 o, V3 d, float
             V3 lo = o - pos;
             float a = d.x * d.x + d.y * d.y + d.z * d.z;
             float b = 2.0f * dot3(d, lo);
-            float cc = (lo.x * lo.x + lo.y * lo.y + lo.z * lo.z) - sh.radius * sh.radius;
+            float cc = (lo.x * lo.x + lo.y * lo.y + lo.z * lo.z) - dv.r2;
             float disc = b * b - 4.0f * a * cc;
             if (disc < 0.0f)
                 continue;
@@ -196,6 +214,7 @@ __device__ __forceinline__ bool s23_intersect(const S23Ctx& c, V3 o, V3 d, float
                 h.t = t1;
             else
                 continue;
+            if (ANY) return true;
             h.shape = (int)i;
             h.is_light_self = false;          // a ShapeLight leaves m_pShape = the inner sphere
             any = true;
@@ -208,20 +227,19 @@ __device__ __forceinline__ bool s23_intersect(const S23Ctx& c, V3 o, V3 d, float
         else
         {
             // RectangleLight::intersect (rayito.h:616-669): two-sided
-            V3 s1 = mk(sh.side1[0], sh.side1[1], sh.side1[2]), s2 = mk(sh.side2[0], sh.side2[1], sh.side2[2]);
-            V3 n = s23_normalized(cross3(s1, s2));
+            V3 n = mk(dv.n[0], dv.n[1], dv.n[2]);
             float n_dot_d = dot3(n, d);
             if (n_dot_d == 0.0f)
                 continue;
-            float t = (dot3(pos, n) - dot3(o, n)) / dot3(d, n);
+            float t = (dv.pos_dot_n - dot3(o, n)) / dot3(d, n);
             if (t >= h.t || t < RT_S23_TMIN)
                 continue;
-            float len1, len2;
-            V3 s1n = s23_normalized(s1, &len1), s2n = s23_normalized(s2, &len2);
+            V3 s1n = mk(dv.s1n[0], dv.s1n[1], dv.s1n[2]), s2n = mk(dv.s2n[0], dv.s2n[1], dv.s2n[2]);
             V3 rel = (o + t * d) - pos;
             float lx = dot3(rel, s1n), ly = dot3(rel, s2n);
-            if (lx < 0.0f || lx > len1 || ly < 0.0f || ly > len2)
+            if (lx < 0.0f || lx > dv.len1 || ly < 0.0f || ly > dv.len2)
                 continue;
+            if (ANY) return true;
             h.t = t;
             h.shape = (int)i;
             h.is_light_self = true;
@@ -236,165 +254,237 @@ __device__ __forceinline__ bool s23_intersect(const S23Ctx& c, V3 o, V3 d, float
     return any;
 }
 
-// Did the camera ray of sample k hit anything, were its jitter drawn at stream position `offset`
-__device__ __forceinline__ bool s23_primary_hits(const S23Ctx& c, uint64_t k, uint64_t offset)
+// ---- 1. geometric guess ------------------------------------------------------------
+// Hit predicate with centred jitter, and whether the four jitter corners agree with it.
+// A segment with a disagreeing sample is "sensitive": its hit count may depend on where
+// in the stream it starts.  This is only a scheduling hint (k_s23_chain); every sample
+// is still confirmed at its true stream position by k_s23_prepass.
+__device__ __forceinline__ bool s23_hits_with_jitter(const S23Ctx& c, uint64_t k, float r1, float r2)
 {
-    MwcState s = s23_rng_at(c, offset);
-    float r1 = s23_next_float(s), r2 = s23_next_float(s);
     float xu, yu;
     s23_screen(c, k, r1, r2, xu, yu);
     V3 o, d;
     s23_camera_ray(c, xu, yu, o, d);
     S23Hit h;
-    return s23_intersect<false>(c, o, d, RT_RAY_TMAX, h);
+    return s23_intersect<false, true>(c, o, d, RT_RAY_TMAX, h);
 }
 
-// ---- 1. geometric guess ------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_s23_guess(const __grid_constant__ S23Ctx c)
 {
     uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool hit = false;
+    bool hit = false, sensitive = false;
     if (k < c.num_samples)
     {
-        float xu, yu;
-        s23_screen(c, k, 0.5f, 0.5f, xu, yu);
-        V3 o, d;
-        s23_camera_ray(c, xu, yu, o, d);
-        S23Hit h;
-        hit = s23_intersect<false>(c, o, d, RT_RAY_TMAX, h);
+        hit = s23_hits_with_jitter(c, k, 0.5f, 0.5f);
+        const float lo = 0.0f, hi = 0.99999994f;
+        sensitive = s23_hits_with_jitter(c, k, lo, lo) != hit || s23_hits_with_jitter(c, k, lo, hi) != hit ||
+                    s23_hits_with_jitter(c, k, hi, lo) != hit || s23_hits_with_jitter(c, k, hi, hi) != hit;
         c.flags[k] = hit ? 1 : 0;
     }
-    // per-segment totals of the guess seed the segment chain (seg_hin = 0 here)
+    // per-segment totals of the guess seed the segment chain (seg_hin = 0 here); a warp's 32
+    // samples lie in one segment (segment lengths are multiples of 32)
     uint32_t votes = __ballot_sync(0xffffffffu, hit);
-    if ((threadIdx.x & 31) == 0 && votes)
+    uint32_t touchy = __ballot_sync(0xffffffffu, sensitive);
+    if ((threadIdx.x & 31) == 0 && k < c.num_samples)
     {
-        uint64_t k0 = k;                         // first sample of this warp; a warp may straddle two segments
-        uint64_t seg0 = k0 / c.seg_len;
-        uint64_t boundary = (seg0 + 1) * c.seg_len;
-        uint32_t in_first = boundary - k0 >= 32 ? 32u : (uint32_t)(boundary - k0);
-        uint32_t lo = in_first == 32 ? votes : (votes & ((1u << in_first) - 1u));
-        uint32_t hi = votes & ~lo;
-        if (lo) atomicAdd(c.seg_hout + seg0, (unsigned long long)__popc(lo));
-        if (hi) atomicAdd(c.seg_hout + seg0 + 1, (unsigned long long)__popc(hi));
+        uint64_t seg = k / c.seg_len;
+        if (votes) atomicAdd(c.seg_hout + seg, (unsigned long long)__popc(votes));
+        if (touchy) atomicOr(c.seg_sensitive + seg, 1u);
     }
 }
 
 // ---- 2. windowed fix-point over one segment -------------------------------------------
-struct S23Block
+// One WARP per segment, windows of 32 samples (one per lane): no shared-memory traffic and
+// no block barriers on the serial chain.  Assumed flags travel in registers from one window
+// to the next.  Rng states come from one state per segment moved by table look-ups: a draw
+// distance below 2^20 costs three modular multiplications per generator
+// (a^lo * a^(64 mid) * a^(4096 hi) * state) instead of a 34-step modular exponentiation.
+#define RT_S23_PRE_WARPS 4                                   /* warps (= segments) per block */
+#define RT_S23_TABLE 384                                     /* 64 + 64 + 256 powers per generator */
+#define RT_S23_TABLE_SPAN (1u << 20)
+
+__device__ __forceinline__ uint64_t s23_mulmod(uint64_t a, uint64_t b, uint64_t m) { return (a * b) % m; }
+
+struct S23Base
 {
-    uint32_t warp_a[RT_S23_PRE_THREADS / 32];
-    unsigned long long warp_b[RT_S23_PRE_THREADS / 32];
-    uint32_t total;
-    unsigned long long first_bad;
-    uint32_t confirmed;
+    uint64_t off;           // draws consumed before this state (>= 2: canonical)
+    uint64_t zr, wr;        // state residues
+    bool z_nonzero, w_nonzero;
 };
 
-__global__ void __launch_bounds__(RT_S23_PRE_THREADS)
-k_s23_prepass(const __grid_constant__ S23Ctx c)
+__device__ __forceinline__ S23Base s23_base_at(const S23Ctx& c, uint64_t off)
 {
-    const uint32_t seg = blockIdx.x;
-    if (!c.seg_dirty[seg])
-        return;
-    __shared__ S23Block sm;
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint64_t begin = (uint64_t)seg * c.seg_len;
-    const uint64_t end = begin + c.seg_len < c.num_samples ? begin + c.seg_len : c.num_samples;
-    uint64_t H = c.seg_hin[seg];
+    S23Base b;
+    b.off = off < 2 ? 2 : off;
+    MwcState s = s23_rng_at(c, b.off);
+    b.zr = s.z % RT_MWC_MZ; b.wr = s.w % RT_MWC_MW;
+    b.z_nonzero = s.z != 0; b.w_nonzero = s.w != 0;
+    return b;
+}
+
+// State `delta` draws after the base (delta < 2^20)
+__device__ __forceinline__ MwcState s23_rng_ahead(const S23Base& b, uint32_t delta, const uint32_t* tz, const uint32_t* tw)
+{
+    uint32_t lo = delta & 63u, mid = 64u + ((delta >> 6) & 63u), hi = 128u + (delta >> 12);
+    uint64_t z = s23_mulmod(s23_mulmod(s23_mulmod(tz[lo], tz[mid], RT_MWC_MZ), tz[hi], RT_MWC_MZ), b.zr, RT_MWC_MZ);
+    uint64_t w = s23_mulmod(s23_mulmod(s23_mulmod(tw[lo], tw[mid], RT_MWC_MW), tw[hi], RT_MWC_MW), b.wr, RT_MWC_MW);
+    MwcState r;
+    r.z = (uint32_t)((z == 0 && b.z_nonzero) ? RT_MWC_MZ : z);     // same representative rule as mwc_jump
+    r.w = (uint32_t)((w == 0 && b.w_nonzero) ? RT_MWC_MW : w);
+    return r;
+}
+
+// Resolves samples [begin, end) given H hits before `begin`; returns the hits before `end`.
+// All 32 lanes of the calling warp take part.
+__device__ __forceinline__ uint64_t s23_resolve_segment(const S23Ctx& c, const uint32_t* tz, const uint32_t* tw,
+                                                        uint64_t begin, uint64_t end, uint64_t H)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t D = c.draws_per_hit;
+    const uint32_t reach = 32u * (2u + D);                   // draws one window can span
     uint64_t P = begin;
-    const unsigned long long NONE = ~0ull;
+    S23Base base = s23_base_at(c, 2ull * P + (uint64_t)D * H);
+    uint32_t a = P + lane < end ? c.flags[P + lane] : 0u;
     while (P < end)
     {
-        const uint64_t wend = P + RT_S23_WINDOW < end ? P + RT_S23_WINDOW : end;
-        const uint64_t base = P + (uint64_t)tid * RT_S23_PRE_PER_THREAD;
-        uint32_t a[RT_S23_PRE_PER_THREAD], cnt = 0;
-        #pragma unroll
-        for (int u = 0; u < RT_S23_PRE_PER_THREAD; ++u)
+        const uint64_t win_off = 2ull * P + (uint64_t)D * H;
+        if (win_off - base.off + reach >= RT_S23_TABLE_SPAN && win_off >= base.off)
+            base = s23_base_at(c, win_off);
+        const uint64_t k = P + lane;
+        const bool live = k < end;
+        // stored flags the next window may need (it starts at most 32 samples further on)
+        const uint32_t ahead = P + 32 + lane < end ? c.flags[P + 32 + lane] : 0u;
+        const uint32_t votes_a = __ballot_sync(0xffffffffu, a != 0);
+        const uint32_t before = __popc(votes_a & ((1u << lane) - 1u));
+        const uint64_t off = 2ull * k + (uint64_t)D * (H + before);
+        bool e = false;
+        if (live)
         {
-            a[u] = base + u < wend ? c.flags[base + u] : 0;
-            cnt += a[u];
+            MwcState st;
+            if (off < base.off)               st = s23_rng_at(c, off);                  // the very first sample
+            else if (reach < RT_S23_TABLE_SPAN) st = s23_rng_ahead(base, (uint32_t)(off - base.off), tz, tw);
+            else                              st = s23_rng_at(c, off);                  // absurdly many light samples
+            float r1 = s23_next_float(st), r2 = s23_next_float(st);
+            e = s23_hits_with_jitter(c, k, r1, r2);
         }
-        // exclusive scan of the assumed counts over the block
-        uint32_t incl = cnt;
-        #pragma unroll
-        for (int off = 1; off < 32; off <<= 1)
+        const uint32_t votes_e = __ballot_sync(0xffffffffu, e);
+        const uint32_t live_mask = __ballot_sync(0xffffffffu, live);
+        const uint32_t diff = (votes_e ^ votes_a) & live_mask;
+        // lanes up to and including the first disagreement ran at their true offsets: final
+        const uint32_t m = diff ? (uint32_t)__ffs(diff) - 1u : 31u;
+        const uint32_t final_mask = (m == 31u ? 0xffffffffu : ((2u << m) - 1u)) & live_mask;
+        if (live && lane <= m)
         {
-            uint32_t v = __shfl_up_sync(0xffffffffu, incl, off);
-            if (lane >= (uint32_t)off) incl += v;
+            c.flags[k] = e ? 1 : 0;
+            c.hits_before[k] = (uint32_t)(H + before);
         }
-        if (lane == 31) sm.warp_a[warp] = incl;
-        __syncthreads();
-        uint32_t before = incl - cnt;
-        for (uint32_t w = 0; w < warp; ++w) before += sm.warp_a[w];
-
-        // evaluate with the offsets the assumption implies
-        uint32_t e[RT_S23_PRE_PER_THREAD];
-        unsigned long long bad = NONE;
-        uint64_t h = H + before;
-        #pragma unroll
-        for (int u = 0; u < RT_S23_PRE_PER_THREAD; ++u)
-        {
-            uint64_t k = base + u;
-            e[u] = 0;
-            if (k < wend)
-            {
-                e[u] = s23_primary_hits(c, k, 2ull * k + (uint64_t)c.draws_per_hit * h) ? 1u : 0u;
-                if (e[u] != a[u] && bad == NONE) bad = k;
-                h += a[u];
-            }
-        }
-        // first disagreement in the window
-        #pragma unroll
-        for (int off = 16; off > 0; off >>= 1)
-        {
-            unsigned long long v = __shfl_xor_sync(0xffffffffu, bad, off);
-            bad = v < bad ? v : bad;
-        }
-        if (lane == 0) sm.warp_b[warp] = bad;
-        __syncthreads();
-        unsigned long long m = NONE;
-        for (uint32_t w = 0; w < RT_S23_PRE_THREADS / 32; ++w) m = sm.warp_b[w] < m ? sm.warp_b[w] : m;
-
-        // samples <= m were evaluated at their true offsets: final.  The rest keep the
-        // evaluated flags as the next assumption.
-        uint32_t conf = 0;
-        h = H + before;
-        #pragma unroll
-        for (int u = 0; u < RT_S23_PRE_PER_THREAD; ++u)
-        {
-            uint64_t k = base + u;
-            if (k < wend)
-            {
-                c.flags[k] = (uint8_t)e[u];
-                if (k <= m)
-                {
-                    c.hits_before[k] = (uint32_t)h;
-                    conf += e[u];
-                }
-                h += a[u];
-            }
-        }
-        #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) conf += __shfl_xor_sync(0xffffffffu, conf, off);
-        __syncthreads();                     // warp_a reads above are done
-        if (lane == 0) sm.warp_a[warp] = conf;
-        __syncthreads();
-        uint32_t total_conf = 0;
-        for (uint32_t w = 0; w < RT_S23_PRE_THREADS / 32; ++w) total_conf += sm.warp_a[w];
-        H += total_conf;
-        P = m == NONE ? wend : (uint64_t)m + 1;
-        __syncthreads();
+        const uint32_t adv = __popc(final_mask);
+        H += __popc(votes_e & final_mask);
+        P += adv;
+        // next window's assumption: what the lanes behind m just evaluated, then stored flags
+        const uint32_t keep = 32u - adv;
+        const uint32_t carried = __shfl_down_sync(0xffffffffu, e ? 1u : 0u, adv & 31u);
+        const uint32_t fresh = __shfl_sync(0xffffffffu, ahead, (lane - keep) & 31u);
+        a = lane < keep ? carried : fresh;
     }
-    if (tid == 0)
+    return H;
+}
+
+__device__ __forceinline__ void s23_load_tables(const S23Ctx& c, uint32_t* tz, uint32_t* tw)
+{
+    for (uint32_t i = threadIdx.x; i < RT_S23_TABLE; i += blockDim.x)
+    {
+        tz[i] = c.pow_table[i];
+        tw[i] = c.pow_table[RT_S23_TABLE + i];
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(RT_S23_PRE_WARPS * 32)
+k_s23_prepass(const __grid_constant__ S23Ctx c)
+{
+    __shared__ uint32_t tz[RT_S23_TABLE], tw[RT_S23_TABLE];
+    s23_load_tables(c, tz, tw);
+    const uint32_t seg = blockIdx.x * RT_S23_PRE_WARPS + (threadIdx.x >> 5);
+    if (seg >= c.num_segs || !c.seg_dirty[seg])
+        return;
+    const uint64_t begin = (uint64_t)seg * c.seg_len;
+    const uint64_t end = begin + c.seg_len < c.num_samples ? begin + c.seg_len : c.num_samples;
+    uint64_t H = s23_resolve_segment(c, tz, tw, begin, end, c.seg_hin[seg]);
+    if ((threadIdx.x & 31) == 0)
         c.seg_hout[seg] = H;
 }
 
-// ---- 3. chain the segments -------------------------------------------------------------
-__global__ void k_s23_segfix(const __grid_constant__ S23Ctx c)
+// One warp walks the segments in order: insensitive ones contribute their guessed count,
+// sensitive ones are resolved in place with the exact incoming count.  Afterwards seg_hin /
+// seg_hout are exact provided the hint was right; k_s23_prepass + k_s23_segfix check that.
+__global__ void __launch_bounds__(32)
+k_s23_chain(const __grid_constant__ S23Ctx c)
 {
-    unsigned long long h = 0;
+    __shared__ uint32_t tz[RT_S23_TABLE], tw[RT_S23_TABLE];
+    s23_load_tables(c, tz, tw);
+    const uint32_t lane = threadIdx.x & 31;
+    // with silhouettes everywhere a serial walk would cost more than the parallel rounds it saves
+    uint32_t sensitive_segs = 0;
+    for (uint32_t s0 = 0; s0 < c.num_segs; s0 += 32)
+        sensitive_segs += __popc(__ballot_sync(0xffffffffu, s0 + lane < c.num_segs && c.seg_sensitive[s0 + lane] != 0));
+    if (sensitive_segs > 64 && sensitive_segs > c.num_segs / 8)
+        return;
+    unsigned long long H = 0;
+    for (uint32_t s0 = 0; s0 < c.num_segs; s0 += 32)
+    {
+        const uint32_t s = s0 + lane;
+        const bool in = s < c.num_segs;
+        unsigned long long count = in ? c.seg_hout[s] - c.seg_hin[s] : 0ull;
+        const uint32_t touchy = __ballot_sync(0xffffffffu, in && c.seg_sensitive[s] != 0);
+        for (uint32_t j = 0; j < 32 && s0 + j < c.num_segs; ++j)
+        {
+            const uint32_t sj = s0 + j;
+            unsigned long long cj = __shfl_sync(0xffffffffu, count, j);
+            if (lane == 0) c.seg_hin[sj] = H;
+            if (touchy & (1u << j))
+            {
+                const uint64_t begin = (uint64_t)sj * c.seg_len;
+                const uint64_t end = begin + c.seg_len < c.num_samples ? begin + c.seg_len : c.num_samples;
+                H = s23_resolve_segment(c, tz, tw, begin, end, H);
+            }
+            else
+                H += cj;
+            if (lane == 0) c.seg_hout[sj] = H;
+        }
+    }
+}
+
+// ---- 3. chain the segments -------------------------------------------------------------
+// One block: exclusive scan of the segments' hit counts -> hits before each segment; a
+// segment whose incoming count changed must be redone.
+#define RT_S23_FIX_THREADS 1024
+__global__ void __launch_bounds__(RT_S23_FIX_THREADS)
+k_s23_segfix(const __grid_constant__ S23Ctx c)
+{
+    __shared__ unsigned long long warp_sum[RT_S23_FIX_THREADS / 32];
+    __shared__ uint32_t dirty_any;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) dirty_any = 0;
+    const uint32_t per = (c.num_segs + RT_S23_FIX_THREADS - 1) / RT_S23_FIX_THREADS;
+    const uint32_t first = tid * per, last = first + per < c.num_segs ? first + per : c.num_segs;
+    unsigned long long mine = 0;
+    for (uint32_t s = first; s < last; ++s)
+        mine += c.seg_hout[s] - c.seg_hin[s];
+    unsigned long long incl = mine;
+    #pragma unroll
+    for (int off = 1; off < 32; off <<= 1)
+    {
+        unsigned long long v = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= (uint32_t)off) incl += v;
+    }
+    if (lane == 31) warp_sum[warp] = incl;
+    __syncthreads();
+    unsigned long long h = incl - mine;
+    for (uint32_t w = 0; w < warp; ++w) h += warp_sum[w];
     uint32_t dirty = 0;
-    for (uint32_t s = 0; s < c.num_segs; ++s)
+    for (uint32_t s = first; s < last; ++s)
     {
         unsigned long long count = c.seg_hout[s] - c.seg_hin[s];
         uint32_t d = c.seg_hin[s] != h ? 1u : 0u;
@@ -404,7 +494,9 @@ __global__ void k_s23_segfix(const __grid_constant__ S23Ctx c)
         c.seg_hout[s] = h + count;
         h += count;
     }
-    *c.any_dirty = dirty;
+    if (dirty) atomicOr(&dirty_any, 1u);
+    __syncthreads();
+    if (tid == 0) *c.any_dirty = dirty_any;
 }
 
 // ---- 4. one pixel sample --------------------------------------------------------------
@@ -468,7 +560,7 @@ k_s23_shade(const __grid_constant__ S23Ctx c)
     S23Hit hit;
     Color3 term[RT_S23_MAX_TERMS];
     for (int t = 0; t < RT_S23_MAX_TERMS; ++t) term[t] = mkc(0.0f, 0.0f, 0.0f);
-    if (s23_intersect<true>(c, o, d, RT_RAY_TMAX, hit))
+    if (s23_intersect<true, false>(c, o, d, RT_RAY_TMAX, hit))
     {
         const RtS23Material& mat = c.materials[c.shapes[hit.shape].material];
         Color3 emit = mkc(mat.emittance[0], mat.emittance[1], mat.emittance[2]);
@@ -491,7 +583,7 @@ k_s23_shade(const __grid_constant__ S23Ctx c)
                 float dist;
                 V3 to_light = s23_normalized(lp - position, &dist);
                 S23Hit sh;
-                bool blocked = s23_intersect<false>(c, position, to_light, dist, sh);
+                bool blocked = s23_intersect<false, false>(c, position, to_light, dist, sh);
                 if (!blocked || (sh.is_light_self && sh.shape == (int)c.lights[l]))
                 {
                     float atten = std_max(0.0f, dot3(hit.normal, to_light));
@@ -522,7 +614,7 @@ k_s23_shade(const __grid_constant__ S23Ctx c)
                         float dist;
                         V3 to_light = s23_normalized(lp - position, &dist);
                         S23Hit sh;
-                        bool blocked = s23_intersect<false>(c, position, to_light, dist, sh);
+                        bool blocked = s23_intersect<false, false>(c, position, to_light, dist, sh);
                         if (!blocked || (sh.is_light_self && sh.shape == (int)c.lights[l]))
                             light_result = light_result + e * cm * s23_shade(mat, hit.normal, d, to_light);
                     }
@@ -571,6 +663,47 @@ k_s23_resolve(const __grid_constant__ S23Ctx c)
 }
 
 // ---- host side -----------------------------------------------------------------------
+// volatile stores keep each intermediate a rounded float (no excess precision, no contraction)
+inline float s23_host_dot(const float* a, const float* b)
+{
+    volatile float x = a[0] * b[0], y = a[1] * b[1], z = a[2] * b[2];
+    volatile float xy = x + y;
+    volatile float r = xy + z;
+    return r;
+}
+
+inline float s23_host_normalize(const float* v, float* out)
+{
+    volatile float len = sqrtf(s23_host_dot(v, v));
+    for (int i = 0; i < 3; ++i) { volatile float q = v[i] / len; out[i] = q; }
+    return len;
+}
+
+inline S23Derived s23_derive(const RtS23Shape& sh)
+{
+    S23Derived d;
+    std::memset(&d, 0, sizeof(d));
+    if (sh.type == RT_S23_PLANE)
+        d.pos_dot_n = s23_host_dot(sh.position, sh.normal);
+    else if (sh.type == RT_S23_SPHERE)
+    {
+        volatile float r2 = sh.radius * sh.radius;
+        d.r2 = r2;
+    }
+    else
+    {
+        const float* a = sh.side1; const float* b = sh.side2;
+        volatile float cx1 = a[1] * b[2], cx2 = a[2] * b[1], cy1 = a[2] * b[0], cy2 = a[0] * b[2], cz1 = a[0] * b[1], cz2 = a[1] * b[0];
+        volatile float cx = cx1 - cx2, cy = cy1 - cy2, cz = cz1 - cz2;
+        float cr[3] = { cx, cy, cz };
+        s23_host_normalize(cr, d.n);
+        d.pos_dot_n = s23_host_dot(sh.position, d.n);
+        d.len1 = s23_host_normalize(sh.side1, d.s1n);
+        d.len2 = s23_host_normalize(sh.side2, d.s2n);
+    }
+    return d;
+}
+
 inline int rt_stage23_impl(int device, const RtS23Scene* scene, const RtCamera* cam, const RtS23Params* prm,
                            float* rgb, uint8_t* rgb8, RtRenderStats* stats)
 {
@@ -606,6 +739,8 @@ inline int rt_stage23_impl(int device, const RtS23Scene* scene, const RtCamera* 
     std::memcpy(c.shapes, scene->shapes, sizeof(RtS23Shape) * scene->num_shapes);
     std::memcpy(c.materials, scene->materials, sizeof(RtS23Material) * scene->num_materials);
     std::memcpy(c.lights, scene->lights, sizeof(uint32_t) * scene->num_lights);
+    for (uint32_t i = 0; i < scene->num_shapes; ++i)
+        c.derived[i] = s23_derive(scene->shapes[i]);
     c.num_shapes = scene->num_shapes;
     c.num_lights = scene->num_lights;
     c.cam = *cam;
@@ -630,21 +765,63 @@ inline int rt_stage23_impl(int device, const RtS23Scene* scene, const RtCamera* 
 
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    // one resident block per segment: the segments of a round run side by side
-    uint32_t want = (uint32_t)sms * 4;
+    // one resident warp per segment: the segments of a round run side by side
+    uint32_t want = (uint32_t)sms * 32;
     c.seg_len = (c.num_samples + want - 1) / want;
-    c.seg_len = ((c.seg_len + RT_S23_WINDOW - 1) / RT_S23_WINDOW) * RT_S23_WINDOW;
+    c.seg_len = ((c.seg_len + 31) / 32) * 32;
     c.num_segs = (uint32_t)((c.num_samples + c.seg_len - 1) / c.seg_len);
 
+    // a^i (i < 64), a^(64 j) (j < 64) and a^(4096 l) (l < 256) for both generators
+    static uint32_t table[2 * RT_S23_TABLE];
+    for (int g = 0; g < 2; ++g)
+    {
+        uint64_t a = g == 0 ? RT_MWC_AZ : RT_MWC_AW, m = g == 0 ? RT_MWC_MZ : RT_MWC_MW;
+        for (uint32_t i = 0; i < 64; ++i)
+        {
+            table[g * RT_S23_TABLE + i] = (uint32_t)mwc_powmod(a, i, m);
+            table[g * RT_S23_TABLE + 64 + i] = (uint32_t)mwc_powmod(a, 64ull * i, m);
+        }
+        for (uint32_t i = 0; i < 256; ++i)
+            table[g * RT_S23_TABLE + 128 + i] = (uint32_t)mwc_powmod(a, 4096ull * i, m);
+    }
+
     const size_t n = (size_t)c.num_samples, px = (size_t)c.width * c.height;
-    size_t bytes_flags = (n + 255) & ~(size_t)255;
-    size_t bytes_hb = n * 4, bytes_terms = n * 16 * c.terms, bytes_seg = (size_t)(c.num_segs + 1) * 8;
-    size_t total = bytes_flags + bytes_hb + bytes_terms + 2 * bytes_seg + (size_t)(c.num_segs + 64) * 4 + px * 12 + px * 3 + 1024;
-    char* block = NULL;
+    const size_t A = 255;       // every sub-buffer starts on a 256-byte boundary
+    size_t bytes_flags = (n + A) & ~A;
+    size_t bytes_hb = (n * 4 + A) & ~A, bytes_terms = (n * 16 * c.terms + A) & ~A;
+    size_t bytes_seg = ((size_t)(c.num_segs + 1) * 8 + A) & ~A, bytes_dirty = ((size_t)c.num_segs * 4 + A) & ~A;
+    size_t bytes_rgb = (px * 12 + A) & ~A, bytes_rgb8 = (px * 3 + A) & ~A;
+    size_t total = bytes_flags + bytes_hb + bytes_terms + 2 * bytes_seg + 2 * bytes_dirty + 256 + bytes_rgb + bytes_rgb8 +
+                   sizeof(table);
+    // working memory is kept between calls (grow only): a sweep re-renders the same image many times
+    static std::mutex cache_lock;
+    static char* cache_block = NULL;
+    static size_t cache_bytes = 0;
+    static int cache_device = -1;
+    std::lock_guard<std::mutex> guard(cache_lock);
+    cudaError_t err = cudaSuccess;
+    if (cache_device != device || cache_bytes < total)
+    {
+        if (cache_block)
+        {
+            cudaSetDevice(cache_device);
+            cudaFree(cache_block);
+            cudaSetDevice(device);
+        }
+        cache_block = NULL;
+        cache_bytes = 0;
+        err = cudaMalloc((void**)&cache_block, total);
+        if (err != cudaSuccess)
+        {
+            cache_block = NULL;
+            cudaGetLastError();
+            return rt_fail(RT_ERR_CUDA, cudaGetErrorString(err));
+        }
+        cache_bytes = total;
+        cache_device = device;
+    }
+    char* block = cache_block;
     cudaEvent_t ev[3] = { NULL, NULL, NULL };
-    cudaError_t err = cudaMalloc((void**)&block, total);
-    if (err != cudaSuccess)
-        return rt_fail(RT_ERR_CUDA, cudaGetErrorString(err));
     int rc = RT_OK;
     uint64_t launches = 0, rounds = 0;
     do
@@ -654,26 +831,31 @@ inline int rt_stage23_impl(int device, const RtS23Scene* scene, const RtCamera* 
         c.hits_before = (uint32_t*)q;               q += bytes_hb;
         c.seg_hin = (unsigned long long*)q;         q += bytes_seg;
         c.seg_hout = (unsigned long long*)q;        q += bytes_seg;
-        c.rgb = (float*)q;                          q += px * 12;
-        c.seg_dirty = (uint32_t*)q;                 q += (size_t)c.num_segs * 4;
-        c.any_dirty = (uint32_t*)q;                 q += 64 * 4;
+        c.rgb = (float*)q;                          q += bytes_rgb;
+        c.seg_dirty = (uint32_t*)q;                 q += bytes_dirty;
+        c.seg_sensitive = (uint32_t*)q;             q += bytes_dirty;
+        c.any_dirty = (uint32_t*)q;                 q += 256;
+        c.pow_table = (const uint32_t*)q;           q += sizeof(table);
         c.flags = (uint8_t*)q;                      q += bytes_flags;
         c.rgb8 = (uint8_t*)q;
         for (int i = 0; i < 3; ++i)
             if ((err = cudaEventCreate(&ev[i])) != cudaSuccess) break;
         if (err != cudaSuccess) break;
+        if ((err = cudaMemcpy((void*)c.pow_table, table, sizeof(table), cudaMemcpyHostToDevice)) != cudaSuccess) break;
         cudaEventRecord(ev[0]);
         if ((err = cudaMemsetAsync(c.seg_hin, 0, 2 * bytes_seg)) != cudaSuccess) break;
+        if ((err = cudaMemsetAsync(c.seg_sensitive, 0, bytes_dirty)) != cudaSuccess) break;
         unsigned sample_blocks = (unsigned)((n + 255) / 256);
         k_s23_guess<<<sample_blocks, 256>>>(c);
-        k_s23_segfix<<<1, 1>>>(c);
-        launches += 2;
+        k_s23_segfix<<<1, RT_S23_FIX_THREADS>>>(c);
+        k_s23_chain<<<1, 32>>>(c);
+        launches += 3;
         // every segment runs at least once (segfix marks only changed ones)
         if ((err = cudaMemsetAsync(c.seg_dirty, 1, (size_t)c.num_segs * 4)) != cudaSuccess) break;
         for (;;)
         {
-            k_s23_prepass<<<c.num_segs, RT_S23_PRE_THREADS>>>(c);
-            k_s23_segfix<<<1, 1>>>(c);
+            k_s23_prepass<<<(c.num_segs + RT_S23_PRE_WARPS - 1) / RT_S23_PRE_WARPS, RT_S23_PRE_WARPS * 32>>>(c);
+            k_s23_segfix<<<1, RT_S23_FIX_THREADS>>>(c);
             launches += 2;
             ++rounds;
             uint32_t dirty = 0;
@@ -711,7 +893,6 @@ inline int rt_stage23_impl(int device, const RtS23Scene* scene, const RtCamera* 
         }
     } while (0);
     for (int i = 0; i < 3; ++i) if (ev[i]) cudaEventDestroy(ev[i]);
-    cudaFree(block);
     if (err != cudaSuccess)
     {
         cudaGetLastError();
