@@ -44,10 +44,18 @@
 #define RT_QBINS 8
 #endif
 #define RT_SBINS 16
+#define RT_LBINS 8
+// minimum resident blocks per SM asked of the shading kernels (register cap = 65536 / (blocks * RT_BLOCK)):
+// 6 blocks = 80 registers; k_light_sample wanted 96 (5 blocks), +2 % on the frame
+#ifndef RT_SHADE_MINBLOCKS
+#define RT_SHADE_MINBLOCKS 6
+#endif
 enum { CTL_PATH_A = 0, CTL_PATH_B = 8, CTL_SHADOW = 16, CTL_MIS = 24, CTL_SHADE = 32, CTL_LIT = 48,   // (room for 8 ray bins)
        CTL_CUR_PATH = 49, CTL_CUR_SHADOW = 50, CTL_CUR_MIS = 51,
        // split traversal: mesh / resume queue counts and cursors, double buffered
-       CTL_MESH_N = 52, CTL_MESH_CUR = 54, CTL_RES_N = 56, CTL_RES_CUR = 58, CTL_WORDS = 64 };
+       CTL_MESH_N = 52, CTL_MESH_CUR = 54, CTL_RES_N = 56, CTL_RES_CUR = 58,
+       // lit paths regrouped by (light, BRDF kind) for one light-sample iteration
+       CTL_LITB = 64, CTL_WORDS = 80 };
 #define CTL_PATH(cur) ((cur) ? CTL_PATH_B : CTL_PATH_A)
 
 // Device pointers and constants of one render call
@@ -225,12 +233,12 @@ __device__ __forceinline__ void camera_ray(const RenderCtx& c, uint32_t p, uint3
     uint32_t perm_lens = c.perms[(size_t)(D5 + 1) * c.num_pixels + p];
     uint32_t perm_sub = c.perms[(size_t)(D5 + 2) * c.num_pixels + p];
     float pu, pv;
-    cmj_sample2d(psi, c.ps, c.ps, perm_sub, pu, pv);
+    cmj2d(psi, c.ps, c.ps, perm_sub, pu, pv);
     float xu = ((float)x + pu) / (float)c.width;
     float yu = 1.0f - ((float)y + pv) / (float)c.height;
     float lens_u, lens_v;
-    cmj_sample2d(psi, c.ps, c.ps, perm_lens, lens_u, lens_v);
-    float time_u = cmj_sample1d(psi, c.spp, perm_time);
+    cmj2d(psi, c.ps, c.ps, perm_lens, lens_u, lens_v);
+    float time_u = cmj1d(psi, c.spp, perm_time);
 
     float xs = (xu - 0.5f) * c.aspect + 0.5f;
     float ys = yu;
@@ -434,7 +442,7 @@ k_split_mesh(const __grid_constant__ DScene sc, const IO io, const SplitBufs sb,
 }
 
 // pathTrace, one bounce, everything that does not need further rays
-__global__ void __launch_bounds__(RT_BLOCK)
+__global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_MINBLOCKS)
 k_shade(const __grid_constant__ RenderCtx c, int cur, uint32_t bounce)
 {
     const BinQ<RT_SBINS> shade = { c.q_shade, c.ctl + CTL_SHADE, c.qcap };
@@ -442,6 +450,7 @@ k_shade(const __grid_constant__ RenderCtx c, int cur, uint32_t bounce)
     if (blockIdx.x == 0 && threadIdx.x == 0)
     {
         for (int b = 0; b < RT_QBINS; ++b) { c.ctl[CTL_SHADOW + b] = 0; c.ctl[CTL_MIS + b] = 0; }
+        for (int b = 0; b < RT_LBINS; ++b) c.ctl[CTL_LITB + b] = 0;
         c.ctl[CTL_CUR_SHADOW] = 0;
         c.ctl[CTL_CUR_MIS] = 0;
         c.ctl[CTL_CUR_PATH] = 0;
@@ -507,7 +516,7 @@ k_shade(const __grid_constant__ RenderCtx c, int cur, uint32_t bounce)
                     uint32_t p = i / c.spp, psi = i % c.spp;
                     uint32_t perm = c.perms[(size_t)(5 * bounce + 0) * c.num_pixels + p];
                     float u, v;
-                    cmj_sample2d(psi, c.ps, c.ps, perm, u, v);
+                    cmj2d(psi, c.ps, c.ps, perm, u, v);
                     V3 incoming;
                     float pdf = 0.0f;
                     float value = brdf_sample(mat.brdf, mat.exponent, incoming, outgoing, normal, u, v, pdf);
@@ -531,10 +540,34 @@ k_shade(const __grid_constant__ RenderCtx c, int cur, uint32_t bounce)
     }
 }
 
-// One light sample of the direct-lighting loop (:336-422): produces at most one
-// shadow ray and one BRDF-MIS probe per lit path
+// Which light does light-sample iteration `lsi` of path sample i use, and with which sample index
+__device__ __forceinline__ void light_choice(const RenderCtx& c, uint32_t bounce, uint32_t lsi, uint32_t p, uint32_t psi,
+                                             uint32_t& idx, uint32_t& light_index)
+{
+    if (c.sc.stage6)
+    {
+        // every light in turn, ls*ls samples each (S6 RaytraceMain.cpp:274-384)
+        light_index = lsi / c.ls2;
+        idx = psi * c.ls2 + lsi % c.ls2;
+    }
+    else
+    {
+        // random light (:358-364)
+        uint32_t n1 = c.ps * c.ls * c.ps * c.ls;
+        uint32_t perm_sel = c.perms[(size_t)(5 * bounce + 1) * c.num_pixels + p];
+        idx = psi * c.nls + lsi;
+        float liu = cmj1d(idx, n1, perm_sel);
+        light_index = (uint32_t)(liu * (float)c.sc.num_lights);
+        if (light_index >= c.sc.num_lights)
+            light_index = c.sc.num_lights - 1;
+    }
+}
+
+// Regroup the lit paths by (chosen light, BRDF kind) so that the lanes of a k_light_sample
+// warp run the same light-sampling and BRDF code.  The bins live in the shade queue's
+// buffer, which is idle between k_shade and the next bounce's path trace.
 __global__ void __launch_bounds__(RT_BLOCK)
-k_light_sample(const __grid_constant__ RenderCtx c, uint32_t bounce, uint32_t lsi)
+k_light_select(const __grid_constant__ RenderCtx c, uint32_t bounce, uint32_t lsi)
 {
     const uint32_t n = c.ctl[CTL_LIT];
     RT_GRID_STRIDE(j, n)
@@ -542,6 +575,27 @@ k_light_sample(const __grid_constant__ RenderCtx c, uint32_t bounce, uint32_t ls
         if (j < n)
         {
             const uint32_t i = c.q_lit[j];
+            uint32_t idx, light_index;
+            light_choice(c, bounce, lsi, i / c.spp, i % c.spp, idx, light_index);
+            const RtMaterial& mat = c.sc.materials[__float_as_uint(c.wo_mat[i].w)];
+            uint32_t bin = (light_index & 3u) | (mat.brdf == RT_BRDF_GLOSSY ? 4u : 0u);
+            bq_push(c.q_shade, c.ctl + CTL_LITB, c.qcap, bin, i);
+        }
+    }
+}
+
+// One light sample of the direct-lighting loop (:336-422): produces at most one
+// shadow ray and one BRDF-MIS probe per lit path
+__global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_MINBLOCKS)
+k_light_sample(const __grid_constant__ RenderCtx c, uint32_t bounce, uint32_t lsi)
+{
+    const BinQ<RT_LBINS> lit = { c.q_shade, c.ctl + CTL_LITB, c.qcap };
+    const uint32_t n = lit.total();
+    RT_GRID_STRIDE(j, n)
+    {
+        if (j < n)
+        {
+            const uint32_t i = lit.at(j);
             uint32_t p = i / c.spp, psi = i % c.spp;
             float4 pt = c.pos_time[i], wm = c.wo_mat[i], h1 = c.hit1[i];
             V3 position = xyz(pt), outgoing = xyz(wm), normal = xyz(h1);
@@ -551,32 +605,20 @@ k_light_sample(const __grid_constant__ RenderCtx c, uint32_t bounce, uint32_t ls
 
             uint32_t n1 = c.ps * c.ls * c.ps * c.ls, n2 = c.ps * c.ls;
             const uint32_t* pp = c.perms + (size_t)(5 * bounce) * c.num_pixels + p;
-            uint32_t perm_sel = pp[(size_t)1 * c.num_pixels];
             uint32_t perm_elem = pp[(size_t)2 * c.num_pixels];
             uint32_t perm_light = pp[(size_t)3 * c.num_pixels];
             uint32_t perm_brdf = pp[(size_t)4 * c.num_pixels];
 
             uint32_t idx, light_index;
+            light_choice(c, bounce, lsi, p, psi, idx, light_index);
             if (c.sc.stage6)
             {
-                // Every light in turn, ls*ls samples each (S6 RaytraceMain.cpp:274-384).
-                // The reference draws these from one serial, data-dependent Rng, which has
-                // no parallel equivalent; the counter-based stream stands in (same strata,
-                // decorrelated per light), so Stage 6 images match statistically, not bitwise.
-                light_index = lsi / c.ls2;
-                idx = psi * c.ls2 + lsi % c.ls2;
+                // The Stage 6 reference draws these samples from one serial, data-dependent Rng,
+                // which has no parallel equivalent; the counter-based stream stands in (same
+                // strata, decorrelated per light), so Stage 6 images match statistically, not bitwise.
                 uint32_t salt = (light_index + 1u) * 0x9e3779b9u;
                 salt ^= salt >> 15; salt *= 0x85ebca6bu; salt ^= salt >> 13;
                 perm_elem ^= salt; perm_light ^= salt * 0x9e3779b9u; perm_brdf ^= salt * 0x85ebca6bu;
-            }
-            else
-            {
-                // Random light (:358-364)
-                idx = psi * c.nls + lsi;
-                float liu = cmj_sample1d(idx, n1, perm_sel);
-                light_index = (uint32_t)(liu * (float)c.sc.num_lights);
-                if (light_index >= c.sc.num_lights)
-                    light_index = c.sc.num_lights - 1;
             }
             uint32_t light_shape = c.sc.lights[light_index];
             DShape lsh = load_shape(c.sc, light_shape);
@@ -584,8 +626,8 @@ k_light_sample(const __grid_constant__ RenderCtx c, uint32_t bounce, uint32_t ls
             Color3 emitted = mkc(lmat.emittance[0], lmat.emittance[1], lmat.emittance[2]);
 
             float lsu, lsv;
-            cmj_sample2d(idx, n2, n2, perm_light, lsu, lsv);
-            float leu = cmj_sample1d(idx, n1, perm_elem);
+            cmj2d(idx, n2, n2, perm_light, lsu, lsv);
+            float leu = cmj1d(idx, n1, perm_elem);
             V3 lpos, lnrm;
             float lpdf;
             light_sample(c.sc, lsh, position, time, lsu, lsv, leu, lpos, lnrm, lpdf);
@@ -612,7 +654,7 @@ k_light_sample(const __grid_constant__ RenderCtx c, uint32_t bounce, uint32_t ls
 
             // BRDF sample towards (hopefully) the same light (:410-422)
             float bsu, bsv;
-            cmj_sample2d(idx, n2, n2, perm_brdf, bsu, bsv);
+            cmj2d(idx, n2, n2, perm_brdf, bsu, bsv);
             V3 bi;
             float bpdf = 0.0f;
             float bres = brdf_sample(mat.brdf, mat.exponent, bi, outgoing, normal, bsu, bsv, bpdf);
@@ -662,13 +704,14 @@ k_trace_mis(const __grid_constant__ RenderCtx c)
 
 // Combine the two MIS samples of light sample `lsi` (:396-439) and, after the last
 // one, fold the bounce's direct lighting into the path (:443-447)
-__global__ void __launch_bounds__(RT_BLOCK)
+__global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_MINBLOCKS)
 k_resolve(const __grid_constant__ RenderCtx c, uint32_t lsi)
 {
     const uint32_t n = c.ctl[CTL_LIT];
     if (blockIdx.x == 0 && threadIdx.x == 0)
     {
         for (int b = 0; b < RT_QBINS; ++b) { c.ctl[CTL_SHADOW + b] = 0; c.ctl[CTL_MIS + b] = 0; }   // refilled by the next light sample
+        for (int b = 0; b < RT_LBINS; ++b) c.ctl[CTL_LITB + b] = 0;
         c.ctl[CTL_CUR_SHADOW] = 0;
         c.ctl[CTL_CUR_MIS] = 0;
     }
@@ -1198,7 +1241,9 @@ static int rt_launch_batch(RtScene* s, const RenderCtx& c, cudaStream_t st, uint
         launches += 2;
         for (uint32_t l = 0; l < c.nls; ++l)
         {
+            k_light_select<<<wide, RT_BLOCK, 0, st>>>(c, b, l);
             k_light_sample<<<wide, RT_BLOCK, 0, st>>>(c, b, l);
+            launches += 1;
             rt_trace_mark(rb, timed, st);
             if (split)
             {

@@ -205,6 +205,17 @@ __host__ __device__ __forceinline__ void cmj_sample2d(uint32_t index, uint32_t x
 }
 
 #ifdef __CUDACC__
+// Entry points used by the renderer's kernels; -DRT_CMJ_CALL=__noinline__ makes them real calls
+// (measured slower together with RT_SHADE_CALL, see rt_shade.cuh)
+#ifndef RT_CMJ_CALL
+#define RT_CMJ_CALL __forceinline__
+#endif
+__device__ RT_CMJ_CALL float cmj1d(uint32_t index, uint32_t samples, uint32_t perm) { return cmj_sample1d(index, samples, perm); }
+__device__ RT_CMJ_CALL void cmj2d(uint32_t index, uint32_t xs, uint32_t ys, uint32_t perm, float& u, float& v)
+{
+    cmj_sample2d(index, xs, ys, perm, u, v);
+}
+
 // ---------------------------------------------------------------------------
 // libm.  The reference calls the C library's float cos/sin/pow; they feed sample
 // DIRECTIONS, so they are reproduced bit for bit (rt_libm.cuh restates glibc 2.39's

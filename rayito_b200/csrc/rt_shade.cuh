@@ -14,6 +14,14 @@
 #include "rt_sampling.cuh"
 #include "rt_trace.cuh"
 
+// Inlined by default.  k_shade / k_light_sample / k_resolve come to 58-76 KB of SASS and show
+// 30 % no-instruction stalls, but making these routines real calls (-DRT_SHADE_CALL=__noinline__)
+// measured 5 % SLOWER on the frame (profiles/README.md, round 1): the calls' spills cost more
+// than the fetch stalls they save.
+#ifndef RT_SHADE_CALL
+#define RT_SHADE_CALL __forceinline__
+#endif
+
 struct Color3
 {
     float r, g, b;
@@ -35,7 +43,7 @@ __device__ __forceinline__ bool same_hemisphere_reject(float n_dot_i, float n_do
 }
 
 // Brdf::evaluateSA; returns the reflectance, pdf through out_pdf
-__device__ __forceinline__ float brdf_evaluate(uint32_t brdf, float exponent, V3 incoming, V3 outgoing, V3 normal, float& out_pdf)
+__device__ RT_SHADE_CALL float brdf_evaluate(uint32_t brdf, float exponent, V3 incoming, V3 outgoing, V3 normal, float& out_pdf)
 {
     if (brdf == RT_BRDF_LAMBERT)
     {
@@ -75,7 +83,7 @@ __device__ __forceinline__ float brdf_evaluate(uint32_t brdf, float exponent, V3
 }
 
 // Brdf::sampleSA
-__device__ __forceinline__ float brdf_sample(uint32_t brdf, float exponent, V3& out_incoming, V3 outgoing, V3 normal,
+__device__ RT_SHADE_CALL float brdf_sample(uint32_t brdf, float exponent, V3& out_incoming, V3 outgoing, V3 normal,
                                              float u1, float u2, float& out_pdf)
 {
     if (brdf == RT_BRDF_LAMBERT)
@@ -129,7 +137,7 @@ __device__ __forceinline__ float sphere_area_pdf(float radius)
 // Light::sampleSurface for the light behind shape `sh`.  Positions are in the
 // space of the ShapeSet's members ("non-local"): the reference does not apply the
 // set's own transform here either.
-__device__ __forceinline__ void light_sample(const DScene& sc, const DShape& sh, V3 ref_pos, float ref_time,
+__device__ RT_SHADE_CALL void light_sample(const DScene& sc, const DShape& sh, V3 ref_pos, float ref_time,
                                              float u1, float u2, float u3,
                                              V3& out_pos, V3& out_normal, float& out_pdf)
 {
@@ -264,7 +272,7 @@ __device__ __forceinline__ void light_sample(const DScene& sc, const DShape& sh,
 
 // Light::intersectPdf for a BRDF-sampled ray that hit the light (RLight.h:220-239,
 // 317-328).  ray_o/ray_d/time describe the probe ray, t/normal its hit.
-__device__ __forceinline__ float light_intersect_pdf(const DScene& sc, const DShape& sh, V3 ray_o, V3 ray_d, float time,
+__device__ RT_SHADE_CALL float light_intersect_pdf(const DScene& sc, const DShape& sh, V3 ray_o, V3 ray_d, float time,
                                                      float t, V3 hit_normal)
 {
     TRS trs = shape_xform(sc, sh, time);
