@@ -53,6 +53,8 @@ WORKLOADS = {
                label="synthetic displaced sphere, 4 999 696 quads = 9 999 392 triangles, 3840x2160 1024spp"),
     "c5-64spp": dict(recipe=5, width=3840, height=2160, ps=8, ls=1, depth=3, grid=(2236, 2236),
                      label="synthetic displaced sphere, 4 999 696 quads = 9 999 392 triangles, 3840x2160 64spp"),
+    "c5-small": dict(recipe=5, width=960, height=540, ps=8, ls=1, depth=3, grid=(2236, 2236),
+                     label="synthetic displaced sphere, 9 999 392 triangles, 960x540 64spp (profiling size)"),
     "c3": dict(recipe=6, stage=6, width=1920, height=1080, ps=8, ls=1, depth=3, grid=(0, 0),
                label="Rayito_Stage6 scene (bumpy.obj, BVH, two area lights, Stage 6 rules) 1920x1080 64spp ls1 depth3"),
 }
@@ -61,6 +63,16 @@ C2_SWEEP = [(1, 1), (2, 2), (4, 4), (8, 8), (16, 16)]
 WORKLOADS["c2"] = dict(stage23=3, width=512, height=512, sweep=C2_SWEEP,
                        label="Rayito_Stage3 built-in scene 512x512, pixel-sample sweep 1/4/16/64/256 spp, "
                              "2 area lights x 16 light samples")
+# DRAM bytes (read + write) per launch of the dominant traversal kernel, from the `ncu --set full`
+# captures summarised under profiles/ (same batch size as the full-size workloads; None = not captured)
+NCU_TRAFFIC = {
+    1: dict(kernel="k_split_top<ANY=1,FRESH=1,ShadowIO> (fresh top-level pass of the shadow rays of one 16 Mi-sample batch)",
+            bytes=1.918768e9 + 650.789120e6, ms=2.1, source="profiles/r01_v6_split_c4small_full_summary.csv",
+            note="mostly per-ray wavefront state (scattered 16-byte records), not scene data: the 3 MB scene is L1/L2-resident"),
+    5: dict(kernel="k_split_mesh<64,ANY=0,PathIO> (face-BVH pass of the path rays of one 16 Mi-sample batch)",
+            bytes=4.922347e9 + 319.387904e6, ms=5.8, source="profiles/r01_v6_mesh_c5small_full_summary.csv",
+            note="random 32-byte node and 48-byte triangle gathers from a 660 MB scene, L2 hit 66 %"),
+}
 CAMERA_SPEC = {       # fov, origin, target, up, focal distance, lens radius, shutter open/close (GUI defaults)
     1: [30, -4, 5, 15, 0, 0, 0, 0, 1, 0, 16, 0, 0, 1],
     2: [30, -4, 10, 30, 0, 5, 0, 0, 1, 0, 16, 0, 0, 1],
@@ -409,7 +421,8 @@ def main():
     roofline = {
         "bound": "hbm", "kernel": "k_trace_paths + k_trace_mis (closest hit) + k_trace_shadow (any hit)",
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-        "traffic": None,
+        "traffic": (NCU_TRAFFIC.get(wl["recipe"]) or {}).get("bytes"),
+        "traffic_detail": NCU_TRAFFIC.get(wl["recipe"]),
         "bytes_per_ray": bytes_total / rays_total,
         "per_ray": {"node_pops": allsum(counted["node_pops"]) / rays_total,
                     "tri_tests": allsum(counted["tri_tests"]) / rays_total,

@@ -356,17 +356,30 @@ __device__ __forceinline__ V3 to_local_normal(const TRS& x, V3 n) { return rotat
 // ---------------------------------------------------------------------------
 // Slab test (BBox::intersects, RAccel.h:47-59).  t0/t1 are clipped in place.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ bool box_test(float4 q0, float4 q1, V3 o, V3 inv, float& t0, float& t1)
+// The two halves of the slab test: the part that depends on the node and the ray only ...
+__device__ __forceinline__ void box_slabs(float4 q0, float4 q1, V3 o, V3 inv, float& bmin, float& bmax)
 {
     V3 a = (mk(q0.x, q0.y, q0.z) - o) * inv;     // vt0 = (m_min - origin) * invDir
     V3 b = (mk(q0.w, q1.x, q1.y) - o) * inv;     // vt1 = (m_max - origin) * invDir
     V3 nr = mk(std_min(a.x, b.x), std_min(a.y, b.y), std_min(a.z, b.z));
     V3 fr = mk(std_max(a.x, b.x), std_max(a.y, b.y), std_max(a.z, b.z));
-    float bmin = std_max(std_max(nr.x, nr.y), nr.z);   // vtNear.maxComponent()
-    float bmax = std_min(std_min(fr.x, fr.y), fr.z);   // vtFar.minComponent()
+    bmin = std_max(std_max(nr.x, nr.y), nr.z);   // vtNear.maxComponent()
+    bmax = std_min(std_min(fr.x, fr.y), fr.z);   // vtFar.minComponent()
+}
+
+// ... and the clipping of the inherited range, which also depends on when the node is popped
+__device__ __forceinline__ bool box_clip(float bmin, float bmax, float& t0, float& t1)
+{
     t0 = std_max(bmin, t0);
     t1 = std_min(bmax, t1);
     return t0 <= t1;
+}
+
+__device__ __forceinline__ bool box_test(float4 q0, float4 q1, V3 o, V3 inv, float& t0, float& t1)
+{
+    float bmin, bmax;
+    box_slabs(q0, q1, o, inv, bmin, bmax);
+    return box_clip(bmin, bmax, t0, t1);
 }
 
 // ---------------------------------------------------------------------------

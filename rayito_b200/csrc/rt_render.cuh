@@ -417,8 +417,15 @@ k_trace_paths(const __grid_constant__ RenderCtx c, int cur)
 }
 
 // ---- split traversal kernels (rt_split.cuh) ---------------------------------
+// minimum resident blocks per SM asked of the split traversal kernels (1 = let the compiler choose)
+#ifndef RT_TOP_MINBLOCKS
+#define RT_TOP_MINBLOCKS 1
+#endif
+#ifndef RT_MESH_MINBLOCKS
+#define RT_MESH_MINBLOCKS 1
+#endif
 template <bool ANY, bool COUNT, bool FRESH, class IO>
-__global__ void __launch_bounds__(RT_BLOCK)
+__global__ void __launch_bounds__(RT_BLOCK, RT_TOP_MINBLOCKS)
 k_split_top(const __grid_constant__ DScene sc, const IO io, const SplitBufs sb, const SplitPass ps, uint64_t* totals, int count_slot)
 {
     split_zero(ps);
@@ -431,7 +438,7 @@ k_split_top(const __grid_constant__ DScene sc, const IO io, const SplitBufs sb, 
 }
 
 template <int CAP, bool ANY, bool COUNT, class IO>
-__global__ void __launch_bounds__(RT_BLOCK)
+__global__ void __launch_bounds__(RT_BLOCK, RT_MESH_MINBLOCKS)
 k_split_mesh(const __grid_constant__ DScene sc, const IO io, const SplitBufs sb, const SplitPass ps, uint64_t* totals)
 {
     split_zero(ps);
@@ -1116,7 +1123,7 @@ inline void rt_trace_mark(RenderBuffers* rb, bool timed, cudaStream_t st)
 // empty queue exit at once.
 template <bool ANY, bool COUNT, class IO>
 static void rt_launch_split_stage(RtScene* s, const RenderCtx& c, const IO& io,
-                                  uint32_t* fresh_cursor, int count_slot, unsigned grid, cudaStream_t st, uint64_t& launches)
+                                  uint32_t* fresh_cursor, int count_slot, unsigned grid, unsigned grid_mesh, cudaStream_t st, uint64_t& launches)
 {
     cudaMemsetAsync(c.ctl + CTL_MESH_N, 0, 8 * sizeof(uint32_t), st);
     SplitPass p;
@@ -1141,8 +1148,8 @@ static void rt_launch_split_stage(RtScene* s, const RenderCtx& c, const IO& io,
         m.zero[0] = c.ctl + CTL_MESH_N + b;
         m.zero[1] = c.ctl + CTL_MESH_CUR + b;
         m.zero[2] = m.zero[3] = NULL;
-        if (deep) k_split_mesh<64, ANY, COUNT, IO><<<grid, RT_BLOCK, 0, st>>>(c.sc, io, c.split, m, c.totals);
-        else      k_split_mesh<32, ANY, COUNT, IO><<<grid, RT_BLOCK, 0, st>>>(c.sc, io, c.split, m, c.totals);
+        if (deep) k_split_mesh<64, ANY, COUNT, IO><<<grid_mesh, RT_BLOCK, 0, st>>>(c.sc, io, c.split, m, c.totals);
+        else      k_split_mesh<32, ANY, COUNT, IO><<<grid_mesh, RT_BLOCK, 0, st>>>(c.sc, io, c.split, m, c.totals);
         SplitPass r;
         r.in_queue = c.q_resume[a];
         r.in_count = c.ctl + CTL_RES_N + a;
@@ -1202,12 +1209,15 @@ static int rt_launch_batch(RtScene* s, const RenderCtx& c, cudaStream_t st, uint
         tg_mis = (unsigned)(dev_sms * std::max(d, 1));
     }
     // split kernels are lighter; size their persistent grid from the heaviest of them
-    unsigned tg_split;
+    unsigned tg_split, tg_mesh;
     {
-        int a = 4, b = 4;
+        int a = 4, b = 4, d = 4;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_split_top<false, COUNT, true, PathIO>, RT_BLOCK, 0);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_split_mesh<64, false, COUNT, PathIO>, RT_BLOCK, 0);
-        tg_split = (unsigned)(dev_sms * std::max(std::min(a, b), 1));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d, k_split_mesh<32, false, COUNT, PathIO>, RT_BLOCK, 0);
+        // one grid for both kinds of pass (separate sizes measured no better)
+        tg_split = (unsigned)(dev_sms * std::max(std::min(a, std::min(b, d)), 1));
+        tg_mesh = tg_split;
     }
 
     k_pixel_setup<<<pix_blocks, RT_BLOCK, 0, st>>>(c);
@@ -1222,7 +1232,7 @@ static int rt_launch_batch(RtScene* s, const RenderCtx& c, cudaStream_t st, uint
             uint64_t before = launches;
             k_stage_prologue<<<1, 1, 0, st>>>(c, cur);
             PathIO io = make_path_io(c, cur);
-            rt_launch_split_stage<false, COUNT>(s, c, io, c.ctl + CTL_CUR_PATH, 0, tg_split, st, launches);
+            rt_launch_split_stage<false, COUNT>(s, c, io, c.ctl + CTL_CUR_PATH, 0, tg_split, tg_mesh, st, launches);
             launches += 1;
             trace_launches += launches - before;
             launches -= 1;      // the shared "+= 2" below accounts for trace + shade
@@ -1249,9 +1259,9 @@ static int rt_launch_batch(RtScene* s, const RenderCtx& c, cudaStream_t st, uint
             {
                 uint64_t before = launches;
                 ShadowIO sio = make_shadow_io(c);
-                rt_launch_split_stage<true, COUNT>(s, c, sio, c.ctl + CTL_CUR_SHADOW, 1, tg_split, st, launches);
+                rt_launch_split_stage<true, COUNT>(s, c, sio, c.ctl + CTL_CUR_SHADOW, 1, tg_split, tg_mesh, st, launches);
                 MisIO mio = make_mis_io(c);
-                rt_launch_split_stage<false, COUNT>(s, c, mio, c.ctl + CTL_CUR_MIS, 0, tg_split, st, launches);
+                rt_launch_split_stage<false, COUNT>(s, c, mio, c.ctl + CTL_CUR_MIS, 0, tg_split, tg_mesh, st, launches);
                 trace_launches += launches - before;
                 launches -= 2;  // the shared "+= 4" below accounts for two traces
             }
