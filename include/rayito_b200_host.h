@@ -24,6 +24,9 @@ enum
     RTH_RECIPE_STAGE7_SCENE2 = 2,
     RTH_RECIPE_STAGE7_SCENE1_MESHLIGHT = 3, /* scene 1 with bumpy.obj as a mesh light (MainWindow.cpp:193-196) */
     RTH_RECIPE_SYNTHETIC_MESH = 5,  /* grid_u x grid_v quads on a displaced sphere */
+    RTH_RECIPE_EDGE_LINEAR_LIST = 7, /* edge-case scenes of the parity tests (host/scene_recipes.h buildEdgeScene) */
+    RTH_RECIPE_EDGE_NO_LIGHTS = 8,
+    RTH_RECIPE_EDGE_EMPTY = 9,
     RTH_RECIPE_STAGE6_SCENE = 6     /* Stage 6 scene + Stage 6 rules (Rayito_Stage6_QT/MainWindow.cpp:38-146); needs obj_path */
 };
 

@@ -191,6 +191,7 @@ bool buildInto(RefScene& rs)
     case 3: return rayito_recipes::buildStage7Scene1(*rs.set, *rs.store, rs.objPath.c_str(), true);
     case 2: return rayito_recipes::buildStage7Scene2(*rs.set, *rs.store);
     case 5: return rayito_recipes::buildSyntheticMeshScene(*rs.set, *rs.store, rs.gridU, rs.gridV);
+    case 7: case 8: case 9: return rayito_recipes::buildEdgeScene(*rs.set, *rs.store, rs.sceneId - 7);
     default: return false;
     }
 }

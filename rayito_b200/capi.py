@@ -96,6 +96,9 @@ RECIPE_STAGE7_SCENE2 = 2
 RECIPE_STAGE7_SCENE1_MESHLIGHT = 3
 RECIPE_SYNTHETIC_MESH = 5
 RECIPE_STAGE6_SCENE = 6
+RECIPE_EDGE_LINEAR_LIST = 7
+RECIPE_EDGE_NO_LIGHTS = 8
+RECIPE_EDGE_EMPTY = 9
 
 # Every symbol include/rayito_b200.h declares (checked by the CPU test-suite)
 CORE_SYMBOLS = [

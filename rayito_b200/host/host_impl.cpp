@@ -326,6 +326,12 @@ RthScene* rth_scene_create(int recipe, const char* obj_path, unsigned grid_u, un
         s->cameraSpec = rayito_recipes::defaultCameraScene1();
         built = rayito_recipes::buildSyntheticMeshScene(s->set, s->store, grid_u, grid_v);
         break;
+    case RTH_RECIPE_EDGE_LINEAR_LIST:
+    case RTH_RECIPE_EDGE_NO_LIGHTS:
+    case RTH_RECIPE_EDGE_EMPTY:
+        s->cameraSpec = rayito_recipes::defaultCameraScene1();
+        built = rayito_recipes::buildEdgeScene(s->set, s->store, recipe - RTH_RECIPE_EDGE_LINEAR_LIST);
+        break;
     default:
         t_hostError = "unknown recipe";
         delete s;
@@ -384,6 +390,8 @@ int rth_raytrace(int recipe, const char* obj_path, unsigned grid_u, unsigned gri
         case RTH_RECIPE_STAGE7_SCENE1_MESHLIGHT: built = rayito_recipes::buildStage7Scene1(set, store, obj_path ? obj_path : "", true); break;
         case RTH_RECIPE_STAGE7_SCENE2: built = rayito_recipes::buildStage7Scene2(set, store); break;
         case RTH_RECIPE_SYNTHETIC_MESH: built = rayito_recipes::buildSyntheticMeshScene(set, store, grid_u, grid_v); break;
+        case RTH_RECIPE_EDGE_LINEAR_LIST: case RTH_RECIPE_EDGE_NO_LIGHTS: case RTH_RECIPE_EDGE_EMPTY:
+            built = rayito_recipes::buildEdgeScene(set, store, recipe - RTH_RECIPE_EDGE_LINEAR_LIST); break;
         default: break;
         }
         if (!built)

@@ -338,6 +338,79 @@ bool buildSyntheticMeshScene(SetT& set, SceneStore& st, unsigned gridU, unsigned
     return true;
 }
 
+// Edge-case scenes for the parity tests (not from the GUI).  They reach code the two GUI
+// scenes do not: variant 0 has only two finite shapes, so the set keeps its linear list
+// instead of a BVH (RScene.h:203-204), a mesh of a pentagon and a hexagon with per-vertex
+// normals (fan triangulation, RMesh.h:226-238, 305-333) under scale + rotation keys, and a
+// tilted rectangle light; variant 1 has no lights at all, a sphere under non-uniform scale and
+// rotation keys, a mirror sphere and a statically squashed sphere; variant 2 is the empty set.
+template <typename SetT>
+bool buildEdgeScene(SetT& set, SceneStore& st, int variant)
+{
+    using namespace Rayito;
+    if (variant == 2)
+        return true;
+    Material* grey = st.keep(new DiffuseMaterial(Color(0.7f, 0.7f, 0.7f)));
+    Plane* plane = st.add(new Plane(Point(), Vector(0.0f, 1.0f, 0.0f), grey, true));
+    plane->transform().translate(0.0f, Vector(0.0f, -2.0f, 0.0f));
+    set.addShape(plane);
+    if (variant == 0)
+    {
+        Material* glossy = st.keep(new GlossyMaterial(Color(0.9f, 0.5f, 0.2f), 0.2f));
+        std::vector<Point> verts;
+        std::vector<Vector> normals;
+        std::vector<Face> faces(2);
+        // a pentagon in the z = 0 plane and a hexagon folded away from it along their shared edge
+        const float px[5] = { 0.0f, 1.0f, 1.4f, 0.5f, -0.4f }, py[5] = { 0.0f, 0.0f, 0.9f, 1.5f, 0.9f };
+        for (int i = 0; i < 5; ++i)
+        {
+            verts.push_back(Point(px[i], py[i], 0.0f));
+            normals.push_back(Vector(0.1f * (px[i] - 0.5f), 0.1f * (py[i] - 0.7f), 1.0f).normalized());
+            faces[0].m_vertexIndices.push_back((unsigned)i);
+            faces[0].m_normalIndices.push_back((unsigned)i);
+        }
+        const float hx[4] = { 1.2f, 0.9f, 0.1f, -0.2f }, hy[4] = { -0.6f, -1.1f, -1.1f, -0.6f }, hz[4] = { -0.3f, -0.6f, -0.6f, -0.3f };
+        faces[1].m_vertexIndices.push_back(1);
+        faces[1].m_vertexIndices.push_back(0);
+        for (int i = 0; i < 4; ++i)
+        {
+            verts.push_back(Point(hx[3 - i], hy[3 - i], hz[3 - i]));
+            faces[1].m_vertexIndices.push_back((unsigned)(5 + i));
+        }
+        Mesh* mesh = RAYITO_RECIPE_WRAP_MESH(new Mesh(verts, normals, faces, glossy));
+        st.add(mesh);
+        mesh->transform().setScaling(0.0f, Vector(1.5f, 0.7f, 1.2f));
+        mesh->transform().setTranslation(0.0f, Vector(-0.5f, -0.5f, 0.3f));
+        mesh->transform().setScaling(1.0f, Vector(1.0f, 1.0f, 1.0f));
+        mesh->transform().setTranslation(1.0f, Vector(-0.2f, -0.8f, 0.0f));
+        mesh->transform().rotate(1.0f, Quaternion(Vector(0.0f, 0.0f, 1.0f), M_PI / 3.0f));
+        set.addShape(mesh);
+
+        RectangleLight* light = st.add(new RectangleLight(Point(), Vector(2.0f, 0.0f, 0.0f), Vector(0.0f, 0.0f, 2.0f),
+                                                          Color(1.0f, 0.9f, 0.8f), 8.0f));
+        light->transform().setTranslation(0.0f, Vector(-1.0f, 3.0f, -1.0f));
+        light->transform().rotate(0.0f, Quaternion(Vector(1.0f, 0.0f, 0.0f), M_PI / 7.0f));
+        set.addShape(light);
+        return true;
+    }
+    Material* blue = st.keep(new DiffuseMaterial(Color(0.3f, 0.4f, 0.9f)));
+    Material* mirror = st.keep(new ReflectionMaterial(Color(0.9f, 0.9f, 0.9f)));
+    Sphere* egg = st.add(new Sphere(Point(), 1.0f, blue));
+    egg->transform().setScaling(0.0f, Vector(2.0f, 1.0f, 0.5f));
+    egg->transform().setTranslation(0.0f, Vector(-1.0f, -0.5f, 0.0f));
+    egg->transform().rotate(0.0f, Quaternion(Vector(0.0f, 1.0f, 0.0f), M_PI / 5.0f));
+    egg->transform().setScaling(1.0f, Vector(1.0f, 1.5f, 1.0f));
+    egg->transform().rotate(1.0f, Quaternion(Vector(0.0f, 0.0f, 1.0f), M_PI / 4.0f));
+    set.addShape(egg);
+    Sphere* ball = st.add(new Sphere(Point(2.0f, -1.0f, 1.0f), 1.0f, mirror));
+    set.addShape(ball);
+    Sphere* disc = st.add(new Sphere(Point(), 1.0f, grey));            // three finite shapes: a (small) BVH
+    disc->transform().setScaling(0.0f, Vector(1.0f, 0.2f, 1.0f));
+    disc->transform().setTranslation(0.0f, Vector(0.5f, 0.5f, -2.0f));
+    set.addShape(disc);
+    return true;
+}
+
 } // namespace rayito_recipes
 
 #endif // RAYITO_B200_SCENE_RECIPES_H

@@ -86,3 +86,23 @@ def scene6_host(capi, obj_path):
 @pytest.fixture(scope="session")
 def scene6_ref(ref6, obj_path):
     return ref6.RefScene(6, obj_path, stage=6)
+
+
+@pytest.fixture(scope="session")
+def scene7_host(capi):
+    return capi.HostScene(capi.RECIPE_EDGE_LINEAR_LIST)
+
+
+@pytest.fixture(scope="session")
+def scene7_ref(ref):
+    return ref.RefScene(7)
+
+
+@pytest.fixture(scope="session")
+def scene8_host(capi):
+    return capi.HostScene(capi.RECIPE_EDGE_NO_LIGHTS)
+
+
+@pytest.fixture(scope="session")
+def scene8_ref(ref):
+    return ref.RefScene(8)

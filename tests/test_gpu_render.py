@@ -213,6 +213,27 @@ def test_stage6_image_matches_reference_within_noise(capi, scene6_host, scene6_r
         assert stats.closest_rays >= W * H * ps * ps
 
 
+@pytest.mark.parametrize("recipe,ls,depth", [(7, 2, 3), (8, 1, 4), (9, 1, 2)])
+def test_edge_scene_images_match_reference(capi, ref, recipe, ls, depth):
+    """Edge-case scenes (host/scene_recipes.h buildEdgeScene): linear shape list with n-gon
+    faces, scale keys and a tilted light; no lights (black image, mirror bounces still traced);
+    the empty set."""
+    host = capi.HostScene(recipe)
+    refscene = ref.RefScene(recipe)
+    dev = capi.DeviceScene(host.desc)
+    spec = host.default_camera_spec()
+    cam = capi.camera_from_spec(spec)
+    W, H, ps = 72, 40, 3
+    theirs, rstats = refscene.render(spec, W, H, ps, ls=ls, depth=depth)
+    mine, stats = dev.render(cam, W, H, ps, ls=ls, depth=depth)
+    dev.close()
+    same, rel = _compare_images(mine, theirs, "edge scene %d" % recipe)
+    assert same == 1.0 and rel == 0.0
+    assert stats.closest_rays == rstats.closest_calls and stats.any_rays == rstats.any_calls
+    if recipe != 7:
+        assert not mine.any()
+
+
 def test_tile_sharding_is_exact(dev1, scene1_host, capi):
     """Any partition of the image into rank-owned tiles reproduces the single-GPU
     image bit for bit (the sample stream is position-addressable), and small

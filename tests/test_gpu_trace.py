@@ -144,6 +144,37 @@ def test_stage6_recorded_path_rays(capi, scene6_host, scene6_ref):
     dev.close()
 
 
+def test_edge_scenes(capi, ref, scene7_host, scene7_ref, scene8_host, scene8_ref):
+    """Linear shape list instead of a top-level BVH, n-gon faces with per-vertex normals, scale
+    keys (the general transform path: divide by the scale, rotate), a tilted rectangle light, a
+    three-shape BVH, no lights -- and the empty set, where every ray misses."""
+    dev = capi.DeviceScene(scene7_host.desc)
+    assert scene7_host.desc.contents.num_top_nodes == 0
+    rays = random_rays(1 << 17, seed=71, center=(0, -0.3, 0.2), radius=7.0, target_radius=2.2, shadow_fraction=0.3)
+    hits = _compare_closest(dev, scene7_ref, rays, "edge scene (linear list)")
+    assert (hits["face"] >= 0).mean() > 0.05 and set(np.unique(hits["tri"])) >= {0, 1, 2, 3}
+    _compare_any(dev, scene7_ref, rays, "edge scene (linear list) any")
+    _compare_closest(dev, scene7_ref, axis_parallel_rays(1 << 15, seed=72), "edge scene axis-parallel")
+    dev.close()
+
+    dev = capi.DeviceScene(scene8_host.desc)
+    assert scene8_host.desc.contents.num_top_nodes == 5
+    rays = random_rays(1 << 17, seed=81, center=(0.3, -0.5, 0), radius=9.0, target_radius=3.0, shadow_fraction=0.3)
+    hits = _compare_closest(dev, scene8_ref, rays, "edge scene (scaled spheres)")
+    assert set(np.unique(hits["shape"])) >= {-1, 0, 1, 2, 3}
+    _compare_any(dev, scene8_ref, rays, "edge scene (scaled spheres) any")
+    _compare_closest(dev, scene8_ref, axis_parallel_rays(1 << 15, seed=82), "edge scene (scaled spheres) axis-parallel")
+    dev.close()
+
+    empty_host = capi.HostScene(capi.RECIPE_EDGE_EMPTY)
+    dev = capi.DeviceScene(empty_host.desc)
+    rays = random_rays(4096, seed=91)
+    hits = _compare_closest(dev, ref.RefScene(9), rays, "empty set")
+    assert (hits["shape"] == -1).all()
+    assert not dev.trace_any(rays).any()
+    dev.close()
+
+
 def test_empty_and_tiny_batches(dev1, capi):
     empty = np.zeros(0, capi.RAY_DTYPE)
     assert len(dev1.trace_closest(empty)) == 0
