@@ -345,8 +345,10 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
     stream = torch.cuda.current_stream(dev)
 
+    extra_flags = int(os.environ.get("RT_BENCH_FLAGS", "0"))      # A/B switches (RT_RENDER_* bits), not for reported runs
+
     def params(flags=0):
-        return capi.RtRenderParams(W, H, ps, ls, depth, args.tile, rank, world, args.batch, flags)
+        return capi.RtRenderParams(W, H, ps, ls, depth, args.tile, rank, world, args.batch, flags | extra_flags)
 
     def step(flags=0):
         st = dscene.render_device(cam, params(flags), image.data_ptr(), stream.cuda_stream)

@@ -206,7 +206,8 @@ enum
 {
     RT_RENDER_COUNT_WORK = 1u,  /* also count node pops / triangle tests (slower) */
     RT_RENDER_TIME_TRACE = 2u,  /* CUDA-event pairs around every traversal stage -> trace_ms */
-    RT_RENDER_UNIFIED_TRAVERSAL = 4u /* one kernel walks both BVH levels (default: split top-level / mesh passes) */
+    RT_RENDER_UNIFIED_TRAVERSAL = 4u, /* one kernel walks both BVH levels (default: split top-level / mesh passes) */
+    RT_RENDER_DYNAMIC_TOP = 8u        /* split mode: per-lane top-level pass instead of the tabulated walk (A/B testing) */
 };
 
 typedef struct RtRenderStats

@@ -42,6 +42,7 @@ class RtRenderParams(C.Structure):
 RT_RENDER_COUNT_WORK = 1
 RT_RENDER_TIME_TRACE = 2
 RT_RENDER_UNIFIED_TRAVERSAL = 4
+RT_RENDER_DYNAMIC_TOP = 8
 
 
 class RtRenderStats(C.Structure):
@@ -257,10 +258,11 @@ class DeviceScene:
         return hits
 
     def render(self, camera, width, height, ps, ls=1, depth=3, rank=0, world=1, tile_size=0,
-               max_batch_samples=0, count_work=False, time_trace=False, unified=False, out=None):
+               max_batch_samples=0, count_work=False, time_trace=False, unified=False, out=None, dynamic_top=False):
         params = RtRenderParams(width, height, ps, ls, depth, tile_size, rank, world, max_batch_samples,
                                 (RT_RENDER_COUNT_WORK if count_work else 0) | (RT_RENDER_TIME_TRACE if time_trace else 0)
-                                | (RT_RENDER_UNIFIED_TRAVERSAL if unified else 0))
+                                | (RT_RENDER_UNIFIED_TRAVERSAL if unified else 0)
+                                | (RT_RENDER_DYNAMIC_TOP if dynamic_top else 0))
         if out is None:
             out = np.zeros((height, width, 3), np.float32)
         stats = RtRenderStats()

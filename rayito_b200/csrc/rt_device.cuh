@@ -23,6 +23,7 @@
 
 #define RT_NODE_LEAF 0x4u        /* RAccel.h:124 */
 #define RT_NODE_AXIS 0x3u        /* RAccel.h:123 */
+#define RT_TOKEN_SHAPE 0x80000000u   /* stack entry that names a shape directly (linear-list mode) */
 
 struct V3
 {
@@ -122,6 +123,22 @@ struct DMesh
 // global normal indices.
 //   v0.w = face index (mesh-local), v1.w = triangle index inside the face,
 //   v2.w = 1 if the face has vertex normals
+// One step of the top-level BVH's depth-first walk for one direction octant (rt_split.cuh,
+// trace_top_static).  The order in which Bvh::intersect pops nodes depends only on the signs
+// of the ray direction (RAccel.h:481-486,540-556), so it is tabulated per octant at upload.
+#define RT_WALK_MAX_DEPTH 8      /* deepest node a tabulated walk may contain (= RT_SPLIT_TOPCAP) */
+#define RT_WALK_MAX_STEPS 96
+#define RT_WALK_TOKEN 0xffffffffu
+struct DTopStep
+{
+    uint32_t node;           // top-level node popped at this step (RT_WALK_TOKEN: linear shape list entry)
+    uint32_t word;           // interior: first child; leaf: shape index
+    uint32_t flags;          // bits 0-2 node flags (axis, leaf) | depth << 8 | pending entries << 16
+    uint32_t pending_depth;  // 4 bits per pending stack entry: its depth
+    uint32_t pending_node[RT_WALK_MAX_DEPTH];   // the explicit stack below this node, bottom first
+    uint32_t pad[4];
+};
+
 struct DScene
 {
     uint32_t set_xform;
@@ -149,6 +166,8 @@ struct DScene
     const float* face_area_cdf;
     const RtMaterial* materials;
     const uint32_t* lights;      // shape index per light
+    const DTopStep* top_walk;    // [8 octants][top_walk_steps], NULL if the top level is too deep to tabulate
+    uint32_t top_walk_steps;
 };
 
 // ---------------------------------------------------------------------------

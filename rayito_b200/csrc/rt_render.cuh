@@ -437,6 +437,22 @@ k_split_top(const __grid_constant__ DScene sc, const IO io, const SplitBufs sb, 
         flush_work_counters(wc, totals);
 }
 
+// Fresh top-level pass over the tabulated walk (scenes whose top level fits DTopStep tables)
+template <bool ANY, bool COUNT, class IO>
+__global__ void __launch_bounds__(RT_BLOCK)
+k_split_top_static(const __grid_constant__ DScene sc, const IO io, const SplitBufs sb, const SplitPass ps, uint64_t* totals, int count_slot)
+{
+    __shared__ float lane_t0[(RT_WALK_MAX_DEPTH + 1) * RT_BLOCK];
+    __shared__ float lane_t1[(RT_WALK_MAX_DEPTH + 1) * RT_BLOCK];
+    split_zero(ps);
+    if (count_slot >= 0 && blockIdx.x == 0 && threadIdx.x == 0)
+        atomicAdd(reinterpret_cast<unsigned long long*>(totals + count_slot), (unsigned long long)io.count());
+    WorkCount wc = { 0, 0, 0, 0 };
+    trace_top_static<ANY, COUNT>(sc, io, sb, ps, wc, lane_t0, lane_t1);
+    if (COUNT)
+        flush_work_counters(wc, totals);
+}
+
 template <int CAP, bool ANY, bool COUNT, class IO>
 __global__ void __launch_bounds__(RT_BLOCK, RT_MESH_MINBLOCKS)
 k_split_mesh(const __grid_constant__ DScene sc, const IO io, const SplitBufs sb, const SplitPass ps, uint64_t* totals)
@@ -1133,7 +1149,17 @@ static void rt_launch_split_stage(RtScene* s, const RenderCtx& c, const IO& io,
     p.out_queue = c.q_meshq[0];
     p.out_count = c.ctl + CTL_MESH_N + 0;
     p.zero[0] = p.zero[1] = p.zero[2] = p.zero[3] = NULL;
-    k_split_top<ANY, COUNT, true, IO><<<grid, RT_BLOCK, 0, st>>>(c.sc, io, c.split, p, c.totals, count_slot);
+    // The tabulated walk pays for shadow rays (incoherent origins: the per-lane pass ran at 12 lanes
+    // and twice the instructions); closest-hit rays visit so few leaves each that the per-lane pass
+    // executes fewer instructions than a warp-wide walk over the union of their leaves
+    // (profiles/README.md, v7).  RT_STATIC_TOP_CLOSEST=1 enables it for them as well.
+#ifndef RT_STATIC_TOP_CLOSEST
+#define RT_STATIC_TOP_CLOSEST 0
+#endif
+    if (c.sc.top_walk_steps > 0 && !s->dynamic_top && (ANY || RT_STATIC_TOP_CLOSEST))
+        k_split_top_static<ANY, COUNT, IO><<<grid, RT_BLOCK, 0, st>>>(c.sc, io, c.split, p, c.totals, count_slot);
+    else
+        k_split_top<ANY, COUNT, true, IO><<<grid, RT_BLOCK, 0, st>>>(c.sc, io, c.split, p, c.totals, count_slot);
     launches += 1;
     const bool deep = s->mesh_stack_need > 32;
     for (uint32_t k = 0; k < s->num_mesh_shapes; ++k)
@@ -1348,6 +1374,7 @@ inline int rt_render_impl(RtScene* s, const RtCamera* camera, const RtRenderPara
 
     const bool count = (prm->flags & RT_RENDER_COUNT_WORK) != 0;
     const bool timed = (prm->flags & RT_RENDER_TIME_TRACE) != 0;
+    s->dynamic_top = (prm->flags & RT_RENDER_DYNAMIC_TOP) != 0;
     const bool split = (prm->flags & RT_RENDER_UNIFIED_TRAVERSAL) == 0 && s->num_mesh_shapes >= 1 &&
                        s->num_mesh_shapes <= RT_SPLIT_MAX_MESHES && s->top_stack_need <= RT_SPLIT_TOPCAP &&
                        s->mesh_stack_need <= 64;

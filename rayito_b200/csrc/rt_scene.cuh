@@ -46,6 +46,7 @@ struct RtScene
     uint64_t* d_work;           // 4 counters
     uint32_t* d_cursor;         // queue cursor of the ray-batch entry points
     struct RenderBuffers* render;   // wavefront state (rt_render.cuh), lazily created
+    bool dynamic_top;           // this render: use the per-lane top-level pass even if a walk table exists
 };
 
 namespace rt_detail
@@ -316,6 +317,76 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
         top_nodes[i] = dn;
     }
 
+    // Depth-first pop order of the top level per direction octant (DTopStep)
+    std::vector<DTopStep> top_walk;
+    uint32_t top_walk_steps = 0;
+    {
+        bool ok = true;
+        uint32_t steps = desc->num_top_nodes ? desc->num_top_nodes : desc->num_finite;
+        if (steps == 0 || steps > RT_WALK_MAX_STEPS)
+            ok = false;
+        for (uint32_t oct = 0; oct < 8 && ok; ++oct)
+        {
+            std::vector<std::pair<uint32_t, uint32_t> > stack;       // (node, depth)
+            if (desc->num_top_nodes)
+                stack.push_back(std::make_pair(0u, 0u));
+            else
+                for (uint32_t k = desc->num_finite; k > 0; --k)        // linear list: shapes in order, all "depth 0"
+                    stack.push_back(std::make_pair(RT_TOKEN_SHAPE | (k - 1), 0u));
+            while (!stack.empty() && ok)
+            {
+                std::pair<uint32_t, uint32_t> cur = stack.back();
+                stack.pop_back();
+                DTopStep st;
+                std::memset(&st, 0, sizeof(st));
+                uint32_t nflags;
+                if (cur.first & RT_TOKEN_SHAPE)
+                {
+                    st.node = RT_WALK_TOKEN;
+                    st.word = cur.first & ~RT_TOKEN_SHAPE;
+                    nflags = RT_NODE_LEAF;
+                }
+                else
+                {
+                    const RtBvhNode& n = desc->top_nodes[cur.first];
+                    st.node = cur.first;
+                    st.word = n.first_child_or_prim;
+                    nflags = n.flags & (RT_NODE_LEAF | RT_NODE_AXIS);
+                }
+                if (cur.second > RT_WALK_MAX_DEPTH || stack.size() > RT_WALK_MAX_DEPTH)
+                {
+                    ok = false;
+                    break;
+                }
+                st.flags = nflags | (cur.second << 8) | ((uint32_t)stack.size() << 16);
+                for (size_t k = 0; k < stack.size(); ++k)
+                {
+                    st.pending_node[k] = stack[k].first;
+                    st.pending_depth |= stack[k].second << (4 * k);
+                }
+                top_walk.push_back(st);
+                if (!(nflags & RT_NODE_LEAF))
+                {
+                    if (cur.second + 1 > RT_WALK_MAX_DEPTH)
+                    {
+                        ok = false;
+                        break;
+                    }
+                    bool neg = (oct >> (nflags & RT_NODE_AXIS)) & 1u;
+                    uint32_t near_id = neg ? st.word : st.word + 1, far_id = neg ? st.word + 1 : st.word;
+                    stack.push_back(std::make_pair(far_id, cur.second + 1));
+                    stack.push_back(std::make_pair(near_id, cur.second + 1));
+                }
+            }
+            if (ok && top_walk.size() != (size_t)(oct + 1) * steps)
+                ok = false;
+        }
+        if (ok)
+            top_walk_steps = steps;
+        else
+            top_walk.clear();
+    }
+
     // Analytic shapes with their per-call constants folded in
     std::vector<DPlane> planes(desc->num_planes);
     for (uint32_t i = 0; i < desc->num_planes; ++i)
@@ -390,6 +461,7 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
     size_t o_cdf = ab.put(desc->face_area_cdf, (size_t)desc->num_cdf * 4);
     size_t o_mats = ab.put(desc->materials, (size_t)desc->num_materials * sizeof(RtMaterial));
     size_t o_lights = ab.put(desc->lights, (size_t)desc->num_lights * 4);
+    size_t o_walk = ab.put(top_walk.data(), top_walk.size() * sizeof(DTopStep));
 
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -419,6 +491,7 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
     sc->d_work = NULL;
     sc->d_cursor = NULL;
     sc->render = NULL;
+    sc->dynamic_top = false;
 
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
@@ -471,6 +544,8 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
     d.face_area_cdf = reinterpret_cast<const float*>(base + o_cdf);
     d.materials = reinterpret_cast<const RtMaterial*>(base + o_mats);
     d.lights = reinterpret_cast<const uint32_t*>(base + o_lights);
+    d.top_walk = top_walk_steps ? reinterpret_cast<const DTopStep*>(base + o_walk) : NULL;
+    d.top_walk_steps = top_walk_steps;
 
     *out_scene = sc;
     return RT_OK;

@@ -382,6 +382,246 @@ __device__ __forceinline__ void trace_top(const DScene& sc, const IO& io, const 
 }
 
 // ---------------------------------------------------------------------------
+// Fresh top-level pass, tabulated walk.
+//
+// The top level is a handful of shapes (8 in the Stage 7 scene: a 15-node BVH), yet the
+// dynamic pass above spends more time in it than the mesh passes spend in a 49 151-node face
+// BVH: every lane is at a different node or shape, so a warp executes the union of all
+// their code paths with 12-20 lanes active.  The ORDER in which Bvh::intersect pops nodes
+// depends only on the direction signs, so here all lanes of a warp that share an octant step
+// through the same tabulated pop sequence (DTopStep) together; what differs per lane is only
+// whether a pop happens at all (its parent passed its slab test) and with which inherited
+// range, kept per lane and per depth.  A node popped by no lane is skipped by the whole warp.
+// Every lane performs exactly the pops, checks and shape tests of the reference, in the same
+// order, on the same values; rays entering a mesh are suspended with the explicit stack the
+// dynamic pass would hold at that point, so the mesh and resume passes are unchanged.
+// ---------------------------------------------------------------------------
+template <bool ANY, bool COUNT, class IO>
+__device__ __forceinline__ void trace_top_static(const DScene& sc, const IO& io, const SplitBufs& sb, const SplitPass& ps,
+                                                 WorkCount& wc, float* lane_t0, float* lane_t1)
+{
+    // lane_t0 / lane_t1: [RT_WALK_MAX_DEPTH + 1][blockDim.x] shared floats
+    const uint32_t lane = threadIdx.x & 31, tid = threadIdx.x, stride = blockDim.x;
+    const uint32_t n = io.count();
+    const uint32_t nsteps = sc.top_walk_steps;
+
+    for (;;)
+    {
+        uint32_t base = 0;
+        if (lane == 0)
+            base = atomicAdd(ps.cursor, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n)
+            break;
+        const uint32_t j = base + lane;
+        const bool live = j < n;
+
+        uint32_t tag = 0;
+        float time = 0.0f, tmax = 0.0f;
+        LocalRay r0;
+        r0.o = r0.d = r0.inv = mk(0.0f, 0.0f, 0.0f);
+        r0.neg = 0;
+        WaveResult res;
+        res.t = 0.0f; res.shape = -1; res.tri_rec = -1; res.any_hit = false;
+        bool open = false;          // still walking
+        bool suspended = false;
+        if (live)
+        {
+            V3 o, d;
+            io.load(j, o, d, tmax, time, tag);
+            res.t = tmax;
+            TRS set_trs = xform_eval(sc, sc.set_xform, time);
+            if (COUNT) wc.xform_evals++;
+            r0.o = to_local_point(set_trs, o);
+            r0.d = to_local_vector(set_trs, d);
+            local_ray_finish(r0);
+            for (uint32_t k = 0; k < sc.num_infinite; ++k)
+            {
+                uint32_t sid = sc.num_finite + k;
+                DShape sh = load_shape(sc, sid);
+                TRS trs = shape_xform(sc, sh, time);
+                V3 lo = to_local_point(trs, r0.o);
+                V3 ld = to_local_vector(trs, r0.d);
+                if (COUNT) { wc.xform_evals++; wc.shape_tests++; }
+                float t;
+                if (plane_test(sc.planes[sh.geom], lo, ld, res.t, t))
+                {
+                    if (ANY) { res.any_hit = true; break; }
+                    res.t = t;
+                    res.shape = (int32_t)sid;
+                }
+            }
+            open = !(ANY && res.any_hit);
+        }
+        lane_t0[tid] = RT_RAY_TMIN;         // depth 0: the root's range (RAccel.h:402-404)
+        lane_t1[tid] = res.t;
+        uint32_t alive = 1u;                // bit d: the node at depth d on the current path was pushed
+
+        uint32_t todo = __ballot_sync(0xffffffffu, open);
+        while (todo)
+        {
+            const uint32_t oct = __shfl_sync(0xffffffffu, r0.neg, __ffs(todo) - 1);
+            const uint32_t grp = __ballot_sync(0xffffffffu, open && r0.neg == oct);
+            todo &= ~grp;
+            const bool in_grp = (grp >> lane) & 1u;
+            const DTopStep* steps = sc.top_walk + (size_t)oct * nsteps;
+            #pragma unroll 1
+            for (uint32_t s = 0; s < nsteps; ++s)
+            {
+                const uint4 hd = __ldg(reinterpret_cast<const uint4*>(steps + s));
+                const uint32_t node = hd.x, word = hd.y, flags = hd.z;
+                const uint32_t depth = (flags >> 8) & 0xffu;
+                const bool here = in_grp && open && ((alive >> depth) & 1u);
+                const uint32_t m_here = __ballot_sync(0xffffffffu, here);
+                if (!(flags & RT_NODE_LEAF))
+                {
+                    bool pass = false;
+                    if (m_here)
+                    {
+                        DNode nd = load_node(sc.top_nodes, node);
+                        if (here)
+                        {
+                            if (COUNT) wc.node_pops++;
+                            float t0 = lane_t0[depth * stride + tid];
+                            float t1 = lane_t1[depth * stride + tid];
+                            bool go = true;
+                            if (!ANY)
+                            {
+                                if (t0 >= res.t)
+                                    go = false;
+                                else if (t1 > res.t)
+                                    t1 = res.t;
+                            }
+                            if (go && box_test(nd.q0, nd.q1, r0.o, r0.inv, t0, t1))
+                            {
+                                pass = true;
+                                lane_t0[(depth + 1) * stride + tid] = t0;
+                                lane_t1[(depth + 1) * stride + tid] = t1;
+                            }
+                        }
+                    }
+                    if (in_grp)
+                        alive = pass ? (alive | (2u << depth)) : (alive & ~(2u << depth));
+                    continue;
+                }
+                if (m_here == 0)
+                    continue;
+                if (COUNT && here && node != RT_WALK_TOKEN) wc.node_pops++;
+
+                // ---- a shape leaf, popped by the lanes in m_here (same code as trace_top's service)
+                const uint32_t shape_id = word;
+                DShape sh = load_shape(sc, shape_id);
+                bool suspend = false;
+                if (sh.type == RT_SHAPE_MESH)
+                {
+                    DMesh m = sc.meshes[sh.geom];
+                    if (here && m.num_nodes > 0)
+                    {
+                        TRS trs = shape_xform(sc, sh, time);
+                        if (COUNT) wc.xform_evals++;
+                        LocalRay rm;
+                        rm.o = to_local_point(trs, r0.o);
+                        rm.d = to_local_vector(trs, r0.d);
+                        local_ray_finish(rm);
+                        DNode root = load_node(sc.mesh_nodes + m.first_node, 0);
+                        if (COUNT) wc.node_pops++;
+                        bool enter = true;
+                        if (!(__float_as_uint(root.q1.w) & RT_NODE_LEAF))
+                        {
+                            float t0 = RT_RAY_TMIN, t1 = ANY ? tmax : res.t;
+                            if (!ANY && t0 >= res.t)
+                                enter = false;
+                            else
+                                enter = box_test(root.q0, root.q1, rm.o, rm.inv, t0, t1);
+                        }
+                        if (enter)
+                        {
+                            suspend = true;
+                            sb.mesh_o[tag] = make_float4(rm.o.x, rm.o.y, rm.o.z, 0.0f);
+                            sb.mesh_d[tag] = make_float4(rm.d.x, rm.d.y, rm.d.z, 0.0f);
+                            // the explicit stack of the dynamic pass at this point: pending far
+                            // children whose parents passed, with the ranges those parents pushed
+                            const uint4 p0 = __ldg(reinterpret_cast<const uint4*>(steps + s) + 1);
+                            const uint4 p1 = __ldg(reinterpret_cast<const uint4*>(steps + s) + 2);
+                            const uint32_t pn[8] = { p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w };
+                            const uint32_t npend = (flags >> 16) & 0xffu;
+                            float4* st = sb.stack + (size_t)tag * RT_SPLIT_TOPCAP;
+                            uint32_t sp = 0;
+                            #pragma unroll
+                            for (uint32_t k = 0; k < RT_WALK_MAX_DEPTH; ++k)
+                            {
+                                if (k < npend)
+                                {
+                                    uint32_t dk = (hd.w >> (4 * k)) & 0xfu;
+                                    if ((alive >> dk) & 1u)
+                                    {
+                                        st[sp] = make_float4(__uint_as_float(pn[k]), lane_t0[dk * stride + tid],
+                                                             lane_t1[dk * stride + tid], 0.0f);
+                                        ++sp;
+                                    }
+                                }
+                            }
+                            sb.ray_o[tag] = make_float4(r0.o.x, r0.o.y, r0.o.z, time);
+                            sb.ray_d[tag] = make_float4(r0.d.x, r0.d.y, r0.d.z, tmax);
+                            sb.hit[tag] = make_float4(res.t, __int_as_float(res.shape), __int_as_float(res.tri_rec),
+                                                      __uint_as_float(shape_id | (sp << 24)));
+                            open = false;
+                            suspended = true;
+                        }
+                    }
+                }
+                else if (here)
+                {
+                    TRS trs = shape_xform(sc, sh, time);
+                    if (COUNT) wc.xform_evals++;
+                    V3 lo = to_local_point(trs, r0.o);
+                    V3 ld = to_local_vector(trs, r0.d);
+                    if (sh.type == RT_SHAPE_SPHERE)
+                    {
+                        DSphere sp = sc.spheres[sh.geom];
+                        if (COUNT) wc.shape_tests++;
+                        V3 c = lo - mk(sp.px, sp.py, sp.pz);
+                        if (ANY)
+                        {
+                            if (sphere_any(c, ld, sp.radius, tmax)) { res.any_hit = true; open = false; }
+                        }
+                        else
+                        {
+                            float t;
+                            if (sphere_closest(c, ld, sp.radius, res.t, t))
+                            {
+                                res.t = t;
+                                res.shape = (int32_t)shape_id;
+                                res.tri_rec = -1;
+                            }
+                        }
+                    }
+                    else if (sh.type == RT_SHAPE_RECT)
+                    {
+                        if (COUNT) wc.shape_tests++;
+                        float t;
+                        if (rect_test(sc.rects[sh.geom], lo, ld, ANY ? tmax : res.t, t))
+                        {
+                            if (ANY) { res.any_hit = true; open = false; }
+                            else
+                            {
+                                res.t = t;
+                                res.shape = (int32_t)shape_id;
+                                res.tri_rec = -1;
+                            }
+                        }
+                    }
+                }
+                if (sh.type == RT_SHAPE_MESH)
+                    warp_queue_push(ps.out_queue, ps.out_count, suspend, tag);
+            }
+        }
+        if (live && !suspended)
+            io.store(tag, res);
+    }
+}
+
+// ---------------------------------------------------------------------------
 // Mesh pass: Mesh::intersect / doesIntersect for suspended rays
 // ---------------------------------------------------------------------------
 template <int CAP, bool ANY, bool COUNT, class IO>

@@ -21,7 +21,6 @@
 
 #include "rt_device.cuh"
 
-#define RT_TOKEN_SHAPE 0x80000000u   /* stack entry that names a shape directly (linear-list mode) */
 
 // Work counters for the algorithmic-bytes figure
 struct WorkCount

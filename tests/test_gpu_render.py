@@ -254,7 +254,7 @@ def test_tile_sharding_is_exact(dev1, scene1_host, capi):
     assert np.array_equal(bits(small), bits(whole))
 
 
-@pytest.mark.parametrize("which", ["scene1", "scene2"])
+@pytest.mark.parametrize("which", ["scene1", "scene2", "scene7", "scene8"])
 def test_split_and_unified_traversal_agree(which, request, capi):
     """The split top-level / mesh passes (default) and the single unified kernel must
     trace the very same rays through the very same nodes: identical images, ray
@@ -264,12 +264,17 @@ def test_split_and_unified_traversal_agree(which, request, capi):
     cam = capi.camera_from_spec(host.default_camera_spec())
     W, H, ps = 96, 54, 3
     img_s, st_s = dev.render(cam, W, H, ps, ls=1, depth=3, count_work=True)
+    img_d, st_d = dev.render(cam, W, H, ps, ls=1, depth=3, count_work=True, dynamic_top=True)
     img_u, st_u = dev.render(cam, W, H, ps, ls=1, depth=3, count_work=True, unified=True)
     dev.close()
-    assert np.array_equal(bits(img_s), bits(img_u))
+    assert np.array_equal(bits(img_s), bits(img_u)) and np.array_equal(bits(img_d), bits(img_u))
+    # the tabulated top-level walk (default), the per-lane top-level pass and the unified kernel
+    # pop the same nodes and test the same shapes
     for field in ("closest_rays", "any_rays", "node_pops", "tri_tests", "shape_tests", "xform_evals"):
         assert getattr(st_s, field) == getattr(st_u, field), field
-    assert st_s.kernel_launches > st_u.kernel_launches
+        assert getattr(st_d, field) == getattr(st_u, field), field
+    if which != "scene8":        # no mesh in that scene: split mode does not apply
+        assert st_s.kernel_launches > st_u.kernel_launches
 
 
 def test_work_counters(dev1, scene1_host, capi):
