@@ -1149,12 +1149,13 @@ static void rt_launch_split_stage(RtScene* s, const RenderCtx& c, const IO& io,
     p.out_queue = c.q_meshq[0];
     p.out_count = c.ctl + CTL_MESH_N + 0;
     p.zero[0] = p.zero[1] = p.zero[2] = p.zero[3] = NULL;
-    // The tabulated walk pays for shadow rays (incoherent origins: the per-lane pass ran at 12 lanes
-    // and twice the instructions); closest-hit rays visit so few leaves each that the per-lane pass
-    // executes fewer instructions than a warp-wide walk over the union of their leaves
-    // (profiles/README.md, v7).  RT_STATIC_TOP_CLOSEST=1 enables it for them as well.
+    // The tabulated walk pays most for shadow rays (incoherent origins: the per-lane pass ran at 12
+    // lanes and twice the instructions, 2.4 -> 1.7 ms per launch).  Closest-hit rays visit so few
+    // leaves each that a warp-wide walk over the union of their leaves executes about as many
+    // instructions as the per-lane pass; same-session A/B at 1920x1080: per-lane 3282, tabulated for
+    // shadow rays only 3360, tabulated for all 3389 Mrays/s (profiles/README.md, v7).
 #ifndef RT_STATIC_TOP_CLOSEST
-#define RT_STATIC_TOP_CLOSEST 0
+#define RT_STATIC_TOP_CLOSEST 1
 #endif
     if (c.sc.top_walk_steps > 0 && !s->dynamic_top && (ANY || RT_STATIC_TOP_CLOSEST))
         k_split_top_static<ANY, COUNT, IO><<<grid, RT_BLOCK, 0, st>>>(c.sc, io, c.split, p, c.totals, count_slot);
