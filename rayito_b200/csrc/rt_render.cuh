@@ -438,8 +438,11 @@ k_split_top(const __grid_constant__ DScene sc, const IO io, const SplitBufs sb, 
 }
 
 // Fresh top-level pass over the tabulated walk (scenes whose top level fits DTopStep tables)
+#ifndef RT_STATIC_MINBLOCKS
+#define RT_STATIC_MINBLOCKS 8      /* 64 registers: 3208 -> 3523 Mrays/s (frame) in same-session A/B; 9, 10, 12 blocks are slower again */
+#endif
 template <bool ANY, bool COUNT, class IO>
-__global__ void __launch_bounds__(RT_BLOCK)
+__global__ void __launch_bounds__(RT_BLOCK, RT_STATIC_MINBLOCKS)
 k_split_top_static(const __grid_constant__ DScene sc, const IO io, const SplitBufs sb, const SplitPass ps, uint64_t* totals, int count_slot)
 {
     __shared__ float lane_t0[(RT_WALK_MAX_DEPTH + 1) * RT_BLOCK];
