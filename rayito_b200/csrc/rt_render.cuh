@@ -1245,9 +1245,11 @@ static int rt_launch_batch(RtScene* s, const RenderCtx& c, cudaStream_t st, uint
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_split_top<false, COUNT, true, PathIO>, RT_BLOCK, 0);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_split_mesh<64, false, COUNT, PathIO>, RT_BLOCK, 0);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d, k_split_mesh<32, false, COUNT, PathIO>, RT_BLOCK, 0);
-        // one grid for both kinds of pass (separate sizes measured no better)
+#ifndef RT_SEPARATE_MESH_GRID
+#define RT_SEPARATE_MESH_GRID 1      /* +0.5 % in same-session A/B */
+#endif
         tg_split = (unsigned)(dev_sms * std::max(std::min(a, std::min(b, d)), 1));
-        tg_mesh = tg_split;
+        tg_mesh = RT_SEPARATE_MESH_GRID ? (unsigned)(dev_sms * std::max(s->mesh_stack_need > 32 ? b : d, 1)) : tg_split;
     }
 
     k_pixel_setup<<<pix_blocks, RT_BLOCK, 0, st>>>(c);

@@ -624,6 +624,9 @@ __device__ __forceinline__ void trace_top_static(const DScene& sc, const IO& io,
 // ---------------------------------------------------------------------------
 // Mesh pass: Mesh::intersect / doesIntersect for suspended rays
 // ---------------------------------------------------------------------------
+#ifndef RT_MESH_PREFETCH
+#define RT_MESH_PREFETCH 0
+#endif
 template <int CAP, bool ANY, bool COUNT, class IO>
 __device__ __forceinline__ void trace_mesh(const DScene& sc, const IO& io, const SplitBufs& sb, const SplitPass& ps, WorkCount& wc)
 {
@@ -648,6 +651,9 @@ __device__ __forceinline__ void trace_mesh(const DScene& sc, const IO& io, const
     uint32_t mesh_shape = 0, meta = 0;
     const DNode* mesh_nodes = sc.mesh_nodes;
     int sp = 0;
+    bool have_cur = false;       // cur_*: the next node to pop, when it did not go through the stack
+    uint32_t cur_node = 0;
+    float cur_t0 = 0.0f, cur_t1 = 0.0f;
     bool parked = false;
     uint32_t park_word = 0, park_count = 0;
 
@@ -668,6 +674,7 @@ __device__ __forceinline__ void trace_mesh(const DScene& sc, const IO& io, const
             {
                 active = true;
                 parked = false;
+                have_cur = false;
                 tag = ps.in_queue[j];
                 float4 a = sb.ray_o[tag], b = sb.ray_d[tag], h = sb.hit[tag];
                 tmax = b.w;
@@ -702,8 +709,9 @@ __device__ __forceinline__ void trace_mesh(const DScene& sc, const IO& io, const
                     box_test(root.q0, root.q1, r1.o, r1.inv, t0, t1);
                     bool neg = (r1.neg >> (rflags & RT_NODE_AXIS)) & 1u;
                     stk_node[0] = neg ? rword + 1 : rword;  stk_t0[0] = t0; stk_t1[0] = t1;
-                    stk_node[1] = neg ? rword : rword + 1;  stk_t0[1] = t0; stk_t1[1] = t1;
-                    sp = 2;
+                    sp = 1;
+                    cur_node = neg ? rword : rword + 1; cur_t0 = t0; cur_t1 = t1;
+                    have_cur = true;
                 }
                 (void)a; (void)b;
             }
@@ -716,10 +724,23 @@ __device__ __forceinline__ void trace_mesh(const DScene& sc, const IO& io, const
         }
 
         #pragma unroll 1
-        for (int it = 0; it < RT_MESH_ADVANCE_STEPS && active && !parked && sp > 0; ++it)
+        for (int it = 0; it < RT_MESH_ADVANCE_STEPS && active && !parked && (have_cur || sp > 0); ++it)
         {
-            --sp;
-            DNode nd = load_node(mesh_nodes, stk_node[sp]);
+            // the near child of the node just entered is popped next: it stays in registers
+            // instead of going through the (local-memory) stack
+            uint32_t node_id;
+            float t0, t1;
+            if (have_cur)
+            {
+                node_id = cur_node; t0 = cur_t0; t1 = cur_t1;
+                have_cur = false;
+            }
+            else
+            {
+                --sp;
+                node_id = stk_node[sp]; t0 = stk_t0[sp]; t1 = stk_t1[sp];
+            }
+            DNode nd = load_node(mesh_nodes, node_id);
             if (COUNT) wc.node_pops++;
             uint32_t flags = __float_as_uint(nd.q1.w);
             uint32_t word = __float_as_uint(nd.q1.z);
@@ -730,8 +751,6 @@ __device__ __forceinline__ void trace_mesh(const DScene& sc, const IO& io, const
                 park_count = flags >> 3;
                 break;
             }
-            float t0 = stk_t0[sp];
-            float t1 = stk_t1[sp];
             if (!ANY)
             {
                 if (t0 >= best)
@@ -747,12 +766,12 @@ __device__ __forceinline__ void trace_mesh(const DScene& sc, const IO& io, const
             uint32_t far_id = neg ? word + 1 : word;
             stk_node[sp] = far_id;  stk_t0[sp] = t0; stk_t1[sp] = t1;
             ++sp;
-            stk_node[sp] = near_id; stk_t0[sp] = t0; stk_t1[sp] = t1;
-            ++sp;
+            cur_node = near_id; cur_t0 = t0; cur_t1 = t1;
+            have_cur = true;
         }
 
         const uint32_t m_tri = __ballot_sync(0xffffffffu, parked);
-        const uint32_t m_adv = __ballot_sync(0xffffffffu, active && !parked && sp > 0);
+        const uint32_t m_adv = __ballot_sync(0xffffffffu, active && !parked && (have_cur || sp > 0));
         const bool do_tri = m_tri != 0 && (m_adv == 0 || exhausted || __popc(m_tri) >= RT_MESH_SERVICE_MIN);
 
         if (do_tri && parked)
@@ -766,7 +785,7 @@ __device__ __forceinline__ void trace_mesh(const DScene& sc, const IO& io, const
                 float t, beta, gamma;
                 if (tri_closest(r1.o, r1.d, p0, p1, p2, ANY ? tmax : best, t, beta, gamma))
                 {
-                    if (ANY) { any_hit = true; sp = 0; break; }
+                    if (ANY) { any_hit = true; sp = 0; have_cur = false; break; }
                     best = t;
                     best_rec = (int32_t)(park_word + k);
                     if (sc.stage6) break;        // S6 RMesh.h:204-209
@@ -776,7 +795,7 @@ __device__ __forceinline__ void trace_mesh(const DScene& sc, const IO& io, const
         }
 
         // retire: hand the slot back to a top-level resume pass (or finish a shadow ray)
-        const bool done = active && !parked && sp == 0;
+        const bool done = active && !parked && !have_cur && sp == 0;
         if (__ballot_sync(0xffffffffu, done))
         {
             bool resume = false;
