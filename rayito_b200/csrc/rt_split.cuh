@@ -627,6 +627,9 @@ __device__ __forceinline__ void trace_top_static(const DScene& sc, const IO& io,
 #ifndef RT_MESH_PREFETCH
 #define RT_MESH_PREFETCH 0
 #endif
+#ifndef RT_MESH_TOPCACHE
+#define RT_MESH_TOPCACHE 1     /* newest far entry cached in registers: +0.6 % C4, +2.6 % C5 */
+#endif
 template <int CAP, bool ANY, bool COUNT, class IO>
 __device__ __forceinline__ void trace_mesh(const DScene& sc, const IO& io, const SplitBufs& sb, const SplitPass& ps, WorkCount& wc)
 {
@@ -654,6 +657,9 @@ __device__ __forceinline__ void trace_mesh(const DScene& sc, const IO& io, const
     bool have_cur = false;       // cur_*: the next node to pop, when it did not go through the stack
     uint32_t cur_node = 0;
     float cur_t0 = 0.0f, cur_t1 = 0.0f;
+    bool top_valid = false;      // RT_MESH_TOPCACHE: the newest stack entry lives in top_* (slot sp - 1)
+    uint32_t top_node = 0;
+    float top_t0 = 0.0f, top_t1 = 0.0f;
     bool parked = false;
     uint32_t park_word = 0, park_count = 0;
 
@@ -675,6 +681,7 @@ __device__ __forceinline__ void trace_mesh(const DScene& sc, const IO& io, const
                 active = true;
                 parked = false;
                 have_cur = false;
+                top_valid = false;
                 tag = ps.in_queue[j];
                 float4 a = sb.ray_o[tag], b = sb.ray_d[tag], h = sb.hit[tag];
                 tmax = b.w;
@@ -708,7 +715,12 @@ __device__ __forceinline__ void trace_mesh(const DScene& sc, const IO& io, const
                     float t0 = RT_RAY_TMIN, t1 = ANY ? tmax : best;
                     box_test(root.q0, root.q1, r1.o, r1.inv, t0, t1);
                     bool neg = (r1.neg >> (rflags & RT_NODE_AXIS)) & 1u;
+#if RT_MESH_TOPCACHE
+                    top_node = neg ? rword + 1 : rword; top_t0 = t0; top_t1 = t1;
+                    top_valid = true;
+#else
                     stk_node[0] = neg ? rword + 1 : rword;  stk_t0[0] = t0; stk_t1[0] = t1;
+#endif
                     sp = 1;
                     cur_node = neg ? rword : rword + 1; cur_t0 = t0; cur_t1 = t1;
                     have_cur = true;
@@ -738,7 +750,17 @@ __device__ __forceinline__ void trace_mesh(const DScene& sc, const IO& io, const
             else
             {
                 --sp;
-                node_id = stk_node[sp]; t0 = stk_t0[sp]; t1 = stk_t1[sp];
+#if RT_MESH_TOPCACHE
+                if (top_valid)
+                {
+                    node_id = top_node; t0 = top_t0; t1 = top_t1;       // the newest entry never left the registers
+                    top_valid = false;
+                }
+                else
+#endif
+                {
+                    node_id = stk_node[sp]; t0 = stk_t0[sp]; t1 = stk_t1[sp];
+                }
             }
             DNode nd = load_node(mesh_nodes, node_id);
             if (COUNT) wc.node_pops++;
@@ -764,7 +786,16 @@ __device__ __forceinline__ void trace_mesh(const DScene& sc, const IO& io, const
             bool neg = (r1.neg >> axis) & 1u;
             uint32_t near_id = neg ? word : word + 1;
             uint32_t far_id = neg ? word + 1 : word;
+#if RT_MESH_TOPCACHE
+            if (top_valid)
+            {
+                stk_node[sp - 1] = top_node; stk_t0[sp - 1] = top_t0; stk_t1[sp - 1] = top_t1;
+            }
+            top_node = far_id; top_t0 = t0; top_t1 = t1;
+            top_valid = true;
+#else
             stk_node[sp] = far_id;  stk_t0[sp] = t0; stk_t1[sp] = t1;
+#endif
             ++sp;
             cur_node = near_id; cur_t0 = t0; cur_t1 = t1;
             have_cur = true;
@@ -785,7 +816,7 @@ __device__ __forceinline__ void trace_mesh(const DScene& sc, const IO& io, const
                 float t, beta, gamma;
                 if (tri_closest(r1.o, r1.d, p0, p1, p2, ANY ? tmax : best, t, beta, gamma))
                 {
-                    if (ANY) { any_hit = true; sp = 0; have_cur = false; break; }
+                    if (ANY) { any_hit = true; sp = 0; have_cur = false; top_valid = false; break; }
                     best = t;
                     best_rec = (int32_t)(park_word + k);
                     if (sc.stage6) break;        // S6 RMesh.h:204-209
