@@ -27,15 +27,17 @@
 
 #include "rt_scene.cuh"
 #include "rt_shade.cuh"
+// threads per block of every kernel of the renderer (the split passes size shared arrays with it)
+#ifndef RT_BLOCK
+#define RT_BLOCK 128
+#endif
+
 #include "rt_wave.cuh"
 #include "rt_split.cuh"
 
 #define RT_DEFAULT_TILE 32u
 #define RT_DEFAULT_BATCH (16u << 20)    /* samples per wavefront batch: ~11 GB of state, amortises kernel tails */
 #define RT_MAX_DEPTH 16u
-#ifndef RT_BLOCK
-#define RT_BLOCK 128
-#endif
 
 // Queue counters.  Ray queues are binned by direction octant (8 bins) so that the
 // lanes of a traversal warp share the near/far child order; the shade queue is binned

@@ -630,9 +630,35 @@ __device__ __forceinline__ void trace_top_static(const DScene& sc, const IO& io,
 #ifndef RT_MESH_TOPCACHE
 #define RT_MESH_TOPCACHE 1     /* newest far entry cached in registers: +0.6 % C4, +2.6 % C5 */
 #endif
+// The first RT_MESH_SMEM_STACK stack slots of every lane live in shared memory ([slot][thread],
+// conflict free); only deeper ones fall back to local memory, whose loads were the top stall of this
+// pass (18 % of samples, profiles/README.md v9).
+#ifndef RT_MESH_SMEM_STACK
+#define RT_MESH_SMEM_STACK 10     /* same-session A/B: +0.3 % on C4, +1.7 % on C5 (14: C4 -0.3 %, C5 +3.5 %) */
+#endif
+#if RT_MESH_SMEM_STACK > 0
+#define RT_MESH_STK_PUT(slot, n_, a_, b_)                                                        \
+    { if ((slot) < RT_MESH_SMEM_STACK) { sm_node[(slot) * RT_BLOCK + threadIdx.x] = (n_);        \
+          sm_t0[(slot) * RT_BLOCK + threadIdx.x] = (a_); sm_t1[(slot) * RT_BLOCK + threadIdx.x] = (b_); } \
+      else { stk_node[(slot) - RT_MESH_SMEM_STACK] = (n_); stk_t0[(slot) - RT_MESH_SMEM_STACK] = (a_);   \
+             stk_t1[(slot) - RT_MESH_SMEM_STACK] = (b_); } }
+#define RT_MESH_STK_GET(slot, n_, a_, b_)                                                        \
+    { if ((slot) < RT_MESH_SMEM_STACK) { (n_) = sm_node[(slot) * RT_BLOCK + threadIdx.x];        \
+          (a_) = sm_t0[(slot) * RT_BLOCK + threadIdx.x]; (b_) = sm_t1[(slot) * RT_BLOCK + threadIdx.x]; } \
+      else { (n_) = stk_node[(slot) - RT_MESH_SMEM_STACK]; (a_) = stk_t0[(slot) - RT_MESH_SMEM_STACK];   \
+             (b_) = stk_t1[(slot) - RT_MESH_SMEM_STACK]; } }
+#else
+#define RT_MESH_STK_PUT(slot, n_, a_, b_) { stk_node[slot] = (n_); stk_t0[slot] = (a_); stk_t1[slot] = (b_); }
+#define RT_MESH_STK_GET(slot, n_, a_, b_) { (n_) = stk_node[slot]; (a_) = stk_t0[slot]; (b_) = stk_t1[slot]; }
+#endif
 template <int CAP, bool ANY, bool COUNT, class IO>
 __device__ __forceinline__ void trace_mesh(const DScene& sc, const IO& io, const SplitBufs& sb, const SplitPass& ps, WorkCount& wc)
 {
+#if RT_MESH_SMEM_STACK > 0
+    __shared__ uint32_t sm_node[RT_MESH_SMEM_STACK * RT_BLOCK];
+    __shared__ float sm_t0[RT_MESH_SMEM_STACK * RT_BLOCK];
+    __shared__ float sm_t1[RT_MESH_SMEM_STACK * RT_BLOCK];
+#endif
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t lt_mask = (1u << lane) - 1;
     const uint32_t n = *ps.in_count;
@@ -719,7 +745,7 @@ __device__ __forceinline__ void trace_mesh(const DScene& sc, const IO& io, const
                     top_node = neg ? rword + 1 : rword; top_t0 = t0; top_t1 = t1;
                     top_valid = true;
 #else
-                    stk_node[0] = neg ? rword + 1 : rword;  stk_t0[0] = t0; stk_t1[0] = t1;
+                    RT_MESH_STK_PUT(0, neg ? rword + 1 : rword, t0, t1);
 #endif
                     sp = 1;
                     cur_node = neg ? rword : rword + 1; cur_t0 = t0; cur_t1 = t1;
@@ -759,7 +785,7 @@ __device__ __forceinline__ void trace_mesh(const DScene& sc, const IO& io, const
                 else
 #endif
                 {
-                    node_id = stk_node[sp]; t0 = stk_t0[sp]; t1 = stk_t1[sp];
+                    RT_MESH_STK_GET(sp, node_id, t0, t1);
                 }
             }
             DNode nd = load_node(mesh_nodes, node_id);
@@ -789,12 +815,12 @@ __device__ __forceinline__ void trace_mesh(const DScene& sc, const IO& io, const
 #if RT_MESH_TOPCACHE
             if (top_valid)
             {
-                stk_node[sp - 1] = top_node; stk_t0[sp - 1] = top_t0; stk_t1[sp - 1] = top_t1;
+                RT_MESH_STK_PUT(sp - 1, top_node, top_t0, top_t1);
             }
             top_node = far_id; top_t0 = t0; top_t1 = t1;
             top_valid = true;
 #else
-            stk_node[sp] = far_id;  stk_t0[sp] = t0; stk_t1[sp] = t1;
+            RT_MESH_STK_PUT(sp, far_id, t0, t1);
 #endif
             ++sp;
             cur_node = near_id; cur_t0 = t0; cur_t1 = t1;
