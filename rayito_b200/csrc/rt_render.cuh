@@ -335,11 +335,18 @@ struct PathIO
     uint32_t* shade_items;
     uint32_t* shade_counts;
     __device__ __forceinline__ uint32_t count() const { return queue.total(); }
+    __device__ __forceinline__ uint32_t tag_at(uint32_t j) const { return queue.at(j); }
+    // the two 16-byte records of a ray and how they decode (used by the prefetching top-level pass)
+    __device__ __forceinline__ const float4* rec_a(uint32_t tag) const { return ray_o + tag; }
+    __device__ __forceinline__ const float4* rec_b(uint32_t tag) const { return ray_d + tag; }
+    __device__ __forceinline__ void decode(float4 a, float4 b, V3& o, V3& d, float& tmax, float& time) const
+    {
+        o = xyz(a); d = xyz(b); tmax = RT_RAY_TMAX; time = a.w;
+    }
     __device__ __forceinline__ bool load(uint32_t j, V3& o, V3& d, float& tmax, float& time, uint32_t& tag) const
     {
         tag = queue.at(j);
-        float4 a = ray_o[tag], b = ray_d[tag];
-        o = xyz(a); d = xyz(b); tmax = RT_RAY_TMAX; time = a.w;
+        decode(ray_o[tag], ray_d[tag], o, d, tmax, time);
         return true;
     }
     __device__ __forceinline__ void store(uint32_t tag, const WaveResult& r) const
@@ -357,11 +364,18 @@ struct MisIO
     const float4* mis_dir;
     float4* mis_hit0;
     __device__ __forceinline__ uint32_t count() const { return queue.total(); }
+    __device__ __forceinline__ uint32_t tag_at(uint32_t j) const { return queue.at(j); }
+    // the two 16-byte records of a ray and how they decode (used by the prefetching top-level pass)
+    __device__ __forceinline__ const float4* rec_a(uint32_t tag) const { return pos_time + tag; }
+    __device__ __forceinline__ const float4* rec_b(uint32_t tag) const { return mis_dir + tag; }
+    __device__ __forceinline__ void decode(float4 a, float4 b, V3& o, V3& d, float& tmax, float& time) const
+    {
+        o = xyz(a); d = xyz(b); tmax = RT_RAY_TMAX; time = a.w;
+    }
     __device__ __forceinline__ bool load(uint32_t j, V3& o, V3& d, float& tmax, float& time, uint32_t& tag) const
     {
         tag = queue.at(j);
-        float4 a = pos_time[tag], b = mis_dir[tag];
-        o = xyz(a); d = xyz(b); tmax = RT_RAY_TMAX; time = a.w;
+        decode(pos_time[tag], mis_dir[tag], o, d, tmax, time);
         return true;
     }
     __device__ __forceinline__ void store(uint32_t tag, const WaveResult& r) const
@@ -377,11 +391,18 @@ struct ShadowIO
     const float4* sh_dir;
     uint8_t* occluded;
     __device__ __forceinline__ uint32_t count() const { return queue.total(); }
+    __device__ __forceinline__ uint32_t tag_at(uint32_t j) const { return queue.at(j); }
+    // the two 16-byte records of a ray and how they decode (used by the prefetching top-level pass)
+    __device__ __forceinline__ const float4* rec_a(uint32_t tag) const { return pos_time + tag; }
+    __device__ __forceinline__ const float4* rec_b(uint32_t tag) const { return sh_dir + tag; }
+    __device__ __forceinline__ void decode(float4 a, float4 b, V3& o, V3& d, float& tmax, float& time) const
+    {
+        o = xyz(a); d = xyz(b); tmax = b.w; time = a.w;
+    }
     __device__ __forceinline__ bool load(uint32_t j, V3& o, V3& d, float& tmax, float& time, uint32_t& tag) const
     {
         tag = queue.at(j);
-        float4 a = pos_time[tag], b = sh_dir[tag];
-        o = xyz(a); d = xyz(b); tmax = b.w; time = a.w;
+        decode(pos_time[tag], sh_dir[tag], o, d, tmax, time);
         return true;
     }
     __device__ __forceinline__ void store(uint32_t tag, const WaveResult& r) const { occluded[tag] = r.any_hit ? 1 : 0; }
@@ -449,11 +470,16 @@ k_split_top_static(const __grid_constant__ DScene sc, const IO io, const SplitBu
 {
     __shared__ float lane_t0[(RT_WALK_MAX_DEPTH + 1) * RT_BLOCK];
     __shared__ float lane_t1[(RT_WALK_MAX_DEPTH + 1) * RT_BLOCK];
+#if RT_STATIC_PREFETCH
+    __shared__ float4 stage_rec[2 * 2 * RT_BLOCK];       // [stage][record a / b][thread]
+#else
+    float4* stage_rec = NULL;
+#endif
     split_zero(ps);
     if (count_slot >= 0 && blockIdx.x == 0 && threadIdx.x == 0)
         atomicAdd(reinterpret_cast<unsigned long long*>(totals + count_slot), (unsigned long long)io.count());
     WorkCount wc = { 0, 0, 0, 0 };
-    trace_top_static<ANY, COUNT>(sc, io, sb, ps, wc, lane_t0, lane_t1);
+    trace_top_static<ANY, COUNT>(sc, io, sb, ps, wc, lane_t0, lane_t1, stage_rec);
     if (COUNT)
         flush_work_counters(wc, totals);
 }
