@@ -66,8 +66,8 @@ WORKLOADS["c2"] = dict(stage23=3, width=512, height=512, sweep=C2_SWEEP,
 # DRAM bytes (read + write) per launch of the dominant traversal kernel, from the `ncu --set full`
 # captures summarised under profiles/ (same batch size as the full-size workloads; None = not captured)
 NCU_TRAFFIC = {
-    1: dict(kernel="k_split_top<ANY=1,FRESH=1,ShadowIO> (fresh top-level pass of the shadow rays of one 16 Mi-sample batch)",
-            bytes=1.918768e9 + 650.789120e6, ms=2.1, source="profiles/r01_v6_split_c4small_full_summary.csv",
+    1: dict(kernel="k_split_top_static<ANY=1,ShadowIO> (tabulated top-level pass of the shadow rays of one 16 Mi-sample batch)",
+            bytes=1.840791e9 + 618.319616e6, ms=1.6, source="profiles/r01_v8_static_top_c4small_full_summary.csv",
             note="mostly per-ray wavefront state (scattered 16-byte records), not scene data: the 3 MB scene is L1/L2-resident"),
     5: dict(kernel="k_split_mesh<64,ANY=0,PathIO> (face-BVH pass of the path rays of one 16 Mi-sample batch)",
             bytes=4.922347e9 + 319.387904e6, ms=5.8, source="profiles/r01_v6_mesh_c5small_full_summary.csv",
