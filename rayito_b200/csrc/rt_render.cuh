@@ -495,6 +495,29 @@ k_split_mesh(const __grid_constant__ DScene sc, const IO io, const SplitBufs sb,
         flush_work_counters(wc, totals);
 }
 
+// Which light does light-sample iteration `lsi` of path sample i use, and with which sample index
+__device__ __forceinline__ void light_choice(const RenderCtx& c, uint32_t bounce, uint32_t lsi, uint32_t p, uint32_t psi,
+                                             uint32_t& idx, uint32_t& light_index)
+{
+    if (c.sc.stage6)
+    {
+        // every light in turn, ls*ls samples each (S6 RaytraceMain.cpp:274-384)
+        light_index = lsi / c.ls2;
+        idx = psi * c.ls2 + lsi % c.ls2;
+    }
+    else
+    {
+        // random light (:358-364)
+        uint32_t n1 = c.ps * c.ls * c.ps * c.ls;
+        uint32_t perm_sel = c.perms[(size_t)(5 * bounce + 1) * c.num_pixels + p];
+        idx = psi * c.nls + lsi;
+        float liu = cmj1d(idx, n1, perm_sel);
+        light_index = (uint32_t)(liu * (float)c.sc.num_lights);
+        if (light_index >= c.sc.num_lights)
+            light_index = c.sc.num_lights - 1;
+    }
+}
+
 // pathTrace, one bounce, everything that does not need further rays
 __global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_MINBLOCKS)
 k_shade(const __grid_constant__ RenderCtx c, int cur, uint32_t bounce)
@@ -504,7 +527,6 @@ k_shade(const __grid_constant__ RenderCtx c, int cur, uint32_t bounce)
     if (blockIdx.x == 0 && threadIdx.x == 0)
     {
         for (int b = 0; b < RT_QBINS; ++b) { c.ctl[CTL_SHADOW + b] = 0; c.ctl[CTL_MIS + b] = 0; }
-        for (int b = 0; b < RT_LBINS; ++b) c.ctl[CTL_LITB + b] = 0;
         c.ctl[CTL_CUR_SHADOW] = 0;
         c.ctl[CTL_CUR_MIS] = 0;
         c.ctl[CTL_CUR_PATH] = 0;
@@ -557,9 +579,15 @@ k_shade(const __grid_constant__ RenderCtx c, int cur, uint32_t bounce)
                     bool dirac = mat.brdf == RT_BRDF_MIRROR;
                     if (dirac)
                         nd++;
+                    uint32_t p = i / c.spp, psi = i % c.spp;
                     if (!dirac && c.nls > 0)
                     {
                         bq_push(c.q_lit, c.ctl + CTL_LIT, c.qcap, 0, i);
+                        // ... and regrouped by (light of light sample 0, BRDF kind) for k_light_sample; the
+                        // bins live in this bounce's consumed path queue
+                        uint32_t idx0, light0;
+                        light_choice(c, bounce, 0, p, psi, idx0, light0);
+                        bq_push(c.q_path[cur], c.ctl + CTL_LITB, c.qcap, (light0 & 3u) | (mat.brdf == RT_BRDF_GLOSSY ? 4u : 0u), i);
                         c.light_thr[i] = make_float4(thr.r, thr.g, thr.b, 0.0f);
                         c.light_res[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                         c.pos_time[i] = make_float4(position.x, position.y, position.z, ro.w);
@@ -567,7 +595,6 @@ k_shade(const __grid_constant__ RenderCtx c, int cur, uint32_t bounce)
                     }
 
                     // Next leg of the path (:451-477)
-                    uint32_t p = i / c.spp, psi = i % c.spp;
                     uint32_t perm = c.perms[(size_t)(5 * bounce + 0) * c.num_pixels + p];
                     float u, v;
                     cmj2d(psi, c.ps, c.ps, perm, u, v);
@@ -594,34 +621,11 @@ k_shade(const __grid_constant__ RenderCtx c, int cur, uint32_t bounce)
     }
 }
 
-// Which light does light-sample iteration `lsi` of path sample i use, and with which sample index
-__device__ __forceinline__ void light_choice(const RenderCtx& c, uint32_t bounce, uint32_t lsi, uint32_t p, uint32_t psi,
-                                             uint32_t& idx, uint32_t& light_index)
-{
-    if (c.sc.stage6)
-    {
-        // every light in turn, ls*ls samples each (S6 RaytraceMain.cpp:274-384)
-        light_index = lsi / c.ls2;
-        idx = psi * c.ls2 + lsi % c.ls2;
-    }
-    else
-    {
-        // random light (:358-364)
-        uint32_t n1 = c.ps * c.ls * c.ps * c.ls;
-        uint32_t perm_sel = c.perms[(size_t)(5 * bounce + 1) * c.num_pixels + p];
-        idx = psi * c.nls + lsi;
-        float liu = cmj1d(idx, n1, perm_sel);
-        light_index = (uint32_t)(liu * (float)c.sc.num_lights);
-        if (light_index >= c.sc.num_lights)
-            light_index = c.sc.num_lights - 1;
-    }
-}
-
 // Regroup the lit paths by (chosen light, BRDF kind) so that the lanes of a k_light_sample
-// warp run the same light-sampling and BRDF code.  The bins live in the shade queue's
-// buffer, which is idle between k_shade and the next bounce's path trace.
+// warp run the same light-sampling and BRDF code (light samples after the first; k_shade does it
+// for the first).  The bins live in this bounce's path queue, consumed before k_shade ran.
 __global__ void __launch_bounds__(RT_BLOCK)
-k_light_select(const __grid_constant__ RenderCtx c, uint32_t bounce, uint32_t lsi)
+k_light_select(const __grid_constant__ RenderCtx c, int cur, uint32_t bounce, uint32_t lsi)
 {
     const uint32_t n = c.ctl[CTL_LIT];
     RT_GRID_STRIDE(j, n)
@@ -633,7 +637,7 @@ k_light_select(const __grid_constant__ RenderCtx c, uint32_t bounce, uint32_t ls
             light_choice(c, bounce, lsi, i / c.spp, i % c.spp, idx, light_index);
             const RtMaterial& mat = c.sc.materials[__float_as_uint(c.wo_mat[i].w)];
             uint32_t bin = (light_index & 3u) | (mat.brdf == RT_BRDF_GLOSSY ? 4u : 0u);
-            bq_push(c.q_shade, c.ctl + CTL_LITB, c.qcap, bin, i);
+            bq_push(c.q_path[cur], c.ctl + CTL_LITB, c.qcap, bin, i);
         }
     }
 }
@@ -641,9 +645,9 @@ k_light_select(const __grid_constant__ RenderCtx c, uint32_t bounce, uint32_t ls
 // One light sample of the direct-lighting loop (:336-422): produces at most one
 // shadow ray and one BRDF-MIS probe per lit path
 __global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_MINBLOCKS)
-k_light_sample(const __grid_constant__ RenderCtx c, uint32_t bounce, uint32_t lsi)
+k_light_sample(const __grid_constant__ RenderCtx c, int cur, uint32_t bounce, uint32_t lsi)
 {
-    const BinQ<RT_LBINS> lit = { c.q_shade, c.ctl + CTL_LITB, c.qcap };
+    const BinQ<RT_LBINS> lit = { c.q_path[cur], c.ctl + CTL_LITB, c.qcap };
     const uint32_t n = lit.total();
     RT_GRID_STRIDE(j, n)
     {
@@ -1228,6 +1232,7 @@ __global__ void k_stage_prologue(const __grid_constant__ RenderCtx c, int cur)
     // counters of the queues this bounce's path trace and shade kernels fill
     for (int b = 0; b < RT_QBINS; ++b) c.ctl[CTL_PATH(cur ^ 1) + b] = 0;
     for (int b = 0; b < RT_SBINS; ++b) c.ctl[CTL_SHADE + b] = 0;
+    for (int b = 0; b < RT_LBINS; ++b) c.ctl[CTL_LITB + b] = 0;      // k_shade regroups the lit paths for light sample 0
     c.ctl[CTL_LIT] = 0;
 }
 
@@ -1311,9 +1316,13 @@ static int rt_launch_batch(RtScene* s, const RenderCtx& c, cudaStream_t st, uint
         launches += 2;
         for (uint32_t l = 0; l < c.nls; ++l)
         {
-            k_light_select<<<wide, RT_BLOCK, 0, st>>>(c, b, l);
-            k_light_sample<<<wide, RT_BLOCK, 0, st>>>(c, b, l);
-            launches += 1;
+            if (l > 0)
+            {
+                // (light sample 0 was regrouped by k_shade itself)
+                k_light_select<<<wide, RT_BLOCK, 0, st>>>(c, cur, b, l);
+                launches += 1;
+            }
+            k_light_sample<<<wide, RT_BLOCK, 0, st>>>(c, cur, b, l);
             rt_trace_mark(rb, timed, st);
             if (split)
             {
