@@ -89,11 +89,11 @@ struct RenderCtx
     float4* wo_mat;             // outgoing xyz, material index
     float4* light_thr;          // throughput at the bounce being lit
     float4* light_res;          // lightResult accumulator
-    float4* sh_dir;             // shadow direction xyz, tMax
-    float4* sh_L;               // light-sample term rgb, valid flag
+    // One 64-byte record per path for the current light sample (one DRAM burst, written whole by
+    // k_light_sample): [4i+0] shadow direction xyz, tMax; [4i+1] light-sample term rgb, valid flag;
+    // [4i+2] probe direction xyz, brdf pdf (0 = none); [4i+3] partial BRDF-sample term rgb, light shape id
+    float4* lrec;
     uint8_t* occluded;
-    float4* mis_dir;            // probe direction xyz, brdf pdf (0 = none)
-    float4* mis_P;              // partial BRDF-sample term rgb, light shape id
     float4* mis_hit0;
     float4* mis_hit1;
     uint32_t qcap;              // capacity of one queue bin (= samples of the batch buffers)
@@ -361,13 +361,13 @@ struct MisIO
 {
     BinQ<RT_QBINS> queue;
     const float4* pos_time;
-    const float4* mis_dir;
+    const float4* lrec;          // probe direction at [4 * tag + 2]
     float4* mis_hit0;
     __device__ __forceinline__ uint32_t count() const { return queue.total(); }
     __device__ __forceinline__ uint32_t tag_at(uint32_t j) const { return queue.at(j); }
     // the two 16-byte records of a ray and how they decode (used by the prefetching top-level pass)
     __device__ __forceinline__ const float4* rec_a(uint32_t tag) const { return pos_time + tag; }
-    __device__ __forceinline__ const float4* rec_b(uint32_t tag) const { return mis_dir + tag; }
+    __device__ __forceinline__ const float4* rec_b(uint32_t tag) const { return lrec + 4 * (size_t)tag + 2; }
     __device__ __forceinline__ void decode(float4 a, float4 b, V3& o, V3& d, float& tmax, float& time) const
     {
         o = xyz(a); d = xyz(b); tmax = RT_RAY_TMAX; time = a.w;
@@ -375,7 +375,7 @@ struct MisIO
     __device__ __forceinline__ bool load(uint32_t j, V3& o, V3& d, float& tmax, float& time, uint32_t& tag) const
     {
         tag = queue.at(j);
-        decode(pos_time[tag], mis_dir[tag], o, d, tmax, time);
+        decode(pos_time[tag], lrec[4 * (size_t)tag + 2], o, d, tmax, time);
         return true;
     }
     __device__ __forceinline__ void store(uint32_t tag, const WaveResult& r) const
@@ -388,13 +388,13 @@ struct ShadowIO
 {
     BinQ<RT_QBINS> queue;
     const float4* pos_time;
-    const float4* sh_dir;
+    const float4* lrec;          // shadow direction at [4 * tag + 0]
     uint8_t* occluded;
     __device__ __forceinline__ uint32_t count() const { return queue.total(); }
     __device__ __forceinline__ uint32_t tag_at(uint32_t j) const { return queue.at(j); }
     // the two 16-byte records of a ray and how they decode (used by the prefetching top-level pass)
     __device__ __forceinline__ const float4* rec_a(uint32_t tag) const { return pos_time + tag; }
-    __device__ __forceinline__ const float4* rec_b(uint32_t tag) const { return sh_dir + tag; }
+    __device__ __forceinline__ const float4* rec_b(uint32_t tag) const { return lrec + 4 * (size_t)tag; }
     __device__ __forceinline__ void decode(float4 a, float4 b, V3& o, V3& d, float& tmax, float& time) const
     {
         o = xyz(a); d = xyz(b); tmax = b.w; time = a.w;
@@ -402,7 +402,7 @@ struct ShadowIO
     __device__ __forceinline__ bool load(uint32_t j, V3& o, V3& d, float& tmax, float& time, uint32_t& tag) const
     {
         tag = queue.at(j);
-        decode(pos_time[tag], sh_dir[tag], o, d, tmax, time);
+        decode(pos_time[tag], lrec[4 * (size_t)tag], o, d, tmax, time);
         return true;
     }
     __device__ __forceinline__ void store(uint32_t tag, const WaveResult& r) const { occluded[tag] = r.any_hit ? 1 : 0; }
@@ -415,12 +415,12 @@ __host__ __device__ __forceinline__ PathIO make_path_io(const RenderCtx& c, int 
 }
 __host__ __device__ __forceinline__ MisIO make_mis_io(const RenderCtx& c)
 {
-    MisIO io = { { c.q_mis, c.ctl + CTL_MIS, c.qcap }, c.pos_time, c.mis_dir, c.mis_hit0 };
+    MisIO io = { { c.q_mis, c.ctl + CTL_MIS, c.qcap }, c.pos_time, c.lrec, c.mis_hit0 };
     return io;
 }
 __host__ __device__ __forceinline__ ShadowIO make_shadow_io(const RenderCtx& c)
 {
-    ShadowIO io = { { c.q_shadow, c.ctl + CTL_SHADOW, c.qcap }, c.pos_time, c.sh_dir, c.occluded };
+    ShadowIO io = { { c.q_shadow, c.ctl + CTL_SHADOW, c.qcap }, c.pos_time, c.lrec, c.occluded };
     return io;
 }
 
@@ -691,6 +691,7 @@ k_light_sample(const __grid_constant__ RenderCtx c, int cur, uint32_t bounce, ui
             light_sample(c.sc, lsh, position, time, lsu, lsv, leu, lpos, lnrm, lpdf);
 
             float4 shl = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            float4 shd = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             if (lpdf > 0.0f)
             {
                 V3 li = position - lpos;
@@ -703,12 +704,11 @@ k_light_sample(const __grid_constant__ RenderCtx c, int cur, uint32_t bounce, ui
                     V3 sd = -li;
                     float mis = power_heuristic(lpdf, bpdf);
                     Color3 L = emitted * mkc(cm, cm, cm) * mc * bres * fabsf(dot3(sd, normal)) * mis / (lpdf * 1.0f);
-                    c.sh_dir[i] = make_float4(sd.x, sd.y, sd.z, dist - RT_RAY_TMIN);
+                    shd = make_float4(sd.x, sd.y, sd.z, dist - RT_RAY_TMIN);
                     shl = make_float4(L.r, L.g, L.b, 1.0f);
                     bq_push(c.q_shadow, c.ctl + CTL_SHADOW, c.qcap, dir_octant(sd), i);
                 }
             }
-            c.sh_L[i] = shl;
 
             // BRDF sample towards (hopefully) the same light (:410-422)
             float bsu, bsv;
@@ -717,15 +717,18 @@ k_light_sample(const __grid_constant__ RenderCtx c, int cur, uint32_t bounce, ui
             float bpdf = 0.0f;
             float bres = brdf_sample(mat.brdf, mat.exponent, bi, outgoing, normal, bsu, bsv, bpdf);
             float4 md = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            float4 mp = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             if (bpdf > 0.0f && bres > 0.0f)
             {
                 V3 pd = -bi;
                 Color3 P = emitted * mkc(cm, cm, cm) * mc * bres * fabsf(dot3(pd, normal));
                 md = make_float4(pd.x, pd.y, pd.z, bpdf);
-                c.mis_P[i] = make_float4(P.r, P.g, P.b, __uint_as_float(light_shape));
+                mp = make_float4(P.r, P.g, P.b, __uint_as_float(light_shape));
                 bq_push(c.q_mis, c.ctl + CTL_MIS, c.qcap, dir_octant(pd), i);
             }
-            c.mis_dir[i] = md;
+            // the whole 64-byte record, every time: full sectors, no read-modify-write
+            float4* rec = c.lrec + 4 * (size_t)i;
+            rec[0] = shd; rec[1] = shl; rec[2] = md; rec[3] = mp;
         }
     }
 }
@@ -779,13 +782,14 @@ k_resolve(const __grid_constant__ RenderCtx c, uint32_t lsi)
             continue;
         uint32_t i = c.q_lit[j];
         Color3 lr = rgb(c.light_res[i]);
-        float4 shl = c.sh_L[i];
+        const float4* rec = c.lrec + 4 * (size_t)i;
+        float4 shl = rec[1];
         if (shl.w != 0.0f && !c.occluded[i])
             lr = lr + rgb(shl);
-        float4 md = c.mis_dir[i];
+        float4 md = rec[2];
         if (md.w > 0.0f)
         {
-            float4 mp = c.mis_P[i], mh0 = c.mis_hit0[i];
+            float4 mp = rec[3], mh0 = c.mis_hit0[i];
             uint32_t light_shape = __float_as_uint(mp.w);
             if (__float_as_int(mh0.y) == (int)light_shape)
             {
@@ -1019,11 +1023,8 @@ inline size_t carve(RenderCtx& c, char* base, size_t samples, size_t pixels, uin
     c.wo_mat = k.take<float4>(samples);
     c.light_thr = k.take<float4>(samples);
     c.light_res = k.take<float4>(samples);
-    c.sh_dir = k.take<float4>(samples);
-    c.sh_L = k.take<float4>(samples);
+    c.lrec = k.take<float4>(samples * 4);
     c.occluded = k.take<uint8_t>(samples);
-    c.mis_dir = k.take<float4>(samples);
-    c.mis_P = k.take<float4>(samples);
     c.mis_hit0 = k.take<float4>(samples);
     c.mis_hit1 = k.take<float4>(samples);
     c.qcap = (uint32_t)samples;
