@@ -79,8 +79,7 @@ struct RenderCtx
 
     uint32_t* pix_xy;           // per pixel: y << 16 | x, or 0xffffffff
     uint32_t* perms;            // [(5*depth+3)][num_pixels]
-    float4* ray_o;              // origin xyz, time
-    float4* ray_d;              // direction xyz, -
+    float4* ray_od;             // [2i] origin xyz, time; [2i+1] direction xyz, - (one 32-byte sector per path)
     float4* hit0;               // t, shape, tri record, -
     float4* hit1;               // normal xyz, colour modifier
     float4* thr;                // throughput rgb, (numBounces | numDirac << 8)
@@ -280,8 +279,8 @@ k_raygen(const __grid_constant__ RenderCtx c)
                 V3 o, d;
                 float time;
                 camera_ray(c, p, psi, xy & 0xffffu, xy >> 16, o, d, time);
-                c.ray_o[i] = make_float4(o.x, o.y, o.z, time);
-                c.ray_d[i] = make_float4(d.x, d.y, d.z, 0.0f);
+                c.ray_od[2 * (size_t)i] = make_float4(o.x, o.y, o.z, time);
+                c.ray_od[2 * (size_t)i + 1] = make_float4(d.x, d.y, d.z, 0.0f);
                 c.thr[i] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(0u));
                 c.res[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                 bq_push(c.q_path[0], c.ctl + CTL_PATH_A, c.qcap, dir_octant(d), i);
@@ -328,8 +327,7 @@ __device__ __forceinline__ void flush_work_counters(const WorkCount& wc, uint64_
 struct PathIO
 {
     BinQ<RT_QBINS> queue;
-    const float4* ray_o;
-    const float4* ray_d;
+    const float4* ray_od;
     float4* hit0;
     // hits are handed to the shading stage binned by shape; misses end the path here
     uint32_t* shade_items;
@@ -337,8 +335,8 @@ struct PathIO
     __device__ __forceinline__ uint32_t count() const { return queue.total(); }
     __device__ __forceinline__ uint32_t tag_at(uint32_t j) const { return queue.at(j); }
     // the two 16-byte records of a ray and how they decode (used by the prefetching top-level pass)
-    __device__ __forceinline__ const float4* rec_a(uint32_t tag) const { return ray_o + tag; }
-    __device__ __forceinline__ const float4* rec_b(uint32_t tag) const { return ray_d + tag; }
+    __device__ __forceinline__ const float4* rec_a(uint32_t tag) const { return ray_od + 2 * (size_t)tag; }
+    __device__ __forceinline__ const float4* rec_b(uint32_t tag) const { return ray_od + 2 * (size_t)tag + 1; }
     __device__ __forceinline__ void decode(float4 a, float4 b, V3& o, V3& d, float& tmax, float& time) const
     {
         o = xyz(a); d = xyz(b); tmax = RT_RAY_TMAX; time = a.w;
@@ -346,7 +344,7 @@ struct PathIO
     __device__ __forceinline__ bool load(uint32_t j, V3& o, V3& d, float& tmax, float& time, uint32_t& tag) const
     {
         tag = queue.at(j);
-        decode(ray_o[tag], ray_d[tag], o, d, tmax, time);
+        decode(ray_od[2 * (size_t)tag], ray_od[2 * (size_t)tag + 1], o, d, tmax, time);
         return true;
     }
     __device__ __forceinline__ void store(uint32_t tag, const WaveResult& r) const
@@ -410,7 +408,7 @@ struct ShadowIO
 
 __host__ __device__ __forceinline__ PathIO make_path_io(const RenderCtx& c, int cur)
 {
-    PathIO io = { { c.q_path[cur], c.ctl + CTL_PATH(cur), c.qcap }, c.ray_o, c.ray_d, c.hit0, c.q_shade, c.ctl + CTL_SHADE };
+    PathIO io = { { c.q_path[cur], c.ctl + CTL_PATH(cur), c.qcap }, c.ray_od, c.hit0, c.q_shade, c.ctl + CTL_SHADE };
     return io;
 }
 __host__ __device__ __forceinline__ MisIO make_mis_io(const RenderCtx& c)
@@ -540,7 +538,7 @@ k_shade(const __grid_constant__ RenderCtx c, int cur, uint32_t bounce)
             int shape = __float_as_int(h0.y);
             if (shape >= 0)
             {
-                float4 ro = c.ray_o[i], rd = c.ray_d[i], th = c.thr[i], rs = c.res[i];
+                float4 ro = c.ray_od[2 * (size_t)i], rd = c.ray_od[2 * (size_t)i + 1], th = c.thr[i], rs = c.res[i];
                 // Intersection::m_normal / m_colorModifier of the winning hit, computed
                 // here where all 32 lanes are busy rather than in the traversal loop
                 float4 h1;
@@ -608,8 +606,8 @@ k_shade(const __grid_constant__ RenderCtx c, int cur, uint32_t bounce)
                         thr = thr * f;
                         nb++;
                         V3 nd3 = -incoming;
-                        c.ray_o[i] = make_float4(position.x, position.y, position.z, ro.w);
-                        c.ray_d[i] = make_float4(nd3.x, nd3.y, nd3.z, 0.0f);
+                        c.ray_od[2 * (size_t)i] = make_float4(position.x, position.y, position.z, ro.w);
+                        c.ray_od[2 * (size_t)i + 1] = make_float4(nd3.x, nd3.y, nd3.z, 0.0f);
                         if (nb < c.depth)
                             bq_push(c.q_path[cur ^ 1], c.ctl + CTL_PATH(cur ^ 1), c.qcap, dir_octant(nd3), i);
                     }
@@ -1013,8 +1011,7 @@ inline size_t carve(RenderCtx& c, char* base, size_t samples, size_t pixels, uin
     Carver k = { base, 0 };
     c.pix_xy = k.take<uint32_t>(pixels);
     c.perms = k.take<uint32_t>(pixels * slots);
-    c.ray_o = k.take<float4>(samples);
-    c.ray_d = k.take<float4>(samples);
+    c.ray_od = k.take<float4>(samples * 2);
     c.hit0 = k.take<float4>(samples);
     c.hit1 = k.take<float4>(samples);
     c.thr = k.take<float4>(samples);
