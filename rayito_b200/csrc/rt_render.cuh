@@ -80,14 +80,11 @@ struct RenderCtx
     uint32_t* pix_xy;           // per pixel: y << 16 | x, or 0xffffffff
     uint32_t* perms;            // [(5*depth+3)][num_pixels]
     float4* ray_od;             // [2i] origin xyz, time; [2i+1] direction xyz, - (one 32-byte sector per path)
-    float4* hit0;               // t, shape, tri record, -
-    float4* hit1;               // normal xyz, colour modifier
+    float4* hit01;              // [2i] t, shape, tri record, -; [2i+1] normal xyz, colour modifier
     float4* thr;                // throughput rgb, (numBounces | numDirac << 8)
     float4* res;                // radiance rgb
-    float4* pos_time;           // hit position xyz, time
-    float4* wo_mat;             // outgoing xyz, material index
-    float4* light_thr;          // throughput at the bounce being lit
-    float4* light_res;          // lightResult accumulator
+    float4* pos_wo;             // [2i] hit position xyz, time; [2i+1] outgoing xyz, material index
+    float4* lit_tr;             // [2i] throughput at the bounce being lit; [2i+1] lightResult accumulator
     // One 64-byte record per path for the current light sample (one DRAM burst, written whole by
     // k_light_sample): [4i+0] shadow direction xyz, tMax; [4i+1] light-sample term rgb, valid flag;
     // [4i+2] probe direction xyz, brdf pdf (0 = none); [4i+3] partial BRDF-sample term rgb, light shape id
@@ -328,7 +325,7 @@ struct PathIO
 {
     BinQ<RT_QBINS> queue;
     const float4* ray_od;
-    float4* hit0;
+    float4* hit01;
     // hits are handed to the shading stage binned by shape; misses end the path here
     uint32_t* shade_items;
     uint32_t* shade_counts;
@@ -349,7 +346,7 @@ struct PathIO
     }
     __device__ __forceinline__ void store(uint32_t tag, const WaveResult& r) const
     {
-        hit0[tag] = make_float4(r.t, __int_as_float(r.shape), __int_as_float(r.tri_rec), 0.0f);
+        hit01[2 * (size_t)tag] = make_float4(r.t, __int_as_float(r.shape), __int_as_float(r.tri_rec), 0.0f);
         if (r.shape >= 0)
             bq_push(shade_items, shade_counts, queue.cap, min((uint32_t)r.shape, (uint32_t)(RT_SBINS - 1)), tag);
     }
@@ -358,13 +355,13 @@ struct PathIO
 struct MisIO
 {
     BinQ<RT_QBINS> queue;
-    const float4* pos_time;
+    const float4* pos_wo;        // hit position, time at [2 * tag]
     const float4* lrec;          // probe direction at [4 * tag + 2]
     float4* mis_hit0;
     __device__ __forceinline__ uint32_t count() const { return queue.total(); }
     __device__ __forceinline__ uint32_t tag_at(uint32_t j) const { return queue.at(j); }
     // the two 16-byte records of a ray and how they decode (used by the prefetching top-level pass)
-    __device__ __forceinline__ const float4* rec_a(uint32_t tag) const { return pos_time + tag; }
+    __device__ __forceinline__ const float4* rec_a(uint32_t tag) const { return pos_wo + 2 * (size_t)tag; }
     __device__ __forceinline__ const float4* rec_b(uint32_t tag) const { return lrec + 4 * (size_t)tag + 2; }
     __device__ __forceinline__ void decode(float4 a, float4 b, V3& o, V3& d, float& tmax, float& time) const
     {
@@ -373,7 +370,7 @@ struct MisIO
     __device__ __forceinline__ bool load(uint32_t j, V3& o, V3& d, float& tmax, float& time, uint32_t& tag) const
     {
         tag = queue.at(j);
-        decode(pos_time[tag], lrec[4 * (size_t)tag + 2], o, d, tmax, time);
+        decode(pos_wo[2 * (size_t)tag], lrec[4 * (size_t)tag + 2], o, d, tmax, time);
         return true;
     }
     __device__ __forceinline__ void store(uint32_t tag, const WaveResult& r) const
@@ -385,13 +382,13 @@ struct MisIO
 struct ShadowIO
 {
     BinQ<RT_QBINS> queue;
-    const float4* pos_time;
+    const float4* pos_wo;        // hit position, time at [2 * tag]
     const float4* lrec;          // shadow direction at [4 * tag + 0]
     uint8_t* occluded;
     __device__ __forceinline__ uint32_t count() const { return queue.total(); }
     __device__ __forceinline__ uint32_t tag_at(uint32_t j) const { return queue.at(j); }
     // the two 16-byte records of a ray and how they decode (used by the prefetching top-level pass)
-    __device__ __forceinline__ const float4* rec_a(uint32_t tag) const { return pos_time + tag; }
+    __device__ __forceinline__ const float4* rec_a(uint32_t tag) const { return pos_wo + 2 * (size_t)tag; }
     __device__ __forceinline__ const float4* rec_b(uint32_t tag) const { return lrec + 4 * (size_t)tag; }
     __device__ __forceinline__ void decode(float4 a, float4 b, V3& o, V3& d, float& tmax, float& time) const
     {
@@ -400,7 +397,7 @@ struct ShadowIO
     __device__ __forceinline__ bool load(uint32_t j, V3& o, V3& d, float& tmax, float& time, uint32_t& tag) const
     {
         tag = queue.at(j);
-        decode(pos_time[tag], lrec[4 * (size_t)tag], o, d, tmax, time);
+        decode(pos_wo[2 * (size_t)tag], lrec[4 * (size_t)tag], o, d, tmax, time);
         return true;
     }
     __device__ __forceinline__ void store(uint32_t tag, const WaveResult& r) const { occluded[tag] = r.any_hit ? 1 : 0; }
@@ -408,17 +405,17 @@ struct ShadowIO
 
 __host__ __device__ __forceinline__ PathIO make_path_io(const RenderCtx& c, int cur)
 {
-    PathIO io = { { c.q_path[cur], c.ctl + CTL_PATH(cur), c.qcap }, c.ray_od, c.hit0, c.q_shade, c.ctl + CTL_SHADE };
+    PathIO io = { { c.q_path[cur], c.ctl + CTL_PATH(cur), c.qcap }, c.ray_od, c.hit01, c.q_shade, c.ctl + CTL_SHADE };
     return io;
 }
 __host__ __device__ __forceinline__ MisIO make_mis_io(const RenderCtx& c)
 {
-    MisIO io = { { c.q_mis, c.ctl + CTL_MIS, c.qcap }, c.pos_time, c.lrec, c.mis_hit0 };
+    MisIO io = { { c.q_mis, c.ctl + CTL_MIS, c.qcap }, c.pos_wo, c.lrec, c.mis_hit0 };
     return io;
 }
 __host__ __device__ __forceinline__ ShadowIO make_shadow_io(const RenderCtx& c)
 {
-    ShadowIO io = { { c.q_shadow, c.ctl + CTL_SHADOW, c.qcap }, c.pos_time, c.lrec, c.occluded };
+    ShadowIO io = { { c.q_shadow, c.ctl + CTL_SHADOW, c.qcap }, c.pos_wo, c.lrec, c.occluded };
     return io;
 }
 
@@ -534,7 +531,7 @@ k_shade(const __grid_constant__ RenderCtx c, int cur, uint32_t bounce)
         if (j < n)
         {
             const uint32_t i = shade.at(j);
-            float4 h0 = c.hit0[i];
+            float4 h0 = c.hit01[2 * (size_t)i];
             int shape = __float_as_int(h0.y);
             if (shape >= 0)
             {
@@ -554,7 +551,7 @@ k_shade(const __grid_constant__ RenderCtx c, int cur, uint32_t bounce)
                     float cmod;
                     hit_shading_inputs(c.sc, r0, ro.w, h, nrm, cmod);
                     h1 = make_float4(nrm.x, nrm.y, nrm.z, cmod);
-                    c.hit1[i] = h1;
+                    c.hit01[2 * (size_t)i + 1] = h1;
                 }
                 uint32_t state = __float_as_uint(th.w);
                 uint32_t nb = state & 0xffu, nd = (state >> 8) & 0xffu;
@@ -586,10 +583,10 @@ k_shade(const __grid_constant__ RenderCtx c, int cur, uint32_t bounce)
                         uint32_t idx0, light0;
                         light_choice(c, bounce, 0, p, psi, idx0, light0);
                         bq_push(c.q_path[cur], c.ctl + CTL_LITB, c.qcap, (light0 & 3u) | (mat.brdf == RT_BRDF_GLOSSY ? 4u : 0u), i);
-                        c.light_thr[i] = make_float4(thr.r, thr.g, thr.b, 0.0f);
-                        c.light_res[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                        c.pos_time[i] = make_float4(position.x, position.y, position.z, ro.w);
-                        c.wo_mat[i] = make_float4(outgoing.x, outgoing.y, outgoing.z, __uint_as_float(sh.material));
+                        c.lit_tr[2 * (size_t)i] = make_float4(thr.r, thr.g, thr.b, 0.0f);
+                        c.lit_tr[2 * (size_t)i + 1] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                        c.pos_wo[2 * (size_t)i] = make_float4(position.x, position.y, position.z, ro.w);
+                        c.pos_wo[2 * (size_t)i + 1] = make_float4(outgoing.x, outgoing.y, outgoing.z, __uint_as_float(sh.material));
                     }
 
                     // Next leg of the path (:451-477)
@@ -633,7 +630,7 @@ k_light_select(const __grid_constant__ RenderCtx c, int cur, uint32_t bounce, ui
             const uint32_t i = c.q_lit[j];
             uint32_t idx, light_index;
             light_choice(c, bounce, lsi, i / c.spp, i % c.spp, idx, light_index);
-            const RtMaterial& mat = c.sc.materials[__float_as_uint(c.wo_mat[i].w)];
+            const RtMaterial& mat = c.sc.materials[__float_as_uint(c.pos_wo[2 * (size_t)i + 1].w)];
             uint32_t bin = (light_index & 3u) | (mat.brdf == RT_BRDF_GLOSSY ? 4u : 0u);
             bq_push(c.q_path[cur], c.ctl + CTL_LITB, c.qcap, bin, i);
         }
@@ -653,7 +650,7 @@ k_light_sample(const __grid_constant__ RenderCtx c, int cur, uint32_t bounce, ui
         {
             const uint32_t i = lit.at(j);
             uint32_t p = i / c.spp, psi = i % c.spp;
-            float4 pt = c.pos_time[i], wm = c.wo_mat[i], h1 = c.hit1[i];
+            float4 pt = c.pos_wo[2 * (size_t)i], wm = c.pos_wo[2 * (size_t)i + 1], h1 = c.hit01[2 * (size_t)i + 1];
             V3 position = xyz(pt), outgoing = xyz(wm), normal = xyz(h1);
             float time = pt.w, cm = h1.w;
             RtMaterial mat = c.sc.materials[__float_as_uint(wm.w)];
@@ -779,7 +776,7 @@ k_resolve(const __grid_constant__ RenderCtx c, uint32_t lsi)
         if (j >= n)
             continue;
         uint32_t i = c.q_lit[j];
-        Color3 lr = rgb(c.light_res[i]);
+        Color3 lr = rgb(c.lit_tr[2 * (size_t)i + 1]);
         const float4* rec = c.lrec + 4 * (size_t)i;
         float4 shl = rec[1];
         if (shl.w != 0.0f && !c.occluded[i])
@@ -791,7 +788,7 @@ k_resolve(const __grid_constant__ RenderCtx c, uint32_t lsi)
             uint32_t light_shape = __float_as_uint(mp.w);
             if (__float_as_int(mh0.y) == (int)light_shape)
             {
-                float4 pt = c.pos_time[i];
+                float4 pt = c.pos_wo[2 * (size_t)i];
                 DShape lsh = load_shape(c.sc, light_shape);
                 // normal of the probe's hit (only needed once the probe found the light)
                 ClosestHit h;
@@ -819,23 +816,23 @@ k_resolve(const __grid_constant__ RenderCtx c, uint32_t lsi)
             {
                 lr = lr / (float)c.ls2;
                 float4 rs = c.res[i];
-                Color3 result = rgb(rs) + rgb(c.light_thr[i]) * lr;
+                Color3 result = rgb(rs) + rgb(c.lit_tr[2 * (size_t)i]) * lr;
                 c.res[i] = make_float4(result.r, result.g, result.b, 0.0f);
                 lr = mkc(0.0f, 0.0f, 0.0f);
             }
-            c.light_res[i] = make_float4(lr.r, lr.g, lr.b, 0.0f);
+            c.lit_tr[2 * (size_t)i + 1] = make_float4(lr.r, lr.g, lr.b, 0.0f);
         }
         else if (lsi + 1 == c.nls)
         {
             float weight = (float)c.sc.num_lights / (float)c.nls;
             lr = lr * weight;
             float4 rs = c.res[i];
-            Color3 result = rgb(rs) + rgb(c.light_thr[i]) * lr;
+            Color3 result = rgb(rs) + rgb(c.lit_tr[2 * (size_t)i]) * lr;
             c.res[i] = make_float4(result.r, result.g, result.b, 0.0f);
         }
         else
         {
-            c.light_res[i] = make_float4(lr.r, lr.g, lr.b, 0.0f);
+            c.lit_tr[2 * (size_t)i + 1] = make_float4(lr.r, lr.g, lr.b, 0.0f);
         }
     }
 }
@@ -1012,14 +1009,11 @@ inline size_t carve(RenderCtx& c, char* base, size_t samples, size_t pixels, uin
     c.pix_xy = k.take<uint32_t>(pixels);
     c.perms = k.take<uint32_t>(pixels * slots);
     c.ray_od = k.take<float4>(samples * 2);
-    c.hit0 = k.take<float4>(samples);
-    c.hit1 = k.take<float4>(samples);
+    c.hit01 = k.take<float4>(samples * 2);
     c.thr = k.take<float4>(samples);
     c.res = k.take<float4>(samples);
-    c.pos_time = k.take<float4>(samples);
-    c.wo_mat = k.take<float4>(samples);
-    c.light_thr = k.take<float4>(samples);
-    c.light_res = k.take<float4>(samples);
+    c.pos_wo = k.take<float4>(samples * 2);
+    c.lit_tr = k.take<float4>(samples * 2);
     c.lrec = k.take<float4>(samples * 4);
     c.occluded = k.take<uint8_t>(samples);
     c.mis_hit0 = k.take<float4>(samples);
