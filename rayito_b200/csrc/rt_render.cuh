@@ -89,7 +89,6 @@ struct RenderCtx
     // k_light_sample): [4i+0] shadow direction xyz, tMax; [4i+1] light-sample term rgb, valid flag;
     // [4i+2] probe direction xyz, brdf pdf (0 = none); [4i+3] partial BRDF-sample term rgb, light shape id
     float4* lrec;
-    uint8_t* occluded;
     float4* mis_hit0;
     float4* mis_hit1;
     uint32_t qcap;              // capacity of one queue bin (= samples of the batch buffers)
@@ -383,8 +382,7 @@ struct ShadowIO
 {
     BinQ<RT_QBINS> queue;
     const float4* pos_wo;        // hit position, time at [2 * tag]
-    const float4* lrec;          // shadow direction at [4 * tag + 0]
-    uint8_t* occluded;
+    float4* lrec;                // shadow direction at [4 * tag + 0]; [4 * tag + 1].w = light sample still valid
     __device__ __forceinline__ uint32_t count() const { return queue.total(); }
     __device__ __forceinline__ uint32_t tag_at(uint32_t j) const { return queue.at(j); }
     // the two 16-byte records of a ray and how they decode (used by the prefetching top-level pass)
@@ -400,7 +398,12 @@ struct ShadowIO
         decode(pos_wo[2 * (size_t)tag], lrec[4 * (size_t)tag], o, d, tmax, time);
         return true;
     }
-    __device__ __forceinline__ void store(uint32_t tag, const WaveResult& r) const { occluded[tag] = r.any_hit ? 1 : 0; }
+    // an occluded light sample is cancelled in place (the record k_resolve reads anyway)
+    __device__ __forceinline__ void store(uint32_t tag, const WaveResult& r) const
+    {
+        if (r.any_hit)
+            reinterpret_cast<float*>(lrec + 4 * (size_t)tag + 1)[3] = 0.0f;
+    }
 };
 
 __host__ __device__ __forceinline__ PathIO make_path_io(const RenderCtx& c, int cur)
@@ -415,7 +418,7 @@ __host__ __device__ __forceinline__ MisIO make_mis_io(const RenderCtx& c)
 }
 __host__ __device__ __forceinline__ ShadowIO make_shadow_io(const RenderCtx& c)
 {
-    ShadowIO io = { { c.q_shadow, c.ctl + CTL_SHADOW, c.qcap }, c.pos_wo, c.lrec, c.occluded };
+    ShadowIO io = { { c.q_shadow, c.ctl + CTL_SHADOW, c.qcap }, c.pos_wo, c.lrec };
     return io;
 }
 
@@ -779,7 +782,7 @@ k_resolve(const __grid_constant__ RenderCtx c, uint32_t lsi)
         Color3 lr = rgb(c.lit_tr[2 * (size_t)i + 1]);
         const float4* rec = c.lrec + 4 * (size_t)i;
         float4 shl = rec[1];
-        if (shl.w != 0.0f && !c.occluded[i])
+        if (shl.w != 0.0f)
             lr = lr + rgb(shl);
         float4 md = rec[2];
         if (md.w > 0.0f)
@@ -1015,7 +1018,6 @@ inline size_t carve(RenderCtx& c, char* base, size_t samples, size_t pixels, uin
     c.pos_wo = k.take<float4>(samples * 2);
     c.lit_tr = k.take<float4>(samples * 2);
     c.lrec = k.take<float4>(samples * 4);
-    c.occluded = k.take<uint8_t>(samples);
     c.mis_hit0 = k.take<float4>(samples);
     c.mis_hit1 = k.take<float4>(samples);
     c.qcap = (uint32_t)samples;
