@@ -293,6 +293,10 @@ typedef struct RtStage1Plane
 int rt_stage1_render(int device, const RtStage1Plane* planes, uint32_t num_planes, const RtCamera* camera,
                      uint32_t width, uint32_t height, uint8_t* rgb8);
 
+/* Device memory the library keeps between calls for speed (one wavefront state block per device,
+ * parked when a scene is destroyed; the Stage 2/3 working set) is freed here.  Optional. */
+void rt_release_cached_memory(void);
+
 /* ---- Stage 2 / Stage 3: the serial-Rng programs ------------------------------- */
 /* Rayito_Stage2/main.cpp and Rayito_Stage3/main.cpp (BASELINE config C2 is the Stage 3
  * pixel-sample sweep).  A handful of analytic shapes in a linear list, closest hit also

@@ -109,7 +109,7 @@ CORE_SYMBOLS = [
     "rt_trace_closest_device", "rt_trace_any_device",
     "rt_render", "rt_render_device", "rt_generate_camera_rays", "rt_tonemap_bgra8",
     "rt_tile_owners", "rt_sample_permutations", "rt_cmj_sample1d", "rt_cmj_sample2d", "rt_stage1_render",
-    "rt_libm_eval", "rt_stage23_render",
+    "rt_libm_eval", "rt_stage23_render", "rt_release_cached_memory",
 ]
 HOST_SYMBOLS = [
     "rth_last_error_string", "rth_scene_create", "rth_scene_destroy", "rth_scene_desc",

@@ -180,18 +180,18 @@ static int ensure_scratch(RtScene* s, size_t in_bytes, size_t out_bytes)
 {
     if (in_bytes > s->scratch_in_bytes)
     {
-        if (s->scratch_in) cudaFree(s->scratch_in);
+        rt_detail::pool_free(s->device, s->scratch_in, s->scratch_in_bytes);
         s->scratch_in = NULL;
         s->scratch_in_bytes = 0;
-        RT_CUDA(cudaMalloc(&s->scratch_in, in_bytes));
+        RT_CUDA(rt_detail::pool_alloc(s->device, &s->scratch_in, in_bytes, &in_bytes));
         s->scratch_in_bytes = in_bytes;
     }
     if (out_bytes > s->scratch_out_bytes)
     {
-        if (s->scratch_out) cudaFree(s->scratch_out);
+        rt_detail::pool_free(s->device, s->scratch_out, s->scratch_out_bytes);
         s->scratch_out = NULL;
         s->scratch_out_bytes = 0;
-        RT_CUDA(cudaMalloc(&s->scratch_out, out_bytes));
+        RT_CUDA(rt_detail::pool_alloc(s->device, &s->scratch_out, out_bytes, &out_bytes));
         s->scratch_out_bytes = out_bytes;
     }
     return RT_OK;
@@ -228,11 +228,11 @@ int rt_scene_destroy(RtScene* s)
     if (s == NULL) return RT_OK;
     cudaSetDevice(s->device);
     rt_render_release(s);
-    if (s->scratch_in) cudaFree(s->scratch_in);
-    if (s->scratch_out) cudaFree(s->scratch_out);
-    if (s->d_work) cudaFree(s->d_work);
-    if (s->d_cursor) cudaFree(s->d_cursor);
-    if (s->arena) cudaFree(s->arena);
+    rt_detail::pool_free(s->device, s->scratch_in, s->scratch_in_bytes);
+    rt_detail::pool_free(s->device, s->scratch_out, s->scratch_out_bytes);
+    rt_detail::pool_free(s->device, s->d_work, s->work_alloc);
+    rt_detail::pool_free(s->device, s->d_cursor, s->cursor_alloc);
+    rt_detail::pool_free(s->device, s->arena, s->arena_alloc);
     delete s;
     return RT_OK;
 }
@@ -320,6 +320,11 @@ int rt_stage1_render(int device, const RtStage1Plane* planes, uint32_t num_plane
                      uint32_t width, uint32_t height, uint8_t* rgb8)
 {
     return rt_stage1_impl(device, planes, num_planes, camera, width, height, rgb8);
+}
+
+void rt_release_cached_memory(void)
+{
+    rt_detail::pool_release_all();
 }
 
 int rt_stage23_render(int device, const RtS23Scene* scene, const RtCamera* camera, const RtS23Params* params,

@@ -23,6 +23,7 @@
 #define RAYITO_B200_RT_RENDER_CUH
 
 #include <algorithm>
+#include <mutex>
 #include <vector>
 
 #include "rt_scene.cuh"
@@ -115,6 +116,7 @@ struct RenderBuffers
     uint32_t* d_tile_ids;
     float* d_image;             // for the host-output entry point
     size_t image_floats;
+    size_t image_bytes, tile_bytes;     // real sizes of d_image / d_tile_ids (pool blocks may be larger than asked)
     cudaEvent_t ev[4];
     std::vector<cudaEvent_t>* trace_events;   // start/stop pairs around traversal kernels (RT_RENDER_TIME_TRACE)
     size_t trace_events_used;
@@ -977,9 +979,10 @@ inline void rt_render_release(RtScene* s)
     RenderBuffers* rb = s->render;
     if (rb == NULL)
         return;
-    if (rb->block) cudaFree(rb->block);
-    if (rb->d_tile_ids) cudaFree(rb->d_tile_ids);
-    if (rb->d_image) cudaFree(rb->d_image);
+    rt_detail::pool_free(s->device, rb->block, rb->block_bytes);
+    rb->block = NULL;
+    rt_detail::pool_free(s->device, rb->d_tile_ids, rb->tile_bytes);
+    rt_detail::pool_free(s->device, rb->d_image, rb->image_bytes);
     for (int i = 0; i < 4; ++i) cudaEventDestroy(rb->ev[i]);
     if (rb->trace_events)
     {
@@ -1107,18 +1110,22 @@ inline int rt_render_reserve(RtScene* s, RenderPlan& plan)
     }
     if (samples > rb->cap_samples || pixels > rb->cap_pixels || plan.slots > rb->cap_perm_slots)
     {
-        if (rb->block) cudaFree(rb->block);
+        rt_detail::pool_free(s->device, rb->block, rb->block_bytes);
         rb->block = NULL;
         rb->cap_samples = rb->cap_pixels = 0;
         RenderCtx probe;
         size_t bytes = rt_detail::carve(probe, NULL, samples, pixels, plan.slots);
+        size_t got_bytes = 0;
         // leave room for the rest of the process: shrink the batch until it fits in
         // at most 60 % of the free device memory, and on allocation failure
         for (;;)
         {
+            // parked blocks count as free: the pool hands them back or releases them on demand
             size_t free_b = 0, total_b = 0;
             cudaMemGetInfo(&free_b, &total_b);
-            cudaError_t e = bytes <= free_b / 10 * 6 ? cudaMalloc(&rb->block, bytes) : cudaErrorMemoryAllocation;
+            free_b += rt_detail::pool_parked_bytes(s->device);
+            cudaError_t e = bytes <= free_b / 10 * 6 ? rt_detail::pool_alloc(s->device, &rb->block, bytes, &got_bytes)
+                                                     : cudaErrorMemoryAllocation;
             if (e == cudaSuccess)
                 break;
             cudaGetLastError();
@@ -1130,7 +1137,7 @@ inline int rt_render_reserve(RtScene* s, RenderPlan& plan)
             samples = pixels * plan.spp;
             bytes = rt_detail::carve(probe, NULL, samples, pixels, plan.slots);
         }
-        rb->block_bytes = bytes;
+        rb->block_bytes = got_bytes;
         rb->cap_samples = samples;
         rb->cap_pixels = pixels;
         rb->cap_perm_slots = plan.slots;
@@ -1138,10 +1145,10 @@ inline int rt_render_reserve(RtScene* s, RenderPlan& plan)
     rt_detail::carve(rb->ctx, static_cast<char*>(rb->block), rb->cap_samples, rb->cap_pixels, rb->cap_perm_slots);
     if (plan.tiles.size() > rb->cap_tiles)
     {
-        if (rb->d_tile_ids) cudaFree(rb->d_tile_ids);
+        rt_detail::pool_free(s->device, rb->d_tile_ids, rb->tile_bytes);
         rb->d_tile_ids = NULL;
         rb->cap_tiles = 0;
-        RT_CUDA(cudaMalloc((void**)&rb->d_tile_ids, plan.tiles.size() * sizeof(uint32_t)));
+        RT_CUDA(rt_detail::pool_alloc(s->device, (void**)&rb->d_tile_ids, plan.tiles.size() * sizeof(uint32_t), &rb->tile_bytes));
         rb->cap_tiles = plan.tiles.size();
     }
     return RT_OK;
@@ -1388,10 +1395,10 @@ inline int rt_render_impl(RtScene* s, const RtCamera* camera, const RtRenderPara
     {
         if (rb->image_floats < image_floats)
         {
-            if (rb->d_image) cudaFree(rb->d_image);
+            rt_detail::pool_free(s->device, rb->d_image, rb->image_bytes);
             rb->d_image = NULL;
             rb->image_floats = 0;
-            RT_CUDA(cudaMalloc((void**)&rb->d_image, image_floats * sizeof(float)));
+            RT_CUDA(rt_detail::pool_alloc(s->device, (void**)&rb->d_image, image_floats * sizeof(float), &rb->image_bytes));
             rb->image_floats = image_floats;
         }
         d_image = rb->d_image;

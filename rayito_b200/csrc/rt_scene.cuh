@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "rt_device.cuh"
+#include "rt_pool.cuh"
 
 extern thread_local std::string g_rt_error;
 
@@ -30,6 +31,7 @@ struct RtScene
     int device;
     void* arena;                // one allocation holding every array below
     size_t arena_bytes;
+    size_t arena_alloc, work_alloc, cursor_alloc;   // real sizes of the pool blocks behind arena / d_work / d_cursor
     DScene d;                   // device pointers into the arena
     int stack_cap;              // traversal stack entries needed (both levels)
     int top_stack_need;         // ... by the top level alone
@@ -490,16 +492,17 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
     sc->scratch_in_bytes = sc->scratch_out_bytes = 0;
     sc->d_work = NULL;
     sc->d_cursor = NULL;
+    sc->arena_alloc = sc->work_alloc = sc->cursor_alloc = 0;
     sc->render = NULL;
     sc->dynamic_top = false;
 
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
-    cudaError_t err = cudaMalloc(&sc->arena, sc->arena_bytes);
-    if (err == cudaSuccess) err = cudaMalloc((void**)&sc->d_work, 4 * sizeof(uint64_t));
+    cudaError_t err = pool_alloc(device, &sc->arena, sc->arena_bytes, &sc->arena_alloc);
+    if (err == cudaSuccess) err = pool_alloc(device, (void**)&sc->d_work, 4 * sizeof(uint64_t), &sc->work_alloc);
     if (err == cudaSuccess) err = cudaMemset(sc->d_work, 0, 4 * sizeof(uint64_t));
-    if (err == cudaSuccess) err = cudaMalloc((void**)&sc->d_cursor, 64);
+    if (err == cudaSuccess) err = pool_alloc(device, (void**)&sc->d_cursor, 64, &sc->cursor_alloc);
     cudaEventRecord(e0, 0);
     if (err == cudaSuccess) err = cudaMemcpy(sc->arena, ab.bytes.data(), sc->arena_bytes, cudaMemcpyHostToDevice);
     cudaEventRecord(e1, 0);
@@ -510,9 +513,9 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
     cudaEventDestroy(e1);
     if (err != cudaSuccess)
     {
-        if (sc->arena) cudaFree(sc->arena);
-        if (sc->d_work) cudaFree(sc->d_work);
-        if (sc->d_cursor) cudaFree(sc->d_cursor);
+        pool_free(device, sc->arena, sc->arena_alloc);
+        pool_free(device, sc->d_work, sc->work_alloc);
+        pool_free(device, sc->d_cursor, sc->cursor_alloc);
         delete sc;
         return rt_cuda_fail(err, "scene upload");
     }

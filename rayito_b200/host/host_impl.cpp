@@ -166,10 +166,15 @@ Image* raytrace(ShapeSet& scene,
                 unsigned int lightSamplesHint,
                 unsigned int maxRayDepth)
 {
+    // RAYITO_B200_TIMING=1 prints where a raytrace() call spends its wall time (stderr)
+    const bool timing = std::getenv("RAYITO_B200_TIMING") != NULL;
+    struct timespec tp[6];
+    clock_gettime(CLOCK_MONOTONIC, &tp[0]);
     // Same order as the reference: lights first, then prepare (RaytraceMain.cpp:494-497)
     std::vector<Shape*> lights;
     scene.findLights(lights);
     scene.prepare();
+    clock_gettime(CLOCK_MONOTONIC, &tp[1]);
 
     rayito_b200::FlatScene flat;
     if (!scene.flattenScene(flat, lights))
@@ -182,8 +187,10 @@ Image* raytrace(ShapeSet& scene,
     const rayito_b200::RenderOptions& opt = rayito_b200::renderOptions();
     RtSceneDesc desc = flat.desc();
     RtScene* dev = NULL;
+    clock_gettime(CLOCK_MONOTONIC, &tp[2]);
     if (rt_scene_create(&desc, opt.device, &dev) != RT_OK)
         throw std::runtime_error(std::string("rayito_b200: rt_scene_create: ") + rt_last_error_string());
+    clock_gettime(CLOCK_MONOTONIC, &tp[3]);
 
     RtRenderParams params;
     std::memset(&params, 0, sizeof(params));
@@ -202,8 +209,19 @@ Image* raytrace(ShapeSet& scene,
     std::memset(image->data(), 0, width * height * 3 * sizeof(float));
     RtRenderStats stats;
     int rc = rt_render(dev, &camera, &params, image->data(), &stats);
+    clock_gettime(CLOCK_MONOTONIC, &tp[4]);
     std::string err = rc == RT_OK ? "" : rt_last_error_string();
     rt_scene_destroy(dev);
+    clock_gettime(CLOCK_MONOTONIC, &tp[5]);
+    if (timing)
+    {
+        double ms[5];
+        for (int i = 0; i < 5; ++i)
+            ms[i] = 1e3 * (double)(tp[i + 1].tv_sec - tp[i].tv_sec) + 1e-6 * (double)(tp[i + 1].tv_nsec - tp[i].tv_nsec);
+        std::fprintf(stderr, "[rayito_b200] raytrace: prepare %.1f ms, flatten %.1f, scene upload %.1f, rt_render %.1f "
+                             "(device %.1f, image download %.1f), destroy %.1f\n",
+                     ms[0], ms[1], ms[2], ms[3], stats.render_ms, stats.download_ms, ms[4]);
+    }
     if (rc != RT_OK)
     {
         delete image;
