@@ -68,10 +68,11 @@ WORKLOADS["c2"] = dict(stage23=3, width=512, height=512, sweep=C2_SWEEP,
 NCU_TRAFFIC = {
     1: dict(kernel="k_split_top_static<ANY=1,ShadowIO> (tabulated top-level pass of the shadow rays of one 16 Mi-sample batch)",
             bytes=1.840791e9 + 618.319616e6, ms=1.6, source="profiles/r01_v8_static_top_c4small_full_summary.csv",
-            note="mostly per-ray wavefront state (scattered 16-byte records), not scene data: the 3 MB scene is L1/L2-resident"),
+            note="captured with --batch 16777216 (per-launch bytes scale with the batch size); mostly per-ray wavefront "
+                 "state (records scattered by slot), not scene data: the 3 MB scene is L1/L2-resident"),
     5: dict(kernel="k_split_mesh<64,ANY=0,PathIO> (face-BVH pass of the path rays of one 16 Mi-sample batch)",
             bytes=4.922347e9 + 319.387904e6, ms=5.8, source="profiles/r01_v6_mesh_c5small_full_summary.csv",
-            note="random 32-byte node and 48-byte triangle gathers from a 660 MB scene, L2 hit 66 %"),
+            note="captured with --batch 16777216; random 32-byte node and 48-byte triangle gathers from a 660 MB scene, L2 hit 66 %"),
 }
 CAMERA_SPEC = {       # fov, origin, target, up, focal distance, lens radius, shutter open/close (GUI defaults)
     1: [30, -4, 5, 15, 0, 0, 0, 0, 1, 0, 16, 0, 0, 1],
@@ -461,7 +462,7 @@ def main():
                        "samples_per_step": samples_total, "rays_per_step": rays_total,
                        "rays_per_sample": rays_total / samples_total,
                        "msamples_per_s": samples_total * args.steps / (max_ms / 1e3) / 1e6,
-                       "l2": "256 MB flush buffer written between timed steps; per-batch path state (~2 GB) >> L2",
+                       "l2": "256 MB flush buffer written between timed steps; per-batch path state (tens of GB) >> L2",
                        "host_prepare_s": host_prepare_s, "render_ms_per_step_rank0": render_ms / args.steps},
             "clocks": clocks, "gpu_launches": int(launches_total), "roofline": roofline,
         }
