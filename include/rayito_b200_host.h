@@ -58,6 +58,22 @@ int rth_raytrace(int recipe, const char* obj_path, unsigned grid_u, unsigned gri
                  int device, unsigned rank, unsigned world, int count_work,
                  float* rgb, RtRenderStats* stats);
 
+/* The same split the way an application is written: the scene-building code runs once
+ * (rth_app_create: MainWindow.cpp:143-229 or another recipe; nothing is prepared or
+ * flattened), then every rth_app_raytrace() is one Rayito::raytrace() call on that scene
+ * -- findLights, prepare() (host BVH build), flatten, upload, render, download -- exactly
+ * what the reference redoes per call (RaytraceMain.cpp:494-497).  bench.py's e2e times this
+ * call.  rgb_on_device != 0: rgb is a DEVICE pointer (width*height*3 floats on `device`)
+ * and the call is rayito_b200::raytraceToDevice(): this rank's tiles stay in HBM for the
+ * application's tile-assembly collective. */
+typedef struct RthApp RthApp;
+RthApp* rth_app_create(int recipe, const char* obj_path, unsigned grid_u, unsigned grid_v);
+void rth_app_destroy(RthApp* app);
+int rth_app_raytrace(RthApp* app, const float* spec14, unsigned width, unsigned height,
+                     unsigned pixel_samples_hint, unsigned light_samples_hint, unsigned max_ray_depth,
+                     int device, unsigned rank, unsigned world, int count_work,
+                     float* rgb, int rgb_on_device, RtRenderStats* stats);
+
 /* Stage 1 program (Rayito_Stage1/main.cpp:65-135): builds its scene (one pink plane at
  * y = -2) and camera (fov 30 at the origin looking down +z) with makeCameraRay's basis
  * arithmetic (main.cpp:28-52), renders on the GPU and returns the P6 payload

@@ -82,7 +82,7 @@ def build_host(force=False):
         cmd = [HOST_CXX, "-O2", "-std=c++11", "-fPIC", "-shared", "-ffp-contract=off", "-Wall",
                "-I" + HOST, "-I" + INCLUDE,
                os.path.join(HOST, "host_impl.cpp"), "-o", HOST_LIB,
-               "-L" + CSRC, "-lrayito_b200", "-Wl,-rpath,$ORIGIN/../csrc", "-Wl,-Bsymbolic"]
+               "-L" + CSRC, "-lrayito_b200", "-pthread", "-Wl,-rpath,$ORIGIN/../csrc", "-Wl,-Bsymbolic"]
         _run(cmd)
     return HOST_LIB
 

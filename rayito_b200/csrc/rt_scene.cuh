@@ -7,9 +7,12 @@
 #ifndef RAYITO_B200_RT_SCENE_CUH
 #define RAYITO_B200_RT_SCENE_CUH
 
+#include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "rt_device.cuh"
@@ -99,17 +102,96 @@ inline int bvh_depth(const RtBvhNode* nodes, uint32_t count, uint32_t num_prims,
     return deepest;
 }
 
+// Host worker threads for the upload path (same switch as the host library:
+// RAYITO_B200_HOST_THREADS, else the hardware concurrency, at most 32)
+inline unsigned host_threads()
+{
+    const char* env = std::getenv("RAYITO_B200_HOST_THREADS");
+    if (env != NULL)
+    {
+        long n = std::strtol(env, NULL, 10);
+        if (n >= 1)
+            return n > 256 ? 256u : (unsigned)n;
+    }
+    unsigned n = std::thread::hardware_concurrency();
+    if (n == 0) n = 1;
+    return n > 32 ? 32u : n;
+}
+
+// body(begin, end) over contiguous pieces of [0, n); pieces of at least `grain` items
+template <typename Body>
+inline void parallel_ranges(size_t n, size_t grain, Body body)
+{
+    size_t pieces = grain ? (n + grain - 1) / grain : 1;
+    unsigned threads = host_threads();
+    if (pieces > threads) pieces = threads;
+    if (pieces <= 1)
+    {
+        body((size_t)0, n);
+        return;
+    }
+    std::vector<std::thread> workers;
+    workers.reserve(pieces - 1);
+    for (size_t c = 1; c < pieces; ++c)
+        workers.push_back(std::thread(body, n * c / pieces, n * (c + 1) / pieces));
+    body((size_t)0, n / pieces);
+    for (size_t i = 0; i < workers.size(); ++i)
+        workers[i].join();
+}
+
+// Lays the scene arrays out in one block (256-byte aligned each).  Arrays are first
+// declared -- put() for data that exists, reserve() for records the caller builds in
+// place -- then finish() allocates the block once and copies the declared data, the
+// large arrays piecewise on the worker threads.  No array is staged twice and nothing
+// is zero-filled first: at 10 M triangles the block is 660 MB.
 struct ArenaBuilder
 {
-    std::vector<unsigned char> bytes;
-    // Append an array, 256-byte aligned; returns its offset
-    size_t put(const void* src, size_t n)
+    struct Segment { size_t offset; const void* src; size_t bytes; };
+    std::vector<Segment> segments;
+    size_t total;
+    unsigned char* block;
+
+    ArenaBuilder() : total(0), block(NULL) { }
+
+    size_t reserve(size_t n)
     {
-        size_t off = (bytes.size() + 255) & ~(size_t)255;
-        bytes.resize(off + (n ? n : 16));
-        if (n) std::memcpy(&bytes[off], src, n);
+        size_t off = (total + 255) & ~(size_t)255;
+        Segment seg = { off, NULL, n ? n : 16 };
+        segments.push_back(seg);
+        total = off + seg.bytes;
         return off;
     }
+    // `src` must stay valid until finish()
+    size_t put(const void* src, size_t n)
+    {
+        size_t off = reserve(n);
+        if (n) segments.back().src = src;
+        return off;
+    }
+    // `storage`: at least `total` bytes, owned by the caller
+    bool finish(void* storage)
+    {
+        block = static_cast<unsigned char*>(storage);
+        if (block == NULL)
+            return false;
+        size_t end = 0;
+        for (size_t i = 0; i < segments.size(); ++i)
+        {
+            const Segment& seg = segments[i];
+            std::memset(block + end, 0, seg.offset - end);      // alignment gap
+            end = seg.offset + seg.bytes;
+            if (seg.src == NULL)
+            {
+                if (seg.bytes <= 16) std::memset(block + seg.offset, 0, seg.bytes);
+                continue;
+            }
+            unsigned char* dst = block + seg.offset;
+            const unsigned char* src = static_cast<const unsigned char*>(seg.src);
+            parallel_ranges(seg.bytes, (size_t)8 << 20, [dst, src](size_t b, size_t e) { std::memcpy(dst + b, src + b, e - b); });
+        }
+        return true;
+    }
+    template <typename V> V* at(size_t offset) { return reinterpret_cast<V*>(block + offset); }
 };
 
 inline float vlen(const float* v) { return std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
@@ -239,10 +321,7 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
         face_first_tri[f + 1] = face_first_tri[f] + (n - 2);
     }
     const uint32_t num_tris = face_first_tri[desc->num_faces];
-    std::vector<float4> tris((size_t)num_tris * 3);
-    std::vector<uint4> tri_normals(num_tris);
     std::vector<DMesh> meshes(desc->num_meshes);
-    std::vector<DNode> mesh_nodes(desc->num_mesh_nodes);
     for (uint32_t m = 0; m < desc->num_meshes; ++m)
     {
         const RtMesh& mesh = desc->meshes[m];
@@ -256,55 +335,6 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
         dm.total_area = mesh.total_area;
         dm.pad = 0;
         meshes[m] = dm;
-        for (uint32_t f = 0; f < mesh.num_faces; ++f)
-        {
-            uint32_t gf = mesh.first_face + f;
-            uint32_t start = desc->face_start[gf];
-            uint32_t n = desc->face_start[gf + 1] - start;
-            bool has_n = desc->face_has_normals[gf] != 0;
-            for (uint32_t k = 0; k + 2 < n; ++k)
-            {
-                uint32_t vi[3] = { desc->vertex_index[start], desc->vertex_index[start + k + 1], desc->vertex_index[start + k + 2] };
-                uint32_t rec = face_first_tri[gf] + k;
-                uint32_t words[3] = { f, k, has_n ? 1u : 0u };
-                for (int c = 0; c < 3; ++c)
-                {
-                    if (vi[c] >= mesh.num_vertices)
-                        return rt_fail(RT_ERR_ARG, "vertex index out of range");
-                    const float* v = desc->vertices + 3 * (size_t)(mesh.first_vertex + vi[c]);
-                    float w;
-                    std::memcpy(&w, &words[c], 4);
-                    tris[(size_t)rec * 3 + c] = make_float4(v[0], v[1], v[2], w);
-                }
-                uint4 ni = make_uint4(0, 0, 0, 0);
-                if (has_n)
-                {
-                    uint32_t a = desc->normal_index[start], b = desc->normal_index[start + k + 1], c = desc->normal_index[start + k + 2];
-                    if (a >= mesh.num_normals || b >= mesh.num_normals || c >= mesh.num_normals)
-                        return rt_fail(RT_ERR_ARG, "normal index out of range");
-                    ni = make_uint4(mesh.first_normal + a, mesh.first_normal + b, mesh.first_normal + c, 0);
-                }
-                tri_normals[rec] = ni;
-            }
-        }
-        for (uint32_t i = 0; i < mesh.num_nodes; ++i)
-        {
-            const RtBvhNode& n = desc->mesh_nodes[mesh.first_node + i];
-            uint32_t word = n.first_child_or_prim, flags = n.flags;
-            if (flags & RT_NODE_LEAF)
-            {
-                uint32_t gf = mesh.first_face + n.first_child_or_prim;
-                word = face_first_tri[gf];
-                flags = RT_NODE_LEAF | ((face_first_tri[gf + 1] - face_first_tri[gf]) << 3);
-            }
-            float wf, ff;
-            std::memcpy(&wf, &word, 4);
-            std::memcpy(&ff, &flags, 4);
-            DNode dn;
-            dn.q0 = make_float4(n.bbox_min[0], n.bbox_min[1], n.bbox_min[2], n.bbox_max[0]);
-            dn.q1 = make_float4(n.bbox_max[1], n.bbox_max[2], wf, ff);
-            mesh_nodes[mesh.first_node + i] = dn;
-        }
     }
     std::vector<DNode> top_nodes(desc->num_top_nodes);
     for (uint32_t i = 0; i < desc->num_top_nodes; ++i)
@@ -442,13 +472,13 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
         xforms[i].pad = 0;
     }
 
-    // One arena, one copy
+    // One arena, one copy to the device
     ArenaBuilder ab;
     size_t o_shapes = ab.put(shapes.data(), shapes.size() * sizeof(DShapeMem));
     size_t o_top = ab.put(top_nodes.data(), top_nodes.size() * sizeof(DNode));
-    size_t o_mnodes = ab.put(mesh_nodes.data(), mesh_nodes.size() * sizeof(DNode));
-    size_t o_tris = ab.put(tris.data(), tris.size() * sizeof(float4));
-    size_t o_trin = ab.put(tri_normals.data(), tri_normals.size() * sizeof(uint4));
+    size_t o_mnodes = ab.reserve((size_t)desc->num_mesh_nodes * sizeof(DNode));     // built in place below
+    size_t o_tris = ab.reserve((size_t)num_tris * 3 * sizeof(float4));
+    size_t o_trin = ab.reserve((size_t)num_tris * sizeof(uint4));
     size_t o_fft = ab.put(face_first_tri.data(), face_first_tri.size() * sizeof(uint32_t));
     size_t o_normals = ab.put(desc->normals, (size_t)desc->num_normals * 12);
     size_t o_xforms = ab.put(xforms.data(), xforms.size() * sizeof(DXform));
@@ -475,10 +505,90 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
         return rt_fail(RT_ERR_ARG, "device ordinal out of range");
     RT_CUDA(cudaSetDevice(device));
 
+    // The staging block is shared by all callers: held until the copy has left it
+    std::lock_guard<std::mutex> stage_guard(stage_lock());
+    if (!ab.finish(stage_acquire_locked(ab.total ? ab.total : 16)))
+        return rt_fail(RT_ERR_ARG, "out of host memory staging the scene");
+
+    // Fan-triangle records and device nodes of every mesh, written straight into the
+    // staging block by the worker threads (faces and nodes are independent of each other)
+    {
+        float4* tris = ab.at<float4>(o_tris);
+        uint4* tri_normals = ab.at<uint4>(o_trin);
+        DNode* mesh_nodes = ab.at<DNode>(o_mnodes);
+        const uint32_t* fft = face_first_tri.data();
+        std::atomic<int> bad(0);
+        for (uint32_t m = 0; m < desc->num_meshes; ++m)
+        {
+            const RtMesh mesh = desc->meshes[m];
+            parallel_ranges(mesh.num_faces, 1u << 14, [=, &bad](size_t fb, size_t fe) {
+                for (size_t f = fb; f < fe; ++f)
+                {
+                    uint32_t gf = mesh.first_face + (uint32_t)f;
+                    uint32_t start = desc->face_start[gf];
+                    uint32_t n = desc->face_start[gf + 1] - start;
+                    bool has_n = desc->face_has_normals[gf] != 0;
+                    for (uint32_t k = 0; k + 2 < n; ++k)
+                    {
+                        uint32_t vi[3] = { desc->vertex_index[start], desc->vertex_index[start + k + 1], desc->vertex_index[start + k + 2] };
+                        uint32_t rec = fft[gf] + k;
+                        uint32_t words[3] = { (uint32_t)f, k, has_n ? 1u : 0u };
+                        for (int c = 0; c < 3; ++c)
+                        {
+                            if (vi[c] >= mesh.num_vertices)
+                            {
+                                bad.store(1);
+                                return;
+                            }
+                            const float* v = desc->vertices + 3 * (size_t)(mesh.first_vertex + vi[c]);
+                            float w;
+                            std::memcpy(&w, &words[c], 4);
+                            tris[(size_t)rec * 3 + c] = make_float4(v[0], v[1], v[2], w);
+                        }
+                        uint4 ni = make_uint4(0, 0, 0, 0);
+                        if (has_n)
+                        {
+                            uint32_t a = desc->normal_index[start], b = desc->normal_index[start + k + 1], c = desc->normal_index[start + k + 2];
+                            if (a >= mesh.num_normals || b >= mesh.num_normals || c >= mesh.num_normals)
+                            {
+                                bad.store(2);
+                                return;
+                            }
+                            ni = make_uint4(mesh.first_normal + a, mesh.first_normal + b, mesh.first_normal + c, 0);
+                        }
+                        tri_normals[rec] = ni;
+                    }
+                }
+            });
+            parallel_ranges(mesh.num_nodes, 1u << 15, [=](size_t nb, size_t ne) {
+                for (size_t i = nb; i < ne; ++i)
+                {
+                    const RtBvhNode& n = desc->mesh_nodes[mesh.first_node + i];
+                    uint32_t word = n.first_child_or_prim, flags = n.flags;
+                    if (flags & RT_NODE_LEAF)
+                    {
+                        uint32_t gf = mesh.first_face + n.first_child_or_prim;
+                        word = fft[gf];
+                        flags = RT_NODE_LEAF | ((fft[gf + 1] - fft[gf]) << 3);
+                    }
+                    float wf, ff;
+                    std::memcpy(&wf, &word, 4);
+                    std::memcpy(&ff, &flags, 4);
+                    DNode dn;
+                    dn.q0 = make_float4(n.bbox_min[0], n.bbox_min[1], n.bbox_min[2], n.bbox_max[0]);
+                    dn.q1 = make_float4(n.bbox_max[1], n.bbox_max[2], wf, ff);
+                    mesh_nodes[mesh.first_node + i] = dn;
+                }
+            });
+        }
+        if (bad.load() != 0)
+            return rt_fail(RT_ERR_ARG, bad.load() == 1 ? "vertex index out of range" : "normal index out of range");
+    }
+
     RtScene* sc = new RtScene();
     sc->device = device;
     sc->arena = NULL;
-    sc->arena_bytes = ab.bytes.size();
+    sc->arena_bytes = ab.total;
     sc->stack_cap = stack_cap;
     sc->top_stack_need = desc->num_top_nodes ? top_depth + 1 : (int)desc->num_finite;
     sc->mesh_stack_need = mesh_depth >= 0 ? mesh_depth + 1 : 0;
@@ -504,7 +614,7 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
     if (err == cudaSuccess) err = cudaMemset(sc->d_work, 0, 4 * sizeof(uint64_t));
     if (err == cudaSuccess) err = pool_alloc(device, (void**)&sc->d_cursor, 64, &sc->cursor_alloc);
     cudaEventRecord(e0, 0);
-    if (err == cudaSuccess) err = cudaMemcpy(sc->arena, ab.bytes.data(), sc->arena_bytes, cudaMemcpyHostToDevice);
+    if (err == cudaSuccess) err = cudaMemcpy(sc->arena, ab.block, sc->arena_bytes, cudaMemcpyHostToDevice);
     cudaEventRecord(e1, 0);
     cudaEventSynchronize(e1);
     sc->upload_ms = 0.0f;

@@ -158,13 +158,16 @@ Mesh* createFromOBJFile(const char* filename)
 }
 
 
-Image* raytrace(ShapeSet& scene,
-                const Camera& cam,
-                size_t width,
-                size_t height,
-                unsigned int pixelSamplesHint,
-                unsigned int lightSamplesHint,
-                unsigned int maxRayDepth)
+// Body of raytrace().  deviceImage == NULL: the reference's contract, a new host Image.
+// Otherwise the pixels of this rank's tiles are left in device memory (returns NULL).
+static Image* raytraceImpl(ShapeSet& scene,
+                           const Camera& cam,
+                           size_t width,
+                           size_t height,
+                           unsigned int pixelSamplesHint,
+                           unsigned int lightSamplesHint,
+                           unsigned int maxRayDepth,
+                           float* deviceImage)
 {
     // RAYITO_B200_TIMING=1 prints where a raytrace() call spends its wall time (stderr)
     const bool timing = std::getenv("RAYITO_B200_TIMING") != NULL;
@@ -176,7 +179,8 @@ Image* raytrace(ShapeSet& scene,
     scene.prepare();
     clock_gettime(CLOCK_MONOTONIC, &tp[1]);
 
-    rayito_b200::FlatScene flat;
+    rayito_b200::FlatScene& flat = rayito_b200::detail_flatCache();
+    flat.reset();
     if (!scene.flattenScene(flat, lights))
         throw std::runtime_error("rayito_b200: cannot flatten scene: " + flat.error);
     flat.semantics = rayito_b200::stageSemantics();
@@ -205,10 +209,16 @@ Image* raytrace(ShapeSet& scene,
     params.max_batch_samples = opt.maxBatchSamples;
     params.flags = opt.countWork ? RT_RENDER_COUNT_WORK : 0;
 
-    Image* image = new Image(width, height);
-    std::memset(image->data(), 0, width * height * 3 * sizeof(float));
+    Image* image = NULL;
     RtRenderStats stats;
-    int rc = rt_render(dev, &camera, &params, image->data(), &stats);
+    int rc;
+    if (deviceImage != NULL)
+        rc = rt_render_device(dev, &camera, &params, deviceImage, &stats, NULL);
+    else
+    {
+        image = new Image(width, height);   // Color() is black: other ranks' tiles stay black
+        rc = rt_render(dev, &camera, &params, image->data(), &stats);
+    }
     clock_gettime(CLOCK_MONOTONIC, &tp[4]);
     std::string err = rc == RT_OK ? "" : rt_last_error_string();
     rt_scene_destroy(dev);
@@ -231,11 +241,48 @@ Image* raytrace(ShapeSet& scene,
     return image;
 }
 
+Image* raytrace(ShapeSet& scene,
+                const Camera& cam,
+                size_t width,
+                size_t height,
+                unsigned int pixelSamplesHint,
+                unsigned int lightSamplesHint,
+                unsigned int maxRayDepth)
+{
+    return raytraceImpl(scene, cam, width, height, pixelSamplesHint, lightSamplesHint, maxRayDepth, NULL);
+}
+
 } // namespace Rayito
 
 
 namespace rayito_b200
 {
+
+void raytraceToDevice(Rayito::ShapeSet& scene,
+                      const Rayito::Camera& cam,
+                      size_t width,
+                      size_t height,
+                      unsigned int pixelSamplesHint,
+                      unsigned int lightSamplesHint,
+                      unsigned int maxRayDepth,
+                      float* deviceImage)
+{
+    if (deviceImage == NULL)
+        throw std::runtime_error("rayito_b200: raytraceToDevice needs a device buffer");
+    Rayito::raytraceImpl(scene, cam, width, height, pixelSamplesHint, lightSamplesHint, maxRayDepth, deviceImage);
+}
+
+FlatScene& detail_flatCache()
+{
+    static thread_local FlatScene cache;
+    return cache;
+}
+
+void releaseHostCaches()
+{
+    detail_flatCache().shrink();
+    buildScratch().release();
+}
 
 unsigned& stageSemantics()
 {
@@ -274,6 +321,14 @@ struct RthScene
     double prepareSeconds;
 };
 
+// An application's scene as its scene-building code leaves it: NOT prepared, NOT flattened
+struct RthApp
+{
+    Rayito::ShapeSet set;
+    rayito_recipes::SceneStore store;
+    unsigned semantics;
+};
+
 namespace
 {
 thread_local std::string t_hostError;
@@ -306,6 +361,13 @@ RthScene* finish(RthScene* s, bool built)
         t_hostError = "flatten failed: " + s->flat.error;
         delete s;
         return NULL;
+    }
+    if (std::getenv("RAYITO_B200_TIMING") != NULL)
+    {
+        struct timespec c;
+        clock_gettime(CLOCK_MONOTONIC, &c);
+        std::fprintf(stderr, "[rayito_b200] rth_scene_create: prepare %.1f ms, flatten %.1f ms\n", 1e3 * s->prepareSeconds,
+                     1e3 * (double)(c.tv_sec - b.tv_sec) + 1e-6 * (double)(c.tv_nsec - b.tv_nsec));
     }
     s->desc = s->flat.desc();
     return s;
@@ -430,6 +492,76 @@ int rth_raytrace(int recipe, const char* obj_path, unsigned grid_u, unsigned gri
         Rayito::Image* image = Rayito::raytrace(set, cam, width, height, ps, ls, depth);
         std::memcpy(rgb, image->data(), (size_t)width * height * 3 * sizeof(float));
         delete image;
+        if (stats) *stats = rayito_b200::lastStats();
+        return 0;
+    }
+    catch (const std::exception& e)
+    {
+        t_hostError = e.what();
+        return -1;
+    }
+}
+
+RthApp* rth_app_create(int recipe, const char* obj_path, unsigned grid_u, unsigned grid_v)
+{
+    RthApp* app = new RthApp();
+    app->semantics = recipe == RTH_RECIPE_STAGE6_SCENE ? RT_SEMANTICS_STAGE6 : RT_SEMANTICS_STAGE7;
+    StageScope stage(app->semantics);
+    bool built = false;
+    const char* obj = obj_path ? obj_path : "";
+    switch (recipe)
+    {
+    case RTH_RECIPE_STAGE6_SCENE: built = rayito_recipes::buildStage6Scene(app->set, app->store, obj); break;
+    case RTH_RECIPE_STAGE7_SCENE1: built = rayito_recipes::buildStage7Scene1(app->set, app->store, obj); break;
+    case RTH_RECIPE_STAGE7_SCENE1_MESHLIGHT: built = rayito_recipes::buildStage7Scene1(app->set, app->store, obj, true); break;
+    case RTH_RECIPE_STAGE7_SCENE2: built = rayito_recipes::buildStage7Scene2(app->set, app->store); break;
+    case RTH_RECIPE_SYNTHETIC_MESH: built = rayito_recipes::buildSyntheticMeshScene(app->set, app->store, grid_u, grid_v); break;
+    case RTH_RECIPE_EDGE_LINEAR_LIST: case RTH_RECIPE_EDGE_NO_LIGHTS: case RTH_RECIPE_EDGE_EMPTY:
+        built = rayito_recipes::buildEdgeScene(app->set, app->store, recipe - RTH_RECIPE_EDGE_LINEAR_LIST); break;
+    default: break;
+    }
+    if (!built)
+    {
+        t_hostError = "scene recipe failed (unknown recipe, or the OBJ mesh could not be read)";
+        delete app;
+        return NULL;
+    }
+    return app;
+}
+
+void rth_app_destroy(RthApp* app) { delete app; }
+
+int rth_app_raytrace(RthApp* app, const float* spec14, unsigned width, unsigned height,
+                     unsigned ps, unsigned ls, unsigned depth,
+                     int device, unsigned rank, unsigned world, int count_work,
+                     float* rgb, int rgb_on_device, RtRenderStats* stats)
+{
+    if (app == NULL || spec14 == NULL || rgb == NULL)
+    {
+        t_hostError = "null argument";
+        return -1;
+    }
+    try
+    {
+        StageScope stage(app->semantics);
+        Rayito::PerspectiveCamera cam(spec14[0],
+                                      Rayito::Point(spec14[1], spec14[2], spec14[3]),
+                                      Rayito::Point(spec14[4], spec14[5], spec14[6]),
+                                      Rayito::Point(spec14[7], spec14[8], spec14[9]),
+                                      spec14[10], spec14[11], spec14[12], spec14[13]);
+        rayito_b200::RenderOptions& opt = rayito_b200::renderOptions();
+        opt.device = device;
+        opt.rank = rank;
+        opt.world = world ? world : 1;
+        opt.countWork = count_work != 0;
+        if (rgb_on_device)
+            rayito_b200::raytraceToDevice(app->set, cam, width, height, ps, ls, depth, rgb);
+        else
+        {
+            Rayito::Image* image = Rayito::raytrace(app->set, cam, width, height, ps, ls, depth);
+            std::memcpy(rgb, image->data(), (size_t)width * height * 3 * sizeof(float));
+            delete image;
+        }
         if (stats) *stats = rayito_b200::lastStats();
         return 0;
     }

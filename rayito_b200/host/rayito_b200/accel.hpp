@@ -9,10 +9,14 @@
 #define RAYITO_B200_ACCEL_HPP
 
 #include <algorithm>
+#include <cstdlib>
 #include <limits>
+#include <new>
+#include <mutex>
 #include <vector>
 
 #include "math.hpp"
+#include "parallel.hpp"
 
 namespace Rayito
 {
@@ -147,90 +151,100 @@ public:
 
     // rootBox: box of the root node when it is not the union of the element boxes
     // (Stage 6 passes m_object.bbox(), S6 RAccel.h:259; Stage 7 the union, RAccel.h:284)
+    //
+    // Node numbering follows the reference's recursion (RAccel.h:366-371): a node takes
+    // the next two free slots for its children, then its left subtree is built completely
+    // before its right subtree.  With one element per leaf a subtree over n elements
+    // always has 2n-1 nodes, so the slots are known before anything below is built:
+    // if a node's first free slot is `base` and its left side gets nL elements, the
+    // children sit at base and base+1, the left child's descendants start at base+2
+    // and the right child's at base+2nL.  Subtrees therefore build independently -- on
+    // worker threads for large meshes -- and land exactly where the serial recursion
+    // puts them; std::partition runs on disjoint ranges, so element order is untouched.
     bool build(const BBox* rootBox = NULL)
     {
-        m_nodes.clear();
         m_maxDepth = 0;
         unsigned int count = m_object.numElements();
         if (count == 0)
+        {
+            m_nodes.release();
             return true;
+        }
 
-        std::vector<Item> items(count);
+        // Uninitialised per-thread scratch, kept between builds (rayito_b200::buildScratch)
+        Item* items = static_cast<Item*>(rayito_b200::buildScratch().get((size_t)count * sizeof(Item)));
+        if (items == NULL)
+            throw std::bad_alloc();
         BBox whole;
-        for (unsigned int i = 0; i < count; ++i)
+        const unsigned int threads = count >= kParallelElements ? rayito_b200::hostThreads() : 1u;
         {
-            items[i].prim = i;
-            items[i].box = m_object.elementBBox(i);
-            whole = whole.combined(items[i].box);
+            // Element boxes; the union keeps the serial left-to-right association
+            // (std::min/max keep their first argument on ties, e.g. -0 against +0)
+            unsigned int chunks = threads > 1 ? rayito_b200::chunkCount(count, kParallelElements / 4) : 1u;
+            std::vector<BBox> partial(chunks);
+            T& object = m_object;
+            Item* out = items;
+            BBox* part = &partial[0];
+            rayito_b200::parallelChunks(count, chunks, [&object, out, part](unsigned c, size_t b, size_t e) {
+                BBox acc;
+                for (size_t i = b; i < e; ++i)
+                {
+                    out[i].prim = (unsigned int)i;
+                    out[i].box = object.elementBBox((unsigned int)i);
+                    acc = acc.combined(out[i].box);
+                }
+                part[c] = acc;
+            });
+            for (unsigned int c = 0; c < chunks; ++c)
+                whole = whole.combined(partial[c]);
         }
-        m_nodes.resize((size_t)count * 2 - 1);
-        m_used = 1;
-        // Depth-first with an explicit work list instead of recursion (degenerate
-        // inputs can be ~N deep); children are still numbered in the reference's
-        // pre-order: a node reserves both child slots, then its left subtree is
-        // built completely before its right subtree (RAccel.h:366-371).
-        std::vector<Job> jobs;
-        Job root = { 0, count, 0, 0, rootBox ? *rootBox : whole };
-        jobs.push_back(root);
-        while (!jobs.empty())
-        {
-            Job job = jobs.back();
-            jobs.pop_back();
-            if (job.depth > m_maxDepth)
-                m_maxDepth = job.depth;
-            BvhNode& node = m_nodes[job.node];
-            node.m_bbox = job.box;
-            if (job.end - job.begin <= 1)
-            {
-                node.m_flags = kLeafNode;
-                node.m_prim = items[job.begin].prim;
-                continue;
-            }
+        m_nodes.allocate((size_t)count * 2 - 1);
 
-            Vector extent = job.box.m_max - job.box.m_min;
-            BvhNodeFlags axis;
-            if (extent.m_x > extent.m_y)
-                axis = extent.m_x > extent.m_z ? kSplitX : kSplitZ;
-            else
-                axis = extent.m_y > extent.m_z ? kSplitY : kSplitZ;
-            float where = (component(job.box.m_max, axis) + component(job.box.m_min, axis)) * 0.5f;
-            node.m_flags = axis;
-
-            Item* first = &items[0];
-            Item* cut = std::partition(first + job.begin, first + job.end, AboveSplit(where, axis));
-            unsigned int mid = (unsigned int)(cut - first);
-            if (mid <= job.begin || mid >= job.end)
-            {
-                mid = job.begin + (job.end - job.begin) / 2;
-                if (mid < job.begin + 1) mid = job.begin + 1;
-                else if (mid > job.end - 1) mid = job.end - 1;
-            }
-
-            BBox leftBox, rightBox;
-            for (unsigned int i = job.begin; i < mid; ++i) leftBox = leftBox.combined(items[i].box);
-            for (unsigned int i = mid; i < job.end; ++i) rightBox = rightBox.combined(items[i].box);
-
-            // In the reference the right child's subtree gets its node numbers only
-            // after the whole left subtree; numbering therefore cannot be assigned
-            // when the job is queued.  Instead the right job is queued first (so it
-            // runs after the left subtree) and takes its children's slots then.
-            // Both children of THIS node, however, are reserved right now.
-            node.m_firstChild = m_used;
-            m_used += 2;
-            Job right = { mid, job.end, node.m_firstChild + 1, job.depth + 1, rightBox };
-            Job left = { job.begin, mid, node.m_firstChild, job.depth + 1, leftBox };
-            jobs.push_back(right);
-            jobs.push_back(left);
-        }
+        Job root = { 0, count, 0, 1, 0, rootBox ? *rootBox : whole };
+        rayito_b200::JobBag<Job> bag;
+        bag.add(root);
+        std::mutex depthMutex;
+        Builder builder = { items, &m_nodes[0], threads > 1 ? kSpawnElements : 0u, &m_maxDepth, &depthMutex };
+        bag.drain(threads, builder);
         return true;
     }
 
-    const BvhNode* nodes() const { return m_nodes.empty() ? NULL : &m_nodes[0]; }
+    const BvhNode* nodes() const { return m_nodes.size() == 0 ? NULL : &m_nodes[0]; }
     unsigned int numNodes() const { return (unsigned int)m_nodes.size(); }
     // Depth of the deepest leaf (root = 0); the traversal stack needs depth + 1
     unsigned int maxDepth() const { return m_maxDepth; }
 
 private:
+    // malloc'ed array whose elements are written before they are read (every slot of a
+    // finished build is); no constructor pass over hundreds of megabytes
+    template <typename V>
+    class RawArray
+    {
+    public:
+        RawArray() : m_data(NULL), m_size(0) { }
+        explicit RawArray(size_t n) : m_data(NULL), m_size(0) { allocate(n); }
+        ~RawArray() { release(); }
+        void allocate(size_t n)
+        {
+            if (n == m_size && m_data != NULL)
+                return;             // a re-prepare() of the same mesh rewrites every slot
+            release();
+            m_data = n ? static_cast<V*>(std::malloc(n * sizeof(V))) : NULL;
+            if (n && m_data == NULL)
+                throw std::bad_alloc();
+            m_size = n;
+        }
+        void release() { std::free(m_data); m_data = NULL; m_size = 0; }
+        size_t size() const { return m_size; }
+        V& operator[](size_t i) { return m_data[i]; }
+        const V& operator[](size_t i) const { return m_data[i]; }
+    private:
+        RawArray(const RawArray&);
+        RawArray& operator=(const RawArray&);
+        V* m_data;
+        size_t m_size;
+    };
+
     struct Item
     {
         unsigned int prim;
@@ -238,8 +252,82 @@ private:
     };
     struct Job
     {
-        unsigned int begin, end, node, depth;
+        unsigned int begin, end;    // element range
+        unsigned int node;          // slot of this subtree's root
+        unsigned int base;          // first slot of its descendants
+        unsigned int depth;
         BBox box;
+    };
+    // Below this many elements a build stays on the calling thread
+    static const unsigned int kParallelElements = 1u << 16;
+    // Subtrees at least this large are handed to the job bag instead of the local stack
+    static const unsigned int kSpawnElements = 1u << 13;
+
+    // Builds one subtree depth-first with an explicit work list instead of recursion
+    // (degenerate inputs can be ~N deep).
+    struct Builder
+    {
+        Item* items;
+        BvhNode* nodes;
+        unsigned int spawnElements;     // 0: never hand subtrees to other workers
+        unsigned int* maxDepth;
+        std::mutex* depthMutex;
+
+        void operator()(const Job& start, rayito_b200::JobBag<Job>& bag) const
+        {
+            unsigned int deepest = 0;
+            std::vector<Job> jobs;
+            jobs.push_back(start);
+            while (!jobs.empty())
+            {
+                Job job = jobs.back();
+                jobs.pop_back();
+                if (job.depth > deepest)
+                    deepest = job.depth;
+                BvhNode& node = nodes[job.node];
+                node.m_bbox = job.box;
+                if (job.end - job.begin <= 1)
+                {
+                    node.m_flags = kLeafNode;
+                    node.m_prim = items[job.begin].prim;
+                    continue;
+                }
+
+                Vector extent = job.box.m_max - job.box.m_min;
+                BvhNodeFlags axis;
+                if (extent.m_x > extent.m_y)
+                    axis = extent.m_x > extent.m_z ? kSplitX : kSplitZ;
+                else
+                    axis = extent.m_y > extent.m_z ? kSplitY : kSplitZ;
+                float where = (component(job.box.m_max, axis) + component(job.box.m_min, axis)) * 0.5f;
+                node.m_flags = axis;
+
+                Item* cut = std::partition(items + job.begin, items + job.end, AboveSplit(where, axis));
+                unsigned int mid = (unsigned int)(cut - items);
+                if (mid <= job.begin || mid >= job.end)
+                {
+                    mid = job.begin + (job.end - job.begin) / 2;
+                    if (mid < job.begin + 1) mid = job.begin + 1;
+                    else if (mid > job.end - 1) mid = job.end - 1;
+                }
+
+                BBox leftBox, rightBox;
+                for (unsigned int i = job.begin; i < mid; ++i) leftBox = leftBox.combined(items[i].box);
+                for (unsigned int i = mid; i < job.end; ++i) rightBox = rightBox.combined(items[i].box);
+
+                node.m_firstChild = job.base;
+                Job left = { job.begin, mid, job.base, job.base + 2, job.depth + 1, leftBox };
+                Job right = { mid, job.end, job.base + 1, job.base + 2 * (mid - job.begin), job.depth + 1, rightBox };
+                if (spawnElements != 0 && right.end - right.begin >= spawnElements)
+                    bag.add(right);
+                else
+                    jobs.push_back(right);
+                jobs.push_back(left);
+            }
+            std::lock_guard<std::mutex> lock(*depthMutex);
+            if (deepest > *maxDepth)
+                *maxDepth = deepest;
+        }
     };
     // RAccel.h:226-240
     struct AboveSplit
@@ -259,8 +347,7 @@ private:
     }
 
     T& m_object;
-    std::vector<BvhNode> m_nodes;
-    unsigned int m_used;
+    RawArray<BvhNode> m_nodes;
     unsigned int m_maxDepth;
 };
 

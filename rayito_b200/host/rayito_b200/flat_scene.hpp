@@ -54,6 +54,26 @@ struct FlatScene
 
     FlatScene() : setXform(0), numFinite(0), numInfinite(0), topDepth(0), semantics(RT_SEMANTICS_STAGE7) { }
 
+    // Empty the scene but keep the arrays' storage: raytrace() flattens into one
+    // per-thread FlatScene so that a large scene's ~GB of tables is not handed back to
+    // the OS and page-faulted in again on every call.
+    void reset()
+    {
+        setXform = 0; numFinite = 0; numInfinite = 0; topDepth = 0;
+        shapes.clear(); topNodes.clear();
+        xforms.clear(); keyTime.clear(); keyScale.clear(); keyRotation.clear(); keyTranslation.clear();
+        planes.clear(); spheres.clear(); rects.clear(); meshes.clear(); meshDepth.clear();
+        vertices.clear(); normals.clear();
+        faceStart.clear(); faceHasNormals.clear(); vertexIndex.clear(); normalIndex.clear();
+        meshNodes.clear(); faceAreaCdf.clear();
+        materials.clear(); lights.clear();
+        semantics = RT_SEMANTICS_STAGE7;
+        error.clear();
+        m_materialIndex.clear();
+    }
+    // Give the storage back (rayito_b200::releaseHostCaches)
+    void shrink() { FlatScene empty; std::swap(*this, empty); }
+
     unsigned addXform(const Rayito::Transform& t)
     {
         RtXform x;

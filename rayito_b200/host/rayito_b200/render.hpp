@@ -146,6 +146,28 @@ struct RenderOptions
 };
 
 RenderOptions& renderOptions();
+
+// raytrace() for a multi-GPU application: same preparation, same render of this rank's
+// screen tiles (renderOptions().rank / .world), but the float image stays in DEVICE memory:
+// deviceImage is width*height*3 floats on renderOptions().device, rows top-down like
+// Image::pixel; pixels of other ranks' tiles are left untouched (zero the buffer first).
+// The application then assembles the frame with one collective over the device buffers
+// (every pixel has exactly one contributing rank, so a sum-reduce is exact) and downloads
+// once, instead of every rank staging a full frame through host memory.  INTEGRATION.md.
+void raytraceToDevice(Rayito::ShapeSet& scene,
+                      const Rayito::Camera& cam,
+                      size_t width,
+                      size_t height,
+                      unsigned int pixelSamplesHint,
+                      unsigned int lightSamplesHint,
+                      unsigned int maxRayDepth,
+                      float* deviceImage);
+// raytrace() keeps its host-side working storage (the flattened scene, BVH build scratch) per
+// calling thread between calls; this hands it back to the allocator.  Device memory cached by
+// the render core is released by rt_release_cached_memory() (include/rayito_b200.h).
+void releaseHostCaches();
+FlatScene& detail_flatCache();
+
 // Statistics of the most recent raytrace() on this thread
 const RtRenderStats& lastStats();
 void detail_setLastStats(const RtRenderStats& stats);

@@ -10,6 +10,7 @@
 #ifndef RAYITO_B200_SCENE_HPP
 #define RAYITO_B200_SCENE_HPP
 
+#include <cstring>
 #include <vector>
 
 #include "accel.hpp"
@@ -326,28 +327,55 @@ public:
             Quaternion rot = m_transform.rotation(time);
             Vector scl = m_transform.scaling(time);
             Vector trn = m_transform.translation(time);
-            for (size_t i = 0; i < m_vertices.size(); ++i)
-                m_bbox.expand(rot * (m_vertices[i] * scl) + trn);
+            // Index-ordered chunks, partial boxes folded in chunk order: the same
+            // left-to-right min/max association as the reference's single loop
+            const unsigned chunks = rayito_b200::chunkCount(m_vertices.size(), 1u << 16);
+            std::vector<BBox> partial(chunks);
+            BBox* part = &partial[0];
+            const Point* verts = m_vertices.empty() ? NULL : &m_vertices[0];
+            rayito_b200::parallelChunks(m_vertices.size(), chunks, [=](unsigned c, size_t b, size_t e) {
+                BBox acc;
+                for (size_t i = b; i < e; ++i)
+                    acc.expand(rot * (verts[i] * scl) + trn);
+                part[c] = acc;
+            });
+            for (unsigned c = 0; c < chunks; ++c)
+                m_bbox = m_bbox.combined(partial[c]);
         }
 
-        m_faceAreaCDF.clear();
-        m_faceAreaCDF.reserve(m_faces.size() + 1);
-        m_totalArea = 0.0f;
-        for (size_t f = 0; f < m_faces.size(); ++f)
+        // Face areas on the worker threads (slot f+1 holds the area of face f), then the
+        // running total in face order on this thread: float addition is not associative,
+        // so the sum itself stays serial (RMesh.h:107-124).
+        const size_t numFaces = m_faces.size();
+        m_faceAreaCDF.resize(numFaces + 1);
         {
-            const std::vector<unsigned int>& vi = m_faces[f].m_vertexIndices;
-            float faceArea = 0.0f;
-            for (size_t tri = 0; tri + 2 < vi.size(); ++tri)
-            {
-                Point p0 = m_vertices[vi[0]];
-                Point p1 = m_vertices[vi[tri + 1]];
-                Point p2 = m_vertices[vi[tri + 2]];
-                faceArea += cross(p1 - p0, p2 - p0).length() * 0.5f;
-            }
-            m_faceAreaCDF.push_back(m_totalArea);
+            float* area = &m_faceAreaCDF[0] + 1;
+            const Face* faces = numFaces ? &m_faces[0] : NULL;
+            const Point* verts = m_vertices.empty() ? NULL : &m_vertices[0];
+            rayito_b200::parallelChunks(numFaces, rayito_b200::chunkCount(numFaces, 1u << 15), [=](unsigned, size_t b, size_t e) {
+                for (size_t f = b; f < e; ++f)
+                {
+                    const std::vector<unsigned int>& vi = faces[f].m_vertexIndices;
+                    float faceArea = 0.0f;
+                    for (size_t tri = 0; tri + 2 < vi.size(); ++tri)
+                    {
+                        Point p0 = verts[vi[0]];
+                        Point p1 = verts[vi[tri + 1]];
+                        Point p2 = verts[vi[tri + 2]];
+                        faceArea += cross(p1 - p0, p2 - p0).length() * 0.5f;
+                    }
+                    area[f] = faceArea;
+                }
+            });
+        }
+        m_totalArea = 0.0f;
+        for (size_t f = 0; f < numFaces; ++f)
+        {
+            float faceArea = m_faceAreaCDF[f + 1];
+            m_faceAreaCDF[f] = m_totalArea;
             m_totalArea += faceArea;
         }
-        m_faceAreaCDF.push_back(m_totalArea);
+        m_faceAreaCDF[numFaces] = m_totalArea;
 
         if (rayito_b200::stageSemantics() == RT_SEMANTICS_STAGE6)
             m_bvh.build(&m_bbox);       // all vertices, used by a face or not (S6 RMesh.h:82-86)
@@ -384,58 +412,97 @@ public:
         m.first_cdf = (uint32_t)out.faceAreaCdf.size();
         m.total_area = m_totalArea;
 
-        for (size_t i = 0; i < m_vertices.size(); ++i)
-        {
-            out.vertices.push_back(m_vertices[i].m_x);
-            out.vertices.push_back(m_vertices[i].m_y);
-            out.vertices.push_back(m_vertices[i].m_z);
-        }
-        for (size_t i = 0; i < m_normals.size(); ++i)
-        {
-            out.normals.push_back(m_normals[i].m_x);
-            out.normals.push_back(m_normals[i].m_y);
-            out.normals.push_back(m_normals[i].m_z);
-        }
+        // Point / Vector are three packed floats and BvhNode is RtBvhNode bit for bit,
+        // so the big arrays are block copies; the face tables are filled by index-ordered
+        // chunks on the host worker threads (rayito_b200/parallel.hpp).
+        static_assert(sizeof(Point) == 12 && sizeof(Vector) == 12, "Point/Vector must be three packed floats");
+        static_assert(sizeof(BvhNode) == sizeof(RtBvhNode), "BvhNode must match RtBvhNode");
+        appendFloats(out.vertices, m_vertices.empty() ? NULL : &m_vertices[0].m_x, m_vertices.size() * 3);
+        appendFloats(out.normals, m_normals.empty() ? NULL : &m_normals[0].m_x, m_normals.size() * 3);
         // face_start is a global offset array with one closing entry per scene
         if (out.faceStart.empty())
             out.faceStart.push_back(0);
-        for (size_t f = 0; f < m_faces.size(); ++f)
+
+        const size_t numFaces = m_faces.size();
+        const unsigned chunks = rayito_b200::chunkCount(numFaces, 1u << 15);
+        std::vector<size_t> chunkIndices(chunks + 1, 0);
+        std::vector<int> chunkError(chunks, 0);
         {
-            const Face& face = m_faces[f];
-            if (face.m_vertexIndices.size() < 3)
-            {
-                out.error = "mesh face with fewer than 3 vertices";
-                return false;
-            }
-            bool hasNormals = !face.m_normalIndices.empty();
-            if (hasNormals && face.m_normalIndices.size() != face.m_vertexIndices.size())
-            {
-                out.error = "mesh face with mismatched normal indices";
-                return false;
-            }
-            for (size_t i = 0; i < face.m_vertexIndices.size(); ++i)
-            {
-                if (face.m_vertexIndices[i] >= m_vertices.size() ||
-                    (hasNormals && face.m_normalIndices[i] >= m_normals.size()))
+            const Face* faces = numFaces ? &m_faces[0] : NULL;
+            const size_t numVerts = m_vertices.size(), numNormals = m_normals.size();
+            size_t* counts = &chunkIndices[0];
+            int* errors = &chunkError[0];
+            rayito_b200::parallelChunks(numFaces, chunks, [=](unsigned c, size_t b, size_t e) {
+                size_t total = 0;
+                int err = 0;
+                for (size_t f = b; f < e && !err; ++f)
                 {
-                    out.error = "mesh face index out of range";
-                    return false;
+                    const Face& face = faces[f];
+                    const size_t n = face.m_vertexIndices.size();
+                    const bool hasNormals = !face.m_normalIndices.empty();
+                    if (n < 3) { err = 1; break; }
+                    if (hasNormals && face.m_normalIndices.size() != n) { err = 2; break; }
+                    for (size_t i = 0; i < n; ++i)
+                        if (face.m_vertexIndices[i] >= numVerts || (hasNormals && face.m_normalIndices[i] >= numNormals))
+                            err = 3;
+                    total += n;
                 }
-                out.vertexIndex.push_back(face.m_vertexIndices[i]);
-                out.normalIndex.push_back(hasNormals ? face.m_normalIndices[i] : RT_NO_INDEX);
-            }
-            out.faceHasNormals.push_back(hasNormals ? 1u : 0u);
-            out.faceStart.push_back((uint32_t)out.vertexIndex.size());
+                counts[c + 1] = total;
+                errors[c] = err;
+            });
         }
-        const BvhNode* nodes = m_bvh.nodes();
-        for (unsigned int i = 0; i < m_bvh.numNodes(); ++i)
+        for (unsigned c = 0; c < chunks; ++c)
         {
-            RtBvhNode n;
-            n.bbox_min[0] = nodes[i].m_bbox.m_min.m_x; n.bbox_min[1] = nodes[i].m_bbox.m_min.m_y; n.bbox_min[2] = nodes[i].m_bbox.m_min.m_z;
-            n.bbox_max[0] = nodes[i].m_bbox.m_max.m_x; n.bbox_max[1] = nodes[i].m_bbox.m_max.m_y; n.bbox_max[2] = nodes[i].m_bbox.m_max.m_z;
-            n.first_child_or_prim = nodes[i].m_firstChild;
-            n.flags = nodes[i].m_flags;
-            out.meshNodes.push_back(n);
+            // first error in face order, as the serial loop reports it
+            if (chunkError[c] != 0)
+            {
+                out.error = chunkError[c] == 1 ? "mesh face with fewer than 3 vertices"
+                          : chunkError[c] == 2 ? "mesh face with mismatched normal indices"
+                                               : "mesh face index out of range";
+                return false;
+            }
+            chunkIndices[c + 1] += chunkIndices[c];
+        }
+        {
+            const size_t indexBase = out.vertexIndex.size(), faceBase = out.faceHasNormals.size();
+            out.vertexIndex.resize(indexBase + chunkIndices[chunks]);
+            out.normalIndex.resize(indexBase + chunkIndices[chunks]);
+            out.faceHasNormals.resize(faceBase + numFaces);
+            out.faceStart.resize(faceBase + numFaces + 1);
+            const Face* faces = numFaces ? &m_faces[0] : NULL;
+            uint32_t* vertexIndex = out.vertexIndex.empty() ? NULL : &out.vertexIndex[0];
+            uint32_t* normalIndex = out.normalIndex.empty() ? NULL : &out.normalIndex[0];
+            uint32_t* faceHasNormals = out.faceHasNormals.empty() ? NULL : &out.faceHasNormals[0];
+            uint32_t* faceStart = &out.faceStart[0];
+            const size_t* offsets = &chunkIndices[0];
+            rayito_b200::parallelChunks(numFaces, chunks, [=](unsigned c, size_t b, size_t e) {
+                size_t at = indexBase + offsets[c];
+                for (size_t f = b; f < e; ++f)
+                {
+                    const Face& face = faces[f];
+                    const size_t n = face.m_vertexIndices.size();
+                    const bool hasNormals = !face.m_normalIndices.empty();
+                    for (size_t i = 0; i < n; ++i)
+                    {
+                        vertexIndex[at + i] = face.m_vertexIndices[i];
+                        normalIndex[at + i] = hasNormals ? face.m_normalIndices[i] : RT_NO_INDEX;
+                    }
+                    at += n;
+                    faceHasNormals[faceBase + f] = hasNormals ? 1u : 0u;
+                    faceStart[faceBase + f + 1] = (uint32_t)at;
+                }
+            });
+        }
+        if (m_bvh.numNodes() != 0)
+        {
+            const size_t nodeBase = out.meshNodes.size();
+            out.meshNodes.resize(nodeBase + m_bvh.numNodes());
+            RtBvhNode* dst = &out.meshNodes[nodeBase];
+            const BvhNode* src = m_bvh.nodes();
+            const size_t numNodes = m_bvh.numNodes();
+            rayito_b200::parallelChunks(numNodes, rayito_b200::chunkCount(numNodes, 1u << 16), [=](unsigned, size_t b, size_t e) {
+                std::memcpy(dst + b, src + b, (e - b) * sizeof(RtBvhNode));
+            });
         }
         out.faceAreaCdf.insert(out.faceAreaCdf.end(), m_faceAreaCDF.begin(), m_faceAreaCDF.end());
         out.meshes.push_back(m);
@@ -449,6 +516,12 @@ public:
     }
 
 protected:
+    static void appendFloats(std::vector<float>& dst, const float* src, size_t n)
+    {
+        if (n != 0)
+            dst.insert(dst.end(), src, src + n);
+    }
+
     std::vector<Point> m_vertices;
     std::vector<Vector> m_normals;
     std::vector<Face> m_faces;
