@@ -88,6 +88,29 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version
+# banner on fd 1), so fd 1 is pointed at stderr for the whole run and the result line goes to the
+# saved descriptor.
+_RESULT_FD = None
+
+
+def claim_stdout():
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -193,7 +216,7 @@ def run_reference(args, wl, rank, world):
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_stage23(args, wl, rank, world, local_rank):
@@ -215,14 +238,14 @@ def run_stage23(args, wl, rank, world, local_rank):
                 times.append(dt)
         value = rays * len(times) / sum(times) / 1e6
         sample = "Stage 3 program at its built-in 4x4 = 16 spp level only (%.1f M rays per step), single thread as written" % (rays / 1e6)
-        print(json.dumps({
+        emit({
             "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["label"], "sample": sample},
             "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": 1, "kind": "reference", "sample": sample},
             "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}), flush=True)
+            "gpu_launches": 0})
         return
 
     import torch
@@ -291,7 +314,7 @@ def run_stage23(args, wl, rank, world, local_rank):
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -307,6 +330,7 @@ def main():
     ap.add_argument("--tile", type=int, default=0)
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
+    claim_stdout()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -470,7 +494,7 @@ def main():
             line["e2e"] = e2e
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

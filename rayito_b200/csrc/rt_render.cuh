@@ -23,6 +23,9 @@
 #define RAYITO_B200_RT_RENDER_CUH
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -1383,12 +1386,18 @@ inline int rt_render_impl(RtScene* s, const RtCamera* camera, const RtRenderPara
     if (s == NULL || camera == NULL || prm == NULL || rgb_out == NULL)
         return rt_fail(RT_ERR_ARG, "null argument");
     RT_CUDA(cudaSetDevice(s->device));
+    // RAYITO_B200_TIMING=1: host-clock phases of this call on stderr
+    const bool host_timing = std::getenv("RAYITO_B200_TIMING") != NULL;
+    std::chrono::steady_clock::time_point hc[5];
+    hc[0] = std::chrono::steady_clock::now();
     RenderPlan plan;
     int rc = rt_plan(s, prm, plan);
     if (rc != RT_OK) return rc;
+    hc[1] = std::chrono::steady_clock::now();
     rc = rt_render_reserve(s, plan);
     if (rc != RT_OK) return rc;
     RenderBuffers* rb = s->render;
+    hc[2] = std::chrono::steady_clock::now();
 
     const size_t image_floats = (size_t)prm->width * prm->height * 3;
     float* d_image = rgb_out;
@@ -1461,7 +1470,17 @@ inline int rt_render_impl(RtScene* s, const RtCamera* camera, const RtRenderPara
         }
     }
     RT_CUDA(cudaEventRecord(rb->ev[3], st));
+    hc[3] = std::chrono::steady_clock::now();
     RT_CUDA(cudaStreamSynchronize(st));
+    hc[4] = std::chrono::steady_clock::now();
+    if (host_timing)
+    {
+        double ms[4];
+        for (int i = 0; i < 4; ++i)
+            ms[i] = std::chrono::duration<double, std::milli>(hc[i + 1] - hc[i]).count();
+        std::fprintf(stderr, "[rayito_b200] rt_render host clock: plan %.1f ms, reserve %.1f, enqueue %.1f, wait %.1f\n",
+                     ms[0], ms[1], ms[2], ms[3]);
+    }
 
     for (size_t k = 0; k < plan.tiles.size(); ++k)
     {

@@ -321,12 +321,31 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
         face_first_tri[f + 1] = face_first_tri[f] + (n - 2);
     }
     const uint32_t num_tris = face_first_tri[desc->num_faces];
+    // Device node slots.  The reference numbers a node's two children b and b+1 with b odd
+    // (the root is node 0, RAccel.h:366-371), and both are fetched whenever the parent's box
+    // is entered.  L2 fills from HBM in aligned 64-byte pieces, so every mesh's nodes are
+    // stored one slot up (node i in slot first_node + i with first_node odd): each sibling
+    // pair is then exactly one aligned 64-byte piece, and the fetch of the near child brings
+    // the far child along.  RAYITO_B200_NODE_ALIGN=0 keeps the pairs straddling (A/B runs).
+    const char* align_env = std::getenv("RAYITO_B200_NODE_ALIGN");
+    const bool align_pairs = !(align_env != NULL && align_env[0] == '0');
+    std::vector<uint32_t> dev_first_node(desc->num_meshes, 0);
+    uint64_t dev_nodes = 0;
+    for (uint32_t m = 0; m < desc->num_meshes; ++m)
+    {
+        if (align_pairs && (dev_nodes & 1u) == 0)
+            ++dev_nodes;
+        dev_first_node[m] = (uint32_t)dev_nodes;
+        dev_nodes += desc->meshes[m].num_nodes;
+    }
+    if (dev_nodes >= 0xffffffffull)
+        return rt_fail(RT_ERR_ARG, "too many mesh BVH nodes");
     std::vector<DMesh> meshes(desc->num_meshes);
     for (uint32_t m = 0; m < desc->num_meshes; ++m)
     {
         const RtMesh& mesh = desc->meshes[m];
         DMesh dm;
-        dm.first_node = mesh.first_node;
+        dm.first_node = dev_first_node[m];
         dm.num_nodes = mesh.num_nodes;
         dm.first_tri = face_first_tri[mesh.first_face];
         dm.first_face = mesh.first_face;
@@ -476,7 +495,7 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
     ArenaBuilder ab;
     size_t o_shapes = ab.put(shapes.data(), shapes.size() * sizeof(DShapeMem));
     size_t o_top = ab.put(top_nodes.data(), top_nodes.size() * sizeof(DNode));
-    size_t o_mnodes = ab.reserve((size_t)desc->num_mesh_nodes * sizeof(DNode));     // built in place below
+    size_t o_mnodes = ab.reserve((size_t)dev_nodes * sizeof(DNode));     // built in place below
     size_t o_tris = ab.reserve((size_t)num_tris * 3 * sizeof(float4));
     size_t o_trin = ab.reserve((size_t)num_tris * sizeof(uint4));
     size_t o_fft = ab.put(face_first_tri.data(), face_first_tri.size() * sizeof(uint32_t));
@@ -504,6 +523,11 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
     if (device < 0 || device >= ndev)
         return rt_fail(RT_ERR_ARG, "device ordinal out of range");
     RT_CUDA(cudaSetDevice(device));
+    if (const char* fetch_env = std::getenv("RAYITO_B200_L2_FETCH"))    // A/B runs: 32 / 64 / 128 bytes
+    {
+        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)std::strtol(fetch_env, NULL, 10));
+        cudaGetLastError();
+    }
 
     // The staging block is shared by all callers: held until the copy has left it
     std::lock_guard<std::mutex> stage_guard(stage_lock());
@@ -560,6 +584,9 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
                     }
                 }
             });
+            const uint32_t dev_first = dev_first_node[m];
+            if (dev_first != 0)
+                std::memset(&mesh_nodes[dev_first - 1], 0, sizeof(DNode));      // the padding slot
             parallel_ranges(mesh.num_nodes, 1u << 15, [=](size_t nb, size_t ne) {
                 for (size_t i = nb; i < ne; ++i)
                 {
@@ -577,7 +604,7 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
                     DNode dn;
                     dn.q0 = make_float4(n.bbox_min[0], n.bbox_min[1], n.bbox_min[2], n.bbox_max[0]);
                     dn.q1 = make_float4(n.bbox_max[1], n.bbox_max[2], wf, ff);
-                    mesh_nodes[mesh.first_node + i] = dn;
+                    mesh_nodes[dev_first + i] = dn;
                 }
             });
         }

@@ -302,3 +302,61 @@ def test_tonemap_matches_display_image(capi):
     expect = np.clip(np.power(rgb[ok].astype(np.float64), 1 / np.float32(2.2)), 0, 1)
     got = out[ok][:, [2, 1, 0]].astype(int)
     assert np.abs(got - np.floor(expect * 255.0)).max() <= 1
+
+
+def test_raytrace_call_and_device_shards_match_reference(capi, scene1_ref, obj_path):
+    """The reference-facing call itself: Rayito::raytrace() on an application-built scene
+    (rth_app_raytrace: findLights + prepare + flatten + upload + render + download per call,
+    RaytraceMain.cpp:485-579) returns the reference's image bit for bit, repeated calls on the
+    same scene agree (prepare() is redone each time, as in the reference), and
+    rayito_b200::raytraceToDevice() per rank leaves tiles in HBM whose sum over ranks -- the
+    multi-GPU tile assembly -- is that same image."""
+    import ctypes as C
+    import torch
+    lib = capi.host()
+    app = lib.rth_app_create(capi.RECIPE_STAGE7_SCENE1, obj_path.encode(), 0, 0)
+    assert app
+    try:
+        host_scene = capi.HostScene(capi.RECIPE_STAGE7_SCENE1, obj_path)
+        spec = host_scene.default_camera_spec()
+        W, H, ps, ls, depth = 96, 54, 3, 1, 3
+        theirs, ref_stats = scene1_ref.render(spec, W, H, ps, ls=ls, depth=depth)
+        stats = capi.RtRenderStats()
+        for _ in range(2):
+            img = np.zeros((H, W, 3), np.float32)
+            rc = lib.rth_app_raytrace(app, spec.ctypes.data, W, H, ps, ls, depth, 0, 0, 1, 0, img.ctypes.data, 0, C.byref(stats))
+            assert rc == 0, lib.rth_last_error_string()
+            assert np.array_equal(bits(img), bits(theirs))
+            assert stats.closest_rays + stats.any_rays == ref_stats.closest_calls + ref_stats.any_calls
+        world = 3
+        total = torch.zeros((H, W, 3), dtype=torch.float32, device="cuda:0")
+        for rank in range(world):
+            shard = torch.zeros((H, W, 3), dtype=torch.float32, device="cuda:0")
+            rc = lib.rth_app_raytrace(app, spec.ctypes.data, W, H, ps, ls, depth, 0, rank, world, 0,
+                                      shard.data_ptr(), 1, C.byref(stats))
+            assert rc == 0, lib.rth_last_error_string()
+            total += shard          # what the NCCL sum-reduce of bench.py does across GPUs
+        torch.cuda.synchronize()
+        assert np.array_equal(bits(total.cpu().numpy()), bits(theirs))
+    finally:
+        lib.rth_app_destroy(app)
+
+
+@pytest.mark.parametrize("align", ["1", "0"])
+def test_large_mesh_threaded_prepare_image_matches_reference(capi, ref, align, monkeypatch):
+    """A mesh big enough for the threaded host path (81 920 quads: subtree jobs, chunked
+    face tables, in-place parallel staging of triangle / node records) renders the reference's
+    image bit for bit, with the sibling-pair node alignment of the device layout on and off."""
+    grid = (320, 256)
+    monkeypatch.setenv("RAYITO_B200_NODE_ALIGN", align)
+    host = capi.HostScene(capi.RECIPE_SYNTHETIC_MESH, None, grid)
+    dev = capi.DeviceScene(host.desc)
+    spec = host.default_camera_spec()
+    cam = capi.camera_from_spec(spec)
+    W, H, ps = 64, 36, 2
+    theirs, rstats = ref.RefScene(5, None, grid).render(spec, W, H, ps, ls=1, depth=3)
+    mine, stats = dev.render(cam, W, H, ps, ls=1, depth=3)
+    dev.close()
+    same, rel = _compare_images(mine, theirs, "large synthetic mesh, align " + align)
+    assert rel <= RMSE_REL_TOL and same >= MIN_IDENTICAL_FRACTION
+    assert stats.closest_rays == rstats.closest_calls and stats.any_rays == rstats.any_calls
