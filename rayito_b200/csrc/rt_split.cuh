@@ -685,7 +685,7 @@ __device__ __forceinline__ void trace_top_static(const DScene& sc, const IO& io,
 // Mesh pass: Mesh::intersect / doesIntersect for suspended rays
 // ---------------------------------------------------------------------------
 #ifndef RT_MESH_PREFETCH
-#define RT_MESH_PREFETCH 0
+#define RT_MESH_PREFETCH 0     /* 1: L2 prefetch of a leaf's triangle records when the lane parks on it */
 #endif
 #ifndef RT_MESH_TOPCACHE
 #define RT_MESH_TOPCACHE 1     /* newest far entry cached in registers: +0.6 % C4, +2.6 % C5 */
@@ -696,29 +696,30 @@ __device__ __forceinline__ void trace_top_static(const DScene& sc, const IO& io,
 #ifndef RT_MESH_SMEM_STACK
 #define RT_MESH_SMEM_STACK 10     /* same-session A/B: +0.3 % on C4, +1.7 % on C5 (14: C4 -0.3 %, C5 +3.5 %) */
 #endif
-#if RT_MESH_SMEM_STACK > 0
-#define RT_MESH_STK_PUT(slot, n_, a_, b_)                                                        \
-    { if ((slot) < RT_MESH_SMEM_STACK) { sm_node[(slot) * RT_BLOCK + threadIdx.x] = (n_);        \
-          sm_t0[(slot) * RT_BLOCK + threadIdx.x] = (a_); sm_t1[(slot) * RT_BLOCK + threadIdx.x] = (b_); } \
-      else { stk_node[(slot) - RT_MESH_SMEM_STACK] = (n_); stk_t0[(slot) - RT_MESH_SMEM_STACK] = (a_);   \
-             stk_t1[(slot) - RT_MESH_SMEM_STACK] = (b_); } }
-#define RT_MESH_STK_GET(slot, n_, a_, b_)                                                        \
-    { if ((slot) < RT_MESH_SMEM_STACK) { (n_) = sm_node[(slot) * RT_BLOCK + threadIdx.x];        \
-          (a_) = sm_t0[(slot) * RT_BLOCK + threadIdx.x]; (b_) = sm_t1[(slot) * RT_BLOCK + threadIdx.x]; } \
-      else { (n_) = stk_node[(slot) - RT_MESH_SMEM_STACK]; (a_) = stk_t0[(slot) - RT_MESH_SMEM_STACK];   \
-             (b_) = stk_t1[(slot) - RT_MESH_SMEM_STACK]; } }
-#else
-#define RT_MESH_STK_PUT(slot, n_, a_, b_) { stk_node[slot] = (n_); stk_t0[slot] = (a_); stk_t1[slot] = (b_); }
-#define RT_MESH_STK_GET(slot, n_, a_, b_) { (n_) = stk_node[slot]; (a_) = stk_t0[slot]; (b_) = stk_t1[slot]; }
+// Trees deeper than 32 (the CAP = 64 instantiation: the 10 M-triangle mesh is 37 deep) keep more
+// slots there: +2.2 % on C5 in the r1b same-session A/B, and the shallow instantiation that C3/C4
+// use is unchanged.
+#ifndef RT_MESH_SMEM_STACK_DEEP
+#define RT_MESH_SMEM_STACK_DEEP 14
 #endif
+#define RT_MESH_STK_PUT(slot, n_, a_, b_)                                                        \
+    { if ((slot) < kSmemStack) { sm_node[(slot) * RT_BLOCK + threadIdx.x] = (n_);                \
+          sm_t0[(slot) * RT_BLOCK + threadIdx.x] = (a_); sm_t1[(slot) * RT_BLOCK + threadIdx.x] = (b_); } \
+      else { stk_node[(slot) - kSmemStack] = (n_); stk_t0[(slot) - kSmemStack] = (a_);           \
+             stk_t1[(slot) - kSmemStack] = (b_); } }
+#define RT_MESH_STK_GET(slot, n_, a_, b_)                                                        \
+    { if ((slot) < kSmemStack) { (n_) = sm_node[(slot) * RT_BLOCK + threadIdx.x];                \
+          (a_) = sm_t0[(slot) * RT_BLOCK + threadIdx.x]; (b_) = sm_t1[(slot) * RT_BLOCK + threadIdx.x]; } \
+      else { (n_) = stk_node[(slot) - kSmemStack]; (a_) = stk_t0[(slot) - kSmemStack];           \
+             (b_) = stk_t1[(slot) - kSmemStack]; } }
 template <int CAP, bool ANY, bool COUNT, class IO>
 __device__ __forceinline__ void trace_mesh(const DScene& sc, const IO& io, const SplitBufs& sb, const SplitPass& ps, WorkCount& wc)
 {
-#if RT_MESH_SMEM_STACK > 0
-    __shared__ uint32_t sm_node[RT_MESH_SMEM_STACK * RT_BLOCK];
-    __shared__ float sm_t0[RT_MESH_SMEM_STACK * RT_BLOCK];
-    __shared__ float sm_t1[RT_MESH_SMEM_STACK * RT_BLOCK];
-#endif
+    constexpr int kSmemStack = CAP > 32 ? RT_MESH_SMEM_STACK_DEEP : RT_MESH_SMEM_STACK;
+    static_assert(kSmemStack >= 1 && kSmemStack < CAP, "shared-memory stack slots");
+    __shared__ uint32_t sm_node[kSmemStack * RT_BLOCK];
+    __shared__ float sm_t0[kSmemStack * RT_BLOCK];
+    __shared__ float sm_t1[kSmemStack * RT_BLOCK];
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t lt_mask = (1u << lane) - 1;
     const uint32_t n = *ps.in_count;
@@ -857,6 +858,15 @@ __device__ __forceinline__ void trace_mesh(const DScene& sc, const IO& io, const
                 parked = true;
                 park_word = word;
                 park_count = flags >> 3;
+#if RT_MESH_PREFETCH
+                // the triangles are tested only once enough lanes are parked: start their trip
+                // from HBM now (48-byte records; a quad face is 96 bytes = two 64-byte pieces)
+                {
+                    const char* rec = reinterpret_cast<const char*>(sc.tris + (size_t)word * 3);
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(rec));
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(rec + 64));
+                }
+#endif
                 break;
             }
             if (!ANY)

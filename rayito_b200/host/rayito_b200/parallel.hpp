@@ -11,6 +11,7 @@
 
 #include <condition_variable>
 #include <cstdlib>
+#include <exception>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -54,16 +55,24 @@ inline void parallelChunks(size_t n, unsigned chunks, Body body)
         body(0u, (size_t)0, n);
         return;
     }
+    // An exception on a worker (std::bad_alloc, say) is carried back to the caller
+    std::vector<std::exception_ptr> failed(chunks);
+    std::exception_ptr* fail = &failed[0];
     std::vector<std::thread> workers;
     workers.reserve(chunks - 1);
     for (unsigned c = 1; c < chunks; ++c)
     {
         size_t b = n * c / chunks, e = n * (c + 1) / chunks;
-        workers.push_back(std::thread(body, c, b, e));
+        workers.push_back(std::thread([body, fail, c, b, e]() {
+            try { body(c, b, e); } catch (...) { fail[c] = std::current_exception(); }
+        }));
     }
-    body(0u, (size_t)0, n / chunks);
+    try { body(0u, (size_t)0, n / chunks); } catch (...) { fail[0] = std::current_exception(); }
     for (size_t i = 0; i < workers.size(); ++i)
         workers[i].join();
+    for (unsigned c = 0; c < chunks; ++c)
+        if (failed[c])
+            std::rethrow_exception(failed[c]);
 }
 
 // A bag of independent jobs processed by `threads` workers; a job may add further jobs.
@@ -89,6 +98,7 @@ public:
         if (threads <= 1)
         {
             work(run);
+            rethrow();
             return;
         }
         std::vector<std::thread> workers;
@@ -98,6 +108,7 @@ public:
         work(run);
         for (size_t i = 0; i < workers.size(); ++i)
             workers[i].join();
+        rethrow();
     }
 
 private:
@@ -115,10 +126,27 @@ private:
             m_jobs.pop_back();
             ++m_running;
             lock.unlock();
-            run(job, *this);
+            std::exception_ptr failure;
+            try { run(job, *this); } catch (...) { failure = std::current_exception(); }
             lock.lock();
+            if (failure)
+            {
+                // first failure wins; the queued jobs are dropped so that everybody drains
+                if (!m_failure) m_failure = failure;
+                m_jobs.clear();
+            }
             if (--m_running == 0 && m_jobs.empty())
                 m_wake.notify_all();
+        }
+    }
+
+    void rethrow()
+    {
+        if (m_failure)
+        {
+            std::exception_ptr failure = m_failure;
+            m_failure = std::exception_ptr();
+            std::rethrow_exception(failure);
         }
     }
 
@@ -126,6 +154,7 @@ private:
     std::condition_variable m_wake;
     std::vector<Job> m_jobs;
     unsigned m_running;
+    std::exception_ptr m_failure;
 };
 
 // Per-thread scratch block that survives between calls: a 10 M-triangle prepare() needs
