@@ -524,15 +524,16 @@ def measure_e2e(args, wl, capi, obj, spec, rank, world, local_rank, dev, dist, t
         raise RuntimeError("rth_app_create: " + lib.rth_last_error_string().decode())
     build_s = time.perf_counter() - t0
     if world == 1:
-        img = np.zeros((H, W, 3), np.float32)
+        pixels = C.c_void_p()
     else:
         d_img = torch.zeros((H, W, 3), dtype=torch.float32, device=dev)
         frame = torch.empty((H, W, 3), dtype=torch.float32, pin_memory=True) if rank == 0 else None
 
     def one():
         if world == 1:
-            rc = lib.rth_app_raytrace(app, spec.ctypes.data, W, H, ps, ls, depth, local_rank, rank, world, 0,
-                                      img.ctypes.data, 0, C.byref(stats))
+            # the Image raytrace() returns stays with the app handle: the host frame is read in place
+            rc = lib.rth_app_raytrace_image(app, spec.ctypes.data, W, H, ps, ls, depth, local_rank, rank, world, 0,
+                                            C.byref(pixels), C.byref(stats))
         else:
             d_img.zero_()
             rc = lib.rth_app_raytrace(app, spec.ctypes.data, W, H, ps, ls, depth, local_rank, rank, world, 0,
@@ -544,6 +545,11 @@ def measure_e2e(args, wl, capi, obj, spec, rank, world, local_rank, dev, dist, t
             if rank == 0:
                 frame.copy_(d_img, non_blocking=True)
             torch.cuda.synchronize(dev)
+        else:
+            # the step's result is in host memory: touch it (mean of the first row) like a consumer would
+            row = np.ctypeslib.as_array(C.cast(pixels, C.POINTER(C.c_float)), shape=(W * 3,))
+            if not np.isfinite(float(row.mean())):
+                raise RuntimeError("e2e frame is not finite")
         return stats.render_ms
 
     one()

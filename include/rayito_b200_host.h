@@ -74,6 +74,15 @@ int rth_app_raytrace(RthApp* app, const float* spec14, unsigned width, unsigned 
                      int device, unsigned rank, unsigned world, int count_work,
                      float* rgb, int rgb_on_device, RtRenderStats* stats);
 
+/* The same call handing back the Image raytrace() returned instead of copying it out:
+ * *pixels = width*height*3 floats owned by the app handle, valid until the next
+ * rth_app_raytrace_image() / rth_app_destroy() (the GUI keeps its frame the same way and
+ * deletes it before the next render, MainWindow.cpp:240-244). */
+int rth_app_raytrace_image(RthApp* app, const float* spec14, unsigned width, unsigned height,
+                           unsigned pixel_samples_hint, unsigned light_samples_hint, unsigned max_ray_depth,
+                           int device, unsigned rank, unsigned world, int count_work,
+                           const float** pixels, RtRenderStats* stats);
+
 /* Stage 1 program (Rayito_Stage1/main.cpp:65-135): builds its scene (one pink plane at
  * y = -2) and camera (fov 30 at the origin looking down +z) with makeCameraRay's basis
  * arithmetic (main.cpp:28-52), renders on the GPU and returns the P6 payload

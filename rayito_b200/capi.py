@@ -114,7 +114,7 @@ CORE_SYMBOLS = [
 HOST_SYMBOLS = [
     "rth_last_error_string", "rth_scene_create", "rth_scene_destroy", "rth_scene_desc",
     "rth_scene_prepare_seconds", "rth_scene_depth", "rth_camera", "rth_scene_default_camera", "rth_raytrace",
-    "rth_app_create", "rth_app_destroy", "rth_app_raytrace",
+    "rth_app_create", "rth_app_destroy", "rth_app_raytrace", "rth_app_raytrace_image",
     "rth_stage1_render", "rth_stage23_render",
 ]
 
@@ -181,6 +181,9 @@ def host():
         lib.rth_app_destroy.argtypes = [vp]
         lib.rth_app_raytrace.argtypes = [vp, vp, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint,
                                          C.c_int, C.c_uint, C.c_uint, C.c_int, vp, C.c_int, C.POINTER(RtRenderStats)]
+        lib.rth_app_raytrace_image.argtypes = [vp, vp, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint,
+                                               C.c_int, C.c_uint, C.c_uint, C.c_int, C.POINTER(C.c_void_p),
+                                               C.POINTER(RtRenderStats)]
         lib.rth_stage1_render.argtypes = [C.c_int, C.c_uint, C.c_uint, vp]
         lib.rth_stage23_render.argtypes = [C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_uint, vp, vp, vp]
         _host = lib

@@ -8,6 +8,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <mutex>
+#include <new>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -216,7 +218,8 @@ static Image* raytraceImpl(ShapeSet& scene,
         rc = rt_render_device(dev, &camera, &params, deviceImage, &stats, NULL);
     else
     {
-        image = new Image(width, height);   // Color() is black: other ranks' tiles stay black
+        // one rank: every pixel is overwritten by the download; several: the others' tiles stay black
+        image = opt.world > 1 ? new Image(width, height) : new Image(width, height, Image::Uncleared());
         rc = rt_render(dev, &camera, &params, image->data(), &stats);
     }
     clock_gettime(CLOCK_MONOTONIC, &tp[4]);
@@ -272,6 +275,53 @@ void raytraceToDevice(Rayito::ShapeSet& scene,
     Rayito::raytraceImpl(scene, cam, width, height, pixelSamplesHint, lightSamplesHint, maxRayDepth, deviceImage);
 }
 
+namespace
+{
+std::mutex g_pixelLock;
+void* g_sparePixels = NULL;
+size_t g_sparePixelBytes = 0;
+}
+
+void* acquirePixels(size_t bytes)
+{
+    if (bytes == 0)
+        bytes = sizeof(float);
+    {
+        std::lock_guard<std::mutex> guard(g_pixelLock);
+        if (g_sparePixels != NULL && g_sparePixelBytes == bytes)
+        {
+            void* block = g_sparePixels;
+            g_sparePixels = NULL;
+            g_sparePixelBytes = 0;
+            return block;
+        }
+    }
+    void* block = std::malloc(bytes);
+    if (block == NULL)
+        throw std::bad_alloc();
+    return block;
+}
+
+void releasePixels(void* block, size_t bytes)
+{
+    if (block == NULL)
+        return;
+    if (bytes == 0)
+        bytes = sizeof(float);
+    void* drop = block;
+    {
+        // keep the larger of the spare and this one
+        std::lock_guard<std::mutex> guard(g_pixelLock);
+        if (g_sparePixels == NULL || g_sparePixelBytes < bytes)
+        {
+            drop = g_sparePixels;
+            g_sparePixels = block;
+            g_sparePixelBytes = bytes;
+        }
+    }
+    std::free(drop);
+}
+
 FlatScene& detail_flatCache()
 {
     static thread_local FlatScene cache;
@@ -282,6 +332,14 @@ void releaseHostCaches()
 {
     detail_flatCache().shrink();
     buildScratch().release();
+    void* spare = NULL;
+    {
+        std::lock_guard<std::mutex> guard(g_pixelLock);
+        spare = g_sparePixels;
+        g_sparePixels = NULL;
+        g_sparePixelBytes = 0;
+    }
+    std::free(spare);
 }
 
 unsigned& stageSemantics()
@@ -327,6 +385,9 @@ struct RthApp
     Rayito::ShapeSet set;
     rayito_recipes::SceneStore store;
     unsigned semantics;
+    Rayito::Image* frame;       // the Image of the last rth_app_raytrace_image(), owned like the GUI owns its frame
+    RthApp() : semantics(RT_SEMANTICS_STAGE7), frame(NULL) { }
+    ~RthApp() { delete frame; }
 };
 
 namespace
@@ -562,6 +623,45 @@ int rth_app_raytrace(RthApp* app, const float* spec14, unsigned width, unsigned 
             std::memcpy(rgb, image->data(), (size_t)width * height * 3 * sizeof(float));
             delete image;
         }
+        if (stats) *stats = rayito_b200::lastStats();
+        return 0;
+    }
+    catch (const std::exception& e)
+    {
+        t_hostError = e.what();
+        return -1;
+    }
+}
+
+int rth_app_raytrace_image(RthApp* app, const float* spec14, unsigned width, unsigned height,
+                           unsigned ps, unsigned ls, unsigned depth,
+                           int device, unsigned rank, unsigned world, int count_work,
+                           const float** pixels, RtRenderStats* stats)
+{
+    if (app == NULL || spec14 == NULL || pixels == NULL)
+    {
+        t_hostError = "null argument";
+        return -1;
+    }
+    try
+    {
+        // the application drops the previous frame before asking for the next one (MainWindow.cpp:243)
+        delete app->frame;
+        app->frame = NULL;
+        *pixels = NULL;
+        StageScope stage(app->semantics);
+        Rayito::PerspectiveCamera cam(spec14[0],
+                                      Rayito::Point(spec14[1], spec14[2], spec14[3]),
+                                      Rayito::Point(spec14[4], spec14[5], spec14[6]),
+                                      Rayito::Point(spec14[7], spec14[8], spec14[9]),
+                                      spec14[10], spec14[11], spec14[12], spec14[13]);
+        rayito_b200::RenderOptions& opt = rayito_b200::renderOptions();
+        opt.device = device;
+        opt.rank = rank;
+        opt.world = world ? world : 1;
+        opt.countWork = count_work != 0;
+        app->frame = Rayito::raytrace(app->set, cam, width, height, ps, ls, depth);
+        *pixels = app->frame->data();
         if (stats) *stats = rayito_b200::lastStats();
         return 0;
     }

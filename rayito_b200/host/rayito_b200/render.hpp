@@ -9,8 +9,19 @@
 #define RAYITO_B200_RENDER_HPP
 
 #include <cstddef>
+#include <cstring>
 
 #include "scene.hpp"
+
+namespace rayito_b200
+{
+// Pixel storage of Rayito::Image.  raytrace() hands the caller a new Image per call and the
+// caller deletes it after display (MainWindow.cpp:243); a 4K float frame is 100 MB, which the C
+// library would map, page-fault in (~25 000 faults) and unmap again on every call.  One spare block
+// is kept per process instead, so a render loop reuses the same pages (releaseHostCaches() frees it).
+void* acquirePixels(size_t bytes);
+void releasePixels(void* block, size_t bytes);
+}
 
 namespace Rayito
 {
@@ -19,8 +30,19 @@ namespace Rayito
 class Image
 {
 public:
-    Image(size_t width, size_t height) : m_width(width), m_height(height), m_pixels(new Color[width * height]) { }
-    virtual ~Image() { delete[] m_pixels; }
+    // Black image, as the reference's `new Color[width * height]`
+    Image(size_t width, size_t height)
+        : m_width(width), m_height(height),
+          m_pixels(static_cast<Color*>(rayito_b200::acquirePixels(width * height * sizeof(Color))))
+    {
+        std::memset(static_cast<void*>(m_pixels), 0, width * height * sizeof(Color));     // 0.0f is all-zero bits
+    }
+    // raytrace()'s own frames when every pixel is about to be overwritten by the download
+    struct Uncleared { };
+    Image(size_t width, size_t height, Uncleared)
+        : m_width(width), m_height(height),
+          m_pixels(static_cast<Color*>(rayito_b200::acquirePixels(width * height * sizeof(Color)))) { }
+    virtual ~Image() { rayito_b200::releasePixels(m_pixels, m_width * m_height * sizeof(Color)); }
 
     size_t width() const { return m_width; }
     size_t height() const { return m_height; }

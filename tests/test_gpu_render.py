@@ -328,6 +328,19 @@ def test_raytrace_call_and_device_shards_match_reference(capi, scene1_ref, obj_p
             assert rc == 0, lib.rth_last_error_string()
             assert np.array_equal(bits(img), bits(theirs))
             assert stats.closest_rays + stats.any_rays == ref_stats.closest_calls + ref_stats.any_calls
+        # the frame handed back in place (Image storage is recycled between calls; a different
+        # size in between must not confuse the spare block)
+        pixels = C.c_void_p()
+        for w2, h2 in ((W, H), (W // 2, H // 2), (W, H)):
+            rc = lib.rth_app_raytrace_image(app, spec.ctypes.data, w2, h2, ps, ls, depth, 0, 0, 1, 0,
+                                            C.byref(pixels), C.byref(stats))
+            assert rc == 0, lib.rth_last_error_string()
+            frame = np.ctypeslib.as_array(C.cast(pixels, C.POINTER(C.c_float)), shape=(h2, w2, 3)).copy()
+            if (w2, h2) == (W, H):
+                assert np.array_equal(bits(frame), bits(theirs))
+            else:
+                small, _ = scene1_ref.render(spec, w2, h2, ps, ls=ls, depth=depth)
+                assert np.array_equal(bits(frame), bits(small))
         world = 3
         total = torch.zeros((H, W, 3), dtype=torch.float32, device="cuda:0")
         for rank in range(world):
