@@ -70,9 +70,10 @@ NCU_TRAFFIC = {
             bytes=1.840791e9 + 618.319616e6, ms=1.6, source="profiles/r01_v8_static_top_c4small_full_summary.csv",
             note="captured with --batch 16777216 (per-launch bytes scale with the batch size); mostly per-ray wavefront "
                  "state (records scattered by slot), not scene data: the 3 MB scene is L1/L2-resident"),
-    5: dict(kernel="k_split_mesh<64,ANY=0,PathIO> (face-BVH pass of the path rays of one 16 Mi-sample batch)",
-            bytes=4.922347e9 + 319.387904e6, ms=5.8, source="profiles/r01_v6_mesh_c5small_full_summary.csv",
-            note="captured with --batch 16777216; random 32-byte node and 48-byte triangle gathers from a 660 MB scene, L2 hit 66 %"),
+    5: dict(kernel="k_split_mesh<64,ANY=1,ShadowIO> (face-BVH pass of the shadow rays of one 16 Mi-sample batch)",
+            bytes=4.352745e9 + 235.469824e6, ms=6.0, source="profiles/r01_v11_mesh_c5small_full_summary.csv",
+            note="captured with --batch 16777216; random 32-byte node and 48-byte triangle gathers from a 660 MB scene, "
+                 "L2 hit 61 %; the closest-hit passes of the same batch read 0.5-1.8 GB each (L2 hit 66-80 %)"),
 }
 CAMERA_SPEC = {       # fov, origin, target, up, focal distance, lens radius, shutter open/close (GUI defaults)
     1: [30, -4, 5, 15, 0, 0, 0, 0, 1, 0, 16, 0, 0, 1],

@@ -16,7 +16,9 @@ for r in rows[hi + 1:]:
         per.setdefault(r[idc], {'name': r[kn].split('(')[0][:44]})[r[mn]] = float(r[mv].replace(',', ''))
 lst = list(per.values())
 ray_idx = [i for i, k in enumerate(lst) if k['name'] == 'k_raygen']
-start, end = ray_idx[batch] - 1, ray_idx[batch + 1] - 1
+batch = min(batch, len(ray_idx) - 1)       # the last batch runs to the end of the list
+start = ray_idx[batch] - 1
+end = ray_idx[batch + 1] - 1 if batch + 1 < len(ray_idx) else len(lst)
 tot = collections.Counter()
 for k in lst[start:end]:
     t = k['gpu__time_duration.sum'] / 1e3
