@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <exception>
 #include <mutex>
+#include <system_error>
 #include <thread>
 #include <vector>
 
@@ -63,9 +64,17 @@ inline void parallelChunks(size_t n, unsigned chunks, Body body)
     for (unsigned c = 1; c < chunks; ++c)
     {
         size_t b = n * c / chunks, e = n * (c + 1) / chunks;
-        workers.push_back(std::thread([body, fail, c, b, e]() {
+        try
+        {
+            workers.push_back(std::thread([body, fail, c, b, e]() {
+                try { body(c, b, e); } catch (...) { fail[c] = std::current_exception(); }
+            }));
+        }
+        catch (const std::system_error&)
+        {
+            // no thread to be had: this chunk runs here
             try { body(c, b, e); } catch (...) { fail[c] = std::current_exception(); }
-        }));
+        }
     }
     try { body(0u, (size_t)0, n / chunks); } catch (...) { fail[0] = std::current_exception(); }
     for (size_t i = 0; i < workers.size(); ++i)
@@ -104,7 +113,10 @@ public:
         std::vector<std::thread> workers;
         workers.reserve(threads - 1);
         for (unsigned t = 1; t < threads; ++t)
-            workers.push_back(std::thread([this, run]() { this->work(run); }));
+        {
+            try { workers.push_back(std::thread([this, run]() { this->work(run); })); }
+            catch (const std::system_error&) { break; }     // fewer workers; the caller drains the rest
+        }
         work(run);
         for (size_t i = 0; i < workers.size(); ++i)
             workers[i].join();
