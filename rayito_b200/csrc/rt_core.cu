@@ -325,6 +325,7 @@ int rt_stage1_render(int device, const RtStage1Plane* planes, uint32_t num_plane
 void rt_release_cached_memory(void)
 {
     rt_detail::pool_release_all();
+    rt_detail::validate_scratch().release();       // the calling thread's BVH validation scratch
 }
 
 int rt_stage23_render(int device, const RtS23Scene* scene, const RtCamera* camera, const RtS23Params* params,

@@ -8,7 +8,9 @@
 #define RAYITO_B200_RT_SCENE_CUH
 
 #include <atomic>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -58,7 +60,7 @@ namespace rt_detail
 {
 
 // Deepest leaf (root = 0) of a reference-format BVH; -1 if malformed.
-inline int bvh_depth(const RtBvhNode* nodes, uint32_t count, uint32_t num_prims, std::string& why)
+inline int bvh_depth_walk(const RtBvhNode* nodes, uint32_t count, uint32_t num_prims, std::string& why)
 {
     if (count == 0)
         return 0;
@@ -194,6 +196,138 @@ struct ArenaBuilder
     template <typename V> V* at(size_t offset) { return reinterpret_cast<V*>(block + offset); }
 };
 
+struct HostScratch
+{
+    void* data;
+    size_t bytes;
+    HostScratch() : data(NULL), bytes(0) { }
+    ~HostScratch() { std::free(data); }
+    void* get(size_t n)
+    {
+        if (n > bytes)
+        {
+            std::free(data);
+            data = std::malloc(n);
+            bytes = data ? n : 0;
+        }
+        return data;
+    }
+    void release() { std::free(data); data = NULL; bytes = 0; }
+};
+inline HostScratch& validate_scratch()
+{
+    static thread_local HostScratch scratch;
+    return scratch;
+}
+
+// bvh_depth for large trees.  The reference numbers children after their parent
+// (RAccel.h:366-371), which makes the checks data-parallel.  Pass A, on the worker threads:
+// every node is examined on its own (leaf primitive, split axis, child range, children
+// numbered after the parent) and leaves its child index in a compact table and its own index
+// in its children's "who points at me" slots.  Pass B: a node whose children do not point
+// back at it shares them with another node.  With all edges pointing forward and one parent
+// per node, one ascending sweep over the compact table gives every depth.  Trees that are
+// not numbered that way (another builder) take the serial walk above.
+inline int bvh_depth(const RtBvhNode* nodes, uint32_t count, uint32_t num_prims, std::string& why)
+{
+    if (count < (1u << 16))
+        return bvh_depth_walk(nodes, count, num_prims, why);
+    const uint32_t kNone = 0xffffffffu;
+    // Scratch kept per calling thread between calls (10 bytes per node: fresh pages would cost
+    // more in page faults than the checks themselves): [0, count) first child (kNone for a leaf),
+    // [count, 2 count) the node pointing at me, then one depth and one "reached" byte per node.
+    static_assert(sizeof(std::atomic<uint32_t>) == sizeof(uint32_t), "atomic<uint32_t> must be a plain word");
+    void* scratch = validate_scratch().get((size_t)count * 10);
+    if (scratch == NULL)
+    {
+        why = "out of host memory validating a BVH";
+        return -1;
+    }
+    std::atomic<uint32_t>* child = static_cast<std::atomic<uint32_t>*>(scratch);
+    std::atomic<uint32_t>* pointer = child + count;
+    unsigned char* depth = reinterpret_cast<unsigned char*>(child + 2 * (size_t)count);
+    unsigned char* reached = depth + count;
+    const std::memory_order relaxed = std::memory_order_relaxed;
+    parallel_ranges(count, 1u << 16, [=](size_t b, size_t e) {
+        for (size_t i = b; i < e; ++i) pointer[i].store(kNone, relaxed);
+    });
+    // 0 ok, 1 not forward-numbered (fall back), 2.. malformed
+    std::atomic<int> verdict(0);
+    auto report = [&verdict](int mine) {
+        int seen = verdict.load();
+        while (seen < mine && !verdict.compare_exchange_weak(seen, mine)) { }
+    };
+    parallel_ranges(count, 1u << 16, [=, &report](size_t b, size_t e) {
+        int mine = 0;
+        for (size_t i = b; i < e; ++i)
+        {
+            const RtBvhNode& n = nodes[i];
+            uint32_t c = kNone;
+            if (n.flags & RT_NODE_LEAF)
+            {
+                if (n.first_child_or_prim >= num_prims) mine = mine > 2 ? mine : 2;
+            }
+            else if ((n.flags & RT_NODE_AXIS) == 3u)
+                mine = mine > 3 ? mine : 3;
+            else if ((uint64_t)n.first_child_or_prim + 1 >= count)
+                mine = mine > 4 ? mine : 4;
+            else if (n.first_child_or_prim <= i)
+                mine = mine > 1 ? mine : 1;
+            else
+            {
+                c = n.first_child_or_prim;
+                pointer[c].store((uint32_t)i, relaxed);
+                pointer[c + 1].store((uint32_t)i, relaxed);
+            }
+            child[i].store(c, relaxed);
+        }
+        if (mine != 0) report(mine);
+    });
+    if (verdict.load() == 0)
+        parallel_ranges(count, 1u << 16, [=, &report](size_t b, size_t e) {
+            for (size_t i = b; i < e; ++i)
+            {
+                const uint32_t c = child[i].load(relaxed);
+                if (c != kNone && (pointer[c].load(relaxed) != i || pointer[c + 1].load(relaxed) != i))
+                {
+                    report(5);
+                    return;
+                }
+            }
+        });
+    if (verdict.load() == 0 && pointer[0].load(relaxed) != kNone)
+        report(5);              // (cannot happen with forward edges; kept for symmetry with the walk)
+    switch (verdict.load())
+    {
+    case 0: break;
+    case 1: return bvh_depth_walk(nodes, count, num_prims, why);
+    case 2: why = "BVH leaf names a primitive that does not exist"; return -1;
+    case 3: why = "BVH node with split axis 3"; return -1;
+    case 4: why = "BVH child index out of range"; return -1;
+    default: why = "BVH has a cycle or shared children"; return -1;
+    }
+    // forward edges, one parent each, the root none: every node somebody points at hangs off
+    // the root.  Nodes nobody points at are unreachable and do not count.
+    std::memset(depth, 0, (size_t)count * 2);
+    reached[0] = 1;
+    int deepest = 0;
+    for (uint32_t i = 0; i < count; ++i)
+    {
+        if (!reached[i])
+            continue;
+        const int d = depth[i];
+        if (d > deepest) deepest = d;
+        const uint32_t c = child[i].load(relaxed);
+        if (c == kNone)
+            continue;
+        if (d >= 200)
+            return 201;             // far past the 49 the callers accept; keeps the byte from wrapping
+        depth[c] = depth[c + 1] = (unsigned char)(d + 1);
+        reached[c] = reached[c + 1] = 1;
+    }
+    return deepest;
+}
+
 inline float vlen(const float* v) { return std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
 
 } // namespace rt_detail
@@ -281,6 +415,11 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
         if (desc->lights[l] >= num_shapes || desc->shapes[desc->lights[l]].light != (int32_t)l)
             return rt_fail(RT_ERR_ARG, "lights[] and RtShape.light disagree");
 
+    // RAYITO_B200_TIMING=1: host-clock phases of the upload path on stderr
+    const bool host_timing = std::getenv("RAYITO_B200_TIMING") != NULL;
+    std::chrono::steady_clock::time_point hc[6];
+    hc[0] = std::chrono::steady_clock::now();
+
     // BVH depths (the reference's fixed 50-entry stack, RAccel.h:379)
     std::string why;
     int top_depth = bvh_depth(desc->top_nodes, desc->num_top_nodes, desc->num_finite, why);
@@ -309,6 +448,7 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
     }
     int stack_cap = (desc->num_top_nodes ? top_depth + 1 : (int)desc->num_finite) + (mesh_depth >= 0 ? mesh_depth + 1 : 0);
 
+    hc[1] = std::chrono::steady_clock::now();
     // Fan-expand faces into triangle records
     std::vector<uint32_t> face_first_tri(desc->num_faces + 1, 0);
     for (uint32_t f = 0; f < desc->num_faces; ++f)
@@ -514,10 +654,15 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
     size_t o_lights = ab.put(desc->lights, (size_t)desc->num_lights * 4);
     size_t o_walk = ab.put(top_walk.data(), top_walk.size() * sizeof(DTopStep));
 
+    hc[2] = std::chrono::steady_clock::now();
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     {
         cudaGetLastError();
+        if (host_timing)
+            std::fprintf(stderr, "[rayito_b200] rt_scene_create host clock (no device): validate BVHs %.1f ms, small records + layout %.1f\n",
+                         std::chrono::duration<double, std::milli>(hc[1] - hc[0]).count(),
+                         std::chrono::duration<double, std::milli>(hc[2] - hc[1]).count());
         return rt_fail(RT_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
     }
     if (device < 0 || device >= ndev)
@@ -530,6 +675,7 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
     }
 
     // The staging block is shared by all callers: held until the copy has left it
+    hc[3] = std::chrono::steady_clock::now();
     std::lock_guard<std::mutex> stage_guard(stage_lock());
     if (!ab.finish(stage_acquire_locked(ab.total ? ab.total : 16)))
         return rt_fail(RT_ERR_ARG, "out of host memory staging the scene");
@@ -633,6 +779,7 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
     sc->render = NULL;
     sc->dynamic_top = false;
 
+    hc[4] = std::chrono::steady_clock::now();
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
@@ -648,6 +795,16 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
     cudaEventElapsedTime(&sc->upload_ms, e0, e1);
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
+    hc[5] = std::chrono::steady_clock::now();
+    if (host_timing)
+    {
+        double ms[5];
+        for (int i = 0; i < 5; ++i)
+            ms[i] = std::chrono::duration<double, std::milli>(hc[i + 1] - hc[i]).count();
+        std::fprintf(stderr, "[rayito_b200] rt_scene_create host clock: validate BVHs %.1f ms, small records + layout %.1f, "
+                             "device select %.1f, stage triangles/nodes %.1f, alloc + copy %.1f (copy alone %.1f, %.1f MB)\n",
+                     ms[0], ms[1], ms[2], ms[3], ms[4], sc->upload_ms, sc->arena_bytes / 1e6);
+    }
     if (err != cudaSuccess)
     {
         pool_free(device, sc->arena, sc->arena_alloc);
