@@ -449,7 +449,7 @@ k_trace_paths(const __grid_constant__ RenderCtx c, int cur)
 #define RT_TOP_MINBLOCKS 1
 #endif
 #ifndef RT_MESH_MINBLOCKS
-#define RT_MESH_MINBLOCKS 1
+#define RT_MESH_MINBLOCKS 8        /* 64-register cap: with box_test_plain the pass would take 65 and lose a block per SM (C5: 1887 vs 1947) */
 #endif
 template <bool ANY, bool COUNT, bool FRESH, class IO>
 __global__ void __launch_bounds__(RT_BLOCK, RT_TOP_MINBLOCKS)

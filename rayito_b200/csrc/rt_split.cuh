@@ -687,6 +687,9 @@ __device__ __forceinline__ void trace_top_static(const DScene& sc, const IO& io,
 #ifndef RT_MESH_PREFETCH
 #define RT_MESH_PREFETCH 0     /* 1: L2 prefetch of a leaf's triangle records when the lane parks on it */
 #endif
+#ifndef RT_MESH_PLAIN_SLABS
+#define RT_MESH_PLAIN_SLABS 1  /* hardware min/max in the slab test of NaN-free rays (box_test_plain): C5 +1.0 %, C4 +0.5 % */
+#endif
 #ifndef RT_MESH_TOPCACHE
 #define RT_MESH_TOPCACHE 1     /* newest far entry cached in registers: +0.6 % C4, +2.6 % C5 */
 #endif
@@ -735,6 +738,7 @@ __device__ __forceinline__ void trace_mesh(const DScene& sc, const IO& io, const
     LocalRay r1;
     r1.o = r1.d = r1.inv = mk(0.0f, 0.0f, 0.0f);
     r1.neg = 0;
+    r1.plain = false;
     float best = 0.0f;           // m_t
     int32_t best_rec = -1;       // triangle record accepted in this mesh, if any
     bool any_hit = false;
@@ -821,6 +825,11 @@ __device__ __forceinline__ void trace_mesh(const DScene& sc, const IO& io, const
                 break;
             continue;
         }
+#if RT_MESH_PLAIN_SLABS
+        // warp-uniform: all rays in flight are NaN-free (practically always; an axis-parallel
+        // ray anywhere in the warp sends the whole warp through the std::min/max form)
+        const bool warp_plain = __all_sync(0xffffffffu, !active || r1.plain);
+#endif
 
         #pragma unroll 1
         for (int it = 0; it < RT_MESH_ADVANCE_STEPS && active && !parked && (have_cur || sp > 0); ++it)
@@ -876,8 +885,14 @@ __device__ __forceinline__ void trace_mesh(const DScene& sc, const IO& io, const
                 if (t1 > best)
                     t1 = best;
             }
+#if RT_MESH_PLAIN_SLABS
+            if (!(warp_plain ? box_test_plain(nd.q0, nd.q1, r1.o, r1.inv, t0, t1)
+                             : box_test(nd.q0, nd.q1, r1.o, r1.inv, t0, t1)))
+                continue;
+#else
             if (!box_test(nd.q0, nd.q1, r1.o, r1.inv, t0, t1))
                 continue;
+#endif
             uint32_t axis = flags & RT_NODE_AXIS;
             bool neg = (r1.neg >> axis) & 1u;
             uint32_t near_id = neg ? word : word + 1;

@@ -32,12 +32,20 @@ struct LocalRay
 {
     V3 o, d, inv;
     uint32_t neg;     // bit a set when inv[a] < 0   (dirSigns, RAccel.h:481-486)
+    bool plain;       // the slab arithmetic of this ray cannot produce a NaN (box_test_plain)
 };
+
+__device__ __forceinline__ bool finite_nonzero(float v) { float a = fabsf(v); return a > 0.0f && a < __int_as_float(0x7f800000); }
+__device__ __forceinline__ bool finite_value(float v) { return fabsf(v) < __int_as_float(0x7f800000); }
 
 __device__ __forceinline__ void local_ray_finish(LocalRay& r)
 {
     r.inv = mk(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
     r.neg = (r.inv.x < 0.0f ? 1u : 0u) | (r.inv.y < 0.0f ? 2u : 0u) | (r.inv.z < 0.0f ? 4u : 0u);
+    // (box - origin) * invDir is NaN only as 0 * inf or inf - inf: a zero or denormal direction
+    // component (invDir infinite) or a non-finite origin.  Every other ray is "plain".
+    r.plain = finite_nonzero(r.inv.x) && finite_nonzero(r.inv.y) && finite_nonzero(r.inv.z) &&
+              finite_value(r.o.x) && finite_value(r.o.y) && finite_value(r.o.z);
 }
 
 __device__ __forceinline__ V3 xyz4(float4 v) { return mk(v.x, v.y, v.z); }
