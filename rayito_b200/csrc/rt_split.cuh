@@ -26,6 +26,9 @@
 #include <cuda_pipeline.h>
 #include "rt_wave.cuh"
 
+#ifndef RT_TOP_PLAIN_SLABS
+#define RT_TOP_PLAIN_SLABS 1   /* hardware min/max in the tabulated top-level walk's slab tests (box_test_plain, see trace_mesh): C4 +1.2 % frame, +1.9 % traversal */
+#endif
 #ifndef RT_TOP_REFILL_MIN
 #define RT_TOP_REFILL_MIN 12
 #endif
@@ -463,6 +466,7 @@ __device__ __forceinline__ void trace_top_static(const DScene& sc, const IO& io,
         LocalRay r0;
         r0.o = r0.d = r0.inv = mk(0.0f, 0.0f, 0.0f);
         r0.neg = 0;
+        r0.plain = false;
         WaveResult res;
         res.t = 0.0f; res.shape = -1; res.tri_rec = -1; res.any_hit = false;
         bool open = false;          // still walking
@@ -504,6 +508,10 @@ __device__ __forceinline__ void trace_top_static(const DScene& sc, const IO& io,
         lane_t1[tid] = res.t;
         uint32_t alive = 1u;                // bit d: the node at depth d on the current path was pushed
 
+#if RT_TOP_PLAIN_SLABS
+        // all rays of this warp's group are NaN-free: hardware min/max in the slab tests (box_test_plain)
+        const bool warp_plain = __all_sync(0xffffffffu, !open || r0.plain);
+#endif
         uint32_t todo = __ballot_sync(0xffffffffu, open);
         while (todo)
         {
@@ -539,7 +547,12 @@ __device__ __forceinline__ void trace_top_static(const DScene& sc, const IO& io,
                                 else if (t1 > res.t)
                                     t1 = res.t;
                             }
+#if RT_TOP_PLAIN_SLABS
+                            if (go && (warp_plain ? box_test_plain(nd.q0, nd.q1, r0.o, r0.inv, t0, t1)
+                                                  : box_test(nd.q0, nd.q1, r0.o, r0.inv, t0, t1)))
+#else
                             if (go && box_test(nd.q0, nd.q1, r0.o, r0.inv, t0, t1))
+#endif
                             {
                                 pass = true;
                                 lane_t0[(depth + 1) * stride + tid] = t0;
