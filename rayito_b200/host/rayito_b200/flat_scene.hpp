@@ -9,7 +9,10 @@
 #define RAYITO_B200_FLAT_SCENE_HPP
 
 #include <map>
+#include <memory>
+#include <new>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "rayito_b200.h"
@@ -23,6 +26,23 @@ namespace rayito_b200
 // application built for the Stage 6 API sets it once before building its scene
 // (or compiles with -DRAYITO_B200_STAGE=6, see rayito.h).
 unsigned& stageSemantics();
+
+// std::vector whose resize() leaves new elements uninitialised: the big face and node tables
+// are sized first and then written by the worker threads; zero-filling hundreds of megabytes
+// on one thread beforehand would cost as much as the fill itself.
+template <typename T>
+struct DefaultInitAllocator : std::allocator<T>
+{
+    template <typename U> struct rebind { typedef DefaultInitAllocator<U> other; };
+    DefaultInitAllocator() { }
+    template <typename U> DefaultInitAllocator(const DefaultInitAllocator<U>&) { }
+    template <typename U> void construct(U* p) { ::new (static_cast<void*>(p)) U; }
+    template <typename U, typename A0, typename... Args> void construct(U* p, A0&& a0, Args&&... args)
+    {
+        ::new (static_cast<void*>(p)) U(std::forward<A0>(a0), std::forward<Args>(args)...);
+    }
+};
+template <typename T> struct RawVector { typedef std::vector<T, DefaultInitAllocator<T> > type; };
 
 struct FlatScene
 {
@@ -42,8 +62,8 @@ struct FlatScene
     std::vector<unsigned> meshDepth;
 
     std::vector<float> vertices, normals;
-    std::vector<uint32_t> faceStart, faceHasNormals, vertexIndex, normalIndex;
-    std::vector<RtBvhNode> meshNodes;
+    RawVector<uint32_t>::type faceStart, faceHasNormals, vertexIndex, normalIndex;
+    RawVector<RtBvhNode>::type meshNodes;
     std::vector<float> faceAreaCdf;
 
     std::vector<RtMaterial> materials;
@@ -145,8 +165,8 @@ struct FlatScene
 private:
     std::map<const void*, unsigned> m_materialIndex;
 
-    template <typename V>
-    static const V* ptr(const std::vector<V>& v) { return v.empty() ? NULL : &v[0]; }
+    template <typename V, typename A>
+    static const V* ptr(const std::vector<V, A>& v) { return v.empty() ? NULL : &v[0]; }
 };
 
 } // namespace rayito_b200
