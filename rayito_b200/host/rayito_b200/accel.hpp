@@ -172,11 +172,21 @@ public:
         }
 
         // Uninitialised per-thread scratch, kept between builds (rayito_b200::buildScratch)
-        Item* items = static_cast<Item*>(rayito_b200::buildScratch().get((size_t)count * sizeof(Item)));
-        if (items == NULL)
-            throw std::bad_alloc();
-        BBox whole;
         const unsigned int threads = count >= kParallelElements ? rayito_b200::hostThreads() : 1u;
+        // RAYITO_B200_WIDE_SPLITS=1: the splits at the top of a large tree use every worker inside
+        // the split.  Off by default: identical results (tested), but no faster -- 5 M quads on
+        // the 16-core GPU host: 0.141 s against 0.123 s with each of those splits left to one
+        // worker (tools/host_prepare_timing.py); the three predicate passes and the scattered
+        // swaps cost what the idle workers would have saved.
+        const char* wideEnv = std::getenv("RAYITO_B200_WIDE_SPLITS");
+        const bool wideTop = threads > 1 && count >= kWideElements && wideEnv != NULL && wideEnv[0] == '1';
+        const size_t itemBytes = ((size_t)count * sizeof(Item) + 63) & ~(size_t)63;
+        char* scratch = static_cast<char*>(rayito_b200::buildScratch().get(itemBytes + (wideTop ? (size_t)count * sizeof(unsigned) : 0)));
+        if (scratch == NULL)
+            throw std::bad_alloc();
+        Item* items = reinterpret_cast<Item*>(scratch);
+        unsigned* swapScratch = reinterpret_cast<unsigned*>(scratch + itemBytes);
+        BBox whole;
         {
             // Element boxes; the union keeps the serial left-to-right association
             // (std::min/max keep their first argument on ties, e.g. -0 against +0)
@@ -202,7 +212,28 @@ public:
 
         Job root = { 0, count, 0, 1, 0, rootBox ? *rootBox : whole };
         rayito_b200::JobBag<Job> bag;
-        bag.add(root);
+        // The few splits at the top of a large tree would otherwise run on one worker while
+        // the others wait for subtrees to exist: they are done here with every worker inside
+        // the split (exact parallel std::partition, chunked box unions folded in order).
+        std::vector<Job> wide(1, root);
+        while (!wide.empty())
+        {
+            Job job = wide.back();
+            wide.pop_back();
+            if (!wideTop || job.end - job.begin < kWideElements)
+            {
+                bag.add(job);
+                continue;
+            }
+            if (job.depth > m_maxDepth)
+                m_maxDepth = job.depth;
+            Job left, right;
+            if (splitNode(items, &m_nodes[0], job, left, right, threads, swapScratch))
+            {
+                wide.push_back(right);
+                wide.push_back(left);
+            }
+        }
         std::mutex depthMutex;
         Builder builder = { items, &m_nodes[0], threads > 1 ? kSpawnElements : 0u, &m_maxDepth, &depthMutex };
         bag.drain(threads, builder);
@@ -262,6 +293,74 @@ private:
     static const unsigned int kParallelElements = 1u << 16;
     // Subtrees at least this large are handed to the job bag instead of the local stack
     static const unsigned int kSpawnElements = 1u << 13;
+    // Nodes over at least this many elements are split with every worker inside the split
+    static const unsigned int kWideElements = 1u << 18;
+
+    // One step of buildRange (RAccel.h:290-374) for the node of `job`: leaf, or split axis,
+    // partition, child boxes and the two child jobs.  workers > 1: the partition and the box
+    // unions run on that many threads with results identical to the one-thread order.
+    static bool splitNode(Item* items, BvhNode* nodes, const Job& job, Job& left, Job& right,
+                          unsigned int workers, unsigned* swapScratch)
+    {
+        BvhNode& node = nodes[job.node];
+        node.m_bbox = job.box;
+        if (job.end - job.begin <= 1)
+        {
+            node.m_flags = kLeafNode;
+            node.m_prim = items[job.begin].prim;
+            return false;
+        }
+
+        Vector extent = job.box.m_max - job.box.m_min;
+        BvhNodeFlags axis;
+        if (extent.m_x > extent.m_y)
+            axis = extent.m_x > extent.m_z ? kSplitX : kSplitZ;
+        else
+            axis = extent.m_y > extent.m_z ? kSplitY : kSplitZ;
+        float where = (component(job.box.m_max, axis) + component(job.box.m_min, axis)) * 0.5f;
+        node.m_flags = axis;
+
+        const size_t n = job.end - job.begin;
+        Item* cut = workers > 1
+            ? rayito_b200::parallelPartition(items + job.begin, n, AboveSplit(where, axis), swapScratch, workers)
+            : std::partition(items + job.begin, items + job.end, AboveSplit(where, axis));
+        unsigned int mid = (unsigned int)(cut - items);
+        if (mid <= job.begin || mid >= job.end)
+        {
+            mid = job.begin + (job.end - job.begin) / 2;
+            if (mid < job.begin + 1) mid = job.begin + 1;
+            else if (mid > job.end - 1) mid = job.end - 1;
+        }
+
+        BBox leftBox = unionOf(items, job.begin, mid, workers);
+        BBox rightBox = unionOf(items, mid, job.end, workers);
+
+        node.m_firstChild = job.base;
+        Job l = { job.begin, mid, job.base, job.base + 2, job.depth + 1, leftBox };
+        Job r = { mid, job.end, job.base + 1, job.base + 2 * (mid - job.begin), job.depth + 1, rightBox };
+        left = l;
+        right = r;
+        return true;
+    }
+
+    // Union of the boxes of items [begin, end) in the serial left-to-right association
+    static BBox unionOf(const Item* items, unsigned int begin, unsigned int end, unsigned int workers)
+    {
+        const size_t n = end - begin;
+        unsigned int chunks = workers > 1 && n >= (1u << 16) ? workers : 1u;
+        std::vector<BBox> partial(chunks);
+        BBox* part = &partial[0];
+        const Item* first = items + begin;
+        rayito_b200::parallelChunks(n, chunks, [first, part](unsigned c, size_t b, size_t e) {
+            BBox acc;
+            for (size_t i = b; i < e; ++i) acc = acc.combined(first[i].box);
+            part[c] = acc;
+        });
+        BBox all;
+        for (unsigned int c = 0; c < chunks; ++c)
+            all = all.combined(partial[c]);
+        return all;
+    }
 
     // Builds one subtree depth-first with an explicit work list instead of recursion
     // (degenerate inputs can be ~N deep).
@@ -284,40 +383,9 @@ private:
                 jobs.pop_back();
                 if (job.depth > deepest)
                     deepest = job.depth;
-                BvhNode& node = nodes[job.node];
-                node.m_bbox = job.box;
-                if (job.end - job.begin <= 1)
-                {
-                    node.m_flags = kLeafNode;
-                    node.m_prim = items[job.begin].prim;
+                Job left, right;
+                if (!splitNode(items, nodes, job, left, right, 1u, NULL))
                     continue;
-                }
-
-                Vector extent = job.box.m_max - job.box.m_min;
-                BvhNodeFlags axis;
-                if (extent.m_x > extent.m_y)
-                    axis = extent.m_x > extent.m_z ? kSplitX : kSplitZ;
-                else
-                    axis = extent.m_y > extent.m_z ? kSplitY : kSplitZ;
-                float where = (component(job.box.m_max, axis) + component(job.box.m_min, axis)) * 0.5f;
-                node.m_flags = axis;
-
-                Item* cut = std::partition(items + job.begin, items + job.end, AboveSplit(where, axis));
-                unsigned int mid = (unsigned int)(cut - items);
-                if (mid <= job.begin || mid >= job.end)
-                {
-                    mid = job.begin + (job.end - job.begin) / 2;
-                    if (mid < job.begin + 1) mid = job.begin + 1;
-                    else if (mid > job.end - 1) mid = job.end - 1;
-                }
-
-                BBox leftBox, rightBox;
-                for (unsigned int i = job.begin; i < mid; ++i) leftBox = leftBox.combined(items[i].box);
-                for (unsigned int i = mid; i < job.end; ++i) rightBox = rightBox.combined(items[i].box);
-
-                node.m_firstChild = job.base;
-                Job left = { job.begin, mid, job.base, job.base + 2, job.depth + 1, leftBox };
-                Job right = { mid, job.end, job.base + 1, job.base + 2 * (mid - job.begin), job.depth + 1, rightBox };
                 if (spawnElements != 0 && right.end - right.begin >= spawnElements)
                     bag.add(right);
                 else

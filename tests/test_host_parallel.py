@@ -1,7 +1,8 @@
 """CPU tests: the host worker threads (rayito_b200/host/rayito_b200/parallel.hpp) must not
 change a single bit of what prepare() + flatten hand to the GPU.  A mesh large enough to
 take the threaded path (>= 65 536 faces: subtree jobs, chunked bounds / areas / face tables)
-is prepared with 1, 3 and 8 workers and compared array by array; the single-thread result is
+(and, at 327 680 faces with RAYITO_B200_WIDE_SPLITS=1, the all-worker splits at the top of the tree
+with their exact parallel std::partition) is prepared with 1, 3 and 8 workers and compared array by array; the single-thread result is
 compared node for node with the compiled reference (oracle/_ref), Bvh<T>::build
 (Rayito_Stage7_QT/RAccel.h:262-374) and Mesh::prepare (RMesh.h:89-129)."""
 import ctypes as C
@@ -10,7 +11,7 @@ import os
 import numpy as np
 import pytest
 
-GRID = (320, 256)       # 81 920 quads
+GRID = (640, 512)       # 327 680 quads: above the 262 144-element threshold of the opt-in all-worker top splits (RAYITO_B200_WIDE_SPLITS=1)
 
 
 def _bytes(ptr, nbytes):
@@ -19,16 +20,18 @@ def _bytes(ptr, nbytes):
     return C.string_at(ptr, nbytes)
 
 
-def _snapshot(capi, threads):
-    old = os.environ.get("RAYITO_B200_HOST_THREADS")
+def _snapshot(capi, threads, wide=False):
+    saved = {k: os.environ.get(k) for k in ("RAYITO_B200_HOST_THREADS", "RAYITO_B200_WIDE_SPLITS")}
     os.environ["RAYITO_B200_HOST_THREADS"] = str(threads)
+    os.environ["RAYITO_B200_WIDE_SPLITS"] = "1" if wide else "0"
     try:
         scene = capi.HostScene(capi.RECIPE_SYNTHETIC_MESH, None, GRID)
     finally:
-        if old is None:
-            del os.environ["RAYITO_B200_HOST_THREADS"]
-        else:
-            os.environ["RAYITO_B200_HOST_THREADS"] = old
+        for k, v in saved.items():
+            if v is None:
+                del os.environ[k]
+            else:
+                os.environ[k] = v
     d = scene.desc.contents
     snap = {
         "top_nodes": _bytes(d.top_nodes, d.num_top_nodes * 32),
@@ -52,10 +55,10 @@ def serial(capi):
     return _snapshot(capi, 1)
 
 
-@pytest.mark.parametrize("threads", [3, 8])
-def test_threaded_prepare_is_bit_identical(capi, serial, threads):
+@pytest.mark.parametrize("threads,wide", [(3, False), (8, False), (3, True), (8, True)])
+def test_threaded_prepare_is_bit_identical(capi, serial, threads, wide):
     _scene, want = serial
-    _scene2, got = _snapshot(capi, threads)
+    _scene2, got = _snapshot(capi, threads, wide)
     assert got["counts"] == want["counts"] and want["counts"][0] == GRID[0] * GRID[1]
     for key in want:
         assert got[key] == want[key], "%s differs with %d host threads" % (key, threads)
@@ -98,3 +101,15 @@ def test_app_handle_builds_without_preparing(capi):
         assert b"CUDA" in lib.rth_last_error_string() or b"device" in lib.rth_last_error_string()
     lib.rth_app_destroy(app)
     assert lib.rth_app_create(12345, None, 0, 0) in (None, 0)
+
+
+def test_parallel_partition_equals_std_partition(tmp_path):
+    """rayito_b200::parallelPartition reproduces libstdc++'s std::partition element for element
+    (300 size / split / thread-count cases, including all-true, all-false and tiny ranges)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "parallel_partition_test")
+    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++11", "-pthread", "-I" + os.path.join(root, "rayito_b200", "host"),
+                    os.path.join(root, "tests", "cpp", "parallel_partition_test.cpp"), "-o", exe], check=True, timeout=300)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True, timeout=300).stdout
+    assert "300 cases identical" in out, out
