@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define RT_ABI_VERSION 1
+#define RT_ABI_VERSION 2
 
 typedef enum RtStatus
 {
@@ -218,7 +218,9 @@ typedef struct RtRenderStats
     uint64_t node_pops;           /* BVH nodes popped, both levels (RT_RENDER_COUNT_WORK) */
     uint64_t tri_tests;           /* triangles tested */
     uint64_t shape_tests;         /* analytic shapes tested */
-    uint64_t xform_evals;         /* keyed transforms evaluated */
+    uint64_t xform_evals;         /* Ray::transformToLocal calls (RRay.h:78-81): the set and every shape entered */
+    uint64_t xform_keyed;         /* ... of which on a transform with >= 1 key (the reference reads key data, RMath.h:681-715) */
+    uint64_t xform_pairs;         /* ... of which on a transform with >= 2 keys (a key pair may be read) */
     uint64_t kernel_launches;     /* CUDA kernels launched by this call */
     uint64_t trace_launches;      /* of which traversal kernels (closest / any hit) */
     float render_ms;              /* device time of the render (CUDA events) */
@@ -247,12 +249,20 @@ int rt_trace_any(RtScene* scene, const RtRay* rays, size_t n, uint8_t* hits);
 
 /* Same, on buffers already resident on the scene's device, enqueued on `stream`
  * (a cudaStream_t passed as void*; NULL = the legacy default stream).  These do
- * not synchronise.  work, if not NULL, is a device array of 4 uint64 counters
- * {node_pops, tri_tests, shape_tests, xform_evals} that the kernel adds to. */
+ * not synchronise; up to 16 calls per scene may be in flight on different streams at once
+ * (each takes its own work cursor), and rt_scene_destroy() waits for the device first.  work, if not NULL, is a device array of 6 uint64 counters
+ * {node_pops, tri_tests, shape_tests, xform_evals, xform_keyed, xform_pairs} (meanings as in
+ * RtRenderStats) that the kernel adds to. */
 int rt_trace_closest_device(RtScene* scene, const RtRay* d_rays, size_t n, RtHit* d_hits,
                             uint64_t* d_work, void* stream);
 int rt_trace_any_device(RtScene* scene, const RtRay* d_rays, size_t n, uint8_t* d_hits,
                         uint64_t* d_work, void* stream);
+
+/* rt_trace_closest / rt_trace_any that also return the work of the batch: work[0..5] =
+ * {node_pops, tri_tests, shape_tests, xform_evals, xform_keyed, xform_pairs}, the numbers
+ * the roofline's algorithmic bytes are made of.  Host buffers. */
+int rt_trace_closest_counted(RtScene* scene, const RtRay* rays, size_t n, RtHit* hits, uint64_t* work);
+int rt_trace_any_counted(RtScene* scene, const RtRay* rays, size_t n, uint8_t* hits, uint64_t* work);
 
 /* raytrace() (RaytraceMain.cpp:485-579): render the tiles of this rank into rgb
  * (width*height*3 floats, row-major, rows top-down like Image::pixel).  Pixels

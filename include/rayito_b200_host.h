@@ -27,6 +27,8 @@ enum
     RTH_RECIPE_EDGE_LINEAR_LIST = 7, /* edge-case scenes of the parity tests (host/scene_recipes.h buildEdgeScene) */
     RTH_RECIPE_EDGE_NO_LIGHTS = 8,
     RTH_RECIPE_EDGE_EMPTY = 9,
+    RTH_RECIPE_EDGE_DEEP_MESH = 10, /* wedge mesh of grid_u rows x grid_v quads (0 = 40 x 8): face BVH ~grid_u + log2(grid_v) deep */
+    RTH_RECIPE_EDGE_DEEP_BOTH = 11, /* ... plus a chain of 18 halving spheres: top-level BVH ~18 deep, both stacks > 64 entries */
     RTH_RECIPE_STAGE6_SCENE = 6     /* Stage 6 scene + Stage 6 rules (Rayito_Stage6_QT/MainWindow.cpp:38-146); needs obj_path */
 };
 

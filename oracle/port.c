@@ -27,6 +27,30 @@
 
 typedef struct { float x, y, z; } vec3;
 
+/* ---- work counters ----------------------------------
+ * What the reference's traversal DOES for a ray batch, counted where the restated
+ * algorithm does it: the roofline's algorithmic bytes are defined by these numbers
+ * (bench.py), and tests/test_gpu_counters.py requires the CUDA kernels' own counters
+ * to equal them on the same rays.
+ *   node_pops    BVH nodes taken off a traversal stack, interior and leaf, both levels
+ *                (one iteration of the loops of RAccel.h:405-468 / 493-560)
+ *   tri_tests    Mesh::intersectTri / doesIntersectTri calls (RMesh.h:226-249)
+ *   shape_tests  plane / sphere / rectangle tests (everything but meshes)
+ *   xform_evals  Ray::transformToLocal calls (RRay.h:78-81): the set itself and every
+ *                shape entered, whatever its transform holds
+ *   xform_keyed  ... of which on a transform with at least one key: the reference reads
+ *                that key's time, scale, rotation and translation (RMath.h:681-715)
+ *   xform_pairs  ... of which on a transform with two or more keys (a key PAIR may be read)
+ *   max_stack    largest number of live stack entries any ray reached (RAccel.h:379: 50) */
+typedef struct
+{
+    uint64_t node_pops, tri_tests, shape_tests, xform_evals, xform_keyed, xform_pairs, max_stack_mesh, max_stack_top;
+} port_work_t;
+static port_work_t g_work;
+
+void port_work_reset(void) { memset(&g_work, 0, sizeof(g_work)); }
+void port_work_get(uint64_t* out8) { memcpy(out8, &g_work, sizeof(g_work)); }
+
 /* ---- RMath.h:180-360 ----------------------------------------------------- */
 static vec3 v3(float x, float y, float z) { vec3 r = { x, y, z }; return r; }
 static vec3 vadd(vec3 a, vec3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
@@ -147,6 +171,9 @@ typedef struct
 static ray_t ray_to_local(const RtSceneDesc* d, uint32_t xf, ray_t r)
 {
     ray_t l = r;
+    g_work.xform_evals++;
+    if (d->xforms[xf].num_keys >= 1) g_work.xform_keyed++;
+    if (d->xforms[xf].num_keys >= 2) g_work.xform_pairs++;
     l.o = to_local_point(d, xf, r.time, r.o);
     l.d = to_local_vector(d, xf, r.time, r.d);
     return l;
@@ -187,6 +214,7 @@ static int tri_test(const RtSceneDesc* d, const RtMesh* m, uint32_t face, uint32
 {
     uint32_t gf = m->first_face + face;
     const uint32_t* vi = d->vertex_index + d->face_start[gf];
+    g_work.tri_tests++;
     vec3 p0 = mesh_vertex(d, m, vi[0]), p1 = mesh_vertex(d, m, vi[tri + 1]), p2 = mesh_vertex(d, m, vi[tri + 2]);
     vec3 e1 = vsub(p1, p0), e2 = vsub(p2, p0);
     vec3 g = vcross(e1, e2);
@@ -238,6 +266,8 @@ static int mesh_bvh(const RtSceneDesc* d, const RtMesh* m, ray_t r, int closest,
     {
         unsigned s = num - 1;
         const RtBvhNode* n = &nodes[steps[s].node];
+        g_work.node_pops++;
+        if (num > g_work.max_stack_mesh) g_work.max_stack_mesh = num;
         if (n->flags & 4u)
         {
             uint32_t face = n->first_child_or_prim;
@@ -282,6 +312,7 @@ static int shape_test(const RtSceneDesc* d, uint32_t sid, ray_t ray, int closest
     {
         /* Plane::intersect / doesIntersect, RScene.h:288-363 */
         const RtPlane* p = &d->planes[sh->geom];
+        g_work.shape_tests++;
         vec3 n = v3(p->normal[0], p->normal[1], p->normal[2]);
         vec3 pos = v3(p->position[0], p->position[1], p->position[2]);
         float ndd = vdot(n, l.d);
@@ -301,6 +332,7 @@ static int shape_test(const RtSceneDesc* d, uint32_t sid, ray_t ray, int closest
     {
         /* Sphere::intersect RScene.h:397-466 / doesIntersect :468-512 */
         const RtSphere* s = &d->spheres[sh->geom];
+        g_work.shape_tests++;
         l.o = vsub(l.o, v3(s->position[0], s->position[1], s->position[2]));
         float a = vlen2(l.d);
         float b = 2.0f * vdot(l.d, l.o);
@@ -331,6 +363,7 @@ static int shape_test(const RtSceneDesc* d, uint32_t sid, ray_t ray, int closest
     {
         /* RectangleLight::intersect RLight.h:58-116 / doesIntersect :118-163 */
         const RtRect* rc = &d->rects[sh->geom];
+        g_work.shape_tests++;
         vec3 pos = v3(rc->position[0], rc->position[1], rc->position[2]);
         vec3 s1 = v3(rc->side1[0], rc->side1[1], rc->side1[2]);
         vec3 s2 = v3(rc->side2[0], rc->side2[1], rc->side2[2]);
@@ -383,6 +416,8 @@ static int top_bvh(const RtSceneDesc* d, ray_t r, int closest, isect_t* is)
     {
         unsigned s = num - 1;
         const RtBvhNode* n = &d->top_nodes[steps[s].node];
+        g_work.node_pops++;
+        if (num > g_work.max_stack_top) g_work.max_stack_top = num;
         if (n->flags & 4u)
         {
             if (shape_test(d, n->first_child_or_prim, r, closest, is))

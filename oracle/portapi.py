@@ -30,6 +30,8 @@ def lib():
         L.port_cmj_1d.argtypes = [u32, u32, u32]
         L.port_cmj_2d.argtypes = [u32, u32, u32, u32, C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.port_camera_ray.argtypes = [vp, u32, u32, u32, u32, u32, u32, u32, vp]
+        L.port_work_reset.argtypes = []
+        L.port_work_get.argtypes = [vp]
         _lib = L
     return _lib
 
@@ -58,3 +60,18 @@ def camera_ray(camera, width, height, ps, depth, x, y, psi, ray_dtype):
     out = np.zeros(1, ray_dtype)
     lib().port_camera_ray(C.byref(camera), width, height, ps, depth, x, y, psi, out.ctypes.data)
     return out[0]
+
+
+WORK_FIELDS = ("node_pops", "tri_tests", "shape_tests", "xform_evals", "xform_keyed", "xform_pairs",
+               "max_stack_mesh", "max_stack_top")
+
+
+def work_reset():
+    lib().port_work_reset()
+
+
+def work_counters():
+    """Counters accumulated by port_trace_* since the last work_reset() (oracle/port.c, 'work counters')."""
+    out = np.zeros(8, np.uint64)
+    lib().port_work_get(out.ctypes.data)
+    return dict(zip(WORK_FIELDS, (int(v) for v in out)))

@@ -192,6 +192,8 @@ bool buildInto(RefScene& rs)
     case 2: return rayito_recipes::buildStage7Scene2(*rs.set, *rs.store);
     case 5: return rayito_recipes::buildSyntheticMeshScene(*rs.set, *rs.store, rs.gridU, rs.gridV);
     case 7: case 8: case 9: return rayito_recipes::buildEdgeScene(*rs.set, *rs.store, rs.sceneId - 7);
+    case 10: return rayito_recipes::buildDeepScene(*rs.set, *rs.store, rs.gridU, rs.gridV, 0);
+    case 11: return rayito_recipes::buildDeepScene(*rs.set, *rs.store, rs.gridU, rs.gridV, 18);
     default: return false;
     }
 }

@@ -48,7 +48,8 @@ RT_RENDER_DYNAMIC_TOP = 8
 class RtRenderStats(C.Structure):
     _fields_ = [("samples", C.c_uint64), ("closest_rays", C.c_uint64), ("any_rays", C.c_uint64),
                 ("node_pops", C.c_uint64), ("tri_tests", C.c_uint64), ("shape_tests", C.c_uint64),
-                ("xform_evals", C.c_uint64), ("kernel_launches", C.c_uint64), ("trace_launches", C.c_uint64),
+                ("xform_evals", C.c_uint64), ("xform_keyed", C.c_uint64), ("xform_pairs", C.c_uint64),
+                ("kernel_launches", C.c_uint64), ("trace_launches", C.c_uint64),
                 ("render_ms", C.c_float), ("trace_ms", C.c_float), ("upload_ms", C.c_float), ("download_ms", C.c_float)]
 
     def as_dict(self):
@@ -100,13 +101,15 @@ RECIPE_STAGE6_SCENE = 6
 RECIPE_EDGE_LINEAR_LIST = 7
 RECIPE_EDGE_NO_LIGHTS = 8
 RECIPE_EDGE_EMPTY = 9
+RECIPE_EDGE_DEEP_MESH = 10
+RECIPE_EDGE_DEEP_BOTH = 11
 
 # Every symbol include/rayito_b200.h declares (checked by the CPU test-suite)
 CORE_SYMBOLS = [
     "rt_last_error_string", "rt_abi_version", "rt_device_count",
     "rt_scene_create", "rt_scene_destroy",
     "rt_trace_closest", "rt_trace_closest_ex", "rt_trace_any",
-    "rt_trace_closest_device", "rt_trace_any_device",
+    "rt_trace_closest_device", "rt_trace_any_device", "rt_trace_closest_counted", "rt_trace_any_counted",
     "rt_render", "rt_render_device", "rt_generate_camera_rays", "rt_tonemap_bgra8",
     "rt_tile_owners", "rt_sample_permutations", "rt_cmj_sample1d", "rt_cmj_sample2d", "rt_stage1_render",
     "rt_libm_eval", "rt_stage23_render", "rt_release_cached_memory",
@@ -135,6 +138,8 @@ def core():
         lib.rt_trace_closest.argtypes = [vp, vp, sz, vp]
         lib.rt_trace_closest_ex.argtypes = [vp, vp, sz, vp]
         lib.rt_trace_any.argtypes = [vp, vp, sz, vp]
+        lib.rt_trace_closest_counted.argtypes = [vp, vp, sz, vp, vp]
+        lib.rt_trace_any_counted.argtypes = [vp, vp, sz, vp, vp]
         lib.rt_trace_closest_device.argtypes = [vp, vp, sz, vp, vp, vp]
         lib.rt_trace_any_device.argtypes = [vp, vp, sz, vp, vp, vp]
         lib.rt_render.argtypes = [vp, C.POINTER(RtCamera), C.POINTER(RtRenderParams), vp, C.POINTER(RtRenderStats)]
@@ -266,6 +271,22 @@ class DeviceScene:
         hits = np.empty(len(rays), np.uint8)
         check(core().rt_trace_any(self.handle, rays.ctypes.data, len(rays), hits.ctypes.data), "rt_trace_any")
         return hits
+
+    WORK_FIELDS = ("node_pops", "tri_tests", "shape_tests", "xform_evals", "xform_keyed", "xform_pairs")
+
+    def trace_counted(self, rays, any_hit=False):
+        """(hits, work counters) of one batch: rt_trace_closest_counted / rt_trace_any_counted"""
+        rays = np.ascontiguousarray(rays)
+        assert rays.dtype == RAY_DTYPE
+        work = np.zeros(6, np.uint64)
+        if any_hit:
+            hits = np.empty(len(rays), np.uint8)
+            check(core().rt_trace_any_counted(self.handle, rays.ctypes.data, len(rays), hits.ctypes.data, work.ctypes.data))
+        else:
+            hits = np.empty(len(rays), HIT_DTYPE)
+            check(core().rt_trace_closest_counted(self.handle, rays.ctypes.data, len(rays), hits.ctypes.data,
+                                                  work.ctypes.data))
+        return hits, dict(zip(self.WORK_FIELDS, (int(v) for v in work)))
 
     def render(self, camera, width, height, ps, ls=1, depth=3, rank=0, world=1, tile_size=0,
                max_batch_samples=0, count_work=False, time_trace=False, unified=False, out=None, dynamic_top=False):

@@ -45,8 +45,8 @@ __device__ __forceinline__ void load_ray(const RtRay* rays, size_t i, V3& o, V3&
 __device__ __forceinline__ void flush_work(const WorkCount& wc, uint64_t* work)
 {
     // Warp-reduce, then one atomic per counter per warp
-    uint32_t v[4] = { wc.node_pops, wc.tri_tests, wc.shape_tests, wc.xform_evals };
-    for (int k = 0; k < 4; ++k)
+    uint32_t v[RT_WORK_COUNTERS] = { wc.node_pops, wc.tri_tests, wc.shape_tests, wc.xform_evals, wc.xform_keyed, wc.xform_pairs };
+    for (int k = 0; k < RT_WORK_COUNTERS; ++k)
     {
         uint32_t x = v[k];
         for (int off = 16; off > 0; off >>= 1)
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(128)
 k_trace_batch(const __grid_constant__ DScene sc, const RtRay* __restrict__ rays, uint32_t n,
               float4* raw, uint8_t* any, uint32_t* cursor, uint64_t* work)
 {
-    WorkCount wc = { 0, 0, 0, 0 };
+    WorkCount wc = RT_WORK_ZERO;
     BatchIO io = { rays, raw, any };
     trace_wave<CAP, ANY, COUNT>(sc, io, n, cursor, wc);
     if (COUNT)
@@ -146,14 +146,17 @@ static int launch_batch_trace(RtScene* s, const RtRay* d_rays, size_t n, float4*
 {
     if (n == 0) return RT_OK;
     if (n >= 0xffffffffull) return rt_fail(RT_ERR_ARG, "ray batch too large (>= 2^32 rays)");
-    RT_CUDA(cudaMemsetAsync(s->d_cursor, 0, sizeof(uint32_t), st));
+    // One work cursor per call, taken round-robin from the scene's 16 slots: calls enqueued on
+    // different streams do not share a cursor (more than 16 calls in flight at once would).
+    uint32_t* cursor = s->d_cursor + (s->cursor_next.fetch_add(1u) % RT_SCENE_CURSORS);
+    RT_CUDA(cudaMemsetAsync(cursor, 0, sizeof(uint32_t), st));
     const uint32_t n32 = (uint32_t)n;
     if (s->stack_cap <= 32)
-        k_trace_batch<32, ANY, COUNT><<<persistent_blocks((const void*)k_trace_batch<32, ANY, COUNT>, s->device), 128, 0, st>>>(s->d, d_rays, n32, raw, any, s->d_cursor, d_work);
+        k_trace_batch<32, ANY, COUNT><<<persistent_blocks((const void*)k_trace_batch<32, ANY, COUNT>, s->device), 128, 0, st>>>(s->d, d_rays, n32, raw, any, cursor, d_work);
     else if (s->stack_cap <= 64)
-        k_trace_batch<64, ANY, COUNT><<<persistent_blocks((const void*)k_trace_batch<64, ANY, COUNT>, s->device), 128, 0, st>>>(s->d, d_rays, n32, raw, any, s->d_cursor, d_work);
+        k_trace_batch<64, ANY, COUNT><<<persistent_blocks((const void*)k_trace_batch<64, ANY, COUNT>, s->device), 128, 0, st>>>(s->d, d_rays, n32, raw, any, cursor, d_work);
     else
-        k_trace_batch<104, ANY, COUNT><<<persistent_blocks((const void*)k_trace_batch<104, ANY, COUNT>, s->device), 128, 0, st>>>(s->d, d_rays, n32, raw, any, s->d_cursor, d_work);
+        k_trace_batch<104, ANY, COUNT><<<persistent_blocks((const void*)k_trace_batch<104, ANY, COUNT>, s->device), 128, 0, st>>>(s->d, d_rays, n32, raw, any, cursor, d_work);
     RT_CUDA(cudaGetLastError());
     return RT_OK;
 }
@@ -227,6 +230,10 @@ int rt_scene_destroy(RtScene* s)
 {
     if (s == NULL) return RT_OK;
     cudaSetDevice(s->device);
+    // The *_device entry points do not synchronise and may still be running on a caller's
+    // (non-blocking) stream: nothing of this scene may go back to the pool, where the next
+    // rt_scene_create would overwrite it, before the device is idle.
+    cudaDeviceSynchronize();
     rt_render_release(s);
     rt_detail::pool_free(s->device, s->scratch_in, s->scratch_in_bytes);
     rt_detail::pool_free(s->device, s->scratch_out, s->scratch_out_bytes);
@@ -298,6 +305,36 @@ int rt_trace_any(RtScene* s, const RtRay* rays, size_t n, uint8_t* hits)
     if (rc != RT_OK) return rc;
     RT_CUDA(cudaMemcpy(hits, s->scratch_out, n, cudaMemcpyDeviceToHost));
     return RT_OK;
+}
+
+// Host-buffer traces that also return the work counters (tests pin them to the oracle's)
+static int trace_counted(RtScene* s, const RtRay* rays, size_t n, void* hits, bool any, uint64_t* work)
+{
+    if (s == NULL || work == NULL || (n && (rays == NULL || hits == NULL))) return rt_fail(RT_ERR_ARG, "null argument");
+    std::memset(work, 0, RT_WORK_COUNTERS * sizeof(uint64_t));
+    if (n == 0) return RT_OK;
+    RT_CUDA(cudaSetDevice(s->device));
+    int rc = ensure_scratch(s, n * sizeof(RtRay), any ? n : n * sizeof(RtHit));
+    if (rc != RT_OK) return rc;
+    RT_CUDA(cudaMemcpy(s->scratch_in, rays, n * sizeof(RtRay), cudaMemcpyHostToDevice));
+    RT_CUDA(cudaMemset(s->d_work, 0, RT_WORK_COUNTERS * sizeof(uint64_t)));
+    const RtRay* d_rays = static_cast<const RtRay*>(s->scratch_in);
+    rc = any ? launch_any<true>(s, d_rays, n, static_cast<uint8_t*>(s->scratch_out), s->d_work, 0)
+             : launch_closest<true, false>(s, d_rays, n, s->scratch_out, static_cast<float4*>(s->scratch_out), s->d_work, 0);
+    if (rc != RT_OK) return rc;
+    RT_CUDA(cudaMemcpy(hits, s->scratch_out, any ? n : n * sizeof(RtHit), cudaMemcpyDeviceToHost));
+    RT_CUDA(cudaMemcpy(work, s->d_work, RT_WORK_COUNTERS * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return RT_OK;
+}
+
+int rt_trace_closest_counted(RtScene* s, const RtRay* rays, size_t n, RtHit* hits, uint64_t* work)
+{
+    return trace_counted(s, rays, n, hits, false, work);
+}
+
+int rt_trace_any_counted(RtScene* s, const RtRay* rays, size_t n, uint8_t* hits, uint64_t* work)
+{
+    return trace_counted(s, rays, n, hits, true, work);
 }
 
 int rt_render(RtScene* s, const RtCamera* camera, const RtRenderParams* params, float* rgb, RtRenderStats* stats)

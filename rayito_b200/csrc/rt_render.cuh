@@ -106,7 +106,7 @@ struct RenderCtx
     uint32_t* q_resume[2];      // ... for a top-level resume pass
     SplitBufs split;            // suspended-ray state
     uint32_t* ctl;              // CTL_WORDS queue counters
-    uint64_t* totals;           // 0 closest rays, 1 any rays, 2..5 work counters
+    uint64_t* totals;           // 0 closest rays, 1 any rays, 2..7 work counters (RT_WORK_COUNTERS)
     float* image;               // width*height*3
 };
 
@@ -315,8 +315,8 @@ k_camera_rays(const __grid_constant__ RenderCtx c, uint32_t psi, RtRay* out)
 
 __device__ __forceinline__ void flush_work_counters(const WorkCount& wc, uint64_t* totals)
 {
-    uint32_t v[4] = { wc.node_pops, wc.tri_tests, wc.shape_tests, wc.xform_evals };
-    for (int k = 0; k < 4; ++k)
+    uint32_t v[RT_WORK_COUNTERS] = { wc.node_pops, wc.tri_tests, wc.shape_tests, wc.xform_evals, wc.xform_keyed, wc.xform_pairs };
+    for (int k = 0; k < RT_WORK_COUNTERS; ++k)
     {
         uint32_t x = v[k];
         for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
@@ -437,7 +437,7 @@ k_trace_paths(const __grid_constant__ RenderCtx c, int cur)
     const uint32_t n = io.count();
     if (blockIdx.x == 0 && threadIdx.x == 0)
         atomicAdd(reinterpret_cast<unsigned long long*>(c.totals + 0), (unsigned long long)n);
-    WorkCount wc = { 0, 0, 0, 0 };
+    WorkCount wc = RT_WORK_ZERO;
     trace_wave<CAP, false, COUNT>(c.sc, io, n, c.ctl + CTL_CUR_PATH, wc);
     if (COUNT)
         flush_work_counters(wc, c.totals);
@@ -458,7 +458,7 @@ k_split_top(const __grid_constant__ DScene sc, const IO io, const SplitBufs sb, 
     split_zero(ps);
     if (FRESH && count_slot >= 0 && blockIdx.x == 0 && threadIdx.x == 0)
         atomicAdd(reinterpret_cast<unsigned long long*>(totals + count_slot), (unsigned long long)io.count());
-    WorkCount wc = { 0, 0, 0, 0 };
+    WorkCount wc = RT_WORK_ZERO;
     trace_top<ANY, COUNT, FRESH>(sc, io, sb, ps, wc);
     if (COUNT)
         flush_work_counters(wc, totals);
@@ -482,7 +482,7 @@ k_split_top_static(const __grid_constant__ DScene sc, const IO io, const SplitBu
     split_zero(ps);
     if (count_slot >= 0 && blockIdx.x == 0 && threadIdx.x == 0)
         atomicAdd(reinterpret_cast<unsigned long long*>(totals + count_slot), (unsigned long long)io.count());
-    WorkCount wc = { 0, 0, 0, 0 };
+    WorkCount wc = RT_WORK_ZERO;
     trace_top_static<ANY, COUNT>(sc, io, sb, ps, wc, lane_t0, lane_t1, stage_rec);
     if (COUNT)
         flush_work_counters(wc, totals);
@@ -493,7 +493,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_MESH_MINBLOCKS)
 k_split_mesh(const __grid_constant__ DScene sc, const IO io, const SplitBufs sb, const SplitPass ps, uint64_t* totals)
 {
     split_zero(ps);
-    WorkCount wc = { 0, 0, 0, 0 };
+    WorkCount wc = RT_WORK_ZERO;
     trace_mesh<CAP, ANY, COUNT>(sc, io, sb, ps, wc);
     if (COUNT)
         flush_work_counters(wc, totals);
@@ -746,7 +746,7 @@ k_trace_shadow(const __grid_constant__ RenderCtx c)
     const uint32_t n = io.count();
     if (blockIdx.x == 0 && threadIdx.x == 0)
         atomicAdd(reinterpret_cast<unsigned long long*>(c.totals + 1), (unsigned long long)n);
-    WorkCount wc = { 0, 0, 0, 0 };
+    WorkCount wc = RT_WORK_ZERO;
     trace_wave<CAP, true, COUNT>(c.sc, io, n, c.ctl + CTL_CUR_SHADOW, wc);
     if (COUNT)
         flush_work_counters(wc, c.totals);
@@ -761,7 +761,7 @@ k_trace_mis(const __grid_constant__ RenderCtx c)
     const uint32_t n = io.count();
     if (blockIdx.x == 0 && threadIdx.x == 0)
         atomicAdd(reinterpret_cast<unsigned long long*>(c.totals + 0), (unsigned long long)n);
-    WorkCount wc = { 0, 0, 0, 0 };
+    WorkCount wc = RT_WORK_ZERO;
     trace_wave<CAP, false, COUNT>(c.sc, io, n, c.ctl + CTL_CUR_MIS, wc);
     if (COUNT)
         flush_work_counters(wc, c.totals);
@@ -1499,6 +1499,8 @@ inline int rt_render_impl(RtScene* s, const RtCamera* camera, const RtRenderPara
         stats->tri_tests = totals[3];
         stats->shape_tests = totals[4];
         stats->xform_evals = totals[5];
+        stats->xform_keyed = totals[6];
+        stats->xform_pairs = totals[7];
         stats->kernel_launches = launches;
         cudaEventElapsedTime(&stats->upload_ms, rb->ev[0], rb->ev[1]);
         cudaEventElapsedTime(&stats->render_ms, rb->ev[1], rb->ev[2]);

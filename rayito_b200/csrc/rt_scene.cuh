@@ -31,6 +31,8 @@ int rt_cuda_fail(cudaError_t e, const char* where);
         if (e__ != cudaSuccess) return rt_cuda_fail(e__, #call);    \
     } while (0)
 
+#define RT_SCENE_CURSORS 16
+
 struct RtScene
 {
     int device;
@@ -50,8 +52,9 @@ struct RtScene
     void* scratch_in;
     void* scratch_out;
     size_t scratch_in_bytes, scratch_out_bytes;
-    uint64_t* d_work;           // 4 counters
-    uint32_t* d_cursor;         // queue cursor of the ray-batch entry points
+    uint64_t* d_work;           // RT_WORK_COUNTERS counters
+    uint32_t* d_cursor;         // RT_SCENE_CURSORS queue cursors of the ray-batch entry points, one per call in flight
+    std::atomic<uint32_t> cursor_next;
     struct RenderBuffers* render;   // wavefront state (rt_render.cuh), lazily created
     bool dynamic_top;           // this render: use the per-lane top-level pass even if a walk table exists
 };
@@ -775,6 +778,7 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
     sc->scratch_in_bytes = sc->scratch_out_bytes = 0;
     sc->d_work = NULL;
     sc->d_cursor = NULL;
+    sc->cursor_next.store(0);
     sc->arena_alloc = sc->work_alloc = sc->cursor_alloc = 0;
     sc->render = NULL;
     sc->dynamic_top = false;
@@ -784,8 +788,8 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     cudaError_t err = pool_alloc(device, &sc->arena, sc->arena_bytes, &sc->arena_alloc);
-    if (err == cudaSuccess) err = pool_alloc(device, (void**)&sc->d_work, 4 * sizeof(uint64_t), &sc->work_alloc);
-    if (err == cudaSuccess) err = cudaMemset(sc->d_work, 0, 4 * sizeof(uint64_t));
+    if (err == cudaSuccess) err = pool_alloc(device, (void**)&sc->d_work, 8 * sizeof(uint64_t), &sc->work_alloc);
+    if (err == cudaSuccess) err = cudaMemset(sc->d_work, 0, 8 * sizeof(uint64_t));
     if (err == cudaSuccess) err = pool_alloc(device, (void**)&sc->d_cursor, 64, &sc->cursor_alloc);
     cudaEventRecord(e0, 0);
     if (err == cudaSuccess) err = cudaMemcpy(sc->arena, ab.block, sc->arena_bytes, cudaMemcpyHostToDevice);

@@ -153,7 +153,7 @@ __device__ __forceinline__ void trace_top(const DScene& sc, const IO& io, const 
                     res.tri_rec = -1;
                     res.any_hit = false;
                     TRS set_trs = xform_eval(sc, sc.set_xform, time);
-                    if (COUNT) wc.xform_evals++;
+                    count_xform<COUNT>(sc, sc.set_xform, wc);
                     r0.o = to_local_point(set_trs, o);
                     r0.d = to_local_vector(set_trs, d);
                     local_ray_finish(r0);
@@ -164,7 +164,8 @@ __device__ __forceinline__ void trace_top(const DScene& sc, const IO& io, const 
                         TRS trs = shape_xform(sc, sh, time);
                         V3 lo = to_local_point(trs, r0.o);
                         V3 ld = to_local_vector(trs, r0.d);
-                        if (COUNT) { wc.xform_evals++; wc.shape_tests++; }
+                        count_xform<COUNT>(sc, sh.xform, wc);
+                        if (COUNT) wc.shape_tests++;
                         float t;
                         if (plane_test(sc.planes[sh.geom], lo, ld, res.t, t))
                         {
@@ -290,7 +291,7 @@ __device__ __forceinline__ void trace_top(const DScene& sc, const IO& io, const 
                 if (m.num_nodes > 0)
                 {
                     TRS trs = shape_xform(sc, sh, time);
-                    if (COUNT) wc.xform_evals++;
+                    count_xform<COUNT>(sc, sh.xform, wc);
                     LocalRay rm;
                     rm.o = to_local_point(trs, r0.o);
                     rm.d = to_local_vector(trs, r0.d);
@@ -317,7 +318,7 @@ __device__ __forceinline__ void trace_top(const DScene& sc, const IO& io, const 
             else
             {
                 TRS trs = shape_xform(sc, sh, time);
-                if (COUNT) wc.xform_evals++;
+                count_xform<COUNT>(sc, sh.xform, wc);
                 V3 lo = to_local_point(trs, r0.o);
                 V3 ld = to_local_vector(trs, r0.d);
                 if (sh.type == RT_SHAPE_SPHERE)
@@ -482,7 +483,7 @@ __device__ __forceinline__ void trace_top_static(const DScene& sc, const IO& io,
 #endif
             res.t = tmax;
             TRS set_trs = xform_eval(sc, sc.set_xform, time);
-            if (COUNT) wc.xform_evals++;
+            count_xform<COUNT>(sc, sc.set_xform, wc);
             r0.o = to_local_point(set_trs, o);
             r0.d = to_local_vector(set_trs, d);
             local_ray_finish(r0);
@@ -493,7 +494,8 @@ __device__ __forceinline__ void trace_top_static(const DScene& sc, const IO& io,
                 TRS trs = shape_xform(sc, sh, time);
                 V3 lo = to_local_point(trs, r0.o);
                 V3 ld = to_local_vector(trs, r0.d);
-                if (COUNT) { wc.xform_evals++; wc.shape_tests++; }
+                count_xform<COUNT>(sc, sh.xform, wc);
+                if (COUNT) wc.shape_tests++;
                 float t;
                 if (plane_test(sc.planes[sh.geom], lo, ld, res.t, t))
                 {
@@ -578,7 +580,7 @@ __device__ __forceinline__ void trace_top_static(const DScene& sc, const IO& io,
                     if (here && m.num_nodes > 0)
                     {
                         TRS trs = shape_xform(sc, sh, time);
-                        if (COUNT) wc.xform_evals++;
+                        count_xform<COUNT>(sc, sh.xform, wc);
                         LocalRay rm;
                         rm.o = to_local_point(trs, r0.o);
                         rm.d = to_local_vector(trs, r0.d);
@@ -633,7 +635,7 @@ __device__ __forceinline__ void trace_top_static(const DScene& sc, const IO& io,
                 else if (here)
                 {
                     TRS trs = shape_xform(sc, sh, time);
-                    if (COUNT) wc.xform_evals++;
+                    count_xform<COUNT>(sc, sh.xform, wc);
                     V3 lo = to_local_point(trs, r0.o);
                     V3 ld = to_local_vector(trs, r0.d);
                     if (sh.type == RT_SHAPE_SPHERE)

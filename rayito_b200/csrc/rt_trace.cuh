@@ -26,7 +26,11 @@
 struct WorkCount
 {
     uint32_t node_pops, tri_tests, shape_tests, xform_evals;
+    uint32_t xform_keyed;    // ... of which on a transform with at least one key (the reference reads key data)
+    uint32_t xform_pairs;    // ... of which on a transform with two or more keys (a key pair may be read)
 };
+#define RT_WORK_COUNTERS 6
+#define RT_WORK_ZERO { 0, 0, 0, 0, 0, 0 }
 
 struct LocalRay
 {
@@ -109,6 +113,19 @@ __device__ __forceinline__ TRS shape_xform(const DScene& sc, const DShape& sh, f
         return r;
     }
     return xform_eval(sc, sh.xform, time);
+}
+
+// One Ray::transformToLocal of the reference (RRay.h:78-81) on transform `xform`
+template <bool COUNT>
+__device__ __forceinline__ void count_xform(const DScene& sc, uint32_t xform, WorkCount& wc)
+{
+    if (COUNT)
+    {
+        wc.xform_evals++;
+        const uint32_t nk = sc.xforms[xform].num_keys;
+        wc.xform_keyed += nk >= 1u ? 1u : 0u;
+        wc.xform_pairs += nk >= 2u ? 1u : 0u;
+    }
 }
 
 // Shading inputs of the winning hit: Intersection::m_normal and m_colorModifier

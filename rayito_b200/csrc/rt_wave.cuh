@@ -105,7 +105,7 @@ __device__ __forceinline__ void trace_wave(const DScene& sc, const IO& io, uint3
                     res.any_hit = false;
                     // ray into set-local space (RScene.h:123-124 / :161)
                     TRS set_trs = xform_eval(sc, sc.set_xform, time);
-                    if (COUNT) wc.xform_evals++;
+                    count_xform<COUNT>(sc, sc.set_xform, wc);
                     r0.o = to_local_point(set_trs, o);
                     r0.d = to_local_vector(set_trs, d);
                     local_ray_finish(r0);
@@ -117,7 +117,8 @@ __device__ __forceinline__ void trace_wave(const DScene& sc, const IO& io, uint3
                         TRS trs = shape_xform(sc, sh, time);
                         V3 lo = to_local_point(trs, r0.o);
                         V3 ld = to_local_vector(trs, r0.d);
-                        if (COUNT) { wc.xform_evals++; wc.shape_tests++; }
+                        count_xform<COUNT>(sc, sh.xform, wc);
+                        if (COUNT) wc.shape_tests++;
                         float t;
                         if (plane_test(sc.planes[sh.geom], lo, ld, res.t, t))
                         {
@@ -245,7 +246,7 @@ __device__ __forceinline__ void trace_wave(const DScene& sc, const IO& io, uint3
         {
             DShape sh = load_shape(sc, park_word);
             TRS trs = shape_xform(sc, sh, time);
-            if (COUNT) wc.xform_evals++;
+            count_xform<COUNT>(sc, sh.xform, wc);
             V3 lo = to_local_point(trs, r0.o);
             V3 ld = to_local_vector(trs, r0.d);
             if (sh.type == RT_SHAPE_MESH)

@@ -402,6 +402,39 @@ struct StageScope
     ~StageScope() { rayito_b200::stageSemantics() = saved; }
 };
 
+
+// One place that maps a recipe id to its scene-building code (the same switch serves
+// rth_scene_create, rth_raytrace and rth_app_create)
+bool buildRecipe(Rayito::ShapeSet& set, rayito_recipes::SceneStore& store, int recipe, const char* obj_path,
+                        unsigned grid_u, unsigned grid_v, rayito_recipes::CameraSpec* camera)
+{
+    const char* obj = obj_path ? obj_path : "";
+    rayito_recipes::CameraSpec cam = rayito_recipes::defaultCameraScene1();
+    bool built = false;
+    switch (recipe)
+    {
+    case RTH_RECIPE_STAGE6_SCENE:
+        cam = rayito_recipes::defaultCameraStage6();
+        built = rayito_recipes::buildStage6Scene(set, store, obj);
+        break;
+    case RTH_RECIPE_STAGE7_SCENE1: built = rayito_recipes::buildStage7Scene1(set, store, obj); break;
+    case RTH_RECIPE_STAGE7_SCENE1_MESHLIGHT: built = rayito_recipes::buildStage7Scene1(set, store, obj, true); break;
+    case RTH_RECIPE_STAGE7_SCENE2:
+        cam = rayito_recipes::defaultCameraScene2();
+        built = rayito_recipes::buildStage7Scene2(set, store);
+        break;
+    case RTH_RECIPE_SYNTHETIC_MESH: built = rayito_recipes::buildSyntheticMeshScene(set, store, grid_u, grid_v); break;
+    case RTH_RECIPE_EDGE_LINEAR_LIST: case RTH_RECIPE_EDGE_NO_LIGHTS: case RTH_RECIPE_EDGE_EMPTY:
+        built = rayito_recipes::buildEdgeScene(set, store, recipe - RTH_RECIPE_EDGE_LINEAR_LIST);
+        break;
+    case RTH_RECIPE_EDGE_DEEP_MESH: built = rayito_recipes::buildDeepScene(set, store, grid_u, grid_v, 0); break;
+    case RTH_RECIPE_EDGE_DEEP_BOTH: built = rayito_recipes::buildDeepScene(set, store, grid_u, grid_v, 18); break;
+    default: break;
+    }
+    if (camera) *camera = cam;
+    return built;
+}
+
 RthScene* finish(RthScene* s, bool built)
 {
     if (!built)
@@ -443,42 +476,8 @@ const char* rth_last_error_string(void) { return t_hostError.c_str(); }
 RthScene* rth_scene_create(int recipe, const char* obj_path, unsigned grid_u, unsigned grid_v)
 {
     RthScene* s = new RthScene();
-    bool built = false;
     StageScope stage(recipe == RTH_RECIPE_STAGE6_SCENE ? RT_SEMANTICS_STAGE6 : RT_SEMANTICS_STAGE7);
-    switch (recipe)
-    {
-    case RTH_RECIPE_STAGE6_SCENE:
-        s->cameraSpec = rayito_recipes::defaultCameraStage6();
-        built = rayito_recipes::buildStage6Scene(s->set, s->store, obj_path ? obj_path : "");
-        break;
-    case RTH_RECIPE_STAGE7_SCENE1:
-        s->cameraSpec = rayito_recipes::defaultCameraScene1();
-        built = rayito_recipes::buildStage7Scene1(s->set, s->store, obj_path ? obj_path : "");
-        break;
-    case RTH_RECIPE_STAGE7_SCENE1_MESHLIGHT:
-        s->cameraSpec = rayito_recipes::defaultCameraScene1();
-        built = rayito_recipes::buildStage7Scene1(s->set, s->store, obj_path ? obj_path : "", true);
-        break;
-    case RTH_RECIPE_STAGE7_SCENE2:
-        s->cameraSpec = rayito_recipes::defaultCameraScene2();
-        built = rayito_recipes::buildStage7Scene2(s->set, s->store);
-        break;
-    case RTH_RECIPE_SYNTHETIC_MESH:
-        s->cameraSpec = rayito_recipes::defaultCameraScene1();
-        built = rayito_recipes::buildSyntheticMeshScene(s->set, s->store, grid_u, grid_v);
-        break;
-    case RTH_RECIPE_EDGE_LINEAR_LIST:
-    case RTH_RECIPE_EDGE_NO_LIGHTS:
-    case RTH_RECIPE_EDGE_EMPTY:
-        s->cameraSpec = rayito_recipes::defaultCameraScene1();
-        built = rayito_recipes::buildEdgeScene(s->set, s->store, recipe - RTH_RECIPE_EDGE_LINEAR_LIST);
-        break;
-    default:
-        t_hostError = "unknown recipe";
-        delete s;
-        return NULL;
-    }
-    return finish(s, built);
+    return finish(s, buildRecipe(s->set, s->store, recipe, obj_path, grid_u, grid_v, &s->cameraSpec));
 }
 
 void rth_scene_destroy(RthScene* s) { delete s; }
@@ -522,19 +521,8 @@ int rth_raytrace(int recipe, const char* obj_path, unsigned grid_u, unsigned gri
     {
         Rayito::ShapeSet set;
         rayito_recipes::SceneStore store;
-        bool built = false;
         StageScope stage(recipe == RTH_RECIPE_STAGE6_SCENE ? RT_SEMANTICS_STAGE6 : RT_SEMANTICS_STAGE7);
-        switch (recipe)
-        {
-        case RTH_RECIPE_STAGE6_SCENE: built = rayito_recipes::buildStage6Scene(set, store, obj_path ? obj_path : ""); break;
-        case RTH_RECIPE_STAGE7_SCENE1: built = rayito_recipes::buildStage7Scene1(set, store, obj_path ? obj_path : ""); break;
-        case RTH_RECIPE_STAGE7_SCENE1_MESHLIGHT: built = rayito_recipes::buildStage7Scene1(set, store, obj_path ? obj_path : "", true); break;
-        case RTH_RECIPE_STAGE7_SCENE2: built = rayito_recipes::buildStage7Scene2(set, store); break;
-        case RTH_RECIPE_SYNTHETIC_MESH: built = rayito_recipes::buildSyntheticMeshScene(set, store, grid_u, grid_v); break;
-        case RTH_RECIPE_EDGE_LINEAR_LIST: case RTH_RECIPE_EDGE_NO_LIGHTS: case RTH_RECIPE_EDGE_EMPTY:
-            built = rayito_recipes::buildEdgeScene(set, store, recipe - RTH_RECIPE_EDGE_LINEAR_LIST); break;
-        default: break;
-        }
+        bool built = buildRecipe(set, store, recipe, obj_path, grid_u, grid_v, NULL);
         if (!built)
         {
             t_hostError = "scene recipe failed";
@@ -568,19 +556,7 @@ RthApp* rth_app_create(int recipe, const char* obj_path, unsigned grid_u, unsign
     RthApp* app = new RthApp();
     app->semantics = recipe == RTH_RECIPE_STAGE6_SCENE ? RT_SEMANTICS_STAGE6 : RT_SEMANTICS_STAGE7;
     StageScope stage(app->semantics);
-    bool built = false;
-    const char* obj = obj_path ? obj_path : "";
-    switch (recipe)
-    {
-    case RTH_RECIPE_STAGE6_SCENE: built = rayito_recipes::buildStage6Scene(app->set, app->store, obj); break;
-    case RTH_RECIPE_STAGE7_SCENE1: built = rayito_recipes::buildStage7Scene1(app->set, app->store, obj); break;
-    case RTH_RECIPE_STAGE7_SCENE1_MESHLIGHT: built = rayito_recipes::buildStage7Scene1(app->set, app->store, obj, true); break;
-    case RTH_RECIPE_STAGE7_SCENE2: built = rayito_recipes::buildStage7Scene2(app->set, app->store); break;
-    case RTH_RECIPE_SYNTHETIC_MESH: built = rayito_recipes::buildSyntheticMeshScene(app->set, app->store, grid_u, grid_v); break;
-    case RTH_RECIPE_EDGE_LINEAR_LIST: case RTH_RECIPE_EDGE_NO_LIGHTS: case RTH_RECIPE_EDGE_EMPTY:
-        built = rayito_recipes::buildEdgeScene(app->set, app->store, recipe - RTH_RECIPE_EDGE_LINEAR_LIST); break;
-    default: break;
-    }
+    bool built = buildRecipe(app->set, app->store, recipe, obj_path, grid_u, grid_v, NULL);
     if (!built)
     {
         t_hostError = "scene recipe failed (unknown recipe, or the OBJ mesh could not be read)";

@@ -411,6 +411,105 @@ bool buildEdgeScene(SetT& set, SceneStore& st, int variant)
     return true;
 }
 
+// Wedge of `levels` x `across` quads whose rows halve in size towards the tip: row j spans
+// x in [2^-j, 2^-(j+1)] (times 2) and z in +-0.3 x.  Bvh::build splits at the MIDPOINT of the
+// longest axis (RAccel.h:319-339), so every split along x peels exactly one row off and the face
+// BVH is about levels + log2(across) deep -- far deeper than a balanced tree over as few faces,
+// which is what the deep-stack traversal kernels need.  Even rows carry per-vertex normals, odd
+// rows are flat shaded.  Geometry is generated in double and rounded once to float.
+inline Rayito::Mesh* makeWedgeMesh(unsigned levels, unsigned across)
+{
+    using namespace Rayito;
+    std::vector<Point> verts;
+    std::vector<Vector> normals;
+    std::vector<Face> faces;
+    for (unsigned j = 0; j <= levels; ++j)
+    {
+        double x = std::ldexp(2.0, -(int)j);
+        for (unsigned i = 0; i <= across; ++i)
+        {
+            double z = x * 0.6 * ((double)i / (double)across - 0.5);
+            double y = 0.15 * x * std::sin(1.7 * i + 0.9 * j);
+            verts.push_back(Point((float)x, (float)y, (float)z));
+            normals.push_back(Vector((float)(0.1 * std::sin(0.8 * i)), 1.0f, (float)(0.1 * std::cos(1.3 * j))).normalized());
+        }
+    }
+    faces.resize((size_t)levels * across);
+    size_t f = 0;
+    for (unsigned j = 0; j < levels; ++j)
+    {
+        for (unsigned i = 0; i < across; ++i, ++f)
+        {
+            unsigned a = j * (across + 1) + i;
+            unsigned idx[4] = { a, a + 1, a + (across + 1) + 1, a + (across + 1) };
+            for (int k = 0; k < 4; ++k)
+            {
+                faces[f].m_vertexIndices.push_back(idx[k]);
+                if ((j & 1u) == 0)
+                    faces[f].m_normalIndices.push_back(idx[k]);
+            }
+        }
+    }
+    return new Mesh(verts, normals, faces, NULL);
+}
+
+// Deep-tree edge scenes for the parity tests: the wedge mesh (face BVH deeper than 32, so the
+// traversal kernels' deep-stack instantiations run) under a rotation key pair, a matte sphere, a
+// rectangle light and a moving sphere light.  chain > 0 adds that many spheres whose positions
+// and radii halve from one to the next, which makes the TOP-level BVH about `chain` deep as well:
+// the two stacks together then need more than 64 entries.
+template <typename SetT>
+bool buildDeepScene(SetT& set, SceneStore& st, unsigned levels, unsigned across, unsigned chain)
+{
+    using namespace Rayito;
+    if (levels == 0) levels = 40;
+    if (across == 0) across = 8;
+    Material* ground = st.keep(new DiffuseMaterial(Color(0.6f, 0.6f, 0.9f)));
+    Material* glossy = st.keep(new GlossyMaterial(Color(0.8f, 0.5f, 0.2f), 0.3f));
+    Material* matte  = st.keep(new DiffuseMaterial(Color(0.3f, 0.8f, 0.4f)));
+    Material* mirror = st.keep(new ReflectionMaterial(Color(0.8f, 0.8f, 0.7f)));
+
+    Plane* plane = st.add(new Plane(Point(), Vector(0.0f, 1.0f, 0.0f), ground, true));
+    plane->transform().translate(0.0f, Vector(0.0f, -2.0f, 0.0f));
+    set.addShape(plane);
+
+    Mesh* wedge = RAYITO_RECIPE_WRAP_MESH(makeWedgeMesh(levels, across));
+    st.add(wedge);
+    wedge->setMaterial(glossy);
+    wedge->transform().setTranslation(0.0f, Vector(-0.5f, -0.5f, 0.0f));
+    wedge->transform().rotate(1.0f, Quaternion(Vector(0.0f, 1.0f, 0.0f), M_PI / 8.0f));
+    set.addShape(wedge);
+
+    Sphere* side = st.add(new Sphere(Point(), 0.75f, matte));
+    side->transform().translate(0.0f, Vector(2.2f, -1.25f, 1.5f));
+    set.addShape(side);
+
+    for (unsigned k = 0; k < chain; ++k)
+    {
+        float s = std::ldexp(1.0f, -(int)k);
+        Sphere* bead = st.add(new Sphere(Point(), 0.4f * s, (k & 1u) ? mirror : matte));
+        bead->transform().setTranslation(0.0f, Vector(-3.0f + 6.0f * s, 1.5f * s - 1.0f, -1.0f));
+        if (k == 2)
+            bead->transform().setTranslation(1.0f, Vector(-3.0f + 6.0f * s, 1.5f * s - 0.6f, -1.0f));
+        set.addShape(bead);
+    }
+
+    RectangleLight* areaLight = st.add(new RectangleLight(Point(),
+                                                          Vector(3.0f, 0.0f, 0.0f),
+                                                          Vector(0.0f, 0.0f, 3.0f),
+                                                          Color(1.0f, 1.0f, 1.0f),
+                                                          5.0f));
+    areaLight->transform().setTranslation(0.0f, Vector(-1.5f, 4.0f, -1.5f));
+    set.addShape(areaLight);
+
+    Sphere* bulb = st.hold(new Sphere(Point(), 0.1f, ground));
+    bulb->transform().setTranslation(0.0f, Vector(0.0f, 0.5f, 3.0f));
+    bulb->transform().setTranslation(1.0f, Vector(1.0f, 1.5f, 3.0f));
+    ShapeLight* sphereLight = st.add(new ShapeLight(bulb, Color(1.0f, 1.0f, 0.3f), 100.0f));
+    set.addShape(sphereLight);
+    return true;
+}
+
 } // namespace rayito_recipes
 
 #endif // RAYITO_B200_SCENE_RECIPES_H

@@ -106,3 +106,30 @@ def scene8_host(capi):
 @pytest.fixture(scope="session")
 def scene8_ref(ref):
     return ref.RefScene(8)
+
+
+# Deep-tree edge scenes (host/scene_recipes.h buildDeepScene): face BVH 42 / 46 deep, and with
+# the sphere chain a top-level BVH 18 deep as well
+DEEP_GRID = (40, 8)
+DEEPER_GRID = (44, 8)
+BIG_GRID = (1000, 1000)     # the displaced sphere at 1 M quads: face BVH depth 32 -> 33 stack entries
+
+
+@pytest.fixture(scope="session")
+def deep_host(capi):
+    return capi.HostScene(capi.RECIPE_EDGE_DEEP_MESH, None, DEEP_GRID)
+
+
+@pytest.fixture(scope="session")
+def deep_ref(ref):
+    return ref.RefScene(10, None, DEEP_GRID)
+
+
+@pytest.fixture(scope="session")
+def deepboth_host(capi):
+    return capi.HostScene(capi.RECIPE_EDGE_DEEP_BOTH, None, DEEPER_GRID)
+
+
+@pytest.fixture(scope="session")
+def deepboth_ref(ref):
+    return ref.RefScene(11, None, DEEPER_GRID)

@@ -51,5 +51,44 @@ def axis_parallel_rays(n, seed):
     return rays
 
 
+def deep_scene_rays(n, seed, shadow_fraction=0.25):
+    """Rays for the wedge-mesh scenes: a quarter aimed at the whole wedge, a quarter at its tip
+    (where the face BVH is deepest), a quarter at the sphere chain / lights, and a quarter GRAZING
+    the wedge from its tip outwards at shutter time 0 (no rotation yet): such a ray pierces the
+    box of every row, nearest rows last, so the far children pile up on the traversal stack --
+    dozens of live entries, which is what the deep-stack kernels exist for."""
+    q = n // 4
+    tip = (-0.5, -0.5, 0.0)
+    a = random_rays(q, seed, center=(0.3, -0.5, 0.0), radius=7.0, target_radius=1.6, shadow_fraction=shadow_fraction)
+    b = random_rays(q, seed + 1, center=tip, radius=5.0, target_radius=0.03, shadow_fraction=shadow_fraction)
+    c = random_rays(q, seed + 2, center=(0.0, 0.0, 0.0), radius=9.0, target_radius=4.0,
+                    shadow_fraction=shadow_fraction)
+    m = n - 3 * q
+    rng = np.random.RandomState(seed + 3)
+    g = np.zeros(m, RAY_DTYPE)
+    spread = 10.0 ** rng.uniform(-14.0, -0.7, size=(m, 1))
+    offs = rng.normal(size=(m, 3)) * spread * 0.2
+    offs[rng.uniform(size=m) < 0.6, 1:] = 0.0         # origin exactly on the wedge's axis: only the slope leaves it
+    offs[:, 0] = -rng.uniform(0.0, 0.3, size=m)
+    g["origin"] = (np.asarray(tip) + offs).astype(np.float32)
+    d = np.concatenate([np.ones((m, 1)), rng.normal(size=(m, 2)) * spread], axis=1)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    g["direction"] = d.astype(np.float32)
+    g["tmax"] = np.float32(1.0e30)
+    g["time"] = np.where(rng.uniform(size=m) < 0.7, 0.0, rng.uniform(size=m)).astype(np.float32)
+    # ... and a fifth of them along the chain of halving spheres of the "deep both" scene, from its
+    # small end outwards (same effect on the TOP-level stack)
+    chain = rng.uniform(size=m) < 0.2
+    axis = np.array([6.0, 1.5, 0.0]) / np.linalg.norm([6.0, 1.5, 0.0])
+    cd = axis + rng.normal(size=(m, 3)) * spread * 0.3
+    cd /= np.linalg.norm(cd, axis=1, keepdims=True)
+    co = np.array([-3.0, -1.0, -1.0]) - rng.uniform(0.0, 0.5, size=(m, 1)) * axis
+    g["origin"][chain] = co[chain].astype(np.float32)
+    g["direction"][chain] = cd[chain].astype(np.float32)
+    k = int(m * shadow_fraction)
+    g["tmax"][:k] = rng.uniform(0.5, 4.0, size=k).astype(np.float32)
+    return np.concatenate([a, b, c, g])
+
+
 def bits(a):
     return np.ascontiguousarray(a, np.float32).view(np.uint32)

@@ -22,7 +22,7 @@ def test_core_exports_every_declared_symbol(capi):
     lib = capi.core()
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.rt_abi_version() == 1
+    assert lib.rt_abi_version() == 2
 
 
 def test_host_exports_every_declared_symbol(capi):
@@ -91,7 +91,7 @@ def test_deep_bvh_is_refused(capi):
     xf = capi.RtXform(0, 0)
     mat = (C.c_float * 8)()
     d = capi.RtSceneDesc()
-    d.abi_version = 1; d.set_xform = 0; d.num_finite = 1; d.num_infinite = 0
+    d.abi_version = 2; d.set_xform = 0; d.num_finite = 1; d.num_infinite = 0
     d.shapes = C.addressof(shape); d.num_top_nodes = 0
     d.num_xforms = 1; d.xforms = C.addressof(xf)
     d.num_meshes = 1; d.meshes = C.addressof(mesh)
@@ -120,7 +120,7 @@ def _single_mesh_desc(capi, nodes, n):
     xf = capi.RtXform(0, 0)
     mat = (C.c_float * 8)()
     d = capi.RtSceneDesc()
-    d.abi_version = 1; d.set_xform = 0; d.num_finite = 1; d.num_infinite = 0
+    d.abi_version = 2; d.set_xform = 0; d.num_finite = 1; d.num_infinite = 0
     d.shapes = C.addressof(shape); d.num_top_nodes = 0
     d.num_xforms = 1; d.xforms = C.addressof(xf)
     d.num_meshes = 1; d.meshes = C.addressof(mesh)

@@ -30,7 +30,7 @@ def _shapes(capi, desc):
     return [capi.RtShape.from_buffer_copy(bytes(s)) for s in arr]
 
 
-@pytest.mark.parametrize("which", ["scene1", "scene2", "scene6", "scene8"])
+@pytest.mark.parametrize("which", ["scene1", "scene2", "scene6", "scene8", "deep", "deepboth"])
 def test_top_level_bvh_identical(which, request):
     host = request.getfixturevalue(which + "_host")
     ref = request.getfixturevalue(which + "_ref")
@@ -42,7 +42,7 @@ def test_top_level_bvh_identical(which, request):
     assert d.num_finite == ref.num_finite and d.num_infinite == ref.num_infinite
 
 
-@pytest.mark.parametrize("which", ["scene1", "scene2", "scene6", "scene7"])
+@pytest.mark.parametrize("which", ["scene1", "scene2", "scene6", "scene7", "deep", "deepboth"])
 def test_mesh_data_and_bvh_identical(which, request, capi):
     host = request.getfixturevalue(which + "_host")
     ref = request.getfixturevalue(which + "_ref")
@@ -79,7 +79,7 @@ def test_mesh_data_and_bvh_identical(which, request, capi):
         theirs = ref.bvh_nodes(si)
         assert mine.shape == theirs.shape
         assert np.array_equal(mine, theirs), "mesh BVH differs for shape %d" % si
-    assert seen >= (1 if which == "scene7" else 2)
+    assert seen >= (1 if which in ("scene7", "deep", "deepboth") else 2)
 
 
 @pytest.mark.parametrize("which", ["scene1", "scene2", "scene7", "scene8"])
