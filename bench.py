@@ -16,11 +16,17 @@ value      whole-job Mrays/s, scene and camera resident in HBM, image left in HB
 e2e        the same metric through the reference-facing C++ call Rayito::raytrace()
            (host scene -> prepare() -> flatten -> upload -> render -> image in host
            memory), wall clock, host<->device copies inside the timed region.
-roofline   the traversal kernels (closest-hit / any-hit): algorithmic bytes per ray
-           B = 48 + 32 N_pop + 36 N_tri + 16 N_shape + 40 K_xf (the
-           counts come from the kernels' own exact work counters, which the tests
-           pin to the reference's traversal) over their summed CUDA-event time,
-           against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
+roofline   the traversal kernels (k_split_top_static, k_split_mesh, k_split_top;
+           closest-hit and any-hit): algorithmic bytes per ray
+           B = 48 + 32 N_pop + 36 N_tri + 16 N_shape + 40 K_xf (K_xf =
+           evaluations of transforms that hold keys) over their summed CUDA-event
+           time, against the measured HBM copy bandwidth in MEASURED_PEAKS.json.  The
+           counts are the kernels' own exact work counters;
+           tests/test_gpu_counters.py::test_render_counters_equal_oracle_on_recorded_rays
+           requires them to equal the oracle's (oracle/port.c, pinned hit for hit to
+           the compiled reference) on every ray the reference casts for a frame.
+also       the default run adds config.also.c5: the 10 M-triangle mesh (configs[4]) at
+           64 spp, device-timed, with its own roofline -- the HBM-bound configuration.
 cpu_baseline / --impl reference
            the UNMODIFIED reference raytrace() (oracle/_ref, 16 worker threads by
            design) on the box's host cores, same scene and spp at a reduced
@@ -63,18 +69,6 @@ C2_SWEEP = [(1, 1), (2, 2), (4, 4), (8, 8), (16, 16)]
 WORKLOADS["c2"] = dict(stage23=3, width=512, height=512, sweep=C2_SWEEP,
                        label="Rayito_Stage3 built-in scene 512x512, pixel-sample sweep 1/4/16/64/256 spp, "
                              "2 area lights x 16 light samples")
-# DRAM bytes (read + write) per launch of the dominant traversal kernel, from the `ncu --set full`
-# captures summarised under profiles/ (same batch size as the full-size workloads; None = not captured)
-NCU_TRAFFIC = {
-    1: dict(kernel="k_split_top_static<ANY=1,ShadowIO> (tabulated top-level pass of the shadow rays of one 16 Mi-sample batch)",
-            bytes=1.840791e9 + 618.319616e6, ms=1.6, source="profiles/r01_v8_static_top_c4small_full_summary.csv",
-            note="captured with --batch 16777216 (per-launch bytes scale with the batch size); mostly per-ray wavefront "
-                 "state (records scattered by slot), not scene data: the 3 MB scene is L1/L2-resident"),
-    5: dict(kernel="k_split_mesh<64,ANY=1,ShadowIO> (face-BVH pass of the shadow rays of one 16 Mi-sample batch)",
-            bytes=4.352745e9 + 235.469824e6, ms=6.0, source="profiles/r01_v11_mesh_c5small_full_summary.csv",
-            note="captured with --batch 16777216; random 32-byte node and 48-byte triangle gathers from a 660 MB scene, "
-                 "L2 hit 61 %; the closest-hit passes of the same batch read 0.5-1.8 GB each (L2 hit 66-80 %)"),
-}
 CAMERA_SPEC = {       # fov, origin, target, up, focal distance, lens radius, shutter open/close (GUI defaults)
     1: [30, -4, 5, 15, 0, 0, 0, 0, 1, 0, 16, 0, 0, 1],
     2: [30, -4, 10, 30, 0, 5, 0, 0, 1, 0, 16, 0, 0, 1],
@@ -173,13 +167,15 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def algorithmic_bytes(stats):
+def algorithmic_bytes(stats, strict=False):
     """B = 32 (ray in) + 16 (hit out) per ray + 32 per node popped
-    + 36 per triangle tested + 16 per analytic shape tested + 40 per keyed
-    transform evaluated."""
+    + 36 per triangle tested + 16 per analytic shape tested + 40 per transform
+    evaluation that reads keys.  A transform with no keys (the ShapeSet's own) reads
+    nothing and is charged nothing; one with a single key reads that key (charged);
+    strict=True charges only transforms with two or more keys (a real key PAIR)."""
     rays = stats["closest_rays"] + stats["any_rays"]
     return (48 * rays + 32 * stats["node_pops"] + 36 * stats["tri_tests"] + 16 * stats["shape_tests"]
-            + 40 * stats["xform_evals"])
+            + 40 * stats["xform_pairs" if strict else "xform_keyed"])
 
 
 def run_reference(args, wl, rank, world):
@@ -318,6 +314,200 @@ def run_stage23(args, wl, rank, world, local_rank):
     emit(line)
 
 
+def load_traffic(workload):
+    """Measured DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per traversal launch at THIS
+    workload's batch size, from the committed ncu capture summarised by tools/ncu_traffic.py into
+    profiles/traffic.json; None when that workload was not captured."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        return json.load(f).get(workload)
+
+
+class Env:
+    """Process-wide handles shared by the measurements of one bench.py run."""
+
+    def __init__(self, args):
+        import numpy as np
+        import torch
+        import torch.distributed as dist
+        from rayito_b200 import build, capi
+        self.np, self.torch, self.dist, self.build, self.capi = np, torch, dist, build, capi
+        self.args = args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: the render core has no CPU fallback")
+        torch.cuda.set_device(self.local_rank)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+        self.dev = torch.device("cuda", self.local_rank)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)     # > 126 MB L2
+        self.stream = torch.cuda.current_stream(self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def allsum(self, x):
+        t = self.torch.tensor([float(x)], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def allmax(self, x):
+        t = self.torch.tensor([float(x)], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+def measure_workload(env, name, steps, warmup, want_e2e, want_cpu):
+    """One workload, device-timed: returns the fields of a result line (rank 0 uses them)."""
+    args, capi, torch, dist = env.args, env.capi, env.torch, env.dist
+    rank, world, local_rank, dev = env.rank, env.world, env.local_rank, env.dev
+    wl = WORKLOADS[name]
+
+    # ---- scene: built with the C++ host API, flattened, uploaded once ------------
+    obj = env.build.model_path("bumpy.obj") if wl["recipe"] in NEEDS_OBJ else None
+    t0 = time.perf_counter()
+    hscene = capi.HostScene(wl["recipe"], obj, wl["grid"])
+    host_prepare_s = time.perf_counter() - t0
+    dscene = capi.DeviceScene(hscene.desc, device=local_rank)
+    spec = hscene.default_camera_spec()
+    cam = capi.camera_from_spec(spec)
+    W, H, ps, ls, depth = wl["width"], wl["height"], wl["ps"], wl["ls"], wl["depth"]
+    scene_bytes = hscene_bytes(hscene)
+
+    image = torch.zeros((H, W, 3), dtype=torch.float32, device=dev)
+    flush, stream = env.flush, env.stream
+    extra_flags = int(os.environ.get("RT_BENCH_FLAGS", "0"))      # A/B switches (RT_RENDER_* bits), not for reported runs
+
+    def params(flags=0):
+        return capi.RtRenderParams(W, H, ps, ls, depth, args.tile, rank, world, args.batch, flags | extra_flags)
+
+    def step(flags=0):
+        st = dscene.render_device(cam, params(flags), image.data_ptr(), stream.cuda_stream)
+        if world > 1:
+            # the one collective of the path: tile assembly on rank 0.  Every pixel is
+            # owned by exactly one rank and zero elsewhere, so the sum is exact.
+            dist.reduce(image, dst=0, op=dist.ReduceOp.SUM)
+        return st
+
+    # exact work counters (deterministic per frame) from one untimed instrumented step
+    image.zero_()
+    counted = step(capi.RT_RENDER_COUNT_WORK).as_dict()
+    log("[rank %d] %s counted step: %s" % (rank, name, counted))
+
+    for _ in range(warmup):
+        image.zero_()
+        flush.zero_()
+        step()
+
+    env.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    trace_ms = 0.0
+    trace_launches = 0
+    render_ms = 0.0
+    ev0.record(stream)
+    for _ in range(steps):
+        image.zero_()
+        flush.zero_()             # L2 flush between timed steps
+        st = step(capi.RT_RENDER_TIME_TRACE)
+        launches += st.kernel_launches
+        trace_ms += st.trace_ms
+        trace_launches += st.trace_launches
+        render_ms += st.render_ms
+    ev1.record(stream)
+    env.barrier()
+    clocks = sampler.stop()
+    elapsed_ms = ev0.elapsed_time(ev1)
+
+    # ---- aggregate over ranks ------------------------------------------------------
+    allsum, allmax = env.allsum, env.allmax
+    rays_rank = counted["closest_rays"] + counted["any_rays"]
+    rays_total = allsum(rays_rank)
+    samples_total = allsum(counted["samples"])
+    max_ms = allmax(elapsed_ms)
+    launches_total = allsum(launches)
+    value = rays_total * steps / (max_ms / 1e3) / 1e6
+    # traversal roofline: sum over ranks of algorithmic bytes / max over ranks of traversal time
+    bytes_rank = algorithmic_bytes(counted)
+    bytes_total = allsum(bytes_rank)
+    bytes_strict_total = allsum(algorithmic_bytes(counted, strict=True))
+    trace_ms_max = allmax(trace_ms)
+    peak, peak_src = load_peaks()
+    achieved = bytes_total * steps / (trace_ms_max / 1e3) / 1e9 / world    # per GPU
+    launches_per_step = trace_launches / max(steps, 1)
+    traffic = load_traffic(name) if world == 1 and not args.batch and not args.tile else None
+    roofline = {
+        "bound": "hbm",
+        "kernel": "traversal passes: k_split_top_static (tabulated top-level walk) + k_split_mesh (face BVH) + "
+                  "k_split_top (resume), closest-hit and any-hit instantiations",
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+        "frac_strict": bytes_strict_total * steps / (trace_ms_max / 1e3) / 1e9 / world / peak,
+        "traffic": traffic["bytes_per_launch"] if traffic else None,
+        "traffic_detail": traffic,
+        "bytes_per_ray": bytes_total / rays_total,
+        "bytes_per_ray_strict": bytes_strict_total / rays_total,
+        "per_ray": {k: allsum(counted[k]) / rays_total for k in
+                    ("node_pops", "tri_tests", "shape_tests", "xform_evals", "xform_keyed", "xform_pairs")},
+        "counters": "the kernels' own exact work counters (one RT_RENDER_COUNT_WORK step); "
+                    "tests/test_gpu_counters.py requires them to equal the oracle's (oracle/port.c) on the same rays",
+        "bytes_formula": "48 per ray + 32 per node popped + 36 per triangle tested + 16 per analytic shape tested + "
+                         "40 per transform evaluation that reads keys (xform_keyed: >= 1 key; frac_strict charges only "
+                         "xform_pairs: >= 2 keys); keyless transforms (the ShapeSet's own) charge nothing",
+        "launches_per_step": launches_per_step,
+        "bytes_per_launch": bytes_rank / max(launches_per_step, 1),
+        "avg_launch_ms": trace_ms / max(trace_launches, 1),
+        "trace_share_of_step": trace_ms_max / max_ms,
+        "trace_mrays_per_s_per_gpu": rays_total * steps / (trace_ms_max / 1e3) / 1e6 / world,
+        "note": ("scene is %.1f MB: %s" % (scene_bytes / 1e6,
+                 "L2-resident by nature of this config, so the HBM fraction is reported as the contract asks but "
+                 "L2 latency / SIMT divergence binds first (SURVEY.md 8d)" if scene_bytes < 100e6 else
+                 "HBM-resident, random node/triangle gathers: the HBM roofline is the binding one")),
+    }
+
+    # free the device scene and wavefront state before the end-to-end leg builds its own
+    dscene.close()
+    del image
+
+    # ---- e2e: through Rayito::raytrace() with host buffers -------------------------
+    e2e = None
+    if want_e2e:
+        e2e = measure_e2e(args, wl, capi, obj, spec, rank, world, local_rank, dev, dist, torch, env.np, rays_total,
+                          scene_bytes, steps)
+
+    # ---- CPU baseline (rank 0, N=1 only) -------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and want_cpu:
+        cpu = measure_cpu_baseline(wl, obj, spec)
+    hscene.close()
+
+    out = {
+        "value": value, "ms_per_step": max_ms / steps, "steps": steps, "warmup": warmup,
+        "config": {"workload": wl["label"], "parallelism": "screen tiles x%d (diagonal interleave), scene replicated" % world,
+                   "samples_per_step": samples_total, "rays_per_step": rays_total,
+                   "rays_per_sample": rays_total / samples_total,
+                   "msamples_per_s": samples_total * steps / (max_ms / 1e3) / 1e6,
+                   "l2": "256 MB flush buffer written between timed steps; per-batch path state (tens of GB) >> L2",
+                   "host_prepare_s": host_prepare_s, "render_ms_per_step_rank0": render_ms / steps},
+        "clocks": clocks, "gpu_launches": int(launches_total), "roofline": roofline,
+    }
+    if e2e is not None:
+        out["e2e"] = e2e
+    if cpu is not None:
+        out["cpu_baseline"] = cpu
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -327,6 +517,7 @@ def main():
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="skip the secondary C5 measurement of the default run")
     ap.add_argument("--batch", type=int, default=0, help="max samples per wavefront batch (0 = core default)")
     ap.add_argument("--tile", type=int, default=0)
     args = ap.parse_args()
@@ -344,160 +535,35 @@ def main():
         run_reference(args, wl, rank, world)
         return
 
-    import numpy as np
-    import torch
-    import torch.distributed as dist
-    from rayito_b200 import build, capi
+    env = Env(args)
+    head = measure_workload(env, args.workload, args.steps, args.warmup, not args.no_e2e, not args.no_cpu_baseline)
+    # The HBM-bound configuration (BASELINE.json configs[4], the 10 M-triangle mesh) rides along with the
+    # default run at 64 spp (the full 1024 spp frame takes 18 s): its own device-timed value and roofline,
+    # under config.also.c5.  C4 stays the headline.
+    also = None
+    if args.workload == "c4" and not args.no_also:
+        also = measure_workload(env, "c5-64spp", max(2, min(args.steps, 3)), 3, False, False)
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the render core has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    dev = torch.device("cuda", local_rank)
-
-    # ---- scene: built with the C++ host API, flattened, uploaded once ------------
-    obj = build.model_path("bumpy.obj") if wl["recipe"] in NEEDS_OBJ else None
-    t0 = time.perf_counter()
-    hscene = capi.HostScene(wl["recipe"], obj, wl["grid"])
-    host_prepare_s = time.perf_counter() - t0
-    dscene = capi.DeviceScene(hscene.desc, device=local_rank)
-    spec = hscene.default_camera_spec()
-    cam = capi.camera_from_spec(spec)
-    W, H, ps, ls, depth = wl["width"], wl["height"], wl["ps"], wl["ls"], wl["depth"]
-
-    image = torch.zeros((H, W, 3), dtype=torch.float32, device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
-    stream = torch.cuda.current_stream(dev)
-
-    extra_flags = int(os.environ.get("RT_BENCH_FLAGS", "0"))      # A/B switches (RT_RENDER_* bits), not for reported runs
-
-    def params(flags=0):
-        return capi.RtRenderParams(W, H, ps, ls, depth, args.tile, rank, world, args.batch, flags | extra_flags)
-
-    def step(flags=0):
-        st = dscene.render_device(cam, params(flags), image.data_ptr(), stream.cuda_stream)
-        if world > 1:
-            # the one collective of the path: tile assembly on rank 0.  Every pixel is
-            # owned by exactly one rank and zero elsewhere, so the sum is exact.
-            dist.reduce(image, dst=0, op=dist.ReduceOp.SUM)
-        return st
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    # exact work counters (deterministic per frame) from one untimed instrumented step
-    image.zero_()
-    counted = step(capi.RT_RENDER_COUNT_WORK).as_dict()
-    log("[rank %d] counted step: %s" % (rank, counted))
-
-    for _ in range(args.warmup):
-        image.zero_()
-        flush.zero_()
-        step()
-
-    barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches = 0
-    trace_ms = 0.0
-    trace_launches = 0
-    render_ms = 0.0
-    ev0.record(stream)
-    for _ in range(args.steps):
-        image.zero_()
-        flush.zero_()             # L2 flush between timed steps
-        st = step(capi.RT_RENDER_TIME_TRACE)
-        launches += st.kernel_launches
-        trace_ms += st.trace_ms
-        trace_launches += st.trace_launches
-        render_ms += st.render_ms
-    ev1.record(stream)
-    barrier()
-    clocks = sampler.stop()
-    elapsed_ms = ev0.elapsed_time(ev1)
-
-    # ---- aggregate over ranks ------------------------------------------------------
-    def allsum(x):
-        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
-    def allmax(x):
-        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    rays_rank = counted["closest_rays"] + counted["any_rays"]
-    rays_total = allsum(rays_rank)
-    samples_total = allsum(counted["samples"])
-    max_ms = allmax(elapsed_ms)
-    launches_total = allsum(launches)
-    value = rays_total * args.steps / (max_ms / 1e3) / 1e6
-    # traversal roofline: sum over ranks of algorithmic bytes / max over ranks of traversal time
-    bytes_rank = algorithmic_bytes(counted)
-    bytes_total = allsum(bytes_rank)
-    trace_ms_max = allmax(trace_ms)
-    peak, peak_src = load_peaks()
-    achieved = bytes_total * args.steps / (trace_ms_max / 1e3) / 1e9 / world    # per GPU
-    roofline = {
-        "bound": "hbm", "kernel": "k_trace_paths + k_trace_mis (closest hit) + k_trace_shadow (any hit)",
-        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-        "traffic": (NCU_TRAFFIC.get(wl["recipe"]) or {}).get("bytes"),
-        "traffic_detail": NCU_TRAFFIC.get(wl["recipe"]),
-        "bytes_per_ray": bytes_total / rays_total,
-        "per_ray": {"node_pops": allsum(counted["node_pops"]) / rays_total,
-                    "tri_tests": allsum(counted["tri_tests"]) / rays_total,
-                    "shape_tests": allsum(counted["shape_tests"]) / rays_total,
-                    "xform_evals": allsum(counted["xform_evals"]) / rays_total},
-        "launches_per_step": trace_launches / max(args.steps, 1),
-        "bytes_per_launch": bytes_rank / max(trace_launches / max(args.steps, 1), 1),
-        "avg_launch_ms": trace_ms / max(trace_launches, 1),
-        "trace_share_of_step": trace_ms_max / max_ms,
-        "trace_mrays_per_s_per_gpu": rays_total * args.steps / (trace_ms_max / 1e3) / 1e6 / world,
-        "note": ("scene is %.1f MB: %s" % (hscene_bytes(hscene) / 1e6,
-                 "L2-resident by nature of this config, so the HBM fraction is reported as the contract asks but "
-                 "L2 latency / SIMT divergence binds first (SURVEY.md 8d)" if hscene_bytes(hscene) < 100e6 else
-                 "HBM-resident, random node/triangle gathers: the HBM roofline is the binding one")),
-    }
-
-    # ---- e2e: through Rayito::raytrace() with host buffers -------------------------
-    e2e = None
-    if not args.no_e2e:
-        e2e = measure_e2e(args, wl, capi, obj, spec, rank, world, local_rank, dev, dist, torch, np, rays_total,
-                          hscene_bytes(hscene))
-
-    # ---- CPU baseline (rank 0, N=1 only) -------------------------------------------
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = measure_cpu_baseline(wl, obj, spec)
-
-    if rank == 0:
+    if env.rank == 0:
         line = {
-            "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": max_ms / args.steps, "higher_is_better": True,
+            "metric": "Mrays/s", "value": head["value"], "unit": "Mrays/s", "n_gpus": env.world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["label"], "parallelism": "screen tiles x%d (diagonal interleave), scene replicated" % world,
-                       "samples_per_step": samples_total, "rays_per_step": rays_total,
-                       "rays_per_sample": rays_total / samples_total,
-                       "msamples_per_s": samples_total * args.steps / (max_ms / 1e3) / 1e6,
-                       "l2": "256 MB flush buffer written between timed steps; per-batch path state (tens of GB) >> L2",
-                       "host_prepare_s": host_prepare_s, "render_ms_per_step_rank0": render_ms / args.steps},
-            "clocks": clocks, "gpu_launches": int(launches_total), "roofline": roofline,
+            "config": head["config"], "clocks": head["clocks"], "gpu_launches": head["gpu_launches"],
+            "roofline": head["roofline"],
         }
-        if e2e is not None:
-            line["e2e"] = e2e
-        if cpu is not None:
-            line["cpu_baseline"] = cpu
+        for key in ("e2e", "cpu_baseline"):
+            if key in head:
+                line[key] = head[key]
+        if also is not None:
+            line["config"]["also"] = {"c5": {
+                "metric": "Mrays/s", "value": also["value"], "unit": "Mrays/s", "ms_per_step": also["ms_per_step"],
+                "steps": also["steps"], "warmup": also["warmup"], "config": also["config"], "clocks": also["clocks"],
+                "gpu_launches": also["gpu_launches"], "roofline": also["roofline"]}}
+            line["gpu_launches"] += also["gpu_launches"]
         emit(line)
-    if world > 1:
-        dist.destroy_process_group()
+    if env.world > 1:
+        env.dist.destroy_process_group()
 
 
 def hscene_bytes(hscene):
@@ -506,7 +572,7 @@ def hscene_bytes(hscene):
             + d.num_indices * 8 + d.num_faces * 8 + d.num_cdf * 4 + d.num_keys * 44)
 
 
-def measure_e2e(args, wl, capi, obj, spec, rank, world, local_rank, dev, dist, torch, np, rays_total, scene_bytes):
+def measure_e2e(args, wl, capi, obj, spec, rank, world, local_rank, dev, dist, torch, np, rays_total, scene_bytes, steps):
     """Wall-clock Mrays/s through the reference-facing call Rayito::raytrace(scene, cam, W, H, ps, ls, depth)
     (rth_app_raytrace), every step: findLights + prepare() (host BVH builds) + flatten + scene upload + render +
     image download.  The application's scene-building code (OBJ read, recipe) runs once before the timed
@@ -557,7 +623,7 @@ def measure_e2e(args, wl, capi, obj, spec, rank, world, local_rank, dev, dist, t
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
-    n = max(1, min(args.steps, 3))
+    n = max(1, steps)
     t0 = time.perf_counter()
     for _ in range(n):
         one()
