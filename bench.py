@@ -345,6 +345,15 @@ class Env:
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
         self.dev = torch.device("cuda", self.local_rank)
+        # the render core's own communicator for the tile assembly (rt_render_multi): rank 0 draws the
+        # NCCL unique id, torch.distributed only carries its 128 bytes to the other ranks
+        self.comm = None
+        if self.world > 1:
+            uid = torch.zeros(capi.Comm.ID_BYTES, dtype=torch.uint8, device=self.dev)
+            if self.rank == 0:
+                uid.copy_(torch.frombuffer(bytearray(capi.Comm.unique_id()), dtype=torch.uint8))
+            dist.broadcast(uid, src=0)
+            self.comm = capi.Comm(uid.cpu().numpy().tobytes(), self.rank, self.world, self.local_rank)
         self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)     # > 126 MB L2
         self.stream = torch.cuda.current_stream(self.dev)
 
@@ -390,12 +399,15 @@ def measure_workload(env, name, steps, warmup, want_e2e, want_cpu):
     def params(flags=0):
         return capi.RtRenderParams(W, H, ps, ls, depth, args.tile, rank, world, args.batch, flags | extra_flags)
 
+    assemble_ms = []
+
     def step(flags=0):
-        st = dscene.render_device(cam, params(flags), image.data_ptr(), stream.cuda_stream)
-        if world > 1:
-            # the one collective of the path: tile assembly on rank 0.  Every pixel is
-            # owned by exactly one rank and zero elsewhere, so the sum is exact.
-            dist.reduce(image, dst=0, op=dist.ReduceOp.SUM)
+        if world == 1:
+            return dscene.render_device(cam, params(flags), image.data_ptr(), stream.cuda_stream)
+        # the one collective of the path, inside the product call: every rank renders its tiles packed,
+        # ncclSend / ncclRecv moves them to rank 0, one kernel there scatters them into the frame
+        st, ms = env.comm.render_multi(dscene, cam, params(flags), image.data_ptr(), 0, stream.cuda_stream)
+        assemble_ms.append(ms)
         return st
 
     # exact work counters (deterministic per frame) from one untimed instrumented step
@@ -483,7 +495,7 @@ def measure_workload(env, name, steps, warmup, want_e2e, want_cpu):
     e2e = None
     if want_e2e:
         e2e = measure_e2e(args, wl, capi, obj, spec, rank, world, local_rank, dev, dist, torch, env.np, rays_total,
-                          scene_bytes, steps)
+                          scene_bytes, steps, env.comm)
 
     # ---- CPU baseline (rank 0, N=1 only) -------------------------------------------
     cpu = None
@@ -493,7 +505,11 @@ def measure_workload(env, name, steps, warmup, want_e2e, want_cpu):
 
     out = {
         "value": value, "ms_per_step": max_ms / steps, "steps": steps, "warmup": warmup,
-        "config": {"workload": wl["label"], "parallelism": "screen tiles x%d (diagonal interleave), scene replicated" % world,
+        "config": {"workload": wl["label"],
+                   "parallelism": "screen tiles x%d (diagonal interleave), scene replicated%s" % (
+                       world, "" if world == 1 else "; tile assembly on rank 0 by rt_render_multi (packed tiles, grouped "
+                       "ncclSend/ncclRecv, scatter kernel): %.3f ms per step on rank 0" % (
+                           sum(assemble_ms[-steps:]) / max(steps, 1))),
                    "samples_per_step": samples_total, "rays_per_step": rays_total,
                    "rays_per_sample": rays_total / samples_total,
                    "msamples_per_s": samples_total * steps / (max_ms / 1e3) / 1e6,
@@ -572,14 +588,15 @@ def hscene_bytes(hscene):
             + d.num_indices * 8 + d.num_faces * 8 + d.num_cdf * 4 + d.num_keys * 44)
 
 
-def measure_e2e(args, wl, capi, obj, spec, rank, world, local_rank, dev, dist, torch, np, rays_total, scene_bytes, steps):
+def measure_e2e(args, wl, capi, obj, spec, rank, world, local_rank, dev, dist, torch, np, rays_total, scene_bytes, steps,
+                comm=None):
     """Wall-clock Mrays/s through the reference-facing call Rayito::raytrace(scene, cam, W, H, ps, ls, depth)
     (rth_app_raytrace), every step: findLights + prepare() (host BVH builds) + flatten + scene upload + render +
     image download.  The application's scene-building code (OBJ read, recipe) runs once before the timed
     region, as it does for the reference arm and the cpu_baseline (which time the reference's raytrace()).
-    N = 1: host image out of raytrace().  N > 1: each rank calls rayito_b200::raytraceToDevice() for its tiles,
-    the tiles are assembled on rank 0 by one NCCL reduce over the device buffers, and rank 0 downloads the
-    frame into pinned host memory."""
+    N = 1: host image out of raytrace().  N > 1: every rank calls rayito_b200::raytraceMulti() on its copy of
+    the scene (prepare + upload + render of its tiles), the packed tiles go to rank 0 over NCCL inside that
+    call, and rank 0's call returns the assembled host Image."""
     import ctypes as C
     W, H, ps, ls, depth = wl["width"], wl["height"], wl["ps"], wl["ls"], wl["depth"]
     stats = capi.RtRenderStats()
@@ -590,11 +607,7 @@ def measure_e2e(args, wl, capi, obj, spec, rank, world, local_rank, dev, dist, t
     if not app:
         raise RuntimeError("rth_app_create: " + lib.rth_last_error_string().decode())
     build_s = time.perf_counter() - t0
-    if world == 1:
-        pixels = C.c_void_p()
-    else:
-        d_img = torch.zeros((H, W, 3), dtype=torch.float32, device=dev)
-        frame = torch.empty((H, W, 3), dtype=torch.float32, pin_memory=True) if rank == 0 else None
+    pixels = C.c_void_p()
 
     def one():
         if world == 1:
@@ -602,17 +615,12 @@ def measure_e2e(args, wl, capi, obj, spec, rank, world, local_rank, dev, dist, t
             rc = lib.rth_app_raytrace_image(app, spec.ctypes.data, W, H, ps, ls, depth, local_rank, rank, world, 0,
                                             C.byref(pixels), C.byref(stats))
         else:
-            d_img.zero_()
-            rc = lib.rth_app_raytrace(app, spec.ctypes.data, W, H, ps, ls, depth, local_rank, rank, world, 0,
-                                      d_img.data_ptr(), 1, C.byref(stats))
+            # rayito_b200::raytraceMulti(): every rank prepares and renders its tiles, rank 0 gets the Image
+            rc = lib.rth_app_raytrace_multi(app, spec.ctypes.data, W, H, ps, ls, depth, comm.handle, 0,
+                                            C.byref(pixels), C.byref(stats))
         if rc != 0:
             raise RuntimeError("rth_app_raytrace: " + lib.rth_last_error_string().decode())
-        if world > 1:
-            dist.reduce(d_img, dst=0, op=dist.ReduceOp.SUM)
-            if rank == 0:
-                frame.copy_(d_img, non_blocking=True)
-            torch.cuda.synchronize(dev)
-        else:
+        if rank == 0:
             # the step's result is in host memory: touch it (mean of the first row) like a consumer would
             row = np.ctypeslib.as_array(C.cast(pixels, C.POINTER(C.c_float)), shape=(W * 3,))
             if not np.isfinite(float(row.mean())):
@@ -640,8 +648,8 @@ def measure_e2e(args, wl, capi, obj, spec, rank, world, local_rank, dev, dist, t
             "h2d_bytes_per_step": int(scene_bytes) * world, "d2h_bytes_per_step": int(W * H * 12),
             "steps": n, "ms_per_step": 1e3 * wall / n, "scene_build_s": build_s,
             "includes": "Rayito::raytrace() per step: findLights + prepare() (host BVH build) + flatten + scene upload + "
-                        "render + image download" + ("" if world == 1 else " (raytraceToDevice per rank, NCCL tile assembly "
-                        "on rank 0, one download)") + "; the application's scene-building code (OBJ read) runs once, "
+                        "render + image download" + ("" if world == 1 else " (raytraceMulti per rank: NCCL tile assembly "
+                        "on rank 0 inside the call, one download)") + "; the application's scene-building code (OBJ read) runs once, "
                         "untimed, as for the reference arm.  Unlike the device-timed `value` loop there is no L2 flush "
                         "and no per-stage CUDA-event timing between the kernels of a call, so e2e can come out a "
                         "percent above `value` on the same box"}

@@ -30,7 +30,8 @@ typedef enum RtStatus
     RT_ERR_CUDA = -2,       /* CUDA runtime failure (including "no device") */
     RT_ERR_DEPTH = -3,      /* a BVH is deeper than 49: the reference's 50-entry
                                traversal stack (RAccel.h:379,414,502) would overflow */
-    RT_ERR_UNSUPPORTED = -4
+    RT_ERR_UNSUPPORTED = -4,
+    RT_ERR_COMM = -5        /* NCCL failure, or no NCCL library to load */
 } RtStatus;
 
 /* Mirrors Rayito::Ray (RRay.h:31-36; sizeof == 32). */
@@ -273,6 +274,46 @@ int rt_render(RtScene* scene, const RtCamera* camera, const RtRenderParams* para
  * before returning so that stats are final. */
 int rt_render_device(RtScene* scene, const RtCamera* camera, const RtRenderParams* params,
                      float* d_rgb, RtRenderStats* stats, void* stream);
+
+/* ---- one frame over several GPUs (one process per GPU) ------------------------------
+ * The reference shards a frame over 16 threads by image chunks that all write one Image
+ * (RaytraceMain.cpp:504-568).  Here ranks own screen tiles (rt_tile_owners): each renders
+ * its tiles into a PACKED buffer -- its tiles in ascending tile index one after the other,
+ * pixel (row r, column q) of the k-th tile at ((k * tile + r) * tile + q) * 3 -- and the
+ * packed buffers are gathered on one rank and scattered into the frame.  That gather is the
+ * only collective of the path (NCCL send / receive over NVLink; the library loads NCCL at
+ * run time, libnccl.so.2 or RAYITO_B200_NCCL_LIB, and reuses a copy the process already
+ * holds).  One RtComm per process and device. */
+#define RT_COMM_ID_BYTES 128
+typedef struct RtComm RtComm;
+/* ncclGetUniqueId: call on one rank, hand the 128 bytes to all the others (MPI, a file, ...). */
+int rt_comm_unique_id(uint8_t* id);
+/* ncclCommInitRank on `device`: collective over all `world` ranks.  world == 1 needs no NCCL. */
+int rt_comm_create(const uint8_t* id, int rank, int world, int device, RtComm** out_comm);
+/* Wrap an ncclComm_t the application already has (borrowed: not destroyed with the handle). */
+int rt_comm_from_nccl(void* nccl_comm, int device, RtComm** out_comm);
+int rt_comm_destroy(RtComm* comm);
+/* raytrace() over all ranks of `comm`: every rank renders the tiles params->rank / world name
+ * (which must equal the communicator's), the root receives everybody's packed tiles and
+ * assembles the frame in d_rgb (device, width*height*3 floats; ignored on the other ranks).
+ * stats = this rank's render; assemble_ms (may be NULL) = device time of gather + scatter.
+ * Enqueues on `stream` and synchronises it before returning. */
+int rt_render_multi(RtScene* scene, const RtCamera* camera, const RtRenderParams* params, RtComm* comm, int root,
+                    float* d_rgb, RtRenderStats* stats, float* assemble_ms, void* stream);
+/* The same with the assembled frame copied to HOST memory on the root (rgb: width*height*3
+ * floats there, ignored elsewhere): what Rayito::raytrace() hands back.  Legacy stream. */
+int rt_render_multi_host(RtScene* scene, const RtCamera* camera, const RtRenderParams* params, RtComm* comm, int root,
+                         float* rgb, RtRenderStats* stats, float* assemble_ms);
+/* Rank, size and device of a communicator (any pointer may be NULL). */
+int rt_comm_rank(const RtComm* comm, int* rank, int* world, int* device);
+/* The two halves, for applications that move the tiles themselves: floats in the packed buffer
+ * of a rank (0 if it owns no tile); render this rank's tiles packed into a device buffer;
+ * scatter a rank's packed tiles into a device frame. */
+size_t rt_packed_floats(uint32_t width, uint32_t height, uint32_t tile_size, uint32_t world, uint32_t rank);
+int rt_render_tiles_packed(RtScene* scene, const RtCamera* camera, const RtRenderParams* params, float* d_packed,
+                           size_t packed_floats, RtRenderStats* stats, void* stream);
+int rt_unpack_tiles(int device, const float* d_packed, uint32_t width, uint32_t height, uint32_t tile_size,
+                    uint32_t world, uint32_t rank, float* d_rgb, void* stream);
 
 /* Generate only the camera rays of pixel-sample `psi` for every pixel of this
  * rank's tiles (RenderThread::run, RaytraceMain.cpp:112-142): rays[y*width+x]. */

@@ -85,6 +85,13 @@ int rth_app_raytrace_image(RthApp* app, const float* spec14, unsigned width, uns
                            int device, unsigned rank, unsigned world, int count_work,
                            const float** pixels, RtRenderStats* stats);
 
+/* One frame over all ranks of a communicator (rt_comm_create): rayito_b200::raytraceMulti() on the
+ * application's scene.  On the root *pixels is the assembled frame (owned by the app handle as
+ * above), on every other rank NULL. */
+int rth_app_raytrace_multi(RthApp* app, const float* spec14, unsigned width, unsigned height,
+                           unsigned pixel_samples_hint, unsigned light_samples_hint, unsigned max_ray_depth,
+                           RtComm* comm, int root, const float** pixels, RtRenderStats* stats);
+
 /* Stage 1 program (Rayito_Stage1/main.cpp:65-135): builds its scene (one pink plane at
  * y = -2) and camera (fov 30 at the origin looking down +z) with makeCameraRay's basis
  * arithmetic (main.cpp:28-52), renders on the GPU and returns the P6 payload

@@ -113,11 +113,13 @@ CORE_SYMBOLS = [
     "rt_render", "rt_render_device", "rt_generate_camera_rays", "rt_tonemap_bgra8",
     "rt_tile_owners", "rt_sample_permutations", "rt_cmj_sample1d", "rt_cmj_sample2d", "rt_stage1_render",
     "rt_libm_eval", "rt_stage23_render", "rt_release_cached_memory",
+    "rt_comm_unique_id", "rt_comm_create", "rt_comm_from_nccl", "rt_comm_destroy", "rt_render_multi",
+    "rt_packed_floats", "rt_render_tiles_packed", "rt_unpack_tiles", "rt_render_multi_host", "rt_comm_rank",
 ]
 HOST_SYMBOLS = [
     "rth_last_error_string", "rth_scene_create", "rth_scene_destroy", "rth_scene_desc",
     "rth_scene_prepare_seconds", "rth_scene_depth", "rth_camera", "rth_scene_default_camera", "rth_raytrace",
-    "rth_app_create", "rth_app_destroy", "rth_app_raytrace", "rth_app_raytrace_image",
+    "rth_app_create", "rth_app_destroy", "rth_app_raytrace", "rth_app_raytrace_image", "rth_app_raytrace_multi",
     "rth_stage1_render", "rth_stage23_render",
 ]
 
@@ -145,6 +147,17 @@ def core():
         lib.rt_render.argtypes = [vp, C.POINTER(RtCamera), C.POINTER(RtRenderParams), vp, C.POINTER(RtRenderStats)]
         lib.rt_render_device.argtypes = [vp, C.POINTER(RtCamera), C.POINTER(RtRenderParams), vp,
                                          C.POINTER(RtRenderStats), vp]
+        lib.rt_comm_unique_id.argtypes = [vp]
+        lib.rt_comm_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+        lib.rt_comm_from_nccl.argtypes = [vp, C.c_int, C.POINTER(vp)]
+        lib.rt_comm_destroy.argtypes = [vp]
+        lib.rt_render_multi.argtypes = [vp, C.POINTER(RtCamera), C.POINTER(RtRenderParams), vp, C.c_int, vp,
+                                        C.POINTER(RtRenderStats), C.POINTER(C.c_float), vp]
+        lib.rt_packed_floats.restype = sz
+        lib.rt_packed_floats.argtypes = [u32, u32, u32, u32, u32]
+        lib.rt_render_tiles_packed.argtypes = [vp, C.POINTER(RtCamera), C.POINTER(RtRenderParams), vp, sz,
+                                               C.POINTER(RtRenderStats), vp]
+        lib.rt_unpack_tiles.argtypes = [C.c_int, vp, u32, u32, u32, u32, u32, vp, vp]
         lib.rt_generate_camera_rays.argtypes = [vp, C.POINTER(RtCamera), C.POINTER(RtRenderParams), u32, vp]
         lib.rt_tonemap_bgra8.argtypes = [C.c_int, vp, sz, C.c_float, C.c_float, vp]
         lib.rt_libm_eval.argtypes = [C.c_int, vp, vp, sz, vp]
@@ -189,6 +202,8 @@ def host():
         lib.rth_app_raytrace_image.argtypes = [vp, vp, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint,
                                                C.c_int, C.c_uint, C.c_uint, C.c_int, C.POINTER(C.c_void_p),
                                                C.POINTER(RtRenderStats)]
+        lib.rth_app_raytrace_multi.argtypes = [vp, vp, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, vp, C.c_int,
+                                               C.POINTER(C.c_void_p), C.POINTER(RtRenderStats)]
         lib.rth_stage1_render.argtypes = [C.c_int, C.c_uint, C.c_uint, vp]
         lib.rth_stage23_render.argtypes = [C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_uint, vp, vp, vp]
         _host = lib
@@ -324,6 +339,47 @@ class DeviceScene:
             self.close()
         except Exception:
             pass
+
+
+class Comm:
+    """RtComm: the tile-assembly communicator of one rank (rt_comm_create)."""
+
+    ID_BYTES = 128
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_uint8 * Comm.ID_BYTES)()
+        check(core().rt_comm_unique_id(buf), "rt_comm_unique_id")
+        return bytes(buf)
+
+    def __init__(self, uid, rank, world, device):
+        self.handle = C.c_void_p()
+        buf = (C.c_uint8 * Comm.ID_BYTES).from_buffer_copy(uid)
+        check(core().rt_comm_create(buf, rank, world, device, C.byref(self.handle)), "rt_comm_create")
+        self.rank, self.world, self.device = rank, world, device
+
+    def render_multi(self, scene, camera, params, d_rgb_ptr, root=0, stream=None):
+        """rt_render_multi: (this rank's RtRenderStats, assemble ms)"""
+        stats = RtRenderStats()
+        ms = C.c_float(0.0)
+        check(core().rt_render_multi(scene.handle, C.byref(camera), C.byref(params), self.handle, root, d_rgb_ptr,
+                                     C.byref(stats), C.byref(ms), stream), "rt_render_multi")
+        return stats, ms.value
+
+    def close(self):
+        if self.handle:
+            core().rt_comm_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def packed_floats(width, height, world, rank, tile_size=0):
+    return int(core().rt_packed_floats(width, height, tile_size, world, rank))
 
 
 def tonemap_bgra8(rgb, exposure_stops=0.0, gamma=2.2, device=0):

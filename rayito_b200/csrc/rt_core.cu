@@ -10,6 +10,7 @@
 #include "rt_trace.cuh"
 #include "rt_wave.cuh"
 #include "rt_render.cuh"
+#include "rt_comm.cuh"
 #include "rt_stage23.cuh"
 
 thread_local std::string g_rt_error;
@@ -346,6 +347,120 @@ int rt_render_device(RtScene* s, const RtCamera* camera, const RtRenderParams* p
                      RtRenderStats* stats, void* stream)
 {
     return rt_render_impl(s, camera, params, d_rgb, true, stats, static_cast<cudaStream_t>(stream));
+}
+
+// ---- multi-GPU tile assembly (rt_comm.cuh) ----------------------------------------
+int rt_comm_unique_id(uint8_t* id)
+{
+    if (id == NULL) return rt_fail(RT_ERR_ARG, "null argument");
+    rt_detail::NcclApi* nccl = rt_detail::nccl_api();
+    if (nccl->handle == NULL) return rt_fail(RT_ERR_COMM, nccl->why);
+    static_assert(sizeof(ncclUniqueId) == RT_COMM_ID_BYTES, "ncclUniqueId size");
+    ncclUniqueId uid;
+    RT_NCCL(nccl->GetUniqueId(&uid));
+    std::memcpy(id, &uid, sizeof(uid));
+    return RT_OK;
+}
+
+int rt_comm_create(const uint8_t* id, int rank, int world, int device, RtComm** out)
+{
+    if (id == NULL || out == NULL || world < 1 || rank < 0 || rank >= world) return rt_fail(RT_ERR_ARG, "bad argument");
+    *out = NULL;
+    RT_CUDA(cudaSetDevice(device));
+    ncclComm_t comm = NULL;
+    if (world > 1)
+    {
+        rt_detail::NcclApi* nccl = rt_detail::nccl_api();
+        if (nccl->handle == NULL) return rt_fail(RT_ERR_COMM, nccl->why);
+        ncclUniqueId uid;
+        std::memcpy(&uid, id, sizeof(uid));
+        RT_NCCL(nccl->CommInitRank(&comm, world, uid, rank));
+    }
+    return rt_comm_wrap(comm, true, rank, world, device, out);
+}
+
+int rt_comm_from_nccl(void* nccl_comm, int device, RtComm** out)
+{
+    if (nccl_comm == NULL || out == NULL) return rt_fail(RT_ERR_ARG, "null argument");
+    *out = NULL;
+    rt_detail::NcclApi* nccl = rt_detail::nccl_api();
+    if (nccl->handle == NULL) return rt_fail(RT_ERR_COMM, nccl->why);
+    int rank = 0, world = 0;
+    RT_NCCL(nccl->CommUserRank(static_cast<ncclComm_t>(nccl_comm), &rank));
+    RT_NCCL(nccl->CommCount(static_cast<ncclComm_t>(nccl_comm), &world));
+    return rt_comm_wrap(static_cast<ncclComm_t>(nccl_comm), false, rank, world, device, out);
+}
+
+int rt_comm_destroy(RtComm* c)
+{
+    if (c == NULL) return RT_OK;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    rt_detail::pool_free(c->device, c->d_packed, c->packed_bytes);
+    rt_detail::pool_free(c->device, c->d_tiles, c->tiles_bytes);
+    rt_detail::pool_free(c->device, c->d_frame, c->frame_bytes);
+    for (int i = 0; i < 3; ++i) cudaEventDestroy(c->ev[i]);
+    if (c->owned && c->comm != NULL)
+        rt_detail::nccl_api()->CommDestroy(c->comm);
+    delete c;
+    return RT_OK;
+}
+
+int rt_comm_rank(const RtComm* c, int* rank, int* world, int* device)
+{
+    if (c == NULL) return rt_fail(RT_ERR_ARG, "null argument");
+    if (rank) *rank = c->rank;
+    if (world) *world = c->world;
+    if (device) *device = c->device;
+    return RT_OK;
+}
+
+int rt_render_multi_host(RtScene* s, const RtCamera* camera, const RtRenderParams* params, RtComm* comm, int root,
+                         float* rgb, RtRenderStats* stats, float* assemble_ms)
+{
+    return rt_render_multi_host_impl(s, camera, params, comm, root, rgb, stats, assemble_ms);
+}
+
+size_t rt_packed_floats(uint32_t width, uint32_t height, uint32_t tile_size, uint32_t world, uint32_t rank)
+{
+    if (width == 0 || height == 0 || world == 0 || rank >= world) return 0;
+    return rt_detail::packed_floats(width, height, tile_size, world, rank);
+}
+
+int rt_render_tiles_packed(RtScene* s, const RtCamera* camera, const RtRenderParams* params, float* d_packed,
+                           size_t packed_floats, RtRenderStats* stats, void* stream)
+{
+    if (packed_floats == 0) return rt_fail(RT_ERR_ARG, "packed_floats must be rt_packed_floats() of this rank");
+    return rt_render_impl(s, camera, params, d_packed, true, stats, static_cast<cudaStream_t>(stream), packed_floats);
+}
+
+int rt_unpack_tiles(int device, const float* d_packed, uint32_t width, uint32_t height, uint32_t tile_size,
+                    uint32_t world, uint32_t rank, float* d_rgb, void* stream)
+{
+    if (d_packed == NULL || d_rgb == NULL || width == 0 || height == 0 || world == 0 || rank >= world)
+        return rt_fail(RT_ERR_ARG, "bad argument");
+    RT_CUDA(cudaSetDevice(device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const uint32_t tile = tile_size ? tile_size : RT_DEFAULT_TILE;
+    const uint32_t tx = (width + tile - 1) / tile, ty = (height + tile - 1) / tile;
+    std::vector<uint32_t> mine;
+    rt_detail::rank_tiles(tx, ty, rank, world, mine);
+    if (mine.empty()) return RT_OK;
+    uint32_t* d_ids = NULL;
+    size_t got = 0;
+    RT_CUDA(rt_detail::pool_alloc(device, (void**)&d_ids, mine.size() * sizeof(uint32_t), &got));
+    cudaError_t e = cudaMemcpyAsync(d_ids, mine.data(), mine.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st);
+    int rc = e == cudaSuccess ? rt_unpack_impl(device, d_packed, d_ids, (uint32_t)mine.size(), tile, tx, width, height, d_rgb, st)
+                              : rt_cuda_fail(e, "tile id upload");
+    cudaStreamSynchronize(st);          // the id list goes back to the pool
+    rt_detail::pool_free(device, d_ids, got);
+    return rc;
+}
+
+int rt_render_multi(RtScene* s, const RtCamera* camera, const RtRenderParams* params, RtComm* comm, int root,
+                    float* d_rgb, RtRenderStats* stats, float* assemble_ms, void* stream)
+{
+    return rt_render_multi_impl(s, camera, params, comm, root, d_rgb, stats, assemble_ms, static_cast<cudaStream_t>(stream));
 }
 
 int rt_generate_camera_rays(RtScene* s, const RtCamera* camera, const RtRenderParams* params, uint32_t psi, RtRay* rays)

@@ -107,8 +107,18 @@ struct RenderCtx
     SplitBufs split;            // suspended-ray state
     uint32_t* ctl;              // CTL_WORDS queue counters
     uint64_t* totals;           // 0 closest rays, 1 any rays, 2..7 work counters (RT_WORK_COUNTERS)
-    float* image;               // width*height*3
+    float* image;               // width*height*3, or (packed != 0) this rank's tiles one after the other
+    uint32_t packed;            // tile-packed output: pixel (tile slot k, row r, column q) at ((k * tile + r) * tile + q) * 3
+    uint32_t tile_base;         // packed: slot of this batch's first tile in the rank's tile list
 };
+
+// Where pixel p of the batch (image coordinates x, y) is written
+__device__ __forceinline__ float* pixel_out(const RenderCtx& c, uint32_t p, uint32_t x, uint32_t y)
+{
+    if (c.packed)
+        return c.image + ((size_t)c.tile_base * c.tile * c.tile + p) * 3;
+    return c.image + ((size_t)y * c.width + x) * 3;
+}
 
 struct RenderBuffers
 {
@@ -213,7 +223,7 @@ k_pixel_setup(const __grid_constant__ RenderCtx c)
         c.pix_xy[p] = 0xffffffffu;
         if (c.image)
         {
-            float* out = c.image + ((size_t)y * c.width + x) * 3;
+            float* out = pixel_out(c, p, x, y);
             out[0] = out[1] = out[2] = 0.0f;
         }
         return;
@@ -862,7 +872,7 @@ k_accumulate(const __grid_constant__ RenderCtx c)
         sum = sum + rgb(r[s]);
     sum = sum / (float)c.spp;
     uint32_t x = xy & 0xffffu, y = xy >> 16;
-    float* out = c.image + ((size_t)y * c.width + x) * 3;
+    float* out = pixel_out(c, p, x, y);
     out[0] = sum.r;
     out[1] = sum.g;
     out[2] = sum.b;
@@ -1380,8 +1390,10 @@ inline int rt_fill_ctx(RtScene* s, const RtCamera* camera, const RtRenderParams*
     return RT_OK;
 }
 
+// packed_floats != 0: rgb_out is a DEVICE buffer of that many floats receiving this rank's tiles packed
+// one after the other (rt_packed_floats) instead of a width*height*3 frame
 inline int rt_render_impl(RtScene* s, const RtCamera* camera, const RtRenderParams* prm, float* rgb_out, bool out_on_device,
-                          RtRenderStats* stats, cudaStream_t st)
+                          RtRenderStats* stats, cudaStream_t st, size_t packed_floats = 0)
 {
     if (s == NULL || camera == NULL || prm == NULL || rgb_out == NULL)
         return rt_fail(RT_ERR_ARG, "null argument");
@@ -1419,6 +1431,10 @@ inline int rt_render_impl(RtScene* s, const RtCamera* camera, const RtRenderPara
     rt_fill_ctx(s, camera, prm, plan, c);
     c.image = d_image;
     c.tile_ids = rb->d_tile_ids;
+    c.packed = packed_floats != 0 ? 1u : 0u;
+    c.tile_base = 0;
+    if (packed_floats != 0 && (!out_on_device || packed_floats < plan.tiles.size() * (size_t)plan.tile * plan.tile * 3))
+        return rt_fail(RT_ERR_ARG, "packed tile buffer must be a device buffer of at least rt_packed_floats() floats");
 
     RT_CUDA(cudaEventRecord(rb->ev[0], st));
     if (!plan.tiles.empty())
@@ -1439,6 +1455,7 @@ inline int rt_render_impl(RtScene* s, const RtCamera* camera, const RtRenderPara
     {
         size_t nt = std::min<size_t>(plan.tiles_per_batch, plan.tiles.size() - t0);
         c.tile_ids = rb->d_tile_ids + t0;
+        c.tile_base = (uint32_t)t0;
         c.num_pixels = (uint32_t)(nt * plan.tile * plan.tile);
         c.num_samples = c.num_pixels * plan.spp;
         rc = count ? rt_launch_batch<true>(s, c, st, launches, timed, trace_launches, split)
@@ -1543,6 +1560,8 @@ inline int rt_camera_rays_impl(RtScene* s, const RtCamera* camera, const RtRende
     RenderCtx c;
     rt_fill_ctx(s, camera, prm, plan, c);
     c.image = NULL;
+    c.packed = 0;
+    c.tile_base = 0;
     if (!plan.tiles.empty())
         cudaMemcpy(rb->d_tile_ids, plan.tiles.data(), plan.tiles.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
     for (size_t t0 = 0; t0 < plan.tiles.size(); t0 += plan.tiles_per_batch)

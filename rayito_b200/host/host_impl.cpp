@@ -169,7 +169,9 @@ static Image* raytraceImpl(ShapeSet& scene,
                            unsigned int pixelSamplesHint,
                            unsigned int lightSamplesHint,
                            unsigned int maxRayDepth,
-                           float* deviceImage)
+                           float* deviceImage,
+                           RtComm* comm = NULL,
+                           int root = 0)
 {
     // RAYITO_B200_TIMING=1 prints where a raytrace() call spends its wall time (stderr)
     const bool timing = std::getenv("RAYITO_B200_TIMING") != NULL;
@@ -190,7 +192,16 @@ static Image* raytraceImpl(ShapeSet& scene,
     if (!cam.describe(camera))
         throw std::runtime_error("rayito_b200: camera has no device description");
 
-    const rayito_b200::RenderOptions& opt = rayito_b200::renderOptions();
+    rayito_b200::RenderOptions opt = rayito_b200::renderOptions();
+    if (comm != NULL)
+    {
+        int rank = 0, world = 1, device = 0;
+        if (rt_comm_rank(comm, &rank, &world, &device) != RT_OK)
+            throw std::runtime_error("rayito_b200: bad communicator");
+        opt.rank = (unsigned)rank;
+        opt.world = (unsigned)world;
+        opt.device = device;
+    }
     RtSceneDesc desc = flat.desc();
     RtScene* dev = NULL;
     clock_gettime(CLOCK_MONOTONIC, &tp[2]);
@@ -214,7 +225,14 @@ static Image* raytraceImpl(ShapeSet& scene,
     Image* image = NULL;
     RtRenderStats stats;
     int rc;
-    if (deviceImage != NULL)
+    if (comm != NULL)
+    {
+        const bool isRoot = (int)opt.rank == root;
+        if (isRoot)
+            image = new Image(width, height, Image::Uncleared());
+        rc = rt_render_multi_host(dev, &camera, &params, comm, root, isRoot ? image->data() : NULL, &stats, NULL);
+    }
+    else if (deviceImage != NULL)
         rc = rt_render_device(dev, &camera, &params, deviceImage, &stats, NULL);
     else
     {
@@ -273,6 +291,21 @@ void raytraceToDevice(Rayito::ShapeSet& scene,
     if (deviceImage == NULL)
         throw std::runtime_error("rayito_b200: raytraceToDevice needs a device buffer");
     Rayito::raytraceImpl(scene, cam, width, height, pixelSamplesHint, lightSamplesHint, maxRayDepth, deviceImage);
+}
+
+Rayito::Image* raytraceMulti(Rayito::ShapeSet& scene,
+                             const Rayito::Camera& cam,
+                             size_t width,
+                             size_t height,
+                             unsigned int pixelSamplesHint,
+                             unsigned int lightSamplesHint,
+                             unsigned int maxRayDepth,
+                             RtComm* comm,
+                             int root)
+{
+    if (comm == NULL)
+        throw std::runtime_error("rayito_b200: raytraceMulti needs a communicator");
+    return Rayito::raytraceImpl(scene, cam, width, height, pixelSamplesHint, lightSamplesHint, maxRayDepth, NULL, comm, root);
 }
 
 namespace
@@ -344,13 +377,13 @@ void releaseHostCaches()
 
 unsigned& stageSemantics()
 {
-    static unsigned semantics = RT_SEMANTICS_STAGE7;
+    static thread_local unsigned semantics = RT_SEMANTICS_STAGE7;
     return semantics;
 }
 
 RenderOptions& renderOptions()
 {
-    static RenderOptions options;
+    static thread_local RenderOptions options;
     return options;
 }
 
@@ -638,6 +671,39 @@ int rth_app_raytrace_image(RthApp* app, const float* spec14, unsigned width, uns
         opt.countWork = count_work != 0;
         app->frame = Rayito::raytrace(app->set, cam, width, height, ps, ls, depth);
         *pixels = app->frame->data();
+        if (stats) *stats = rayito_b200::lastStats();
+        return 0;
+    }
+    catch (const std::exception& e)
+    {
+        t_hostError = e.what();
+        return -1;
+    }
+}
+
+int rth_app_raytrace_multi(RthApp* app, const float* spec14, unsigned width, unsigned height,
+                            unsigned ps, unsigned ls, unsigned depth, RtComm* comm, int root,
+                            const float** pixels, RtRenderStats* stats)
+{
+    if (app == NULL || spec14 == NULL || comm == NULL || pixels == NULL)
+    {
+        t_hostError = "null argument";
+        return -1;
+    }
+    try
+    {
+        delete app->frame;
+        app->frame = NULL;
+        *pixels = NULL;
+        StageScope stage(app->semantics);
+        Rayito::PerspectiveCamera cam(spec14[0],
+                                      Rayito::Point(spec14[1], spec14[2], spec14[3]),
+                                      Rayito::Point(spec14[4], spec14[5], spec14[6]),
+                                      Rayito::Point(spec14[7], spec14[8], spec14[9]),
+                                      spec14[10], spec14[11], spec14[12], spec14[13]);
+        app->frame = rayito_b200::raytraceMulti(app->set, cam, width, height, ps, ls, depth, comm, root);
+        if (app->frame != NULL)
+            *pixels = app->frame->data();
         if (stats) *stats = rayito_b200::lastStats();
         return 0;
     }

@@ -156,7 +156,8 @@ Image* raytrace(ShapeSet& scene,
 namespace rayito_b200
 {
 
-// Process-wide knobs of the GPU backend behind raytrace()
+// Knobs of the GPU backend behind raytrace(), per calling thread (one host thread drives one
+// GPU: a thread's settings never leak into another thread's calls)
 struct RenderOptions
 {
     int device;              // CUDA device ordinal
@@ -184,6 +185,20 @@ void raytraceToDevice(Rayito::ShapeSet& scene,
                       unsigned int lightSamplesHint,
                       unsigned int maxRayDepth,
                       float* deviceImage);
+// raytrace() of ONE frame by all the ranks of a communicator (one process per GPU; rt_comm_create
+// / rt_comm_from_nccl in include/rayito_b200.h): every rank prepares the same scene and renders
+// its screen tiles, the tiles travel to the root rank over NCCL and are assembled there.  The
+// root gets the Image (caller deletes it, as for raytrace()); every other rank gets NULL.  Rank,
+// world size and device come from the communicator, not from renderOptions().
+Rayito::Image* raytraceMulti(Rayito::ShapeSet& scene,
+                             const Rayito::Camera& cam,
+                             size_t width,
+                             size_t height,
+                             unsigned int pixelSamplesHint,
+                             unsigned int lightSamplesHint,
+                             unsigned int maxRayDepth,
+                             RtComm* comm,
+                             int root = 0);
 // raytrace() keeps its host-side working storage (the flattened scene, BVH build scratch) per
 // calling thread between calls; this hands it back to the allocator.  Device memory cached by
 // the render core is released by rt_release_cached_memory() (include/rayito_b200.h).

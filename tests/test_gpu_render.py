@@ -254,6 +254,49 @@ def test_tile_sharding_is_exact(dev1, scene1_host, capi):
     assert np.array_equal(bits(small), bits(whole))
 
 
+def test_packed_tiles_gather_and_scatter(dev1, scene1_host, capi):
+    """The multi-GPU tile assembly, rank by rank on one device: every rank's tiles rendered into
+    its packed buffer (rt_render_tiles_packed), each packed buffer scattered into the frame
+    (rt_unpack_tiles) -- what rt_render_multi does around its ncclSend / ncclRecv -- gives the
+    single-GPU image bit for bit, including tiles that hang over the image edge and a rank that
+    owns no tile at all; rt_render_multi itself on a one-rank communicator renders in place."""
+    import ctypes as C
+    import torch
+    spec = scene1_host.default_camera_spec()
+    cam = capi.camera_from_spec(spec)
+    W, H, ps = 100, 60, 2
+    whole, _ = dev1.render(cam, W, H, ps)
+    lib = capi.core()
+    for world, tile in ((2, 16), (3, 32), (5, 64), (2, 0)):
+        frame = torch.full((H, W, 3), -1.0, dtype=torch.float32, device="cuda:0")
+        total = 0
+        for rank in range(world):
+            n = capi.packed_floats(W, H, world, rank, tile)
+            ts = tile if tile else 32
+            owners, _ = capi.tile_owners(W, H, world, tile)
+            assert n == int((owners == rank).sum()) * ts * ts * 3
+            if n == 0:
+                continue
+            packed = torch.full((n,), -2.0, dtype=torch.float32, device="cuda:0")
+            params = capi.RtRenderParams(W, H, ps, 1, 3, tile, rank, world, 1024 if rank == 0 else 0, 0)
+            stats = capi.RtRenderStats()
+            capi.check(lib.rt_render_tiles_packed(dev1.handle, C.byref(cam), C.byref(params), packed.data_ptr(), n,
+                                                  C.byref(stats), None), "rt_render_tiles_packed")
+            total += stats.samples
+            capi.check(lib.rt_unpack_tiles(0, packed.data_ptr(), W, H, tile, world, rank, frame.data_ptr(), None),
+                       "rt_unpack_tiles")
+        torch.cuda.synchronize()
+        assert total == W * H * ps * ps
+        assert np.array_equal(bits(frame.cpu().numpy()), bits(whole)), (world, tile)
+    comm = capi.Comm(bytes(capi.Comm.ID_BYTES), 0, 1, 0)
+    frame = torch.zeros((H, W, 3), dtype=torch.float32, device="cuda:0")
+    params = capi.RtRenderParams(W, H, ps, 1, 3, 0, 0, 1, 0, 0)
+    stats, _ms = comm.render_multi(dev1, cam, params, frame.data_ptr())
+    comm.close()
+    assert stats.samples == W * H * ps * ps
+    assert np.array_equal(bits(frame.cpu().numpy()), bits(whole))
+
+
 @pytest.mark.parametrize("which", ["scene1", "scene2", "scene7", "scene8"])
 def test_split_and_unified_traversal_agree(which, request, capi):
     """The split top-level / mesh passes (default) and the single unified kernel must

@@ -1,5 +1,8 @@
-"""CPU tests of the N>1 path: the screen-tile partition (host code of the core) and
-the tile assembly collective, exercised with world_size-2 gloo process groups."""
+"""CPU tests of the N>1 path: the screen-tile partition and the packed-tile layout (host code
+of the core: rt_tile_owners, rt_packed_floats) and the tile assembly protocol of
+rt_render_multi -- pack own tiles, send to the root, scatter -- exercised with world_size-2
+gloo process groups.  (The device halves, rt_render_tiles_packed / rt_unpack_tiles, are
+checked on the GPU by tests/test_gpu_render.py::test_packed_tiles_gather_and_scatter.)"""
 import os
 import socket
 import sys
@@ -47,8 +50,38 @@ def _worker(rank, world, port, width, height, tile, out_path):
     truth = np.stack([xx * 1.0, yy * 2.0, xx * yy * 0.5 + 1.0], axis=-1).astype(np.float32)
     mine = owners[yy // ts, xx // ts] == rank
     image = np.where(mine[..., None], truth, 0.0).astype(np.float32)
-    t = torch.from_numpy(image.copy())
-    dist.reduce(t, dst=0, op=dist.ReduceOp.SUM)      # the path's one collective: tile assembly
+    # the path's one collective (rt_render_multi): every rank packs its tiles -- ascending tile
+    # index, pixel (r, q) of the k-th tile at ((k * ts + r) * ts + q) * 3 -- and sends the packed
+    # buffer to the root, which scatters each rank's tiles into the frame
+    tiles_y, tiles_x = owners.shape
+
+    def pack(r):
+        ids = np.flatnonzero(owners.ravel() == r)
+        buf = np.full((len(ids), ts, ts, 3), np.nan, np.float32)     # off-image pixels are never read
+        for k, tid in enumerate(ids):
+            y0, x0 = (tid // tiles_x) * ts, (tid % tiles_x) * ts
+            h, w = min(ts, height - y0), min(ts, width - x0)
+            buf[k, :h, :w] = image[y0:y0 + h, x0:x0 + w]
+        return ids, buf
+
+    ids, mine_packed = pack(rank)
+    assert mine_packed.size == capi.packed_floats(width, height, world, rank, tile)
+    frame = image.copy()
+    if rank == 0:
+        for r in range(1, world):
+            n = capi.packed_floats(width, height, world, r, tile)
+            got = torch.empty(n, dtype=torch.float32)
+            if n:
+                dist.recv(got, src=r)
+            rids = np.flatnonzero(owners.ravel() == r)
+            buf = got.numpy().reshape(len(rids), ts, ts, 3)
+            for k, tid in enumerate(rids):
+                y0, x0 = (tid // tiles_x) * ts, (tid % tiles_x) * ts
+                h, w = min(ts, height - y0), min(ts, width - x0)
+                frame[y0:y0 + h, x0:x0 + w] = buf[k, :h, :w]
+    elif mine_packed.size:
+        dist.send(torch.from_numpy(mine_packed.reshape(-1).copy()), dst=0)
+    t = torch.from_numpy(frame)
     rays = torch.tensor([float(mine.sum())], dtype=torch.float64)
     dist.all_reduce(rays, op=dist.ReduceOp.SUM)       # bench.py's whole-job ray count
     elapsed = torch.tensor([1.0 + rank], dtype=torch.float64)
@@ -60,7 +93,7 @@ def _worker(rank, world, port, width, height, tile, out_path):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("width,height,tile", [(100, 60, 16), (64, 64, 32)])
+@pytest.mark.parametrize("width,height,tile", [(100, 60, 16), (64, 64, 32), (33, 65, 0)])
 def test_tile_assembly_world2_gloo(tmp_path, width, height, tile):
     import torch.multiprocessing as mp
     port = _free_port()
