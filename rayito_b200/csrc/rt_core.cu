@@ -476,6 +476,7 @@ int rt_stage1_render(int device, const RtStage1Plane* planes, uint32_t num_plane
 
 void rt_release_cached_memory(void)
 {
+    rt_detail::s23_release();                      // the Stage 2/3 working set goes back to the pool first
     rt_detail::pool_release_all();
     rt_detail::validate_scratch().release();       // the calling thread's BVH validation scratch
 }

@@ -504,7 +504,11 @@ k_split_mesh(const __grid_constant__ DScene sc, const IO io, const SplitBufs sb,
 {
     split_zero(ps);
     WorkCount wc = RT_WORK_ZERO;
+#if RT_MESH_PAIR
+    trace_mesh_pair<CAP, ANY, COUNT>(sc, io, sb, ps, wc);
+#else
     trace_mesh<CAP, ANY, COUNT>(sc, io, sb, ps, wc);
+#endif
     if (COUNT)
         flush_work_counters(wc, totals);
 }

@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <system_error>
 #include <thread>
 #include <vector>
 
@@ -137,9 +138,21 @@ inline void parallel_ranges(size_t n, size_t grain, Body body)
     }
     std::vector<std::thread> workers;
     workers.reserve(pieces - 1);
-    for (size_t c = 1; c < pieces; ++c)
-        workers.push_back(std::thread(body, n * c / pieces, n * (c + 1) / pieces));
+    size_t started = 1;             // pieces [1, started) run on workers; the rest falls to this thread
+    for (; started < pieces; ++started)
+    {
+        try
+        {
+            workers.push_back(std::thread(body, n * started / pieces, n * (started + 1) / pieces));
+        }
+        catch (const std::system_error&)
+        {
+            break;                  // no more threads to be had: the caller does the remaining pieces itself
+        }
+    }
     body((size_t)0, n / pieces);
+    if (started < pieces)
+        body(n * started / pieces, n);
     for (size_t i = 0; i < workers.size(); ++i)
         workers[i].join();
 }
@@ -355,6 +368,18 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
 
     if (desc->semantics != RT_SEMANTICS_STAGE7 && desc->semantics != RT_SEMANTICS_STAGE6)
         return rt_fail(RT_ERR_ARG, "unknown RtSceneDesc.semantics");
+    // every array with a non-zero count must be there
+    if ((desc->num_xforms && desc->xforms == NULL) ||
+        (desc->num_keys && (desc->key_time == NULL || desc->key_scale == NULL || desc->key_rotation == NULL || desc->key_translation == NULL)) ||
+        (desc->num_top_nodes && desc->top_nodes == NULL) || (desc->num_mesh_nodes && desc->mesh_nodes == NULL) ||
+        (desc->num_planes && desc->planes == NULL) || (desc->num_spheres && desc->spheres == NULL) ||
+        (desc->num_rects && desc->rects == NULL) || (desc->num_meshes && desc->meshes == NULL) ||
+        (desc->num_vertices && desc->vertices == NULL) || (desc->num_normals && desc->normals == NULL) ||
+        (desc->num_faces && (desc->face_start == NULL || desc->face_has_normals == NULL)) ||
+        (desc->num_indices && (desc->vertex_index == NULL || desc->normal_index == NULL)) ||
+        (desc->num_cdf && desc->face_area_cdf == NULL) || (desc->num_materials && desc->materials == NULL) ||
+        (desc->num_lights && desc->lights == NULL))
+        return rt_fail(RT_ERR_ARG, "RtSceneDesc: an array with a non-zero count is null");
     for (uint32_t i = 0; i < desc->num_xforms; ++i)
     {
         const RtXform& x = desc->xforms[i];
@@ -481,8 +506,9 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
         dev_first_node[m] = (uint32_t)dev_nodes;
         dev_nodes += desc->meshes[m].num_nodes;
     }
-    if (dev_nodes >= 0xffffffffull)
-        return rt_fail(RT_ERR_ARG, "too many mesh BVH nodes");
+    // the face-BVH pass packs (child pair index, split axis) and (leaf flag, first triangle record) into one word each
+    if (dev_nodes >= (1ull << 29) || num_tris >= (1ull << 31))
+        return rt_fail(RT_ERR_UNSUPPORTED, "more than 2^29 mesh BVH nodes or 2^31 fan triangles");
     std::vector<DMesh> meshes(desc->num_meshes);
     for (uint32_t m = 0; m < desc->num_meshes; ++m)
     {
@@ -736,13 +762,19 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
             const uint32_t dev_first = dev_first_node[m];
             if (dev_first != 0)
                 std::memset(&mesh_nodes[dev_first - 1], 0, sizeof(DNode));      // the padding slot
-            parallel_ranges(mesh.num_nodes, 1u << 15, [=](size_t nb, size_t ne) {
+            parallel_ranges(mesh.num_nodes, 1u << 15, [=, &bad](size_t nb, size_t ne) {
                 for (size_t i = nb; i < ne; ++i)
                 {
                     const RtBvhNode& n = desc->mesh_nodes[mesh.first_node + i];
                     uint32_t word = n.first_child_or_prim, flags = n.flags;
                     if (flags & RT_NODE_LEAF)
                     {
+                        // (also nodes the walk from the root never reaches: they are converted like the rest)
+                        if (n.first_child_or_prim >= mesh.num_faces)
+                        {
+                            bad.store(3);
+                            return;
+                        }
                         uint32_t gf = mesh.first_face + n.first_child_or_prim;
                         word = fft[gf];
                         flags = RT_NODE_LEAF | ((fft[gf + 1] - fft[gf]) << 3);
@@ -758,7 +790,9 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
             });
         }
         if (bad.load() != 0)
-            return rt_fail(RT_ERR_ARG, bad.load() == 1 ? "vertex index out of range" : "normal index out of range");
+            return rt_fail(RT_ERR_ARG, bad.load() == 1 ? "vertex index out of range" :
+                                       bad.load() == 2 ? "normal index out of range" :
+                                                         "mesh BVH leaf (not reachable from the root) names a face that does not exist");
     }
 
     RtScene* sc = new RtScene();

@@ -980,4 +980,329 @@ __device__ __forceinline__ void trace_mesh(const DScene& sc, const IO& io, const
     }
 }
 
+// ---------------------------------------------------------------------------
+// Mesh pass, sibling-pair form (default).
+//
+// trace_mesh above does one dependent 32-byte fetch per node popped: pop, fetch the node, wait,
+// test its box, descend.  The by-line profile of config C5 (profiles/README.md, r01 v11) put 45 %
+// of the stall samples on the first use of the node just fetched: the pass is a chain of memory
+// round trips, ~24 per ray (one per pop, plus one for a leaf's triangles).
+//
+// The reference numbers the two children of a node b and b+1 (RAccel.h:366-371) and the upload
+// puts every such pair on one aligned 64-byte piece (rt_scene.cuh).  So one fetch of the PAIR when
+// a node is expanded gives both children's boxes, kinds (interior / leaf) and payloads (own child
+// pair / triangle range) at once, and everything the reference decides when it later pops either
+// child can be decided from data already in registers:
+//   * the near child is popped right after the push (RAccel.h:540-556): its cull check and slab
+//     test run at once; only if it passes is its own pair fetched -- the one dependent fetch;
+//   * the far child's slab values do not depend on when it is popped, only the clip against the
+//     current m_t does: A = max(slab_near, t0) and B = min(slab_far, t1) are computed at push time
+//     with the reference's operations, and the pop evaluates `t0 >= m_t` and A <= min(B, m_t) --
+//     the same numbers (min is associative on numbers; a NaN slab value makes both forms fail);
+//     a far child that fails already at push time (A <= B false, or t0 >= m_t: m_t only shrinks)
+//     fails at pop time too, so it is not even pushed;
+//   * a leaf is never box-tested (RAccel.h:506-511): its triangle range comes from the pair, so a
+//     leaf is popped without any fetch of its node.
+// Every lane still pops exactly the reference's nodes in the reference's order (the work counters,
+// which count a far child's pop when the reference would pop it, stay equal to the oracle's) and
+// tests the same triangles against the same m_t, so hits are bit-identical; what changes is that a
+// ray now waits for memory once per node EXPANDED (~11 per ray on C5) instead of once per node
+// popped (~24).
+// Stack entry (16 bytes, shared memory then local): interior (pair | axis << 29, t0, A, B);
+// leaf (LEAF | first triangle record, triangle count, -, -).
+// ---------------------------------------------------------------------------
+#ifndef RT_MESH_PAIR
+#define RT_MESH_PAIR 1
+#endif
+#ifndef RT_PAIR_SMEM_STACK
+#define RT_PAIR_SMEM_STACK 8
+#endif
+#ifndef RT_PAIR_SMEM_STACK_DEEP
+#define RT_PAIR_SMEM_STACK_DEEP 10
+#endif
+#ifndef RT_PAIR_ADVANCE_STEPS
+#define RT_PAIR_ADVANCE_STEPS 3
+#endif
+#define RT_PAIR_LEAF 0x80000000u
+#define RT_PAIR_MAX_NODES (1u << 29)      /* pair index and split axis share a word */
+
+template <bool PLAIN>
+__device__ __forceinline__ void pair_slabs(float4 q0, float4 q1, V3 o, V3 inv, float& lo, float& hi)
+{
+    if (PLAIN)
+    {
+        V3 a = (mk(q0.x, q0.y, q0.z) - o) * inv;
+        V3 b = (mk(q0.w, q1.x, q1.y) - o) * inv;
+        lo = fmaxf(fmaxf(fminf(a.x, b.x), fminf(a.y, b.y)), fminf(a.z, b.z));
+        hi = fminf(fminf(fmaxf(a.x, b.x), fmaxf(a.y, b.y)), fmaxf(a.z, b.z));
+    }
+    else
+        box_slabs(q0, q1, o, inv, lo, hi);
+}
+
+template <int CAP, bool ANY, bool COUNT, class IO>
+__device__ __forceinline__ void trace_mesh_pair(const DScene& sc, const IO& io, const SplitBufs& sb, const SplitPass& ps, WorkCount& wc)
+{
+    constexpr int kSmemStack = CAP > 32 ? RT_PAIR_SMEM_STACK_DEEP : RT_PAIR_SMEM_STACK;
+    static_assert(kSmemStack >= 1 && kSmemStack < CAP, "shared-memory stack slots");
+    __shared__ float4 sm_stack[kSmemStack * RT_BLOCK];
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t lt_mask = (1u << lane) - 1;
+    const uint32_t n = *ps.in_count;
+
+    float4 lm_stack[CAP - kSmemStack];
+
+    bool active = false;
+    bool exhausted = false;
+    uint32_t tag = 0;
+    float tmax = 0.0f;
+    LocalRay r1;
+    r1.o = r1.d = r1.inv = mk(0.0f, 0.0f, 0.0f);
+    r1.neg = 0;
+    r1.plain = false;
+    float best = 0.0f;           // m_t
+    int32_t best_rec = -1;       // triangle record accepted in this mesh, if any
+    bool any_hit = false;
+    uint32_t mesh_shape = 0;
+    const DNode* mesh_nodes = sc.mesh_nodes;
+    int sp = 0;
+    bool have_cur = false;       // cur_*: an interior node whose box test passed, waiting to be expanded
+    uint32_t cur_ref = 0;        // its child pair | split axis << 29
+    float cur_t0 = 0.0f, cur_t1 = 0.0f;
+    bool parked = false;
+    uint32_t park_word = 0, park_count = 0;
+
+#define RT_PAIR_PUT(slot, v_)                                                           \
+    { if ((slot) < kSmemStack) sm_stack[(slot) * RT_BLOCK + threadIdx.x] = (v_);        \
+      else lm_stack[(slot) - kSmemStack] = (v_); }
+#define RT_PAIR_GET(slot, v_)                                                           \
+    { if ((slot) < kSmemStack) (v_) = sm_stack[(slot) * RT_BLOCK + threadIdx.x];        \
+      else (v_) = lm_stack[(slot) - kSmemStack]; }
+
+    for (;;)
+    {
+        uint32_t idle = __ballot_sync(0xffffffffu, !active);
+        if (!exhausted && (idle == 0xffffffffu || __popc(idle) >= RT_MESH_REFILL_MIN))
+        {
+            uint32_t need = __popc(idle);
+            uint32_t base = 0;
+            if (lane == 0)
+                base = atomicAdd(ps.cursor, need);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base + need >= n)
+                exhausted = true;
+            uint32_t j = base + __popc(idle & lt_mask);
+            if (!active && j < n)
+            {
+                active = true;
+                parked = false;
+                have_cur = false;
+                tag = ps.in_queue[j];
+                float4 b = sb.ray_d[tag], h = sb.hit[tag];
+                tmax = b.w;
+                best = h.x;
+                best_rec = -1;
+                any_hit = false;
+                mesh_shape = __float_as_uint(h.w) & 0xffffffu;
+                DShape sh = load_shape(sc, mesh_shape);
+                DMesh m = sc.meshes[sh.geom];
+                // the top pass already warped the ray into mesh-local space and found that it enters
+                // the root; redo the root's slab test (same inputs, same bits) only to get the clipped
+                // range its children inherit
+                float4 mo = sb.mesh_o[tag], md = sb.mesh_d[tag];
+                r1.o = xyz4(mo);
+                r1.d = xyz4(md);
+                local_ray_finish(r1);
+                mesh_nodes = sc.mesh_nodes + m.first_node;
+                DNode root = load_node(mesh_nodes, 0);
+                uint32_t rflags = __float_as_uint(root.q1.w);
+                uint32_t rword = __float_as_uint(root.q1.z);
+                sp = 0;
+                if (rflags & RT_NODE_LEAF)
+                {
+                    parked = true;
+                    park_word = rword;
+                    park_count = rflags >> 3;
+                }
+                else
+                {
+                    float t0 = RT_RAY_TMIN, t1 = ANY ? tmax : best;
+                    box_test(root.q0, root.q1, r1.o, r1.inv, t0, t1);
+                    cur_ref = rword | ((rflags & RT_NODE_AXIS) << 29);
+                    cur_t0 = t0;
+                    cur_t1 = t1;
+                    have_cur = true;
+                }
+            }
+        }
+        if (__ballot_sync(0xffffffffu, active) == 0)
+        {
+            if (exhausted)
+                break;
+            continue;
+        }
+        // warp-uniform: all rays in flight are NaN-free (see trace_mesh)
+        const bool warp_plain = __all_sync(0xffffffffu, !active || r1.plain);
+
+        #pragma unroll 1
+        for (int it = 0; it < RT_PAIR_ADVANCE_STEPS && active && !parked && (have_cur || sp > 0); ++it)
+        {
+            // ---- find the next node to expand: pops that fail their (cheap, register-only) checks
+            // are retired here, so that the lanes of the warp meet again at the fetch below
+            while (!have_cur && sp > 0)
+            {
+                --sp;
+                float4 e;
+                RT_PAIR_GET(sp, e);
+                const uint32_t ref = __float_as_uint(e.x);
+                if (COUNT) wc.node_pops++;
+                if (ref & RT_PAIR_LEAF)
+                {
+                    parked = true;
+                    park_word = ref & ~RT_PAIR_LEAF;
+                    park_count = __float_as_uint(e.y);
+                    break;
+                }
+                float t1 = e.w;
+                if (!ANY)
+                {
+                    if (e.y >= best)            // t0 >= m_t  (RAccel.h:523-526)
+                        continue;
+                    t1 = warp_plain ? fminf(e.w, best) : ((e.w > best) ? best : e.w);   // min(B, m_t)
+                }
+                if (!(e.z <= t1))               // A <= min(B, m_t)
+                    continue;
+                cur_ref = ref;
+                cur_t0 = e.z;
+                cur_t1 = t1;
+                have_cur = true;
+            }
+            if (!have_cur)
+                break;
+            have_cur = false;
+
+            // ---- expand: one 64-byte fetch brings both children
+            const uint32_t pair = cur_ref & (RT_PAIR_MAX_NODES - 1u);
+            const uint32_t axis = cur_ref >> 29;
+            const float4* p = reinterpret_cast<const float4*>(mesh_nodes + pair);
+            const float4 a0 = __ldg(p), a1 = __ldg(p + 1), b0 = __ldg(p + 2), b1 = __ldg(p + 3);
+            float lo0, hi0, lo1, hi1;
+            if (warp_plain)
+            {
+                pair_slabs<true>(a0, a1, r1.o, r1.inv, lo0, hi0);
+                pair_slabs<true>(b0, b1, r1.o, r1.inv, lo1, hi1);
+            }
+            else
+            {
+                pair_slabs<false>(a0, a1, r1.o, r1.inv, lo0, hi0);
+                pair_slabs<false>(b0, b1, r1.o, r1.inv, lo1, hi1);
+            }
+            const bool neg = (r1.neg >> axis) & 1u;      // near = first child when the direction is negative on the axis
+            const float near_lo = neg ? lo0 : lo1, near_hi = neg ? hi0 : hi1;
+            const float far_lo = neg ? lo1 : lo0, far_hi = neg ? hi1 : hi0;
+            const uint32_t near_word = __float_as_uint(neg ? a1.z : b1.z), near_flags = __float_as_uint(neg ? a1.w : b1.w);
+            const uint32_t far_word = __float_as_uint(neg ? b1.z : a1.z), far_flags = __float_as_uint(neg ? b1.w : a1.w);
+            const float t0 = cur_t0, t1 = cur_t1;
+
+            // far child: pushed first (popped after everything below the near child)
+            if (far_flags & RT_NODE_LEAF)
+            {
+                RT_PAIR_PUT(sp, make_float4(__uint_as_float(RT_PAIR_LEAF | far_word), __uint_as_float(far_flags >> 3), 0.0f, 0.0f));
+                ++sp;
+            }
+            else
+            {
+                // what its pop will compute that does not depend on m_t: A = max(slab near, t0), B = min(slab far, t1)
+                const float A = warp_plain ? fmaxf(far_lo, t0) : std_max(far_lo, t0);
+                const float B = warp_plain ? fminf(far_hi, t1) : std_min(far_hi, t1);
+                bool keep = A <= B;
+                if (!ANY && t0 >= best)
+                    keep = false;
+                if (keep)
+                {
+                    RT_PAIR_PUT(sp, make_float4(__uint_as_float(far_word | ((far_flags & RT_NODE_AXIS) << 29)), t0, A, B));
+                    ++sp;
+                }
+                else if (COUNT)
+                    wc.node_pops++;         // the reference pops it (and drops it) later: same count
+            }
+
+            // near child: popped at once
+            if (COUNT) wc.node_pops++;
+            if (near_flags & RT_NODE_LEAF)
+            {
+                parked = true;
+                park_word = near_word;
+                park_count = near_flags >> 3;
+                break;
+            }
+            if (!ANY && t0 >= best)
+                continue;
+            // (t1 <= m_t already: it is the parent's clipped range and m_t has not changed since)
+            const float A = warp_plain ? fmaxf(near_lo, t0) : std_max(near_lo, t0);
+            const float B = warp_plain ? fminf(near_hi, t1) : std_min(near_hi, t1);
+            if (A <= B)
+            {
+                cur_ref = near_word | ((near_flags & RT_NODE_AXIS) << 29);
+                cur_t0 = A;
+                cur_t1 = B;
+                have_cur = true;
+            }
+        }
+
+        const uint32_t m_tri = __ballot_sync(0xffffffffu, parked);
+        const uint32_t m_adv = __ballot_sync(0xffffffffu, active && !parked && (have_cur || sp > 0));
+        const bool do_tri = m_tri != 0 && (m_adv == 0 || exhausted || __popc(m_tri) >= RT_MESH_SERVICE_MIN);
+
+        if (do_tri && parked)
+        {
+            for (uint32_t k = 0; k < park_count; ++k)
+            {
+                V3 p0, p1, p2;
+                uint32_t w0, w1, w2;
+                load_tri(sc, park_word + k, p0, p1, p2, w0, w1, w2);
+                if (COUNT) wc.tri_tests++;
+                float t, beta, gamma;
+                if (tri_closest(r1.o, r1.d, p0, p1, p2, ANY ? tmax : best, t, beta, gamma))
+                {
+                    if (ANY) { any_hit = true; sp = 0; have_cur = false; break; }
+                    best = t;
+                    best_rec = (int32_t)(park_word + k);
+                    if (sc.stage6) break;        // S6 RMesh.h:204-209
+                }
+            }
+            parked = false;
+        }
+
+        // retire: hand the slot back to a top-level resume pass (or finish a shadow ray)
+        const bool done = active && !parked && !have_cur && sp == 0;
+        if (__ballot_sync(0xffffffffu, done))
+        {
+            bool resume = false;
+            if (done)
+            {
+                if (ANY && any_hit)
+                {
+                    WaveResult r;
+                    r.t = tmax; r.shape = -1; r.tri_rec = -1; r.any_hit = true;
+                    io.store(tag, r);
+                }
+                else
+                {
+                    if (best_rec >= 0)
+                    {
+                        float4 h = sb.hit[tag];
+                        sb.hit[tag] = make_float4(best, __int_as_float((int32_t)mesh_shape), __int_as_float(best_rec), h.w);
+                    }
+                    resume = true;
+                }
+                active = false;
+            }
+            warp_queue_push(ps.out_queue, ps.out_count, resume, tag);
+        }
+    }
+#undef RT_PAIR_PUT
+#undef RT_PAIR_GET
+}
+
 #endif // RAYITO_B200_RT_SPLIT_CUH

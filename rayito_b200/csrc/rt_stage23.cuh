@@ -28,6 +28,7 @@
 
 #include <mutex>
 
+#include "rt_pool.cuh"
 #include "rt_sampling.cuh"
 #include "rt_shade.cuh"
 
@@ -704,6 +705,36 @@ inline S23Derived s23_derive(const RtS23Shape& sh)
     return d;
 }
 
+// Working set kept between calls (one block, grow only)
+struct S23Cache
+{
+    std::mutex lock;
+    char* block;
+    size_t bytes;
+    int device;
+    S23Cache() : block(NULL), bytes(0), device(-1) { }
+};
+inline S23Cache& s23_cache() { static S23Cache c; return c; }
+inline void s23_release_locked(S23Cache& c)
+{
+    if (c.block != NULL)
+    {
+        cudaSetDevice(c.device);
+        cudaDeviceSynchronize();
+        pool_free(c.device, c.block, c.bytes);
+    }
+    c.block = NULL;
+    c.bytes = 0;
+    c.device = -1;
+}
+// rt_release_cached_memory(): park the Stage 2/3 working set in the pool, which is released next
+inline void s23_release()
+{
+    S23Cache& c = s23_cache();
+    std::lock_guard<std::mutex> guard(c.lock);
+    s23_release_locked(c);
+}
+
 inline int rt_stage23_impl(int device, const RtS23Scene* scene, const RtCamera* cam, const RtS23Params* prm,
                            float* rgb, uint8_t* rgb8, RtRenderStats* stats)
 {
@@ -771,19 +802,22 @@ inline int rt_stage23_impl(int device, const RtS23Scene* scene, const RtCamera* 
     c.seg_len = ((c.seg_len + 31) / 32) * 32;
     c.num_segs = (uint32_t)((c.num_samples + c.seg_len - 1) / c.seg_len);
 
-    // a^i (i < 64), a^(64 j) (j < 64) and a^(4096 l) (l < 256) for both generators
+    // a^i (i < 64), a^(64 j) (j < 64) and a^(4096 l) (l < 256) for both generators, filled once
     static uint32_t table[2 * RT_S23_TABLE];
-    for (int g = 0; g < 2; ++g)
-    {
-        uint64_t a = g == 0 ? RT_MWC_AZ : RT_MWC_AW, m = g == 0 ? RT_MWC_MZ : RT_MWC_MW;
-        for (uint32_t i = 0; i < 64; ++i)
+    static std::once_flag table_once;
+    std::call_once(table_once, []() {
+        for (int g = 0; g < 2; ++g)
         {
-            table[g * RT_S23_TABLE + i] = (uint32_t)mwc_powmod(a, i, m);
-            table[g * RT_S23_TABLE + 64 + i] = (uint32_t)mwc_powmod(a, 64ull * i, m);
+            uint64_t a = g == 0 ? RT_MWC_AZ : RT_MWC_AW, m = g == 0 ? RT_MWC_MZ : RT_MWC_MW;
+            for (uint32_t i = 0; i < 64; ++i)
+            {
+                table[g * RT_S23_TABLE + i] = (uint32_t)mwc_powmod(a, i, m);
+                table[g * RT_S23_TABLE + 64 + i] = (uint32_t)mwc_powmod(a, 64ull * i, m);
+            }
+            for (uint32_t i = 0; i < 256; ++i)
+                table[g * RT_S23_TABLE + 128 + i] = (uint32_t)mwc_powmod(a, 4096ull * i, m);
         }
-        for (uint32_t i = 0; i < 256; ++i)
-            table[g * RT_S23_TABLE + 128 + i] = (uint32_t)mwc_powmod(a, 4096ull * i, m);
-    }
+    });
 
     const size_t n = (size_t)c.num_samples, px = (size_t)c.width * c.height;
     const size_t A = 255;       // every sub-buffer starts on a 256-byte boundary
@@ -793,34 +827,25 @@ inline int rt_stage23_impl(int device, const RtS23Scene* scene, const RtCamera* 
     size_t bytes_rgb = (px * 12 + A) & ~A, bytes_rgb8 = (px * 3 + A) & ~A;
     size_t total = bytes_flags + bytes_hb + bytes_terms + 2 * bytes_seg + 2 * bytes_dirty + 256 + bytes_rgb + bytes_rgb8 +
                    sizeof(table);
-    // working memory is kept between calls (grow only): a sweep re-renders the same image many times
-    static std::mutex cache_lock;
-    static char* cache_block = NULL;
-    static size_t cache_bytes = 0;
-    static int cache_device = -1;
-    std::lock_guard<std::mutex> guard(cache_lock);
+    // working memory is kept between calls (grow only): a sweep re-renders the same image many times.
+    // The block comes from the device pool, so rt_release_cached_memory() can hand it back (s23_release).
+    S23Cache& cache = s23_cache();
+    std::lock_guard<std::mutex> guard(cache.lock);
     cudaError_t err = cudaSuccess;
-    if (cache_device != device || cache_bytes < total)
+    if (cache.device != device || cache.bytes < total)
     {
-        if (cache_block)
-        {
-            cudaSetDevice(cache_device);
-            cudaFree(cache_block);
-            cudaSetDevice(device);
-        }
-        cache_block = NULL;
-        cache_bytes = 0;
-        err = cudaMalloc((void**)&cache_block, total);
+        s23_release_locked(cache);
+        err = pool_alloc(device, (void**)&cache.block, total, &cache.bytes);
         if (err != cudaSuccess)
         {
-            cache_block = NULL;
+            cache.block = NULL;
+            cache.bytes = 0;
             cudaGetLastError();
             return rt_fail(RT_ERR_CUDA, cudaGetErrorString(err));
         }
-        cache_bytes = total;
-        cache_device = device;
+        cache.device = device;
     }
-    char* block = cache_block;
+    char* block = cache.block;
     cudaEvent_t ev[3] = { NULL, NULL, NULL };
     int rc = RT_OK;
     uint64_t launches = 0, rounds = 0;
