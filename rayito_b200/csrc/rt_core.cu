@@ -69,6 +69,7 @@ struct BatchIO
         load_ray(rays, j, o, d, tmax, time);
         return true;
     }
+    __device__ __forceinline__ const float4* xf_row(uint32_t) const { return nullptr; }     // ray batches: no per-sample cache
     __device__ __forceinline__ void store(uint32_t tag, const WaveResult& r) const
     {
         if (raw) raw[tag] = make_float4(r.t, __int_as_float(r.shape), __int_as_float(r.tri_rec), 0.0f);

@@ -53,13 +53,27 @@ struct DNode
 //              translation(t) needs evaluating
 //   STATIC     TRANSLATE with at most one key: the translation is a constant, kept
 //              in the shape record itself
+//   RIGID      every scale key exactly (1,1,1), rotations arbitrary: scaling(t) is exactly (1,1,1)
+//              for every t by the same argument, so only translation(t) and rotation(t) are evaluated
 #define RT_XF_GENERAL 0u
 #define RT_XF_TRANSLATE 1u
 #define RT_XF_STATIC 2u
+#define RT_XF_RIGID 3u
+
+// Per-sample transform cache (rt_render.cuh).  Every ray of a pixel sample carries the sample's
+// time, and translation(t) / rotation(t) / scaling(t) are pure functions of it, so the renderer
+// evaluates every ANIMATED transform (two or more keys) once per sample, all lanes together, when
+// the camera ray is generated, and the traversal / shading kernels read the values back instead of
+// re-running the key search, the lerps and the normalised quaternion lerp (a square root and four
+// IEEE divisions) every time one of the sample's rays enters the shape -- which they did at 4-12
+// of 32 lanes, half of all warp instructions of the top-level passes (profiles/README.md, r02).
+// A sample's row holds, per animated transform in upload order: TRANSLATE one float4 (t.xyz, -);
+// RIGID two (t.xyz, qw) (qv.xyz, -); GENERAL three (t.xyz, qw) (qv.xyz, s.x) (s.y, s.z, -, -).
+#define RT_XF_CACHE_MAX_STRIDE 32u     /* float4 per sample; scenes with more animated data evaluate directly */
 
 struct DShapeMem         // 32 bytes in HBM, two 128-bit loads
 {
-    uint32_t type_kind;  // RT_SHAPE_* | RT_XF_* << 8
+    uint32_t type_kind;  // RT_SHAPE_* | RT_XF_* << 8 | (offset in the per-sample transform cache + 1, 0 = not cached) << 16
     uint32_t geom, xform, material;
     int32_t light;
     float tx, ty, tz;    // translation of a STATIC transform
@@ -70,6 +84,7 @@ struct DShape            // the same, decoded into registers (load_shape)
     uint32_t type, geom, xform, material;
     int32_t light;
     uint32_t xkind;
+    uint32_t cache_slot; // offset in the per-sample transform cache + 1, 0 = evaluate directly
     float tx, ty, tz;
 };
 
@@ -168,6 +183,10 @@ struct DScene
     const uint32_t* lights;      // shape index per light
     const DTopStep* top_walk;    // [8 octants][top_walk_steps], NULL if the top level is too deep to tabulate
     uint32_t top_walk_steps;
+    // per-sample transform cache: the animated transforms in row order (xform index, row offset, kind)
+    const uint4* anim;           // x = xform, y = row offset (float4), z = RT_XF_*
+    uint32_t num_anim;
+    uint32_t anim_stride;        // float4 per sample (0 = no cache)
 };
 
 // ---------------------------------------------------------------------------
@@ -264,7 +283,7 @@ __device__ __noinline__ TRS xform_eval(const DScene& sc, uint32_t xform, float t
         r.qv = mk(0.0f, 0.0f, 0.0f);
         return r;
     }
-    if (x.kind != RT_XF_GENERAL)
+    if (x.kind == RT_XF_TRANSLATE || x.kind == RT_XF_STATIC)
     {
         // translation-only transform: rotation(t) and scaling(t) are exactly identity
         r.s = mk(1.0f, 1.0f, 1.0f);
@@ -290,10 +309,11 @@ __device__ __noinline__ TRS xform_eval(const DScene& sc, uint32_t xform, float t
     const float* T = sc.key_trans + 3 * i;
     const float* S = sc.key_scale + 3 * i;
     const float* R = sc.key_rot + 4 * i;
+    const bool rigid = x.kind == RT_XF_RIGID;       // scaling(t) == (1,1,1) exactly, whatever t
     if (mix == 0.0f)
     {
         r.t = mk(T[0], T[1], T[2]);
-        r.s = mk(S[0], S[1], S[2]);
+        r.s = rigid ? mk(1.0f, 1.0f, 1.0f) : mk(S[0], S[1], S[2]);
         r.qw = R[0];
         r.qv = mk(R[1], R[2], R[3]);
     }
@@ -301,7 +321,7 @@ __device__ __noinline__ TRS xform_eval(const DScene& sc, uint32_t xform, float t
     {
         float om = 1.0f - mix;
         r.t = mk(T[0], T[1], T[2]) * om + mk(T[3], T[4], T[5]) * mix;
-        r.s = mk(S[0], S[1], S[2]) * om + mk(S[3], S[4], S[5]) * mix;
+        r.s = rigid ? mk(1.0f, 1.0f, 1.0f) : mk(S[0], S[1], S[2]) * om + mk(S[3], S[4], S[5]) * mix;
         // lerp(q1, q2, t) = (q1*(1-t) + q2*t).normalized()   (RMath.h:576-580)
         float w = om * R[0] + mix * R[4];
         V3 v = mk(R[1], R[2], R[3]) * om + mk(R[5], R[6], R[7]) * mix;
@@ -309,6 +329,42 @@ __device__ __noinline__ TRS xform_eval(const DScene& sc, uint32_t xform, float t
         if (len > 0) { w /= len; v = v / len; }
         r.qw = w;
         r.qv = v;
+    }
+    return r;
+}
+
+// The transform cache: write one transform's values into a sample's row / read them back
+__device__ __forceinline__ void xform_cache_store(float4* row, uint32_t off, uint32_t kind, const TRS& r)
+{
+    if (kind == RT_XF_TRANSLATE)
+    {
+        row[off] = make_float4(r.t.x, r.t.y, r.t.z, 0.0f);
+        return;
+    }
+    row[off] = make_float4(r.t.x, r.t.y, r.t.z, r.qw);
+    row[off + 1] = make_float4(r.qv.x, r.qv.y, r.qv.z, r.s.x);
+    if (kind != RT_XF_RIGID)
+        row[off + 2] = make_float4(r.s.y, r.s.z, 0.0f, 0.0f);
+}
+__device__ __forceinline__ TRS xform_cache_load(const float4* row, uint32_t off, uint32_t kind, bool stage6)
+{
+    TRS r;
+    r.absent = stage6;
+    const float4 a = __ldg(row + off);
+    r.t = mk(a.x, a.y, a.z);
+    r.s = mk(1.0f, 1.0f, 1.0f);
+    r.qw = 1.0f;
+    r.qv = mk(0.0f, 0.0f, 0.0f);
+    if (kind != RT_XF_TRANSLATE)
+    {
+        const float4 b = __ldg(row + off + 1);
+        r.qw = a.w;
+        r.qv = mk(b.x, b.y, b.z);
+        if (kind != RT_XF_RIGID)
+        {
+            const float4 c = __ldg(row + off + 2);
+            r.s = mk(b.w, c.x, c.y);
+        }
     }
     return r;
 }

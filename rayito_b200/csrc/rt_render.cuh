@@ -96,6 +96,7 @@ struct RenderCtx
     float4* lrec;
     float4* mis_hit0;
     float4* mis_hit1;
+    float4* xf_cache;           // per-sample transform cache: sc.anim_stride float4 per sample (rt_device.cuh), or NULL
     uint32_t qcap;              // capacity of one queue bin (= samples of the batch buffers)
     uint32_t* q_path[2];        // RT_QBINS bins each
     uint32_t* q_shade;          // RT_SBINS bins: hit paths waiting for k_shade
@@ -111,6 +112,12 @@ struct RenderCtx
     uint32_t packed;            // tile-packed output: pixel (tile slot k, row r, column q) at ((k * tile + r) * tile + q) * 3
     uint32_t tile_base;         // packed: slot of this batch's first tile in the rank's tile list
 };
+
+// Sample i's row of the per-sample transform cache (NULL when the scene has no animated transform)
+__device__ __forceinline__ const float4* xf_row(const RenderCtx& c, uint32_t i)
+{
+    return c.xf_cache ? c.xf_cache + (size_t)i * c.sc.anim_stride : nullptr;
+}
 
 // Where pixel p of the batch (image coordinates x, y) is written
 __device__ __forceinline__ float* pixel_out(const RenderCtx& c, uint32_t p, uint32_t x, uint32_t y)
@@ -249,8 +256,10 @@ __device__ __forceinline__ void camera_ray(const RenderCtx& c, uint32_t p, uint3
     cmj2d(psi, c.ps, c.ps, perm_sub, pu, pv);
     float xu = ((float)x + pu) / (float)c.width;
     float yu = 1.0f - ((float)y + pv) / (float)c.height;
-    float lens_u, lens_v;
-    cmj2d(psi, c.ps, c.ps, perm_lens, lens_u, lens_v);
+    // (the lens sample is a pure function of (psi, permutation): a pinhole camera never looks at it)
+    float lens_u = 0.0f, lens_v = 0.0f;
+    if (c.cam.lens_radius > 0)
+        cmj2d(psi, c.ps, c.ps, perm_lens, lens_u, lens_v);
     float time_u = cmj1d(psi, c.spp, perm_time);
 
     float xs = (xu - 0.5f) * c.aspect + 0.5f;
@@ -291,6 +300,16 @@ k_raygen(const __grid_constant__ RenderCtx c)
                 V3 o, d;
                 float time;
                 camera_ray(c, p, psi, xy & 0xffffu, xy >> 16, o, d, time);
+                if (c.xf_cache)
+                {
+                    // every animated transform of the scene at this sample's time, once, all lanes together
+                    float4* row = c.xf_cache + (size_t)i * c.sc.anim_stride;
+                    for (uint32_t k = 0; k < c.sc.num_anim; ++k)
+                    {
+                        const uint4 a = __ldg(c.sc.anim + k);
+                        xform_cache_store(row, a.y, a.z, xform_eval(c.sc, a.x, time));
+                    }
+                }
                 c.ray_od[2 * (size_t)i] = make_float4(o.x, o.y, o.z, time);
                 c.ray_od[2 * (size_t)i + 1] = make_float4(d.x, d.y, d.z, 0.0f);
                 c.thr[i] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(0u));
@@ -344,6 +363,9 @@ struct PathIO
     // hits are handed to the shading stage binned by shape; misses end the path here
     uint32_t* shade_items;
     uint32_t* shade_counts;
+    const float4* xf_cache;
+    uint32_t xf_stride;
+    __device__ __forceinline__ const float4* xf_row(uint32_t tag) const { return xf_cache ? xf_cache + (size_t)tag * xf_stride : nullptr; }
     __device__ __forceinline__ uint32_t count() const { return queue.total(); }
     __device__ __forceinline__ uint32_t tag_at(uint32_t j) const { return queue.at(j); }
     // the two 16-byte records of a ray and how they decode (used by the prefetching top-level pass)
@@ -373,6 +395,9 @@ struct MisIO
     const float4* pos_wo;        // hit position, time at [2 * tag]
     const float4* lrec;          // probe direction at [4 * tag + 2]
     float4* mis_hit0;
+    const float4* xf_cache;
+    uint32_t xf_stride;
+    __device__ __forceinline__ const float4* xf_row(uint32_t tag) const { return xf_cache ? xf_cache + (size_t)tag * xf_stride : nullptr; }
     __device__ __forceinline__ uint32_t count() const { return queue.total(); }
     __device__ __forceinline__ uint32_t tag_at(uint32_t j) const { return queue.at(j); }
     // the two 16-byte records of a ray and how they decode (used by the prefetching top-level pass)
@@ -399,6 +424,9 @@ struct ShadowIO
     BinQ<RT_QBINS> queue;
     const float4* pos_wo;        // hit position, time at [2 * tag]
     float4* lrec;                // shadow direction at [4 * tag + 0]; [4 * tag + 1].w = light sample still valid
+    const float4* xf_cache;
+    uint32_t xf_stride;
+    __device__ __forceinline__ const float4* xf_row(uint32_t tag) const { return xf_cache ? xf_cache + (size_t)tag * xf_stride : nullptr; }
     __device__ __forceinline__ uint32_t count() const { return queue.total(); }
     __device__ __forceinline__ uint32_t tag_at(uint32_t j) const { return queue.at(j); }
     // the two 16-byte records of a ray and how they decode (used by the prefetching top-level pass)
@@ -424,17 +452,18 @@ struct ShadowIO
 
 __host__ __device__ __forceinline__ PathIO make_path_io(const RenderCtx& c, int cur)
 {
-    PathIO io = { { c.q_path[cur], c.ctl + CTL_PATH(cur), c.qcap }, c.ray_od, c.hit01, c.q_shade, c.ctl + CTL_SHADE };
+    PathIO io = { { c.q_path[cur], c.ctl + CTL_PATH(cur), c.qcap }, c.ray_od, c.hit01, c.q_shade, c.ctl + CTL_SHADE,
+                  c.xf_cache, c.sc.anim_stride };
     return io;
 }
 __host__ __device__ __forceinline__ MisIO make_mis_io(const RenderCtx& c)
 {
-    MisIO io = { { c.q_mis, c.ctl + CTL_MIS, c.qcap }, c.pos_wo, c.lrec, c.mis_hit0 };
+    MisIO io = { { c.q_mis, c.ctl + CTL_MIS, c.qcap }, c.pos_wo, c.lrec, c.mis_hit0, c.xf_cache, c.sc.anim_stride };
     return io;
 }
 __host__ __device__ __forceinline__ ShadowIO make_shadow_io(const RenderCtx& c)
 {
-    ShadowIO io = { { c.q_shadow, c.ctl + CTL_SHADOW, c.qcap }, c.pos_wo, c.lrec };
+    ShadowIO io = { { c.q_shadow, c.ctl + CTL_SHADOW, c.qcap }, c.pos_wo, c.lrec, c.xf_cache, c.sc.anim_stride };
     return io;
 }
 
@@ -572,7 +601,7 @@ k_shade(const __grid_constant__ RenderCtx c, int cur, uint32_t bounce)
                     r0.inv = r0.d; r0.neg = 0;
                     V3 nrm;
                     float cmod;
-                    hit_shading_inputs(c.sc, r0, ro.w, h, nrm, cmod);
+                    hit_shading_inputs(c.sc, r0, ro.w, h, nrm, cmod, xf_row(c, i));
                     h1 = make_float4(nrm.x, nrm.y, nrm.z, cmod);
                     c.hit01[2 * (size_t)i + 1] = h1;
                 }
@@ -706,7 +735,7 @@ k_light_sample(const __grid_constant__ RenderCtx c, int cur, uint32_t bounce, ui
             float leu = cmj1d(idx, n1, perm_elem);
             V3 lpos, lnrm;
             float lpdf;
-            light_sample(c.sc, lsh, position, time, lsu, lsv, leu, lpos, lnrm, lpdf);
+            light_sample(c.sc, lsh, position, time, lsu, lsv, leu, lpos, lnrm, lpdf, xf_row(c, i));
 
             float4 shl = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             float4 shd = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -823,8 +852,8 @@ k_resolve(const __grid_constant__ RenderCtx c, uint32_t lsi)
                 r0.inv = r0.d; r0.neg = 0;
                 V3 hn;
                 float hcm;
-                hit_shading_inputs(c.sc, r0, pt.w, h, hn, hcm);
-                float lpdf = light_intersect_pdf(c.sc, lsh, xyz(pt), xyz(md), pt.w, mh0.x, hn);
+                hit_shading_inputs(c.sc, r0, pt.w, h, hn, hcm, xf_row(c, i));
+                float lpdf = light_intersect_pdf(c.sc, lsh, xyz(pt), xyz(md), pt.w, mh0.x, hn, xf_row(c, i));
                 if (lpdf > 0.0f)
                 {
                     float mis = power_heuristic(md.w, lpdf);
@@ -1027,7 +1056,7 @@ struct Carver
     }
 };
 
-inline size_t carve(RenderCtx& c, char* base, size_t samples, size_t pixels, uint32_t slots)
+inline size_t carve(RenderCtx& c, char* base, size_t samples, size_t pixels, uint32_t slots, uint32_t xf_stride)
 {
     Carver k = { base, 0 };
     c.pix_xy = k.take<uint32_t>(pixels);
@@ -1041,6 +1070,7 @@ inline size_t carve(RenderCtx& c, char* base, size_t samples, size_t pixels, uin
     c.lrec = k.take<float4>(samples * 4);
     c.mis_hit0 = k.take<float4>(samples);
     c.mis_hit1 = k.take<float4>(samples);
+    c.xf_cache = xf_stride ? k.take<float4>(samples * xf_stride) : NULL;
     c.qcap = (uint32_t)samples;
     c.q_path[0] = k.take<uint32_t>(samples * RT_QBINS);
     c.q_path[1] = k.take<uint32_t>(samples * RT_QBINS);
@@ -1132,7 +1162,7 @@ inline int rt_render_reserve(RtScene* s, RenderPlan& plan)
         rb->block = NULL;
         rb->cap_samples = rb->cap_pixels = 0;
         RenderCtx probe;
-        size_t bytes = rt_detail::carve(probe, NULL, samples, pixels, plan.slots);
+        size_t bytes = rt_detail::carve(probe, NULL, samples, pixels, plan.slots, s->d.anim_stride);
         size_t got_bytes = 0;
         // leave room for the rest of the process: shrink the batch until it fits in
         // at most 60 % of the free device memory, and on allocation failure
@@ -1153,14 +1183,14 @@ inline int rt_render_reserve(RtScene* s, RenderPlan& plan)
             plan.tiles_per_batch = (plan.tiles_per_batch + 1) / 2;
             pixels = (size_t)plan.tiles_per_batch * plan.tile * plan.tile;
             samples = pixels * plan.spp;
-            bytes = rt_detail::carve(probe, NULL, samples, pixels, plan.slots);
+            bytes = rt_detail::carve(probe, NULL, samples, pixels, plan.slots, s->d.anim_stride);
         }
         rb->block_bytes = got_bytes;
         rb->cap_samples = samples;
         rb->cap_pixels = pixels;
         rb->cap_perm_slots = plan.slots;
     }
-    rt_detail::carve(rb->ctx, static_cast<char*>(rb->block), rb->cap_samples, rb->cap_pixels, rb->cap_perm_slots);
+    rt_detail::carve(rb->ctx, static_cast<char*>(rb->block), rb->cap_samples, rb->cap_pixels, rb->cap_perm_slots, s->d.anim_stride);
     if (plan.tiles.size() > rb->cap_tiles)
     {
         rt_detail::pool_free(s->device, rb->d_tile_ids, rb->tile_bytes);

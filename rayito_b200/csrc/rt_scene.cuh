@@ -398,7 +398,7 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
     for (uint32_t i = 0; i < desc->num_xforms; ++i)
     {
         const RtXform& x = desc->xforms[i];
-        bool translate_only = true;
+        bool translate_only = true, unit_scale = true;
         for (uint32_t k = x.first_key; k < x.first_key + x.num_keys; ++k)
         {
             const float* r = desc->key_rotation + 4 * (size_t)k;
@@ -406,12 +406,46 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
             // +0 only: a -0 component would not behave like the keyless identity
             uint32_t bits[3];
             std::memcpy(bits, r + 1, 12);
-            if (!(r[0] == 1.0f && bits[0] == 0 && bits[1] == 0 && bits[2] == 0 &&
-                  sc3[0] == 1.0f && sc3[1] == 1.0f && sc3[2] == 1.0f))
+            const bool unit = sc3[0] == 1.0f && sc3[1] == 1.0f && sc3[2] == 1.0f;
+            if (!unit)
+                unit_scale = false;
+            if (!(r[0] == 1.0f && bits[0] == 0 && bits[1] == 0 && bits[2] == 0 && unit))
                 translate_only = false;
         }
         if (translate_only)
             xf_kind[i] = x.num_keys <= 1 ? RT_XF_STATIC : RT_XF_TRANSLATE;
+        else if (unit_scale)
+            xf_kind[i] = RT_XF_RIGID;
+    }
+    // Rows of the per-sample transform cache (rt_device.cuh): every transform with two or more keys,
+    // two- and three-float4 entries on 32-byte boundaries so that an entry is one or two DRAM sectors
+    std::vector<uint4> anim;
+    std::vector<uint32_t> xf_cache_slot(desc->num_xforms, 0u);      // row offset + 1
+    uint32_t anim_stride = 0;
+    if (desc->semantics == RT_SEMANTICS_STAGE7 && std::getenv("RAYITO_B200_NO_XFORM_CACHE") == NULL)
+    {
+        for (int pass = 0; pass < 2; ++pass)        // wide entries first (aligned), then the one-float4 translations
+            for (uint32_t i = 0; i < desc->num_xforms; ++i)
+            {
+                if (desc->xforms[i].num_keys < 2 || i == desc->set_xform)
+                    continue;
+                const bool narrow = xf_kind[i] == RT_XF_TRANSLATE;
+                if (narrow != (pass == 1))
+                    continue;
+                uint32_t width = narrow ? 1u : xf_kind[i] == RT_XF_RIGID ? 2u : 3u;
+                if (!narrow && (anim_stride & 1u))
+                    ++anim_stride;
+                anim.push_back(make_uint4(i, anim_stride, xf_kind[i], 0u));
+                xf_cache_slot[i] = anim_stride + 1u;
+                anim_stride += width;
+            }
+        anim_stride = (anim_stride + 1u) & ~1u;
+        if (anim_stride > RT_XF_CACHE_MAX_STRIDE)
+        {
+            anim.clear();
+            std::fill(xf_cache_slot.begin(), xf_cache_slot.end(), 0u);
+            anim_stride = 0;
+        }
     }
 
     std::vector<DShapeMem> shapes(num_shapes);
@@ -430,7 +464,7 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
             return rt_fail(RT_ERR_ARG, "shape light index out of range");
         DShapeMem d;
         std::memset(&d, 0, sizeof(d));
-        d.type_kind = s.type | (xf_kind[s.xform] << 8);
+        d.type_kind = s.type | (xf_kind[s.xform] << 8) | (xf_cache_slot[s.xform] << 16);
         d.geom = s.geom; d.xform = s.xform; d.material = s.material; d.light = s.light;
         if (xf_kind[s.xform] == RT_XF_STATIC && desc->xforms[s.xform].num_keys == 1)
         {
@@ -682,6 +716,7 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
     size_t o_mats = ab.put(desc->materials, (size_t)desc->num_materials * sizeof(RtMaterial));
     size_t o_lights = ab.put(desc->lights, (size_t)desc->num_lights * 4);
     size_t o_walk = ab.put(top_walk.data(), top_walk.size() * sizeof(DTopStep));
+    size_t o_anim = ab.put(anim.data(), anim.size() * sizeof(uint4));
 
     hc[2] = std::chrono::steady_clock::now();
     int ndev = 0;
@@ -881,6 +916,9 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
     d.lights = reinterpret_cast<const uint32_t*>(base + o_lights);
     d.top_walk = top_walk_steps ? reinterpret_cast<const DTopStep*>(base + o_walk) : NULL;
     d.top_walk_steps = top_walk_steps;
+    d.anim = reinterpret_cast<const uint4*>(base + o_anim);
+    d.num_anim = (uint32_t)anim.size();
+    d.anim_stride = anim_stride;
 
     *out_scene = sc;
     return RT_OK;

@@ -139,12 +139,12 @@ __device__ __forceinline__ float sphere_area_pdf(float radius)
 // set's own transform here either.
 __device__ RT_SHADE_CALL void light_sample(const DScene& sc, const DShape& sh, V3 ref_pos, float ref_time,
                                              float u1, float u2, float u3,
-                                             V3& out_pos, V3& out_normal, float& out_pdf)
+                                             V3& out_pos, V3& out_normal, float& out_pdf, const float4* row = nullptr)
 {
     out_pdf = 0.0f;
     out_pos = mk(0.0f, 0.0f, 0.0f);
     out_normal = mk(0.0f, 0.0f, 0.0f);
-    TRS trs = shape_xform(sc, sh, ref_time);
+    TRS trs = shape_xform(sc, sh, ref_time, row);
     if (sh.type == RT_SHAPE_RECT)
     {
         // RLight.h:186-218
@@ -273,9 +273,9 @@ __device__ RT_SHADE_CALL void light_sample(const DScene& sc, const DShape& sh, V
 // Light::intersectPdf for a BRDF-sampled ray that hit the light (RLight.h:220-239,
 // 317-328).  ray_o/ray_d/time describe the probe ray, t/normal its hit.
 __device__ RT_SHADE_CALL float light_intersect_pdf(const DScene& sc, const DShape& sh, V3 ray_o, V3 ray_d, float time,
-                                                     float t, V3 hit_normal)
+                                                     float t, V3 hit_normal, const float4* row = nullptr)
 {
-    TRS trs = shape_xform(sc, sh, time);
+    TRS trs = shape_xform(sc, sh, time, row);
     if (sh.type == RT_SHAPE_RECT)
     {
         DRect rc = sc.rects[sh.geom];

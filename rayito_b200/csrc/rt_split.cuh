@@ -161,7 +161,7 @@ __device__ __forceinline__ void trace_top(const DScene& sc, const IO& io, const 
                     {
                         uint32_t sid = sc.num_finite + k;
                         DShape sh = load_shape(sc, sid);
-                        TRS trs = shape_xform(sc, sh, time);
+                        TRS trs = shape_xform(sc, sh, time, io.xf_row(tag));
                         V3 lo = to_local_point(trs, r0.o);
                         V3 ld = to_local_vector(trs, r0.d);
                         count_xform<COUNT>(sc, sh.xform, wc);
@@ -290,7 +290,7 @@ __device__ __forceinline__ void trace_top(const DScene& sc, const IO& io, const 
                 DMesh m = sc.meshes[sh.geom];
                 if (m.num_nodes > 0)
                 {
-                    TRS trs = shape_xform(sc, sh, time);
+                    TRS trs = shape_xform(sc, sh, time, io.xf_row(tag));
                     count_xform<COUNT>(sc, sh.xform, wc);
                     LocalRay rm;
                     rm.o = to_local_point(trs, r0.o);
@@ -317,7 +317,7 @@ __device__ __forceinline__ void trace_top(const DScene& sc, const IO& io, const 
             }
             else
             {
-                TRS trs = shape_xform(sc, sh, time);
+                TRS trs = shape_xform(sc, sh, time, io.xf_row(tag));
                 count_xform<COUNT>(sc, sh.xform, wc);
                 V3 lo = to_local_point(trs, r0.o);
                 V3 ld = to_local_vector(trs, r0.d);
@@ -491,7 +491,7 @@ __device__ __forceinline__ void trace_top_static(const DScene& sc, const IO& io,
             {
                 uint32_t sid = sc.num_finite + k;
                 DShape sh = load_shape(sc, sid);
-                TRS trs = shape_xform(sc, sh, time);
+                TRS trs = shape_xform(sc, sh, time, io.xf_row(tag));
                 V3 lo = to_local_point(trs, r0.o);
                 V3 ld = to_local_vector(trs, r0.d);
                 count_xform<COUNT>(sc, sh.xform, wc);
@@ -579,7 +579,7 @@ __device__ __forceinline__ void trace_top_static(const DScene& sc, const IO& io,
                     DMesh m = sc.meshes[sh.geom];
                     if (here && m.num_nodes > 0)
                     {
-                        TRS trs = shape_xform(sc, sh, time);
+                        TRS trs = shape_xform(sc, sh, time, io.xf_row(tag));
                         count_xform<COUNT>(sc, sh.xform, wc);
                         LocalRay rm;
                         rm.o = to_local_point(trs, r0.o);
@@ -634,7 +634,7 @@ __device__ __forceinline__ void trace_top_static(const DScene& sc, const IO& io,
                 }
                 else if (here)
                 {
-                    TRS trs = shape_xform(sc, sh, time);
+                    TRS trs = shape_xform(sc, sh, time, io.xf_row(tag));
                     count_xform<COUNT>(sc, sh.xform, wc);
                     V3 lo = to_local_point(trs, r0.o);
                     V3 ld = to_local_vector(trs, r0.d);
@@ -674,10 +674,11 @@ __device__ __forceinline__ void trace_top_static(const DScene& sc, const IO& io,
                         }
                     }
                 }
-                if (sh.type == RT_SHAPE_MESH)
-                    warp_queue_push(ps.out_queue, ps.out_count, suspend, tag);
+                (void)suspend;
             }
         }
+        // rays that entered a mesh: one queue append per chunk (a lane suspends at most once per walk)
+        warp_queue_push(ps.out_queue, ps.out_count, suspended, tag);
         if (live && !suspended)
             io.store(tag, res);
 #if RT_STATIC_PREFETCH
@@ -1218,13 +1219,13 @@ __device__ __forceinline__ void trace_mesh_pair(const DScene& sc, const IO& io, 
                 bool keep = A <= B;
                 if (!ANY && t0 >= best)
                     keep = false;
-                if (keep)
+                // (when counting work every far child is pushed, so that its pop is counted exactly when the
+                // reference pops it -- an any-hit ray may stop before; the pop's own checks then drop it)
+                if (keep || COUNT)
                 {
                     RT_PAIR_PUT(sp, make_float4(__uint_as_float(far_word | ((far_flags & RT_NODE_AXIS) << 29)), t0, A, B));
                     ++sp;
                 }
-                else if (COUNT)
-                    wc.node_pops++;         // the reference pops it (and drops it) later: same count
             }
 
             // near child: popped at once

@@ -91,7 +91,7 @@ __device__ __forceinline__ DShape load_shape(const DScene& sc, uint32_t i)
     const uint4* p = reinterpret_cast<const uint4*>(sc.shapes + i);
     uint4 a = __ldg(p);
     uint4 b = __ldg(p + 1);
-    s.type = a.x & 0xffu; s.xkind = (a.x >> 8) & 0x3u;
+    s.type = a.x & 0xffu; s.xkind = (a.x >> 8) & 0x3u; s.cache_slot = a.x >> 16;
     s.geom = a.y; s.xform = a.z; s.material = a.w;
     s.light = (int32_t)b.x;
     s.tx = __uint_as_float(b.y); s.ty = __uint_as_float(b.z); s.tz = __uint_as_float(b.w);
@@ -100,8 +100,11 @@ __device__ __forceinline__ DShape load_shape(const DScene& sc, uint32_t i)
 
 // The shape's transform at `time`.  STATIC transforms come straight from the shape
 // record (no key loads, no search); the rest go through xform_eval.
-__device__ __forceinline__ TRS shape_xform(const DScene& sc, const DShape& sh, float time)
+// `row`: this sample's row of the per-sample transform cache, or NULL (ray-batch entry points).
+__device__ __forceinline__ TRS shape_xform(const DScene& sc, const DShape& sh, float time, const float4* row = nullptr)
 {
+    if (row != nullptr && sh.cache_slot != 0u)
+        return xform_cache_load(row, sh.cache_slot - 1u, sh.xkind, sc.stage6 != 0);
     if (sh.xkind == RT_XF_STATIC)
     {
         TRS r;
@@ -134,14 +137,15 @@ __device__ __forceinline__ void count_xform(const DScene& sc, uint32_t xform, Wo
 // arithmetic per shape is the reference's (RScene.h:321-328, 457-463;
 // RLight.h:107-113; RMesh.h:305-333, 70-71; RScene.h:152-153).
 __device__ __forceinline__ void hit_shading_inputs(const DScene& sc, const LocalRay& r0, float time,
-                                                   const ClosestHit& hit, V3& normal, float& color_mod)
+                                                   const ClosestHit& hit, V3& normal, float& color_mod,
+                                                   const float4* row = nullptr)
 {
     normal = mk(0.0f, 0.0f, 0.0f);
     color_mod = 1.0f;
     if (hit.shape < 0)
         return;
     DShape sh = load_shape(sc, (uint32_t)hit.shape);
-    TRS trs = shape_xform(sc, sh, time);
+    TRS trs = shape_xform(sc, sh, time, row);
     V3 lo = to_local_point(trs, r0.o);
     V3 ld = to_local_vector(trs, r0.d);
     V3 n;

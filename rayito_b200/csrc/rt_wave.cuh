@@ -49,6 +49,7 @@ struct WaveResult
 // IO policy contract:
 //   bool  load(uint32_t j, V3& o, V3& d, float& tmax, float& time, uint32_t& tag)
 //   void  store(uint32_t tag, const WaveResult& r)
+//   const float4* xf_row(uint32_t tag)      the ray's row of the per-sample transform cache, or NULL
 template <int CAP, bool ANY, bool COUNT, class IO>
 __device__ __forceinline__ void trace_wave(const DScene& sc, const IO& io, uint32_t n, uint32_t* cursor, WorkCount& wc)
 {
@@ -114,7 +115,7 @@ __device__ __forceinline__ void trace_wave(const DScene& sc, const IO& io, uint3
                     {
                         uint32_t sid = sc.num_finite + k;
                         DShape sh = load_shape(sc, sid);
-                        TRS trs = shape_xform(sc, sh, time);
+                        TRS trs = shape_xform(sc, sh, time, io.xf_row(tag));
                         V3 lo = to_local_point(trs, r0.o);
                         V3 ld = to_local_vector(trs, r0.d);
                         count_xform<COUNT>(sc, sh.xform, wc);
@@ -245,7 +246,7 @@ __device__ __forceinline__ void trace_wave(const DScene& sc, const IO& io, uint3
         if (do_shape && parked == PARK_SHAPE)
         {
             DShape sh = load_shape(sc, park_word);
-            TRS trs = shape_xform(sc, sh, time);
+            TRS trs = shape_xform(sc, sh, time, io.xf_row(tag));
             count_xform<COUNT>(sc, sh.xform, wc);
             V3 lo = to_local_point(trs, r0.o);
             V3 ld = to_local_vector(trs, r0.d);

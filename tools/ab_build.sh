@@ -11,7 +11,7 @@ for r in $(seq 1 $rounds); do
   i=0
   for cfg in "$@"; do
     cp /tmp/librt_$i.so rayito_b200/csrc/librayito_b200.so
-    python bench.py --workload ${WORKLOAD:-c4-1080p} --steps 2 --warmup 2 --no-e2e --no-cpu-baseline 2>/dev/null | \
+    python bench.py --workload ${WORKLOAD:-c4-1080p} --steps 2 --warmup 2 --no-e2e --no-cpu-baseline --no-also 2>/dev/null | \
       python -c "import json,sys; d=json.loads(sys.stdin.read()); r=d['roofline']; print('[$cfg]', 'Mrays/s %.0f' % d['value'], 'trace %.0f' % r['trace_mrays_per_s_per_gpu'], 'share %.2f' % r['trace_share_of_step'])"
     i=$((i+1))
   done

@@ -5,7 +5,7 @@
 rounds=$1; shift
 for r in $(seq 1 $rounds); do
   for cfg in "$@"; do
-    env $cfg python bench.py --workload ${WORKLOAD:-c4-1080p} --steps ${STEPS:-2} --warmup ${WARMUP:-2} --no-e2e --no-cpu-baseline 2>/dev/null | \
+    env $cfg python bench.py --workload ${WORKLOAD:-c4-1080p} --steps ${STEPS:-2} --warmup ${WARMUP:-2} --no-e2e --no-cpu-baseline --no-also 2>/dev/null | \
       python -c "import json,sys; d=json.loads(sys.stdin.read()); r=d['roofline']; print('[$cfg]', 'Mrays/s %.0f' % d['value'], 'trace %.0f' % r['trace_mrays_per_s_per_gpu'], 'share %.2f' % r['trace_share_of_step'], 'frac %.3f' % r['frac'])"
   done
 done
