@@ -422,7 +422,11 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
     std::vector<uint4> anim;
     std::vector<uint32_t> xf_cache_slot(desc->num_xforms, 0u);      // row offset + 1
     uint32_t anim_stride = 0;
-    if (desc->semantics == RT_SEMANTICS_STAGE7 && std::getenv("RAYITO_B200_NO_XFORM_CACHE") == NULL)
+    // RAYITO_B200_XFORM_CACHE = none | rotations (default) | all  (A/B runs).  Interpolated translations are cheap
+    // to re-evaluate (a key search and three lerps); interpolated rotations are not.
+    const char* cache_env = std::getenv("RAYITO_B200_XFORM_CACHE");
+    const int cache_mode = cache_env == NULL ? 1 : cache_env[0] == 'n' ? 0 : cache_env[0] == 'a' ? 2 : 1;
+    if (desc->semantics == RT_SEMANTICS_STAGE7 && cache_mode != 0)
     {
         for (int pass = 0; pass < 2; ++pass)        // wide entries first (aligned), then the one-float4 translations
             for (uint32_t i = 0; i < desc->num_xforms; ++i)
@@ -430,7 +434,7 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
                 if (desc->xforms[i].num_keys < 2 || i == desc->set_xform)
                     continue;
                 const bool narrow = xf_kind[i] == RT_XF_TRANSLATE;
-                if (narrow != (pass == 1))
+                if (narrow != (pass == 1) || (narrow && cache_mode != 2))
                     continue;
                 uint32_t width = narrow ? 1u : xf_kind[i] == RT_XF_RIGID ? 2u : 3u;
                 if (!narrow && (anim_stride & 1u))

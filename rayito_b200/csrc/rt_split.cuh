@@ -1024,6 +1024,9 @@ __device__ __forceinline__ void trace_mesh(const DScene& sc, const IO& io, const
 #ifndef RT_PAIR_ADVANCE_STEPS
 #define RT_PAIR_ADVANCE_STEPS 3
 #endif
+#ifndef RT_PAIR_TWO_LEAF
+#define RT_PAIR_TWO_LEAF 1      /* park on both leaves of a two-leaf pair at once */
+#endif
 #define RT_PAIR_LEAF 0x80000000u
 #define RT_PAIR_MAX_NODES (1u << 29)      /* pair index and split axis share a word */
 
@@ -1072,6 +1075,7 @@ __device__ __forceinline__ void trace_mesh_pair(const DScene& sc, const IO& io, 
     float cur_t0 = 0.0f, cur_t1 = 0.0f;
     bool parked = false;
     uint32_t park_word = 0, park_count = 0;
+    uint32_t park2_word = 0, park2_count = 0;   // a second leaf to test right after the first (both children leaves)
 
 #define RT_PAIR_PUT(slot, v_)                                                           \
     { if ((slot) < kSmemStack) sm_stack[(slot) * RT_BLOCK + threadIdx.x] = (v_);        \
@@ -1098,6 +1102,7 @@ __device__ __forceinline__ void trace_mesh_pair(const DScene& sc, const IO& io, 
                 active = true;
                 parked = false;
                 have_cur = false;
+                park2_count = 0;
                 tag = ps.in_queue[j];
                 float4 b = sb.ray_d[tag], h = sb.hit[tag];
                 tmax = b.w;
@@ -1205,6 +1210,19 @@ __device__ __forceinline__ void trace_mesh_pair(const DScene& sc, const IO& io, 
             const uint32_t far_word = __float_as_uint(neg ? b1.z : a1.z), far_flags = __float_as_uint(neg ? b1.w : a1.w);
             const float t0 = cur_t0, t1 = cur_t1;
 
+            // Both children leaves (the bottom of the tree): the reference tests the near leaf's
+            // triangles, pops the far leaf next (a leaf is never culled) and tests its triangles.
+            // Park on both at once: one triangle phase, no stack traffic.
+            if (RT_PAIR_TWO_LEAF && (far_flags & near_flags & RT_NODE_LEAF) != 0u)
+            {
+                if (COUNT) wc.node_pops++;
+                parked = true;
+                park_word = near_word;
+                park_count = near_flags >> 3;
+                park2_word = far_word;
+                park2_count = far_flags >> 3;
+                break;
+            }
             // far child: pushed first (popped after everything below the near child)
             if (far_flags & RT_NODE_LEAF)
             {
@@ -1257,20 +1275,31 @@ __device__ __forceinline__ void trace_mesh_pair(const DScene& sc, const IO& io, 
 
         if (do_tri && parked)
         {
-            for (uint32_t k = 0; k < park_count; ++k)
+            #pragma unroll 1
+            for (int leaf = 0; leaf < 2; ++leaf)
             {
-                V3 p0, p1, p2;
-                uint32_t w0, w1, w2;
-                load_tri(sc, park_word + k, p0, p1, p2, w0, w1, w2);
-                if (COUNT) wc.tri_tests++;
-                float t, beta, gamma;
-                if (tri_closest(r1.o, r1.d, p0, p1, p2, ANY ? tmax : best, t, beta, gamma))
+                for (uint32_t k = 0; k < park_count; ++k)
                 {
-                    if (ANY) { any_hit = true; sp = 0; have_cur = false; break; }
-                    best = t;
-                    best_rec = (int32_t)(park_word + k);
-                    if (sc.stage6) break;        // S6 RMesh.h:204-209
+                    V3 p0, p1, p2;
+                    uint32_t w0, w1, w2;
+                    load_tri(sc, park_word + k, p0, p1, p2, w0, w1, w2);
+                    if (COUNT) wc.tri_tests++;
+                    float t, beta, gamma;
+                    if (tri_closest(r1.o, r1.d, p0, p1, p2, ANY ? tmax : best, t, beta, gamma))
+                    {
+                        if (ANY) { any_hit = true; sp = 0; have_cur = false; park2_count = 0; break; }
+                        best = t;
+                        best_rec = (int32_t)(park_word + k);
+                        if (sc.stage6) break;        // S6 RMesh.h:204-209
+                    }
                 }
+                if (park2_count == 0)
+                    break;
+                // the far leaf of a two-leaf pair: popped now
+                if (COUNT) wc.node_pops++;
+                park_word = park2_word;
+                park_count = park2_count;
+                park2_count = 0;
             }
             parked = false;
         }
