@@ -375,10 +375,14 @@ struct PathIO
     {
         o = xyz(a); d = xyz(b); tmax = RT_RAY_TMAX; time = a.w;
     }
+    __device__ __forceinline__ void load_tag(uint32_t tag, V3& o, V3& d, float& tmax, float& time) const
+    {
+        decode(ray_od[2 * (size_t)tag], ray_od[2 * (size_t)tag + 1], o, d, tmax, time);
+    }
     __device__ __forceinline__ bool load(uint32_t j, V3& o, V3& d, float& tmax, float& time, uint32_t& tag) const
     {
         tag = queue.at(j);
-        decode(ray_od[2 * (size_t)tag], ray_od[2 * (size_t)tag + 1], o, d, tmax, time);
+        load_tag(tag, o, d, tmax, time);
         return true;
     }
     __device__ __forceinline__ void store(uint32_t tag, const WaveResult& r) const
@@ -407,10 +411,14 @@ struct MisIO
     {
         o = xyz(a); d = xyz(b); tmax = RT_RAY_TMAX; time = a.w;
     }
+    __device__ __forceinline__ void load_tag(uint32_t tag, V3& o, V3& d, float& tmax, float& time) const
+    {
+        decode(pos_wo[2 * (size_t)tag], lrec[4 * (size_t)tag + 2], o, d, tmax, time);
+    }
     __device__ __forceinline__ bool load(uint32_t j, V3& o, V3& d, float& tmax, float& time, uint32_t& tag) const
     {
         tag = queue.at(j);
-        decode(pos_wo[2 * (size_t)tag], lrec[4 * (size_t)tag + 2], o, d, tmax, time);
+        load_tag(tag, o, d, tmax, time);
         return true;
     }
     __device__ __forceinline__ void store(uint32_t tag, const WaveResult& r) const
@@ -436,10 +444,14 @@ struct ShadowIO
     {
         o = xyz(a); d = xyz(b); tmax = b.w; time = a.w;
     }
+    __device__ __forceinline__ void load_tag(uint32_t tag, V3& o, V3& d, float& tmax, float& time) const
+    {
+        decode(pos_wo[2 * (size_t)tag], lrec[4 * (size_t)tag], o, d, tmax, time);
+    }
     __device__ __forceinline__ bool load(uint32_t j, V3& o, V3& d, float& tmax, float& time, uint32_t& tag) const
     {
         tag = queue.at(j);
-        decode(pos_wo[2 * (size_t)tag], lrec[4 * (size_t)tag], o, d, tmax, time);
+        load_tag(tag, o, d, tmax, time);
         return true;
     }
     // an occluded light sample is cancelled in place (the record k_resolve reads anyway)
@@ -1082,8 +1094,6 @@ inline size_t carve(RenderCtx& c, char* base, size_t samples, size_t pixels, uin
     c.q_meshq[1] = k.take<uint32_t>(samples);
     c.q_resume[0] = k.take<uint32_t>(samples);
     c.q_resume[1] = k.take<uint32_t>(samples);
-    c.split.ray_o = k.take<float4>(samples);
-    c.split.ray_d = k.take<float4>(samples);
     c.split.hit = k.take<float4>(samples);
     c.split.stack = k.take<float4>(samples * RT_SPLIT_TOPCAP);
     c.split.mesh_o = k.take<float4>(samples);

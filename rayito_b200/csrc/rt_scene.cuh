@@ -422,11 +422,39 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
     std::vector<uint4> anim;
     std::vector<uint32_t> xf_cache_slot(desc->num_xforms, 0u);      // row offset + 1
     uint32_t anim_stride = 0;
-    // RAYITO_B200_XFORM_CACHE = none | rotations (default) | all  (A/B runs).  Interpolated translations are cheap
-    // to re-evaluate (a key search and three lerps); interpolated rotations are not.
+    // Which transforms are worth a cache entry (same-session A/Bs, profiles/README.md round 2):
+    //   * interpolated ROTATIONS only -- an interpolated translation is a key search and three lerps, cheaper to
+    //     redo than to fetch (C4: rotations +2.5 %, everything +1.6 %);
+    //   * only shapes that are SMALL in the scene (top-level box under a quarter of the root box's area): a shape
+    //     that fills the scene is entered by most rays of a warp, so its in-place evaluation already runs with the
+    //     warp converged and the cache only adds memory traffic (the 10 M-triangle mesh of C5: -2 %);
+    //   * at most four of them: every entry is evaluated for every sample whether a ray of that sample meets the
+    //     shape or not (scene 2, twenty animated shapes, everything cached: -20 %).
+    // RAYITO_B200_XFORM_CACHE = none | auto (default) | rotations | all overrides the choice (A/B runs).
     const char* cache_env = std::getenv("RAYITO_B200_XFORM_CACHE");
-    const int cache_mode = cache_env == NULL ? 1 : cache_env[0] == 'n' ? 0 : cache_env[0] == 'a' ? 2 : 1;
-    if (desc->semantics == RT_SEMANTICS_STAGE7 && cache_mode != 0)
+    const int cache_mode = cache_env == NULL ? 3 : cache_env[0] == 'n' ? 0 : cache_env[0] == 'r' ? 1 : cache_env[0] == 'a' && cache_env[1] == 'l' ? 2 : 3;
+    std::vector<float> xf_area_ratio(desc->num_xforms, 0.0f);      // largest top-level box of a shape using the transform / root box
+    if (cache_mode == 3 && desc->num_top_nodes > 0)
+    {
+        auto half_area = [](const RtBvhNode& n) {
+            float dx = n.bbox_max[0] - n.bbox_min[0], dy = n.bbox_max[1] - n.bbox_min[1], dz = n.bbox_max[2] - n.bbox_min[2];
+            return dx * dy + dy * dz + dz * dx;
+        };
+        const float root = half_area(desc->top_nodes[0]);
+        for (uint32_t i = 0; i < desc->num_top_nodes; ++i)
+        {
+            const RtBvhNode& n = desc->top_nodes[i];
+            if (!(n.flags & RT_NODE_LEAF) || n.first_child_or_prim >= desc->num_finite)
+                continue;
+            const uint32_t xf = desc->shapes[n.first_child_or_prim].xform;
+            if (xf >= desc->num_xforms)
+                continue;           // (reported below)
+            const float ratio = root > 0.0f ? half_area(n) / root : 1.0f;
+            if (ratio > xf_area_ratio[xf]) xf_area_ratio[xf] = ratio;
+        }
+    }
+    uint32_t cached_entries = 0;
+    if (desc->semantics == RT_SEMANTICS_STAGE7 && cache_mode != 0 && !(cache_mode == 3 && desc->num_top_nodes == 0))
     {
         for (int pass = 0; pass < 2; ++pass)        // wide entries first (aligned), then the one-float4 translations
             for (uint32_t i = 0; i < desc->num_xforms; ++i)
@@ -436,6 +464,9 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
                 const bool narrow = xf_kind[i] == RT_XF_TRANSLATE;
                 if (narrow != (pass == 1) || (narrow && cache_mode != 2))
                     continue;
+                if (cache_mode == 3 && (xf_area_ratio[i] <= 0.0f || xf_area_ratio[i] >= 0.25f || cached_entries >= 4))
+                    continue;
+                ++cached_entries;
                 uint32_t width = narrow ? 1u : xf_kind[i] == RT_XF_RIGID ? 2u : 3u;
                 if (!narrow && (anim_stride & 1u))
                     ++anim_stride;

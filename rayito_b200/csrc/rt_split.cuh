@@ -51,15 +51,15 @@
 #define RT_SPLIT_TOPCAP 8        /* top-level stack entries a suspended ray can carry */
 #define RT_SPLIT_MAX_MESHES 12   /* more mesh shapes than this: use the unified kernel */
 
-// Per-slot suspended-ray state (slot = path sample index / ray index)
+// Per-slot suspended-ray state (slot = path sample index / ray index).  Kept small: every word is
+// written and read back through scattered 16-byte accesses.  The set-local ray itself is NOT saved:
+// a resume pass recomputes it from the stage's own ray record (same inputs, same bits).
 struct SplitBufs
 {
-    float4* ray_o;      // set-local origin xyz, time
-    float4* ray_d;      // set-local direction xyz, tMax
     float4* hit;        // m_t, winner shape, winner triangle record, (mesh shape to enter | sp << 24)
     float4* stack;      // RT_SPLIT_TOPCAP entries per slot: node, t0, t1, -
-    float4* mesh_o;     // mesh-local origin xyz (computed by the top pass at mesh entry)
-    float4* mesh_d;     // mesh-local direction xyz
+    float4* mesh_o;     // mesh-local origin xyz (computed by the top pass at mesh entry), m_t (closest hit) or tMax (any hit)
+    float4* mesh_d;     // mesh-local direction xyz, mesh shape to enter
 };
 
 // One pass: where the work comes from, where suspended / resumed slots go, and
@@ -197,11 +197,17 @@ __device__ __forceinline__ void trace_top(const DScene& sc, const IO& io, const 
                 }
                 else
                 {
-                    // resume a suspended ray: the mesh pass has updated m_t / the winner
+                    // resume a suspended ray: the mesh pass has updated m_t / the winner; the set-local ray is
+                    // recomputed from the stage's ray record exactly as the fresh pass computed it
                     tag = ps.in_queue[j];
-                    float4 a = sb.ray_o[tag], b = sb.ray_d[tag], h = sb.hit[tag];
-                    r0.o = xyz4(a); time = a.w;
-                    r0.d = xyz4(b); tmax = b.w;
+                    float4 h = sb.hit[tag];
+                    {
+                        V3 o, d;
+                        io.load_tag(tag, o, d, tmax, time);
+                        TRS set_trs = xform_eval(sc, sc.set_xform, time);
+                        r0.o = to_local_point(set_trs, o);
+                        r0.d = to_local_vector(set_trs, d);
+                    }
                     local_ray_finish(r0);
                     res.t = h.x;
                     res.shape = __float_as_int(h.y);
@@ -310,8 +316,8 @@ __device__ __forceinline__ void trace_top(const DScene& sc, const IO& io, const 
                     if (enter)
                     {
                         suspend = true;
-                        sb.mesh_o[tag] = make_float4(rm.o.x, rm.o.y, rm.o.z, 0.0f);
-                        sb.mesh_d[tag] = make_float4(rm.d.x, rm.d.y, rm.d.z, 0.0f);
+                        sb.mesh_o[tag] = make_float4(rm.o.x, rm.o.y, rm.o.z, ANY ? tmax : res.t);
+                        sb.mesh_d[tag] = make_float4(rm.d.x, rm.d.y, rm.d.z, __uint_as_float(park_shape));
                     }
                 }
             }
@@ -363,8 +369,6 @@ __device__ __forceinline__ void trace_top(const DScene& sc, const IO& io, const 
         {
             if (suspend)
             {
-                sb.ray_o[tag] = make_float4(r0.o.x, r0.o.y, r0.o.z, time);
-                sb.ray_d[tag] = make_float4(r0.d.x, r0.d.y, r0.d.z, tmax);
                 sb.hit[tag] = make_float4(res.t, __int_as_float(res.shape), __int_as_float(res.tri_rec),
                                           __uint_as_float(park_shape | ((uint32_t)sp << 24)));
                 float4* st = sb.stack + (size_t)tag * RT_SPLIT_TOPCAP;
@@ -599,8 +603,8 @@ __device__ __forceinline__ void trace_top_static(const DScene& sc, const IO& io,
                         if (enter)
                         {
                             suspend = true;
-                            sb.mesh_o[tag] = make_float4(rm.o.x, rm.o.y, rm.o.z, 0.0f);
-                            sb.mesh_d[tag] = make_float4(rm.d.x, rm.d.y, rm.d.z, 0.0f);
+                            sb.mesh_o[tag] = make_float4(rm.o.x, rm.o.y, rm.o.z, ANY ? tmax : res.t);
+                            sb.mesh_d[tag] = make_float4(rm.d.x, rm.d.y, rm.d.z, __uint_as_float(shape_id));
                             // the explicit stack of the dynamic pass at this point: pending far
                             // children whose parents passed, with the ranges those parents pushed
                             const uint4 p0 = __ldg(reinterpret_cast<const uint4*>(steps + s) + 1);
@@ -623,8 +627,6 @@ __device__ __forceinline__ void trace_top_static(const DScene& sc, const IO& io,
                                     }
                                 }
                             }
-                            sb.ray_o[tag] = make_float4(r0.o.x, r0.o.y, r0.o.z, time);
-                            sb.ray_d[tag] = make_float4(r0.d.x, r0.d.y, r0.d.z, tmax);
                             sb.hit[tag] = make_float4(res.t, __int_as_float(res.shape), __int_as_float(res.tri_rec),
                                                       __uint_as_float(shape_id | (sp << 24)));
                             open = false;
@@ -790,19 +792,18 @@ __device__ __forceinline__ void trace_mesh(const DScene& sc, const IO& io, const
                 have_cur = false;
                 top_valid = false;
                 tag = ps.in_queue[j];
-                float4 a = sb.ray_o[tag], b = sb.ray_d[tag], h = sb.hit[tag];
-                tmax = b.w;
-                best = h.x;
+                float4 mo = sb.mesh_o[tag], md = sb.mesh_d[tag];
+                tmax = mo.w;            // (any hit)
+                best = mo.w;            // (closest hit)
                 best_rec = -1;
                 any_hit = false;
-                meta = __float_as_uint(h.w);
+                meta = __float_as_uint(md.w);
                 mesh_shape = meta & 0xffffffu;
                 DShape sh = load_shape(sc, mesh_shape);
                 DMesh m = sc.meshes[sh.geom];
                 // the top pass already warped the ray into mesh-local space and found
                 // that it enters the root; redo the root's slab test (same inputs, same
                 // bits) only to get the clipped range its children inherit
-                float4 mo = sb.mesh_o[tag], md = sb.mesh_d[tag];
                 r1.o = xyz4(mo);
                 r1.d = xyz4(md);
                 local_ray_finish(r1);
@@ -832,7 +833,6 @@ __device__ __forceinline__ void trace_mesh(const DScene& sc, const IO& io, const
                     cur_node = neg ? rword : rword + 1; cur_t0 = t0; cur_t1 = t1;
                     have_cur = true;
                 }
-                (void)a; (void)b;
             }
         }
         if (__ballot_sync(0xffffffffu, active) == 0)
@@ -969,8 +969,10 @@ __device__ __forceinline__ void trace_mesh(const DScene& sc, const IO& io, const
                 {
                     if (best_rec >= 0)
                     {
-                        float4 h = sb.hit[tag];
-                        sb.hit[tag] = make_float4(best, __int_as_float((int32_t)mesh_shape), __int_as_float(best_rec), h.w);
+                        // (t, shape, triangle record); the fourth word (mesh shape | sp) stays as the top pass wrote it
+                        float* h = reinterpret_cast<float*>(sb.hit + tag);
+                        *reinterpret_cast<float2*>(h) = make_float2(best, __int_as_float((int32_t)mesh_shape));
+                        h[2] = __int_as_float(best_rec);
                     }
                     resume = true;
                 }
@@ -1025,7 +1027,10 @@ __device__ __forceinline__ void trace_mesh(const DScene& sc, const IO& io, const
 #define RT_PAIR_ADVANCE_STEPS 3
 #endif
 #ifndef RT_PAIR_TWO_LEAF
-#define RT_PAIR_TWO_LEAF 1      /* park on both leaves of a two-leaf pair at once */
+#define RT_PAIR_TWO_LEAF 0      /* 1: park on both leaves of a two-leaf pair at once (same-session A/B: C5 -2 %, C4 +-0) */
+#endif
+#ifndef RT_PAIR_PREFETCH_FAR
+#define RT_PAIR_PREFETCH_FAR 0  /* 1: L2 prefetch of a far child's own pair when it is pushed */
 #endif
 #define RT_PAIR_LEAF 0x80000000u
 #define RT_PAIR_MAX_NODES (1u << 29)      /* pair index and split axis share a word */
@@ -1104,18 +1109,17 @@ __device__ __forceinline__ void trace_mesh_pair(const DScene& sc, const IO& io, 
                 have_cur = false;
                 park2_count = 0;
                 tag = ps.in_queue[j];
-                float4 b = sb.ray_d[tag], h = sb.hit[tag];
-                tmax = b.w;
-                best = h.x;
+                float4 mo = sb.mesh_o[tag], md = sb.mesh_d[tag];
+                tmax = mo.w;            // (any hit)
+                best = mo.w;            // (closest hit)
                 best_rec = -1;
                 any_hit = false;
-                mesh_shape = __float_as_uint(h.w) & 0xffffffu;
+                mesh_shape = __float_as_uint(md.w) & 0xffffffu;
                 DShape sh = load_shape(sc, mesh_shape);
                 DMesh m = sc.meshes[sh.geom];
                 // the top pass already warped the ray into mesh-local space and found that it enters
                 // the root; redo the root's slab test (same inputs, same bits) only to get the clipped
                 // range its children inherit
-                float4 mo = sb.mesh_o[tag], md = sb.mesh_d[tag];
                 r1.o = xyz4(mo);
                 r1.d = xyz4(md);
                 local_ray_finish(r1);
@@ -1243,6 +1247,9 @@ __device__ __forceinline__ void trace_mesh_pair(const DScene& sc, const IO& io, 
                 {
                     RT_PAIR_PUT(sp, make_float4(__uint_as_float(far_word | ((far_flags & RT_NODE_AXIS) << 29)), t0, A, B));
                     ++sp;
+#if RT_PAIR_PREFETCH_FAR
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(mesh_nodes + far_word));
+#endif
                 }
             }
 
@@ -1321,8 +1328,10 @@ __device__ __forceinline__ void trace_mesh_pair(const DScene& sc, const IO& io, 
                 {
                     if (best_rec >= 0)
                     {
-                        float4 h = sb.hit[tag];
-                        sb.hit[tag] = make_float4(best, __int_as_float((int32_t)mesh_shape), __int_as_float(best_rec), h.w);
+                        // (t, shape, triangle record); the fourth word (mesh shape | sp) stays as the top pass wrote it
+                        float* h = reinterpret_cast<float*>(sb.hit + tag);
+                        *reinterpret_cast<float2*>(h) = make_float2(best, __int_as_float((int32_t)mesh_shape));
+                        h[2] = __int_as_float(best_rec);
                     }
                     resume = true;
                 }
