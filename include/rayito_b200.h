@@ -324,6 +324,10 @@ int rt_generate_camera_rays(RtScene* scene, const RtCamera* camera, const RtRend
  * 8 bits.  out is width*height*4 bytes B,G,R,A.  Host buffers. */
 int rt_tonemap_bgra8(int device, const float* rgb, size_t num_pixels, float exposure_stops, float gamma,
                      uint8_t* bgra);
+/* The same on DEVICE buffers -- the frame rt_render_device / rt_render_multi left in HBM goes to
+ * display bytes without a trip through host memory.  Enqueued on `stream`, not synchronised. */
+int rt_tonemap_bgra8_device(int device, const float* d_rgb, size_t num_pixels, float exposure_stops, float gamma,
+                            uint8_t* d_bgra, void* stream);
 
 /* ---- Stage 1 (BASELINE.json configs[0]) ------------------------------------------ */
 
@@ -343,6 +347,11 @@ typedef struct RtStage1Plane
  * tan of the full field of view).  rgb8 = width*height*3 bytes, the P6 payload. */
 int rt_stage1_render(int device, const RtStage1Plane* planes, uint32_t num_planes, const RtCamera* camera,
                      uint32_t width, uint32_t height, uint8_t* rgb8);
+
+/* The same, also returning pixelColor before clamp() (rgb: width*height*3 floats), which is what
+ * the program streams out when built with WRITE_PFM (main.cpp:57,122-123). */
+int rt_stage1_render_float(int device, const RtStage1Plane* planes, uint32_t num_planes, const RtCamera* camera,
+                           uint32_t width, uint32_t height, float* rgb, uint8_t* rgb8);
 
 /* Device memory the library keeps between calls for speed (one wavefront state block per device,
  * parked when a scene is destroyed; the Stage 2/3 working set) is freed here.  Optional. */

@@ -97,6 +97,8 @@ int rth_app_raytrace_multi(RthApp* app, const float* spec14, unsigned width, uns
  * arithmetic (main.cpp:28-52), renders on the GPU and returns the P6 payload
  * (width*height*3 bytes); what `make && ./rayito` writes after the "P6" header. */
 int rth_stage1_render(int device, unsigned width, unsigned height, unsigned char* rgb8);
+/* ... also handing back pixelColor before clamp() (rgb: width*height*3 floats; what WRITE_PFM streams out) */
+int rth_stage1_render_float(int device, unsigned width, unsigned height, float* rgb, unsigned char* rgb8);
 
 /* Stage 2 and Stage 3 programs (Rayito_Stage2/main.cpp:93-228, Rayito_Stage3/main.cpp:162-279):
  * build the program's scene and camera (fov 45 at (0,5,15) looking at the origin) with

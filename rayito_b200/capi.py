@@ -110,7 +110,8 @@ CORE_SYMBOLS = [
     "rt_scene_create", "rt_scene_destroy",
     "rt_trace_closest", "rt_trace_closest_ex", "rt_trace_any",
     "rt_trace_closest_device", "rt_trace_any_device", "rt_trace_closest_counted", "rt_trace_any_counted",
-    "rt_render", "rt_render_device", "rt_generate_camera_rays", "rt_tonemap_bgra8",
+    "rt_render", "rt_render_device", "rt_generate_camera_rays", "rt_tonemap_bgra8", "rt_tonemap_bgra8_device",
+    "rt_stage1_render_float",
     "rt_tile_owners", "rt_sample_permutations", "rt_cmj_sample1d", "rt_cmj_sample2d", "rt_stage1_render",
     "rt_libm_eval", "rt_stage23_render", "rt_release_cached_memory",
     "rt_comm_unique_id", "rt_comm_create", "rt_comm_from_nccl", "rt_comm_destroy", "rt_render_multi",
@@ -120,7 +121,7 @@ HOST_SYMBOLS = [
     "rth_last_error_string", "rth_scene_create", "rth_scene_destroy", "rth_scene_desc",
     "rth_scene_prepare_seconds", "rth_scene_depth", "rth_camera", "rth_scene_default_camera", "rth_raytrace",
     "rth_app_create", "rth_app_destroy", "rth_app_raytrace", "rth_app_raytrace_image", "rth_app_raytrace_multi",
-    "rth_stage1_render", "rth_stage23_render",
+    "rth_stage1_render", "rth_stage1_render_float", "rth_stage23_render",
 ]
 
 _core = None
@@ -160,6 +161,7 @@ def core():
         lib.rt_unpack_tiles.argtypes = [C.c_int, vp, u32, u32, u32, u32, u32, vp, vp]
         lib.rt_generate_camera_rays.argtypes = [vp, C.POINTER(RtCamera), C.POINTER(RtRenderParams), u32, vp]
         lib.rt_tonemap_bgra8.argtypes = [C.c_int, vp, sz, C.c_float, C.c_float, vp]
+        lib.rt_tonemap_bgra8_device.argtypes = [C.c_int, vp, sz, C.c_float, C.c_float, vp, vp]
         lib.rt_libm_eval.argtypes = [C.c_int, vp, vp, sz, vp]
         lib.rt_tile_owners.argtypes = [u32, u32, u32, u32, vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]
         lib.rt_sample_permutations.argtypes = [u32, u32, u32, u32, u32, vp]

@@ -475,6 +475,19 @@ int rt_stage1_render(int device, const RtStage1Plane* planes, uint32_t num_plane
     return rt_stage1_impl(device, planes, num_planes, camera, width, height, rgb8);
 }
 
+int rt_stage1_render_float(int device, const RtStage1Plane* planes, uint32_t num_planes, const RtCamera* camera,
+                            uint32_t width, uint32_t height, float* rgb, uint8_t* rgb8)
+{
+    if (rgb == NULL) return rt_fail(RT_ERR_ARG, "null argument");
+    return rt_stage1_impl(device, planes, num_planes, camera, width, height, rgb8, rgb);
+}
+
+int rt_tonemap_bgra8_device(int device, const float* d_rgb, size_t num_pixels, float exposure_stops, float gamma,
+                            uint8_t* d_bgra, void* stream)
+{
+    return rt_tonemap_device_impl(device, d_rgb, num_pixels, exposure_stops, gamma, d_bgra, static_cast<cudaStream_t>(stream));
+}
+
 void rt_release_cached_memory(void)
 {
     rt_detail::s23_release();                      // the Stage 2/3 working set goes back to the pool first

@@ -958,7 +958,7 @@ __global__ void k_tonemap(const float* __restrict__ rgb_in, size_t n, float expo
 // corners, closest one-sided plane in list order, kRayTMin = 1e-5, 8-bit truncation.
 // Stage 1's Vector::normalize divides unconditionally (rayito.h:194).
 __global__ void k_stage1(const RtStage1Plane* __restrict__ planes, uint32_t num_planes, const RtCamera cam,
-                         uint32_t width, uint32_t height, uint8_t* __restrict__ out)
+                         uint32_t width, uint32_t height, uint8_t* __restrict__ out, float* __restrict__ out_f)
 {
     uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t y = blockIdx.y;
@@ -988,6 +988,12 @@ __global__ void k_stage1(const RtStage1Plane* __restrict__ planes, uint32_t num_
         best = t;
         r = planes[k].color[0]; g = planes[k].color[1]; b = planes[k].color[2];
     }
+    if (out_f)
+    {
+        // pixelColor before clamp(): what the WRITE_PFM build streams out (main.cpp:122-123)
+        float* pf = out_f + ((size_t)y * width + x) * 3;
+        pf[0] = r; pf[1] = g; pf[2] = b;
+    }
     r = std_max(0.0f, std_min(1.0f, r));
     g = std_max(0.0f, std_min(1.0f, g));
     b = std_max(0.0f, std_min(1.0f, b));
@@ -998,7 +1004,7 @@ __global__ void k_stage1(const RtStage1Plane* __restrict__ planes, uint32_t num_
 }
 
 inline int rt_stage1_impl(int device, const RtStage1Plane* planes, uint32_t num_planes, const RtCamera* cam,
-                          uint32_t width, uint32_t height, uint8_t* rgb8)
+                          uint32_t width, uint32_t height, uint8_t* rgb8, float* rgb = NULL)
 {
     if (cam == NULL || rgb8 == NULL || (num_planes && planes == NULL) || width < 2 || height < 2)
         return rt_fail(RT_ERR_ARG, "bad argument (Stage 1 needs width, height >= 2)");
@@ -1011,20 +1017,24 @@ inline int rt_stage1_impl(int device, const RtStage1Plane* planes, uint32_t num_
     RT_CUDA(cudaSetDevice(device));
     RtStage1Plane* d_planes = NULL;
     uint8_t* d_out = NULL;
+    float* d_out_f = NULL;
     size_t bytes = (size_t)width * height * 3;
     cudaError_t e = cudaMalloc((void**)&d_planes, sizeof(RtStage1Plane) * (num_planes ? num_planes : 1));
     if (e == cudaSuccess) e = cudaMalloc((void**)&d_out, bytes);
+    if (e == cudaSuccess && rgb != NULL) e = cudaMalloc((void**)&d_out_f, bytes * sizeof(float));
     if (e == cudaSuccess && num_planes)
         e = cudaMemcpy(d_planes, planes, sizeof(RtStage1Plane) * num_planes, cudaMemcpyHostToDevice);
     if (e == cudaSuccess)
     {
         dim3 grid((width + 127) / 128, height);
-        k_stage1<<<grid, 128>>>(d_planes, num_planes, *cam, width, height, d_out);
+        k_stage1<<<grid, 128>>>(d_planes, num_planes, *cam, width, height, d_out, d_out_f);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaMemcpy(rgb8, d_out, bytes, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && rgb != NULL) e = cudaMemcpy(rgb, d_out_f, bytes * sizeof(float), cudaMemcpyDeviceToHost);
     if (d_planes) cudaFree(d_planes);
     if (d_out) cudaFree(d_out);
+    if (d_out_f) cudaFree(d_out_f);
     if (e != cudaSuccess) return rt_cuda_fail(e, "stage 1 render");
     return RT_OK;
 }
@@ -1621,6 +1631,27 @@ inline int rt_camera_rays_impl(RtScene* s, const RtCamera* camera, const RtRende
     cudaError_t e = cudaMemcpy(rays, d_rays, n * sizeof(RtRay), cudaMemcpyDeviceToHost);
     cudaFree(d_rays);
     if (e != cudaSuccess) return rt_cuda_fail(e, "camera rays");
+    return RT_OK;
+}
+
+// Same on device buffers (the frame rt_render_device / rt_render_multi left in HBM), enqueued on `st`
+inline int rt_tonemap_device_impl(int device, const float* d_rgb, size_t num_pixels, float exposure_stops, float gamma,
+                                  uint8_t* d_bgra, cudaStream_t st)
+{
+    if (d_rgb == NULL || d_bgra == NULL)
+        return rt_fail(RT_ERR_ARG, "null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    {
+        cudaGetLastError();
+        return rt_fail(RT_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+    }
+    RT_CUDA(cudaSetDevice(device));
+    if (num_pixels == 0) return RT_OK;
+    float gamma_exp = 1.0f / gamma;
+    float exposure = std::pow(2.0f, exposure_stops);
+    k_tonemap<<<(unsigned)((num_pixels + 255) / 256), 256, 0, st>>>(d_rgb, num_pixels, exposure, gamma_exp, d_bgra);
+    RT_CUDA(cudaGetLastError());
     return RT_OK;
 }
 

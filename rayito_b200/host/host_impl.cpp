@@ -714,7 +714,7 @@ int rth_app_raytrace_multi(RthApp* app, const float* spec14, unsigned width, uns
     }
 }
 
-int rth_stage1_render(int device, unsigned width, unsigned height, unsigned char* rgb8)
+int rth_stage1_render_float(int device, unsigned width, unsigned height, float* rgb, unsigned char* rgb8)
 {
     using namespace Rayito;
     // Scene of Rayito_Stage1/main.cpp:68-74
@@ -745,10 +745,16 @@ int rth_stage1_render(int device, unsigned width, unsigned height, unsigned char
     cam.right[0] = right.m_x; cam.right[1] = right.m_y; cam.right[2] = right.m_z;
     cam.up[0] = up.m_x; cam.up[1] = up.m_y; cam.up[2] = up.m_z;
     cam.tan_fov = std::tan(30.0f * M_PI / 180.0f);
-    int rc = rt_stage1_render(device, &plane, 1, &cam, width, height, rgb8);
+    int rc = rgb != NULL ? rt_stage1_render_float(device, &plane, 1, &cam, width, height, rgb, rgb8)
+                         : rt_stage1_render(device, &plane, 1, &cam, width, height, rgb8);
     if (rc != RT_OK)
         t_hostError = rt_last_error_string();
     return rc;
+}
+
+int rth_stage1_render(int device, unsigned width, unsigned height, unsigned char* rgb8)
+{
+    return rth_stage1_render_float(device, width, height, NULL, rgb8);
 }
 
 } // extern "C"
