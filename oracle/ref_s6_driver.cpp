@@ -9,7 +9,7 @@
 // bench.py's cpu_baseline / --impl reference leg may load that library.
 //
 // What it exposes:
-//   * scene construction through rayito_b200/host/scene_recipes.h (the same file
+//   * scene construction through fixtures/scene_recipes.h (the same file
 //     the product compiles against its own headers),
 //   * closest-hit / any-hit on caller supplied ray batches, with the winning
 //     (shape, face, triangle) recovered by a Mesh subclass (no reference edits),

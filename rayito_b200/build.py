@@ -2,6 +2,7 @@
 
     librayito_b200.so   CUDA render core + C ABI      (rayito_b200/csrc, nvcc, sm_100a only)
     librayito_host.so   C++ mirror of the Rayito API  (rayito_b200/host, g++)
+    fixtures/librayito_fixtures.so   recipe scenes of the tests and of bench.py (not product)
 
 nvcc cross-compiles without a GPU, so this runs in the CPU-only build container;
 the resulting .so files are git-ignored but travel to the GPU box with the snapshot.
@@ -18,6 +19,8 @@ HOST = os.path.join(ROOT, "rayito_b200", "host")
 INCLUDE = os.path.join(ROOT, "include")
 CORE_LIB = os.path.join(CSRC, "librayito_b200.so")
 HOST_LIB = os.path.join(HOST, "librayito_host.so")
+FIXTURES = os.path.join(ROOT, "fixtures")
+FIXTURES_LIB = os.path.join(FIXTURES, "librayito_fixtures.so")
 ASSETS = os.path.join(ROOT, "assets", "_models")
 REFERENCE = "/root/reference"
 
@@ -87,6 +90,21 @@ def build_host(force=False):
     return HOST_LIB
 
 
+def build_fixtures(force=False):
+    """fixtures/librayito_fixtures.so: the recipe scenes of the tests and of bench.py, built with
+    the host library's public API (test infrastructure, not product)."""
+    build_host()
+    srcs = _sources(FIXTURES, (".cpp", ".h")) + _sources(HOST, (".hpp", ".h")) + _sources(INCLUDE, (".h",))
+    if force or _newer(FIXTURES_LIB, srcs + [HOST_LIB]):
+        cmd = [HOST_CXX, "-O2", "-std=c++11", "-fPIC", "-shared", "-ffp-contract=off", "-Wall",
+               "-I" + FIXTURES, "-I" + HOST, "-I" + INCLUDE,
+               os.path.join(FIXTURES, "fixtures.cpp"), "-o", FIXTURES_LIB,
+               "-L" + HOST, "-lrayito_host", "-L" + CSRC, "-lrayito_b200", "-pthread",
+               "-Wl,-rpath,$ORIGIN/../rayito_b200/host", "-Wl,-rpath,$ORIGIN/../rayito_b200/csrc", "-Wl,-Bsymbolic"]
+        _run(cmd)
+    return FIXTURES_LIB
+
+
 def stage_assets():
     """Copy the reference's OBJ fixtures into assets/_models (git-ignored) when the
     reference tree is present; the GPU box has no /root/reference and uses the copy."""
@@ -114,6 +132,7 @@ def build_all(force=False):
     stage_assets()
     build_core(force)
     build_host(force)
+    build_fixtures(force)
     build_oracle()
 
 

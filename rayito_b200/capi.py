@@ -118,10 +118,13 @@ CORE_SYMBOLS = [
     "rt_packed_floats", "rt_render_tiles_packed", "rt_unpack_tiles", "rt_render_multi_host", "rt_comm_rank",
 ]
 HOST_SYMBOLS = [
-    "rth_last_error_string", "rth_scene_create", "rth_scene_destroy", "rth_scene_desc",
-    "rth_scene_prepare_seconds", "rth_scene_depth", "rth_camera", "rth_scene_default_camera", "rth_raytrace",
+    "rth_last_error_string", "rth_camera", "rth_stage1_render", "rth_stage1_render_float", "rth_stage23_render",
+]
+# fixtures/rayito_fixtures.h (test infrastructure: the recipe scenes)
+FIXTURE_SYMBOLS = [
+    "rthf_last_error_string", "rth_scene_create", "rth_scene_destroy", "rth_scene_desc",
+    "rth_scene_prepare_seconds", "rth_scene_depth", "rth_scene_default_camera", "rth_raytrace",
     "rth_app_create", "rth_app_destroy", "rth_app_raytrace", "rth_app_raytrace_image", "rth_app_raytrace_multi",
-    "rth_stage1_render", "rth_stage1_render_float", "rth_stage23_render",
 ]
 
 _core = None
@@ -172,15 +175,42 @@ def core():
     return _core
 
 
+class _HostLibs:
+    """librayito_host.so (product) and fixtures/librayito_fixtures.so (recipe scenes) behind one
+    attribute lookup, so that callers write lib.rth_xxx whichever library holds it."""
+
+    def __init__(self, host_lib, fixtures_lib):
+        self.product = host_lib
+        self.fixtures = fixtures_lib
+
+    def __getattr__(self, name):
+        for lib in (self.__dict__["fixtures"], self.__dict__["product"]):
+            try:
+                return getattr(lib, name)
+            except AttributeError:
+                continue
+        raise AttributeError(name)
+
+    def rth_last_error_string(self):
+        """Last error texts of both libraries on this thread (each keeps its own)."""
+        a, b = self.product.rth_last_error_string(), self.fixtures.rthf_last_error_string()
+        return a + (b" | " if a and b else b"") + b
+
+
 def host():
-    """librayito_host.so (the C++ mirror of the Rayito API)."""
+    """librayito_host.so (the C++ mirror of the Rayito API) plus the fixtures library."""
     global _host
     if _host is None:
         core()
-        path = _build.build_host()
-        lib = C.CDLL(path, mode=C.RTLD_LOCAL)
         vp = C.c_void_p
-        lib.rth_last_error_string.restype = C.c_char_p
+        hl = C.CDLL(_build.build_host(), mode=C.RTLD_GLOBAL)
+        hl.rth_last_error_string.restype = C.c_char_p
+        hl.rth_camera.argtypes = [vp, C.POINTER(RtCamera)]
+        hl.rth_stage1_render.argtypes = [C.c_int, C.c_uint, C.c_uint, vp]
+        hl.rth_stage1_render_float.argtypes = [C.c_int, C.c_uint, C.c_uint, vp, vp]
+        hl.rth_stage23_render.argtypes = [C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_uint, vp, vp, vp]
+        lib = C.CDLL(_build.build_fixtures(), mode=C.RTLD_LOCAL)
+        lib.rthf_last_error_string.restype = C.c_char_p
         lib.rth_scene_create.restype = vp
         lib.rth_scene_create.argtypes = [C.c_int, C.c_char_p, C.c_uint, C.c_uint]
         lib.rth_scene_destroy.argtypes = [vp]
@@ -190,7 +220,6 @@ def host():
         lib.rth_scene_prepare_seconds.argtypes = [vp]
         lib.rth_scene_depth.restype = C.c_uint
         lib.rth_scene_depth.argtypes = [vp, C.c_int]
-        lib.rth_camera.argtypes = [vp, C.POINTER(RtCamera)]
         lib.rth_scene_default_camera.argtypes = [vp, vp]
         lib.rth_raytrace.argtypes = [C.c_int, C.c_char_p, C.c_uint, C.c_uint, vp, C.c_uint, C.c_uint,
                                      C.c_uint, C.c_uint, C.c_uint, C.c_int, C.c_uint, C.c_uint, C.c_int,
@@ -206,9 +235,7 @@ def host():
                                                C.POINTER(RtRenderStats)]
         lib.rth_app_raytrace_multi.argtypes = [vp, vp, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, vp, C.c_int,
                                                C.POINTER(C.c_void_p), C.POINTER(RtRenderStats)]
-        lib.rth_stage1_render.argtypes = [C.c_int, C.c_uint, C.c_uint, vp]
-        lib.rth_stage23_render.argtypes = [C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_uint, vp, vp, vp]
-        _host = lib
+        _host = _HostLibs(hl, lib)
     return _host
 
 

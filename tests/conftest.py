@@ -108,7 +108,7 @@ def scene8_ref(ref):
     return ref.RefScene(8)
 
 
-# Deep-tree edge scenes (host/scene_recipes.h buildDeepScene): face BVH 42 / 46 deep, and with
+# Deep-tree edge scenes (fixtures/scene_recipes.h buildDeepScene): face BVH 42 / 46 deep, and with
 # the sphere chain a top-level BVH 18 deep as well
 DEEP_GRID = (40, 8)
 DEEPER_GRID = (44, 8)

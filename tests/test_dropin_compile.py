@@ -11,7 +11,7 @@ def test_stage6_application_builds_against_dropin_headers(tmp_path, obj_path, ca
     host = os.path.join(ROOT, "rayito_b200", "host")
     core = os.path.join(ROOT, "rayito_b200", "csrc")
     exe = str(tmp_path / "stage6_app")
-    subprocess.run(["/usr/bin/g++", "-O1", "-std=c++11", "-DRAYITO_B200_STAGE=6", "-I" + host,
+    subprocess.run(["/usr/bin/g++", "-O1", "-std=c++11", "-DRAYITO_B200_STAGE=6", "-I" + host, "-I" + os.path.join(ROOT, "fixtures"),
                     "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "stage6_app.cpp"),
                     "-L" + host, "-lrayito_host", "-L" + core, "-lrayito_b200",
                     "-Wl,-rpath," + host, "-Wl,-rpath," + core, "-o", exe], check=True, timeout=300)

@@ -215,7 +215,7 @@ def test_stage6_image_matches_reference_within_noise(capi, scene6_host, scene6_r
 
 @pytest.mark.parametrize("recipe,ls,depth", [(7, 2, 3), (8, 1, 4), (9, 1, 2)])
 def test_edge_scene_images_match_reference(capi, ref, recipe, ls, depth):
-    """Edge-case scenes (host/scene_recipes.h buildEdgeScene): linear shape list with n-gon
+    """Edge-case scenes (fixtures/scene_recipes.h buildEdgeScene): linear shape list with n-gon
     faces, scale keys and a tilted light; no lights (black image, mirror bounces still traced);
     the empty set."""
     host = capi.HostScene(recipe)
