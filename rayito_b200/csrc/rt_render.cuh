@@ -90,10 +90,16 @@ struct RenderCtx
     float4* res;                // radiance rgb
     float4* pos_wo;             // [2i] hit position xyz, time; [2i+1] outgoing xyz, material index
     float4* lit_tr;             // [2i] throughput at the bounce being lit; [2i+1] lightResult accumulator
-    // One 64-byte record per path for the current light sample (one DRAM burst, written whole by
-    // k_light_sample): [4i+0] shadow direction xyz, tMax; [4i+1] light-sample term rgb, valid flag;
-    // [4i+2] probe direction xyz, brdf pdf (0 = none); [4i+3] partial BRDF-sample term rgb, light shape id
+    // The two rays of the current light sample, one 32-byte sector each, so that a traversal pass
+    // fetches a ray with ONE scattered sector read (origin and direction in separate arrays were two):
+    // [4i+0] shadow direction xyz, tMax; [4i+1] origin xyz, time;
+    // [4i+2] probe direction xyz, brdf pdf (0 = none); [4i+3] origin xyz, time (again).
+    // Written whole (64 bytes) by k_light_sample.
     float4* lrec;
+    // ... and what k_resolve adds up afterwards, 32 bytes written whole by k_light_sample:
+    // [2i+0] light-sample term rgb, valid flag (cleared by an occluded shadow ray);
+    // [2i+1] partial BRDF-sample term rgb, light shape id
+    float4* lterm;
     float4* mis_hit0;
     float4* mis_hit1;
     float4* xf_cache;           // per-sample transform cache: sc.anim_stride float4 per sample (rt_device.cuh), or NULL
@@ -396,8 +402,7 @@ struct PathIO
 struct MisIO
 {
     BinQ<RT_QBINS> queue;
-    const float4* pos_wo;        // hit position, time at [2 * tag]
-    const float4* lrec;          // probe direction at [4 * tag + 2]
+    const float4* lrec;          // probe direction at [4 * tag + 2], origin and time at [4 * tag + 3]
     float4* mis_hit0;
     const float4* xf_cache;
     uint32_t xf_stride;
@@ -405,7 +410,7 @@ struct MisIO
     __device__ __forceinline__ uint32_t count() const { return queue.total(); }
     __device__ __forceinline__ uint32_t tag_at(uint32_t j) const { return queue.at(j); }
     // the two 16-byte records of a ray and how they decode (used by the prefetching top-level pass)
-    __device__ __forceinline__ const float4* rec_a(uint32_t tag) const { return pos_wo + 2 * (size_t)tag; }
+    __device__ __forceinline__ const float4* rec_a(uint32_t tag) const { return lrec + 4 * (size_t)tag + 3; }
     __device__ __forceinline__ const float4* rec_b(uint32_t tag) const { return lrec + 4 * (size_t)tag + 2; }
     __device__ __forceinline__ void decode(float4 a, float4 b, V3& o, V3& d, float& tmax, float& time) const
     {
@@ -413,7 +418,7 @@ struct MisIO
     }
     __device__ __forceinline__ void load_tag(uint32_t tag, V3& o, V3& d, float& tmax, float& time) const
     {
-        decode(pos_wo[2 * (size_t)tag], lrec[4 * (size_t)tag + 2], o, d, tmax, time);
+        decode(lrec[4 * (size_t)tag + 3], lrec[4 * (size_t)tag + 2], o, d, tmax, time);
     }
     __device__ __forceinline__ bool load(uint32_t j, V3& o, V3& d, float& tmax, float& time, uint32_t& tag) const
     {
@@ -430,15 +435,15 @@ struct MisIO
 struct ShadowIO
 {
     BinQ<RT_QBINS> queue;
-    const float4* pos_wo;        // hit position, time at [2 * tag]
-    float4* lrec;                // shadow direction at [4 * tag + 0]; [4 * tag + 1].w = light sample still valid
+    const float4* lrec;          // shadow direction and tMax at [4 * tag + 0], origin and time at [4 * tag + 1]
+    float4* lterm;               // [2 * tag].w = light sample still valid
     const float4* xf_cache;
     uint32_t xf_stride;
     __device__ __forceinline__ const float4* xf_row(uint32_t tag) const { return xf_cache ? xf_cache + (size_t)tag * xf_stride : nullptr; }
     __device__ __forceinline__ uint32_t count() const { return queue.total(); }
     __device__ __forceinline__ uint32_t tag_at(uint32_t j) const { return queue.at(j); }
     // the two 16-byte records of a ray and how they decode (used by the prefetching top-level pass)
-    __device__ __forceinline__ const float4* rec_a(uint32_t tag) const { return pos_wo + 2 * (size_t)tag; }
+    __device__ __forceinline__ const float4* rec_a(uint32_t tag) const { return lrec + 4 * (size_t)tag + 1; }
     __device__ __forceinline__ const float4* rec_b(uint32_t tag) const { return lrec + 4 * (size_t)tag; }
     __device__ __forceinline__ void decode(float4 a, float4 b, V3& o, V3& d, float& tmax, float& time) const
     {
@@ -446,7 +451,7 @@ struct ShadowIO
     }
     __device__ __forceinline__ void load_tag(uint32_t tag, V3& o, V3& d, float& tmax, float& time) const
     {
-        decode(pos_wo[2 * (size_t)tag], lrec[4 * (size_t)tag], o, d, tmax, time);
+        decode(lrec[4 * (size_t)tag + 1], lrec[4 * (size_t)tag], o, d, tmax, time);
     }
     __device__ __forceinline__ bool load(uint32_t j, V3& o, V3& d, float& tmax, float& time, uint32_t& tag) const
     {
@@ -458,7 +463,7 @@ struct ShadowIO
     __device__ __forceinline__ void store(uint32_t tag, const WaveResult& r) const
     {
         if (r.any_hit)
-            reinterpret_cast<float*>(lrec + 4 * (size_t)tag + 1)[3] = 0.0f;
+            reinterpret_cast<float*>(lterm + 2 * (size_t)tag)[3] = 0.0f;
     }
 };
 
@@ -470,12 +475,12 @@ __host__ __device__ __forceinline__ PathIO make_path_io(const RenderCtx& c, int 
 }
 __host__ __device__ __forceinline__ MisIO make_mis_io(const RenderCtx& c)
 {
-    MisIO io = { { c.q_mis, c.ctl + CTL_MIS, c.qcap }, c.pos_wo, c.lrec, c.mis_hit0, c.xf_cache, c.sc.anim_stride };
+    MisIO io = { { c.q_mis, c.ctl + CTL_MIS, c.qcap }, c.lrec, c.mis_hit0, c.xf_cache, c.sc.anim_stride };
     return io;
 }
 __host__ __device__ __forceinline__ ShadowIO make_shadow_io(const RenderCtx& c)
 {
-    ShadowIO io = { { c.q_shadow, c.ctl + CTL_SHADOW, c.qcap }, c.pos_wo, c.lrec, c.xf_cache, c.sc.anim_stride };
+    ShadowIO io = { { c.q_shadow, c.ctl + CTL_SHADOW, c.qcap }, c.lrec, c.lterm, c.xf_cache, c.sc.anim_stride };
     return io;
 }
 
@@ -530,11 +535,12 @@ k_split_top_static(const __grid_constant__ DScene sc, const IO io, const SplitBu
 #else
     float4* stage_rec = NULL;
 #endif
+    __shared__ uint32_t stage_q[(RT_BLOCK / 32) * RT_STAGE_Q];
     split_zero(ps);
     if (count_slot >= 0 && blockIdx.x == 0 && threadIdx.x == 0)
         atomicAdd(reinterpret_cast<unsigned long long*>(totals + count_slot), (unsigned long long)io.count());
     WorkCount wc = RT_WORK_ZERO;
-    trace_top_static<ANY, COUNT>(sc, io, sb, ps, wc, lane_t0, lane_t1, stage_rec);
+    trace_top_static<ANY, COUNT>(sc, io, sb, ps, wc, lane_t0, lane_t1, stage_rec, stage_q);
     if (COUNT)
         flush_work_counters(wc, totals);
 }
@@ -785,9 +791,12 @@ k_light_sample(const __grid_constant__ RenderCtx c, int cur, uint32_t bounce, ui
                 mp = make_float4(P.r, P.g, P.b, __uint_as_float(light_shape));
                 bq_push(c.q_mis, c.ctl + CTL_MIS, c.qcap, dir_octant(pd), i);
             }
-            // the whole 64-byte record, every time: full sectors, no read-modify-write
+            // the whole 64-byte ray record and the whole 32-byte term record, every time: full sectors,
+            // no read-modify-write
             float4* rec = c.lrec + 4 * (size_t)i;
-            rec[0] = shd; rec[1] = shl; rec[2] = md; rec[3] = mp;
+            rec[0] = shd; rec[1] = pt; rec[2] = md; rec[3] = pt;
+            float4* term = c.lterm + 2 * (size_t)i;
+            term[0] = shl; term[1] = mp;
         }
     }
 }
@@ -842,17 +851,18 @@ k_resolve(const __grid_constant__ RenderCtx c, uint32_t lsi)
         uint32_t i = c.q_lit[j];
         Color3 lr = rgb(c.lit_tr[2 * (size_t)i + 1]);
         const float4* rec = c.lrec + 4 * (size_t)i;
-        float4 shl = rec[1];
+        const float4* term = c.lterm + 2 * (size_t)i;
+        float4 shl = term[0];
         if (shl.w != 0.0f)
             lr = lr + rgb(shl);
         float4 md = rec[2];
         if (md.w > 0.0f)
         {
-            float4 mp = rec[3], mh0 = c.mis_hit0[i];
+            float4 mp = term[1], mh0 = c.mis_hit0[i];
             uint32_t light_shape = __float_as_uint(mp.w);
             if (__float_as_int(mh0.y) == (int)light_shape)
             {
-                float4 pt = c.pos_wo[2 * (size_t)i];
+                float4 pt = rec[3];
                 DShape lsh = load_shape(c.sc, light_shape);
                 // normal of the probe's hit (only needed once the probe found the light)
                 ClosestHit h;
@@ -1090,6 +1100,7 @@ inline size_t carve(RenderCtx& c, char* base, size_t samples, size_t pixels, uin
     c.pos_wo = k.take<float4>(samples * 2);
     c.lit_tr = k.take<float4>(samples * 2);
     c.lrec = k.take<float4>(samples * 4);
+    c.lterm = k.take<float4>(samples * 2);
     c.mis_hit0 = k.take<float4>(samples);
     c.mis_hit1 = k.take<float4>(samples);
     c.xf_cache = xf_stride ? k.take<float4>(samples * xf_stride) : NULL;
@@ -1104,10 +1115,8 @@ inline size_t carve(RenderCtx& c, char* base, size_t samples, size_t pixels, uin
     c.q_meshq[1] = k.take<uint32_t>(samples);
     c.q_resume[0] = k.take<uint32_t>(samples);
     c.q_resume[1] = k.take<uint32_t>(samples);
-    c.split.hit = k.take<float4>(samples);
-    c.split.stack = k.take<float4>(samples * RT_SPLIT_TOPCAP);
-    c.split.mesh_o = k.take<float4>(samples);
-    c.split.mesh_d = k.take<float4>(samples);
+    c.split.rec = k.take<float4>(samples * 4);
+    c.split.stack = k.take<float4>(samples * (RT_SPLIT_TOPCAP - 1));
     c.ctl = k.take<uint32_t>(CTL_WORDS);
     c.totals = k.take<uint64_t>(8);
     return k.off + 256;

@@ -51,16 +51,27 @@
 #define RT_SPLIT_TOPCAP 8        /* top-level stack entries a suspended ray can carry */
 #define RT_SPLIT_MAX_MESHES 12   /* more mesh shapes than this: use the unified kernel */
 
-// Per-slot suspended-ray state (slot = path sample index / ray index).  Kept small: every word is
-// written and read back through scattered 16-byte accesses.  The set-local ray itself is NOT saved:
-// a resume pass recomputes it from the stage's own ray record (same inputs, same bits).
+// Per-slot suspended-ray state (slot = path sample index / ray index).  Kept small and packed: one
+// 64-byte record per slot, written whole by the top-level pass that suspends the ray (two full DRAM
+// sectors: separate 16-byte arrays made every store a partial-sector write that L2 has to fill from
+// HBM first), read back half by half -- the mesh pass needs only the first 32 bytes, the resume pass
+// only the second.  The set-local ray itself is NOT saved: a resume pass recomputes it from the
+// stage's own ray record (same inputs, same bits).
+//   rec[4 * slot + 0]  mesh-local origin xyz (computed by the top pass at mesh entry), m_t (closest hit) or tMax (any hit)
+//   rec[4 * slot + 1]  mesh-local direction xyz, mesh shape to enter
+//   rec[4 * slot + 2]  m_t, winner shape, winner triangle record, (mesh shape to enter | sp << 24)
+//   rec[4 * slot + 3]  top-level stack entry 0: node, t0, t1, -
+//   stack[(RT_SPLIT_TOPCAP - 1) * slot + k - 1]   top-level stack entries k >= 1
 struct SplitBufs
 {
-    float4* hit;        // m_t, winner shape, winner triangle record, (mesh shape to enter | sp << 24)
-    float4* stack;      // RT_SPLIT_TOPCAP entries per slot: node, t0, t1, -
-    float4* mesh_o;     // mesh-local origin xyz (computed by the top pass at mesh entry), m_t (closest hit) or tMax (any hit)
-    float4* mesh_d;     // mesh-local direction xyz, mesh shape to enter
+    float4* rec;
+    float4* stack;
 };
+__device__ __forceinline__ float4* split_rec(const SplitBufs& sb, uint32_t slot) { return sb.rec + 4 * (size_t)slot; }
+__device__ __forceinline__ float4* split_stack_entry(const SplitBufs& sb, uint32_t slot, int k)
+{
+    return k == 0 ? sb.rec + 4 * (size_t)slot + 3 : sb.stack + (size_t)slot * (RT_SPLIT_TOPCAP - 1) + (k - 1);
+}
 
 // One pass: where the work comes from, where suspended / resumed slots go, and
 // which counters this kernel zeroes for the passes after it (none of which it uses)
@@ -95,6 +106,47 @@ __device__ __forceinline__ void warp_queue_push(uint32_t* queue, uint32_t* count
     base = __shfl_sync(0xffffffffu, base, leader);
     if (want)
         queue[base + __popc(mask & ((1u << lane) - 1))] = value;
+}
+
+// The same through a per-warp staging buffer in shared memory: entries collect over several rounds
+// and go out with ONE atomicAdd.  Every ray that enters a mesh is appended to one global queue; on
+// the 10 M-triangle scene that was one atomic on one address per 32 rays from every warp of the
+// GPU, and 47 % of the top-level pass's stall samples sat on that atomic's return value
+// (profiles/README.md, round 2): same-address atomics serialise in L2.  All 32 lanes must call.
+#ifndef RT_STAGE_Q
+#define RT_STAGE_Q 224      /* entries per warp; flushed when fewer than 32 are free */
+#endif
+struct WarpStage
+{
+    uint32_t* buf;          // RT_STAGE_Q words of shared memory owned by this warp
+    uint32_t count;         // warp-uniform
+};
+__device__ __forceinline__ void warp_stage_flush(WarpStage& st, uint32_t* queue, uint32_t* counter)
+{
+    if (st.count == 0)
+        return;
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    if (lane == 0)
+        base = atomicAdd(counter, st.count);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    __syncwarp();
+    for (uint32_t k = lane; k < st.count; k += 32)
+        queue[base + k] = st.buf[k];
+    __syncwarp();
+    st.count = 0;
+}
+__device__ __forceinline__ void warp_stage_push(WarpStage& st, uint32_t* queue, uint32_t* counter, bool want, uint32_t value)
+{
+    const uint32_t mask = __ballot_sync(0xffffffffu, want);
+    if (mask == 0)
+        return;
+    const uint32_t lane = threadIdx.x & 31;
+    if (want)
+        st.buf[st.count + __popc(mask & ((1u << lane) - 1))] = value;
+    st.count += __popc(mask);
+    if (st.count > RT_STAGE_Q - 32)
+        warp_stage_flush(st, queue, counter);
 }
 
 // ---------------------------------------------------------------------------
@@ -200,7 +252,7 @@ __device__ __forceinline__ void trace_top(const DScene& sc, const IO& io, const 
                     // resume a suspended ray: the mesh pass has updated m_t / the winner; the set-local ray is
                     // recomputed from the stage's ray record exactly as the fresh pass computed it
                     tag = ps.in_queue[j];
-                    float4 h = sb.hit[tag];
+                    float4 h = split_rec(sb, tag)[2];
                     {
                         V3 o, d;
                         io.load_tag(tag, o, d, tmax, time);
@@ -214,13 +266,12 @@ __device__ __forceinline__ void trace_top(const DScene& sc, const IO& io, const 
                     res.tri_rec = __float_as_int(h.z);
                     res.any_hit = false;
                     sp = (int)(__float_as_uint(h.w) >> 24);
-                    const float4* st = sb.stack + (size_t)tag * RT_SPLIT_TOPCAP;
                     #pragma unroll
                     for (int k = 0; k < RT_SPLIT_TOPCAP; ++k)
                     {
                         if (k < sp)
                         {
-                            float4 e = st[k];
+                            float4 e = *split_stack_entry(sb, tag, k);
                             stk_node[k] = __float_as_uint(e.x);
                             stk_t0[k] = e.y;
                             stk_t1[k] = e.z;
@@ -316,8 +367,9 @@ __device__ __forceinline__ void trace_top(const DScene& sc, const IO& io, const 
                     if (enter)
                     {
                         suspend = true;
-                        sb.mesh_o[tag] = make_float4(rm.o.x, rm.o.y, rm.o.z, ANY ? tmax : res.t);
-                        sb.mesh_d[tag] = make_float4(rm.d.x, rm.d.y, rm.d.z, __uint_as_float(park_shape));
+                        float4* rec = split_rec(sb, tag);
+                        rec[0] = make_float4(rm.o.x, rm.o.y, rm.o.z, ANY ? tmax : res.t);
+                        rec[1] = make_float4(rm.d.x, rm.d.y, rm.d.z, __uint_as_float(park_shape));
                     }
                 }
             }
@@ -369,13 +421,15 @@ __device__ __forceinline__ void trace_top(const DScene& sc, const IO& io, const 
         {
             if (suspend)
             {
-                sb.hit[tag] = make_float4(res.t, __int_as_float(res.shape), __int_as_float(res.tri_rec),
-                                          __uint_as_float(park_shape | ((uint32_t)sp << 24)));
-                float4* st = sb.stack + (size_t)tag * RT_SPLIT_TOPCAP;
+                float4* rec = split_rec(sb, tag);
+                rec[2] = make_float4(res.t, __int_as_float(res.shape), __int_as_float(res.tri_rec),
+                                     __uint_as_float(park_shape | ((uint32_t)sp << 24)));
+                // (entry 0 is written even when the stack is empty: the record goes out as whole sectors)
+                rec[3] = make_float4(__uint_as_float(stk_node[0]), stk_t0[0], stk_t1[0], 0.0f);
                 #pragma unroll
-                for (int k = 0; k < RT_SPLIT_TOPCAP; ++k)
+                for (int k = 1; k < RT_SPLIT_TOPCAP; ++k)
                     if (k < sp)
-                        st[k] = make_float4(__uint_as_float(stk_node[k]), stk_t0[k], stk_t1[k], 0.0f);
+                        *split_stack_entry(sb, tag, k) = make_float4(__uint_as_float(stk_node[k]), stk_t0[k], stk_t1[k], 0.0f);
                 active = false;
             }
             warp_queue_push(ps.out_queue, ps.out_count, suspend, tag);
@@ -410,8 +464,9 @@ __device__ __forceinline__ void trace_top(const DScene& sc, const IO& io, const 
 #endif
 template <bool ANY, bool COUNT, class IO>
 __device__ __forceinline__ void trace_top_static(const DScene& sc, const IO& io, const SplitBufs& sb, const SplitPass& ps,
-                                                 WorkCount& wc, float* lane_t0, float* lane_t1, float4* stage_rec)
+                                                 WorkCount& wc, float* lane_t0, float* lane_t1, float4* stage_rec, uint32_t* stage_q)
 {
+    WarpStage out_stage = { stage_q + (threadIdx.x >> 5) * RT_STAGE_Q, 0u };
     // lane_t0 / lane_t1: [RT_WALK_MAX_DEPTH + 1][blockDim.x] shared floats
     const uint32_t lane = threadIdx.x & 31, tid = threadIdx.x, stride = blockDim.x;
     const uint32_t n = io.count();
@@ -603,16 +658,17 @@ __device__ __forceinline__ void trace_top_static(const DScene& sc, const IO& io,
                         if (enter)
                         {
                             suspend = true;
-                            sb.mesh_o[tag] = make_float4(rm.o.x, rm.o.y, rm.o.z, ANY ? tmax : res.t);
-                            sb.mesh_d[tag] = make_float4(rm.d.x, rm.d.y, rm.d.z, __uint_as_float(shape_id));
+                            float4* rec = split_rec(sb, tag);
+                            rec[0] = make_float4(rm.o.x, rm.o.y, rm.o.z, ANY ? tmax : res.t);
+                            rec[1] = make_float4(rm.d.x, rm.d.y, rm.d.z, __uint_as_float(shape_id));
                             // the explicit stack of the dynamic pass at this point: pending far
                             // children whose parents passed, with the ranges those parents pushed
                             const uint4 p0 = __ldg(reinterpret_cast<const uint4*>(steps + s) + 1);
                             const uint4 p1 = __ldg(reinterpret_cast<const uint4*>(steps + s) + 2);
                             const uint32_t pn[8] = { p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w };
                             const uint32_t npend = (flags >> 16) & 0xffu;
-                            float4* st = sb.stack + (size_t)tag * RT_SPLIT_TOPCAP;
                             uint32_t sp = 0;
+                            float4 entry0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                             #pragma unroll
                             for (uint32_t k = 0; k < RT_WALK_MAX_DEPTH; ++k)
                             {
@@ -621,14 +677,17 @@ __device__ __forceinline__ void trace_top_static(const DScene& sc, const IO& io,
                                     uint32_t dk = (hd.w >> (4 * k)) & 0xfu;
                                     if ((alive >> dk) & 1u)
                                     {
-                                        st[sp] = make_float4(__uint_as_float(pn[k]), lane_t0[dk * stride + tid],
-                                                             lane_t1[dk * stride + tid], 0.0f);
+                                        const float4 e = make_float4(__uint_as_float(pn[k]), lane_t0[dk * stride + tid],
+                                                                     lane_t1[dk * stride + tid], 0.0f);
+                                        if (sp == 0) entry0 = e;
+                                        else *split_stack_entry(sb, tag, (int)sp) = e;
                                         ++sp;
                                     }
                                 }
                             }
-                            sb.hit[tag] = make_float4(res.t, __int_as_float(res.shape), __int_as_float(res.tri_rec),
-                                                      __uint_as_float(shape_id | (sp << 24)));
+                            rec[2] = make_float4(res.t, __int_as_float(res.shape), __int_as_float(res.tri_rec),
+                                                 __uint_as_float(shape_id | (sp << 24)));
+                            rec[3] = entry0;        // (always: the 64-byte record goes out as whole sectors)
                             open = false;
                             suspended = true;
                         }
@@ -679,8 +738,8 @@ __device__ __forceinline__ void trace_top_static(const DScene& sc, const IO& io,
                 (void)suspend;
             }
         }
-        // rays that entered a mesh: one queue append per chunk (a lane suspends at most once per walk)
-        warp_queue_push(ps.out_queue, ps.out_count, suspended, tag);
+        // rays that entered a mesh (a lane suspends at most once per walk): staged, appended every few chunks
+        warp_stage_push(out_stage, ps.out_queue, ps.out_count, suspended, tag);
         if (live && !suspended)
             io.store(tag, res);
 #if RT_STATIC_PREFETCH
@@ -697,6 +756,7 @@ __device__ __forceinline__ void trace_top_static(const DScene& sc, const IO& io,
 #if RT_STATIC_PREFETCH
     __pipeline_wait_prior(0);
 #endif
+    warp_stage_flush(out_stage, ps.out_queue, ps.out_count);
 }
 
 // ---------------------------------------------------------------------------
@@ -792,7 +852,7 @@ __device__ __forceinline__ void trace_mesh(const DScene& sc, const IO& io, const
                 have_cur = false;
                 top_valid = false;
                 tag = ps.in_queue[j];
-                float4 mo = sb.mesh_o[tag], md = sb.mesh_d[tag];
+                float4 mo = split_rec(sb, tag)[0], md = split_rec(sb, tag)[1];
                 tmax = mo.w;            // (any hit)
                 best = mo.w;            // (closest hit)
                 best_rec = -1;
@@ -970,7 +1030,7 @@ __device__ __forceinline__ void trace_mesh(const DScene& sc, const IO& io, const
                     if (best_rec >= 0)
                     {
                         // (t, shape, triangle record); the fourth word (mesh shape | sp) stays as the top pass wrote it
-                        float* h = reinterpret_cast<float*>(sb.hit + tag);
+                        float* h = reinterpret_cast<float*>(split_rec(sb, tag) + 2);
                         *reinterpret_cast<float2*>(h) = make_float2(best, __int_as_float((int32_t)mesh_shape));
                         h[2] = __int_as_float(best_rec);
                     }
@@ -1055,6 +1115,8 @@ __device__ __forceinline__ void trace_mesh_pair(const DScene& sc, const IO& io, 
     constexpr int kSmemStack = CAP > 32 ? RT_PAIR_SMEM_STACK_DEEP : RT_PAIR_SMEM_STACK;
     static_assert(kSmemStack >= 1 && kSmemStack < CAP, "shared-memory stack slots");
     __shared__ float4 sm_stack[kSmemStack * RT_BLOCK];
+    __shared__ uint32_t sm_stage_q[(RT_BLOCK / 32) * RT_STAGE_Q];
+    WarpStage out_stage = { sm_stage_q + (threadIdx.x >> 5) * RT_STAGE_Q, 0u };
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t lt_mask = (1u << lane) - 1;
     const uint32_t n = *ps.in_count;
@@ -1109,7 +1171,7 @@ __device__ __forceinline__ void trace_mesh_pair(const DScene& sc, const IO& io, 
                 have_cur = false;
                 park2_count = 0;
                 tag = ps.in_queue[j];
-                float4 mo = sb.mesh_o[tag], md = sb.mesh_d[tag];
+                float4 mo = split_rec(sb, tag)[0], md = split_rec(sb, tag)[1];
                 tmax = mo.w;            // (any hit)
                 best = mo.w;            // (closest hit)
                 best_rec = -1;
@@ -1329,7 +1391,7 @@ __device__ __forceinline__ void trace_mesh_pair(const DScene& sc, const IO& io, 
                     if (best_rec >= 0)
                     {
                         // (t, shape, triangle record); the fourth word (mesh shape | sp) stays as the top pass wrote it
-                        float* h = reinterpret_cast<float*>(sb.hit + tag);
+                        float* h = reinterpret_cast<float*>(split_rec(sb, tag) + 2);
                         *reinterpret_cast<float2*>(h) = make_float2(best, __int_as_float((int32_t)mesh_shape));
                         h[2] = __int_as_float(best_rec);
                     }
@@ -1337,9 +1399,10 @@ __device__ __forceinline__ void trace_mesh_pair(const DScene& sc, const IO& io, 
                 }
                 active = false;
             }
-            warp_queue_push(ps.out_queue, ps.out_count, resume, tag);
+            warp_stage_push(out_stage, ps.out_queue, ps.out_count, resume, tag);
         }
     }
+    warp_stage_flush(out_stage, ps.out_queue, ps.out_count);
 #undef RT_PAIR_PUT
 #undef RT_PAIR_GET
 }
