@@ -184,7 +184,9 @@ class _HostLibs:
         self.fixtures = fixtures_lib
 
     def __getattr__(self, name):
-        for lib in (self.__dict__["fixtures"], self.__dict__["product"]):
+        # the product library first: dlsym on the fixtures handle also finds the product's symbols (a
+        # dependency), and would hand back a function object without the argument types declared below
+        for lib in (self.__dict__["product"], self.__dict__["fixtures"]):
             try:
                 return getattr(lib, name)
             except AttributeError:

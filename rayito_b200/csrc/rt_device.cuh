@@ -73,7 +73,8 @@ struct DNode
 
 struct DShapeMem         // 32 bytes in HBM, two 128-bit loads
 {
-    uint32_t type_kind;  // RT_SHAPE_* | RT_XF_* << 8 | (offset in the per-sample transform cache + 1, 0 = not cached) << 16
+    uint32_t type_kind;  // RT_SHAPE_* | RT_XF_* << 8 | (traversal kernels may read the cache entry) << 10
+                         // | (offset in the per-sample transform cache + 1, 0 = not cached) << 16
     uint32_t geom, xform, material;
     int32_t light;
     float tx, ty, tz;    // translation of a STATIC transform
@@ -85,6 +86,7 @@ struct DShape            // the same, decoded into registers (load_shape)
     int32_t light;
     uint32_t xkind;
     uint32_t cache_slot; // offset in the per-sample transform cache + 1, 0 = evaluate directly
+    uint32_t trav_cached;// the traversal kernels read the entry too (shapes that are small in the scene)
     float tx, ty, tz;
 };
 

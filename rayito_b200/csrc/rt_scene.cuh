@@ -422,25 +422,28 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
     std::vector<uint4> anim;
     std::vector<uint32_t> xf_cache_slot(desc->num_xforms, 0u);      // row offset + 1
     uint32_t anim_stride = 0;
-    // Which transforms are worth a cache entry (same-session A/Bs, profiles/README.md round 2):
+    // Which transforms get a cache entry, and who reads it (same-session A/Bs, profiles/README.md round 2):
     //   * interpolated ROTATIONS only -- an interpolated translation is a key search and three lerps, cheaper to
     //     redo than to fetch (C4: rotations +2.5 %, everything +1.6 %);
-    //   * only shapes that are SMALL in the scene (top-level box under a quarter of the root box's area): a shape
-    //     that fills the scene is entered by most rays of a warp, so its in-place evaluation already runs with the
-    //     warp converged and the cache only adds memory traffic (the 10 M-triangle mesh of C5: -2 %);
-    //   * at most four of them: every entry is evaluated for every sample whether a ray of that sample meets the
-    //     shape or not (scene 2, twenty animated shapes, everything cached: -20 %).
+    //   * only when the scene has at most four of them: every entry is evaluated for every sample whether a ray of
+    //     that sample meets the shape or not (scene 2, ten tumbling boxes: -9 %; everything cached -20 %);
+    //   * the shading kernels read every entry (normal of the hit, light pdfs); the TRAVERSAL kernels read only the
+    //     entries of shapes that are small in the scene (top-level box under a quarter of the root box's area).  A
+    //     shape that fills the scene is entered by most rays of a warp, so its in-place evaluation already runs
+    //     with the warp converged and a fetch only adds memory traffic (the 10 M-triangle mesh of C5: traversal
+    //     -1.5 % with the fetch, frame +2 % from the shading side).
     // RAYITO_B200_XFORM_CACHE = none | auto (default) | rotations | all overrides the choice (A/B runs).
     const char* cache_env = std::getenv("RAYITO_B200_XFORM_CACHE");
     const int cache_mode = cache_env == NULL ? 3 : cache_env[0] == 'n' ? 0 : cache_env[0] == 'r' ? 1 : cache_env[0] == 'a' && cache_env[1] == 'l' ? 2 : 3;
-    std::vector<float> xf_area_ratio(desc->num_xforms, 0.0f);      // largest top-level box of a shape using the transform / root box
-    if (cache_mode == 3 && desc->num_top_nodes > 0)
+    std::vector<float> xf_area_ratio(desc->num_xforms, 2.0f);      // largest top-level box of a shape using the transform / root box
+    if (desc->num_top_nodes > 0)
     {
         auto half_area = [](const RtBvhNode& n) {
             float dx = n.bbox_max[0] - n.bbox_min[0], dy = n.bbox_max[1] - n.bbox_min[1], dz = n.bbox_max[2] - n.bbox_min[2];
             return dx * dy + dy * dz + dz * dx;
         };
         const float root = half_area(desc->top_nodes[0]);
+        std::vector<float> seen(desc->num_xforms, -1.0f);
         for (uint32_t i = 0; i < desc->num_top_nodes; ++i)
         {
             const RtBvhNode& n = desc->top_nodes[i];
@@ -450,11 +453,19 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
             if (xf >= desc->num_xforms)
                 continue;           // (reported below)
             const float ratio = root > 0.0f ? half_area(n) / root : 1.0f;
-            if (ratio > xf_area_ratio[xf]) xf_area_ratio[xf] = ratio;
+            if (ratio > seen[xf]) seen[xf] = ratio;
         }
+        for (uint32_t i = 0; i < desc->num_xforms; ++i)
+            if (seen[i] >= 0.0f) xf_area_ratio[i] = seen[i];
     }
+    uint32_t num_rotating = 0;
+    for (uint32_t i = 0; i < desc->num_xforms; ++i)
+        if (desc->xforms[i].num_keys >= 2 && i != desc->set_xform && xf_kind[i] != RT_XF_TRANSLATE)
+            ++num_rotating;
+    std::vector<uint32_t> xf_trav_cached(desc->num_xforms, 0u);     // traversal kernels may read the entry
     uint32_t cached_entries = 0;
-    if (desc->semantics == RT_SEMANTICS_STAGE7 && cache_mode != 0 && !(cache_mode == 3 && desc->num_top_nodes == 0))
+    (void)cached_entries;
+    if (desc->semantics == RT_SEMANTICS_STAGE7 && cache_mode != 0 && !(cache_mode == 3 && num_rotating > 4))
     {
         for (int pass = 0; pass < 2; ++pass)        // wide entries first (aligned), then the one-float4 translations
             for (uint32_t i = 0; i < desc->num_xforms; ++i)
@@ -464,8 +475,7 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
                 const bool narrow = xf_kind[i] == RT_XF_TRANSLATE;
                 if (narrow != (pass == 1) || (narrow && cache_mode != 2))
                     continue;
-                if (cache_mode == 3 && (xf_area_ratio[i] <= 0.0f || xf_area_ratio[i] >= 0.25f || cached_entries >= 4))
-                    continue;
+                xf_trav_cached[i] = (cache_mode != 3 || xf_area_ratio[i] < 0.25f) ? 1u : 0u;
                 ++cached_entries;
                 uint32_t width = narrow ? 1u : xf_kind[i] == RT_XF_RIGID ? 2u : 3u;
                 if (!narrow && (anim_stride & 1u))
@@ -479,6 +489,7 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
         {
             anim.clear();
             std::fill(xf_cache_slot.begin(), xf_cache_slot.end(), 0u);
+            std::fill(xf_trav_cached.begin(), xf_trav_cached.end(), 0u);
             anim_stride = 0;
         }
     }
@@ -499,7 +510,7 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
             return rt_fail(RT_ERR_ARG, "shape light index out of range");
         DShapeMem d;
         std::memset(&d, 0, sizeof(d));
-        d.type_kind = s.type | (xf_kind[s.xform] << 8) | (xf_cache_slot[s.xform] << 16);
+        d.type_kind = s.type | (xf_kind[s.xform] << 8) | (xf_trav_cached[s.xform] << 10) | (xf_cache_slot[s.xform] << 16);
         d.geom = s.geom; d.xform = s.xform; d.material = s.material; d.light = s.light;
         if (xf_kind[s.xform] == RT_XF_STATIC && desc->xforms[s.xform].num_keys == 1)
         {

@@ -49,6 +49,10 @@
 #endif
 
 #define RT_SPLIT_TOPCAP 8        /* top-level stack entries a suspended ray can carry */
+#define RT_SPLIT_DIRECT 0x80000000u
+#ifndef RT_MESH_DIRECT_FINISH
+#define RT_MESH_DIRECT_FINISH 1     /* 0: every suspended ray goes through a resume pass (A/B runs) */
+#endif
 #define RT_SPLIT_MAX_MESHES 12   /* more mesh shapes than this: use the unified kernel */
 
 // Per-slot suspended-ray state (slot = path sample index / ray index).  Kept small and packed: one
@@ -58,7 +62,8 @@
 // only the second.  The set-local ray itself is NOT saved: a resume pass recomputes it from the
 // stage's own ray record (same inputs, same bits).
 //   rec[4 * slot + 0]  mesh-local origin xyz (computed by the top pass at mesh entry), m_t (closest hit) or tMax (any hit)
-//   rec[4 * slot + 1]  mesh-local direction xyz, mesh shape to enter
+//   rec[4 * slot + 1]  mesh-local direction xyz, mesh shape to enter | RT_SPLIT_DIRECT when no top-level work is pending
+//                      (the mesh pass then finishes the ray itself instead of queueing it for a resume pass)
 //   rec[4 * slot + 2]  m_t, winner shape, winner triangle record, (mesh shape to enter | sp << 24)
 //   rec[4 * slot + 3]  top-level stack entry 0: node, t0, t1, -
 //   stack[(RT_SPLIT_TOPCAP - 1) * slot + k - 1]   top-level stack entries k >= 1
@@ -136,8 +141,15 @@ __device__ __forceinline__ void warp_stage_flush(WarpStage& st, uint32_t* queue,
     __syncwarp();
     st.count = 0;
 }
+#ifndef RT_STAGED_PUSH
+#define RT_STAGED_PUSH 1        /* 0: one atomic per call (A/B runs) */
+#endif
 __device__ __forceinline__ void warp_stage_push(WarpStage& st, uint32_t* queue, uint32_t* counter, bool want, uint32_t value)
 {
+#if !RT_STAGED_PUSH
+    warp_queue_push(queue, counter, want, value);
+    return;
+#endif
     const uint32_t mask = __ballot_sync(0xffffffffu, want);
     if (mask == 0)
         return;
@@ -213,7 +225,7 @@ __device__ __forceinline__ void trace_top(const DScene& sc, const IO& io, const 
                     {
                         uint32_t sid = sc.num_finite + k;
                         DShape sh = load_shape(sc, sid);
-                        TRS trs = shape_xform(sc, sh, time, io.xf_row(tag));
+                        TRS trs = shape_xform_trav(sc, sh, time, io.xf_row(tag));
                         V3 lo = to_local_point(trs, r0.o);
                         V3 ld = to_local_vector(trs, r0.d);
                         count_xform<COUNT>(sc, sh.xform, wc);
@@ -347,7 +359,7 @@ __device__ __forceinline__ void trace_top(const DScene& sc, const IO& io, const 
                 DMesh m = sc.meshes[sh.geom];
                 if (m.num_nodes > 0)
                 {
-                    TRS trs = shape_xform(sc, sh, time, io.xf_row(tag));
+                    TRS trs = shape_xform_trav(sc, sh, time, io.xf_row(tag));
                     count_xform<COUNT>(sc, sh.xform, wc);
                     LocalRay rm;
                     rm.o = to_local_point(trs, r0.o);
@@ -369,13 +381,13 @@ __device__ __forceinline__ void trace_top(const DScene& sc, const IO& io, const 
                         suspend = true;
                         float4* rec = split_rec(sb, tag);
                         rec[0] = make_float4(rm.o.x, rm.o.y, rm.o.z, ANY ? tmax : res.t);
-                        rec[1] = make_float4(rm.d.x, rm.d.y, rm.d.z, __uint_as_float(park_shape));
+                        rec[1] = make_float4(rm.d.x, rm.d.y, rm.d.z, __uint_as_float(park_shape | (sp == 0 && RT_MESH_DIRECT_FINISH ? RT_SPLIT_DIRECT : 0u)));
                     }
                 }
             }
             else
             {
-                TRS trs = shape_xform(sc, sh, time, io.xf_row(tag));
+                TRS trs = shape_xform_trav(sc, sh, time, io.xf_row(tag));
                 count_xform<COUNT>(sc, sh.xform, wc);
                 V3 lo = to_local_point(trs, r0.o);
                 V3 ld = to_local_vector(trs, r0.d);
@@ -550,7 +562,7 @@ __device__ __forceinline__ void trace_top_static(const DScene& sc, const IO& io,
             {
                 uint32_t sid = sc.num_finite + k;
                 DShape sh = load_shape(sc, sid);
-                TRS trs = shape_xform(sc, sh, time, io.xf_row(tag));
+                TRS trs = shape_xform_trav(sc, sh, time, io.xf_row(tag));
                 V3 lo = to_local_point(trs, r0.o);
                 V3 ld = to_local_vector(trs, r0.d);
                 count_xform<COUNT>(sc, sh.xform, wc);
@@ -638,7 +650,7 @@ __device__ __forceinline__ void trace_top_static(const DScene& sc, const IO& io,
                     DMesh m = sc.meshes[sh.geom];
                     if (here && m.num_nodes > 0)
                     {
-                        TRS trs = shape_xform(sc, sh, time, io.xf_row(tag));
+                        TRS trs = shape_xform_trav(sc, sh, time, io.xf_row(tag));
                         count_xform<COUNT>(sc, sh.xform, wc);
                         LocalRay rm;
                         rm.o = to_local_point(trs, r0.o);
@@ -660,7 +672,7 @@ __device__ __forceinline__ void trace_top_static(const DScene& sc, const IO& io,
                             suspend = true;
                             float4* rec = split_rec(sb, tag);
                             rec[0] = make_float4(rm.o.x, rm.o.y, rm.o.z, ANY ? tmax : res.t);
-                            rec[1] = make_float4(rm.d.x, rm.d.y, rm.d.z, __uint_as_float(shape_id));
+
                             // the explicit stack of the dynamic pass at this point: pending far
                             // children whose parents passed, with the ranges those parents pushed
                             const uint4 p0 = __ldg(reinterpret_cast<const uint4*>(steps + s) + 1);
@@ -688,6 +700,7 @@ __device__ __forceinline__ void trace_top_static(const DScene& sc, const IO& io,
                             rec[2] = make_float4(res.t, __int_as_float(res.shape), __int_as_float(res.tri_rec),
                                                  __uint_as_float(shape_id | (sp << 24)));
                             rec[3] = entry0;        // (always: the 64-byte record goes out as whole sectors)
+                            rec[1] = make_float4(rm.d.x, rm.d.y, rm.d.z, __uint_as_float(shape_id | (sp == 0 && RT_MESH_DIRECT_FINISH ? RT_SPLIT_DIRECT : 0u)));
                             open = false;
                             suspended = true;
                         }
@@ -695,7 +708,7 @@ __device__ __forceinline__ void trace_top_static(const DScene& sc, const IO& io,
                 }
                 else if (here)
                 {
-                    TRS trs = shape_xform(sc, sh, time, io.xf_row(tag));
+                    TRS trs = shape_xform_trav(sc, sh, time, io.xf_row(tag));
                     count_xform<COUNT>(sc, sh.xform, wc);
                     V3 lo = to_local_point(trs, r0.o);
                     V3 ld = to_local_vector(trs, r0.d);
@@ -1135,6 +1148,7 @@ __device__ __forceinline__ void trace_mesh_pair(const DScene& sc, const IO& io, 
     int32_t best_rec = -1;       // triangle record accepted in this mesh, if any
     bool any_hit = false;
     uint32_t mesh_shape = 0;
+    bool direct = false;         // no top-level work is pending behind this mesh: finish the ray here
     const DNode* mesh_nodes = sc.mesh_nodes;
     int sp = 0;
     bool have_cur = false;       // cur_*: an interior node whose box test passed, waiting to be expanded
@@ -1177,6 +1191,7 @@ __device__ __forceinline__ void trace_mesh_pair(const DScene& sc, const IO& io, 
                 best_rec = -1;
                 any_hit = false;
                 mesh_shape = __float_as_uint(md.w) & 0xffffffu;
+                direct = (__float_as_uint(md.w) & RT_SPLIT_DIRECT) != 0u;
                 DShape sh = load_shape(sc, mesh_shape);
                 DMesh m = sc.meshes[sh.geom];
                 // the top pass already warped the ray into mesh-local space and found that it enters
@@ -1385,6 +1400,26 @@ __device__ __forceinline__ void trace_mesh_pair(const DScene& sc, const IO& io, 
                     WaveResult r;
                     r.t = tmax; r.shape = -1; r.tri_rec = -1; r.any_hit = true;
                     io.store(tag, r);
+                }
+                else if (direct)
+                {
+                    // this mesh was the last thing the top-level walk had to look at: the ray is finished
+                    // (a shadow ray that found nothing has nothing to report)
+                    if (!ANY)
+                    {
+                        WaveResult r;
+                        r.any_hit = false;
+                        if (best_rec >= 0)
+                        {
+                            r.t = best; r.shape = (int32_t)mesh_shape; r.tri_rec = best_rec;
+                        }
+                        else
+                        {
+                            const float4 h = split_rec(sb, tag)[2];
+                            r.t = h.x; r.shape = __float_as_int(h.y); r.tri_rec = __float_as_int(h.z);
+                        }
+                        io.store(tag, r);
+                    }
                 }
                 else
                 {

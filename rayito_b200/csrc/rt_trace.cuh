@@ -91,7 +91,7 @@ __device__ __forceinline__ DShape load_shape(const DScene& sc, uint32_t i)
     const uint4* p = reinterpret_cast<const uint4*>(sc.shapes + i);
     uint4 a = __ldg(p);
     uint4 b = __ldg(p + 1);
-    s.type = a.x & 0xffu; s.xkind = (a.x >> 8) & 0x3u; s.cache_slot = a.x >> 16;
+    s.type = a.x & 0xffu; s.xkind = (a.x >> 8) & 0x3u; s.trav_cached = (a.x >> 10) & 1u; s.cache_slot = a.x >> 16;
     s.geom = a.y; s.xform = a.z; s.material = a.w;
     s.light = (int32_t)b.x;
     s.tx = __uint_as_float(b.y); s.ty = __uint_as_float(b.z); s.tz = __uint_as_float(b.w);
@@ -129,6 +129,12 @@ __device__ __forceinline__ void count_xform(const DScene& sc, uint32_t xform, Wo
         wc.xform_keyed += nk >= 1u ? 1u : 0u;
         wc.xform_pairs += nk >= 2u ? 1u : 0u;
     }
+}
+
+// The same for the traversal kernels, which read the cache only for shapes marked for it (rt_scene.cuh)
+__device__ __forceinline__ TRS shape_xform_trav(const DScene& sc, const DShape& sh, float time, const float4* row)
+{
+    return shape_xform(sc, sh, time, sh.trav_cached ? row : nullptr);
 }
 
 // Shading inputs of the winning hit: Intersection::m_normal and m_colorModifier

@@ -115,7 +115,7 @@ __device__ __forceinline__ void trace_wave(const DScene& sc, const IO& io, uint3
                     {
                         uint32_t sid = sc.num_finite + k;
                         DShape sh = load_shape(sc, sid);
-                        TRS trs = shape_xform(sc, sh, time, io.xf_row(tag));
+                        TRS trs = shape_xform_trav(sc, sh, time, io.xf_row(tag));
                         V3 lo = to_local_point(trs, r0.o);
                         V3 ld = to_local_vector(trs, r0.d);
                         count_xform<COUNT>(sc, sh.xform, wc);
@@ -246,7 +246,7 @@ __device__ __forceinline__ void trace_wave(const DScene& sc, const IO& io, uint3
         if (do_shape && parked == PARK_SHAPE)
         {
             DShape sh = load_shape(sc, park_word);
-            TRS trs = shape_xform(sc, sh, time, io.xf_row(tag));
+            TRS trs = shape_xform_trav(sc, sh, time, io.xf_row(tag));
             count_xform<COUNT>(sc, sh.xform, wc);
             V3 lo = to_local_point(trs, r0.o);
             V3 ld = to_local_vector(trs, r0.d);
