@@ -185,6 +185,7 @@ struct DScene
     const uint32_t* lights;      // shape index per light
     const DTopStep* top_walk;    // [8 octants][top_walk_steps], NULL if the top level is too deep to tabulate
     uint32_t top_walk_steps;
+    uint32_t top_walk_levels;    // deepest node of the walk + 2: rows of the per-lane range table
     // per-sample transform cache: the animated transforms in row order (xform index, row offset, kind)
     const uint4* anim;           // x = xform, y = row offset (float4), z = RT_XF_*
     uint32_t num_anim;

@@ -528,19 +528,22 @@ template <bool ANY, bool COUNT, class IO>
 __global__ void __launch_bounds__(RT_BLOCK, RT_STATIC_MINBLOCKS)
 k_split_top_static(const __grid_constant__ DScene sc, const IO io, const SplitBufs sb, const SplitPass ps, uint64_t* totals, int count_slot)
 {
-    __shared__ float lane_t0[(RT_WALK_MAX_DEPTH + 1) * RT_BLOCK];
-    __shared__ float lane_t1[(RT_WALK_MAX_DEPTH + 1) * RT_BLOCK];
+    // per lane and per depth of the walk, the range a node's children inherit: (walk depth + 2) levels, sized by
+    // the launch (the tables allow RT_WALK_MAX_DEPTH, the Stage 7 scene needs 4: the shared memory a block does not
+    // take stays L1 cache, and this pass lives on L1 hits of the top-level nodes and shape records)
+    extern __shared__ float lane_ranges[];
+    float* lane_t0 = lane_ranges;
+    float* lane_t1 = lane_ranges + (sc.top_walk_levels) * RT_BLOCK;
 #if RT_STATIC_PREFETCH
     __shared__ float4 stage_rec[2 * 2 * RT_BLOCK];       // [stage][record a / b][thread]
 #else
     float4* stage_rec = NULL;
 #endif
-    __shared__ uint32_t stage_q[(RT_BLOCK / 32) * RT_STAGE_Q];
     split_zero(ps);
     if (count_slot >= 0 && blockIdx.x == 0 && threadIdx.x == 0)
         atomicAdd(reinterpret_cast<unsigned long long*>(totals + count_slot), (unsigned long long)io.count());
     WorkCount wc = RT_WORK_ZERO;
-    trace_top_static<ANY, COUNT>(sc, io, sb, ps, wc, lane_t0, lane_t1, stage_rec, stage_q);
+    trace_top_static<ANY, COUNT>(sc, io, sb, ps, wc, lane_t0, lane_t1, stage_rec);
     if (COUNT)
         flush_work_counters(wc, totals);
 }
@@ -707,8 +710,97 @@ k_light_select(const __grid_constant__ RenderCtx c, int cur, uint32_t bounce, ui
     }
 }
 
-// One light sample of the direct-lighting loop (:336-422): produces at most one
-// shadow ray and one BRDF-MIS probe per lit path
+// One light sample of the direct-lighting loop (:336-422) for lit path sample i: produces at most one
+// shadow ray and one BRDF-MIS probe.  LT / BR >= 0: the light's shape type / the surface's BRDF are
+// known at compile time (the lit paths are regrouped by (light, BRDF kind) anyway, see k_light_select), so
+// one launch per bin runs a kernel that holds only that light's sampling and that BRDF's code -- the
+// all-in-one kernel is 64 KB of SASS and spent a quarter of its stall samples waiting for instructions
+// (profiles/README.md, round 2).
+template <int LT, int BR>
+__device__ __forceinline__ void light_sample_one(const RenderCtx& c, uint32_t bounce, uint32_t lsi, uint32_t i)
+{
+    uint32_t p = i / c.spp, psi = i % c.spp;
+    float4 pt = c.pos_wo[2 * (size_t)i], wm = c.pos_wo[2 * (size_t)i + 1], h1 = c.hit01[2 * (size_t)i + 1];
+    V3 position = xyz(pt), outgoing = xyz(wm), normal = xyz(h1);
+    float time = pt.w, cm = h1.w;
+    RtMaterial mat = c.sc.materials[__float_as_uint(wm.w)];
+    if (BR >= 0) mat.brdf = (uint32_t)BR;          // the bin holds this BRDF only: the other branches compile away
+    Color3 mc = mkc(mat.color[0], mat.color[1], mat.color[2]);
+
+    uint32_t n1 = c.ps * c.ls * c.ps * c.ls, n2 = c.ps * c.ls;
+    const uint32_t* pp = c.perms + (size_t)(5 * bounce) * c.num_pixels + p;
+    uint32_t perm_elem = pp[(size_t)2 * c.num_pixels];
+    uint32_t perm_light = pp[(size_t)3 * c.num_pixels];
+    uint32_t perm_brdf = pp[(size_t)4 * c.num_pixels];
+
+    uint32_t idx, light_index;
+    light_choice(c, bounce, lsi, p, psi, idx, light_index);
+    if (c.sc.stage6)
+    {
+        // The Stage 6 reference draws these samples from one serial, data-dependent Rng,
+        // which has no parallel equivalent; the counter-based stream stands in (same
+        // strata, decorrelated per light), so Stage 6 images match statistically, not bitwise.
+        uint32_t salt = (light_index + 1u) * 0x9e3779b9u;
+        salt ^= salt >> 15; salt *= 0x85ebca6bu; salt ^= salt >> 13;
+        perm_elem ^= salt; perm_light ^= salt * 0x9e3779b9u; perm_brdf ^= salt * 0x85ebca6bu;
+    }
+    uint32_t light_shape = c.sc.lights[light_index];
+    DShape lsh = load_shape(c.sc, light_shape);
+    if (LT >= 0) lsh.type = (uint32_t)LT;          // every light of the bin is of this kind
+    RtMaterial lmat = c.sc.materials[lsh.material];
+    Color3 emitted = mkc(lmat.emittance[0], lmat.emittance[1], lmat.emittance[2]);
+
+    float lsu, lsv;
+    cmj2d(idx, n2, n2, perm_light, lsu, lsv);
+    float leu = cmj1d(idx, n1, perm_elem);
+    V3 lpos, lnrm;
+    float lpdf;
+    light_sample(c.sc, lsh, position, time, lsu, lsv, leu, lpos, lnrm, lpdf, xf_row(c, i));
+
+    float4 shl = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    float4 shd = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (lpdf > 0.0f)
+    {
+        V3 li = position - lpos;
+        float dist;
+        li = normalized3(li, &dist);
+        float bpdf = 0.0f;
+        float bres = brdf_evaluate(mat.brdf, mat.exponent, li, outgoing, normal, bpdf);
+        if (bres > 0.0f && bpdf > 0.0f)
+        {
+            V3 sd = -li;
+            float mis = power_heuristic(lpdf, bpdf);
+            Color3 L = emitted * mkc(cm, cm, cm) * mc * bres * fabsf(dot3(sd, normal)) * mis / (lpdf * 1.0f);
+            shd = make_float4(sd.x, sd.y, sd.z, dist - RT_RAY_TMIN);
+            shl = make_float4(L.r, L.g, L.b, 1.0f);
+            bq_push(c.q_shadow, c.ctl + CTL_SHADOW, c.qcap, dir_octant(sd), i);
+        }
+    }
+
+    // BRDF sample towards (hopefully) the same light (:410-422)
+    float bsu, bsv;
+    cmj2d(idx, n2, n2, perm_brdf, bsu, bsv);
+    V3 bi;
+    float bpdf = 0.0f;
+    float bres = brdf_sample(mat.brdf, mat.exponent, bi, outgoing, normal, bsu, bsv, bpdf);
+    float4 md = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    float4 mp = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (bpdf > 0.0f && bres > 0.0f)
+    {
+        V3 pd = -bi;
+        Color3 P = emitted * mkc(cm, cm, cm) * mc * bres * fabsf(dot3(pd, normal));
+        md = make_float4(pd.x, pd.y, pd.z, bpdf);
+        mp = make_float4(P.r, P.g, P.b, __uint_as_float(light_shape));
+        bq_push(c.q_mis, c.ctl + CTL_MIS, c.qcap, dir_octant(pd), i);
+    }
+    // the whole 64-byte ray record and the whole 32-byte term record, every time: full sectors,
+    // no read-modify-write
+    float4* rec = c.lrec + 4 * (size_t)i;
+    rec[0] = shd; rec[1] = pt; rec[2] = md; rec[3] = pt;
+    float4* term = c.lterm + 2 * (size_t)i;
+    term[0] = shl; term[1] = mp;
+}
+
 __global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_MINBLOCKS)
 k_light_sample(const __grid_constant__ RenderCtx c, int cur, uint32_t bounce, uint32_t lsi)
 {
@@ -717,87 +809,21 @@ k_light_sample(const __grid_constant__ RenderCtx c, int cur, uint32_t bounce, ui
     RT_GRID_STRIDE(j, n)
     {
         if (j < n)
-        {
-            const uint32_t i = lit.at(j);
-            uint32_t p = i / c.spp, psi = i % c.spp;
-            float4 pt = c.pos_wo[2 * (size_t)i], wm = c.pos_wo[2 * (size_t)i + 1], h1 = c.hit01[2 * (size_t)i + 1];
-            V3 position = xyz(pt), outgoing = xyz(wm), normal = xyz(h1);
-            float time = pt.w, cm = h1.w;
-            RtMaterial mat = c.sc.materials[__float_as_uint(wm.w)];
-            Color3 mc = mkc(mat.color[0], mat.color[1], mat.color[2]);
+            light_sample_one<-1, -1>(c, bounce, lsi, lit.at(j));
+    }
+}
 
-            uint32_t n1 = c.ps * c.ls * c.ps * c.ls, n2 = c.ps * c.ls;
-            const uint32_t* pp = c.perms + (size_t)(5 * bounce) * c.num_pixels + p;
-            uint32_t perm_elem = pp[(size_t)2 * c.num_pixels];
-            uint32_t perm_light = pp[(size_t)3 * c.num_pixels];
-            uint32_t perm_brdf = pp[(size_t)4 * c.num_pixels];
-
-            uint32_t idx, light_index;
-            light_choice(c, bounce, lsi, p, psi, idx, light_index);
-            if (c.sc.stage6)
-            {
-                // The Stage 6 reference draws these samples from one serial, data-dependent Rng,
-                // which has no parallel equivalent; the counter-based stream stands in (same
-                // strata, decorrelated per light), so Stage 6 images match statistically, not bitwise.
-                uint32_t salt = (light_index + 1u) * 0x9e3779b9u;
-                salt ^= salt >> 15; salt *= 0x85ebca6bu; salt ^= salt >> 13;
-                perm_elem ^= salt; perm_light ^= salt * 0x9e3779b9u; perm_brdf ^= salt * 0x85ebca6bu;
-            }
-            uint32_t light_shape = c.sc.lights[light_index];
-            DShape lsh = load_shape(c.sc, light_shape);
-            RtMaterial lmat = c.sc.materials[lsh.material];
-            Color3 emitted = mkc(lmat.emittance[0], lmat.emittance[1], lmat.emittance[2]);
-
-            float lsu, lsv;
-            cmj2d(idx, n2, n2, perm_light, lsu, lsv);
-            float leu = cmj1d(idx, n1, perm_elem);
-            V3 lpos, lnrm;
-            float lpdf;
-            light_sample(c.sc, lsh, position, time, lsu, lsv, leu, lpos, lnrm, lpdf, xf_row(c, i));
-
-            float4 shl = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            float4 shd = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            if (lpdf > 0.0f)
-            {
-                V3 li = position - lpos;
-                float dist;
-                li = normalized3(li, &dist);
-                float bpdf = 0.0f;
-                float bres = brdf_evaluate(mat.brdf, mat.exponent, li, outgoing, normal, bpdf);
-                if (bres > 0.0f && bpdf > 0.0f)
-                {
-                    V3 sd = -li;
-                    float mis = power_heuristic(lpdf, bpdf);
-                    Color3 L = emitted * mkc(cm, cm, cm) * mc * bres * fabsf(dot3(sd, normal)) * mis / (lpdf * 1.0f);
-                    shd = make_float4(sd.x, sd.y, sd.z, dist - RT_RAY_TMIN);
-                    shl = make_float4(L.r, L.g, L.b, 1.0f);
-                    bq_push(c.q_shadow, c.ctl + CTL_SHADOW, c.qcap, dir_octant(sd), i);
-                }
-            }
-
-            // BRDF sample towards (hopefully) the same light (:410-422)
-            float bsu, bsv;
-            cmj2d(idx, n2, n2, perm_brdf, bsu, bsv);
-            V3 bi;
-            float bpdf = 0.0f;
-            float bres = brdf_sample(mat.brdf, mat.exponent, bi, outgoing, normal, bsu, bsv, bpdf);
-            float4 md = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            float4 mp = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            if (bpdf > 0.0f && bres > 0.0f)
-            {
-                V3 pd = -bi;
-                Color3 P = emitted * mkc(cm, cm, cm) * mc * bres * fabsf(dot3(pd, normal));
-                md = make_float4(pd.x, pd.y, pd.z, bpdf);
-                mp = make_float4(P.r, P.g, P.b, __uint_as_float(light_shape));
-                bq_push(c.q_mis, c.ctl + CTL_MIS, c.qcap, dir_octant(pd), i);
-            }
-            // the whole 64-byte ray record and the whole 32-byte term record, every time: full sectors,
-            // no read-modify-write
-            float4* rec = c.lrec + 4 * (size_t)i;
-            rec[0] = shd; rec[1] = pt; rec[2] = md; rec[3] = pt;
-            float4* term = c.lterm + 2 * (size_t)i;
-            term[0] = shl; term[1] = mp;
-        }
+// The same for ONE bin of the regrouped queue
+template <int LT, int BR>
+__global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_MINBLOCKS)
+k_light_sample_bin(const __grid_constant__ RenderCtx c, int cur, uint32_t bounce, uint32_t lsi, uint32_t bin)
+{
+    const uint32_t n = c.ctl[CTL_LITB + bin];
+    const uint32_t* items = c.q_path[cur] + (size_t)bin * c.qcap;
+    RT_GRID_STRIDE(j, n)
+    {
+        if (j < n)
+            light_sample_one<LT, BR>(c, bounce, lsi, items[j]);
     }
 }
 
@@ -1271,7 +1297,8 @@ static void rt_launch_split_stage(RtScene* s, const RenderCtx& c, const IO& io,
 #define RT_STATIC_TOP_CLOSEST 1
 #endif
     if (c.sc.top_walk_steps > 0 && !s->dynamic_top && (ANY || RT_STATIC_TOP_CLOSEST))
-        k_split_top_static<ANY, COUNT, IO><<<grid, RT_BLOCK, 0, st>>>(c.sc, io, c.split, p, c.totals, count_slot);
+        k_split_top_static<ANY, COUNT, IO><<<grid, RT_BLOCK, 2 * c.sc.top_walk_levels * RT_BLOCK * sizeof(float), st>>>(
+            c.sc, io, c.split, p, c.totals, count_slot);
     else
         k_split_top<ANY, COUNT, true, IO><<<grid, RT_BLOCK, 0, st>>>(c.sc, io, c.split, p, c.totals, count_slot);
     launches += 1;
@@ -1312,6 +1339,52 @@ __global__ void k_stage_prologue(const __grid_constant__ RenderCtx c, int cur)
     for (int b = 0; b < RT_SBINS; ++b) c.ctl[CTL_SHADE + b] = 0;
     for (int b = 0; b < RT_LBINS; ++b) c.ctl[CTL_LITB + b] = 0;      // k_shade regroups the lit paths for light sample 0
     c.ctl[CTL_LIT] = 0;
+}
+
+// k_light_sample, one specialised launch per (light, BRDF kind) bin when the scene allows it
+#ifndef RT_LIGHT_SPECIALISE
+#define RT_LIGHT_SPECIALISE 1
+#endif
+template <int LT>
+static void rt_launch_light_bin(const RenderCtx& c, int cur, uint32_t bounce, uint32_t lsi, uint32_t bin, bool glossy,
+                                unsigned grid, cudaStream_t st)
+{
+    if (glossy) k_light_sample_bin<LT, RT_BRDF_GLOSSY><<<grid, RT_BLOCK, 0, st>>>(c, cur, bounce, lsi, bin);
+    else        k_light_sample_bin<LT, RT_BRDF_LAMBERT><<<grid, RT_BLOCK, 0, st>>>(c, cur, bounce, lsi, bin);
+}
+static void rt_launch_light_sample(RtScene* s, const RenderCtx& c, int cur, uint32_t bounce, uint32_t lsi, unsigned grid,
+                                   cudaStream_t st, uint64_t& launches)
+{
+    // bin = (light index & 3) | (glossy ? 4 : 0); a bin's light kind is known when every light that maps to it is
+    // of one kind (always, with at most four lights)
+    const size_t nl = s->light_types.size();
+    bool uniform = RT_LIGHT_SPECIALISE && nl > 0 && !s->d.stage6;
+    int kind[4] = { -1, -1, -1, -1 };
+    for (size_t l = 0; l < nl && uniform; ++l)
+    {
+        int& k = kind[l & 3];
+        if (k >= 0 && k != (int)s->light_types[l]) uniform = false;
+        k = (int)s->light_types[l];
+    }
+    if (!uniform)
+    {
+        k_light_sample<<<grid, RT_BLOCK, 0, st>>>(c, cur, bounce, lsi);
+        return;
+    }
+    unsigned extra = 0;
+    for (uint32_t bin = 0; bin < RT_LBINS; ++bin)
+    {
+        const int lt = kind[bin & 3];
+        const bool glossy = (bin & 4u) != 0;
+        if (lt < 0 || (glossy ? !s->has_glossy : !s->has_lambert))
+            continue;               // nothing can land in this bin
+        if (lt == RT_SHAPE_RECT)        rt_launch_light_bin<RT_SHAPE_RECT>(c, cur, bounce, lsi, bin, glossy, grid, st);
+        else if (lt == RT_SHAPE_SPHERE) rt_launch_light_bin<RT_SHAPE_SPHERE>(c, cur, bounce, lsi, bin, glossy, grid, st);
+        else                            rt_launch_light_bin<RT_SHAPE_MESH>(c, cur, bounce, lsi, bin, glossy, grid, st);
+        ++extra;
+    }
+    if (extra > 1)
+        launches += extra - 1;      // the caller counts one launch for this stage
 }
 
 template <bool COUNT>
@@ -1400,7 +1473,7 @@ static int rt_launch_batch(RtScene* s, const RenderCtx& c, cudaStream_t st, uint
                 k_light_select<<<wide, RT_BLOCK, 0, st>>>(c, cur, b, l);
                 launches += 1;
             }
-            k_light_sample<<<wide, RT_BLOCK, 0, st>>>(c, cur, b, l);
+            rt_launch_light_sample(s, c, cur, b, l, wide, st, launches);
             rt_trace_mark(rb, timed, st);
             if (split)
             {

@@ -48,6 +48,8 @@ struct RtScene
     uint32_t num_tris;
     uint32_t num_faces;
     std::vector<uint32_t> light_shapes;
+    std::vector<uint32_t> light_types;  // RT_SHAPE_* of every light, findLights() order
+    bool has_lambert, has_glossy;       // BRDF kinds among the scene's materials
     float upload_ms;
     // scratch for the host-buffer entry points (grown on demand)
     void* scratch_in;
@@ -889,6 +891,15 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
     sc->num_tris = num_tris;
     sc->num_faces = desc->num_faces;
     sc->light_shapes.assign(desc->lights, desc->lights + desc->num_lights);
+    sc->light_types.clear();
+    for (uint32_t l = 0; l < desc->num_lights; ++l)
+        sc->light_types.push_back(desc->shapes[desc->lights[l]].type);
+    sc->has_lambert = sc->has_glossy = false;
+    for (uint32_t m = 0; m < desc->num_materials; ++m)
+    {
+        if (desc->materials[m].brdf == RT_BRDF_LAMBERT) sc->has_lambert = true;
+        if (desc->materials[m].brdf == RT_BRDF_GLOSSY) sc->has_glossy = true;
+    }
     sc->scratch_in = sc->scratch_out = NULL;
     sc->scratch_in_bytes = sc->scratch_out_bytes = 0;
     sc->d_work = NULL;
@@ -962,6 +973,7 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
     d.lights = reinterpret_cast<const uint32_t*>(base + o_lights);
     d.top_walk = top_walk_steps ? reinterpret_cast<const DTopStep*>(base + o_walk) : NULL;
     d.top_walk_steps = top_walk_steps;
+    d.top_walk_levels = (uint32_t)(desc->num_top_nodes ? top_depth : 0) + 2u;
     d.anim = reinterpret_cast<const uint4*>(base + o_anim);
     d.num_anim = (uint32_t)anim.size();
     d.anim_stride = anim_stride;

@@ -113,54 +113,6 @@ __device__ __forceinline__ void warp_queue_push(uint32_t* queue, uint32_t* count
         queue[base + __popc(mask & ((1u << lane) - 1))] = value;
 }
 
-// The same through a per-warp staging buffer in shared memory: entries collect over several rounds
-// and go out with ONE atomicAdd.  Every ray that enters a mesh is appended to one global queue; on
-// the 10 M-triangle scene that was one atomic on one address per 32 rays from every warp of the
-// GPU, and 47 % of the top-level pass's stall samples sat on that atomic's return value
-// (profiles/README.md, round 2): same-address atomics serialise in L2.  All 32 lanes must call.
-#ifndef RT_STAGE_Q
-#define RT_STAGE_Q 224      /* entries per warp; flushed when fewer than 32 are free */
-#endif
-struct WarpStage
-{
-    uint32_t* buf;          // RT_STAGE_Q words of shared memory owned by this warp
-    uint32_t count;         // warp-uniform
-};
-__device__ __forceinline__ void warp_stage_flush(WarpStage& st, uint32_t* queue, uint32_t* counter)
-{
-    if (st.count == 0)
-        return;
-    const uint32_t lane = threadIdx.x & 31;
-    uint32_t base = 0;
-    if (lane == 0)
-        base = atomicAdd(counter, st.count);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    __syncwarp();
-    for (uint32_t k = lane; k < st.count; k += 32)
-        queue[base + k] = st.buf[k];
-    __syncwarp();
-    st.count = 0;
-}
-#ifndef RT_STAGED_PUSH
-#define RT_STAGED_PUSH 1        /* 0: one atomic per call (A/B runs) */
-#endif
-__device__ __forceinline__ void warp_stage_push(WarpStage& st, uint32_t* queue, uint32_t* counter, bool want, uint32_t value)
-{
-#if !RT_STAGED_PUSH
-    warp_queue_push(queue, counter, want, value);
-    return;
-#endif
-    const uint32_t mask = __ballot_sync(0xffffffffu, want);
-    if (mask == 0)
-        return;
-    const uint32_t lane = threadIdx.x & 31;
-    if (want)
-        st.buf[st.count + __popc(mask & ((1u << lane) - 1))] = value;
-    st.count += __popc(mask);
-    if (st.count > RT_STAGE_Q - 32)
-        warp_stage_flush(st, queue, counter);
-}
-
 // ---------------------------------------------------------------------------
 // Top-level pass.  FRESH: rays come from the stage's IO (queue of path slots);
 // otherwise they are resumed from their suspended state.
@@ -476,9 +428,8 @@ __device__ __forceinline__ void trace_top(const DScene& sc, const IO& io, const 
 #endif
 template <bool ANY, bool COUNT, class IO>
 __device__ __forceinline__ void trace_top_static(const DScene& sc, const IO& io, const SplitBufs& sb, const SplitPass& ps,
-                                                 WorkCount& wc, float* lane_t0, float* lane_t1, float4* stage_rec, uint32_t* stage_q)
+                                                 WorkCount& wc, float* lane_t0, float* lane_t1, float4* stage_rec)
 {
-    WarpStage out_stage = { stage_q + (threadIdx.x >> 5) * RT_STAGE_Q, 0u };
     // lane_t0 / lane_t1: [RT_WALK_MAX_DEPTH + 1][blockDim.x] shared floats
     const uint32_t lane = threadIdx.x & 31, tid = threadIdx.x, stride = blockDim.x;
     const uint32_t n = io.count();
@@ -751,8 +702,8 @@ __device__ __forceinline__ void trace_top_static(const DScene& sc, const IO& io,
                 (void)suspend;
             }
         }
-        // rays that entered a mesh (a lane suspends at most once per walk): staged, appended every few chunks
-        warp_stage_push(out_stage, ps.out_queue, ps.out_count, suspended, tag);
+        // rays that entered a mesh: one queue append per chunk (a lane suspends at most once per walk)
+        warp_queue_push(ps.out_queue, ps.out_count, suspended, tag);
         if (live && !suspended)
             io.store(tag, res);
 #if RT_STATIC_PREFETCH
@@ -769,7 +720,6 @@ __device__ __forceinline__ void trace_top_static(const DScene& sc, const IO& io,
 #if RT_STATIC_PREFETCH
     __pipeline_wait_prior(0);
 #endif
-    warp_stage_flush(out_stage, ps.out_queue, ps.out_count);
 }
 
 // ---------------------------------------------------------------------------
@@ -1128,8 +1078,6 @@ __device__ __forceinline__ void trace_mesh_pair(const DScene& sc, const IO& io, 
     constexpr int kSmemStack = CAP > 32 ? RT_PAIR_SMEM_STACK_DEEP : RT_PAIR_SMEM_STACK;
     static_assert(kSmemStack >= 1 && kSmemStack < CAP, "shared-memory stack slots");
     __shared__ float4 sm_stack[kSmemStack * RT_BLOCK];
-    __shared__ uint32_t sm_stage_q[(RT_BLOCK / 32) * RT_STAGE_Q];
-    WarpStage out_stage = { sm_stage_q + (threadIdx.x >> 5) * RT_STAGE_Q, 0u };
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t lt_mask = (1u << lane) - 1;
     const uint32_t n = *ps.in_count;
@@ -1434,10 +1382,9 @@ __device__ __forceinline__ void trace_mesh_pair(const DScene& sc, const IO& io, 
                 }
                 active = false;
             }
-            warp_stage_push(out_stage, ps.out_queue, ps.out_count, resume, tag);
+            warp_queue_push(ps.out_queue, ps.out_count, resume, tag);
         }
     }
-    warp_stage_flush(out_stage, ps.out_queue, ps.out_count);
 #undef RT_PAIR_PUT
 #undef RT_PAIR_GET
 }
