@@ -1141,8 +1141,8 @@ inline size_t carve(RenderCtx& c, char* base, size_t samples, size_t pixels, uin
     c.q_meshq[1] = k.take<uint32_t>(samples);
     c.q_resume[0] = k.take<uint32_t>(samples);
     c.q_resume[1] = k.take<uint32_t>(samples);
-    c.split.rec = k.take<float4>(samples * 4);
-    c.split.stack = k.take<float4>(samples * (RT_SPLIT_TOPCAP - 1));
+    c.split.rec = k.take<float4>(samples * RT_SPLIT_REC);
+    c.split.stack = k.take<float4>(samples * (RT_SPLIT_TOPCAP - 5));
     c.ctl = k.take<uint32_t>(CTL_WORDS);
     c.totals = k.take<uint64_t>(8);
     return k.off + 256;

@@ -55,27 +55,37 @@
 #endif
 #define RT_SPLIT_MAX_MESHES 12   /* more mesh shapes than this: use the unified kernel */
 
-// Per-slot suspended-ray state (slot = path sample index / ray index).  Kept small and packed: one
-// 64-byte record per slot, written whole by the top-level pass that suspends the ray (two full DRAM
-// sectors: separate 16-byte arrays made every store a partial-sector write that L2 has to fill from
-// HBM first), read back half by half -- the mesh pass needs only the first 32 bytes, the resume pass
-// only the second.  The set-local ray itself is NOT saved: a resume pass recomputes it from the
-// stage's own ray record (same inputs, same bits).
-//   rec[4 * slot + 0]  mesh-local origin xyz (computed by the top pass at mesh entry), m_t (closest hit) or tMax (any hit)
-//   rec[4 * slot + 1]  mesh-local direction xyz, mesh shape to enter | RT_SPLIT_DIRECT when no top-level work is pending
-//                      (the mesh pass then finishes the ray itself instead of queueing it for a resume pass)
-//   rec[4 * slot + 2]  m_t, winner shape, winner triangle record, (mesh shape to enter | sp << 24)
-//   rec[4 * slot + 3]  top-level stack entry 0: node, t0, t1, -
-//   stack[(RT_SPLIT_TOPCAP - 1) * slot + k - 1]   top-level stack entries k >= 1
+// Per-slot suspended-ray state (slot = path sample index / ray index): one 128-byte record per slot,
+// of which a suspension writes and a later pass reads only the 32-byte SECTORS it needs, each sector
+// always whole.  (Separate 16-byte arrays made every store a partial-sector write that L2 has to
+// fill from HBM first -- half the DRAM reads of the top-level passes on the 10 M-triangle scene --
+// and a record written whole regardless of its content costs the small scenes more than it saves.)
+// The set-local ray itself is NOT saved: a resume pass recomputes it from the stage's own ray record
+// (same inputs, same bits).
+//   sector 0  rec[0] mesh-local origin xyz (computed by the top pass at mesh entry), m_t (closest hit) or tMax (any hit)
+//             rec[1] mesh-local direction xyz, mesh shape to enter | RT_SPLIT_DIRECT when no top-level work is pending
+//                    (the mesh pass then finishes the ray itself instead of queueing it for a resume pass)
+//   sector 1  rec[2] m_t, winner shape, winner triangle record, (mesh shape to enter | sp << 24)
+//             rec[3] top-level stack entry 0: node, t0, t1, -
+//   sector 2  rec[4], rec[5] stack entries 1, 2        (written when sp > 1)
+//   sector 3  rec[6], rec[7] stack entries 3, 4        (written when sp > 3)
+//   stack[(RT_SPLIT_TOPCAP - 5) * slot + k - 5]   stack entries k >= 5
+#define RT_SPLIT_REC 8          /* float4 per record */
 struct SplitBufs
 {
     float4* rec;
     float4* stack;
 };
-__device__ __forceinline__ float4* split_rec(const SplitBufs& sb, uint32_t slot) { return sb.rec + 4 * (size_t)slot; }
+__device__ __forceinline__ float4* split_rec(const SplitBufs& sb, uint32_t slot) { return sb.rec + RT_SPLIT_REC * (size_t)slot; }
 __device__ __forceinline__ float4* split_stack_entry(const SplitBufs& sb, uint32_t slot, int k)
 {
-    return k == 0 ? sb.rec + 4 * (size_t)slot + 3 : sb.stack + (size_t)slot * (RT_SPLIT_TOPCAP - 1) + (k - 1);
+    return k < 5 ? sb.rec + RT_SPLIT_REC * (size_t)slot + 3 + k : sb.stack + (size_t)slot * (RT_SPLIT_TOPCAP - 5) + (k - 5);
+}
+// After entries 0 .. sp-1 were written: fill the other half of a half-written sector
+__device__ __forceinline__ void split_stack_pad(const SplitBufs& sb, uint32_t slot, int sp)
+{
+    if (sp == 0) *split_stack_entry(sb, slot, 0) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (sp == 2 || sp == 4) *split_stack_entry(sb, slot, sp) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 }
 
 // One pass: where the work comes from, where suspended / resumed slots go, and
@@ -388,12 +398,11 @@ __device__ __forceinline__ void trace_top(const DScene& sc, const IO& io, const 
                 float4* rec = split_rec(sb, tag);
                 rec[2] = make_float4(res.t, __int_as_float(res.shape), __int_as_float(res.tri_rec),
                                      __uint_as_float(park_shape | ((uint32_t)sp << 24)));
-                // (entry 0 is written even when the stack is empty: the record goes out as whole sectors)
-                rec[3] = make_float4(__uint_as_float(stk_node[0]), stk_t0[0], stk_t1[0], 0.0f);
                 #pragma unroll
-                for (int k = 1; k < RT_SPLIT_TOPCAP; ++k)
+                for (int k = 0; k < RT_SPLIT_TOPCAP; ++k)
                     if (k < sp)
                         *split_stack_entry(sb, tag, k) = make_float4(__uint_as_float(stk_node[k]), stk_t0[k], stk_t1[k], 0.0f);
+                split_stack_pad(sb, tag, sp);       // sectors go out whole
                 active = false;
             }
             warp_queue_push(ps.out_queue, ps.out_count, suspend, tag);
@@ -631,7 +640,6 @@ __device__ __forceinline__ void trace_top_static(const DScene& sc, const IO& io,
                             const uint32_t pn[8] = { p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w };
                             const uint32_t npend = (flags >> 16) & 0xffu;
                             uint32_t sp = 0;
-                            float4 entry0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                             #pragma unroll
                             for (uint32_t k = 0; k < RT_WALK_MAX_DEPTH; ++k)
                             {
@@ -640,17 +648,15 @@ __device__ __forceinline__ void trace_top_static(const DScene& sc, const IO& io,
                                     uint32_t dk = (hd.w >> (4 * k)) & 0xfu;
                                     if ((alive >> dk) & 1u)
                                     {
-                                        const float4 e = make_float4(__uint_as_float(pn[k]), lane_t0[dk * stride + tid],
-                                                                     lane_t1[dk * stride + tid], 0.0f);
-                                        if (sp == 0) entry0 = e;
-                                        else *split_stack_entry(sb, tag, (int)sp) = e;
+                                        *split_stack_entry(sb, tag, (int)sp) = make_float4(__uint_as_float(pn[k]), lane_t0[dk * stride + tid],
+                                                                                           lane_t1[dk * stride + tid], 0.0f);
                                         ++sp;
                                     }
                                 }
                             }
+                            split_stack_pad(sb, tag, (int)sp);      // sectors go out whole
                             rec[2] = make_float4(res.t, __int_as_float(res.shape), __int_as_float(res.tri_rec),
                                                  __uint_as_float(shape_id | (sp << 24)));
-                            rec[3] = entry0;        // (always: the 64-byte record goes out as whole sectors)
                             rec[1] = make_float4(rm.d.x, rm.d.y, rm.d.z, __uint_as_float(shape_id | (sp == 0 && RT_MESH_DIRECT_FINISH ? RT_SPLIT_DIRECT : 0u)));
                             open = false;
                             suspended = true;
