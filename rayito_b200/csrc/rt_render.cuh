@@ -73,6 +73,7 @@ struct RenderCtx
     uint32_t width, height;
     uint32_t ps, ls, depth;
     uint32_t spp;               // ps * ps
+    uint32_t spp_shift;         // log2(spp) when spp is a power of two, else 0xffffffff
     uint32_t nls;               // light-sample iterations per bounce: ls*ls (Stage 7, one random light each),
                                 // num_lights*ls*ls (Stage 6, every light in turn); 0 without lights
     uint32_t ls2;               // ls * ls
@@ -123,6 +124,21 @@ struct RenderCtx
 __device__ __forceinline__ const float4* xf_row(const RenderCtx& c, uint32_t i)
 {
     return c.xf_cache ? c.xf_cache + (size_t)i * c.sc.anim_stride : nullptr;
+}
+
+// Sample index -> (pixel of the batch, sample of the pixel); a shift and a mask for power-of-two sample counts
+__device__ __forceinline__ void sample_split(const RenderCtx& c, uint32_t i, uint32_t& p, uint32_t& psi)
+{
+    if (c.spp_shift != 0xffffffffu)
+    {
+        p = i >> c.spp_shift;
+        psi = i & (c.spp - 1u);
+    }
+    else
+    {
+        p = i / c.spp;
+        psi = i % c.spp;
+    }
 }
 
 // Where pixel p of the batch (image coordinates x, y) is written
@@ -299,7 +315,8 @@ k_raygen(const __grid_constant__ RenderCtx c)
     {
         if (i < c.num_samples)
         {
-            uint32_t p = i / c.spp, psi = i % c.spp;
+            uint32_t p, psi;
+            sample_split(c, i, p, psi);
             uint32_t xy = c.pix_xy[p];
             if (xy != 0xffffffffu)
             {
@@ -586,12 +603,100 @@ __device__ __forceinline__ void light_choice(const RenderCtx& c, uint32_t bounce
     }
 }
 
-// pathTrace, one bounce, everything that does not need further rays
-__global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_MINBLOCKS)
-k_shade(const __grid_constant__ RenderCtx c, int cur, uint32_t bounce)
+// pathTrace, one bounce, everything that does not need further rays, for hit path sample i.
+// ST / BR >= 0: shape type and BRDF of the hit are known at compile time (the shade queue is binned by
+// hit shape, and a shape has one type and one material), so a launch per bin runs a kernel that holds
+// only that shape's normal code and that BRDF's sampling.
+template <int ST, int BR>
+__device__ __forceinline__ void shade_one(const RenderCtx& c, int cur, uint32_t bounce, uint32_t i)
 {
-    const BinQ<RT_SBINS> shade = { c.q_shade, c.ctl + CTL_SHADE, c.qcap };
-    const uint32_t n = shade.total();
+    float4 h0 = c.hit01[2 * (size_t)i];
+    int shape = __float_as_int(h0.y);
+    if (shape >= 0)
+    {
+        float4 ro = c.ray_od[2 * (size_t)i], rd = c.ray_od[2 * (size_t)i + 1], th = c.thr[i], rs = c.res[i];
+        // Intersection::m_normal / m_colorModifier of the winning hit, computed
+        // here where all 32 lanes are busy rather than in the traversal loop
+        float4 h1;
+        {
+            ClosestHit h;
+            h.t = h0.x; h.shape = shape; h.tri_rec = __float_as_int(h0.z);
+            TRS set_trs = xform_eval(c.sc, c.sc.set_xform, ro.w);
+            LocalRay r0;
+            r0.o = to_local_point(set_trs, xyz(ro));
+            r0.d = to_local_vector(set_trs, xyz(rd));
+            r0.inv = r0.d; r0.neg = 0;
+            V3 nrm;
+            float cmod;
+            hit_shading_inputs(c.sc, r0, ro.w, h, nrm, cmod, xf_row(c, i), ST);
+            h1 = make_float4(nrm.x, nrm.y, nrm.z, cmod);
+            c.hit01[2 * (size_t)i + 1] = h1;
+        }
+        uint32_t state = __float_as_uint(th.w);
+        uint32_t nb = state & 0xffu, nd = (state >> 8) & 0xffu;
+        Color3 thr = rgb(th), result = rgb(rs);
+        DShape sh = load_shape(c.sc, (uint32_t)shape);
+        RtMaterial mat = c.sc.materials[sh.material];
+        if (BR >= 0) mat.brdf = (uint32_t)BR;      // every hit of the bin has this BRDF: the others compile away
+
+        // Emission only when seen directly or through mirrors (:303-306)
+        // (Stage 6: only when seen directly, S6 RaytraceMain.cpp:250)
+        if (nb == 0 || (nb == nd && !c.sc.stage6))
+            result = result + thr * mkc(mat.emittance[0], mat.emittance[1], mat.emittance[2]);
+
+        if (mat.brdf != RT_BRDF_NONE)      // an Emitter ends the path (:320-323)
+        {
+            V3 o = xyz(ro), d = xyz(rd);
+            V3 position = o + h0.x * d;
+            V3 normal = xyz(h1);
+            V3 outgoing = -d;
+            float cm = h1.w;
+            bool dirac = mat.brdf == RT_BRDF_MIRROR;
+            if (dirac)
+                nd++;
+            uint32_t p, psi;
+            sample_split(c, i, p, psi);
+            if (!dirac && c.nls > 0)
+            {
+                bq_push(c.q_lit, c.ctl + CTL_LIT, c.qcap, 0, i);
+                // ... and regrouped by (light of light sample 0, BRDF kind) for k_light_sample; the
+                // bins live in this bounce's consumed path queue
+                uint32_t idx0, light0;
+                light_choice(c, bounce, 0, p, psi, idx0, light0);
+                bq_push(c.q_path[cur], c.ctl + CTL_LITB, c.qcap, (light0 & 3u) | (mat.brdf == RT_BRDF_GLOSSY ? 4u : 0u), i);
+                c.lit_tr[2 * (size_t)i] = make_float4(thr.r, thr.g, thr.b, 0.0f);
+                c.lit_tr[2 * (size_t)i + 1] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                c.pos_wo[2 * (size_t)i] = make_float4(position.x, position.y, position.z, ro.w);
+                c.pos_wo[2 * (size_t)i + 1] = make_float4(outgoing.x, outgoing.y, outgoing.z, __uint_as_float(sh.material));
+            }
+
+            // Next leg of the path (:451-477)
+            uint32_t perm = c.perms[(size_t)(5 * bounce + 0) * c.num_pixels + p];
+            float u, v;
+            cmj2d(psi, c.ps, c.ps, perm, u, v);
+            V3 incoming;
+            float pdf = 0.0f;
+            float value = brdf_sample(mat.brdf, mat.exponent, incoming, outgoing, normal, u, v, pdf);
+            if (pdf > 0.0f)
+            {
+                Color3 mc = mkc(mat.color[0], mat.color[1], mat.color[2]);
+                Color3 f = mkc(cm, cm, cm) * mc * value * (fabsf(dot3(-incoming, normal)) / (pdf * 1.0f));
+                thr = thr * f;
+                nb++;
+                V3 nd3 = -incoming;
+                c.ray_od[2 * (size_t)i] = make_float4(position.x, position.y, position.z, ro.w);
+                c.ray_od[2 * (size_t)i + 1] = make_float4(nd3.x, nd3.y, nd3.z, 0.0f);
+                if (nb < c.depth)
+                    bq_push(c.q_path[cur ^ 1], c.ctl + CTL_PATH(cur ^ 1), c.qcap, dir_octant(nd3), i);
+            }
+        }
+        c.thr[i] = make_float4(thr.r, thr.g, thr.b, __uint_as_float(nb | (nd << 8)));
+        c.res[i] = make_float4(result.r, result.g, result.b, 0.0f);
+    }
+}
+
+__device__ __forceinline__ void shade_prologue(const RenderCtx& c)
+{
     if (blockIdx.x == 0 && threadIdx.x == 0)
     {
         for (int b = 0; b < RT_QBINS; ++b) { c.ctl[CTL_SHADOW + b] = 0; c.ctl[CTL_MIS + b] = 0; }
@@ -599,93 +704,34 @@ k_shade(const __grid_constant__ RenderCtx c, int cur, uint32_t bounce)
         c.ctl[CTL_CUR_MIS] = 0;
         c.ctl[CTL_CUR_PATH] = 0;
     }
+}
+
+__global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_MINBLOCKS)
+k_shade(const __grid_constant__ RenderCtx c, int cur, uint32_t bounce)
+{
+    const BinQ<RT_SBINS> shade = { c.q_shade, c.ctl + CTL_SHADE, c.qcap };
+    const uint32_t n = shade.total();
+    shade_prologue(c);
     RT_GRID_STRIDE(j, n)
     {
         if (j < n)
-        {
-            const uint32_t i = shade.at(j);
-            float4 h0 = c.hit01[2 * (size_t)i];
-            int shape = __float_as_int(h0.y);
-            if (shape >= 0)
-            {
-                float4 ro = c.ray_od[2 * (size_t)i], rd = c.ray_od[2 * (size_t)i + 1], th = c.thr[i], rs = c.res[i];
-                // Intersection::m_normal / m_colorModifier of the winning hit, computed
-                // here where all 32 lanes are busy rather than in the traversal loop
-                float4 h1;
-                {
-                    ClosestHit h;
-                    h.t = h0.x; h.shape = shape; h.tri_rec = __float_as_int(h0.z);
-                    TRS set_trs = xform_eval(c.sc, c.sc.set_xform, ro.w);
-                    LocalRay r0;
-                    r0.o = to_local_point(set_trs, xyz(ro));
-                    r0.d = to_local_vector(set_trs, xyz(rd));
-                    r0.inv = r0.d; r0.neg = 0;
-                    V3 nrm;
-                    float cmod;
-                    hit_shading_inputs(c.sc, r0, ro.w, h, nrm, cmod, xf_row(c, i));
-                    h1 = make_float4(nrm.x, nrm.y, nrm.z, cmod);
-                    c.hit01[2 * (size_t)i + 1] = h1;
-                }
-                uint32_t state = __float_as_uint(th.w);
-                uint32_t nb = state & 0xffu, nd = (state >> 8) & 0xffu;
-                Color3 thr = rgb(th), result = rgb(rs);
-                DShape sh = load_shape(c.sc, (uint32_t)shape);
-                RtMaterial mat = c.sc.materials[sh.material];
+            shade_one<-1, -1>(c, cur, bounce, shade.at(j));
+    }
+}
 
-                // Emission only when seen directly or through mirrors (:303-306)
-                // (Stage 6: only when seen directly, S6 RaytraceMain.cpp:250)
-                if (nb == 0 || (nb == nd && !c.sc.stage6))
-                    result = result + thr * mkc(mat.emittance[0], mat.emittance[1], mat.emittance[2]);
-
-                if (mat.brdf != RT_BRDF_NONE)      // an Emitter ends the path (:320-323)
-                {
-                    V3 o = xyz(ro), d = xyz(rd);
-                    V3 position = o + h0.x * d;
-                    V3 normal = xyz(h1);
-                    V3 outgoing = -d;
-                    float cm = h1.w;
-                    bool dirac = mat.brdf == RT_BRDF_MIRROR;
-                    if (dirac)
-                        nd++;
-                    uint32_t p = i / c.spp, psi = i % c.spp;
-                    if (!dirac && c.nls > 0)
-                    {
-                        bq_push(c.q_lit, c.ctl + CTL_LIT, c.qcap, 0, i);
-                        // ... and regrouped by (light of light sample 0, BRDF kind) for k_light_sample; the
-                        // bins live in this bounce's consumed path queue
-                        uint32_t idx0, light0;
-                        light_choice(c, bounce, 0, p, psi, idx0, light0);
-                        bq_push(c.q_path[cur], c.ctl + CTL_LITB, c.qcap, (light0 & 3u) | (mat.brdf == RT_BRDF_GLOSSY ? 4u : 0u), i);
-                        c.lit_tr[2 * (size_t)i] = make_float4(thr.r, thr.g, thr.b, 0.0f);
-                        c.lit_tr[2 * (size_t)i + 1] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                        c.pos_wo[2 * (size_t)i] = make_float4(position.x, position.y, position.z, ro.w);
-                        c.pos_wo[2 * (size_t)i + 1] = make_float4(outgoing.x, outgoing.y, outgoing.z, __uint_as_float(sh.material));
-                    }
-
-                    // Next leg of the path (:451-477)
-                    uint32_t perm = c.perms[(size_t)(5 * bounce + 0) * c.num_pixels + p];
-                    float u, v;
-                    cmj2d(psi, c.ps, c.ps, perm, u, v);
-                    V3 incoming;
-                    float pdf = 0.0f;
-                    float value = brdf_sample(mat.brdf, mat.exponent, incoming, outgoing, normal, u, v, pdf);
-                    if (pdf > 0.0f)
-                    {
-                        Color3 mc = mkc(mat.color[0], mat.color[1], mat.color[2]);
-                        Color3 f = mkc(cm, cm, cm) * mc * value * (fabsf(dot3(-incoming, normal)) / (pdf * 1.0f));
-                        thr = thr * f;
-                        nb++;
-                        V3 nd3 = -incoming;
-                        c.ray_od[2 * (size_t)i] = make_float4(position.x, position.y, position.z, ro.w);
-                        c.ray_od[2 * (size_t)i + 1] = make_float4(nd3.x, nd3.y, nd3.z, 0.0f);
-                        if (nb < c.depth)
-                            bq_push(c.q_path[cur ^ 1], c.ctl + CTL_PATH(cur ^ 1), c.qcap, dir_octant(nd3), i);
-                    }
-                }
-                c.thr[i] = make_float4(thr.r, thr.g, thr.b, __uint_as_float(nb | (nd << 8)));
-                c.res[i] = make_float4(result.r, result.g, result.b, 0.0f);
-            }
-        }
+// The same for ONE bin (= one shape) of the shade queue; `first`: this launch also resets the counters
+template <int ST, int BR>
+__global__ void __launch_bounds__(RT_BLOCK, RT_SHADE_MINBLOCKS)
+k_shade_bin(const __grid_constant__ RenderCtx c, int cur, uint32_t bounce, uint32_t bin, int first)
+{
+    const uint32_t n = c.ctl[CTL_SHADE + bin];
+    const uint32_t* items = c.q_shade + (size_t)bin * c.qcap;
+    if (first)
+        shade_prologue(c);
+    RT_GRID_STRIDE(j, n)
+    {
+        if (j < n)
+            shade_one<ST, BR>(c, cur, bounce, items[j]);
     }
 }
 
@@ -702,7 +748,9 @@ k_light_select(const __grid_constant__ RenderCtx c, int cur, uint32_t bounce, ui
         {
             const uint32_t i = c.q_lit[j];
             uint32_t idx, light_index;
-            light_choice(c, bounce, lsi, i / c.spp, i % c.spp, idx, light_index);
+            uint32_t p, psi;
+            sample_split(c, i, p, psi);
+            light_choice(c, bounce, lsi, p, psi, idx, light_index);
             const RtMaterial& mat = c.sc.materials[__float_as_uint(c.pos_wo[2 * (size_t)i + 1].w)];
             uint32_t bin = (light_index & 3u) | (mat.brdf == RT_BRDF_GLOSSY ? 4u : 0u);
             bq_push(c.q_path[cur], c.ctl + CTL_LITB, c.qcap, bin, i);
@@ -719,7 +767,8 @@ k_light_select(const __grid_constant__ RenderCtx c, int cur, uint32_t bounce, ui
 template <int LT, int BR>
 __device__ __forceinline__ void light_sample_one(const RenderCtx& c, uint32_t bounce, uint32_t lsi, uint32_t i)
 {
-    uint32_t p = i / c.spp, psi = i % c.spp;
+    uint32_t p, psi;
+    sample_split(c, i, p, psi);
     float4 pt = c.pos_wo[2 * (size_t)i], wm = c.pos_wo[2 * (size_t)i + 1], h1 = c.hit01[2 * (size_t)i + 1];
     V3 position = xyz(pt), outgoing = xyz(wm), normal = xyz(h1);
     float time = pt.w, cm = h1.w;
@@ -1341,6 +1390,46 @@ __global__ void k_stage_prologue(const __grid_constant__ RenderCtx c, int cur)
     c.ctl[CTL_LIT] = 0;
 }
 
+// k_shade, one specialised launch per hit shape (= bin of the shade queue) when the scene has fewer shapes than bins
+#ifndef RT_SHADE_SPECIALISE
+#define RT_SHADE_SPECIALISE 1
+#endif
+template <int ST>
+static void rt_launch_shade_bin(const RenderCtx& c, int cur, uint32_t bounce, uint32_t bin, int first, uint32_t brdf,
+                                unsigned grid, cudaStream_t st)
+{
+    switch (brdf)
+    {
+    case RT_BRDF_LAMBERT: k_shade_bin<ST, RT_BRDF_LAMBERT><<<grid, RT_BLOCK, 0, st>>>(c, cur, bounce, bin, first); break;
+    case RT_BRDF_GLOSSY:  k_shade_bin<ST, RT_BRDF_GLOSSY><<<grid, RT_BLOCK, 0, st>>>(c, cur, bounce, bin, first); break;
+    case RT_BRDF_MIRROR:  k_shade_bin<ST, RT_BRDF_MIRROR><<<grid, RT_BLOCK, 0, st>>>(c, cur, bounce, bin, first); break;
+    default:              k_shade_bin<ST, RT_BRDF_NONE><<<grid, RT_BLOCK, 0, st>>>(c, cur, bounce, bin, first); break;
+    }
+}
+static void rt_launch_shade(RtScene* s, const RenderCtx& c, int cur, uint32_t bounce, unsigned grid, cudaStream_t st,
+                            uint64_t& launches)
+{
+    const size_t ns = s->shape_types.size();
+    if (!RT_SHADE_SPECIALISE || ns == 0 || ns > RT_SBINS - 1 || s->d.stage6)
+    {
+        k_shade<<<grid, RT_BLOCK, 0, st>>>(c, cur, bounce);
+        return;
+    }
+    for (size_t b = 0; b < ns; ++b)
+    {
+        const int first = b == 0 ? 1 : 0;
+        const uint32_t brdf = s->shape_brdfs[b];
+        switch (s->shape_types[b])
+        {
+        case RT_SHAPE_PLANE:  rt_launch_shade_bin<RT_SHAPE_PLANE>(c, cur, bounce, (uint32_t)b, first, brdf, grid, st); break;
+        case RT_SHAPE_SPHERE: rt_launch_shade_bin<RT_SHAPE_SPHERE>(c, cur, bounce, (uint32_t)b, first, brdf, grid, st); break;
+        case RT_SHAPE_RECT:   rt_launch_shade_bin<RT_SHAPE_RECT>(c, cur, bounce, (uint32_t)b, first, brdf, grid, st); break;
+        default:              rt_launch_shade_bin<RT_SHAPE_MESH>(c, cur, bounce, (uint32_t)b, first, brdf, grid, st); break;
+        }
+    }
+    launches += ns - 1;         // the caller counts one launch for this stage
+}
+
 // k_light_sample, one specialised launch per (light, BRDF kind) bin when the scene allows it
 #ifndef RT_LIGHT_SPECIALISE
 #define RT_LIGHT_SPECIALISE 1
@@ -1463,7 +1552,7 @@ static int rt_launch_batch(RtScene* s, const RenderCtx& c, cudaStream_t st, uint
             trace_launches += 1;
         }
         rt_trace_mark(rb, timed, st);
-        k_shade<<<wide, RT_BLOCK, 0, st>>>(c, cur, b);
+        rt_launch_shade(s, c, cur, b, wide, st, launches);
         launches += 2;
         for (uint32_t l = 0; l < c.nls; ++l)
         {
@@ -1515,6 +1604,10 @@ inline int rt_fill_ctx(RtScene* s, const RtCamera* camera, const RtRenderParams*
     c.ls = prm->light_samples_hint;
     c.depth = prm->max_ray_depth;
     c.spp = plan.spp;
+    c.spp_shift = 0xffffffffu;
+    if ((plan.spp & (plan.spp - 1u)) == 0u)
+        for (uint32_t k = 0; k < 32; ++k)
+            if ((1u << k) == plan.spp) c.spp_shift = k;
     // samplers.m_numLightSamples = lights.empty() ? 0 : ls*ls  (RaytraceMain.cpp:77)
     c.ls2 = prm->light_samples_hint * prm->light_samples_hint;
     c.nls = s->d.num_lights == 0 ? 0 : c.ls2;

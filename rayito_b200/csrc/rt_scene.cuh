@@ -49,6 +49,8 @@ struct RtScene
     uint32_t num_faces;
     std::vector<uint32_t> light_shapes;
     std::vector<uint32_t> light_types;  // RT_SHAPE_* of every light, findLights() order
+    std::vector<uint32_t> shape_types;  // RT_SHAPE_* of every shape (finite, then infinite)
+    std::vector<uint32_t> shape_brdfs;  // RT_BRDF_* of every shape's material
     bool has_lambert, has_glossy;       // BRDF kinds among the scene's materials
     float upload_ms;
     // scratch for the host-buffer entry points (grown on demand)
@@ -894,6 +896,13 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
     sc->light_types.clear();
     for (uint32_t l = 0; l < desc->num_lights; ++l)
         sc->light_types.push_back(desc->shapes[desc->lights[l]].type);
+    sc->shape_types.clear();
+    sc->shape_brdfs.clear();
+    for (uint32_t i = 0; i < num_shapes; ++i)
+    {
+        sc->shape_types.push_back(desc->shapes[i].type);
+        sc->shape_brdfs.push_back(desc->materials[desc->shapes[i].material].brdf);
+    }
     sc->has_lambert = sc->has_glossy = false;
     for (uint32_t m = 0; m < desc->num_materials; ++m)
     {

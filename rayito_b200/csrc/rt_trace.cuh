@@ -144,13 +144,15 @@ __device__ __forceinline__ TRS shape_xform_trav(const DScene& sc, const DShape& 
 // RLight.h:107-113; RMesh.h:305-333, 70-71; RScene.h:152-153).
 __device__ __forceinline__ void hit_shading_inputs(const DScene& sc, const LocalRay& r0, float time,
                                                    const ClosestHit& hit, V3& normal, float& color_mod,
-                                                   const float4* row = nullptr)
+                                                   const float4* row = nullptr, int known_type = -1)
 {
     normal = mk(0.0f, 0.0f, 0.0f);
     color_mod = 1.0f;
     if (hit.shape < 0)
         return;
     DShape sh = load_shape(sc, (uint32_t)hit.shape);
+    if (known_type >= 0)
+        sh.type = (uint32_t)known_type;     // a compile-time constant at the call site: the other kinds compile away
     TRS trs = shape_xform(sc, sh, time, row);
     V3 lo = to_local_point(trs, r0.o);
     V3 ld = to_local_vector(trs, r0.d);
