@@ -61,6 +61,10 @@ WORKLOADS = {
                      label="synthetic displaced sphere, 4 999 696 quads = 9 999 392 triangles, 3840x2160 64spp"),
     "c5-small": dict(recipe=5, width=960, height=540, ps=8, ls=1, depth=3, grid=(2236, 2236),
                      label="synthetic displaced sphere, 9 999 392 triangles, 960x540 64spp (profiling size)"),
+    # PERF MODE face BVH (binned SAH, rth_set_tree_mode(1)): measured parity, not bit-exact (tests/test_perf_tree.py);
+    # its roofline counts the work done on ITS tree.  Never part of the default run.
+    "c5-64spp-sah": dict(recipe=5, width=3840, height=2160, ps=8, ls=1, depth=3, grid=(2236, 2236), tree=1,
+                         label="synthetic displaced sphere, 9 999 392 triangles, 3840x2160 64spp, PERF-MODE tree (binned SAH)"),
     "c3": dict(recipe=6, stage=6, width=1920, height=1080, ps=8, ls=1, depth=3, grid=(0, 0),
                label="Rayito_Stage6 scene (bumpy.obj, BVH, two area lights, Stage 6 rules) 1920x1080 64spp ls1 depth3"),
 }
@@ -384,7 +388,7 @@ def measure_workload(env, name, steps, warmup, want_e2e, want_cpu):
     # ---- scene: built with the C++ host API, flattened, uploaded once ------------
     obj = env.build.model_path("bumpy.obj") if wl["recipe"] in NEEDS_OBJ else None
     t0 = time.perf_counter()
-    hscene = capi.HostScene(wl["recipe"], obj, wl["grid"])
+    hscene = capi.HostScene(wl["recipe"], obj, wl["grid"], tree=wl.get("tree", 0))
     host_prepare_s = time.perf_counter() - t0
     dscene = capi.DeviceScene(hscene.desc, device=local_rank)
     spec = hscene.default_camera_spec()
@@ -627,6 +631,7 @@ def measure_e2e(args, wl, capi, obj, spec, rank, world, local_rank, dev, dist, t
                 raise RuntimeError("e2e frame is not finite")
         return stats.render_ms
 
+    lib.rth_set_tree_mode(wl.get("tree", 0))
     one()
     if world > 1:
         dist.barrier()
@@ -639,6 +644,7 @@ def measure_e2e(args, wl, capi, obj, spec, rank, world, local_rank, dev, dist, t
     if world > 1:
         dist.barrier()
     wall = time.perf_counter() - t0
+    lib.rth_set_tree_mode(0)
     lib.rth_app_destroy(app)
     t = torch.tensor([wall], dtype=torch.float64, device=dev)
     if world > 1:

@@ -22,6 +22,13 @@ extern "C" {
 
 const char* rth_last_error_string(void);
 
+/* Which face BVH Mesh::prepare() builds from now on, on the calling thread (C++: rayito_b200::treeMode()).
+ * 0 = the reference's tree, node for node (Bvh<T>::buildRange, Rayito_Stage7_QT/RAccel.h:290-374; default:
+ * hit records bit-equal to the reference); 1 = PERF MODE, a binned-SAH tree in the same node format, traversed
+ * by the same kernels.  The reference's slab test is not watertight, so another tree may decide a grazing
+ * ray differently: with mode 1 parity is measured (tests/test_gpu_perf_tree.py), not bit-exact. */
+int rth_set_tree_mode(unsigned mode);
+
 /* PerspectiveCamera constructor (RaytraceMain.cpp:205-222).  spec14 = fov degrees,
  * origin xyz, target xyz, up xyz, focal distance, lens radius, shutter open, close. */
 int rth_camera(const float* spec14, RtCamera* out);

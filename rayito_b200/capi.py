@@ -119,7 +119,9 @@ CORE_SYMBOLS = [
 ]
 HOST_SYMBOLS = [
     "rth_last_error_string", "rth_camera", "rth_stage1_render", "rth_stage1_render_float", "rth_stage23_render",
+    "rth_set_tree_mode",
 ]
+TREE_REFERENCE, TREE_SAH = 0, 1     # rth_set_tree_mode (include/rayito_b200_host.h)
 # fixtures/rayito_fixtures.h (test infrastructure: the recipe scenes)
 FIXTURE_SYMBOLS = [
     "rthf_last_error_string", "rth_scene_create", "rth_scene_destroy", "rth_scene_desc",
@@ -211,6 +213,7 @@ def host():
         hl.rth_stage1_render.argtypes = [C.c_int, C.c_uint, C.c_uint, vp]
         hl.rth_stage1_render_float.argtypes = [C.c_int, C.c_uint, C.c_uint, vp, vp]
         hl.rth_stage23_render.argtypes = [C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_uint, vp, vp, vp]
+        hl.rth_set_tree_mode.argtypes = [C.c_uint]
         lib = C.CDLL(_build.build_fixtures(), mode=C.RTLD_LOCAL)
         lib.rthf_last_error_string.restype = C.c_char_p
         lib.rth_scene_create.restype = vp
@@ -249,10 +252,16 @@ def check(rc, what="rayito_b200"):
 class HostScene:
     """A recipe scene built with the C++ host API, prepared and flattened."""
 
-    def __init__(self, recipe, obj_path=None, grid=(0, 0)):
+    def __init__(self, recipe, obj_path=None, grid=(0, 0), tree=TREE_REFERENCE):
         lib = host()
         path = obj_path.encode() if obj_path else None
-        self.handle = lib.rth_scene_create(recipe, path, grid[0], grid[1])
+        # tree: which face BVH prepare() builds (TREE_SAH = the perf-mode tree, parity measured not bit-exact)
+        if lib.rth_set_tree_mode(tree) != 0:
+            raise RtError("rth_set_tree_mode: " + lib.rth_last_error_string().decode())
+        try:
+            self.handle = lib.rth_scene_create(recipe, path, grid[0], grid[1])
+        finally:
+            lib.rth_set_tree_mode(TREE_REFERENCE)
         if not self.handle:
             raise RtError("rth_scene_create: " + lib.rth_last_error_string().decode())
         self.recipe = recipe

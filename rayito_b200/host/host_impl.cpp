@@ -380,6 +380,12 @@ unsigned& stageSemantics()
     return semantics;
 }
 
+unsigned& treeMode()
+{
+    static thread_local unsigned mode = kTreeReference;
+    return mode;
+}
+
 RenderOptions& renderOptions()
 {
     static thread_local RenderOptions options;
@@ -409,6 +415,17 @@ extern "C"
 {
 
 const char* rth_last_error_string(void) { return t_hostError.c_str(); }
+
+int rth_set_tree_mode(unsigned mode)
+{
+    if (mode != rayito_b200::kTreeReference && mode != rayito_b200::kTreeSah)
+    {
+        t_hostError = "rth_set_tree_mode: unknown mode";
+        return -1;
+    }
+    rayito_b200::treeMode() = mode;
+    return 0;
+}
 
 int rth_camera(const float* spec14, RtCamera* out)
 {

@@ -139,6 +139,24 @@ struct BvhNode
 // would overflow (RAccel.h:379,414,502).  The GPU path refuses such trees.
 const unsigned int kMaxTraversalSteps = 50;
 
+} // namespace Rayito
+
+namespace rayito_b200
+{
+// Which face BVH Mesh::prepare() builds (per calling thread, like stageSemantics()).
+//   kTreeReference  the reference's tree, node for node (RAccel.h:262-374): hit records bit-equal.
+//   kTreeSah        PERF MODE: same node format, numbering, leaf size and traversal, but every node is
+//                   split where a binned surface-area heuristic puts the cut instead of at the midpoint
+//                   of its longest axis.  The reference's slab test is not watertight, so a different
+//                   tree can decide a grazing ray differently: parity is MEASURED, not bit-exact
+//                   (tests/test_gpu_perf_tree.py states the bars).  Never the default.
+enum TreeMode { kTreeReference = 0, kTreeSah = 1 };
+unsigned& treeMode();
+}
+
+namespace Rayito
+{
+
 // BVH over the elements of T (T provides numElements() and elementBBox(i)).
 // One element per leaf; interior nodes split the longest axis of the node box at
 // its midpoint; elements whose box centre lies ABOVE the split go first ("left"
@@ -161,7 +179,7 @@ public:
     // and the right child's at base+2nL.  Subtrees therefore build independently -- on
     // worker threads for large meshes -- and land exactly where the serial recursion
     // puts them; std::partition runs on disjoint ranges, so element order is untouched.
-    bool build(const BBox* rootBox = NULL)
+    bool build(const BBox* rootBox = NULL, unsigned mode = rayito_b200::kTreeReference)
     {
         m_maxDepth = 0;
         unsigned int count = m_object.numElements();
@@ -173,19 +191,9 @@ public:
 
         // Uninitialised per-thread scratch, kept between builds (rayito_b200::buildScratch)
         const unsigned int threads = count >= kParallelElements ? rayito_b200::hostThreads() : 1u;
-        // RAYITO_B200_WIDE_SPLITS=1: the splits at the top of a large tree use every worker inside
-        // the split.  Off by default: identical results (tested), but no faster -- 5 M quads on
-        // the 16-core GPU host: 0.141 s against 0.123 s with each of those splits left to one
-        // worker (tools/host_prepare_timing.py); the three predicate passes and the scattered
-        // swaps cost what the idle workers would have saved.
-        const char* wideEnv = std::getenv("RAYITO_B200_WIDE_SPLITS");
-        const bool wideTop = threads > 1 && count >= kWideElements && wideEnv != NULL && wideEnv[0] == '1';
-        const size_t itemBytes = ((size_t)count * sizeof(Item) + 63) & ~(size_t)63;
-        char* scratch = static_cast<char*>(rayito_b200::buildScratch().get(itemBytes + (wideTop ? (size_t)count * sizeof(unsigned) : 0)));
-        if (scratch == NULL)
+        Item* items = static_cast<Item*>(rayito_b200::buildScratch().get((size_t)count * sizeof(Item)));
+        if (items == NULL)
             throw std::bad_alloc();
-        Item* items = reinterpret_cast<Item*>(scratch);
-        unsigned* swapScratch = reinterpret_cast<unsigned*>(scratch + itemBytes);
         BBox whole;
         {
             // Element boxes; the union keeps the serial left-to-right association
@@ -210,32 +218,14 @@ public:
         }
         m_nodes.allocate((size_t)count * 2 - 1);
 
+        // The few splits at the top of a large tree run on one worker each while the others wait
+        // for subtrees to exist (5 M quads on the 16-core GPU host: 0.12 s in all; running those
+        // splits on every worker with an exact parallel std::partition was measured no faster).
         Job root = { 0, count, 0, 1, 0, rootBox ? *rootBox : whole };
         rayito_b200::JobBag<Job> bag;
-        // The few splits at the top of a large tree would otherwise run on one worker while
-        // the others wait for subtrees to exist: they are done here with every worker inside
-        // the split (exact parallel std::partition, chunked box unions folded in order).
-        std::vector<Job> wide(1, root);
-        while (!wide.empty())
-        {
-            Job job = wide.back();
-            wide.pop_back();
-            if (!wideTop || job.end - job.begin < kWideElements)
-            {
-                bag.add(job);
-                continue;
-            }
-            if (job.depth > m_maxDepth)
-                m_maxDepth = job.depth;
-            Job left, right;
-            if (splitNode(items, &m_nodes[0], job, left, right, threads, swapScratch))
-            {
-                wide.push_back(right);
-                wide.push_back(left);
-            }
-        }
+        bag.add(root);
         std::mutex depthMutex;
-        Builder builder = { items, &m_nodes[0], threads > 1 ? kSpawnElements : 0u, &m_maxDepth, &depthMutex };
+        Builder builder = { items, &m_nodes[0], threads > 1 ? kSpawnElements : 0u, &m_maxDepth, &depthMutex, mode };
         bag.drain(threads, builder);
         return true;
     }
@@ -293,14 +283,9 @@ private:
     static const unsigned int kParallelElements = 1u << 16;
     // Subtrees at least this large are handed to the job bag instead of the local stack
     static const unsigned int kSpawnElements = 1u << 13;
-    // Nodes over at least this many elements are split with every worker inside the split
-    static const unsigned int kWideElements = 1u << 18;
-
     // One step of buildRange (RAccel.h:290-374) for the node of `job`: leaf, or split axis,
-    // partition, child boxes and the two child jobs.  workers > 1: the partition and the box
-    // unions run on that many threads with results identical to the one-thread order.
-    static bool splitNode(Item* items, BvhNode* nodes, const Job& job, Job& left, Job& right,
-                          unsigned int workers, unsigned* swapScratch)
+    // partition, child boxes and the two child jobs.
+    static bool splitNode(Item* items, BvhNode* nodes, const Job& job, Job& left, Job& right, unsigned mode)
     {
         BvhNode& node = nodes[job.node];
         node.m_bbox = job.box;
@@ -310,6 +295,8 @@ private:
             node.m_prim = items[job.begin].prim;
             return false;
         }
+        if (mode == rayito_b200::kTreeSah && splitNodeSah(items, node, job, left, right))
+            return true;
 
         Vector extent = job.box.m_max - job.box.m_min;
         BvhNodeFlags axis;
@@ -320,10 +307,7 @@ private:
         float where = (component(job.box.m_max, axis) + component(job.box.m_min, axis)) * 0.5f;
         node.m_flags = axis;
 
-        const size_t n = job.end - job.begin;
-        Item* cut = workers > 1
-            ? rayito_b200::parallelPartition(items + job.begin, n, AboveSplit(where, axis), swapScratch, workers)
-            : std::partition(items + job.begin, items + job.end, AboveSplit(where, axis));
+        Item* cut = std::partition(items + job.begin, items + job.end, AboveSplit(where, axis));
         unsigned int mid = (unsigned int)(cut - items);
         if (mid <= job.begin || mid >= job.end)
         {
@@ -332,8 +316,8 @@ private:
             else if (mid > job.end - 1) mid = job.end - 1;
         }
 
-        BBox leftBox = unionOf(items, job.begin, mid, workers);
-        BBox rightBox = unionOf(items, mid, job.end, workers);
+        BBox leftBox = unionOf(items, job.begin, mid);
+        BBox rightBox = unionOf(items, mid, job.end);
 
         node.m_firstChild = job.base;
         Job l = { job.begin, mid, job.base, job.base + 2, job.depth + 1, leftBox };
@@ -344,24 +328,106 @@ private:
     }
 
     // Union of the boxes of items [begin, end) in the serial left-to-right association
-    static BBox unionOf(const Item* items, unsigned int begin, unsigned int end, unsigned int workers)
+    static BBox unionOf(const Item* items, unsigned int begin, unsigned int end)
     {
-        const size_t n = end - begin;
-        unsigned int chunks = workers > 1 && n >= (1u << 16) ? workers : 1u;
-        std::vector<BBox> partial(chunks);
-        BBox* part = &partial[0];
-        const Item* first = items + begin;
-        rayito_b200::parallelChunks(n, chunks, [first, part](unsigned c, size_t b, size_t e) {
-            BBox acc;
-            for (size_t i = b; i < e; ++i) acc = acc.combined(first[i].box);
-            part[c] = acc;
-        });
         BBox all;
-        for (unsigned int c = 0; c < chunks; ++c)
-            all = all.combined(partial[c]);
+        for (unsigned int i = begin; i < end; ++i)
+            all = all.combined(items[i].box);
         return all;
     }
 
+    // PERF MODE split (rayito_b200::kTreeSah): binned surface-area heuristic over the element
+    // centres, 16 bins on each axis.  Keeps every convention the traversal relies on -- the first
+    // ("left") child holds the HIGH side of the cut on the node's split axis, children are numbered
+    // base, base + 1 and one element ends up in each leaf -- so the device kernels and the upload do
+    // not know which builder made the tree.  false: no cut separates the centres (all equal); the
+    // caller then cuts the range in half as the reference does.
+    static const int kSahBins = 16;
+    static float halfArea(const BBox& b)
+    {
+        Vector e = b.m_max - b.m_min;
+        return e.m_x * e.m_y + e.m_y * e.m_z + e.m_z * e.m_x;
+    }
+    struct BinAbove
+    {
+        BvhNodeFlags axis;
+        float lo, scale;
+        int cut;
+        int bin(const Item& it) const
+        {
+            float c = (component(it.box.m_max, axis) + component(it.box.m_min, axis)) * 0.5f;
+            int k = (int)((c - lo) * scale);
+            return k < 0 ? 0 : (k > kSahBins - 1 ? kSahBins - 1 : k);
+        }
+        bool operator()(const Item& it) const { return bin(it) >= cut; }
+    };
+    static bool splitNodeSah(Item* items, BvhNode& node, const Job& job, Job& left, Job& right)
+    {
+        BBox centres;
+        for (unsigned int i = job.begin; i < job.end; ++i)
+            centres.expand((items[i].box.m_max + items[i].box.m_min) * 0.5f);
+        float bestCost = std::numeric_limits<float>::max();
+        BinAbove best = { kSplitX, 0.0f, 0.0f, 0 };
+        BBox bestLow, bestHigh;
+        unsigned int bestHighCount = 0;
+        for (BvhNodeFlags axis = kSplitX; axis <= kSplitZ; ++axis)
+        {
+            const float lo = component(centres.m_min, axis), hi = component(centres.m_max, axis);
+            if (!(hi > lo))
+                continue;
+            BinAbove f = { axis, lo, (float)kSahBins / (hi - lo), 0 };
+            BBox box[kSahBins];
+            unsigned int count[kSahBins] = { 0 };
+            for (unsigned int i = job.begin; i < job.end; ++i)
+            {
+                int k = f.bin(items[i]);
+                box[k] = box[k].combined(items[i].box);
+                ++count[k];
+            }
+            // suffix boxes (high side of every cut), then one sweep up from the low side
+            BBox highBox[kSahBins];
+            unsigned int highCount[kSahBins];
+            BBox acc;
+            unsigned int n = 0;
+            for (int k = kSahBins - 1; k >= 0; --k)
+            {
+                acc = acc.combined(box[k]);
+                n += count[k];
+                highBox[k] = acc;
+                highCount[k] = n;
+            }
+            BBox low;
+            unsigned int lowCount = 0;
+            for (int cut = 1; cut < kSahBins; ++cut)
+            {
+                low = low.combined(box[cut - 1]);
+                lowCount += count[cut - 1];
+                if (lowCount == 0 || highCount[cut] == 0)
+                    continue;
+                float cost = halfArea(low) * (float)lowCount + halfArea(highBox[cut]) * (float)highCount[cut];
+                if (cost < bestCost)
+                {
+                    bestCost = cost;
+                    best = f;
+                    best.cut = cut;
+                    bestLow = low;
+                    bestHigh = highBox[cut];
+                    bestHighCount = highCount[cut];
+                }
+            }
+        }
+        if (bestHighCount == 0)
+            return false;
+        node.m_flags = best.axis;
+        std::partition(items + job.begin, items + job.end, best);
+        const unsigned int mid = job.begin + bestHighCount;
+        node.m_firstChild = job.base;
+        Job l = { job.begin, mid, job.base, job.base + 2, job.depth + 1, bestHigh };
+        Job r = { mid, job.end, job.base + 1, job.base + 2 * (mid - job.begin), job.depth + 1, bestLow };
+        left = l;
+        right = r;
+        return true;
+    }
     // Builds one subtree depth-first with an explicit work list instead of recursion
     // (degenerate inputs can be ~N deep).
     struct Builder
@@ -371,6 +437,7 @@ private:
         unsigned int spawnElements;     // 0: never hand subtrees to other workers
         unsigned int* maxDepth;
         std::mutex* depthMutex;
+        unsigned mode;
 
         void operator()(const Job& start, rayito_b200::JobBag<Job>& bag) const
         {
@@ -384,7 +451,7 @@ private:
                 if (job.depth > deepest)
                     deepest = job.depth;
                 Job left, right;
-                if (!splitNode(items, nodes, job, left, right, 1u, NULL))
+                if (!splitNode(items, nodes, job, left, right, mode))
                     continue;
                 if (spawnElements != 0 && right.end - right.begin >= spawnElements)
                     bag.add(right);

@@ -170,81 +170,6 @@ private:
     std::exception_ptr m_failure;
 };
 
-// std::partition, with the element order libstdc++ produces, on several threads.
-//
-// libstdc++'s partition for bidirectional iterators walks one cursor up from the left past
-// elements that satisfy the predicate and one down from the right past elements that do not,
-// swaps the two it stops at and repeats until the cursors meet.  With m elements satisfying the
-// predicate, the cursors meet at m, so the elements that move are exactly the "false" ones in
-// [0, m) and the "true" ones in [m, n), and the k-th false from the left changes places with the
-// k-th true from the right.  Everything else stays where it is.  That makes the permutation a
-// pair of ordered index lists and one swap per pair -- data-parallel, and identical to the
-// serial result element for element (tests/cpp/parallel_partition_test.cpp checks it against
-// std::partition itself).  The BVH build depends on that order (RAccel.h:337-352).
-// `scratch`: room for n unsigned ints.  Returns the partition point, as std::partition does.
-template <typename T, typename Pred>
-inline T* parallelPartition(T* first, size_t n, Pred pred, unsigned* scratch, unsigned chunks)
-{
-    if (chunks <= 1 || n < 2)
-        return std::partition(first, first + n, pred);
-    // pass 1: how many elements of each chunk satisfy the predicate
-    std::vector<size_t> trues(chunks + 1, 0);
-    size_t* tr = &trues[0];
-    parallelChunks(n, chunks, [=](unsigned c, size_t b, size_t e) {
-        size_t count = 0;
-        for (size_t i = b; i < e; ++i)
-            count += pred(first[i]) ? 1 : 0;
-        tr[c + 1] = count;
-    });
-    size_t m = 0;
-    for (unsigned c = 0; c < chunks; ++c)
-        m += trues[c + 1];
-    if (m == 0 || m == n)
-        return first + m;
-    // pass 2: movers per chunk -- falses below m (left list), trues at or above m (right list)
-    std::vector<size_t> leftAt(chunks + 1, 0), rightAt(chunks + 1, 0);
-    size_t* la = &leftAt[0];
-    size_t* ra = &rightAt[0];
-    parallelChunks(n, chunks, [=](unsigned c, size_t b, size_t e) {
-        size_t lo = 0, hi = 0;
-        for (size_t i = b; i < e; ++i)
-        {
-            const bool t = pred(first[i]);
-            if (i < m) lo += t ? 0 : 1; else hi += t ? 1 : 0;
-        }
-        la[c + 1] = lo;
-        ra[c + 1] = hi;
-    });
-    for (unsigned c = 0; c < chunks; ++c)
-    {
-        leftAt[c + 1] += leftAt[c];
-        rightAt[c + 1] += rightAt[c];
-    }
-    const size_t movers = leftAt[chunks];       // == rightAt[chunks]
-    // pass 3: the two index lists.  left[k]: k-th false from the left; right[k]: k-th true from
-    // the RIGHT, i.e. the (movers-1-k)-th in ascending order.
-    unsigned* left = scratch;
-    unsigned* right = scratch + movers;
-    parallelChunks(n, chunks, [=](unsigned c, size_t b, size_t e) {
-        size_t lo = la[c], hi = ra[c];
-        for (size_t i = b; i < e; ++i)
-        {
-            const bool t = pred(first[i]);
-            if (i < m) { if (!t) left[lo++] = (unsigned)i; }
-            else if (t) right[movers - 1 - hi++] = (unsigned)i;
-        }
-    });
-    // pass 4: the swaps (disjoint pairs)
-    unsigned swapChunks = chunks;
-    if (movers < (size_t)swapChunks * 1024)
-        swapChunks = (unsigned)(movers / 1024) ? (unsigned)(movers / 1024) : 1u;
-    parallelChunks(movers, swapChunks, [=](unsigned, size_t b, size_t e) {
-        for (size_t k = b; k < e; ++k)
-            std::swap(first[left[k]], first[right[k]]);
-    });
-    return first + m;
-}
-
 // Per-thread scratch block that survives between calls: a 10 M-triangle prepare() needs
 // 140 MB of build items, and handing that back to the OS after every raytrace() means
 // ~35 000 page faults to get it again on the next one.  releaseHostCaches() frees it.

@@ -377,10 +377,11 @@ public:
         }
         m_faceAreaCDF[numFaces] = m_totalArea;
 
+        // (rayito_b200::treeMode(): the reference's tree unless the application asked for the perf-mode one)
         if (rayito_b200::stageSemantics() == RT_SEMANTICS_STAGE6)
-            m_bvh.build(&m_bbox);       // all vertices, used by a face or not (S6 RMesh.h:82-86)
+            m_bvh.build(&m_bbox, rayito_b200::treeMode());       // all vertices, used by a face or not (S6 RMesh.h:82-86)
         else
-            m_bvh.build();
+            m_bvh.build(NULL, rayito_b200::treeMode());
     }
 
     virtual unsigned int numElements() const { return (unsigned int)m_faces.size(); }

@@ -1,8 +1,7 @@
 """CPU tests: the host worker threads (rayito_b200/host/rayito_b200/parallel.hpp) must not
 change a single bit of what prepare() + flatten hand to the GPU.  A mesh large enough to
 take the threaded path (>= 65 536 faces: subtree jobs, chunked bounds / areas / face tables)
-(and, at 327 680 faces with RAYITO_B200_WIDE_SPLITS=1, the all-worker splits at the top of the tree
-with their exact parallel std::partition) is prepared with 1, 3 and 8 workers and compared array by array; the single-thread result is
+is prepared with 1, 3 and 8 workers and compared array by array; the single-thread result is
 compared node for node with the compiled reference (oracle/_ref), Bvh<T>::build
 (Rayito_Stage7_QT/RAccel.h:262-374) and Mesh::prepare (RMesh.h:89-129)."""
 import ctypes as C
@@ -11,7 +10,7 @@ import os
 import numpy as np
 import pytest
 
-GRID = (640, 512)       # 327 680 quads: above the 262 144-element threshold of the opt-in all-worker top splits (RAYITO_B200_WIDE_SPLITS=1)
+GRID = (640, 512)       # 327 680 quads
 
 
 def _bytes(ptr, nbytes):
@@ -20,12 +19,11 @@ def _bytes(ptr, nbytes):
     return C.string_at(ptr, nbytes)
 
 
-def _snapshot(capi, threads, wide=False):
-    saved = {k: os.environ.get(k) for k in ("RAYITO_B200_HOST_THREADS", "RAYITO_B200_WIDE_SPLITS")}
+def _snapshot(capi, threads, tree=0):
+    saved = {k: os.environ.get(k) for k in ("RAYITO_B200_HOST_THREADS",)}
     os.environ["RAYITO_B200_HOST_THREADS"] = str(threads)
-    os.environ["RAYITO_B200_WIDE_SPLITS"] = "1" if wide else "0"
     try:
-        scene = capi.HostScene(capi.RECIPE_SYNTHETIC_MESH, None, GRID)
+        scene = capi.HostScene(capi.RECIPE_SYNTHETIC_MESH, None, GRID, tree=tree)
     finally:
         for k, v in saved.items():
             if v is None:
@@ -55,10 +53,10 @@ def serial(capi):
     return _snapshot(capi, 1)
 
 
-@pytest.mark.parametrize("threads,wide", [(3, False), (8, False), (3, True), (8, True)])
-def test_threaded_prepare_is_bit_identical(capi, serial, threads, wide):
+@pytest.mark.parametrize("threads", [3, 8])
+def test_threaded_prepare_is_bit_identical(capi, serial, threads):
     _scene, want = serial
-    _scene2, got = _snapshot(capi, threads, wide)
+    _scene2, got = _snapshot(capi, threads)
     assert got["counts"] == want["counts"] and want["counts"][0] == GRID[0] * GRID[1]
     for key in want:
         assert got[key] == want[key], "%s differs with %d host threads" % (key, threads)
@@ -103,13 +101,51 @@ def test_app_handle_builds_without_preparing(capi):
     assert lib.rth_app_create(12345, None, 0, 0) in (None, 0)
 
 
-def test_parallel_partition_equals_std_partition(tmp_path):
-    """rayito_b200::parallelPartition reproduces libstdc++'s std::partition element for element
-    (300 size / split / thread-count cases, including all-true, all-false and tiny ranges)."""
-    import subprocess
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    exe = str(tmp_path / "parallel_partition_test")
-    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++11", "-pthread", "-I" + os.path.join(root, "rayito_b200", "host"),
-                    os.path.join(root, "tests", "cpp", "parallel_partition_test.cpp"), "-o", exe], check=True, timeout=300)
-    out = subprocess.run([exe], check=True, capture_output=True, text=True, timeout=300).stdout
-    assert "300 cases identical" in out, out
+def _check_tree(nodes, num_faces):
+    """Structural validity of a face BVH in the reference's node format: every face in exactly one
+    leaf, children numbered b, b+1, every child's box inside its parent's, the first child on the
+    HIGH side of the split axis (what the traversal's near / far choice relies on)."""
+    boxes = nodes[:, :6].view(np.float32)
+    word, flags = nodes[:, 6], nodes[:, 7]
+    leaf = (flags & 4) != 0
+    assert nodes.shape[0] == 2 * num_faces - 1
+    assert np.array_equal(np.sort(word[leaf]), np.arange(num_faces, dtype=np.uint32))
+    inner = np.nonzero(~leaf)[0]
+    first = word[inner].astype(np.int64)
+    kids = np.sort(np.concatenate([first, first + 1]))
+    assert np.array_equal(kids, np.arange(1, nodes.shape[0]))          # every node but the root is somebody's child, once
+    for c in (first, first + 1):
+        assert (boxes[c, :3] >= boxes[inner, :3]).all() and (boxes[c, 3:] <= boxes[inner, 3:]).all()
+    axis = (flags[inner] & 3).astype(np.int64)
+    assert (axis <= 2).all()
+    centre = 0.5 * (boxes[:, :3] + boxes[:, 3:])
+    rows = np.arange(len(inner))
+    # box centres of the two sides: the first child is the high side (ties allowed where the range was cut in half)
+    assert (centre[first, axis][rows] >= centre[first + 1, axis][rows] - 1e-6).mean() > 0.99
+    depth = np.zeros(nodes.shape[0], np.int32)
+    order = inner[np.argsort(inner)]
+    for i in order:                 # children are numbered above their parent
+        depth[word[i]] = depth[word[i] + 1] = depth[i] + 1
+    return int(depth.max())
+
+
+def test_perf_mode_tree_is_a_valid_bvh_and_threads_do_not_change_it(capi, serial):
+    """rth_set_tree_mode(1): the binned-SAH face BVH (PERF MODE, rayito_b200/host/rayito_b200/accel.hpp) has the
+    reference's node format and conventions, differs from the reference's tree, and is the same whatever the
+    number of host workers; everything else prepare() produces is untouched."""
+    _ref_scene, want = serial
+    scene1, one = _snapshot(capi, 1, tree=capi.TREE_SAH)
+    _scene8, eight = _snapshot(capi, 8, tree=capi.TREE_SAH)
+    assert one["mesh_nodes"] == eight["mesh_nodes"] and one["depth"] == eight["depth"]
+    assert one["mesh_nodes"] != want["mesh_nodes"]
+    for key in ("vertices", "normals", "face_start", "vertex_index", "normal_index", "cdf", "top_nodes", "counts"):
+        assert one[key] == want[key], key
+    nodes = np.frombuffer(one["mesh_nodes"], np.uint32).reshape(-1, 8)
+    depth = _check_tree(nodes, GRID[0] * GRID[1])
+    assert depth == one["depth"]
+    ref_depth = _check_tree(np.frombuffer(want["mesh_nodes"], np.uint32).reshape(-1, 8), GRID[0] * GRID[1])
+    assert ref_depth == want["depth"]
+    assert depth <= ref_depth       # the midpoint rule degenerates at the poles of the displaced sphere
+    # a later scene on the same thread gets the reference's tree again (the mode is per call of HostScene)
+    _again, back = _snapshot(capi, 1)
+    assert back["mesh_nodes"] == want["mesh_nodes"]
