@@ -65,6 +65,10 @@ WORKLOADS = {
     # its roofline counts the work done on ITS tree.  Never part of the default run.
     "c5-64spp-sah": dict(recipe=5, width=3840, height=2160, ps=8, ls=1, depth=3, grid=(2236, 2236), tree=1,
                          label="synthetic displaced sphere, 9 999 392 triangles, 3840x2160 64spp, PERF-MODE tree (binned SAH)"),
+    # the reference's tree built ON THE GPU inside the scene upload (rth_set_tree_mode(2), rt_scene_create_ex):
+    # same tree node for node, so `value` is unchanged; the e2e leg shows what the host build and the node upload cost
+    "c5-64spp-devbuild": dict(recipe=5, width=3840, height=2160, ps=8, ls=1, depth=3, grid=(2236, 2236), tree=2,
+                              label="synthetic displaced sphere, 9 999 392 triangles, 3840x2160 64spp, face BVH built on the device"),
     "c3": dict(recipe=6, stage=6, width=1920, height=1080, ps=8, ls=1, depth=3, grid=(0, 0),
                label="Rayito_Stage6 scene (bumpy.obj, BVH, two area lights, Stage 6 rules) 1920x1080 64spp ls1 depth3"),
 }
@@ -390,7 +394,7 @@ def measure_workload(env, name, steps, warmup, want_e2e, want_cpu):
     t0 = time.perf_counter()
     hscene = capi.HostScene(wl["recipe"], obj, wl["grid"], tree=wl.get("tree", 0))
     host_prepare_s = time.perf_counter() - t0
-    dscene = capi.DeviceScene(hscene.desc, device=local_rank)
+    dscene = capi.DeviceScene(hscene.desc, device=local_rank, build_bvh_on_device=wl.get("tree", 0) == capi.TREE_DEVICE)
     spec = hscene.default_camera_spec()
     cam = capi.camera_from_spec(spec)
     W, H, ps, ls, depth = wl["width"], wl["height"], wl["ps"], wl["ls"], wl["depth"]

@@ -240,7 +240,19 @@ int rt_device_count(void);
 /* Upload a prepared scene to `device`.  Stands behind scene.prepare() at
  * RaytraceMain.cpp:497.  Fails with RT_ERR_DEPTH if any BVH is deeper than 49. */
 int rt_scene_create(const RtSceneDesc* desc, int device, RtScene** out_scene);
+/* The same with options.  RT_SCENE_BUILD_MESH_BVH: Bvh<Mesh>::build (RAccel.h:262-374, called from
+ * Mesh::prepare, RMesh.h:128) runs ON THE DEVICE for every mesh, out of the uploaded faces: desc->mesh_nodes
+ * is not read (may be NULL; RtMesh.first_node / num_nodes are ignored, a mesh of F faces gets 2F-1 nodes) and
+ * no node crosses PCIe.  The tree is the reference's, node for node -- element order of std::partition,
+ * slot numbering of the recursion, boxes down to the sign of a zero (rayito_b200/csrc/rt_build.cuh) --
+ * so hit records stay bit-equal.  Stage 7 semantics only. */
+enum { RT_SCENE_BUILD_MESH_BVH = 1u };
+int rt_scene_create_ex(const RtSceneDesc* desc, int device, uint32_t flags, RtScene** out_scene);
 int rt_scene_destroy(RtScene* scene);
+/* Read a mesh's face BVH back in the reference's node format (RtBvhNode: leaves name their face), whoever built
+ * it: `nodes` receives min(capacity, 2F-1) nodes.  depth (may be NULL): deepest leaf, root = 0; build_ms (may
+ * be NULL): device time of the device build of all meshes, 0 for a host-built scene.  For tests and tools. */
+int rt_scene_mesh_nodes(RtScene* scene, uint32_t mesh, RtBvhNode* nodes, uint32_t capacity, uint32_t* depth, float* build_ms);
 
 /* ShapeSet::intersect (RScene.h:120-156) for n rays; host buffers. */
 int rt_trace_closest(RtScene* scene, const RtRay* rays, size_t n, RtHit* hits);

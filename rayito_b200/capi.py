@@ -110,6 +110,7 @@ CORE_SYMBOLS = [
     "rt_scene_create", "rt_scene_destroy",
     "rt_trace_closest", "rt_trace_closest_ex", "rt_trace_any",
     "rt_trace_closest_device", "rt_trace_any_device", "rt_trace_closest_counted", "rt_trace_any_counted",
+    "rt_scene_create_ex", "rt_scene_mesh_nodes",
     "rt_render", "rt_render_device", "rt_generate_camera_rays", "rt_tonemap_bgra8", "rt_tonemap_bgra8_device",
     "rt_stage1_render_float",
     "rt_tile_owners", "rt_sample_permutations", "rt_cmj_sample1d", "rt_cmj_sample2d", "rt_stage1_render",
@@ -121,7 +122,8 @@ HOST_SYMBOLS = [
     "rth_last_error_string", "rth_camera", "rth_stage1_render", "rth_stage1_render_float", "rth_stage23_render",
     "rth_set_tree_mode",
 ]
-TREE_REFERENCE, TREE_SAH = 0, 1     # rth_set_tree_mode (include/rayito_b200_host.h)
+TREE_REFERENCE, TREE_SAH, TREE_DEVICE = 0, 1, 2     # rth_set_tree_mode (include/rayito_b200_host.h)
+RT_SCENE_BUILD_MESH_BVH = 1                         # rt_scene_create_ex flags (include/rayito_b200.h)
 # fixtures/rayito_fixtures.h (test infrastructure: the recipe scenes)
 FIXTURE_SYMBOLS = [
     "rthf_last_error_string", "rth_scene_create", "rth_scene_destroy", "rth_scene_desc",
@@ -142,6 +144,8 @@ def core():
         vp, sz, u32 = C.c_void_p, C.c_size_t, C.c_uint32
         lib.rt_last_error_string.restype = C.c_char_p
         lib.rt_scene_create.argtypes = [vp, C.c_int, C.POINTER(vp)]
+        lib.rt_scene_create_ex.argtypes = [vp, C.c_int, u32, C.POINTER(vp)]
+        lib.rt_scene_mesh_nodes.argtypes = [vp, u32, vp, u32, C.POINTER(u32), C.POINTER(C.c_float)]
         lib.rt_scene_destroy.argtypes = [vp]
         lib.rt_trace_closest.argtypes = [vp, vp, sz, vp]
         lib.rt_trace_closest_ex.argtypes = [vp, vp, sz, vp]
@@ -307,10 +311,22 @@ def camera_from_spec(spec14):
 class DeviceScene:
     """RtScene handle: a flattened scene uploaded to one GPU."""
 
-    def __init__(self, desc, device=0):
+    def __init__(self, desc, device=0, build_bvh_on_device=False):
         self.handle = C.c_void_p()
-        check(core().rt_scene_create(C.cast(desc, C.c_void_p), device, C.byref(self.handle)), "rt_scene_create")
+        if build_bvh_on_device:
+            check(core().rt_scene_create_ex(C.cast(desc, C.c_void_p), device, RT_SCENE_BUILD_MESH_BVH, C.byref(self.handle)),
+                  "rt_scene_create_ex")
+        else:
+            check(core().rt_scene_create(C.cast(desc, C.c_void_p), device, C.byref(self.handle)), "rt_scene_create")
         self.device = device
+
+    def mesh_nodes(self, mesh, num_faces):
+        """(nodes as uint32 [2F-1, 8] in the reference's RtBvhNode layout, deepest leaf, device build ms)"""
+        nodes = np.zeros((max(2 * num_faces - 1, 0), 8), np.uint32)
+        depth, ms = C.c_uint32(0), C.c_float(0.0)
+        check(core().rt_scene_mesh_nodes(self.handle, mesh, nodes.ctypes.data, nodes.shape[0], C.byref(depth), C.byref(ms)),
+              "rt_scene_mesh_nodes")
+        return nodes, int(depth.value), float(ms.value)
 
     def trace_closest(self, rays, extended=False):
         rays = np.ascontiguousarray(rays)

@@ -7,6 +7,7 @@
 #include <string>
 
 #include "rt_scene.cuh"
+#include "rt_build.cuh"
 #include "rt_trace.cuh"
 #include "rt_wave.cuh"
 #include "rt_render.cuh"
@@ -225,7 +226,48 @@ int rt_device_count(void)
 
 int rt_scene_create(const RtSceneDesc* desc, int device, RtScene** out_scene)
 {
-    return rt_scene_build(desc, device, out_scene);
+    return rt_scene_build(desc, device, 0u, out_scene);
+}
+
+int rt_scene_create_ex(const RtSceneDesc* desc, int device, uint32_t flags, RtScene** out_scene)
+{
+    return rt_scene_build(desc, device, flags, out_scene);
+}
+
+int rt_scene_mesh_nodes(RtScene* s, uint32_t mesh, RtBvhNode* nodes, uint32_t capacity, uint32_t* depth, float* build_ms)
+{
+    if (s == NULL || mesh >= s->mesh_faces.size() || (capacity && nodes == NULL))
+        return rt_fail(RT_ERR_ARG, "null argument or mesh index out of range");
+    RT_CUDA(cudaSetDevice(s->device));
+    if (depth) *depth = s->mesh_depth < 0 ? 0u : (uint32_t)s->mesh_depth;      // (deepest of all meshes)
+    if (build_ms) *build_ms = s->bvh_build_ms;
+    const uint32_t faces = s->mesh_faces[mesh];
+    const uint32_t count = std::min<uint32_t>(capacity, faces ? 2 * faces - 1 : 0u);
+    if (count == 0)
+        return RT_OK;
+    std::vector<DNode> dn(count);
+    std::vector<uint32_t> fft((size_t)faces + 1);
+    RT_CUDA(cudaMemcpy(dn.data(), s->d.mesh_nodes + s->mesh_first_node[mesh], (size_t)count * sizeof(DNode), cudaMemcpyDeviceToHost));
+    RT_CUDA(cudaMemcpy(fft.data(), s->d.face_first_tri + s->mesh_first_face[mesh], fft.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    for (uint32_t i = 0; i < count; ++i)
+    {
+        RtBvhNode& n = nodes[i];
+        n.bbox_min[0] = dn[i].q0.x; n.bbox_min[1] = dn[i].q0.y; n.bbox_min[2] = dn[i].q0.z;
+        n.bbox_max[0] = dn[i].q0.w; n.bbox_max[1] = dn[i].q1.x; n.bbox_max[2] = dn[i].q1.y;
+        uint32_t word, flags;
+        std::memcpy(&word, &dn[i].q1.z, 4);
+        std::memcpy(&flags, &dn[i].q1.w, 4);
+        if (flags & RT_NODE_LEAF)
+        {
+            // leaves are stored as (first triangle record, count): back to the face that owns the record
+            const uint32_t* at = std::upper_bound(fft.data(), fft.data() + fft.size(), word);
+            word = (uint32_t)(at - fft.data()) - 1u;
+            flags = RT_NODE_LEAF;
+        }
+        n.first_child_or_prim = word;
+        n.flags = flags;
+    }
+    return RT_OK;
 }
 
 int rt_scene_destroy(RtScene* s)

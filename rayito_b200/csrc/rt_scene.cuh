@@ -53,6 +53,10 @@ struct RtScene
     std::vector<uint32_t> shape_brdfs;  // RT_BRDF_* of every shape's material
     bool has_lambert, has_glossy;       // BRDF kinds among the scene's materials
     float upload_ms;
+    float bvh_build_ms;                      // device time of the face-BVH build (RT_SCENE_BUILD_MESH_BVH), else 0
+    int mesh_depth;                          // deepest leaf of any face BVH (-1: no mesh)
+    std::vector<uint32_t> mesh_first_node;   // device node slot of every mesh's root
+    std::vector<uint32_t> mesh_first_face, mesh_faces;
     // scratch for the host-buffer entry points (grown on demand)
     void* scratch_in;
     void* scratch_out;
@@ -352,12 +356,26 @@ inline float vlen(const float* v) { return std::sqrt(v[0] * v[0] + v[1] * v[1] +
 
 } // namespace rt_detail
 
-inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_scene)
+namespace rt_build
+{
+// rt_build.cuh: the face BVH of one mesh built on the device, node for node the reference's tree
+inline int build_mesh(int device, DNode* nodes, const float4* tris, const uint32_t* fft, uint32_t first_face, uint32_t num_faces,
+                      int* depth, float* build_ms);
+}
+
+// flags: RT_SCENE_* of include/rayito_b200.h.  RT_SCENE_BUILD_MESH_BVH: desc->mesh_nodes is not read (may be
+// NULL); every mesh's face BVH is built on the device after the upload (rt_build.cuh).
+inline int rt_scene_build(const RtSceneDesc* desc, int device, uint32_t flags, RtScene** out_scene)
 {
     using namespace rt_detail;
     if (desc == NULL || out_scene == NULL)
         return rt_fail(RT_ERR_ARG, "null argument");
     *out_scene = NULL;
+    if (flags & ~(uint32_t)RT_SCENE_BUILD_MESH_BVH)
+        return rt_fail(RT_ERR_ARG, "unknown scene flags");
+    const bool dev_build = (flags & RT_SCENE_BUILD_MESH_BVH) != 0;
+    if (dev_build && desc->semantics != RT_SEMANTICS_STAGE7)
+        return rt_fail(RT_ERR_UNSUPPORTED, "the device BVH build reproduces the Stage 7 builder only (Stage 6 roots its face BVH in the all-vertex box)");
     if (desc->abi_version != RT_ABI_VERSION)
         return rt_fail(RT_ERR_ARG, "RtSceneDesc.abi_version mismatch");
     const uint32_t num_shapes = desc->num_finite + desc->num_infinite;
@@ -375,7 +393,7 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
     // every array with a non-zero count must be there
     if ((desc->num_xforms && desc->xforms == NULL) ||
         (desc->num_keys && (desc->key_time == NULL || desc->key_scale == NULL || desc->key_rotation == NULL || desc->key_translation == NULL)) ||
-        (desc->num_top_nodes && desc->top_nodes == NULL) || (desc->num_mesh_nodes && desc->mesh_nodes == NULL) ||
+        (desc->num_top_nodes && desc->top_nodes == NULL) || (!dev_build && desc->num_mesh_nodes && desc->mesh_nodes == NULL) ||
         (desc->num_planes && desc->planes == NULL) || (desc->num_spheres && desc->spheres == NULL) ||
         (desc->num_rects && desc->rects == NULL) || (desc->num_meshes && desc->meshes == NULL) ||
         (desc->num_vertices && desc->vertices == NULL) || (desc->num_normals && desc->normals == NULL) ||
@@ -540,15 +558,19 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
     if (top_depth > 49)
         return rt_fail(RT_ERR_DEPTH, "top-level BVH deeper than 49");
     int mesh_depth = -1;
+    std::vector<uint32_t> mesh_num_nodes(desc->num_meshes, 0);     // nodes of every mesh's face BVH (given, or to be built)
     for (uint32_t m = 0; m < desc->num_meshes; ++m)
     {
         const RtMesh& mesh = desc->meshes[m];
-        if ((uint64_t)mesh.first_node + mesh.num_nodes > desc->num_mesh_nodes ||
+        mesh_num_nodes[m] = dev_build ? (mesh.num_faces ? 2 * mesh.num_faces - 1 : 0u) : mesh.num_nodes;
+        if ((!dev_build && (uint64_t)mesh.first_node + mesh.num_nodes > desc->num_mesh_nodes) ||
             (uint64_t)mesh.first_face + mesh.num_faces > desc->num_faces ||
             (uint64_t)mesh.first_vertex + mesh.num_vertices > desc->num_vertices ||
             (uint64_t)mesh.first_normal + mesh.num_normals > desc->num_normals ||
             (uint64_t)mesh.first_cdf + mesh.num_faces + 1 > desc->num_cdf)
             return rt_fail(RT_ERR_ARG, "mesh ranges out of bounds");
+        if (dev_build)
+            continue;           // depth: known once the device has built the tree
         if (mesh.num_nodes != 0 && mesh.num_nodes != 2 * mesh.num_faces - 1)
             return rt_fail(RT_ERR_ARG, "mesh BVH must have 2*faces-1 nodes");
         int d = bvh_depth(desc->mesh_nodes + mesh.first_node, mesh.num_nodes, mesh.num_faces, why);
@@ -588,7 +610,7 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
         if (align_pairs && (dev_nodes & 1u) == 0)
             ++dev_nodes;
         dev_first_node[m] = (uint32_t)dev_nodes;
-        dev_nodes += desc->meshes[m].num_nodes;
+        dev_nodes += mesh_num_nodes[m];
     }
     // the face-BVH pass packs (child pair index, split axis) and (leaf flag, first triangle record) into one word each
     if (dev_nodes >= (1ull << 29) || num_tris >= (1ull << 31))
@@ -599,7 +621,7 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
         const RtMesh& mesh = desc->meshes[m];
         DMesh dm;
         dm.first_node = dev_first_node[m];
-        dm.num_nodes = mesh.num_nodes;
+        dm.num_nodes = mesh_num_nodes[m];
         dm.first_tri = face_first_tri[mesh.first_face];
         dm.first_face = mesh.first_face;
         dm.num_faces = mesh.num_faces;
@@ -748,7 +770,8 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
     ArenaBuilder ab;
     size_t o_shapes = ab.put(shapes.data(), shapes.size() * sizeof(DShapeMem));
     size_t o_top = ab.put(top_nodes.data(), top_nodes.size() * sizeof(DNode));
-    size_t o_mnodes = ab.reserve((size_t)dev_nodes * sizeof(DNode));     // built in place below
+    // (with a device build the node slots go last and are not part of the copy: nothing of the tree crosses PCIe)
+    size_t o_mnodes = dev_build ? 0 : ab.reserve((size_t)dev_nodes * sizeof(DNode));     // built in place below
     size_t o_tris = ab.reserve((size_t)num_tris * 3 * sizeof(float4));
     size_t o_trin = ab.reserve((size_t)num_tris * sizeof(uint4));
     size_t o_fft = ab.put(face_first_tri.data(), face_first_tri.size() * sizeof(uint32_t));
@@ -767,6 +790,13 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
     size_t o_lights = ab.put(desc->lights, (size_t)desc->num_lights * 4);
     size_t o_walk = ab.put(top_walk.data(), top_walk.size() * sizeof(DTopStep));
     size_t o_anim = ab.put(anim.data(), anim.size() * sizeof(uint4));
+    const size_t copy_bytes = ab.total;
+    size_t arena_total = ab.total;
+    if (dev_build)
+    {
+        o_mnodes = (ab.total + 255) & ~(size_t)255;
+        arena_total = o_mnodes + (size_t)(dev_nodes ? dev_nodes : 1) * sizeof(DNode);
+    }
 
     hc[2] = std::chrono::steady_clock::now();
     int ndev = 0;
@@ -799,7 +829,7 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
     {
         float4* tris = ab.at<float4>(o_tris);
         uint4* tri_normals = ab.at<uint4>(o_trin);
-        DNode* mesh_nodes = ab.at<DNode>(o_mnodes);
+        DNode* mesh_nodes = dev_build ? NULL : ab.at<DNode>(o_mnodes);
         const uint32_t* fft = face_first_tri.data();
         std::atomic<int> bad(0);
         for (uint32_t m = 0; m < desc->num_meshes; ++m)
@@ -844,6 +874,8 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
                     }
                 }
             });
+            if (dev_build)
+                continue;
             const uint32_t dev_first = dev_first_node[m];
             if (dev_first != 0)
                 std::memset(&mesh_nodes[dev_first - 1], 0, sizeof(DNode));      // the padding slot
@@ -883,7 +915,7 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
     RtScene* sc = new RtScene();
     sc->device = device;
     sc->arena = NULL;
-    sc->arena_bytes = ab.total;
+    sc->arena_bytes = arena_total;
     sc->stack_cap = stack_cap;
     sc->top_stack_need = desc->num_top_nodes ? top_depth + 1 : (int)desc->num_finite;
     sc->mesh_stack_need = mesh_depth >= 0 ? mesh_depth + 1 : 0;
@@ -927,7 +959,7 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
     if (err == cudaSuccess) err = cudaMemset(sc->d_work, 0, 8 * sizeof(uint64_t));
     if (err == cudaSuccess) err = pool_alloc(device, (void**)&sc->d_cursor, 64, &sc->cursor_alloc);
     cudaEventRecord(e0, 0);
-    if (err == cudaSuccess) err = cudaMemcpy(sc->arena, ab.block, sc->arena_bytes, cudaMemcpyHostToDevice);
+    if (err == cudaSuccess) err = cudaMemcpy(sc->arena, ab.block, copy_bytes, cudaMemcpyHostToDevice);
     cudaEventRecord(e1, 0);
     cudaEventSynchronize(e1);
     sc->upload_ms = 0.0f;
@@ -942,7 +974,7 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
             ms[i] = std::chrono::duration<double, std::milli>(hc[i + 1] - hc[i]).count();
         std::fprintf(stderr, "[rayito_b200] rt_scene_create host clock: validate BVHs %.1f ms, small records + layout %.1f, "
                              "device select %.1f, stage triangles/nodes %.1f, alloc + copy %.1f (copy alone %.1f, %.1f MB)\n",
-                     ms[0], ms[1], ms[2], ms[3], ms[4], sc->upload_ms, sc->arena_bytes / 1e6);
+                     ms[0], ms[1], ms[2], ms[3], ms[4], sc->upload_ms, copy_bytes / 1e6);
     }
     if (err != cudaSuccess)
     {
@@ -986,6 +1018,49 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, RtScene** out_sce
     d.anim = reinterpret_cast<const uint4*>(base + o_anim);
     d.num_anim = (uint32_t)anim.size();
     d.anim_stride = anim_stride;
+
+    sc->mesh_first_node = dev_first_node;
+    sc->mesh_first_face.resize(desc->num_meshes);
+    sc->mesh_faces.resize(desc->num_meshes);
+    for (uint32_t m = 0; m < desc->num_meshes; ++m)
+    {
+        sc->mesh_first_face[m] = desc->meshes[m].first_face;
+        sc->mesh_faces[m] = desc->meshes[m].num_faces;
+    }
+    sc->bvh_build_ms = 0.0f;
+    sc->mesh_depth = mesh_depth;
+    if (dev_build)
+    {
+        // Bvh<Mesh>::build for every mesh, on the device, out of the triangle records just uploaded
+        DNode* nodes = reinterpret_cast<DNode*>(static_cast<char*>(sc->arena) + o_mnodes);
+        cudaMemsetAsync(nodes, 0, sizeof(DNode), 0);        // the padding slot in front of the first tree
+        int rc = RT_OK;
+        for (uint32_t m = 0; m < desc->num_meshes && rc == RT_OK; ++m)
+        {
+            int depth = 0;
+            float ms = 0.0f;
+            rc = rt_build::build_mesh(device, nodes + dev_first_node[m], d.tris, d.face_first_tri, desc->meshes[m].first_face,
+                                      desc->meshes[m].num_faces, &depth, &ms);
+            sc->bvh_build_ms += ms;
+            if (rc == RT_OK && depth > 49)
+                rc = rt_fail(RT_ERR_DEPTH, "mesh BVH deeper than 49: the reference's 50-entry traversal stack would overflow");
+            if (depth > mesh_depth) mesh_depth = depth;
+        }
+        if (rc != RT_OK)
+        {
+            pool_free(device, sc->arena, sc->arena_alloc);
+            pool_free(device, sc->d_work, sc->work_alloc);
+            pool_free(device, sc->d_cursor, sc->cursor_alloc);
+            delete sc;
+            return rc;
+        }
+        sc->mesh_depth = mesh_depth;
+        sc->stack_cap = (desc->num_top_nodes ? top_depth + 1 : (int)desc->num_finite) + (mesh_depth >= 0 ? mesh_depth + 1 : 0);
+        sc->mesh_stack_need = mesh_depth >= 0 ? mesh_depth + 1 : 0;
+        if (host_timing)
+            std::fprintf(stderr, "[rayito_b200] rt_scene_create: face BVHs built on the device in %.2f ms (deepest leaf %d)\n",
+                         sc->bvh_build_ms, mesh_depth);
+    }
 
     *out_scene = sc;
     return RT_OK;

@@ -204,7 +204,9 @@ static Image* raytraceImpl(ShapeSet& scene,
     RtSceneDesc desc = flat.desc();
     RtScene* dev = NULL;
     clock_gettime(CLOCK_MONOTONIC, &tp[2]);
-    if (rt_scene_create(&desc, opt.device, &dev) != RT_OK)
+    const uint32_t sceneFlags = rayito_b200::treeMode() == rayito_b200::kTreeDevice && flat.semantics == RT_SEMANTICS_STAGE7
+                                    ? (uint32_t)RT_SCENE_BUILD_MESH_BVH : 0u;      // prepare() left the face BVHs to the GPU
+    if (rt_scene_create_ex(&desc, opt.device, sceneFlags, &dev) != RT_OK)
         throw std::runtime_error(std::string("rayito_b200: rt_scene_create: ") + rt_last_error_string());
     clock_gettime(CLOCK_MONOTONIC, &tp[3]);
 
@@ -418,7 +420,7 @@ const char* rth_last_error_string(void) { return t_hostError.c_str(); }
 
 int rth_set_tree_mode(unsigned mode)
 {
-    if (mode != rayito_b200::kTreeReference && mode != rayito_b200::kTreeSah)
+    if (mode != rayito_b200::kTreeReference && mode != rayito_b200::kTreeSah && mode != rayito_b200::kTreeDevice)
     {
         t_hostError = "rth_set_tree_mode: unknown mode";
         return -1;

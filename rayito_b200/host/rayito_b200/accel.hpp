@@ -150,7 +150,11 @@ namespace rayito_b200
 //                   of its longest axis.  The reference's slab test is not watertight, so a different
 //                   tree can decide a grazing ray differently: parity is MEASURED, not bit-exact
 //                   (tests/test_gpu_perf_tree.py states the bars).  Never the default.
-enum TreeMode { kTreeReference = 0, kTreeSah = 1 };
+//   kTreeDevice     the reference's tree again, node for node, but built ON THE GPU inside raytrace()'s scene
+//                   upload (rt_scene_create_ex with RT_SCENE_BUILD_MESH_BVH, rayito_b200/csrc/rt_build.cuh):
+//                   prepare() leaves the face BVH unbuilt and no node crosses PCIe.  Stage 7 rules only;
+//                   with Stage 6 rules the host builds as usual.
+enum TreeMode { kTreeReference = 0, kTreeSah = 1, kTreeDevice = 2 };
 unsigned& treeMode();
 }
 
@@ -228,6 +232,13 @@ public:
         Builder builder = { items, &m_nodes[0], threads > 1 ? kSpawnElements : 0u, &m_maxDepth, &depthMutex, mode };
         bag.drain(threads, builder);
         return true;
+    }
+
+    // No tree on the host (rayito_b200::kTreeDevice: the GPU builds it during the upload)
+    void clear()
+    {
+        m_nodes.release();
+        m_maxDepth = 0;
     }
 
     const BvhNode* nodes() const { return m_nodes.size() == 0 ? NULL : &m_nodes[0]; }

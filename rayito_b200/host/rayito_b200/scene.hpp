@@ -378,7 +378,9 @@ public:
         m_faceAreaCDF[numFaces] = m_totalArea;
 
         // (rayito_b200::treeMode(): the reference's tree unless the application asked for the perf-mode one)
-        if (rayito_b200::stageSemantics() == RT_SEMANTICS_STAGE6)
+        if (rayito_b200::treeMode() == rayito_b200::kTreeDevice && rayito_b200::stageSemantics() == RT_SEMANTICS_STAGE7)
+            m_bvh.clear();              // built on the GPU out of the uploaded faces (rt_scene_create_ex)
+        else if (rayito_b200::stageSemantics() == RT_SEMANTICS_STAGE6)
             m_bvh.build(&m_bbox, rayito_b200::treeMode());       // all vertices, used by a face or not (S6 RMesh.h:82-86)
         else
             m_bvh.build(NULL, rayito_b200::treeMode());
