@@ -65,10 +65,11 @@ WORKLOADS = {
     # its roofline counts the work done on ITS tree.  Never part of the default run.
     "c5-64spp-sah": dict(recipe=5, width=3840, height=2160, ps=8, ls=1, depth=3, grid=(2236, 2236), tree=1,
                          label="synthetic displaced sphere, 9 999 392 triangles, 3840x2160 64spp, PERF-MODE tree (binned SAH)"),
-    # the reference's tree built ON THE GPU inside the scene upload (rth_set_tree_mode(2), rt_scene_create_ex):
-    # same tree node for node, so `value` is unchanged; the e2e leg shows what the host build and the node upload cost
-    "c5-64spp-devbuild": dict(recipe=5, width=3840, height=2160, ps=8, ls=1, depth=3, grid=(2236, 2236), tree=2,
-                              label="synthetic displaced sphere, 9 999 392 triangles, 3840x2160 64spp, face BVH built on the device"),
+    # the default builds the face BVH of a mesh this large ON THE GPU inside the scene upload (rth_set_tree_mode(3),
+    # rt_scene_create_ex); this workload forces the host build of the same tree (node for node, so `value` is the
+    # same): its e2e leg shows what the host build and the node upload cost
+    "c5-64spp-hostbuild": dict(recipe=5, width=3840, height=2160, ps=8, ls=1, depth=3, grid=(2236, 2236), tree=0,
+                               label="synthetic displaced sphere, 9 999 392 triangles, 3840x2160 64spp, face BVH built on the host's cores"),
     "c3": dict(recipe=6, stage=6, width=1920, height=1080, ps=8, ls=1, depth=3, grid=(0, 0),
                label="Rayito_Stage6 scene (bumpy.obj, BVH, two area lights, Stage 6 rules) 1920x1080 64spp ls1 depth3"),
 }
@@ -392,9 +393,12 @@ def measure_workload(env, name, steps, warmup, want_e2e, want_cpu):
     # ---- scene: built with the C++ host API, flattened, uploaded once ------------
     obj = env.build.model_path("bumpy.obj") if wl["recipe"] in NEEDS_OBJ else None
     t0 = time.perf_counter()
-    hscene = capi.HostScene(wl["recipe"], obj, wl["grid"], tree=wl.get("tree", 0))
+    # the product's default (TREE_AUTO): meshes of 65 536 faces or more get their face BVH built on the device
+    # during the upload, the same tree node for node (tests/test_gpu_build.py)
+    tree = wl.get("tree", capi.TREE_AUTO)
+    hscene = capi.HostScene(wl["recipe"], obj, wl["grid"], tree=tree)
     host_prepare_s = time.perf_counter() - t0
-    dscene = capi.DeviceScene(hscene.desc, device=local_rank, build_bvh_on_device=wl.get("tree", 0) == capi.TREE_DEVICE)
+    dscene = capi.DeviceScene(hscene.desc, device=local_rank, build_bvh_on_device=tree in (capi.TREE_DEVICE, capi.TREE_AUTO))
     spec = hscene.default_camera_spec()
     cam = capi.camera_from_spec(spec)
     W, H, ps, ls, depth = wl["width"], wl["height"], wl["ps"], wl["ls"], wl["depth"]
@@ -635,7 +639,7 @@ def measure_e2e(args, wl, capi, obj, spec, rank, world, local_rank, dev, dist, t
                 raise RuntimeError("e2e frame is not finite")
         return stats.render_ms
 
-    lib.rth_set_tree_mode(wl.get("tree", 0))
+    lib.rth_set_tree_mode(wl.get("tree", capi.TREE_AUTO))
     one()
     if world > 1:
         dist.barrier()
@@ -648,7 +652,7 @@ def measure_e2e(args, wl, capi, obj, spec, rank, world, local_rank, dev, dist, t
     if world > 1:
         dist.barrier()
     wall = time.perf_counter() - t0
-    lib.rth_set_tree_mode(0)
+    lib.rth_set_tree_mode(capi.TREE_AUTO)
     lib.rth_app_destroy(app)
     t = torch.tensor([wall], dtype=torch.float64, device=dev)
     if world > 1:

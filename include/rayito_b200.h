@@ -241,9 +241,9 @@ int rt_device_count(void);
  * RaytraceMain.cpp:497.  Fails with RT_ERR_DEPTH if any BVH is deeper than 49. */
 int rt_scene_create(const RtSceneDesc* desc, int device, RtScene** out_scene);
 /* The same with options.  RT_SCENE_BUILD_MESH_BVH: Bvh<Mesh>::build (RAccel.h:262-374, called from
- * Mesh::prepare, RMesh.h:128) runs ON THE DEVICE for every mesh, out of the uploaded faces: desc->mesh_nodes
- * is not read (may be NULL; RtMesh.first_node / num_nodes are ignored, a mesh of F faces gets 2F-1 nodes) and
- * no node crosses PCIe.  The tree is the reference's, node for node -- element order of std::partition,
+ * Mesh::prepare, RMesh.h:128) runs ON THE DEVICE, out of the uploaded faces, for every mesh that comes without
+ * nodes (RtMesh.num_nodes == 0: a mesh of F faces then gets 2F-1 nodes; meshes that bring their nodes keep
+ * them), and no node of those trees crosses PCIe.  The tree is the reference's, node for node -- element order of std::partition,
  * slot numbering of the recursion, boxes down to the sign of a zero (rayito_b200/csrc/rt_build.cuh) --
  * so hit records stay bit-equal.  Stage 7 semantics only. */
 enum { RT_SCENE_BUILD_MESH_BVH = 1u };

@@ -23,6 +23,7 @@ extern "C" {
 const char* rth_last_error_string(void);
 
 /* Which face BVH Mesh::prepare() builds from now on, on the calling thread (C++: rayito_b200::treeMode()).
+ * 3 = DEFAULT: per mesh, mode 2 from 65 536 faces up and mode 0 below (the same tree either way);
  * 0 = the reference's tree, node for node (Bvh<T>::buildRange, Rayito_Stage7_QT/RAccel.h:290-374; default:
  * hit records bit-equal to the reference); 1 = PERF MODE, a binned-SAH tree in the same node format, traversed
  * by the same kernels.  The reference's slab test is not watertight, so another tree may decide a grazing

@@ -122,7 +122,7 @@ HOST_SYMBOLS = [
     "rth_last_error_string", "rth_camera", "rth_stage1_render", "rth_stage1_render_float", "rth_stage23_render",
     "rth_set_tree_mode",
 ]
-TREE_REFERENCE, TREE_SAH, TREE_DEVICE = 0, 1, 2     # rth_set_tree_mode (include/rayito_b200_host.h)
+TREE_REFERENCE, TREE_SAH, TREE_DEVICE, TREE_AUTO = 0, 1, 2, 3     # rth_set_tree_mode (include/rayito_b200_host.h); AUTO is the library default
 RT_SCENE_BUILD_MESH_BVH = 1                         # rt_scene_create_ex flags (include/rayito_b200.h)
 # fixtures/rayito_fixtures.h (test infrastructure: the recipe scenes)
 FIXTURE_SYMBOLS = [
@@ -259,13 +259,16 @@ class HostScene:
     def __init__(self, recipe, obj_path=None, grid=(0, 0), tree=TREE_REFERENCE):
         lib = host()
         path = obj_path.encode() if obj_path else None
-        # tree: which face BVH prepare() builds (TREE_SAH = the perf-mode tree, parity measured not bit-exact)
+        # tree: which face BVH prepare() builds.  The recipe scenes default to trees built on the HOST so that their
+        # flattened description is complete (tests compare it, rt_scene_create takes it); TREE_AUTO is what an
+        # application gets (large meshes left to the GPU: create the DeviceScene with build_bvh_on_device=True),
+        # TREE_SAH the perf-mode tree (parity measured, not bit-exact)
         if lib.rth_set_tree_mode(tree) != 0:
             raise RtError("rth_set_tree_mode: " + lib.rth_last_error_string().decode())
         try:
             self.handle = lib.rth_scene_create(recipe, path, grid[0], grid[1])
         finally:
-            lib.rth_set_tree_mode(TREE_REFERENCE)
+            lib.rth_set_tree_mode(TREE_AUTO)
         if not self.handle:
             raise RtError("rth_scene_create: " + lib.rth_last_error_string().decode())
         self.recipe = recipe

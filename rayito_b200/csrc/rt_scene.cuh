@@ -363,8 +363,9 @@ inline int build_mesh(int device, DNode* nodes, const float4* tris, const uint32
                       int* depth, float* build_ms);
 }
 
-// flags: RT_SCENE_* of include/rayito_b200.h.  RT_SCENE_BUILD_MESH_BVH: desc->mesh_nodes is not read (may be
-// NULL); every mesh's face BVH is built on the device after the upload (rt_build.cuh).
+// flags: RT_SCENE_* of include/rayito_b200.h.  RT_SCENE_BUILD_MESH_BVH: the face BVH of every mesh that comes
+// without nodes (RtMesh.num_nodes == 0) is built on the device after the upload (rt_build.cuh); meshes that
+// bring their nodes keep them.
 inline int rt_scene_build(const RtSceneDesc* desc, int device, uint32_t flags, RtScene** out_scene)
 {
     using namespace rt_detail;
@@ -393,7 +394,7 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, uint32_t flags, R
     // every array with a non-zero count must be there
     if ((desc->num_xforms && desc->xforms == NULL) ||
         (desc->num_keys && (desc->key_time == NULL || desc->key_scale == NULL || desc->key_rotation == NULL || desc->key_translation == NULL)) ||
-        (desc->num_top_nodes && desc->top_nodes == NULL) || (!dev_build && desc->num_mesh_nodes && desc->mesh_nodes == NULL) ||
+        (desc->num_top_nodes && desc->top_nodes == NULL) || (desc->num_mesh_nodes && desc->mesh_nodes == NULL) ||
         (desc->num_planes && desc->planes == NULL) || (desc->num_spheres && desc->spheres == NULL) ||
         (desc->num_rects && desc->rects == NULL) || (desc->num_meshes && desc->meshes == NULL) ||
         (desc->num_vertices && desc->vertices == NULL) || (desc->num_normals && desc->normals == NULL) ||
@@ -559,17 +560,19 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, uint32_t flags, R
         return rt_fail(RT_ERR_DEPTH, "top-level BVH deeper than 49");
     int mesh_depth = -1;
     std::vector<uint32_t> mesh_num_nodes(desc->num_meshes, 0);     // nodes of every mesh's face BVH (given, or to be built)
+    std::vector<char> mesh_on_device(desc->num_meshes, 0);          // ... to be built on the device
     for (uint32_t m = 0; m < desc->num_meshes; ++m)
     {
         const RtMesh& mesh = desc->meshes[m];
-        mesh_num_nodes[m] = dev_build ? (mesh.num_faces ? 2 * mesh.num_faces - 1 : 0u) : mesh.num_nodes;
-        if ((!dev_build && (uint64_t)mesh.first_node + mesh.num_nodes > desc->num_mesh_nodes) ||
+        mesh_on_device[m] = dev_build && mesh.num_nodes == 0 && mesh.num_faces > 0;
+        mesh_num_nodes[m] = mesh_on_device[m] ? 2 * mesh.num_faces - 1 : mesh.num_nodes;
+        if ((uint64_t)mesh.first_node + mesh.num_nodes > desc->num_mesh_nodes ||
             (uint64_t)mesh.first_face + mesh.num_faces > desc->num_faces ||
             (uint64_t)mesh.first_vertex + mesh.num_vertices > desc->num_vertices ||
             (uint64_t)mesh.first_normal + mesh.num_normals > desc->num_normals ||
             (uint64_t)mesh.first_cdf + mesh.num_faces + 1 > desc->num_cdf)
             return rt_fail(RT_ERR_ARG, "mesh ranges out of bounds");
-        if (dev_build)
+        if (mesh_on_device[m])
             continue;           // depth: known once the device has built the tree
         if (mesh.num_nodes != 0 && mesh.num_nodes != 2 * mesh.num_faces - 1)
             return rt_fail(RT_ERR_ARG, "mesh BVH must have 2*faces-1 nodes");
@@ -603,14 +606,22 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, uint32_t flags, R
     // the far child along.  RAYITO_B200_NODE_ALIGN=0 keeps the pairs straddling (A/B runs).
     const char* align_env = std::getenv("RAYITO_B200_NODE_ALIGN");
     const bool align_pairs = !(align_env != NULL && align_env[0] == '0');
+    // Trees that come from the host first (they are part of the copy), trees the device builds behind them
     std::vector<uint32_t> dev_first_node(desc->num_meshes, 0);
-    uint64_t dev_nodes = 0;
-    for (uint32_t m = 0; m < desc->num_meshes; ++m)
+    uint64_t dev_nodes = 0, host_tree_nodes = 0;
+    for (int pass = 0; pass < 2; ++pass)
     {
-        if (align_pairs && (dev_nodes & 1u) == 0)
-            ++dev_nodes;
-        dev_first_node[m] = (uint32_t)dev_nodes;
-        dev_nodes += mesh_num_nodes[m];
+        for (uint32_t m = 0; m < desc->num_meshes; ++m)
+        {
+            if ((mesh_on_device[m] != 0) != (pass == 1))
+                continue;
+            if (align_pairs && (dev_nodes & 1u) == 0)
+                ++dev_nodes;
+            dev_first_node[m] = (uint32_t)dev_nodes;
+            dev_nodes += mesh_num_nodes[m];
+        }
+        if (pass == 0)
+            host_tree_nodes = dev_nodes;
     }
     // the face-BVH pass packs (child pair index, split axis) and (leaf flag, first triangle record) into one word each
     if (dev_nodes >= (1ull << 29) || num_tris >= (1ull << 31))
@@ -770,8 +781,6 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, uint32_t flags, R
     ArenaBuilder ab;
     size_t o_shapes = ab.put(shapes.data(), shapes.size() * sizeof(DShapeMem));
     size_t o_top = ab.put(top_nodes.data(), top_nodes.size() * sizeof(DNode));
-    // (with a device build the node slots go last and are not part of the copy: nothing of the tree crosses PCIe)
-    size_t o_mnodes = dev_build ? 0 : ab.reserve((size_t)dev_nodes * sizeof(DNode));     // built in place below
     size_t o_tris = ab.reserve((size_t)num_tris * 3 * sizeof(float4));
     size_t o_trin = ab.reserve((size_t)num_tris * sizeof(uint4));
     size_t o_fft = ab.put(face_first_tri.data(), face_first_tri.size() * sizeof(uint32_t));
@@ -790,13 +799,11 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, uint32_t flags, R
     size_t o_lights = ab.put(desc->lights, (size_t)desc->num_lights * 4);
     size_t o_walk = ab.put(top_walk.data(), top_walk.size() * sizeof(DTopStep));
     size_t o_anim = ab.put(anim.data(), anim.size() * sizeof(uint4));
+    // The node slots go last: the host's trees are staged in place below and copied with the rest, the slots of
+    // the trees the device builds lie behind them and are not part of the copy (nothing of those crosses PCIe)
+    size_t o_mnodes = ab.reserve((size_t)host_tree_nodes * sizeof(DNode));
     const size_t copy_bytes = ab.total;
-    size_t arena_total = ab.total;
-    if (dev_build)
-    {
-        o_mnodes = (ab.total + 255) & ~(size_t)255;
-        arena_total = o_mnodes + (size_t)(dev_nodes ? dev_nodes : 1) * sizeof(DNode);
-    }
+    const size_t arena_total = std::max(ab.total, o_mnodes + (size_t)(dev_nodes ? dev_nodes : 1) * sizeof(DNode));
 
     hc[2] = std::chrono::steady_clock::now();
     int ndev = 0;
@@ -829,7 +836,7 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, uint32_t flags, R
     {
         float4* tris = ab.at<float4>(o_tris);
         uint4* tri_normals = ab.at<uint4>(o_trin);
-        DNode* mesh_nodes = dev_build ? NULL : ab.at<DNode>(o_mnodes);
+        DNode* mesh_nodes = ab.at<DNode>(o_mnodes);
         const uint32_t* fft = face_first_tri.data();
         std::atomic<int> bad(0);
         for (uint32_t m = 0; m < desc->num_meshes; ++m)
@@ -874,7 +881,7 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, uint32_t flags, R
                     }
                 }
             });
-            if (dev_build)
+            if (mesh_on_device[m])
                 continue;
             const uint32_t dev_first = dev_first_node[m];
             if (dev_first != 0)
@@ -1033,10 +1040,13 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, uint32_t flags, R
     {
         // Bvh<Mesh>::build for every mesh, on the device, out of the triangle records just uploaded
         DNode* nodes = reinterpret_cast<DNode*>(static_cast<char*>(sc->arena) + o_mnodes);
-        cudaMemsetAsync(nodes, 0, sizeof(DNode), 0);        // the padding slot in front of the first tree
         int rc = RT_OK;
         for (uint32_t m = 0; m < desc->num_meshes && rc == RT_OK; ++m)
         {
+            if (!mesh_on_device[m])
+                continue;
+            if (dev_first_node[m] != 0)
+                cudaMemsetAsync(nodes + dev_first_node[m] - 1, 0, sizeof(DNode), 0);      // the padding slot
             int depth = 0;
             float ms = 0.0f;
             rc = rt_build::build_mesh(device, nodes + dev_first_node[m], d.tris, d.face_first_tri, desc->meshes[m].first_face,

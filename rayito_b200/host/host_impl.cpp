@@ -204,9 +204,34 @@ static Image* raytraceImpl(ShapeSet& scene,
     RtSceneDesc desc = flat.desc();
     RtScene* dev = NULL;
     clock_gettime(CLOCK_MONOTONIC, &tp[2]);
-    const uint32_t sceneFlags = rayito_b200::treeMode() == rayito_b200::kTreeDevice && flat.semantics == RT_SEMANTICS_STAGE7
-                                    ? (uint32_t)RT_SCENE_BUILD_MESH_BVH : 0u;      // prepare() left the face BVHs to the GPU
-    if (rt_scene_create_ex(&desc, opt.device, sceneFlags, &dev) != RT_OK)
+    // (kTreeDevice / kTreeAuto: prepare() left the face BVH of some meshes to the GPU; meshes that came with
+    // their nodes keep them)
+    const unsigned treeMode = rayito_b200::treeMode();
+    const bool deviceTrees = (treeMode == rayito_b200::kTreeDevice || treeMode == rayito_b200::kTreeAuto) &&
+                             flat.semantics == RT_SEMANTICS_STAGE7;
+    int created = rt_scene_create_ex(&desc, opt.device, deviceTrees ? (uint32_t)RT_SCENE_BUILD_MESH_BVH : 0u, &dev);
+    if (created == RT_ERR_UNSUPPORTED && deviceTrees)
+    {
+        // a mesh the device build declines (see rt_build.cuh): build every tree on the host after all
+        rayito_b200::treeMode() = rayito_b200::kTreeReference;
+        try
+        {
+            scene.prepare();
+            flat.reset();
+            if (!scene.flattenScene(flat, lights))
+                throw std::runtime_error("rayito_b200: cannot flatten scene: " + flat.error);
+            flat.semantics = rayito_b200::stageSemantics();
+        }
+        catch (...)
+        {
+            rayito_b200::treeMode() = treeMode;
+            throw;
+        }
+        rayito_b200::treeMode() = treeMode;
+        desc = flat.desc();
+        created = rt_scene_create(&desc, opt.device, &dev);
+    }
+    if (created != RT_OK)
         throw std::runtime_error(std::string("rayito_b200: rt_scene_create: ") + rt_last_error_string());
     clock_gettime(CLOCK_MONOTONIC, &tp[3]);
 
@@ -384,7 +409,7 @@ unsigned& stageSemantics()
 
 unsigned& treeMode()
 {
-    static thread_local unsigned mode = kTreeReference;
+    static thread_local unsigned mode = kTreeAuto;
     return mode;
 }
 
@@ -420,7 +445,7 @@ const char* rth_last_error_string(void) { return t_hostError.c_str(); }
 
 int rth_set_tree_mode(unsigned mode)
 {
-    if (mode != rayito_b200::kTreeReference && mode != rayito_b200::kTreeSah && mode != rayito_b200::kTreeDevice)
+    if (mode > rayito_b200::kTreeAuto)
     {
         t_hostError = "rth_set_tree_mode: unknown mode";
         return -1;

@@ -377,13 +377,18 @@ public:
         }
         m_faceAreaCDF[numFaces] = m_totalArea;
 
-        // (rayito_b200::treeMode(): the reference's tree unless the application asked for the perf-mode one)
-        if (rayito_b200::treeMode() == rayito_b200::kTreeDevice && rayito_b200::stageSemantics() == RT_SEMANTICS_STAGE7)
+        // (rayito_b200::treeMode(): the reference's tree unless the application asked for the perf-mode one;
+        // a large mesh's is built by the GPU during the upload)
+        const unsigned mode = rayito_b200::treeMode();
+        const bool onDevice = rayito_b200::stageSemantics() == RT_SEMANTICS_STAGE7 &&
+                              (mode == rayito_b200::kTreeDevice ||
+                               (mode == rayito_b200::kTreeAuto && m_faces.size() >= rayito_b200::kDeviceBuildFaces));
+        if (onDevice)
             m_bvh.clear();              // built on the GPU out of the uploaded faces (rt_scene_create_ex)
         else if (rayito_b200::stageSemantics() == RT_SEMANTICS_STAGE6)
-            m_bvh.build(&m_bbox, rayito_b200::treeMode());       // all vertices, used by a face or not (S6 RMesh.h:82-86)
+            m_bvh.build(&m_bbox, mode);       // all vertices, used by a face or not (S6 RMesh.h:82-86)
         else
-            m_bvh.build(NULL, rayito_b200::treeMode());
+            m_bvh.build(NULL, mode);
     }
 
     virtual unsigned int numElements() const { return (unsigned int)m_faces.size(); }

@@ -81,6 +81,49 @@ def test_device_build_c5_mesh(capi):
     dev.close()
 
 
+@pytest.mark.parametrize("on_device", [0, 1])
+def test_device_build_mixed_with_host_trees(capi, scene1_host, scene1_ref, on_device):
+    """A scene in which one mesh brings its nodes and the other leaves them to the GPU (what the default tree mode
+    produces when only some meshes are large): both trees are where they belong and hits are the reference's."""
+    d = scene1_host.desc.contents
+    assert d.num_meshes == 2
+    meshes = (capi.RtMesh * 2).from_address(C.cast(d.meshes, C.c_void_p).value)
+    mixed = (capi.RtMesh * 2)()
+    for m in range(2):
+        C.memmove(C.byref(mixed[m]), C.byref(meshes[m]), C.sizeof(capi.RtMesh))
+    mixed[on_device].num_nodes = 0
+    desc = capi.RtSceneDesc()
+    C.memmove(C.byref(desc), C.byref(d), C.sizeof(capi.RtSceneDesc))
+    desc.meshes = C.addressof(mixed)
+    dev = capi.DeviceScene(C.pointer(desc), build_bvh_on_device=True)
+    want = _host_nodes(capi, scene1_host)
+    for m, (faces, nodes) in enumerate(want):
+        got, _depth, _ms = dev.mesh_nodes(m, faces)
+        assert np.array_equal(got, nodes), "mesh %d (built on the %s)" % (m, "device" if m == on_device else "host")
+    rays = random_rays(1 << 16, seed=302, center=(0.1, 0, 0), radius=6.0, target_radius=2.5, shadow_fraction=0.25)
+    hits = dev.trace_closest(rays, extended=True)
+    ref_hits = scene1_ref.trace_closest(rays)
+    for f in ("shape", "face", "tri"):
+        assert np.array_equal(hits[f], ref_hits[f]), f
+    assert np.array_equal(bits(hits["t"]), bits(ref_hits["t"]))
+    dev.close()
+
+
+def test_default_tree_mode_builds_large_meshes_on_the_device(capi):
+    """rayito_b200::treeMode() defaults to kTreeAuto: a mesh of 65 536 faces or more comes out of prepare() without
+    nodes and gets the reference's tree from the GPU; smaller ones are built on the host as before."""
+    small = capi.HostScene(capi.RECIPE_SYNTHETIC_MESH, None, SYNTH_GRID, tree=capi.TREE_AUTO)
+    assert small.desc.contents.num_mesh_nodes == 2 * SYNTH_GRID[0] * SYNTH_GRID[1] - 1
+    grid = (640, 512)
+    big = capi.HostScene(capi.RECIPE_SYNTHETIC_MESH, None, grid, tree=capi.TREE_AUTO)
+    assert big.desc.contents.num_mesh_nodes == 0
+    ref_scene = capi.HostScene(capi.RECIPE_SYNTHETIC_MESH, None, grid)
+    dev = capi.DeviceScene(big.desc, build_bvh_on_device=True)
+    got, depth, _ms = dev.mesh_nodes(0, grid[0] * grid[1])
+    assert np.array_equal(got, _host_nodes(capi, ref_scene)[0][1]) and depth == ref_scene.depth(0)
+    dev.close()
+
+
 def test_raytrace_with_device_build_matches_reference(capi, obj_path, scene1_host, scene1_ref):
     """Rayito::raytrace() with rayito_b200::treeMode() = kTreeDevice: same image as the reference, bit for bit."""
     lib = capi.host()
@@ -95,7 +138,7 @@ def test_raytrace_with_device_build_matches_reference(capi, obj_path, scene1_hos
     try:
         rc = lib.rth_app_raytrace(app, spec.ctypes.data, W, H, ps, 1, 3, 0, 0, 1, 0, img.ctypes.data, 0, C.byref(stats))
     finally:
-        lib.rth_set_tree_mode(capi.TREE_REFERENCE)
+        lib.rth_set_tree_mode(capi.TREE_AUTO)
         lib.rth_app_destroy(app)
     assert rc == 0, lib.rth_last_error_string()
     assert np.array_equal(bits(img), bits(theirs))

@@ -4,7 +4,10 @@ line table nvdisasm prints for the same cubin (build with -lineinfo).
 
     cuobjdump -xelf all librayito_b200.so ; nvdisasm -g -c rt_core.sm_100a.cubin > dis.txt
     ncu -i prof.ncu-rep --page source --csv --kernel-id :::N > sass.csv
-    python tools/ncu_by_line.py dis.txt sass.csv '<mangled kernel name>' [top]
+    python tools/ncu_by_line.py dis.txt sass.csv '<mangled kernel name>' [top] [section]
+
+section: when the csv holds several launches (one "Kernel Name" block per launch and view), use only the
+block with this index (0-based); default: all blocks (they must then be launches of the same kernel).
 """
 import csv
 import collections
@@ -37,6 +40,11 @@ def main():
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
     table = line_table(dis_path, mangled)
     rows = list(csv.reader(open(csv_path)))
+    if len(sys.argv) > 5:
+        starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"] + [len(rows)]
+        k = int(sys.argv[5])
+        rows = rows[starts[k]:starts[k + 1]]
+        print("# section %d: %s" % (k, rows[0][1][:100]))
     hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
     hdr = rows[hdr_i]
     col = {name: hdr.index(name) for name in ("Address", "Source", "# Samples", "Instructions Executed",
