@@ -124,8 +124,11 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region."""
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons DURING the timed region.  The sampler is started before the warm-up
+    (nvidia-smi takes a few hundred ms to print its first line) and every line carries nvidia-smi's own
+    timestamp; only the lines between begin() and end() count (a region shorter than the sampling period
+    falls back to the lines nearest to it, and says so)."""
+    QUERY = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
 
@@ -133,47 +136,68 @@ class ClockSampler:
         self.gpu = gpu_index
         self.lines = []
         self.proc = None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits", "-lms", "200"],
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except OSError:
             self.proc = None
 
+    def begin(self):
+        self.t0 = time.time()
+
+    def end(self):
+        self.t1 = time.time()
+
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        import datetime
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)            # let the line that covers the end of the region arrive
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, power, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         for line in self.lines:
             parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 8:
+            if len(parts) < 9:
                 continue
             try:
-                sm.append(float(parts[1]))
-                mx.append(float(parts[2]))
-                power.append(float(parts[3]))
+                stamp = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((stamp, float(parts[2]), float(parts[3]), float(parts[4]),
+                             [n for n, v in zip(names, parts[5:9]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for name, val in zip(names, parts[4:8]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+        t0 = self.t0 if self.t0 is not None else -1e30
+        t1 = self.t1 if self.t1 is not None else 1e30
+        inside = [r for r in rows if t0 <= r[0] <= t1]
+        note = None
+        if not inside and rows:
+            mid = 0.5 * (t0 + t1)
+            inside = sorted(rows, key=lambda r: abs(r[0] - mid))[:2]
+            note = "timed region shorter than the sampling period: the %d samples nearest to it (within %.2f s)" % (
+                len(inside), max(abs(r[0] - mid) for r in inside))
+        sm = sorted(r[1] for r in inside)
+        reasons = set()
+        for r in inside:
+            reasons.update(r[4])
+        out = {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(r[2] for r in inside) if inside else None,
+               "power_w_max": max(r[3] for r in inside) if inside else None, "samples": len(inside), "reasons": sorted(reasons)}
+        if note:
+            out["note"] = note
+        return out
 
 
 def algorithmic_bytes(stats, strict=False):
@@ -274,11 +298,13 @@ def run_stage23(args, wl, rank, world, local_rank):
                             launches=st.kernel_launches, rounds=st.trace_launches, samples=st.samples))
         return out
 
-    for _ in range(max(args.warmup, 3)):
-        sweep()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        sweep()
+    sampler.begin()
     runs = [sweep() for _ in range(args.steps)]
+    sampler.end()
     clocks = sampler.stop()
     rays = sum(l["rays"] for l in runs[0])
     dev_ms = sum(l["device_ms"] for r in runs for l in r)
@@ -408,8 +434,12 @@ def measure_workload(env, name, steps, warmup, want_e2e, want_cpu):
     flush, stream = env.flush, env.stream
     extra_flags = int(os.environ.get("RT_BENCH_FLAGS", "0"))      # A/B switches (RT_RENDER_* bits), not for reported runs
 
+    shard_rank, shard_world = rank, world
+    if args.shard and world == 1:
+        shard_rank, shard_world = (int(v) for v in args.shard.split("/"))
+
     def params(flags=0):
-        return capi.RtRenderParams(W, H, ps, ls, depth, args.tile, rank, world, args.batch, flags | extra_flags)
+        return capi.RtRenderParams(W, H, ps, ls, depth, args.tile, shard_rank, shard_world, args.batch, flags | extra_flags)
 
     assemble_ms = []
 
@@ -427,14 +457,15 @@ def measure_workload(env, name, steps, warmup, want_e2e, want_cpu):
     counted = step(capi.RT_RENDER_COUNT_WORK).as_dict()
     log("[rank %d] %s counted step: %s" % (rank, name, counted))
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(warmup):
         image.zero_()
         flush.zero_()
         step()
 
     env.barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.begin()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches = 0
     trace_ms = 0.0
@@ -451,6 +482,7 @@ def measure_workload(env, name, steps, warmup, want_e2e, want_cpu):
         render_ms += st.render_ms
     ev1.record(stream)
     env.barrier()
+    sampler.end()
     clocks = sampler.stop()
     elapsed_ms = ev0.elapsed_time(ev1)
 
@@ -548,6 +580,8 @@ def main():
     ap.add_argument("--no-also", action="store_true", help="skip the secondary C5 measurement of the default run")
     ap.add_argument("--batch", type=int, default=0, help="max samples per wavefront batch (0 = core default)")
     ap.add_argument("--tile", type=int, default=0)
+    ap.add_argument("--shard", default="", help="R/W: render only rank R's screen tiles of a W-rank partition on this one GPU "
+                                                "(what one rank of a W-GPU run does, without the other ranks; for A/B runs)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     claim_stdout()
