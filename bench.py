@@ -550,7 +550,7 @@ def measure_workload(env, name, steps, warmup, want_e2e, want_cpu):
     out = {
         "value": value, "ms_per_step": max_ms / steps, "steps": steps, "warmup": warmup,
         "config": {"workload": wl["label"],
-                   "parallelism": "screen tiles x%d (diagonal interleave), scene replicated%s" % (
+                   "parallelism": "screen tiles x%d (lattice interleave (tx + m ty) mod world), scene replicated%s" % (
                        world, "" if world == 1 else "; tile assembly on rank 0 by rt_render_multi (packed tiles, grouped "
                        "ncclSend/ncclRecv, scatter kernel): %.3f ms per step on rank 0" % (
                            sum(assemble_ms[-steps:]) / max(steps, 1))),

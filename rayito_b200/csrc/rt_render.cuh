@@ -1197,14 +1197,58 @@ inline size_t carve(RenderCtx& c, char* base, size_t samples, size_t pixels, uin
     return k.off + 256;
 }
 
-// Tiles of `rank`: diagonal interleave so every rank gets tiles from all image
-// regions (sky rows are ~1 ray/sample, mesh pixels 6+)
+// Which rank renders tile (tx, ty): (tx + m * ty) mod world, a lattice.  Every rank gets tiles from all image
+// regions (sky rows are ~1 ray/sample, mesh pixels 6+), and m is the multiplier whose lattice keeps a rank's own
+// tiles FARTHEST APART (largest shortest vector among the tiles of one rank): m = 1, the diagonal interleave of
+// round 1, puts a rank's tiles corner to corner along diagonals, so a rank's share of the expensive pixels followed
+// whatever diagonal structure the image has (8 ranks on config C4: per-rank frame times spread by 3.4 %, session Q/S
+// in profiles/README.md); for world = 8 the choice is m = 3 (shortest vector (2,2) instead of (1,-1)).
+// RAYITO_B200_TILE_DEAL=diagonal keeps m = 1 (A/B runs).
+inline uint32_t tile_lattice_multiplier(uint32_t world)
+{
+    static std::mutex lock;
+    static std::vector<uint32_t> known(1, 0u);      // known[w]: multiplier of world size w (0 = not computed yet)
+    const char* env = std::getenv("RAYITO_B200_TILE_DEAL");
+    if (world < 3 || (env != NULL && env[0] == 'd'))
+        return 1u;
+    std::lock_guard<std::mutex> guard(lock);
+    if (known.size() <= world)
+        known.resize((size_t)world + 1, 0u);
+    if (known[world] == 0)
+    {
+        const int w = (int)world;
+        const int reach = w < 64 ? w : 64;
+        long best_len = -1;
+        uint32_t best_m = 1;
+        for (int m = 1; m < w; ++m)
+        {
+            long shortest = (long)w * w;            // (w, 0) is always in the lattice
+            for (int dy = 0; dy <= reach; ++dy)
+                for (int dx = -reach; dx <= reach; ++dx)
+                {
+                    if ((dx == 0 && dy == 0) || ((dx + m * dy) % w + w) % w != 0)
+                        continue;
+                    long len = (long)dx * dx + (long)dy * dy;
+                    if (len < shortest) shortest = len;
+                }
+            if (shortest > best_len)
+            {
+                best_len = shortest;
+                best_m = (uint32_t)m;
+            }
+        }
+        known[world] = best_m;
+    }
+    return known[world];
+}
+
 inline void rank_tiles(uint32_t tiles_x, uint32_t tiles_y, uint32_t rank, uint32_t world, std::vector<uint32_t>& out)
 {
     out.clear();
+    const uint32_t m = tile_lattice_multiplier(world);
     for (uint32_t ty = 0; ty < tiles_y; ++ty)
         for (uint32_t tx = 0; tx < tiles_x; ++tx)
-            if ((tx + ty) % world == rank)
+            if ((tx + m * ty) % world == rank)
                 out.push_back(ty * tiles_x + tx);
 }
 

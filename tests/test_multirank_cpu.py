@@ -22,9 +22,13 @@ def test_partition_covers_every_tile_once_and_is_balanced(capi, width, height, w
     assert counts.sum() == owners.size
     if owners.size >= 4 * world:
         assert counts.max() - counts.min() <= max(2, owners.size // (4 * world))
-    # diagonal interleave: horizontally and vertically adjacent tiles belong to different ranks
+    # lattice interleave (tx + m ty) mod world: horizontally adjacent tiles belong to different ranks, and a rank's
+    # own tiles keep their distance (for 8 ranks no two of them touch, not even corner to corner)
     if world > 1 and owners.shape[1] > 1:
         assert (owners[:, 1:] != owners[:, :-1]).all()
+    if world == 8:
+        assert (owners[1:, :] != owners[:-1, :]).all()
+        assert (owners[1:, 1:] != owners[:-1, :-1]).all() and (owners[1:, :-1] != owners[:-1, 1:]).all()
 
 
 def _free_port():

@@ -34,7 +34,7 @@ def main():
     total_bytes = total_ms = 0.0
     n = 0
     for d in launches.values():
-        name = d["kernel"].split("(")[0]
+        name = d["kernel"].split("(")[0].replace("void ", "")
         if not name.startswith("k_split"):
             continue
         b = d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0)
