@@ -533,6 +533,7 @@ int rt_tonemap_bgra8_device(int device, const float* d_rgb, size_t num_pixels, f
 void rt_release_cached_memory(void)
 {
     rt_detail::s23_release();                      // the Stage 2/3 working set goes back to the pool first
+    rt_detail::release_parked_render();            // ... and the wavefront state parked by the last scene destroyed
     rt_detail::pool_release_all();
     rt_detail::validate_scratch().release();       // the calling thread's BVH validation scratch
 }

@@ -153,6 +153,7 @@ struct RenderBuffers
 {
     size_t cap_samples, cap_pixels, cap_tiles;
     uint32_t cap_perm_slots;
+    uint32_t cap_anim_stride;   // transform-cache row width the block was sized for (a later scene may need wider rows)
     void* block;                // one allocation for all per-sample state
     size_t block_bytes;
     RenderCtx ctx;              // pointers filled in
@@ -1128,15 +1129,14 @@ inline int rt_stage1_impl(int device, const RtStage1Plane* planes, uint32_t num_
 // host orchestration
 // ---------------------------------------------------------------------------
 
-inline void rt_render_release(RtScene* s)
+// Give a RenderBuffers' device memory and events back for good
+inline void rt_render_free(int device, RenderBuffers* rb)
 {
-    RenderBuffers* rb = s->render;
     if (rb == NULL)
         return;
-    rt_detail::pool_free(s->device, rb->block, rb->block_bytes);
-    rb->block = NULL;
-    rt_detail::pool_free(s->device, rb->d_tile_ids, rb->tile_bytes);
-    rt_detail::pool_free(s->device, rb->d_image, rb->image_bytes);
+    rt_detail::pool_free(device, rb->block, rb->block_bytes);
+    rt_detail::pool_free(device, rb->d_tile_ids, rb->tile_bytes);
+    rt_detail::pool_free(device, rb->d_image, rb->image_bytes);
     for (int i = 0; i < 4; ++i) cudaEventDestroy(rb->ev[i]);
     if (rb->trace_events)
     {
@@ -1144,7 +1144,74 @@ inline void rt_render_release(RtScene* s)
         delete rb->trace_events;
     }
     delete rb;
+}
+
+// Rayito::raytrace() builds a fresh device scene per call, so the wavefront state of the previous call -- its
+// 88 GB block carved into arrays, its events -- used to be taken apart at rt_scene_destroy and put together again by
+// the next call's first render: a cudaMemGetInfo, a pool search and a dozen event creations per call, 5 to 80 ms on
+// the boxes of round 2 (RAYITO_B200_TIMING=1, "reserve").  One RenderBuffers per device is parked WHOLE instead and
+// adopted by the next scene that renders on that device.  rt_release_cached_memory() frees it.
+namespace rt_detail
+{
+inline std::mutex& parked_render_lock() { static std::mutex m; return m; }
+inline std::vector<std::pair<int, RenderBuffers*> >& parked_render() { static std::vector<std::pair<int, RenderBuffers*> > v; return v; }
+
+inline RenderBuffers* take_parked_render(int device)
+{
+    std::lock_guard<std::mutex> guard(parked_render_lock());
+    std::vector<std::pair<int, RenderBuffers*> >& v = parked_render();
+    for (size_t i = 0; i < v.size(); ++i)
+        if (v[i].first == device)
+        {
+            RenderBuffers* rb = v[i].second;
+            v.erase(v.begin() + i);
+            return rb;
+        }
+    return NULL;
+}
+
+inline void release_parked_render()
+{
+    std::vector<std::pair<int, RenderBuffers*> > all;
+    {
+        std::lock_guard<std::mutex> guard(parked_render_lock());
+        all.swap(parked_render());
+    }
+    int current = 0;
+    cudaGetDevice(&current);
+    for (size_t i = 0; i < all.size(); ++i)
+    {
+        cudaSetDevice(all[i].first);
+        rt_render_free(all[i].first, all[i].second);
+    }
+    cudaSetDevice(current);
+}
+} // namespace rt_detail
+
+inline void rt_render_release(RtScene* s)
+{
+    RenderBuffers* rb = s->render;
+    if (rb == NULL)
+        return;
     s->render = NULL;
+    RenderBuffers* old = NULL;
+    {
+        std::lock_guard<std::mutex> guard(rt_detail::parked_render_lock());
+        std::vector<std::pair<int, RenderBuffers*> >& v = rt_detail::parked_render();
+        size_t at = v.size();
+        for (size_t i = 0; i < v.size(); ++i)
+            if (v[i].first == s->device) at = i;
+        if (at == v.size())
+            v.push_back(std::make_pair(s->device, rb));
+        else if (v[at].second->block_bytes <= rb->block_bytes)
+        {
+            old = v[at].second;         // keep the larger working set
+            v[at].second = rb;
+        }
+        else
+            old = rb;
+    }
+    rt_render_free(s->device, old);
 }
 
 namespace rt_detail
@@ -1299,12 +1366,17 @@ inline int rt_render_reserve(RtScene* s, RenderPlan& plan)
     RenderBuffers* rb = s->render;
     if (rb == NULL)
     {
-        rb = new RenderBuffers();
-        std::memset(rb, 0, sizeof(*rb));
-        for (int i = 0; i < 4; ++i) cudaEventCreate(&rb->ev[i]);
+        rb = rt_detail::take_parked_render(s->device);       // the previous scene's, whole (see rt_render_release)
+        if (rb == NULL)
+        {
+            rb = new RenderBuffers();
+            std::memset(rb, 0, sizeof(*rb));
+            for (int i = 0; i < 4; ++i) cudaEventCreate(&rb->ev[i]);
+        }
         s->render = rb;
     }
-    if (samples > rb->cap_samples || pixels > rb->cap_pixels || plan.slots > rb->cap_perm_slots)
+    if (samples > rb->cap_samples || pixels > rb->cap_pixels || plan.slots > rb->cap_perm_slots ||
+        s->d.anim_stride > rb->cap_anim_stride)
     {
         rt_detail::pool_free(s->device, rb->block, rb->block_bytes);
         rb->block = NULL;
@@ -1337,6 +1409,7 @@ inline int rt_render_reserve(RtScene* s, RenderPlan& plan)
         rb->cap_samples = samples;
         rb->cap_pixels = pixels;
         rb->cap_perm_slots = plan.slots;
+        rb->cap_anim_stride = s->d.anim_stride;
     }
     rt_detail::carve(rb->ctx, static_cast<char*>(rb->block), rb->cap_samples, rb->cap_pixels, rb->cap_perm_slots, s->d.anim_stride);
     if (plan.tiles.size() > rb->cap_tiles)

@@ -374,9 +374,15 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, uint32_t flags, R
     *out_scene = NULL;
     if (flags & ~(uint32_t)RT_SCENE_BUILD_MESH_BVH)
         return rt_fail(RT_ERR_ARG, "unknown scene flags");
-    const bool dev_build = (flags & RT_SCENE_BUILD_MESH_BVH) != 0;
+    bool dev_build = (flags & RT_SCENE_BUILD_MESH_BVH) != 0;
     if (dev_build && desc->semantics != RT_SEMANTICS_STAGE7)
-        return rt_fail(RT_ERR_UNSUPPORTED, "the device BVH build reproduces the Stage 7 builder only (Stage 6 roots its face BVH in the all-vertex box)");
+    {
+        // nothing to build is fine; a mesh without nodes is not
+        for (uint32_t m = 0; desc->meshes != NULL && m < desc->num_meshes; ++m)
+            if (desc->meshes[m].num_nodes == 0 && desc->meshes[m].num_faces > 0)
+                return rt_fail(RT_ERR_UNSUPPORTED, "the device BVH build reproduces the Stage 7 builder only (Stage 6 roots its face BVH in the all-vertex box)");
+        dev_build = false;
+    }
     if (desc->abi_version != RT_ABI_VERSION)
         return rt_fail(RT_ERR_ARG, "RtSceneDesc.abi_version mismatch");
     const uint32_t num_shapes = desc->num_finite + desc->num_infinite;

@@ -124,6 +124,20 @@ def test_default_tree_mode_builds_large_meshes_on_the_device(capi):
     dev.close()
 
 
+def test_build_flag_is_harmless_for_a_stage6_scene(capi, scene6_host, scene6_ref):
+    """Stage 6 rules root the face BVH in the all-vertex box, which only the host builds: prepare() keeps building there
+    whatever the tree mode, and RT_SCENE_BUILD_MESH_BVH on a scene whose meshes all bring their nodes builds nothing."""
+    assert scene6_host.desc.contents.num_mesh_nodes > 0
+    dev = capi.DeviceScene(scene6_host.desc, build_bvh_on_device=True)
+    rays = random_rays(1 << 15, seed=303, center=(0, 0, 0), radius=8.0, target_radius=2.0)
+    hits = dev.trace_closest(rays, extended=True)
+    want = scene6_ref.trace_closest(rays)
+    for f in ("shape", "face", "tri"):
+        assert np.array_equal(hits[f], want[f]), f
+    assert np.array_equal(bits(hits["t"]), bits(want["t"]))
+    dev.close()
+
+
 def test_raytrace_with_device_build_matches_reference(capi, obj_path, scene1_host, scene1_ref):
     """Rayito::raytrace() with rayito_b200::treeMode() = kTreeDevice: same image as the reference, bit for bit."""
     lib = capi.host()
