@@ -1782,26 +1782,6 @@ inline int rt_render_impl(RtScene* s, const RtCamera* camera, const RtRenderPara
     if (packed_floats != 0 && (!out_on_device || packed_floats < plan.tiles.size() * (size_t)plan.tile * plan.tile * 3))
         return rt_fail(RT_ERR_ARG, "packed tile buffer must be a device buffer of at least rt_packed_floats() floats");
 
-    // A/B switch (RAYITO_B200_L2_PERSIST=1): ask L2 to keep a small scene's arena resident against the per-path
-    // state streaming through it (access policy window on the launching stream).  Measured: see profiles/README.md.
-    if (std::getenv("RAYITO_B200_L2_PERSIST") != NULL)
-    {
-        cudaDeviceProp prop;
-        if (cudaGetDeviceProperties(&prop, s->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0 &&
-            s->arena_bytes <= (size_t)prop.persistingL2CacheMaxSize && s->arena_bytes <= (size_t)prop.accessPolicyMaxWindowSize)
-        {
-            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, s->arena_bytes);
-            cudaStreamAttrValue attr;
-            std::memset(&attr, 0, sizeof(attr));
-            attr.accessPolicyWindow.base_ptr = s->arena;
-            attr.accessPolicyWindow.num_bytes = s->arena_bytes;
-            attr.accessPolicyWindow.hitRatio = 1.0f;
-            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-            cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
-        }
-        cudaGetLastError();
-    }
     RT_CUDA(cudaEventRecord(rb->ev[0], st));
     if (!plan.tiles.empty())
         RT_CUDA(cudaMemcpyAsync(rb->d_tile_ids, plan.tiles.data(), plan.tiles.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
