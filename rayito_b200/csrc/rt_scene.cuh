@@ -580,6 +580,9 @@ inline int rt_scene_build(const RtSceneDesc* desc, int device, uint32_t flags, R
             return rt_fail(RT_ERR_ARG, "mesh ranges out of bounds");
         if (mesh_on_device[m])
             continue;           // depth: known once the device has built the tree
+        if (mesh.num_faces != 0 && mesh.num_nodes == 0)
+            return rt_fail(RT_ERR_ARG, "mesh has faces but no BVH nodes: prepare() it on the host, or create the scene with "
+                                       "rt_scene_create_ex(..., RT_SCENE_BUILD_MESH_BVH, ...) to have its tree built on the device");
         if (mesh.num_nodes != 0 && mesh.num_nodes != 2 * mesh.num_faces - 1)
             return rt_fail(RT_ERR_ARG, "mesh BVH must have 2*faces-1 nodes");
         int d = bvh_depth(desc->mesh_nodes + mesh.first_node, mesh.num_nodes, mesh.num_faces, why);

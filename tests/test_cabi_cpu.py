@@ -215,3 +215,45 @@ def test_large_bvh_validation_on_worker_threads(capi):
     d, keep = _single_mesh_desc(capi, np.ascontiguousarray(big), n + extra)
     rc = lib.rt_scene_create(C.byref(d), 0, C.byref(h))
     assert rc == -3, lib.rt_last_error_string()
+
+
+def test_scene_create_ex_argument_checks(capi, obj_path):
+    """rt_scene_create_ex (RT_SCENE_BUILD_MESH_BVH): unknown flags are refused; a mesh that comes without nodes needs the
+    flag (it must not silently vanish from the scene); Stage 6 rules cannot be built on the device; with the flag a
+    node-less Stage 7 scene passes every host-side check and only stops at 'no CUDA device' on a CPU box."""
+    lib = capi.core()
+    h = C.c_void_p()
+    no_gpu = lib.rt_device_count() == 0
+    host_built = capi.HostScene(capi.RECIPE_SYNTHETIC_MESH, None, (24, 16))
+    assert lib.rt_scene_create_ex(C.cast(host_built.desc, C.c_void_p), 0, 0x80, C.byref(h)) == -1
+    assert b"flags" in lib.rt_last_error_string()
+    left_to_gpu = capi.HostScene(capi.RECIPE_SYNTHETIC_MESH, None, (24, 16), tree=capi.TREE_DEVICE)
+    assert left_to_gpu.desc.contents.num_mesh_nodes == 0 and left_to_gpu.desc.contents.num_faces == 24 * 16
+    assert lib.rt_scene_create(C.cast(left_to_gpu.desc, C.c_void_p), 0, C.byref(h)) == -1
+    assert b"no BVH nodes" in lib.rt_last_error_string()
+    rc = lib.rt_scene_create_ex(C.cast(left_to_gpu.desc, C.c_void_p), 0, capi.RT_SCENE_BUILD_MESH_BVH, C.byref(h))
+    if no_gpu:
+        assert rc == -2 and b"no CUDA device" in lib.rt_last_error_string()
+    else:
+        assert rc == 0
+        lib.rt_scene_destroy(h)
+    # Stage 6 rules: prepare() builds on the host whatever the tree mode, so the flag has nothing to do ...
+    s6 = capi.HostScene(capi.RECIPE_STAGE6_SCENE, obj_path, tree=capi.TREE_DEVICE)
+    assert s6.desc.contents.num_mesh_nodes > 0
+    # ... and a Stage 6 description WITHOUT nodes is refused
+    bad = capi.RtSceneDesc.from_buffer_copy(bytes(left_to_gpu.desc.contents))
+    bad.semantics = 6
+    rc = lib.rt_scene_create_ex(C.byref(bad), 0, capi.RT_SCENE_BUILD_MESH_BVH, C.byref(h))
+    assert rc in (-1, -4)       # (keyed transforms are refused under Stage 6 rules before the build question comes up)
+
+
+def test_tree_mode_switch(capi):
+    lib = capi.host()
+    assert lib.rth_set_tree_mode(7) != 0 and b"unknown mode" in lib.rth_last_error_string()
+    for mode in (capi.TREE_REFERENCE, capi.TREE_SAH, capi.TREE_DEVICE, capi.TREE_AUTO):
+        assert lib.rth_set_tree_mode(mode) == 0
+    # the default: small meshes keep their host-built tree, meshes of 65 536 faces or more leave it to the GPU
+    small = capi.HostScene(capi.RECIPE_SYNTHETIC_MESH, None, (64, 48), tree=capi.TREE_AUTO)
+    assert small.desc.contents.num_mesh_nodes == 2 * 64 * 48 - 1
+    big = capi.HostScene(capi.RECIPE_SYNTHETIC_MESH, None, (320, 256), tree=capi.TREE_AUTO)
+    assert big.desc.contents.num_mesh_nodes == 0 and big.desc.contents.num_faces == 320 * 256
