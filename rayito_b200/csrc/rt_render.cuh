@@ -26,6 +26,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <map>
 #include <mutex>
 #include <vector>
 
@@ -1593,54 +1594,70 @@ static void rt_launch_light_sample(RtScene* s, const RenderCtx& c, int cur, uint
         launches += extra - 1;      // the caller counts one launch for this stage
 }
 
+namespace rt_detail
+{
+struct RenderGrids { int sms, path, shadow, mis, split_top, split_mesh64, split_mesh32; };
+}
+
 template <bool COUNT>
 static int rt_launch_batch(RtScene* s, const RenderCtx& c, cudaStream_t st, uint64_t& launches, bool timed, uint64_t& trace_launches, bool split)
 {
     RenderBuffers* rb = s->render;
     const int cap = s->stack_cap;
-    int dev_sms = 148;
-    cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, s->device);
-    const unsigned wide = (unsigned)std::min<uint64_t>(((uint64_t)c.num_samples + RT_BLOCK - 1) / RT_BLOCK, (uint64_t)dev_sms * 32);
-    const unsigned pix_blocks = (c.num_pixels + RT_BLOCK - 1) / RT_BLOCK;
-    // persistent traversal kernels: exactly as many blocks as can be resident
-    unsigned tg_path, tg_shadow, tg_mis;
+    // Grid sizes of the persistent kernels: exactly as many blocks as can be resident.  The occupancy queries behind them
+    // are host calls the GPU waits for at the start of every frame, so they are made once per device and kernel family.
+    typedef rt_detail::RenderGrids Grids;
+    static std::mutex grids_lock;                                 // (one pair per instantiation, i.e. per COUNT)
+    static std::map<std::pair<int, int>, Grids> grids_known;      // (device, stack capacity class)
+    Grids g;
     {
-        int a = 4, b = 4, d = 4;
-        if (cap <= 32)
+        const int cap_class = cap <= 32 ? 32 : (cap <= 64 ? 64 : 104);
+        std::lock_guard<std::mutex> guard(grids_lock);
+        auto it = grids_known.find(std::make_pair(s->device, cap_class));
+        if (it == grids_known.end())
         {
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_trace_paths<32, COUNT>, RT_BLOCK, 0);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_trace_shadow<32, COUNT>, RT_BLOCK, 0);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d, k_trace_mis<32, COUNT>, RT_BLOCK, 0);
-        }
-        else if (cap <= 64)
-        {
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_trace_paths<64, COUNT>, RT_BLOCK, 0);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_trace_shadow<64, COUNT>, RT_BLOCK, 0);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d, k_trace_mis<64, COUNT>, RT_BLOCK, 0);
+            g.sms = 148;
+            cudaDeviceGetAttribute(&g.sms, cudaDevAttrMultiProcessorCount, s->device);
+            g.path = g.shadow = g.mis = g.split_top = g.split_mesh64 = g.split_mesh32 = 4;
+            if (cap_class == 32)
+            {
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.path, k_trace_paths<32, COUNT>, RT_BLOCK, 0);
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.shadow, k_trace_shadow<32, COUNT>, RT_BLOCK, 0);
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.mis, k_trace_mis<32, COUNT>, RT_BLOCK, 0);
+            }
+            else if (cap_class == 64)
+            {
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.path, k_trace_paths<64, COUNT>, RT_BLOCK, 0);
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.shadow, k_trace_shadow<64, COUNT>, RT_BLOCK, 0);
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.mis, k_trace_mis<64, COUNT>, RT_BLOCK, 0);
+            }
+            else
+            {
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.path, k_trace_paths<104, COUNT>, RT_BLOCK, 0);
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.shadow, k_trace_shadow<104, COUNT>, RT_BLOCK, 0);
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.mis, k_trace_mis<104, COUNT>, RT_BLOCK, 0);
+            }
+            // split kernels are lighter; their persistent grid is sized from the heaviest of them
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.split_top, k_split_top<false, COUNT, true, PathIO>, RT_BLOCK, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.split_mesh64, k_split_mesh<64, false, COUNT, PathIO>, RT_BLOCK, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.split_mesh32, k_split_mesh<32, false, COUNT, PathIO>, RT_BLOCK, 0);
+            cudaGetLastError();
+            grids_known[std::make_pair(s->device, cap_class)] = g;
         }
         else
-        {
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_trace_paths<104, COUNT>, RT_BLOCK, 0);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_trace_shadow<104, COUNT>, RT_BLOCK, 0);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d, k_trace_mis<104, COUNT>, RT_BLOCK, 0);
-        }
-        tg_path = (unsigned)(dev_sms * std::max(a, 1));
-        tg_shadow = (unsigned)(dev_sms * std::max(b, 1));
-        tg_mis = (unsigned)(dev_sms * std::max(d, 1));
+            g = it->second;
     }
-    // split kernels are lighter; size their persistent grid from the heaviest of them
-    unsigned tg_split, tg_mesh;
-    {
-        int a = 4, b = 4, d = 4;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_split_top<false, COUNT, true, PathIO>, RT_BLOCK, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_split_mesh<64, false, COUNT, PathIO>, RT_BLOCK, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d, k_split_mesh<32, false, COUNT, PathIO>, RT_BLOCK, 0);
+    const int dev_sms = g.sms;
+    const unsigned wide = (unsigned)std::min<uint64_t>(((uint64_t)c.num_samples + RT_BLOCK - 1) / RT_BLOCK, (uint64_t)dev_sms * 32);
+    const unsigned pix_blocks = (c.num_pixels + RT_BLOCK - 1) / RT_BLOCK;
+    const unsigned tg_path = (unsigned)(dev_sms * std::max(g.path, 1));
+    const unsigned tg_shadow = (unsigned)(dev_sms * std::max(g.shadow, 1));
+    const unsigned tg_mis = (unsigned)(dev_sms * std::max(g.mis, 1));
 #ifndef RT_SEPARATE_MESH_GRID
 #define RT_SEPARATE_MESH_GRID 1      /* +0.5 % in same-session A/B */
 #endif
-        tg_split = (unsigned)(dev_sms * std::max(std::min(a, std::min(b, d)), 1));
-        tg_mesh = RT_SEPARATE_MESH_GRID ? (unsigned)(dev_sms * std::max(s->mesh_stack_need > 32 ? b : d, 1)) : tg_split;
-    }
+    const unsigned tg_split = (unsigned)(dev_sms * std::max(std::min(g.split_top, std::min(g.split_mesh64, g.split_mesh32)), 1));
+    const unsigned tg_mesh = RT_SEPARATE_MESH_GRID ? (unsigned)(dev_sms * std::max(s->mesh_stack_need > 32 ? g.split_mesh64 : g.split_mesh32, 1)) : tg_split;
 
     k_pixel_setup<<<pix_blocks, RT_BLOCK, 0, st>>>(c);
     k_raygen<<<wide, RT_BLOCK, 0, st>>>(c);
