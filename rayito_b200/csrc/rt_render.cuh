@@ -58,6 +58,18 @@
 #ifndef RT_SHADE_MINBLOCKS
 #define RT_SHADE_MINBLOCKS 6
 #endif
+// Grid-stride kernels (ray generation, shading, light sampling, resolve): blocks per SM of their grids.  Round 1 used 32
+// (606 k threads, each walking ~220 queue entries of a 128 Mi-sample batch).  Same-session A/B on C4 (sessions AB-AD,
+// profiles/README.md): 6 / 12 / 24 per SM (whole waves of the 6 resident blocks) 4862-4878, 32: 4879-4925, 48: 4913-4960,
+// 128: 4988, 512: 4980-5013, 1024: 4943, 2048: 4850, one entry per thread: 4344; with k_raygen at 128-512 as well 5025-5040
+// (3840x2160: 4930 -> 5069); C5 2541 -> 2609.  More, shorter-lived blocks keep more gathers in flight and even out
+// the end of every launch; past ~1000 per SM block scheduling itself starts to cost.
+#ifndef RT_WIDE_SHADE_PER_SM
+#define RT_WIDE_SHADE_PER_SM 512
+#endif
+#ifndef RT_WIDE_GEN_PER_SM
+#define RT_WIDE_GEN_PER_SM 256
+#endif
 enum { CTL_PATH_A = 0, CTL_PATH_B = 8, CTL_SHADOW = 16, CTL_MIS = 24, CTL_SHADE = 32, CTL_LIT = 48,   // (room for 8 ray bins)
        CTL_CUR_PATH = 49, CTL_CUR_SHADOW = 50, CTL_CUR_MIS = 51,
        // split traversal: mesh / resume queue counts and cursors, double buffered
@@ -1648,7 +1660,12 @@ static int rt_launch_batch(RtScene* s, const RenderCtx& c, cudaStream_t st, uint
             g = it->second;
     }
     const int dev_sms = g.sms;
-    const unsigned wide = (unsigned)std::min<uint64_t>(((uint64_t)c.num_samples + RT_BLOCK - 1) / RT_BLOCK, (uint64_t)dev_sms * 32);
+    // Grid-stride kernels: blocks per SM (RT_WIDE_*_PER_SM; the environment overrides them for A/B runs)
+    static const int wide_shade_per_sm = std::getenv("RAYITO_B200_WIDE_SHADE") ? std::atoi(std::getenv("RAYITO_B200_WIDE_SHADE")) : RT_WIDE_SHADE_PER_SM;
+    static const int wide_gen_per_sm = std::getenv("RAYITO_B200_WIDE_GEN") ? std::atoi(std::getenv("RAYITO_B200_WIDE_GEN")) : RT_WIDE_GEN_PER_SM;
+    const uint64_t sample_blocks = ((uint64_t)c.num_samples + RT_BLOCK - 1) / RT_BLOCK;
+    const unsigned wide = (unsigned)std::min<uint64_t>(sample_blocks, (uint64_t)dev_sms * std::max(wide_shade_per_sm, 1));
+    const unsigned wide_gen = (unsigned)std::min<uint64_t>(sample_blocks, (uint64_t)dev_sms * std::max(wide_gen_per_sm, 1));
     const unsigned pix_blocks = (c.num_pixels + RT_BLOCK - 1) / RT_BLOCK;
     const unsigned tg_path = (unsigned)(dev_sms * std::max(g.path, 1));
     const unsigned tg_shadow = (unsigned)(dev_sms * std::max(g.shadow, 1));
@@ -1660,7 +1677,7 @@ static int rt_launch_batch(RtScene* s, const RenderCtx& c, cudaStream_t st, uint
     const unsigned tg_mesh = RT_SEPARATE_MESH_GRID ? (unsigned)(dev_sms * std::max(s->mesh_stack_need > 32 ? g.split_mesh64 : g.split_mesh32, 1)) : tg_split;
 
     k_pixel_setup<<<pix_blocks, RT_BLOCK, 0, st>>>(c);
-    k_raygen<<<wide, RT_BLOCK, 0, st>>>(c);
+    k_raygen<<<wide_gen, RT_BLOCK, 0, st>>>(c);
     launches += 2;
     int cur = 0;
     for (uint32_t b = 0; b < c.depth; ++b)
