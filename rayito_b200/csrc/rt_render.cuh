@@ -127,6 +127,7 @@ struct RenderCtx
     uint32_t* q_resume[2];      // ... for a top-level resume pass
     SplitBufs split;            // suspended-ray state
     uint32_t* ctl;              // CTL_WORDS queue counters
+    uint32_t* bin_hint;         // largest count seen so far per shade bin [0, RT_SBINS) and light bin [RT_SBINS, +RT_LBINS): sizes the next batches' grids
     uint64_t* totals;           // 0 closest rays, 1 any rays, 2..7 work counters (RT_WORK_COUNTERS)
     float* image;               // width*height*3, or (packed != 0) this rank's tiles one after the other
     uint32_t packed;            // tile-packed output: pixel (tile slot k, row r, column q) at ((k * tile + r) * tile + q) * 3
@@ -175,6 +176,14 @@ struct RenderBuffers
     size_t image_floats;
     size_t image_bytes, tile_bytes;     // real sizes of d_image / d_tile_ids (pool blocks may be larger than asked)
     cudaEvent_t ev[4];
+    // Per-bin grid sizing (rt_launch_shade / rt_launch_light_sample): the kernels record the largest count of every bin
+    // (bin_hint), a batch's end copies the table to pinned memory, and a later batch -- whichever first finds the copy
+    // done -- sizes each bin's grid from it instead of from the batch
+    uint32_t* d_bin_hint;
+    uint32_t* h_bin_hint;
+    uint32_t bin_hint_used[RT_SBINS + RT_LBINS];
+    bool bin_hint_valid, bin_hint_pending;
+    cudaEvent_t bin_hint_ev;
     std::vector<cudaEvent_t>* trace_events;   // start/stop pairs around traversal kernels (RT_RENDER_TIME_TRACE)
     size_t trace_events_used;
 };
@@ -740,6 +749,8 @@ k_shade_bin(const __grid_constant__ RenderCtx c, int cur, uint32_t bounce, uint3
 {
     const uint32_t n = c.ctl[CTL_SHADE + bin];
     const uint32_t* items = c.q_shade + (size_t)bin * c.qcap;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && c.bin_hint != NULL)
+        atomicMax(c.bin_hint + bin, n);
     if (first)
         shade_prologue(c);
     RT_GRID_STRIDE(j, n)
@@ -883,6 +894,8 @@ k_light_sample_bin(const __grid_constant__ RenderCtx c, int cur, uint32_t bounce
 {
     const uint32_t n = c.ctl[CTL_LITB + bin];
     const uint32_t* items = c.q_path[cur] + (size_t)bin * c.qcap;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && c.bin_hint != NULL)
+        atomicMax(c.bin_hint + RT_SBINS + bin, n);
     RT_GRID_STRIDE(j, n)
     {
         if (j < n)
@@ -1150,6 +1163,9 @@ inline void rt_render_free(int device, RenderBuffers* rb)
     rt_detail::pool_free(device, rb->block, rb->block_bytes);
     rt_detail::pool_free(device, rb->d_tile_ids, rb->tile_bytes);
     rt_detail::pool_free(device, rb->d_image, rb->image_bytes);
+    if (rb->d_bin_hint) cudaFree(rb->d_bin_hint);
+    if (rb->h_bin_hint) cudaFreeHost(rb->h_bin_hint);
+    if (rb->bin_hint_ev) cudaEventDestroy(rb->bin_hint_ev);
     for (int i = 0; i < 4; ++i) cudaEventDestroy(rb->ev[i]);
     if (rb->trace_events)
     {
@@ -1385,6 +1401,18 @@ inline int rt_render_reserve(RtScene* s, RenderPlan& plan)
             rb = new RenderBuffers();
             std::memset(rb, 0, sizeof(*rb));
             for (int i = 0; i < 4; ++i) cudaEventCreate(&rb->ev[i]);
+            const size_t hint_bytes = (RT_SBINS + RT_LBINS) * sizeof(uint32_t);
+            if (cudaMalloc((void**)&rb->d_bin_hint, hint_bytes) == cudaSuccess && cudaMemset(rb->d_bin_hint, 0, hint_bytes) == cudaSuccess &&
+                cudaHostAlloc((void**)&rb->h_bin_hint, hint_bytes, cudaHostAllocDefault) == cudaSuccess &&
+                cudaEventCreateWithFlags(&rb->bin_hint_ev, cudaEventDisableTiming) == cudaSuccess)
+                std::memset(rb->h_bin_hint, 0, hint_bytes);
+            else
+            {
+                cudaGetLastError();         // no hints: every bin's grid stays sized by the batch
+                if (rb->d_bin_hint) cudaFree(rb->d_bin_hint);
+                if (rb->h_bin_hint) cudaFreeHost(rb->h_bin_hint);
+                rb->d_bin_hint = rb->h_bin_hint = NULL;
+            }
         }
         s->render = rb;
     }
@@ -1536,9 +1564,24 @@ static void rt_launch_shade_bin(const RenderCtx& c, int cur, uint32_t bounce, ui
     default:              k_shade_bin<ST, RT_BRDF_NONE><<<grid, RT_BLOCK, 0, st>>>(c, cur, bounce, bin, first); break;
     }
 }
-static void rt_launch_shade(RtScene* s, const RenderCtx& c, int cur, uint32_t bounce, unsigned grid, cudaStream_t st,
+// Grid of ONE bin's launch.  `grid` is sized by the batch; most bins hold a small fraction of it (a frame of config C4: the
+// floor plane's bin 26 M entries, the rectangle light's a few thousand), and 75 776 blocks take ~100 us just to start and
+// find nothing.  Once a count of the bin is known from an earlier batch (RenderBuffers.bin_hint_used: the largest seen, with
+// a quarter on top) the bin gets that many blocks, never fewer than eight per SM.  The kernels are grid-stride loops, so any
+// size is correct; only the time changes.
+static unsigned rt_bin_grid(const RtScene* s, unsigned hint_index, unsigned grid, int sms)
+{
+    const RenderBuffers* rb = s->render;
+    if (!rb->bin_hint_valid)
+        return grid;
+    const uint64_t want = ((uint64_t)rb->bin_hint_used[hint_index] * 5 / 4 + RT_BLOCK - 1) / RT_BLOCK + 1;
+    return (unsigned)std::min<uint64_t>(grid, std::max<uint64_t>(want, (uint64_t)sms * 8));
+}
+
+static void rt_launch_shade(RtScene* s, const RenderCtx& c, int cur, uint32_t bounce, unsigned grid_all, int sms, cudaStream_t st,
                             uint64_t& launches)
 {
+    unsigned grid = grid_all;
     const size_t ns = s->shape_types.size();
     if (!RT_SHADE_SPECIALISE || ns == 0 || ns > RT_SBINS - 1 || s->d.stage6)
     {
@@ -1549,6 +1592,7 @@ static void rt_launch_shade(RtScene* s, const RenderCtx& c, int cur, uint32_t bo
     {
         const int first = b == 0 ? 1 : 0;
         const uint32_t brdf = s->shape_brdfs[b];
+        grid = rt_bin_grid(s, (unsigned)b, grid_all, sms);
         switch (s->shape_types[b])
         {
         case RT_SHAPE_PLANE:  rt_launch_shade_bin<RT_SHAPE_PLANE>(c, cur, bounce, (uint32_t)b, first, brdf, grid, st); break;
@@ -1571,9 +1615,10 @@ static void rt_launch_light_bin(const RenderCtx& c, int cur, uint32_t bounce, ui
     if (glossy) k_light_sample_bin<LT, RT_BRDF_GLOSSY><<<grid, RT_BLOCK, 0, st>>>(c, cur, bounce, lsi, bin);
     else        k_light_sample_bin<LT, RT_BRDF_LAMBERT><<<grid, RT_BLOCK, 0, st>>>(c, cur, bounce, lsi, bin);
 }
-static void rt_launch_light_sample(RtScene* s, const RenderCtx& c, int cur, uint32_t bounce, uint32_t lsi, unsigned grid,
+static void rt_launch_light_sample(RtScene* s, const RenderCtx& c, int cur, uint32_t bounce, uint32_t lsi, unsigned grid_all, int sms,
                                    cudaStream_t st, uint64_t& launches)
 {
+    unsigned grid = grid_all;
     // bin = (light index & 3) | (glossy ? 4 : 0); a bin's light kind is known when every light that maps to it is
     // of one kind (always, with at most four lights)
     const size_t nl = s->light_types.size();
@@ -1597,6 +1642,7 @@ static void rt_launch_light_sample(RtScene* s, const RenderCtx& c, int cur, uint
         const bool glossy = (bin & 4u) != 0;
         if (lt < 0 || (glossy ? !s->has_glossy : !s->has_lambert))
             continue;               // nothing can land in this bin
+        grid = rt_bin_grid(s, RT_SBINS + bin, grid_all, sms);
         if (lt == RT_SHAPE_RECT)        rt_launch_light_bin<RT_SHAPE_RECT>(c, cur, bounce, lsi, bin, glossy, grid, st);
         else if (lt == RT_SHAPE_SPHERE) rt_launch_light_bin<RT_SHAPE_SPHERE>(c, cur, bounce, lsi, bin, glossy, grid, st);
         else                            rt_launch_light_bin<RT_SHAPE_MESH>(c, cur, bounce, lsi, bin, glossy, grid, st);
@@ -1676,6 +1722,15 @@ static int rt_launch_batch(RtScene* s, const RenderCtx& c, cudaStream_t st, uint
     const unsigned tg_split = (unsigned)(dev_sms * std::max(std::min(g.split_top, std::min(g.split_mesh64, g.split_mesh32)), 1));
     const unsigned tg_mesh = RT_SEPARATE_MESH_GRID ? (unsigned)(dev_sms * std::max(s->mesh_stack_need > 32 ? g.split_mesh64 : g.split_mesh32, 1)) : tg_split;
 
+    // bin counts of an earlier batch, if their copy has arrived (see rt_bin_grid)
+    if (rb->bin_hint_pending && cudaEventQuery(rb->bin_hint_ev) == cudaSuccess)
+    {
+        std::memcpy(rb->bin_hint_used, rb->h_bin_hint, sizeof(rb->bin_hint_used));
+        rb->bin_hint_valid = true;
+        rb->bin_hint_pending = false;
+    }
+    cudaGetLastError();     // (cudaErrorNotReady from the query is not an error)
+
     k_pixel_setup<<<pix_blocks, RT_BLOCK, 0, st>>>(c);
     k_raygen<<<wide_gen, RT_BLOCK, 0, st>>>(c);
     launches += 2;
@@ -1703,7 +1758,7 @@ static int rt_launch_batch(RtScene* s, const RenderCtx& c, cudaStream_t st, uint
             trace_launches += 1;
         }
         rt_trace_mark(rb, timed, st);
-        rt_launch_shade(s, c, cur, b, wide, st, launches);
+        rt_launch_shade(s, c, cur, b, wide, dev_sms, st, launches);
         launches += 2;
         for (uint32_t l = 0; l < c.nls; ++l)
         {
@@ -1713,7 +1768,7 @@ static int rt_launch_batch(RtScene* s, const RenderCtx& c, cudaStream_t st, uint
                 k_light_select<<<wide, RT_BLOCK, 0, st>>>(c, cur, b, l);
                 launches += 1;
             }
-            rt_launch_light_sample(s, c, cur, b, l, wide, st, launches);
+            rt_launch_light_sample(s, c, cur, b, l, wide, dev_sms, st, launches);
             rt_trace_mark(rb, timed, st);
             if (split)
             {
@@ -1740,6 +1795,12 @@ static int rt_launch_batch(RtScene* s, const RenderCtx& c, cudaStream_t st, uint
     }
     k_accumulate<<<pix_blocks, RT_BLOCK, 0, st>>>(c);
     launches += 1;
+    if (rb->d_bin_hint != NULL && !rb->bin_hint_pending)
+    {
+        cudaMemcpyAsync(rb->h_bin_hint, rb->d_bin_hint, sizeof(rb->bin_hint_used), cudaMemcpyDeviceToHost, st);
+        cudaEventRecord(rb->bin_hint_ev, st);
+        rb->bin_hint_pending = true;
+    }
     RT_CUDA(cudaGetLastError());
     return RT_OK;
 }
@@ -1747,6 +1808,7 @@ static int rt_launch_batch(RtScene* s, const RenderCtx& c, cudaStream_t st, uint
 inline int rt_fill_ctx(RtScene* s, const RtCamera* camera, const RtRenderParams* prm, const RenderPlan& plan, RenderCtx& c)
 {
     c = s->render->ctx;
+    c.bin_hint = s->render->d_bin_hint;
     c.sc = s->d;
     c.cam = *camera;
     c.width = prm->width;
